@@ -1,0 +1,110 @@
+/* jubik_b200.h -- C ABI of the B200-native J-UBIK instrument-response hot path.
+ *
+ * The reference (NIFTy-PPL/J-UBIK) has no FFI of its own: the hot path is a set of Python
+ * callables built by its response/likelihood builders and lowered by JAX/XLA.  Each entry point
+ * below replaces the XLA lowering of one of those callables; a jax.ffi / ctypes / cffi shim binds
+ * them 1:1.  Reference interfaces replaced (paths under the reference repo):
+ *
+ *   jubik_plan_create          jubik/convolve.py:104-131 (PSF crop/pad/shift/normalise + its FFT, hoisted
+ *                              out of the per-call path), jubik/response.py:12-45,48-112 (exposure cut,
+ *                              readout mask), instruments/erosita/erosita_response.py:307,327-328
+ *                              (pixel area, effective area), instruments/*_likelihood.py (data binding)
+ *   jubik_psf_apply            vmap(linpatch_convolve) -- erosita_response.py:209-212,
+ *                              chandra_response.py:127-130, jubik/convolve.py:66-145
+ *   jubik_psf_apply_T          jax.linear_transpose / VJP of the above
+ *   jubik_response_apply       R = mask(exposure(psf(x * pixel_area))) -- erosita_response.py:349-350,
+ *                              chandra_response.py:138-142 (dense layout, masked pixels = 0)
+ *   jubik_response_apply_T     its transpose
+ *   jubik_poisson_energy_and_grad   jft.Poissonian(d).amend(R): value_and_grad of
+ *                              sum(lambda) - d.log(lambda) -- erosita_likelihood.py:85-89,
+ *                              chandra_likelihood.py:37, formula demos/x-ray-imaging.py:313
+ *   jubik_poisson_metric_apply R^T diag(1/lambda) R v  (Fisher metric NIFTy builds by linearize+transpose)
+ *
+ * Conventions: every array pointer is a DEVICE pointer to contiguous C-order memory (float64 unless
+ * stated); `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous
+ * on that stream; return value 0 = ok, otherwise an error code whose text is jubik_last_error().
+ * No allocation happens after plan creation.  A plan owns one workspace: use one plan per stream.
+ * There is no CPU fallback: without a CUDA device every entry point fails.
+ */
+#ifndef JUBIK_B200_H
+#define JUBIK_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jubik_plan jubik_plan;
+
+enum { JUBIK_KERNEL_FULL = 0,    /* (T, n*n, E, N, N) origin-centred, as psf_interpolator returns   */
+       JUBIK_KERNEL_CROPPED = 1  /* (T, n*n, E, 2dx, 2dx) centred = what convolve.py:107-111 extracts */ };
+enum { JUBIK_DATA_F64 = 0, JUBIK_DATA_I64 = 1 };
+
+enum { JUBIK_OK = 0, JUBIK_ERR_ARG = 1, JUBIK_ERR_UNSUPPORTED = 2, JUBIK_ERR_CUDA = 3, JUBIK_ERR_ALLOC = 4 };
+
+typedef struct jubik_plan_desc {
+    int32_t n0, n1;            /* spatial shape of the sky (square, even)                       */
+    int32_t n_energy;          /* E                                                             */
+    int32_t n_modules;         /* T: telescope modules / observations (vmap axis of the PSF)    */
+    int32_t max_samples;       /* S_max: leading batch axis the workspace is sized for          */
+    int32_t n_patches;         /* n_patches_per_axis (>= 3, convolve.py:107-111)                */
+    int32_t margin;            /* m                                                             */
+    int32_t kernel_layout;     /* JUBIK_KERNEL_*                                                */
+    int32_t data_dtype;        /* JUBIK_DATA_*                                                  */
+    int32_t has_exposure_cut;  /* 0: exposure_cut=None                                          */
+    int32_t fft_length;        /* 0 = choose; otherwise force this transform length (>= P)      */
+    int32_t reserved;
+    double d0, d1;             /* pixel distances (domain.distances[-2:]); cancel analytically   */
+    double exposure_cut;
+    double pixel_area;         /* x * pixel_area in R (1.0 if unused)                            */
+    const double* kernel;      /* device, layout above                                          */
+    const double* exposure;    /* device (T,E,N,N) raw exposures, or NULL (psf-only plan)       */
+    const double* eff_area;    /* device (T,E) or NULL                                          */
+    const void* data;          /* device (T,E,N,N) counts, dense, masked entries ignored; or NULL*/
+} jubik_plan_desc;
+
+typedef struct jubik_plan_info {
+    int32_t N, n, m, dx, w, P, L, PH, S_max, T, E;
+    int32_t exact_period;      /* 1: circular period == P (reference semantics for any PSF support) */
+    int32_t psf_half_support;  /* max |offset| with a non-zero PSF value                            */
+    int32_t fft_r1, fft_r2, col_block;
+    size_t bytes_khat, bytes_workspace, bytes_total;
+} jubik_plan_info;
+
+const char* jubik_last_error(void);
+int jubik_version(void);
+/* 1 if an FFT of this length is compiled in */
+int jubik_fft_length_supported(int length);
+/* number of CUDA devices visible (0 => every other call fails) */
+int jubik_device_count(void);
+
+int jubik_plan_create(jubik_plan** plan, const jubik_plan_desc* desc, void* stream);
+int jubik_plan_destroy(jubik_plan* plan);
+int jubik_plan_get_info(const jubik_plan* plan, jubik_plan_info* info);
+/* (re)bind the observed counts, dense (T,E,N,N) */
+int jubik_plan_set_data(jubik_plan* plan, const void* data, int data_dtype, void* stream);
+/* kernels launched through this plan so far (bench.py's gpu_launches) */
+long long jubik_plan_launch_count(const jubik_plan* plan);
+
+/* x:(S,E,N,N) -> out:(S,T,E,N,N) */
+int jubik_psf_apply(jubik_plan* plan, const double* x, int n_samples, double* out, void* stream);
+/* g:(S,T,E,N,N) -> out:(S,E,N,N) */
+int jubik_psf_apply_T(jubik_plan* plan, const double* g, int n_samples, double* out, void* stream);
+int jubik_response_apply(jubik_plan* plan, const double* x, int n_samples, double* out, void* stream);
+int jubik_response_apply_T(jubik_plan* plan, const double* g, int n_samples, double* out, void* stream);
+/* x:(S,E,N,N) -> energy:(S,), grad:(S,E,N,N); grad may be NULL (energy only) */
+int jubik_poisson_energy_and_grad(jubik_plan* plan, const double* x, int n_samples,
+                                  double* energy, double* grad, void* stream);
+/* out = R^T diag(1/(R x)) R v ; x,v,out:(S,E,N,N) */
+int jubik_poisson_metric_apply(jubik_plan* plan, const double* x, const double* v, int n_samples,
+                               double* out, void* stream);
+/* Same as jubik_poisson_energy_and_grad with HOST buffers (pinned or pageable): H2D of x, the kernels,
+ * D2H of energy and grad, all on `stream`, then a stream synchronise.  This is the end-to-end call. */
+int jubik_poisson_energy_and_grad_host(jubik_plan* plan, const double* x_host, int n_samples,
+                                       double* energy_host, double* grad_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,90 @@
+"""Build libjubik_b200.so (sm_100a) in-tree with nvcc.
+
+One object per FFT length listed in csrc/fft_list.h (compiled in parallel) plus csrc/capi.cu.
+Usage:  python -m jubik_b200.build [--force] [--jobs N] [--verbose]
+The same recipe is what __graft_entry__.build() runs.  No torch extension machinery is involved:
+the product is a plain C-ABI shared library (include/jubik_b200.h).
+"""
+from __future__ import annotations
+
+import argparse
+import concurrent.futures as cf
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libjubik_b200.so")
+
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xptxas", "-v",
+    "-Xcudafe", "--diag_suppress=177",
+]
+
+
+def fft_list():
+    txt = open(os.path.join(CSRC, "fft_list.h")).read()
+    return [tuple(int(v) for v in m.groups())
+            for m in re.finditer(r"X\((\d+),\s*(\d+),\s*(\d+),\s*(\d+)\)", txt)]
+
+
+def _sources_mtime():
+    newest = 0.0
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        for f in os.listdir(root):
+            newest = max(newest, os.path.getmtime(os.path.join(root, f)))
+    return newest
+
+
+def _run(cmd, log):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(log, "w") as fh:
+        fh.write(" ".join(cmd) + "\n" + r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: %s\n%s" % (" ".join(cmd), r.stdout[-4000:]))
+    return r.stdout
+
+
+def build(force=False, jobs=None, verbose=False):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: jubik_b200 needs the CUDA toolkit to build")
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _sources_mtime():
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    jobs = jobs or os.cpu_count() or 4
+    tasks = []
+    for (L, r1, r2, cb) in fft_list():
+        obj = os.path.join(OBJ, "fft_%d.o" % L)
+        cmd = [nvcc] + NVCC_FLAGS + ["-DJB_INST_L=%d" % L, "-DJB_INST_R1=%d" % r1, "-DJB_INST_R2=%d" % r2,
+                                    "-DJB_INST_CB=%d" % cb, "-c", os.path.join(CSRC, "fft_inst.cu"), "-o", obj]
+        tasks.append((cmd, obj))
+    obj = os.path.join(OBJ, "capi.o")
+    tasks.append(([nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "capi.cu"), "-o", obj], obj))
+    with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
+        futs = {ex.submit(_run, cmd, o + ".log"): o for cmd, o in tasks}
+        for f in cf.as_completed(futs):
+            out = f.result()
+            if verbose:
+                print(out)
+    objs = [o for _, o in tasks]
+    _run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"], os.path.join(OBJ, "link.log"))
+    return LIB
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--jobs", type=int, default=None)
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build(a.force, a.jobs, a.verbose))
+
+
+if __name__ == "__main__":
+    sys.exit(main())

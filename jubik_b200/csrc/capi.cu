@@ -1,0 +1,420 @@
+// capi.cu -- the C ABI declared in include/jubik_b200.h: plan creation (PSF spectra precomputed and kept
+// resident, exposure/mask/data folded into dense device planes) and the per-call kernel sequences.
+#include "ops.cuh"
+#include "fft_list.h"
+#include "../../include/jubik_b200.h"
+#include <string>
+#include <vector>
+#include <new>
+
+#define JB_X_DECL(L, R1, R2, CB) JB_DECLARE_FFT(L)
+JB_FFT_LIST(JB_X_DECL)
+#undef JB_X_DECL
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#ifndef JB_EMU
+int dev_malloc(void** p, size_t n) { return cudaMalloc(p, n) == cudaSuccess ? 0 : 1; }
+void dev_free(void* p) { if (p) cudaFree(p); }
+int h2d(void* d, const void* h, size_t n, jb_stream_t st) { return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st) != cudaSuccess; }
+int d2h(void* h, const void* d, size_t n, jb_stream_t st) { return cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st) != cudaSuccess; }
+int stream_sync(jb_stream_t st) { return cudaStreamSynchronize(st) != cudaSuccess; }
+std::string cuda_msg(cudaError_t e) { return std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e); }
+int device_count() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+#else
+int dev_malloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
+void dev_free(void* p) { free(p); }
+int h2d(void* d, const void* h, size_t n, jb_stream_t) { memcpy(d, h, n); return 0; }
+int d2h(void* h, const void* d, size_t n, jb_stream_t) { memcpy(h, d, n); return 0; }
+int stream_sync(jb_stream_t) { return 0; }
+std::string cuda_msg(cudaError_t) { return "emu"; }
+int device_count() { return 1; }
+#endif
+
+const JbFftOps* find_ops(int L) {
+#define JB_X_FIND(LL, R1, R2, CB) if (L == LL) return jb_fft_ops_##LL();
+    JB_FFT_LIST(JB_X_FIND)
+#undef JB_X_FIND
+    return nullptr;
+}
+const int k_lengths[] = {
+#define JB_X_LEN(LL, R1, R2, CB) LL,
+    JB_FFT_LIST(JB_X_LEN)
+#undef JB_X_LEN
+};
+}  // namespace
+
+struct jubik_plan {
+    JbGeom g;
+    const JbFftOps* ops = nullptr;
+    int S_max = 0;
+    int exact = 0, support = 0;
+    int has_expo = 0, has_data = 0;
+    int rpc_in = 1, rpc_out = 1, thr_rows = 128, thr_cols = 128;
+    long long launches = 0;
+    // device memory
+    cd* khat = nullptr;
+    cd* tw_nk = nullptr;
+    cd* tw_kn = nullptr;
+    double* wgt = nullptr;
+    double* expo = nullptr;    // (T,E,N,N) effective exposure, 0 == masked
+    double* data = nullptr;    // (T,E,N,N)
+    cd* bufA = nullptr;        // (S_max*T*E, n^2, P, PH)
+    cd* bufB = nullptr;        // (S_max*T*E, n^2, w, PH)
+    double* gbuf = nullptr;    // (S_max,T,E,N,N) cotangent / lambda scratch
+    double* lbuf = nullptr;    // (S_max,T,E,N,N) lambda for the metric (allocated on first use)
+    double* partial = nullptr; // energy partials
+    double* xdev = nullptr;    // staging for the host-buffer entry point (allocated on first use)
+    double* gdev = nullptr;
+    double* edev = nullptr;
+    size_t bytes_khat = 0, bytes_ws = 0, bytes_total = 0;
+    int nblk_out = 0;
+};
+
+#define JB_CK(call)                                                           \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) return fail(JUBIK_ERR_CUDA, std::string(#call) + " -> " + cuda_msg(e_)); \
+    } while (0)
+#define JB_LAUNCHED(p, call) do { JB_CK(call); ++(p)->launches; } while (0)
+
+extern "C" {
+
+const char* jubik_last_error(void) { return g_err.c_str(); }
+int jubik_version(void) { return 100; }
+int jubik_fft_length_supported(int length) { return find_ops(length) != nullptr; }
+int jubik_device_count(void) { return device_count(); }
+
+int jubik_plan_destroy(jubik_plan* p) {
+    if (!p) return JUBIK_OK;
+    dev_free(p->khat); dev_free(p->tw_nk); dev_free(p->tw_kn); dev_free(p->wgt); dev_free(p->expo);
+    dev_free(p->data); dev_free(p->bufA); dev_free(p->bufB); dev_free(p->gbuf); dev_free(p->lbuf);
+    dev_free(p->partial); dev_free(p->xdev); dev_free(p->gdev); dev_free(p->edev);
+    delete p;
+    return JUBIK_OK;
+}
+
+static int alloc(jubik_plan* p, void** ptr, size_t bytes, const char* what) {
+    if (dev_malloc(ptr, bytes)) return fail(JUBIK_ERR_ALLOC, std::string("device allocation failed for ") + what +
+                                                                 " (" + std::to_string(bytes) + " bytes)");
+    p->bytes_total += bytes;
+    return 0;
+}
+
+static void choose_launch_shapes(jubik_plan* p) {
+    const JbGeom& g = p->g;
+    const JbFftOps* o = p->ops;
+    // rows kernels: aim for >= 8 sequences per CTA, <= 256 threads; items per pass ~ B*R2 and B*(R1/2+1)
+    int rpc = 1;
+    while (rpc * g.n < 8 && rpc < g.N) rpc *= 2;
+    p->rpc_in = p->rpc_out = rpc;
+    int B = rpc * g.n;
+    int items = B * (o->R2 > 1 ? (o->R2 > o->R1 / 2 + 1 ? o->R2 : o->R1 / 2 + 1) : 1);
+    int thr = ((items + 31) / 32) * 32;
+    if (thr < 64) thr = 64;
+    if (thr > 256) thr = 256;
+    p->thr_rows = thr;
+    int citems = o->CB * (o->R2 > 1 ? (o->R1 > o->R2 ? o->R1 : o->R2) : 1);
+    int ct = ((citems + 31) / 32) * 32;
+    if (ct < 32) ct = 32;
+    if (ct > 128) ct = 128;
+    p->thr_cols = ct;
+}
+
+int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (!out || !d) return fail(JUBIK_ERR_ARG, "null plan/desc pointer");
+    *out = nullptr;
+    if (device_count() < 1) return fail(JUBIK_ERR_CUDA, "no CUDA device: jubik_b200 has no CPU fallback");
+    if (d->n0 != d->n1) return fail(JUBIK_ERR_UNSUPPORTED, "only square skies are supported (the reference's window "
+                                    "weights use shape[0] for both axes, convolve.py:20-25)");
+    const int N = d->n0, n = d->n_patches, m = d->margin;
+    if (N < 4 || (N & 1)) return fail(JUBIK_ERR_ARG, "spatial size must be even and >= 4 (odd sizes break the "
+                                      "reference's centre crop, convolve.py:107-111)");
+    if (n < 3) return fail(JUBIK_ERR_ARG, "n_patches_per_axis must be >= 3 (n <= 2 gives an empty kernel crop in the "
+                           "reference, convolve.py:107-111)");
+    if (n > JB_MAXN) return fail(JUBIK_ERR_UNSUPPORTED, "n_patches_per_axis > 64");
+    if (m < 1) return fail(JUBIK_ERR_ARG, "margin must be >= 1 (margin 0 makes the reference's [m:-m] crop empty)");
+    if (d->n_energy < 1 || d->n_modules < 1 || d->max_samples < 1) return fail(JUBIK_ERR_ARG, "E, T, S_max must be >= 1");
+    if (!d->kernel) return fail(JUBIK_ERR_ARG, "kernel pointer is null");
+    if (d->has_exposure_cut && d->exposure_cut < 0) return fail(JUBIK_ERR_ARG, "exposure_cut should be non-negative or None!");
+    const int dx = N / n;  // int(N/n), convolve.py:104
+    if (dx < 1) return fail(JUBIK_ERR_ARG, "more patches than pixels");
+    if (N - 2 * dx < 2) return fail(JUBIK_ERR_ARG, "kernel crop (N-2dx)//2 must be >= 1");
+    jubik_plan* p = new (std::nothrow) jubik_plan();
+    if (!p) return fail(JUBIK_ERR_ALLOC, "host allocation failed");
+    JbGeom& g = p->g;
+    memset(&g, 0, sizeof(g));
+    g.N = N; g.n = n; g.m = m; g.dx = dx; g.w = 2 * dx; g.hp = dx / 2; g.P = g.w + 2 * m;
+    g.S = d->max_samples; g.T = d->n_modules; g.E = d->n_energy;
+    p->S_max = d->max_samples;
+    // window starts with jax.lax.dynamic_slice clamping (convolve.py:55-57)
+    {
+        int frame = N + 2 * g.hp;
+        for (int j = 0; j < n; ++j) {
+            int o = j * dx;
+            if (o > frame - g.w) o = frame - g.w;
+            if (o < 0) o = 0;
+            g.offs[j] = o;
+        }
+    }
+    const size_t nn2 = (size_t)n * n, TE = (size_t)g.T * g.E, STE = TE * p->S_max;
+    int rc = 0;
+#define JB_TRY(expr) do { rc = (expr); if (rc) { jubik_plan_destroy(p); return rc; } } while (0)
+#define JB_TRYCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { jubik_plan_destroy(p); \
+        return fail(JUBIK_ERR_CUDA, std::string(#call) + " -> " + cuda_msg(e_)); } ++p->launches; } while (0)
+
+    // ---- PSF sums + support (decides the transform length)
+    JbKsrc ks;
+    ks.ptr = d->kernel; ks.cropped = (d->kernel_layout == JUBIK_KERNEL_CROPPED); ks.T = g.T; ks.E = g.E;
+    double* sums = nullptr;
+    int* supp = nullptr;
+    JB_TRY(alloc(p, (void**)&sums, TE * nn2 * sizeof(double), "psf sums"));
+    if (dev_malloc((void**)&supp, TE * nn2 * sizeof(int))) { dev_free(sums); jubik_plan_destroy(p); return fail(JUBIK_ERR_ALLOC, "psf support"); }
+    auto cleanup_tmp = [&]() { dev_free(sums); dev_free(supp); };
+    {
+        cudaError_t e = jb_launch(k_prep_sum, dim3((unsigned)nn2, (unsigned)TE), dim3(256), 256 * sizeof(double), st, g, ks, sums, supp);
+        if (e != cudaSuccess) { cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "k_prep_sum -> " + cuda_msg(e)); }
+        ++p->launches;
+        std::vector<int> hs(TE * nn2);
+        if (d2h(hs.data(), supp, hs.size() * sizeof(int), st) || stream_sync(st)) { cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "reading PSF support failed"); }
+        int mx = 0;
+        for (int v : hs) mx = v > mx ? v : mx;
+        p->support = mx;
+    }
+    // ---- transform length: exact period P if compiled in; else (compact PSF only) the next larger length
+    int L = 0;
+    if (d->fft_length > 0) {
+        if (d->fft_length < g.P) { cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_ARG, "fft_length < P = 2*int(N/n) + 2*margin"); }
+        if (!find_ops(d->fft_length)) { cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_UNSUPPORTED, "fft_length " + std::to_string(d->fft_length) + " is not compiled in"); }
+        L = d->fft_length;
+    } else if (find_ops(g.P)) {
+        L = g.P;
+    } else {
+        for (int c : k_lengths) if (c >= g.P && (L == 0 || c < L)) L = c;
+    }
+    if (L == 0) { cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_UNSUPPORTED, "no compiled FFT length >= P = " + std::to_string(g.P)); }
+    if (L != g.P && p->support > m) {
+        cleanup_tmp(); jubik_plan_destroy(p);
+        return fail(JUBIK_ERR_UNSUPPORTED, "P = " + std::to_string(g.P) + " is not a compiled FFT length and the PSF half-support (" +
+                    std::to_string(p->support) + ") exceeds the margin (" + std::to_string(m) +
+                    "): the reference's period-P wrap-around cannot be reproduced with a padded transform");
+    }
+    p->exact = (L == g.P);
+    g.L = L; g.PH = L / 2 + 1;
+    p->ops = find_ops(L);
+    const JbFftOps* o = p->ops;
+    choose_launch_shapes(p);
+
+    // ---- twiddles and window weights (host, long double), uploaded once
+    {
+        const int R1 = o->R1, R2 = o->R2;
+        std::vector<cd> a((size_t)L), b((size_t)L);
+        const long double two_pi = 6.283185307179586476925286766559005768L;
+        for (int k1 = 0; k1 < R1; ++k1)
+            for (int n2 = 0; n2 < R2; ++n2) {
+                long long e = ((long long)k1 * n2) % L;
+                long double ang = -two_pi * (long double)e / (long double)L;
+                cd v = cd_make((double)cosl(ang), (double)sinl(ang));
+                a[(size_t)k1 * R2 + n2] = v;
+                b[(size_t)n2 * R1 + k1] = v;
+            }
+        JB_TRY(alloc(p, (void**)&p->tw_nk, L * sizeof(cd), "twiddles"));
+        JB_TRY(alloc(p, (void**)&p->tw_kn, L * sizeof(cd), "twiddles"));
+        // weights: convolve.py:18-25  b = concat(linspace(0,1,w/2), reversed)
+        std::vector<double> wv((size_t)g.w);
+        int half = g.w / 2;
+        for (int i = 0; i < half; ++i) {
+            // numpy linspace: start + i*step with step = 1/(half-1), last sample forced to 1; linspace(0,1,1) == [0.]
+            double v = 0.0;
+            if (half > 1) { double step = 1.0 / (double)(half - 1); v = (i == half - 1) ? 1.0 : (double)i * step; }
+            wv[i] = v; wv[g.w - 1 - i] = v;
+        }
+        JB_TRY(alloc(p, (void**)&p->wgt, g.w * sizeof(double), "weights"));
+        if (h2d(p->tw_nk, a.data(), L * sizeof(cd), st) || h2d(p->tw_kn, b.data(), L * sizeof(cd), st) ||
+            h2d(p->wgt, wv.data(), g.w * sizeof(double), st) || stream_sync(st)) {
+            cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "uploading twiddles failed");
+        }
+    }
+    // ---- workspace
+    const size_t nstrips = (size_t)jb_cdiv(g.PH, o->CB);
+    p->bytes_khat = TE * nn2 * nstrips * (size_t)L * o->CB * sizeof(cd);
+    size_t bA = STE * nn2 * (size_t)g.P * g.PH * sizeof(cd);
+    size_t bB = STE * nn2 * (size_t)g.w * g.PH * sizeof(cd);
+    size_t bG = STE * (size_t)N * N * sizeof(double);
+    p->nblk_out = jb_cdiv(N, p->rpc_out);
+    size_t bP = STE * (size_t)p->nblk_out * sizeof(double);
+    p->bytes_ws = bA + bB + bG + bP;
+    if (alloc(p, (void**)&p->khat, p->bytes_khat, "PSF spectra") || alloc(p, (void**)&p->bufA, bA, "spectrum workspace A") ||
+        alloc(p, (void**)&p->bufB, bB, "spectrum workspace B") || alloc(p, (void**)&p->gbuf, bG, "cotangent workspace") ||
+        alloc(p, (void**)&p->partial, bP, "energy partials")) {
+        std::string msg = g_err; cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_ALLOC, msg);
+    }
+    // ---- PSF spectra: rows r2c -> columns FFT -> normalise -> resident in k_cols' register order
+    {
+        int prpc = 8;
+        int items = prpc * (o->R2 > 1 ? (o->R2 > o->R1 / 2 + 1 ? o->R2 : o->R1 / 2 + 1) : 1);
+        int thr = ((items + 31) / 32) * 32; if (thr < 32) thr = 32; if (thr > 256) thr = 256;
+        cudaError_t e = o->prep_rows(g, ks, p->tw_nk, p->bufB, prpc, thr, st);
+        if (e == cudaSuccess) { ++p->launches; e = o->prep_cols(g, p->bufB, sums, p->tw_nk, p->khat, p->thr_cols, st); }
+        if (e == cudaSuccess) ++p->launches;
+        if (e != cudaSuccess || stream_sync(st)) { cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "PSF spectrum kernels -> " + cuda_msg(e)); }
+    }
+    p->bytes_total -= TE * nn2 * sizeof(double);
+    cleanup_tmp();
+    // ---- exposure / mask / data
+    if (d->exposure) {
+        size_t tot = TE * (size_t)N * N;
+        JB_TRY(alloc(p, (void**)&p->expo, tot * sizeof(double), "exposure"));
+        JB_TRYCK(jb_launch(k_prep_expo, dim3(592), dim3(256), 0, st, d->exposure, d->eff_area, d->exposure_cut,
+                           (int)(d->has_exposure_cut != 0), d->pixel_area, (size_t)N * N, tot, p->expo));
+        p->has_expo = 1;
+    }
+    if (d->data) {
+        rc = jubik_plan_set_data(p, d->data, d->data_dtype, stream_);
+        if (rc) { jubik_plan_destroy(p); return rc; }
+    }
+    if (stream_sync(st)) { jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "plan creation: stream sync failed"); }
+    *out = p;
+    return JUBIK_OK;
+}
+
+int jubik_plan_set_data(jubik_plan* p, const void* data, int dtype, void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (!p || !data) return fail(JUBIK_ERR_ARG, "null plan/data");
+    size_t tot = (size_t)p->g.T * p->g.E * p->g.N * p->g.N;
+    if (!p->data) { int rc = alloc(p, (void**)&p->data, tot * sizeof(double), "data"); if (rc) return rc; }
+    if (dtype == JUBIK_DATA_I64) {
+        JB_LAUNCHED(p, jb_launch(k_i64_to_f64, dim3(592), dim3(256), 0, st, (const long long*)data, tot, p->data));
+    } else if (dtype == JUBIK_DATA_F64) {
+#ifndef JB_EMU
+        JB_CK(cudaMemcpyAsync(p->data, data, tot * sizeof(double), cudaMemcpyDeviceToDevice, st));
+#else
+        memcpy(p->data, data, tot * sizeof(double));
+#endif
+    } else {
+        return fail(JUBIK_ERR_ARG, "unknown data dtype");
+    }
+    p->has_data = 1;
+    return JUBIK_OK;
+}
+
+int jubik_plan_get_info(const jubik_plan* p, jubik_plan_info* i) {
+    if (!p || !i) return fail(JUBIK_ERR_ARG, "null plan/info");
+    const JbGeom& g = p->g;
+    i->N = g.N; i->n = g.n; i->m = g.m; i->dx = g.dx; i->w = g.w; i->P = g.P; i->L = g.L; i->PH = g.PH;
+    i->S_max = p->S_max; i->T = g.T; i->E = g.E; i->exact_period = p->exact; i->psf_half_support = p->support;
+    i->fft_r1 = p->ops->R1; i->fft_r2 = p->ops->R2; i->col_block = p->ops->CB;
+    i->bytes_khat = p->bytes_khat; i->bytes_workspace = p->bytes_ws; i->bytes_total = p->bytes_total;
+    return JUBIK_OK;
+}
+
+long long jubik_plan_launch_count(const jubik_plan* p) { return p ? p->launches : 0; }
+
+static int check_call(jubik_plan* p, const void* a, const void* b, int S) {
+    if (!p) return fail(JUBIK_ERR_ARG, "null plan");
+    if (!a || !b) return fail(JUBIK_ERR_ARG, "null array pointer");
+    if (S < 1 || S > p->S_max) return fail(JUBIK_ERR_ARG, "n_samples must be in [1, max_samples]");
+    return 0;
+}
+
+// forward chain with the chosen epilogue
+static int run_forward(jubik_plan* p, const double* x, int S, const JbEpi& ep, jb_stream_t st) {
+    const JbGeom& g = p->g;
+    const JbFftOps* o = p->ops;
+    JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.E, p->rpc_in, p->thr_rows, st));
+    JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, S * g.T * g.E, p->thr_cols, st));
+    JB_LAUNCHED(p, o->rows_out(g, p->bufA, p->tw_kn, ep, S * g.T * g.E, p->rpc_out, p->thr_rows, st));
+    return 0;
+}
+
+// adjoint chain; expo != nullptr multiplies the incoming cotangent by the effective exposure
+static int run_adjoint(jubik_plan* p, const double* gin, const double* expo, int S, double* out, jb_stream_t st) {
+    const JbGeom& g = p->g;
+    const JbFftOps* o = p->ops;
+    JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.E, p->rpc_in, p->thr_rows, st));
+    JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, S * g.T * g.E, p->thr_cols, st));
+    JB_LAUNCHED(p, o->rows_adj_out(g, p->bufB, p->wgt, p->tw_kn, out, S * g.E, p->rpc_out, p->thr_rows, st));
+    return 0;
+}
+
+int jubik_psf_apply(jubik_plan* p, const double* x, int S, double* out, void* stream_) {
+    if (int rc = check_call(p, x, out, S)) return rc;
+    JbEpi ep; memset(&ep, 0, sizeof(ep));
+    ep.mode = JB_EPI_PSF; ep.out = out;
+    return run_forward(p, x, S, ep, (jb_stream_t)stream_);
+}
+
+int jubik_psf_apply_T(jubik_plan* p, const double* gin, int S, double* out, void* stream_) {
+    if (int rc = check_call(p, gin, out, S)) return rc;
+    return run_adjoint(p, gin, nullptr, S, out, (jb_stream_t)stream_);
+}
+
+int jubik_response_apply(jubik_plan* p, const double* x, int S, double* out, void* stream_) {
+    if (int rc = check_call(p, x, out, S)) return rc;
+    if (!p->has_expo) return fail(JUBIK_ERR_ARG, "plan was created without exposures");
+    JbEpi ep; memset(&ep, 0, sizeof(ep));
+    ep.mode = JB_EPI_RESP; ep.out = out; ep.expo = p->expo;
+    return run_forward(p, x, S, ep, (jb_stream_t)stream_);
+}
+
+int jubik_response_apply_T(jubik_plan* p, const double* gin, int S, double* out, void* stream_) {
+    if (int rc = check_call(p, gin, out, S)) return rc;
+    if (!p->has_expo) return fail(JUBIK_ERR_ARG, "plan was created without exposures");
+    return run_adjoint(p, gin, p->expo, S, out, (jb_stream_t)stream_);
+}
+
+int jubik_poisson_energy_and_grad(jubik_plan* p, const double* x, int S, double* energy, double* grad, void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (int rc = check_call(p, x, energy, S)) return rc;
+    if (!p->has_expo || !p->has_data) return fail(JUBIK_ERR_ARG, "plan needs exposures and data for the Poisson energy");
+    const JbGeom& g = p->g;
+    JbEpi ep; memset(&ep, 0, sizeof(ep));
+    ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
+    if (int rc = run_forward(p, x, S, ep, st)) return rc;
+    JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
+                             (const double*)p->partial, g.T * g.E * p->nblk_out, energy));
+    if (grad) return run_adjoint(p, p->gbuf, nullptr, S, grad, st);
+    return JUBIK_OK;
+}
+
+int jubik_poisson_metric_apply(jubik_plan* p, const double* x, const double* v, int S, double* out, void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (int rc = check_call(p, x, out, S)) return rc;
+    if (!v) return fail(JUBIK_ERR_ARG, "null array pointer");
+    if (!p->has_expo) return fail(JUBIK_ERR_ARG, "plan was created without exposures");
+    const JbGeom& g = p->g;
+    if (!p->lbuf) {
+        size_t bG = (size_t)p->S_max * g.T * g.E * g.N * g.N * sizeof(double);
+        if (int rc = alloc(p, (void**)&p->lbuf, bG, "lambda workspace")) return rc;
+    }
+    JbEpi ep; memset(&ep, 0, sizeof(ep));
+    ep.mode = JB_EPI_RESP; ep.out = p->lbuf; ep.expo = p->expo;
+    if (int rc = run_forward(p, x, S, ep, st)) return rc;
+    ep.mode = JB_EPI_METRIC; ep.out = p->gbuf; ep.lam = p->lbuf;
+    if (int rc = run_forward(p, v, S, ep, st)) return rc;
+    return run_adjoint(p, p->gbuf, nullptr, S, out, st);
+}
+
+int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, double* eh, double* gh, void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (int rc = check_call(p, xh, eh, S)) return rc;
+    const JbGeom& g = p->g;
+    size_t bx = (size_t)p->S_max * g.E * g.N * g.N * sizeof(double);
+    if (!p->xdev) {
+        if (alloc(p, (void**)&p->xdev, bx, "host-call staging x") || alloc(p, (void**)&p->gdev, bx, "host-call staging grad") ||
+            alloc(p, (void**)&p->edev, p->S_max * sizeof(double), "host-call staging energy"))
+            return JUBIK_ERR_ALLOC;
+    }
+    size_t nx = (size_t)S * g.E * g.N * g.N * sizeof(double);
+    if (h2d(p->xdev, xh, nx, st)) return fail(JUBIK_ERR_CUDA, "H2D copy of x failed");
+    if (int rc = jubik_poisson_energy_and_grad(p, p->xdev, S, p->edev, gh ? p->gdev : nullptr, stream_)) return rc;
+    if (d2h(eh, p->edev, S * sizeof(double), st)) return fail(JUBIK_ERR_CUDA, "D2H copy of energy failed");
+    if (gh && d2h(gh, p->gdev, nx, st)) return fail(JUBIK_ERR_CUDA, "D2H copy of grad failed");
+    if (stream_sync(st)) return fail(JUBIK_ERR_CUDA, "stream synchronise failed");
+    return JUBIK_OK;
+}
+
+}  // extern "C"

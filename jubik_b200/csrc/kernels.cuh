@@ -1,0 +1,467 @@
+// kernels.cuh -- the hot path of J-UBIK's instrument response as sm_100a kernels.
+//
+// Reference chain (all /root/reference): jubik/convolve.py:66-145 linpatch_convolve =
+//   slice_patches(margin 0) :87  ->  * bilinear weights :88-90  ->  zero-pad m :92-101  ->
+//   circular FFT convolution with the prepared PSF :104-131,148-176  ->  transpose of
+//   slice_patches(margin m) :135-143 (overlap-add)  ->  crop m :144,
+// then jubik/response.py:44 (exposure), :110 (readout mask) and the Poisson energy
+// sum(lambda) - d log(lambda) (NIFTy jft.Poissonian; formula demos/x-ray-imaging.py:313).
+//
+// Decomposition used here (separable 2-D FFT with the intermediate spectra in L2/HBM):
+//   forward   R : k_rows_fwd (r2c of windowed sky rows) -> k_cols (column FFT * K^ * column IFFT)
+//                 -> k_rows_out (c2r + overlap-add as a GATHER + exposure/mask/Poisson epilogue)
+//   adjoint R^T : k_rows_adj_in (r2c of cotangent rows) -> k_cols (conj K^) -> k_rows_adj_out
+//                 (c2r + crop + weights + overlap-add gather, summed over modules)
+// Linearity is exploited twice: (1) the sky-row transform of window column-block i is shared by
+// the (<=2) row-patches j that contain the row -- one FFT, stored twice with the row weight;
+// (2) the spectra of all row-patches j (and modules t, in the adjoint) that land on one output
+// row are summed BEFORE the inverse row transform -- one c2r per (row, i) instead of one per
+// patch row.  Overlap-add is a deterministic gather; no atomics, no memset.
+//
+// Patch k = i*n + j sits at row offset offs[j], column offset offs[i] (meshgrid "xy",
+// convolve.py:59-63).
+#pragma once
+#include "fft_pass.cuh"
+
+#define JB_MAXN 64
+
+struct JbGeom {
+    int N, n, m, dx, w, hp, P;  // dx=int(N/n), w=2dx, hp=dx//2, P=w+2m  (convolve.py:43-51,104-105)
+    int L, PH;                  // FFT length (>= P) and stored spectrum columns L/2+1
+    int S, T, E;
+    int offs[JB_MAXN];          // clamped window starts in the hp-padded frame (lax.dynamic_slice)
+};
+
+enum { JB_EPI_PSF = 0, JB_EPI_RESP = 1, JB_EPI_POISSON = 2, JB_EPI_METRIC = 3 };
+
+struct JbEpi {
+    int mode;
+    const double* expo;   // (T,E,N,N) thresholded exposure * eff_area * pixel_area ; 0 == masked
+    const double* data;   // (T,E,N,N) counts as fp64
+    const double* lam;    // (S,T,E,N,N) for JB_EPI_METRIC
+    double* out;          // (S,T,E,N,N)
+    double* partial;      // per-CTA energy partials, [STE][gridDim.x]
+};
+
+// Row-patch list of an image row: all j with u = r + shift - offs[j] in [0, len).
+// Stored in shared memory as (j, u) pairs; cnt <= n.
+JB_D void jb_build_jlist(const JbGeom& g, int r0, int rpc, int shift, int len, int* jcnt, int* jj, int* ju) {
+    for (int rr = jb_tid(); rr < rpc; rr += jb_nthr()) {
+        int r = r0 + rr, c = 0;
+        if (r < g.N) {
+            for (int j = 0; j < g.n; ++j) {
+                int u = r + shift - g.offs[j];
+                if (u >= 0 && u < len) { jj[rr * g.n + c] = j; ju[rr * g.n + c] = u; ++c; }
+            }
+        }
+        jcnt[rr] = c;
+    }
+}
+
+JB_D size_t jb_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// ------------------------------------------------------------------ forward: sky rows -> spectra
+// grid (ceil(N/rpc), S*E).  x:(S,E,N,N).  bufB:(S*E, n*n, w, PH) rows u0 of the UN-padded window.
+template <class FP>
+JB_GLOBAL void k_rows_fwd(JbGeom g, const double* __restrict__ x, const double* __restrict__ wgt,
+                          const cd* __restrict__ tw_nk, cd* __restrict__ bufB, int rpc) {
+    JB_SMEM(unsigned char, smraw);
+    const int B = rpc * g.n;
+    cd* sm = reinterpret_cast<cd*>(smraw);
+    int* jcnt = reinterpret_cast<int*>(smraw + jb_align16((size_t)B * FP::LS * sizeof(cd)));
+    int* jj = jcnt + rpc;
+    int* ju = jj + rpc * g.n;
+    const int r0 = blockIdx.x * rpc, se = blockIdx.y;
+    jb_build_jlist(g, r0, rpc, g.hp, g.w, jcnt, jj, ju);
+    JB_SYNC();
+    const double* xp = x + (size_t)se * g.N * g.N;
+    const int n = g.n, N = g.N, m = g.m, w = g.w, hp = g.hp, PH = g.PH;
+    const size_t nn2 = (size_t)n * n;
+    auto ld = [&](int b, int p) -> double {
+        int rr = b / n, i = b - rr * n, r = r0 + rr;
+        int q = p - m;
+        int c = g.offs[i] - hp + q;
+        if (r >= N || q < 0 || q >= w || c < 0 || c >= N) return 0.0;
+        return jb_ldg(xp + (size_t)r * N + c) * jb_ldg(wgt + q);
+    };
+    auto st = [&](int b, int k, cd X) {
+        int rr = b / n, i = b - rr * n;
+        for (int q = 0; q < jcnt[rr]; ++q) {
+            int j = jj[rr * n + q], u0 = ju[rr * n + q];
+            double wr = jb_ldg(wgt + u0);
+            bufB[(((size_t)se * nn2 + (size_t)i * n + j) * w + u0) * PH + k] = cd_scale(X, wr);
+        }
+    };
+    rows_r2c<FP>(sm, tw_nk, B, ld, st);
+}
+
+// ---------------------------------------------------------- adjoint: cotangent rows -> spectra
+// grid (ceil(N/rpc), S*T*E).  gin:(S,T,E,N,N) (optionally * expo).  bufA:(STE, n*n, P, PH).
+template <class FP>
+JB_GLOBAL void k_rows_adj_in(JbGeom g, const double* __restrict__ gin, const double* __restrict__ expo,
+                             const cd* __restrict__ tw_nk, cd* __restrict__ bufA, int rpc) {
+    JB_SMEM(unsigned char, smraw);
+    const int B = rpc * g.n;
+    cd* sm = reinterpret_cast<cd*>(smraw);
+    int* jcnt = reinterpret_cast<int*>(smraw + jb_align16((size_t)B * FP::LS * sizeof(cd)));
+    int* jj = jcnt + rpc;
+    int* ju = jj + rpc * g.n;
+    const int r0 = blockIdx.x * rpc, ste = blockIdx.y;
+    jb_build_jlist(g, r0, rpc, g.hp + g.m, g.P, jcnt, jj, ju);
+    JB_SYNC();
+    const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, P = g.P;
+    const size_t nn2 = (size_t)n * n;
+    const double* gp = gin + (size_t)ste * N * N;
+    const double* ep = expo ? expo + (size_t)(ste % (g.T * g.E)) * N * N : nullptr;
+    auto ld = [&](int b, int p) -> double {
+        int rr = b / n, i = b - rr * n, r = r0 + rr;
+        int c = g.offs[i] - hp - m + p;
+        if (r >= N || p >= P || c < 0 || c >= N) return 0.0;
+        double v = jb_ldg(gp + (size_t)r * N + c);
+        if (ep) v *= jb_ldg(ep + (size_t)r * N + c);
+        return v;
+    };
+    auto st = [&](int b, int k, cd X) {
+        int rr = b / n, i = b - rr * n;
+        for (int q = 0; q < jcnt[rr]; ++q) {
+            int j = jj[rr * n + q], u = ju[rr * n + q];
+            bufA[(((size_t)ste * nn2 + (size_t)i * n + j) * P + u) * PH + k] = X;
+        }
+    };
+    rows_r2c<FP>(sm, tw_nk, B, ld, st);
+}
+
+// --------------------------------------------------------------------------- column pass
+// grid (nstrips, n*n, planes).  One CTA owns CB spectrum columns of one patch: forward column FFT,
+// multiply by the resident PSF spectrum (conj for the adjoint), inverse column FFT.
+//   forward : in  bufB rows p-m for p in [m, m+w)  (plane s*E+e)   out bufA rows p in [0,P)
+//   adjoint : in  bufA rows p in [0,P)                              out bufB rows p-m, p in [m,m+w)
+// Rows whose image row lies outside [0,N) were never written by the row kernels and are read as 0.
+// Khat layout per (t,e,patch): [strip][k2][k1][b]  -- exactly the register distribution after the
+// forward transform, so the load is perfectly coalesced and needs no index arithmetic.
+template <class FP, int CB, bool ADJ>
+JB_GLOBAL void k_cols(JbGeom g, const cd* __restrict__ in, cd* __restrict__ out,
+                      const cd* __restrict__ khat, const cd* __restrict__ tw_nk) {
+    JB_SMEM(cd, sm);
+    constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2;
+    const int strip = blockIdx.x, k = blockIdx.y, plane = blockIdx.z;
+    const int n = g.n, N = g.N, m = g.m, w = g.w, hp = g.hp, PH = g.PH, P = g.P;
+    const int j = k % n;
+    const int TE = g.T * g.E;
+    const int s = plane / TE, te = plane - s * TE, e = te % g.E;
+    const size_t nn2 = (size_t)n * n;
+    const int nstrips = gridDim.x;
+    const int col0 = strip * CB;
+    // image-row validity of patch rows
+    int in_p0, in_rows, vlo, vhi, out_p0, out_rows;
+    size_t in_plane, out_plane = plane;
+    if (!ADJ) {
+        in_p0 = m; in_rows = w; out_p0 = 0; out_rows = P;
+        in_plane = (size_t)s * g.E + e;
+        int lo = hp - g.offs[j], hi = N + hp - g.offs[j];  // valid u0 range
+        vlo = m + (lo > 0 ? lo : 0);
+        vhi = m + (hi < w ? hi : w);
+    } else {
+        in_p0 = 0; in_rows = P; out_p0 = m; out_rows = w;
+        in_plane = plane;
+        int lo = hp + m - g.offs[j], hi = N + hp + m - g.offs[j];
+        vlo = lo > 0 ? lo : 0;
+        vhi = hi < P ? hi : P;
+    }
+    const cd* ib = in + ((in_plane * nn2 + k) * in_rows) * PH;
+    cd* ob = out + ((out_plane * nn2 + k) * out_rows) * PH;
+    const cd* kb = khat + (((size_t)te * nn2 + k) * nstrips + strip) * ((size_t)L * CB);
+    auto ld = [&](int p, int b) -> cd {
+        int col = col0 + b;
+        if (col >= PH || p < vlo || p >= vhi) return cd_make(0.0, 0.0);
+        return ib[(size_t)(p - in_p0) * PH + col];
+    };
+    auto mid = [&](int k1, int k2, int b, cd X) -> cd {
+        cd kv = jb_ld_stream(kb + ((size_t)(k2 * R1 + k1)) * CB + b);
+        return ADJ ? cd_mulc(X, kv) : cd_mul(X, kv);
+    };
+    auto st = [&](int p, int b, cd v) {
+        int col = col0 + b;
+        if (col < PH && p >= out_p0 && p < out_p0 + out_rows) ob[(size_t)(p - out_p0) * PH + col] = v;
+    };
+    cols_cfft<FP, CB, true>(sm, tw_nk, ld, mid, st);
+}
+
+// fixed-order shared-memory tree: the same inputs always give the same bits
+template <bool MAX>
+JB_D double jb_block_reduce(double v, double* red) {
+    int t = jb_tid(), nt = jb_nthr();
+    red[t] = v;
+    JB_SYNC();
+    int p2 = 1;
+    while (p2 * 2 <= nt) p2 *= 2;
+    if (t + p2 < nt) red[t] = MAX ? (red[t + p2] > red[t] ? red[t + p2] : red[t]) : red[t] + red[t + p2];
+    JB_SYNC();
+    for (int sft = p2 / 2; sft > 0; sft >>= 1) {
+        if (t < sft) red[t] = MAX ? (red[t + sft] > red[t] ? red[t + sft] : red[t]) : red[t] + red[t + sft];
+        JB_SYNC();
+    }
+    double r = red[0];
+    JB_SYNC();
+    return r;
+}
+JB_D double jb_block_sum(double v, double* red) { return jb_block_reduce<false>(v, red); }
+
+// --------------------------------------------- forward: spectra -> image rows (+ epilogue)
+// grid (ceil(N/rpc), S*T*E).  Sums the spectra of every row-patch j that covers image row r,
+// one c2r per (row, i), overlap-add over i as a gather, then the exposure/mask/Poisson epilogue.
+template <class FP>
+JB_GLOBAL void k_rows_out(JbGeom g, const cd* __restrict__ bufA, const cd* __restrict__ tw_kn,
+                          JbEpi ep, int rpc) {
+    JB_SMEM(unsigned char, smraw);
+    const int B = rpc * g.n;
+    const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, P = g.P;
+    size_t off = 0;
+    cd* sm = reinterpret_cast<cd*>(smraw);
+    off += jb_align16((size_t)B * FP::LS * sizeof(cd));
+    double* tile = reinterpret_cast<double*>(smraw + off);
+    off += jb_align16((size_t)B * P * sizeof(double));
+    double* red = reinterpret_cast<double*>(smraw + off);
+    off += jb_align16((size_t)jb_nthr() * sizeof(double));
+    int* jcnt = reinterpret_cast<int*>(smraw + off);
+    int* jj = jcnt + rpc;
+    int* ju = jj + rpc * n;
+    const int r0 = blockIdx.x * rpc, ste = blockIdx.y;
+    jb_build_jlist(g, r0, rpc, hp + m, P, jcnt, jj, ju);
+    JB_SYNC();
+    const size_t nn2 = (size_t)n * n;
+    const cd* ab = bufA + (size_t)ste * nn2 * P * PH;
+    auto ld = [&](int b, int k) -> cd {
+        int rr = b / n, i = b - rr * n;
+        cd acc = cd_make(0.0, 0.0);
+        for (int q = 0; q < jcnt[rr]; ++q) {
+            int j = jj[rr * n + q], u = ju[rr * n + q];
+            acc = cd_add(acc, ab[(((size_t)i * n + j) * P + u) * PH + k]);
+        }
+        return acc;
+    };
+    auto st = [&](int b, int p, double v) {
+        if (p < P) tile[(size_t)b * P + p] = v;
+    };
+    rows_c2r<FP>(sm, tw_kn, B, ld, st);
+    JB_SYNC();
+    const int te = ste % (g.T * g.E);
+    double esum = 0.0;
+    for (int idx = jb_tid(); idx < rpc * N; idx += jb_nthr()) {
+        int rr = idx / N, c = idx - rr * N, r = r0 + rr;
+        if (r >= N) continue;
+        double conv = 0.0;
+        for (int i = 0; i < n; ++i) {
+            int p = c - (g.offs[i] - hp - m);
+            if (p >= 0 && p < P) conv += tile[(size_t)(rr * n + i) * P + p];
+        }
+        size_t o = ((size_t)ste * N + r) * N + c;
+        size_t oe = ((size_t)te * N + r) * N + c;
+        if (ep.mode == JB_EPI_PSF) {
+            ep.out[o] = conv;
+        } else {
+            double ex = jb_ldg(ep.expo + oe);
+            if (ep.mode == JB_EPI_RESP) {
+                ep.out[o] = (ex != 0.0) ? ex * conv : 0.0;
+            } else if (ep.mode == JB_EPI_POISSON) {
+                double gout = 0.0;
+                if (ex != 0.0) {
+                    double lam = ex * conv, d = jb_ldg(ep.data + oe);
+                    esum += lam - d * log(lam);
+                    gout = ex * (1.0 - d / lam);
+                }
+                ep.out[o] = gout;
+            } else {  // JB_EPI_METRIC: R^T-ready  ex * (R v) / lambda
+                double gout = 0.0;
+                if (ex != 0.0) gout = ex * (ex * conv) / ep.lam[o];
+                ep.out[o] = gout;
+            }
+        }
+    }
+    if (ep.mode == JB_EPI_POISSON) {
+        double tot = jb_block_sum(esum, red);
+        if (jb_tid() == 0) ep.partial[(size_t)ste * gridDim.x + blockIdx.x] = tot;
+    }
+}
+
+// ------------------------------- adjoint: spectra -> sky-gradient rows (sum over modules t)
+// grid (ceil(N/rpc), S*E).  bufB:(STE, n*n, w, PH).  grad:(S,E,N,N).
+template <class FP>
+JB_GLOBAL void k_rows_adj_out(JbGeom g, const cd* __restrict__ bufB, const double* __restrict__ wgt,
+                              const cd* __restrict__ tw_kn, double* __restrict__ grad, int rpc) {
+    JB_SMEM(unsigned char, smraw);
+    const int B = rpc * g.n;
+    const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, w = g.w;
+    size_t off = 0;
+    cd* sm = reinterpret_cast<cd*>(smraw);
+    off += jb_align16((size_t)B * FP::LS * sizeof(cd));
+    double* tile = reinterpret_cast<double*>(smraw + off);
+    off += jb_align16((size_t)B * w * sizeof(double));
+    int* jcnt = reinterpret_cast<int*>(smraw + off);
+    int* jj = jcnt + rpc;
+    int* ju = jj + rpc * n;
+    const int r0 = blockIdx.x * rpc, se = blockIdx.y;
+    const int s = se / g.E, e = se - s * g.E;
+    jb_build_jlist(g, r0, rpc, hp, w, jcnt, jj, ju);
+    JB_SYNC();
+    const size_t nn2 = (size_t)n * n;
+    auto ld = [&](int b, int k) -> cd {
+        int rr = b / n, i = b - rr * n;
+        cd acc = cd_make(0.0, 0.0);
+        for (int t = 0; t < g.T; ++t) {
+            const cd* bb = bufB + ((size_t)(s * g.T + t) * g.E + e) * nn2 * w * PH;
+            for (int q = 0; q < jcnt[rr]; ++q) {
+                int j = jj[rr * n + q], u0 = ju[rr * n + q];
+                double wr = jb_ldg(wgt + u0);
+                cd v = bb[(((size_t)i * n + j) * w + u0) * PH + k];
+                acc.x += wr * v.x;
+                acc.y += wr * v.y;
+            }
+        }
+        return acc;
+    };
+    auto st = [&](int b, int p, double v) {
+        int q = p - m;
+        if (q >= 0 && q < w) tile[(size_t)b * w + q] = v * jb_ldg(wgt + q);
+    };
+    rows_c2r<FP>(sm, tw_kn, B, ld, st);
+    JB_SYNC();
+    for (int idx = jb_tid(); idx < rpc * N; idx += jb_nthr()) {
+        int rr = idx / N, c = idx - rr * N, r = r0 + rr;
+        if (r >= N) continue;
+        double acc = 0.0;
+        for (int i = 0; i < n; ++i) {
+            int v = c - (g.offs[i] - hp);
+            if (v >= 0 && v < w) acc += tile[(size_t)(rr * n + i) * w + v];
+        }
+        grad[((size_t)se * N + r) * N + c] = acc;
+    }
+}
+
+// ============================================================================ plan-time kernels
+// PSF preparation, convolve.py:104-131: fftshift -> centre crop (2dx)^2 -> zero-pad m ->
+// ifftshift -> / (sum * dvol).  In offset coordinates d in [-dx, dx): value(d_row, d_col) =
+// kernel[d mod N] (FULL layout, origin-centred) or cut[d + dx] (CROPPED layout, centred).
+struct JbKsrc {
+    const double* ptr;
+    int cropped;  // 0: (T, n*n, E, N, N) origin-centred ; 1: (T, n*n, E, w, w) centred
+    int T, E;
+};
+
+JB_D double jb_kval(const JbGeom& g, const JbKsrc& ks, int t, int k, int e, int dr, int dc) {
+    size_t base = ((size_t)t * g.n * g.n + k) * ks.E + e;
+    if (ks.cropped) {
+        return ks.ptr[(base * g.w + (dr + g.dx)) * g.w + (dc + g.dx)];
+    } else {
+        int a = dr < 0 ? dr + g.N : dr, b = dc < 0 ? dc + g.N : dc;
+        return ks.ptr[(base * g.N + a) * g.N + b];
+    }
+}
+
+// one CTA per (te, k): sum of the cropped kernel and its half-support (max |d| with value != 0)
+JB_GLOBAL_S void k_prep_sum(JbGeom g, JbKsrc ks, double* __restrict__ sums, int* __restrict__ support) {
+    JB_SMEM(double, red);
+    const int k = blockIdx.x, te = blockIdx.y, t = te / ks.E, e = te - t * ks.E;
+    double acc = 0.0;
+    int sup = 0;
+    for (int idx = jb_tid(); idx < g.w * g.w; idx += jb_nthr()) {
+        int qr = idx / g.w, qc = idx - qr * g.w;
+        int dr = qr - g.dx, dc = qc - g.dx;
+        double v = jb_kval(g, ks, t, k, e, dr, dc);
+        acc += v;
+        if (v != 0.0) {
+            int ar = dr < 0 ? -dr : dr, ac = dc < 0 ? -dc : dc;
+            int a = ar > ac ? ar : ac;
+            sup = a > sup ? a : sup;
+        }
+    }
+    double tot = jb_block_sum(acc, red);
+    double mx = jb_block_reduce<true>((double)sup, red);
+    if (jb_tid() == 0) {
+        sums[(size_t)te * g.n * g.n + k] = tot;
+        support[(size_t)te * g.n * g.n + k] = (int)mx;
+    }
+}
+
+// grid (ceil(w/rpc), TE*n*n): r2c of the w non-zero rows of the prepared kernel (period L).
+// scratch:(TE*n*n, w, PH), row q <-> offset d_row = q - dx.
+template <class FP>
+JB_GLOBAL void k_prep_rows(JbGeom g, JbKsrc ks, const cd* __restrict__ tw_nk, cd* __restrict__ scratch, int rpc) {
+    JB_SMEM(cd, sm);
+    constexpr int L = FP::L;
+    const int q0 = blockIdx.x * rpc, pk = blockIdx.y;
+    const int nn2 = g.n * g.n;
+    const int te = pk / nn2, k = pk - te * nn2, t = te / ks.E, e = te - t * ks.E;
+    auto ld = [&](int b, int p) -> double {
+        int q = q0 + b;
+        if (q >= g.w) return 0.0;
+        int dc;
+        if (p < g.dx) dc = p;
+        else if (p >= L - g.dx) dc = p - L;
+        else return 0.0;
+        return jb_kval(g, ks, t, k, e, q - g.dx, dc);
+    };
+    auto st = [&](int b, int kk, cd X) {
+        int q = q0 + b;
+        if (q < g.w) scratch[((size_t)pk * g.w + q) * g.PH + kk] = X;
+    };
+    rows_r2c<FP>(sm, tw_nk, rpc, ld, st);
+}
+
+// grid (nstrips, n*n, TE): forward column FFT of the kernel row spectra, normalise by
+// 1/(sum * L^2) (the 1/L^2 of the inverse 2-D FFT is folded in here), store in k_cols' layout.
+template <class FP, int CB>
+JB_GLOBAL void k_prep_cols(JbGeom g, const cd* __restrict__ scratch, const double* __restrict__ sums,
+                           const cd* __restrict__ tw_nk, cd* __restrict__ khat) {
+    JB_SMEM(cd, sm);
+    constexpr int L = FP::L, R1 = FP::R1;
+    const int strip = blockIdx.x, k = blockIdx.y, te = blockIdx.z;
+    const int nn2 = g.n * g.n, PH = g.PH, dx = g.dx, w = g.w;
+    const int nstrips = gridDim.x, col0 = strip * CB;
+    const size_t pk = (size_t)te * nn2 + k;
+    const cd* ib = scratch + pk * w * PH;
+    cd* kb = khat + (pk * nstrips + strip) * ((size_t)L * CB);
+    const double scale = 1.0 / (sums[pk] * (double)L * (double)L);
+    auto ld = [&](int p, int b) -> cd {
+        int col = col0 + b, q;
+        if (p < dx) q = p + dx;
+        else if (p >= L - dx) q = p - L + dx;
+        else return cd_make(0.0, 0.0);
+        if (col >= PH) return cd_make(0.0, 0.0);
+        return ib[(size_t)q * PH + col];
+    };
+    auto mid = [&](int k1, int k2, int b, cd X) -> cd {
+        kb[((size_t)(k2 * R1 + k1)) * CB + b] = cd_scale(X, scale);
+        return X;
+    };
+    auto st = [&](int, int, cd) {};
+    cols_cfft<FP, CB, false>(sm, tw_nk, ld, mid, st);
+}
+
+// energy[s] = sum over (t,e) planes and row blocks of the per-CTA partials; one CTA per sample
+JB_GLOBAL_S void k_reduce_energy(const double* __restrict__ partial, int per_sample, double* __restrict__ energy) {
+    JB_SMEM(double, red);
+    const int s = blockIdx.x;
+    double acc = 0.0;
+    for (int i = jb_tid(); i < per_sample; i += jb_nthr()) acc += partial[(size_t)s * per_sample + i];
+    double tot = jb_block_sum(acc, red);
+    if (jb_tid() == 0) energy[s] = tot;
+}
+
+// expo_eff = (expo < cut ? 0 : expo) * eff_area[t,e] * pixel_area   (response.py:37-44,
+// erosita_response.py:327-328,349-350); data int64 -> fp64
+JB_GLOBAL_S void k_prep_expo(const double* __restrict__ expo, const double* __restrict__ eff, double cut,
+                           int has_cut, double pixel_area, size_t plane, size_t total, double* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * jb_nthr() + jb_tid(); i < total; i += (size_t)gridDim.x * jb_nthr()) {
+        double v = expo[i];
+        if (has_cut && v < cut) v = 0.0;
+        double f = pixel_area;
+        if (eff) f *= eff[i / plane];
+        out[i] = (v == 0.0) ? 0.0 : v * f;
+    }
+}
+
+JB_GLOBAL_S void k_i64_to_f64(const long long* __restrict__ in, size_t total, double* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * jb_nthr() + jb_tid(); i < total; i += (size_t)gridDim.x * jb_nthr())
+        out[i] = (double)in[i];
+}

@@ -1,0 +1,89 @@
+// ops.cuh -- per-FFT-length launch table.  Each supported transform length is instantiated in its own
+// translation unit (fft_L*.cu, one line each) so the lengths compile in parallel; capi.cu picks the
+// table by length at plan creation.
+#pragma once
+#include "kernels.cuh"
+
+struct JbFftOps {
+    int L, R1, R2, CB;
+    int ls;  // cd per real sequence in the exchange buffer
+    cudaError_t (*rows_fwd)(const JbGeom&, const double* x, const double* wgt, const cd* tw_nk, cd* bufB,
+                            int planes, int rpc, int threads, jb_stream_t);
+    cudaError_t (*rows_adj_in)(const JbGeom&, const double* gin, const double* expo, const cd* tw_nk, cd* bufA,
+                               int planes, int rpc, int threads, jb_stream_t);
+    cudaError_t (*cols)(const JbGeom&, bool adj, const cd* in, cd* out, const cd* khat, const cd* tw_nk,
+                        int planes, int threads, jb_stream_t);
+    cudaError_t (*rows_out)(const JbGeom&, const cd* bufA, const cd* tw_kn, const JbEpi&, int planes, int rpc,
+                            int threads, jb_stream_t);
+    cudaError_t (*rows_adj_out)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw_kn, double* grad,
+                                int planes, int rpc, int threads, jb_stream_t);
+    cudaError_t (*prep_rows)(const JbGeom&, const JbKsrc&, const cd* tw_nk, cd* scratch, int rpc, int threads,
+                             jb_stream_t);
+    cudaError_t (*prep_cols)(const JbGeom&, const cd* scratch, const double* sums, const cd* tw_nk, cd* khat,
+                             int threads, jb_stream_t);
+};
+
+inline int jb_cdiv(int a, int b) { return (a + b - 1) / b; }
+inline size_t jb_al16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+template <class FP, int CB>
+struct JbOpsImpl {
+    static size_t smem_rows_in(const JbGeom& g, int rpc) {
+        size_t B = (size_t)rpc * g.n;
+        return jb_al16(B * FP::LS * sizeof(cd)) + sizeof(int) * (rpc + 2 * (size_t)rpc * g.n) + 16;
+    }
+    static cudaError_t rows_fwd(const JbGeom& g, const double* x, const double* wgt, const cd* tw_nk, cd* bufB,
+                                int planes, int rpc, int threads, jb_stream_t st) {
+        return jb_launch(k_rows_fwd<FP>, dim3(jb_cdiv(g.N, rpc), planes), dim3(threads), smem_rows_in(g, rpc), st,
+                         g, x, wgt, tw_nk, bufB, rpc);
+    }
+    static cudaError_t rows_adj_in(const JbGeom& g, const double* gin, const double* expo, const cd* tw_nk,
+                                   cd* bufA, int planes, int rpc, int threads, jb_stream_t st) {
+        return jb_launch(k_rows_adj_in<FP>, dim3(jb_cdiv(g.N, rpc), planes), dim3(threads), smem_rows_in(g, rpc),
+                         st, g, gin, expo, tw_nk, bufA, rpc);
+    }
+    static cudaError_t cols(const JbGeom& g, bool adj, const cd* in, cd* out, const cd* khat, const cd* tw_nk,
+                            int planes, int threads, jb_stream_t st) {
+        dim3 grid(jb_cdiv(g.PH, CB), g.n * g.n, planes);
+        size_t smem = (FP::R2 == 1) ? 16 : (size_t)FP::L * CB * sizeof(cd);
+        if (adj) return jb_launch(k_cols<FP, CB, true>, grid, dim3(threads), smem, st, g, in, out, khat, tw_nk);
+        return jb_launch(k_cols<FP, CB, false>, grid, dim3(threads), smem, st, g, in, out, khat, tw_nk);
+    }
+    static cudaError_t rows_out(const JbGeom& g, const cd* bufA, const cd* tw_kn, const JbEpi& ep, int planes,
+                                int rpc, int threads, jb_stream_t st) {
+        size_t B = (size_t)rpc * g.n;
+        size_t smem = jb_al16(B * FP::LS * sizeof(cd)) + jb_al16(B * g.P * sizeof(double)) +
+                      jb_al16((size_t)threads * sizeof(double)) + sizeof(int) * (rpc + 2 * (size_t)rpc * g.n) + 16;
+        return jb_launch(k_rows_out<FP>, dim3(jb_cdiv(g.N, rpc), planes), dim3(threads), smem, st, g, bufA, tw_kn,
+                         ep, rpc);
+    }
+    static cudaError_t rows_adj_out(const JbGeom& g, const cd* bufB, const double* wgt, const cd* tw_kn,
+                                    double* grad, int planes, int rpc, int threads, jb_stream_t st) {
+        size_t B = (size_t)rpc * g.n;
+        size_t smem = jb_al16(B * FP::LS * sizeof(cd)) + jb_al16(B * g.w * sizeof(double)) +
+                      sizeof(int) * (rpc + 2 * (size_t)rpc * g.n) + 16;
+        return jb_launch(k_rows_adj_out<FP>, dim3(jb_cdiv(g.N, rpc), planes), dim3(threads), smem, st, g, bufB,
+                         wgt, tw_kn, grad, rpc);
+    }
+    static cudaError_t prep_rows(const JbGeom& g, const JbKsrc& ks, const cd* tw_nk, cd* scratch, int rpc,
+                                 int threads, jb_stream_t st) {
+        size_t smem = jb_al16((size_t)rpc * FP::LS * sizeof(cd)) + 16;
+        return jb_launch(k_prep_rows<FP>, dim3(jb_cdiv(g.w, rpc), ks.T * ks.E * g.n * g.n), dim3(threads), smem, st,
+                         g, ks, tw_nk, scratch, rpc);
+    }
+    static cudaError_t prep_cols(const JbGeom& g, const cd* scratch, const double* sums, const cd* tw_nk, cd* khat,
+                                 int threads, jb_stream_t st) {
+        dim3 grid(jb_cdiv(g.PH, CB), g.n * g.n, g.T * g.E);
+        size_t smem = (FP::R2 == 1) ? 16 : (size_t)FP::L * CB * sizeof(cd);
+        return jb_launch(k_prep_cols<FP, CB>, grid, dim3(threads), smem, st, g, scratch, sums, tw_nk, khat);
+    }
+    static const JbFftOps* table() {
+        static const JbFftOps t = {FP::L, FP::R1, FP::R2, CB, FP::LS, rows_fwd, rows_adj_in, cols,
+                                   rows_out, rows_adj_out, prep_rows, prep_cols};
+        return &t;
+    }
+};
+
+#define JB_DEFINE_FFT(LEN, R1, R2, CB) \
+    const JbFftOps* jb_fft_ops_##LEN() { return JbOpsImpl<FftPlan<LEN, R1, R2>, CB>::table(); }
+#define JB_DECLARE_FFT(LEN) const JbFftOps* jb_fft_ops_##LEN();

@@ -1,0 +1,240 @@
+"""ResponsePlan -- device-resident state of one instrument response (PSF spectra, effective exposure,
+mask, counts) and the calls that run the CUDA hot path on torch CUDA tensors.
+
+torch is used for device memory and streams only; every flop of the path runs in libjubik_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _lib
+from ._lib import PlanDesc, PlanInfo, check
+
+
+class RawPlan:
+    """Pointer-level wrapper around jubik_plan* (no array library involved)."""
+
+    def __init__(self, lib, desc: PlanDesc, stream=0):
+        self.lib = lib
+        self.handle = C.c_void_p()
+        check(lib, lib.jubik_plan_create(C.byref(self.handle), C.byref(desc), C.c_void_p(stream)))
+        info = PlanInfo()
+        check(lib, lib.jubik_plan_get_info(self.handle, C.byref(info)))
+        self.info = {k: getattr(info, k) for k, _ in PlanInfo._fields_}
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.jubik_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def call(self, name, *args):
+        check(self.lib, getattr(self.lib, name)(self.handle, *args))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.jubik_plan_launch_count(self.handle))
+
+
+def make_desc(N, E, T, n_patches, margin, kernel_ptr, cropped, max_samples=1, exposure_ptr=None,
+              exposure_cut=None, eff_area_ptr=None, pixel_area=1.0, data_ptr=None, data_is_int=False,
+              distances=(1.0, 1.0), fft_length=0, N1=None):
+    d = PlanDesc()
+    d.n0, d.n1 = int(N), int(N if N1 is None else N1)
+    d.n_energy, d.n_modules, d.max_samples = int(E), int(T), int(max_samples)
+    d.n_patches, d.margin = int(n_patches), int(margin)
+    d.kernel_layout = _lib.KERNEL_CROPPED if cropped else _lib.KERNEL_FULL
+    d.data_dtype = _lib.DATA_I64 if data_is_int else _lib.DATA_F64
+    d.has_exposure_cut = 0 if exposure_cut is None else 1
+    d.exposure_cut = 0.0 if exposure_cut is None else float(exposure_cut)
+    d.fft_length = int(fft_length)
+    d.d0, d.d1 = float(distances[0]), float(distances[1])
+    d.pixel_area = float(pixel_area)
+    d.kernel = kernel_ptr
+    d.exposure = exposure_ptr
+    d.eff_area = eff_area_ptr
+    d.data = data_ptr
+    return d
+
+
+class ResponsePlan:
+    """R(x) = mask(exposure(psf(x * pixel_area))) and the Poisson likelihood on it, on one GPU.
+
+    kernel   : torch.float64 CUDA tensor (T, n*n, E, N, N) origin-centred  [reference layout,
+               erosita_psf_utils.py:262-263] or, with cropped=True, (T, n*n, E, 2dx, 2dx) centred.
+    exposure : (T, E, N, N) raw exposures or None (PSF-only plan); thresholded with exposure_cut
+               exactly like response.py:37-40 / :85-87 (mask == thresholded exposure == 0).
+    data     : (T, E, N, N) dense counts (int64 or float64) or None.
+    """
+
+    def __init__(self, kernel, N, n_patches, margin, exposure=None, exposure_cut=None, eff_area=None,
+                 pixel_area=1.0, data=None, max_samples=1, cropped=False, distances=(1.0, 1.0),
+                 fft_length=0):
+        import torch
+        lib = _lib.load()
+        if not (kernel.is_cuda and kernel.dtype == torch.float64):
+            raise TypeError("kernel must be a float64 CUDA tensor (jubik_b200 has no CPU path)")
+        if kernel.dim() != 5:
+            raise ValueError("kernel must have shape (T, n*n, E, H, W)")
+        kernel = kernel.contiguous()
+        T, nn2, E = kernel.shape[0], kernel.shape[1], kernel.shape[2]
+        if nn2 != n_patches * n_patches:
+            raise ValueError("kernel.shape[1] must be n_patches_per_axis**2")
+        dx = int(N / n_patches)
+        exp_hw = (2 * dx, 2 * dx) if cropped else (N, N)
+        if tuple(kernel.shape[-2:]) != exp_hw:
+            raise ValueError("kernel spatial shape %s does not match layout %s" % (tuple(kernel.shape[-2:]), exp_hw))
+        self.device = kernel.device
+        self.T, self.E, self.N, self.S_max = T, E, N, max_samples
+        keep = []
+        eptr = fptr = dptr = None
+        if exposure is not None:
+            exposure = exposure.to(self.device, torch.float64).contiguous()
+            if tuple(exposure.shape) != (T, E, N, N):
+                raise ValueError("exposure should have shape (T, E, N, N)")
+            eptr = exposure.data_ptr()
+            keep.append(exposure)
+        if eff_area is not None:
+            eff_area = eff_area.to(self.device, torch.float64).contiguous()
+            if tuple(eff_area.shape) != (T, E):
+                raise ValueError("eff_area should have shape (T, E)")
+            fptr = eff_area.data_ptr()
+            keep.append(eff_area)
+        data_is_int = False
+        if data is not None:
+            data, data_is_int = self._prep_data(data)
+            dptr = data.data_ptr()
+            keep.append(data)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            desc = make_desc(N, E, T, n_patches, margin, kernel.data_ptr(), cropped, max_samples, eptr,
+                             exposure_cut, fptr, pixel_area, dptr, data_is_int, distances, fft_length)
+            self.raw = RawPlan(lib, desc, stream)
+        self.info = self.raw.info
+        del keep
+
+    def _prep_data(self, data):
+        import torch
+        data = data.to(self.device)
+        if data.dtype in (torch.int64,):
+            is_int = True
+        elif data.dtype in (torch.int32, torch.int16, torch.uint8, torch.int8):
+            data, is_int = data.to(torch.int64), True
+        else:
+            data, is_int = data.to(torch.float64), False
+        data = data.contiguous()
+        if tuple(data.shape) != (self.T, self.E, self.N, self.N):
+            raise ValueError("data should have shape (T, E, N, N)")
+        return data, is_int
+
+    # -------------------------------------------------------------------------------- helpers
+    def _stream(self):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _sky(self, x):
+        import torch
+        if not (x.is_cuda and x.dtype == torch.float64):
+            raise TypeError("input must be a float64 CUDA tensor")
+        squeeze = x.dim() == 3
+        if squeeze:
+            x = x.unsqueeze(0)
+        if x.dim() != 4 or tuple(x.shape[1:]) != (self.E, self.N, self.N):
+            raise ValueError("sky should have shape ([S,] E, N, N)")
+        if x.shape[0] > self.S_max:
+            raise ValueError("more samples than the plan's max_samples")
+        return x.contiguous(), squeeze
+
+    def _det(self, g):
+        import torch
+        if not (g.is_cuda and g.dtype == torch.float64):
+            raise TypeError("input must be a float64 CUDA tensor")
+        squeeze = g.dim() == 4
+        if squeeze:
+            g = g.unsqueeze(0)
+        if g.dim() != 5 or tuple(g.shape[1:]) != (self.T, self.E, self.N, self.N):
+            raise ValueError("detector-space input should have shape ([S,] T, E, N, N)")
+        if g.shape[0] > self.S_max:
+            raise ValueError("more samples than the plan's max_samples")
+        return g.contiguous(), squeeze
+
+    def _fwd(self, name, x):
+        import torch
+        x, sq = self._sky(x)
+        out = torch.empty((x.shape[0], self.T, self.E, self.N, self.N), dtype=torch.float64, device=self.device)
+        self.raw.call(name, C.c_void_p(x.data_ptr()), x.shape[0], C.c_void_p(out.data_ptr()), self._stream())
+        return out[0] if sq else out
+
+    def _adj(self, name, g):
+        import torch
+        g, sq = self._det(g)
+        out = torch.empty((g.shape[0], self.E, self.N, self.N), dtype=torch.float64, device=self.device)
+        self.raw.call(name, C.c_void_p(g.data_ptr()), g.shape[0], C.c_void_p(out.data_ptr()), self._stream())
+        return out[0] if sq else out
+
+    # ---------------------------------------------------------------------------------- calls
+    def psf(self, x):
+        """vmap(linpatch_convolve) over modules: ([S,]E,N,N) -> ([S,]T,E,N,N)."""
+        return self._fwd("jubik_psf_apply", x)
+
+    def psf_T(self, g):
+        return self._adj("jubik_psf_apply_T", g)
+
+    def response(self, x):
+        """Dense R(x): exposure * psf(x * pixel_area), masked pixels = 0."""
+        return self._fwd("jubik_response_apply", x)
+
+    def response_T(self, g):
+        return self._adj("jubik_response_apply_T", g)
+
+    def set_data(self, data):
+        data, is_int = self._prep_data(data)
+        self.raw.call("jubik_plan_set_data", C.c_void_p(data.data_ptr()),
+                      _lib.DATA_I64 if is_int else _lib.DATA_F64, self._stream())
+        import torch
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def energy_and_grad(self, x, need_grad=True):
+        """Poisson energy sum(lambda) - d.log(lambda) per sample and its gradient w.r.t. the sky."""
+        import torch
+        x, sq = self._sky(x)
+        S = x.shape[0]
+        energy = torch.empty((S,), dtype=torch.float64, device=self.device)
+        grad = torch.empty_like(x) if need_grad else None
+        self.raw.call("jubik_poisson_energy_and_grad", C.c_void_p(x.data_ptr()), S, C.c_void_p(energy.data_ptr()),
+                      C.c_void_p(grad.data_ptr()) if need_grad else None, self._stream())
+        if sq:
+            return energy[0], (grad[0] if need_grad else None)
+        return energy, grad
+
+    def energy(self, x):
+        return self.energy_and_grad(x, need_grad=False)[0]
+
+    def metric(self, x, v):
+        """Fisher metric pulled back through R:  R^T diag(1/(R x)) R v."""
+        import torch
+        x, sq = self._sky(x)
+        v, _ = self._sky(v)
+        out = torch.empty_like(x)
+        self.raw.call("jubik_poisson_metric_apply", C.c_void_p(x.data_ptr()), C.c_void_p(v.data_ptr()), x.shape[0],
+                      C.c_void_p(out.data_ptr()), self._stream())
+        return out[0] if sq else out
+
+    def energy_and_grad_host(self, x_host, energy_host, grad_host):
+        """End-to-end call on HOST tensors (pinned for full PCIe speed): H2D, kernels, D2H, sync."""
+        S = x_host.shape[0] if x_host.dim() == 4 else 1
+        self.raw.call("jubik_poisson_energy_and_grad_host", C.c_void_p(x_host.data_ptr()), S,
+                      C.c_void_p(energy_host.data_ptr()),
+                      C.c_void_p(grad_host.data_ptr()) if grad_host is not None else None, self._stream())
+
+    @property
+    def launch_count(self):
+        return self.raw.launch_count
+
+    def close(self):
+        self.raw.close()
