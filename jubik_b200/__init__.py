@@ -1,0 +1,12 @@
+"""jubik_b200 -- B200-native (sm_100a CUDA) implementation of J-UBIK's instrument-response hot path:
+spatially-variant PSF convolution (linpatch_convolve) fused with exposure, readout mask and the Poisson
+log-likelihood, forward and exact adjoint, float64.  See DESIGN.md / INTEGRATION.md.
+
+Importing the package does not need a GPU; every compute entry point does and raises otherwise.
+"""
+from ._lib import JubikError, load as load_library  # noqa: F401
+from .api import (Domain, PoissonLikelihood, Vector, build_exposure_function, build_psf_operator,  # noqa: F401
+                  build_readout_function, build_response, linpatch_convolve)
+from .plan import ResponsePlan  # noqa: F401
+
+__version__ = "0.1.0"

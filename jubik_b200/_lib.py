@@ -20,7 +20,7 @@ EXPORTS = [
     "jubik_plan_create", "jubik_plan_destroy", "jubik_plan_get_info", "jubik_plan_set_data",
     "jubik_plan_launch_count", "jubik_psf_apply", "jubik_psf_apply_T", "jubik_response_apply",
     "jubik_response_apply_T", "jubik_poisson_energy_and_grad", "jubik_poisson_metric_apply",
-    "jubik_poisson_energy_and_grad_host",
+    "jubik_poisson_energy_and_grad_host", "jubik_poisson_profile", "jubik_measure_fp64_tflops",
 ]
 
 
@@ -64,6 +64,8 @@ def bind(lib):
     lib.jubik_poisson_energy_and_grad.argtypes = [vp, vp, i, vp, vp, vp]
     lib.jubik_poisson_metric_apply.argtypes = [vp, vp, vp, i, vp, vp]
     lib.jubik_poisson_energy_and_grad_host.argtypes = [vp, vp, i, vp, vp, vp]
+    lib.jubik_poisson_profile.argtypes = [vp, vp, i, vp, vp, C.POINTER(C.c_float), vp]
+    lib.jubik_measure_fp64_tflops.argtypes = [C.POINTER(d), vp]
     for name in EXPORTS:
         if name not in ("jubik_last_error", "jubik_plan_launch_count"):
             getattr(lib, name).restype = i

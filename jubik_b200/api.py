@@ -1,0 +1,203 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+Same names, argument meaning and error behaviour as the reference so that callers (and tests) read like
+the reference's own:
+
+    Domain                      jubik/data.py:19-29
+    linpatch_convolve           jubik/convolve.py:66-145
+    build_exposure_function     jubik/response.py:12-45
+    build_readout_function      jubik/response.py:48-112
+    build_psf_operator          instruments/erosita/erosita_response.py:206-212 (psf_op), chandra :127-130
+    build_response              erosita_response.py:307-358 / chandra_response.py:127-149 -> response_dict
+    PoissonLikelihood           jft.Poissonian(masked_data).amend(R)  (erosita_likelihood.py:85-89,
+                                chandra_likelihood.py:37)
+
+Arrays are torch float64 CUDA tensors.  The compute runs in libjubik_b200.so through ResponsePlan; torch is
+only the memory/stream carrier (plus the trivial un-fused elementwise exposure/readout callables that the
+reference also exposes separately).  There is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import NamedTuple
+
+from .plan import ResponsePlan
+
+
+class Domain(NamedTuple):
+    """jubik/data.py:19-29 -- only shape[-2:] and distances[-2:] are consumed by the hot path."""
+    shape: tuple
+    distances: tuple
+
+
+class Vector:
+    """Minimal stand-in for nifty.re.Vector (pytree wrapper around a dict of arrays)."""
+
+    def __init__(self, tree):
+        self.tree = tree
+
+    def __getitem__(self, k):
+        return self.tree[k]
+
+    def keys(self):
+        return self.tree.keys()
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _as_cuda(a, device=None):
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: jubik_b200 has no CPU fallback")
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        t = torch.as_tensor(a)
+    return t.to(device or "cuda", torch.float64)
+
+
+_PLAN_CACHE = {}
+
+
+def linpatch_convolve(x, domain, kernel, n_patches_per_axis, margin):
+    """Drop-in for jubik.linpatch_convolve (convolve.py:66-145).
+
+    x: (..., N, N); kernel: (n*n, ..., N, N) origin-centred, same leading axes as x.  A plan (PSF spectra)
+    is built per distinct kernel tensor and cached; hot loops should hold a plan via build_psf_operator.
+    """
+    if not isinstance(domain, Domain):
+        raise ValueError("domain has to be an instance of jubik.Domain")
+    torch = _torch()
+    x = _as_cuda(x)
+    kernel = _as_cuda(kernel, x.device)
+    N = domain.shape[-1]
+    lead = tuple(x.shape[:-2])
+    E = 1
+    for s in lead:
+        E *= s
+    key = (kernel.data_ptr(), kernel._version, tuple(kernel.shape), N, n_patches_per_axis, margin, x.device.index)
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        k5 = kernel.reshape((1, kernel.shape[0], E) + tuple(kernel.shape[-2:]))
+        plan = ResponsePlan(k5, N, n_patches_per_axis, margin, distances=tuple(domain.distances[-2:]))
+        if len(_PLAN_CACHE) >= 4:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE))).close()
+        _PLAN_CACHE[key] = plan
+    y = plan.psf(x.reshape((E, N, N)))[0]
+    return y.reshape(lead + (N, N))
+
+
+def build_exposure_function(exposures, exposure_cut=None):
+    """response.py:12-45: thresholds `exposures` IN PLACE (like the reference) and returns x -> exposures*x."""
+    if exposure_cut is not None:
+        if exposure_cut < 0:
+            raise ValueError("exposure_cut should be non-negative or None!")
+        exposures[exposures < exposure_cut] = 0
+
+    def exposure(x):
+        return exposures * x
+    return exposure
+
+
+def build_readout_function(flags, threshold=None, keys=None):
+    """response.py:48-112: x (T,E,N,N) -> Vector{key: x[i][~mask[i]]}, mask = thresholded flags == 0."""
+    if threshold is not None and threshold < 0:
+        raise ValueError("threshold should be positive!")
+    if threshold is not None:
+        flags[flags < threshold] = 0
+    mask = flags == 0
+    if keys is None:
+        keys = ['masked input']
+    elif len(keys) != flags.shape[0]:
+        raise ValueError("length of keys should match the number of flag maps.")
+
+    def _apply_readout(x):
+        if len(mask.shape) != 4:
+            raise ValueError("flags should have shape (n, m, q, l)!")
+        if len(x.shape) != 4:
+            raise ValueError("input should have shape (n, m, q, l)!")
+        return Vector({key: x[i][~mask[i]] for i, key in enumerate(keys)})
+    return _apply_readout
+
+
+def build_psf_operator(kernel, domain, n_patches_per_axis, margin, max_samples=1, cropped=False):
+    """psf_op of erosita_response.py:209-212 / chandra_response.py:127-130 with the PSF spectra resident.
+
+    kernel: (T, n*n, E, N, N).  Returns (psf_func, plan); psf_func(x) maps ([S,]E,N,N) -> ([S,]T,E,N,N)."""
+    if not isinstance(domain, Domain):
+        raise ValueError("domain has to be an instance of jubik.Domain")
+    kernel = _as_cuda(kernel)
+    plan = ResponsePlan(kernel, domain.shape[-1], n_patches_per_axis, margin, max_samples=max_samples,
+                        cropped=cropped, distances=tuple(domain.distances[-2:]))
+    return plan.psf, plan
+
+
+def build_response(kernel, exposures, domain, n_patches_per_axis, margin, pixel_area, exposure_cut=None,
+                   effective_area=None, keys=None, max_samples=1, cropped=False, data=None):
+    """Response dictionary with the reference's keys ('pix_area', 'psf', 'exposure', 'mask', 'R') plus the
+    fused entries ('R_dense', 'R_dense_T', 'plan').
+
+    R(x) = mask(exposure(psf(x * pixel_area)))  -- erosita_response.py:349-350, chandra_response.py:138-142.
+    The exposure cut is applied to both the exposure and the readout mask, as both instruments do
+    (SURVEY Appendix A10)."""
+    torch = _torch()
+    if not isinstance(domain, Domain):
+        raise ValueError("domain has to be an instance of jubik.Domain")
+    kernel = _as_cuda(kernel)
+    expo_raw = _as_cuda(exposures, kernel.device).clone()
+    T = kernel.shape[0]
+    eff = None if effective_area is None else _as_cuda(effective_area, kernel.device)
+    plan = ResponsePlan(kernel, domain.shape[-1], n_patches_per_axis, margin, exposure=expo_raw,
+                        exposure_cut=exposure_cut, eff_area=eff, pixel_area=pixel_area, data=data,
+                        max_samples=max_samples, cropped=cropped, distances=tuple(domain.distances[-2:]))
+    expo_thr = expo_raw.clone()
+    tmp = build_exposure_function(expo_thr, exposure_cut)
+    if eff is not None:
+        def exposure_func(x):
+            return tmp(x) * eff[:, :, None, None]
+    else:
+        exposure_func = tmp
+    mask_func = build_readout_function(expo_raw.clone(), exposure_cut,
+                                       list(keys) if keys is not None else list(range(T)))
+
+    def response_func(x):
+        return mask_func(plan.response(x))
+
+    return {'pix_area': pixel_area, 'psf': plan.psf, 'exposure': exposure_func, 'mask': mask_func,
+            'R': response_func, 'R_dense': plan.response, 'R_dense_T': plan.response_T, 'plan': plan}
+
+
+class PoissonLikelihood:
+    """jft.Poissonian(masked_data).amend(R) on the fused CUDA path.
+
+    `data` is either dense (T,E,N,N) counts or a Vector/dict of the reference's compacted 1-D arrays per key
+    (response.py:110), which is scattered back onto the dense grid once (transpose of the mask)."""
+
+    def __init__(self, response_dict, data, keys=None):
+        torch = _torch()
+        self.plan = response_dict['plan']
+        if isinstance(data, (Vector, dict)):
+            tree = data.tree if isinstance(data, Vector) else data
+            keys = list(tree.keys()) if keys is None else keys
+            p = self.plan
+            probe = torch.ones((p.T, p.E, p.N, p.N), dtype=torch.float64, device=p.device)
+            expo = response_dict['exposure'](probe)
+            mask = expo != 0
+            dense = torch.zeros((p.T, p.E, p.N, p.N), dtype=torch.float64, device=p.device)
+            for i, k in enumerate(keys):
+                dense[i][mask[i]] = torch.as_tensor(tree[k]).to(p.device, torch.float64)
+            data = dense
+        self.plan.set_data(torch.as_tensor(data))
+
+    def energy(self, x):
+        return self.plan.energy(x)
+
+    def value_and_grad(self, x):
+        return self.plan.energy_and_grad(x)
+
+    def metric(self, x, v):
+        return self.plan.metric(x, v)
+
+    __call__ = energy

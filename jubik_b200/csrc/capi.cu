@@ -71,14 +71,27 @@ struct jubik_plan {
     double* edev = nullptr;
     size_t bytes_khat = 0, bytes_ws = 0, bytes_total = 0;
     int nblk_out = 0;
+    // per-kernel timing (jubik_poisson_profile): events recorded after every launch while enabled
+    int prof_on = 0, prof_n = 0;
+#ifndef JB_EMU
+    cudaEvent_t prof_ev[16] = {};
+#endif
 };
+
+static inline void jb_mark(jubik_plan* p, jb_stream_t st) {
+#ifndef JB_EMU
+    if (p->prof_on && p->prof_n < 16) cudaEventRecord(p->prof_ev[p->prof_n++], st);
+#else
+    (void)p; (void)st;
+#endif
+}
 
 #define JB_CK(call)                                                           \
     do {                                                                      \
         cudaError_t e_ = (call);                                              \
         if (e_ != cudaSuccess) return fail(JUBIK_ERR_CUDA, std::string(#call) + " -> " + cuda_msg(e_)); \
     } while (0)
-#define JB_LAUNCHED(p, call) do { JB_CK(call); ++(p)->launches; } while (0)
+#define JB_LAUNCHED(p, call) do { JB_CK(call); ++(p)->launches; jb_mark(p, st); } while (0)
 
 extern "C" {
 
@@ -378,6 +391,69 @@ int jubik_poisson_energy_and_grad(jubik_plan* p, const double* x, int S, double*
                              (const double*)p->partial, g.T * g.E * p->nblk_out, energy));
     if (grad) return run_adjoint(p, p->gbuf, nullptr, S, grad, st);
     return JUBIK_OK;
+}
+
+// Same work as jubik_poisson_energy_and_grad with a CUDA event after every kernel; ms_out[0..6] =
+// rows_fwd, cols_fwd, rows_out(+Poisson), reduce, rows_adj_in, cols_adj, rows_adj_out.  Synchronises.
+int jubik_poisson_profile(jubik_plan* p, const double* x, int S, double* energy, double* grad, float* ms_out, void* stream_) {
+#ifndef JB_EMU
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (!ms_out || !grad) return fail(JUBIK_ERR_ARG, "null pointer");
+    for (int i = 0; i < 16; ++i) if (!p->prof_ev[i]) JB_CK(cudaEventCreate(&p->prof_ev[i]));
+    p->prof_on = 1; p->prof_n = 0;
+    jb_mark(p, st);
+    int rc = jubik_poisson_energy_and_grad(p, x, S, energy, grad, stream_);
+    p->prof_on = 0;
+    if (rc) return rc;
+    JB_CK(cudaStreamSynchronize(st));
+    for (int i = 0; i + 1 < p->prof_n && i < 7; ++i) JB_CK(cudaEventElapsedTime(&ms_out[i], p->prof_ev[i], p->prof_ev[i + 1]));
+    return JUBIK_OK;
+#else
+    (void)p; (void)x; (void)S; (void)energy; (void)grad; (void)ms_out; (void)stream_;
+    return fail(JUBIK_ERR_UNSUPPORTED, "profiling needs CUDA");
+#endif
+}
+
+// Measured FP64 FMA throughput of this device (DFMA micro-benchmark: 8 independent chains per thread),
+// the second roofline denominator of SURVEY 8(d).  Synchronises.
+JB_GLOBAL_S void k_dfma_peak(double* out, int iters) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999999, c = 1e-12;
+    for (int i = 0; i < iters; ++i) {
+        a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+        a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) out[0] = s;
+}
+
+int jubik_measure_fp64_tflops(double* tflops_out, void* stream_) {
+#ifndef JB_EMU
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (!tflops_out) return fail(JUBIK_ERR_ARG, "null pointer");
+    double* d = nullptr;
+    JB_CK(cudaMalloc((void**)&d, 8));
+    cudaEvent_t a, b;
+    JB_CK(cudaEventCreate(&a)); JB_CK(cudaEventCreate(&b));
+    const int blocks = 148 * 8, threads = 256, iters = 1 << 15;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        JB_CK(cudaEventRecord(a, st));
+        k_dfma_peak<<<blocks, threads, 0, st>>>(d, iters);
+        JB_CK(cudaEventRecord(b, st));
+        JB_CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        JB_CK(cudaEventElapsedTime(&ms, a, b));
+        double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    *tflops_out = best;
+    return JUBIK_OK;
+#else
+    (void)tflops_out; (void)stream_;
+    return fail(JUBIK_ERR_UNSUPPORTED, "needs CUDA");
+#endif
 }
 
 int jubik_poisson_metric_apply(jubik_plan* p, const double* x, const double* v, int S, double* out, void* stream_) {

@@ -232,9 +232,32 @@ class ResponsePlan:
                       C.c_void_p(energy_host.data_ptr()),
                       C.c_void_p(grad_host.data_ptr()) if grad_host is not None else None, self._stream())
 
+    KERNEL_NAMES = ("rows_fwd", "cols_fwd", "rows_out", "reduce", "rows_adj_in", "cols_adj", "rows_adj_out")
+
+    def profile(self, x):
+        """energy_and_grad with a CUDA event after each kernel -> (energy, grad, {kernel: ms})."""
+        import torch
+        x, sq = self._sky(x)
+        S = x.shape[0]
+        energy = torch.empty((S,), dtype=torch.float64, device=self.device)
+        grad = torch.empty_like(x)
+        ms = (C.c_float * 7)()
+        self.raw.call("jubik_poisson_profile", C.c_void_p(x.data_ptr()), S, C.c_void_p(energy.data_ptr()),
+                      C.c_void_p(grad.data_ptr()), ms, self._stream())
+        return energy, grad, dict(zip(self.KERNEL_NAMES, [float(v) for v in ms]))
+
     @property
     def launch_count(self):
         return self.raw.launch_count
 
     def close(self):
         self.raw.close()
+
+
+def measure_fp64_tflops():
+    """DFMA micro-benchmark on the current device (second roofline denominator)."""
+    import torch
+    lib = _lib.load()
+    out = C.c_double()
+    check(lib, lib.jubik_measure_fp64_tflops(C.byref(out), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out.value

@@ -1,0 +1,210 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via jubik_b200.ResponsePlan) against
+(1) the golden vectors generated from the reference's own sources (tests/golden/make_golden.py) and
+(2) the NumPy oracle on the same seeded inputs.  Tolerance: 1e-10 relative (BASELINE.json north_star),
+measured as max|a-b| / max|b| per array and relative error on the scalar energy.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from tests import synth
+from oracle import jubik_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def rel(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def dev(torch, a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+GOLDEN = ["lp_N32_n4_m4_full", "lp_N32_n4_m6_compact", "lp_N30_n4_m3_trunc", "lp_N24_n3_m2_full"]
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_linpatch_forward_and_transpose(torch_cuda, golden_dir, name):
+    import jubik_b200 as jb
+    torch = torch_cuda
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    x, kern, n, m = z["x"], z["kernel"], int(z["n"]), int(z["m"])
+    N = x.shape[-1]
+    plan = jb.ResponsePlan(dev(torch, kern[None]), N, n, m)
+    y = plan.psf(dev(torch, x))[0].cpu().numpy()
+    assert rel(y, z["y"]) < TOL
+    yT = plan.psf_T(dev(torch, z["g"][None])).cpu().numpy()
+    assert rel(yT, z["yT"]) < TOL
+    # the reference-named entry point
+    dom = jb.Domain(tuple(x.shape), tuple(z["distances"]))
+    y2 = jb.linpatch_convolve(dev(torch, x), dom, dev(torch, kern), n, m).cpu().numpy()
+    assert rel(y2, z["y"]) < TOL
+    plan.close()
+
+
+# (N, n, m, T, E, S, full_support, eff_area)  -> FFT length exercised
+CASES = [
+    (256, 4, 16, 1, 1, 1, True, False),    # C1: P=160 exact period, full-support PSF wraps around
+    (240, 4, 10, 2, 2, 2, False, True),    # P=140 -> L=160 padded transform, compact PSF, S/T/E batching
+    (250, 4, 18, 1, 2, 1, True, False),    # N % n != 0 truncation, P=160
+    (408, 4, 64, 1, 1, 1, False, False),   # C3 patch geometry: P=332 -> L=336
+    (512, 4, 64, 1, 2, 1, True, False),    # C2 patch geometry: P=384 exact, full support
+    (768, 6, 64, 2, 1, 1, False, True),    # P=384, more patches, two modules
+    (1024, 4, 64, 1, 1, 1, False, False),  # C4 patch geometry: P=640
+    (816, 4, 128, 1, 1, 1, False, False),  # C5 patch geometry: P=664 -> L=672
+]
+
+
+def build_case(N, n, m, T, E, S, full, eff):
+    dx = N // n
+    dom = orc.Domain((E, N, N), synth.DIST)
+    if full:
+        kern, cropped = synth.psf_full(T, n, E, N), False
+    else:
+        kern, cropped = synth.psf_cropped(T, n, E, dx, half_support=m), True
+    expo = synth.exposure(T, E, N)
+    ea = synth.eff_area(T, E) if eff else None
+    x = synth.sky(S, E, N)
+    R = orc.Response(dom, kern, n, m, expo, 500.0, synth.PIXEL_AREA, eff_area=ea, cropped=cropped)
+    d = synth.counts_from(R.dense(synth.sky(1, E, N, seed=5)[0]))
+    return dom, kern, cropped, expo, ea, x, R, d
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "N%d_n%d_m%d_T%d_E%d_S%d_%s" % (c[:6] + ("full" if c[6] else "compact",)))
+def test_oracle_parity_all_entry_points(torch_cuda, case):
+    import jubik_b200 as jb
+    torch = torch_cuda
+    N, n, m, T, E, S, full, eff = case
+    dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
+    plan = jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
+                           eff_area=None if ea is None else dev(torch, ea), pixel_area=synth.PIXEL_AREA,
+                           data=dev(torch, d), max_samples=S, cropped=cropped)
+    xd = dev(torch, x)
+    g = synth.direction((S, T, E, N, N))
+    gd = dev(torch, g)
+    assert rel(plan.psf(xd).cpu().numpy(), np.stack([R.psf(x[s]) for s in range(S)])) < TOL
+    assert rel(plan.psf_T(gd).cpu().numpy(), np.stack([R.psf_T(g[s]) for s in range(S)])) < TOL
+    assert rel(plan.response(xd).cpu().numpy(), np.stack([R.dense(x[s]) for s in range(S)])) < TOL
+    assert rel(plan.response_T(gd).cpu().numpy(), np.stack([R.dense_T(g[s]) for s in range(S)])) < TOL
+    e, gr = plan.energy_and_grad(xd)
+    eo, go = zip(*[orc.energy_and_grad(R, d, x[s]) for s in range(S)])
+    assert np.abs((e.cpu().numpy() - np.array(eo)) / np.array(eo)).max() < TOL
+    assert rel(gr.cpu().numpy(), np.stack(go)) < TOL
+    v = synth.direction((S, E, N, N), seed=9)
+    mo = np.stack([orc.metric_apply(R, x[s], v[s]) for s in range(S)])
+    assert rel(plan.metric(xd, dev(torch, v)).cpu().numpy(), mo) < TOL
+    # host-buffer end-to-end entry point gives the same numbers
+    xh = torch.as_tensor(x).pin_memory()
+    eh = torch.empty((S,), dtype=torch.float64).pin_memory()
+    gh = torch.empty_like(xh).pin_memory()
+    plan.energy_and_grad_host(xh, eh, gh)
+    assert torch.equal(eh, e.cpu()) and torch.equal(gh, gr.cpu())
+    plan.close()
+
+
+def test_readout_and_likelihood_wrappers_match_reference_layout(torch_cuda):
+    """response_dict['R'] returns the reference's ragged {key: 1-D} tree (response.py:110) and the
+    likelihood accepts the compacted data tree (data.pkl layout)."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    N, n, m, T, E = 240, 4, 10, 2, 2
+    dom_o, kern, cropped, expo, ea, x, R, d = build_case(N, n, m, T, E, 1, False, True)
+    dom = jb.Domain(dom_o.shape, dom_o.distances)
+    rd = jb.build_response(dev(torch, kern), dev(torch, expo), dom, n, m, synth.PIXEL_AREA, exposure_cut=500.0,
+                           effective_area=dev(torch, ea), keys=["tm1", "tm2"], cropped=True)
+    out = rd["R"](dev(torch, x[0]))
+    ref = R(x[0])
+    for k_ref, k in zip(ref.tree, ["tm1", "tm2"]):
+        a, b = out[k].cpu().numpy(), ref.tree[k_ref]
+        assert a.shape == b.shape and rel(a, b) < TOL
+    # compacted data tree -> dense scatter -> same energy as the dense oracle
+    mask = R.mask
+    tree = {k: torch.as_tensor(d[i][~mask[i]]) for i, k in enumerate(["tm1", "tm2"])}
+    lh = jb.PoissonLikelihood(rd, tree)
+    e, gr = lh.value_and_grad(dev(torch, x[0]))
+    eo, go = orc.energy_and_grad(R, d, x[0])
+    assert abs(float(e) - eo) / abs(eo) < TOL and rel(gr.cpu().numpy(), go) < TOL
+
+
+def test_delta_kernel_is_window_weighted_identity(torch_cuda):
+    """Analogue of test/test_convolve.py:32-41 (delta kernel => identity) for linpatch_convolve: a delta PSF
+    gives x times the window coverage, which is exactly 1 away from the dx/2 border (Appendix A3)."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    N, n, m = 256, 4, 16
+    dx = N // n
+    kern = np.zeros((1, n * n, 1, N, N))
+    kern[..., 0, 0] = 3.0  # un-normalised delta
+    x = synth.sky(1, 1, N)[0]
+    y = jb.ResponsePlan(dev(torch, kern), N, n, m).psf(dev(torch, x))[0].cpu().numpy()
+    inner = slice(dx // 2 + 1, N - dx // 2 - 1)
+    assert np.abs(y[:, inner, inner] / x[:, inner, inner] - 1).max() < 1e-12
+
+
+def test_full_size_chandra_adjointness_linearity_and_fd(torch_cuda):
+    """BASELINE.json configs[1] at full size (1024^2, 3 bins, 8x8 patches, margin 64): size-independent
+    properties -- dot-product adjointness (test_slice_patches.py:55-66 style), linearity (:48-53), and a
+    finite-difference check of the fused energy gradient."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    N, n, m, T, E, S = 1024, 8, 64, 1, 3, 1
+    dx = N // n
+    kern = dev(torch, synth.psf_cropped(T, n, E, dx, half_support=m))
+    expo = dev(torch, synth.exposure(T, E, N))
+    plan = jb.ResponsePlan(kern, N, n, m, exposure=expo, exposure_cut=500.0, pixel_area=synth.PIXEL_AREA,
+                           cropped=True, max_samples=S)
+    x = dev(torch, synth.sky(S, E, N))
+    g = dev(torch, synth.direction((S, T, E, N, N)))
+    lhs = torch.vdot(g.flatten(), plan.response(x).flatten())
+    rhs = torch.vdot(plan.response_T(g).flatten(), x.flatten())
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-12
+    lhs = torch.vdot(g.flatten(), plan.psf(x).flatten())
+    rhs = torch.vdot(plan.psf_T(g).flatten(), x.flatten())
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-12
+    x2 = dev(torch, synth.sky(S, E, N, seed=11))
+    lin = plan.psf(2.0 * x + 3.0 * x2) - (2.0 * plan.psf(x) + 3.0 * plan.psf(x2))
+    assert float(lin.abs().max()) / float(plan.psf(x).abs().max()) < 1e-12
+    # Poisson data from the model itself, then FD of the energy along a random direction
+    lam = plan.response(dev(torch, synth.sky(1, E, N, seed=5)))
+    d = torch.poisson(lam.clamp(min=0.0))[0]
+    plan.set_data(d)
+    e0, gr = plan.energy_and_grad(x)
+    v = dev(torch, synth.direction((S, E, N, N), seed=9)) * x  # relative perturbation keeps x > 0
+    eps = 1e-4
+    ep = plan.energy(x + eps * v)
+    em = plan.energy(x - eps * v)
+    fd = float((ep - em).sum()) / (2 * eps)
+    an = float(torch.vdot(gr.flatten(), v.flatten()))
+    assert abs(fd - an) / abs(an) < 1e-6
+    # determinism: bitwise identical on repetition
+    e1, gr1 = plan.energy_and_grad(x)
+    assert torch.equal(e0, e1) and torch.equal(gr, gr1)
+    plan.close()
+
+
+def test_error_behaviour_matches_reference(torch_cuda):
+    import jubik_b200 as jb
+    torch = torch_cuda
+    x = torch.zeros((1, 32, 32), dtype=torch.float64, device="cuda")
+    k = torch.ones((16, 1, 32, 32), dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError):  # convolve.py:82-83
+        jb.linpatch_convolve(x, ((1, 32, 32), (1, 1, 1)), k, 4, 4)
+    with pytest.raises(jb.JubikError):  # n <= 2 breaks the reference's kernel crop (Appendix A4)
+        jb.ResponsePlan(torch.ones((1, 4, 1, 32, 32), dtype=torch.float64, device="cuda"), 32, 2, 4)
+    with pytest.raises(jb.JubikError):  # negative cut, response.py:37-39
+        jb.ResponsePlan(k[None], 32, 4, 4, exposure=torch.ones((1, 1, 32, 32), dtype=torch.float64, device="cuda"),
+                        exposure_cut=-1.0)
+    with pytest.raises(jb.JubikError):  # non-smooth P with a PSF wider than the margin
+        jb.ResponsePlan(torch.ones((1, 16, 1, 64, 64), dtype=torch.float64, device="cuda"), 64, 4, 5)
