@@ -1,0 +1,85 @@
+"""Multi-GPU sharding of the Poisson likelihood (one process per GPU, torch.distributed).
+
+The path shards without halo exchange: every (sample s, module t, energy e) response plane is
+independent in the forward direction.  Two partitions are provided:
+
+  * by SAMPLE  (VI sample axis; BASELINE config 5): rank r owns samples r::world.  Energies are per sample, the
+    sky gradient of a sample is complete on its owner.  Collectives: one all-reduce of the (S,) energy vector
+    (owners fill their entries, others contribute zeros) and -- only if the caller wants the sample-summed
+    gradient (KL gradient w.r.t. the mean) -- one all-reduce of (E,N,N).
+  * by MODULE  (telescope modules / observations; BASELINE config 3): rank r owns modules r::world of every
+    sample.  Each rank holds only its modules' PSF spectra, exposures and data; partial energies and partial
+    sky gradients are summed with one all-reduce each.
+
+The collective is NCCL over NVLink when the tensors are CUDA tensors and gloo in the CPU tests; the compute
+object is anything with energy_and_grad(x) -> (energy (S,), grad (S,E,N,N)) -- ResponsePlan in production.
+"""
+from __future__ import annotations
+
+
+def owned(n_items, rank, world):
+    """Indices owned by `rank` under a round-robin partition of n_items over world ranks."""
+    return list(range(rank, n_items, world))
+
+
+def split_counts(n_items, world):
+    return [len(range(r, n_items, world)) for r in range(world)]
+
+
+class SampleShardedLikelihood:
+    """Poisson likelihood over S samples, samples partitioned round-robin over ranks."""
+
+    def __init__(self, plan, n_samples, rank=None, world=None, group=None):
+        import torch.distributed as dist
+        self.plan = plan
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.S = n_samples
+        self.mine = owned(n_samples, self.rank, self.world)
+
+    def local(self, x_all):
+        """Select this rank's samples from a replicated (S,E,N,N) batch."""
+        return x_all[self.mine]
+
+    def energy_and_grad(self, x_local, reduce_grad=True):
+        """x_local: this rank's samples (len(mine),E,N,N).
+        Returns (energies of ALL samples (S,), sample-summed gradient (E,N,N) or the local gradients)."""
+        import torch
+        e_loc, g_loc = self.plan.energy_and_grad(x_local)
+        e_all = torch.zeros((self.S,), dtype=e_loc.dtype, device=e_loc.device)
+        if len(self.mine):
+            e_all[self.mine] = e_loc
+        self.dist.all_reduce(e_all, group=self.group)
+        if not reduce_grad:
+            return e_all, g_loc
+        g_sum = g_loc.sum(0) if len(self.mine) else torch.zeros(g_loc.shape[1:], dtype=g_loc.dtype, device=g_loc.device)
+        self.dist.all_reduce(g_sum, group=self.group)
+        return e_all, g_sum
+
+
+class ModuleShardedLikelihood:
+    """Poisson likelihood with the telescope-module axis T partitioned round-robin over ranks.
+    `plan` must have been built from this rank's modules only (kernel[mine], exposure[mine], data[mine])."""
+
+    def __init__(self, plan, n_modules, rank=None, world=None, group=None):
+        import torch.distributed as dist
+        self.plan = plan
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.mine = owned(n_modules, self.rank, self.world)
+
+    def energy_and_grad(self, x):
+        """x: replicated (S,E,N,N).  Returns the full energy (S,) and full gradient (S,E,N,N) on every rank."""
+        import torch
+        if len(self.mine):
+            e, g = self.plan.energy_and_grad(x)
+        else:
+            e = torch.zeros((x.shape[0],), dtype=x.dtype, device=x.device)
+            g = torch.zeros_like(x)
+        self.dist.all_reduce(e, group=self.group)
+        self.dist.all_reduce(g, group=self.group)
+        return e, g

@@ -17,7 +17,10 @@ from jubik_b200.build import fft_list, CSRC  # noqa: E402
 
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libjubik_emu.so")
-FLAGS = ["-std=c++20", "-O1", "-fPIC", "-DJB_EMU", "-x", "c++", "-pthread", "-w"]
+# -fno-gnu-unique / -Bsymbolic: keep this library's symbols from merging with libjubik_b200.so when a test
+# process loads both (they are built from the same sources)
+FLAGS = ["-std=c++20", "-O1", "-fPIC", "-DJB_EMU", "-x", "c++", "-pthread", "-w", "-fno-gnu-unique",
+         "-fvisibility-inlines-hidden"]
 
 
 def _run(cmd):
@@ -44,7 +47,7 @@ def build(force=False, lengths=None):
     with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         for f in [ex.submit(_run, c) for c, _ in tasks]:
             f.result()
-    _run(["g++", "-shared", "-o", LIB] + [o for _, o in tasks] + ["-pthread"])
+    _run(["g++", "-shared", "-Wl,-Bsymbolic", "-o", LIB] + [o for _, o in tasks] + ["-pthread"])
     return LIB
 
 

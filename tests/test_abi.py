@@ -1,0 +1,76 @@
+"""The C-ABI shared library: builds for sm_100a without a GPU, exports every symbol include/jubik_b200.h
+declares, and the product refuses to run without a device (no CPU fallback, no oracle import)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from jubik_b200 import build
+    return build.build(force=False)
+
+
+def declared_functions():
+    txt = open(os.path.join(ROOT, "include", "jubik_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(jubik_[A-Za-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    names = declared_functions()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(lib, name), name
+    from jubik_b200 import _lib
+    assert sorted(_lib.EXPORTS) == names
+
+
+def test_library_contains_sm100a_code(lib_path):
+    out = subprocess.run(["cuobjdump", "-lelf", lib_path], stdout=subprocess.PIPE, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_supported_lengths_and_versions(lib_path):
+    from jubik_b200 import _lib
+    lib = _lib.load(require_device=False)
+    assert lib.jubik_version() >= 100
+    for L in (160, 336, 384, 640, 672):     # P of BASELINE configs C1..C5 (332 -> 336, 664 -> 672)
+        assert lib.jubik_fft_length_supported(L) == 1
+    assert lib.jubik_fft_length_supported(332) == 0
+
+
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_product_fails_loudly_without_gpu(lib_path):
+    import jubik_b200 as jb
+    from jubik_b200 import _lib
+    from jubik_b200.plan import make_desc, RawPlan
+    with pytest.raises(jb.JubikError, match="no CUDA device"):
+        jb.load_library(require_device=True)
+    lib = _lib.load(require_device=False)
+    with pytest.raises(jb.JubikError, match="no CPU fallback"):
+        RawPlan(lib, make_desc(32, 1, 1, 4, 4, 1, False), 0)
+    import torch
+    with pytest.raises((TypeError, RuntimeError)):
+        jb.ResponsePlan(torch.ones((1, 16, 1, 32, 32), dtype=torch.float64), 32, 4, 4)
+
+
+def test_product_package_never_touches_oracle_or_emulation():
+    pkg = os.path.join(ROOT, "jubik_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "_build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+                assert "libjubik_emu" not in txt, f
+    code = "import sys; import jubik_b200; assert not any(m.startswith('oracle') for m in sys.modules)"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)

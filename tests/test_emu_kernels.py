@@ -1,0 +1,65 @@
+"""CPU check of the CUDA kernels' logic: the SAME sources (jubik_b200/csrc) compiled with -DJB_EMU for host
+threads (tests/emu/build_emu.py), driven through the same C ABI, against the golden vectors and the oracle.
+This is test infrastructure for a box without a GPU; the product never loads the emulation library.
+The GPU parity tests proper are tests/test_gpu_parity.py (-m gpu)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import jubik_oracle as orc
+from tests import synth
+from tests.emu.emu_plan import EmuPlan
+
+TOL = 1e-10
+GOLDEN = ["lp_N32_n4_m4_full", "lp_N32_n4_m6_compact", "lp_N30_n4_m3_trunc", "lp_N24_n3_m2_full"]
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(b).max())
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_emulated_kernels_match_reference_golden(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    n, m = int(z["n"]), int(z["m"])
+    p = EmuPlan(z["kernel"][None], z["x"].shape[-1], n, m)
+    assert p.info["exact_period"] == 1
+    assert rel(p.psf(z["x"])[0], z["y"]) < TOL
+    assert rel(p.psf_T(z["g"][None]), z["yT"]) < TOL
+
+
+@pytest.mark.parametrize("case", [
+    (120, 4, 10, 2, 2, 2, False, True),   # P=80 -> padded single... L=160 two-pass, compact PSF, S/T/E batching
+    (126, 4, 18, 1, 1, 1, True, False),   # N % n != 0, P = 98 -> needs compact? full support => must fail cleanly
+])
+def test_emulated_two_pass_fft_against_oracle(case):
+    N, n, m, T, E, S, full, eff = case
+    dx = N // n
+    dom = orc.Domain((E, N, N), synth.DIST)
+    if full:
+        kern, cropped = synth.psf_full(T, n, E, N), False
+    else:
+        kern, cropped = synth.psf_cropped(T, n, E, dx, half_support=m), True
+    expo = synth.exposure(T, E, N)
+    ea = synth.eff_area(T, E) if eff else None
+    if full:
+        from jubik_b200 import JubikError
+        with pytest.raises(JubikError, match="half-support"):
+            EmuPlan(kern, N, n, m, exposure=expo, exposure_cut=500.0, cropped=cropped)
+        return
+    x = synth.sky(S, E, N)
+    R = orc.Response(dom, kern, n, m, expo, 500.0, synth.PIXEL_AREA, eff_area=ea, cropped=cropped)
+    d = synth.counts_from(R.dense(synth.sky(1, E, N, seed=5)[0]))
+    p = EmuPlan(kern, N, n, m, exposure=expo, exposure_cut=500.0, eff_area=ea, pixel_area=synth.PIXEL_AREA,
+                data=d, max_samples=S, cropped=cropped, fft_length=160)
+    assert p.info["L"] == 160 and p.info["exact_period"] == 0
+    g = synth.direction((S, T, E, N, N))
+    assert rel(p.psf(x), np.stack([R.psf(x[s]) for s in range(S)])) < TOL
+    assert rel(p.response_T(g), np.stack([R.dense_T(g[s]) for s in range(S)])) < TOL
+    e, gr = p.energy_and_grad(x)
+    eo, go = zip(*[orc.energy_and_grad(R, d, x[s]) for s in range(S)])
+    assert np.abs((e - np.array(eo)) / np.array(eo)).max() < TOL
+    assert rel(gr, np.stack(go)) < TOL
+    v = synth.direction((S, E, N, N), seed=9)
+    assert rel(p.metric(x, v), np.stack([orc.metric_apply(R, x[s], v[s]) for s in range(S)])) < TOL
