@@ -7,7 +7,7 @@
 #include <vector>
 #include <new>
 
-#define JB_X_DECL(L, R1, R2, CB) JB_DECLARE_FFT(L)
+#define JB_X_DECL(L, R1, R2, CB, PIPE) JB_DECLARE_FFT(L)
 JB_FFT_LIST(JB_X_DECL)
 #undef JB_X_DECL
 
@@ -33,14 +33,46 @@ std::string cuda_msg(cudaError_t) { return "emu"; }
 int device_count() { return 1; }
 #endif
 
+// 2-D fp64 TMA view of a (rows x PH) complex row-major buffer; box = CB columns x BR rows.
+int make_tile_src(JbTileSrc* ts, const cd* base, size_t rows, int PH, int CB, int BR, std::string* err) {
+    memset(ts, 0, sizeof(*ts));
+    ts->base = base; ts->PH = PH; ts->BR = BR;
+#ifndef JB_EMU
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            *err = "cuTensorMapEncodeTiled is not available from the driver";
+            return 1;
+        }
+        encode = (encode_fn)fn;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)2 * PH, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)PH * sizeof(cd)};
+    cuuint32_t box[2] = {(cuuint32_t)(2 * CB), (cuuint32_t)BR};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&ts->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r); return 1; }
+#else
+    (void)rows; (void)CB; (void)err;
+#endif
+    return 0;
+}
+
 const JbFftOps* find_ops(int L) {
-#define JB_X_FIND(LL, R1, R2, CB) if (L == LL) return jb_fft_ops_##LL();
+#define JB_X_FIND(LL, R1, R2, CB, PIPE) if (L == LL) return jb_fft_ops_##LL();
     JB_FFT_LIST(JB_X_FIND)
 #undef JB_X_FIND
     return nullptr;
 }
 const int k_lengths[] = {
-#define JB_X_LEN(LL, R1, R2, CB) LL,
+#define JB_X_LEN(LL, R1, R2, CB, PIPE) LL,
     JB_FFT_LIST(JB_X_LEN)
 #undef JB_X_LEN
 };
@@ -71,6 +103,8 @@ struct jubik_plan {
     double* edev = nullptr;
     size_t bytes_khat = 0, bytes_ws = 0, bytes_total = 0;
     int nblk_out = 0;
+    int use_pipe = 0, n_sm = 1;
+    JbTileSrc src_fwd, src_adj;  // TMA views of bufB / bufA for the pipelined column pass
     // per-kernel timing (jubik_poisson_profile): events recorded after every launch while enabled
     int prof_on = 0, prof_n = 0;
 #ifndef JB_EMU
@@ -265,6 +299,24 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
         alloc(p, (void**)&p->partial, bP, "energy partials")) {
         std::string msg = g_err; cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_ALLOC, msg);
     }
+    // ---- pipelined column pass: TMA views of the two spectrum workspaces
+    p->use_pipe = o->pipe && !getenv("JUBIK_B200_COLS_V1");
+    if (p->use_pipe) {
+        std::string err;
+        int brB = g.w < 64 ? g.w : 64, brA = g.P < 64 ? g.P : 64;
+        if (make_tile_src(&p->src_fwd, p->bufB, STE * nn2 * (size_t)g.w, g.PH, o->CB, brB, &err) ||
+            make_tile_src(&p->src_adj, p->bufA, STE * nn2 * (size_t)g.P, g.PH, o->CB, brA, &err)) {
+            cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, err);
+        }
+#ifndef JB_EMU
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        p->n_sm = sms > 0 ? sms : 148;
+#else
+        p->n_sm = 2;
+#endif
+    }
     // ---- PSF spectra: rows r2c -> columns FFT -> normalise -> resident in k_cols' register order
     {
         int prpc = 8;
@@ -338,7 +390,11 @@ static int run_forward(jubik_plan* p, const double* x, int S, const JbEpi& ep, j
     const JbGeom& g = p->g;
     const JbFftOps* o = p->ops;
     JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.E, p->rpc_in, p->thr_rows, st));
-    JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, S * g.T * g.E, p->thr_cols, st));
+    if (p->use_pipe) {
+        JB_LAUNCHED(p, o->cols_pipe(g, false, p->src_fwd, p->bufA, p->khat, p->tw_nk, S * g.T * g.E, p->n_sm, st));
+    } else {
+        JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, S * g.T * g.E, p->thr_cols, st));
+    }
     JB_LAUNCHED(p, o->rows_out(g, p->bufA, p->tw_kn, ep, S * g.T * g.E, p->rpc_out, p->thr_rows, st));
     return 0;
 }
@@ -348,7 +404,11 @@ static int run_adjoint(jubik_plan* p, const double* gin, const double* expo, int
     const JbGeom& g = p->g;
     const JbFftOps* o = p->ops;
     JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.E, p->rpc_in, p->thr_rows, st));
-    JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, S * g.T * g.E, p->thr_cols, st));
+    if (p->use_pipe) {
+        JB_LAUNCHED(p, o->cols_pipe(g, true, p->src_adj, p->bufB, p->khat, p->tw_nk, S * g.T * g.E, p->n_sm, st));
+    } else {
+        JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, S * g.T * g.E, p->thr_cols, st));
+    }
     JB_LAUNCHED(p, o->rows_adj_out(g, p->bufB, p->wgt, p->tw_kn, out, S * g.E, p->rpc_out, p->thr_rows, st));
     return 0;
 }

@@ -1,13 +1,15 @@
-// fft_list.h -- transform lengths compiled into the library: X(L, R1, R2, CB)
-//   L = R1*R2 (R1 even; R2 == 1 => single in-register pass), CB = spectrum columns per column-pass CTA.
+// fft_list.h -- transform lengths compiled into the library: X(L, R1, R2, CB, PIPE)
+//   L = R1*R2 (R1 even; R2 == 1 => single in-register pass), CB = spectrum columns per column-pass work item,
+//   PIPE = 1: column pass runs as the persistent TMA pipeline (cols_pipe.cuh; needs 4*L*CB*16 B <= 227 KB and
+//   CB*16 B == 128 B rows), 0: the plain one-CTA-per-strip kernel.
 // The build (Makefile / __graft_entry__.build) compiles fft_inst.cu once per line.
 #pragma once
 #define JB_FFT_LIST(X) \
-    X(20, 20, 1, 8)    \
-    X(24, 24, 1, 8)    \
-    X(28, 28, 1, 8)    \
-    X(160, 16, 10, 16) \
-    X(336, 24, 14, 16) \
-    X(384, 24, 16, 16) \
-    X(640, 32, 20, 8)  \
-    X(672, 28, 24, 8)
+    X(20, 20, 1, 8, 0)    \
+    X(24, 24, 1, 8, 0)    \
+    X(28, 28, 1, 8, 0)    \
+    X(160, 16, 10, 8, 1)  \
+    X(336, 24, 14, 8, 1)  \
+    X(384, 24, 16, 8, 1)  \
+    X(640, 32, 20, 8, 0)  \
+    X(672, 28, 24, 8, 0)

@@ -21,7 +21,7 @@
 #define JB_D __device__ __forceinline__
 #define JB_GLOBAL __global__
 #define JB_GLOBAL_S static __global__
-#define JB_SMEM(T, name) extern __shared__ __align__(16) unsigned char jb_smem_raw_[]; \
+#define JB_SMEM(T, name) extern __shared__ __align__(128) unsigned char jb_smem_raw_[]; \
                          T* name = reinterpret_cast<T*>(jb_smem_raw_)
 typedef cudaStream_t jb_stream_t;
 typedef double2 cd;

@@ -3,16 +3,20 @@
 // table by length at plan creation.
 #pragma once
 #include "kernels.cuh"
+#include "cols_pipe.cuh"
 
 struct JbFftOps {
     int L, R1, R2, CB;
-    int ls;  // cd per real sequence in the exchange buffer
+    int ls;    // cd per real sequence in the exchange buffer
+    int pipe;  // 1: cols_pipe (persistent TMA pipeline) is available for this length
     cudaError_t (*rows_fwd)(const JbGeom&, const double* x, const double* wgt, const cd* tw_nk, cd* bufB,
                             int planes, int rpc, int threads, jb_stream_t);
     cudaError_t (*rows_adj_in)(const JbGeom&, const double* gin, const double* expo, const cd* tw_nk, cd* bufA,
                                int planes, int rpc, int threads, jb_stream_t);
     cudaError_t (*cols)(const JbGeom&, bool adj, const cd* in, cd* out, const cd* khat, const cd* tw_nk,
                         int planes, int threads, jb_stream_t);
+    cudaError_t (*cols_pipe)(const JbGeom&, bool adj, const JbTileSrc& src, cd* out, const cd* khat, const cd* tw_nk,
+                             int planes, int ctas, jb_stream_t);
     cudaError_t (*rows_out)(const JbGeom&, const cd* bufA, const cd* tw_kn, const JbEpi&, int planes, int rpc,
                             int threads, jb_stream_t);
     cudaError_t (*rows_adj_out)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw_kn, double* grad,
@@ -26,8 +30,21 @@ struct JbFftOps {
 inline int jb_cdiv(int a, int b) { return (a + b - 1) / b; }
 inline size_t jb_al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-template <class FP, int CB>
+template <class FP, int CB, int PIPE>
 struct JbOpsImpl {
+    static cudaError_t cols_pipe(const JbGeom& g, bool adj, const JbTileSrc& src, cd* out, const cd* khat,
+                                 const cd* tw_nk, int planes, int ctas, jb_stream_t st) {
+        if constexpr (PIPE && FP::R2 > 1) {
+            size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + 64;
+            if (adj) return jb_launch(k_cols_pipe<FP, CB, true>, dim3(ctas), dim3(JB_PIPE_THREADS), smem, st, src, g,
+                                      out, khat, tw_nk, planes);
+            return jb_launch(k_cols_pipe<FP, CB, false>, dim3(ctas), dim3(JB_PIPE_THREADS), smem, st, src, g, out,
+                             khat, tw_nk, planes);
+        } else {
+            (void)g; (void)adj; (void)src; (void)out; (void)khat; (void)tw_nk; (void)planes; (void)ctas; (void)st;
+            return (cudaError_t)1;
+        }
+    }
     static size_t smem_rows_in(const JbGeom& g, int rpc) {
         size_t B = (size_t)rpc * g.n;
         return jb_al16(B * FP::LS * sizeof(cd)) + sizeof(int) * (rpc + 2 * (size_t)rpc * g.n) + 16;
@@ -78,12 +95,13 @@ struct JbOpsImpl {
         return jb_launch(k_prep_cols<FP, CB>, grid, dim3(threads), smem, st, g, scratch, sums, tw_nk, khat);
     }
     static const JbFftOps* table() {
-        static const JbFftOps t = {FP::L, FP::R1, FP::R2, CB, FP::LS, rows_fwd, rows_adj_in, cols,
+        static const JbFftOps t = {FP::L, FP::R1, FP::R2, CB, FP::LS, (PIPE && FP::R2 > 1) ? 1 : 0,
+                                   rows_fwd, rows_adj_in, cols, cols_pipe,
                                    rows_out, rows_adj_out, prep_rows, prep_cols};
         return &t;
     }
 };
 
-#define JB_DEFINE_FFT(LEN, R1, R2, CB) \
-    const JbFftOps* jb_fft_ops_##LEN() { return JbOpsImpl<FftPlan<LEN, R1, R2>, CB>::table(); }
+#define JB_DEFINE_FFT(LEN, R1, R2, CB, PIPE) \
+    const JbFftOps* jb_fft_ops_##LEN() { return JbOpsImpl<FftPlan<LEN, R1, R2>, CB, PIPE>::table(); }
 #define JB_DECLARE_FFT(LEN) const JbFftOps* jb_fft_ops_##LEN();
