@@ -104,6 +104,7 @@ struct jubik_plan {
     size_t bytes_khat = 0, bytes_ws = 0, bytes_total = 0;
     int nblk_out = 0;
     int use_pipe = 0, n_sm = 1;
+    int fast_rows = 0;         // rows_fast.cuh kernels (two-pass length and <= JB_MAXQ row-patches per image row)
     JbTileSrc src_fwd, src_adj;  // TMA views of bufB / bufA for the pipelined column pass
     // per-kernel timing (jubik_poisson_profile): events recorded after every launch while enabled
     int prof_on = 0, prof_n = 0;
@@ -299,6 +300,21 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
         alloc(p, (void**)&p->partial, bP, "energy partials")) {
         std::string msg = g_err; cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_ALLOC, msg);
     }
+    // ---- low-overhead row kernels need at most JB_MAXQ row-patches covering any image row
+    {
+        int mx = 0;
+        for (int r = 0; r < N; ++r) {
+            int c0 = 0, c1 = 0;
+            for (int j = 0; j < n; ++j) {
+                int u0 = r + g.hp - g.offs[j], u1 = r + g.hp + m - g.offs[j];
+                if (u0 >= 0 && u0 < g.w) ++c0;
+                if (u1 >= 0 && u1 < g.P) ++c1;
+            }
+            mx = c0 > mx ? c0 : mx;
+            mx = c1 > mx ? c1 : mx;
+        }
+        p->fast_rows = (o->R2 > 1) && mx <= JB_MAXQ && !getenv("JUBIK_B200_ROWS_V1");
+    }
     // ---- pipelined column pass: TMA views of the two spectrum workspaces
     p->use_pipe = o->pipe && !getenv("JUBIK_B200_COLS_V1");
     if (p->use_pipe) {
@@ -389,13 +405,13 @@ static int check_call(jubik_plan* p, const void* a, const void* b, int S) {
 static int run_forward(jubik_plan* p, const double* x, int S, const JbEpi& ep, jb_stream_t st) {
     const JbGeom& g = p->g;
     const JbFftOps* o = p->ops;
-    JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.E, p->rpc_in, p->thr_rows, st));
+    JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.E, p->rpc_in, p->thr_rows, p->fast_rows, st));
     if (p->use_pipe) {
         JB_LAUNCHED(p, o->cols_pipe(g, false, p->src_fwd, p->bufA, p->khat, p->tw_nk, S * g.T * g.E, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, S * g.T * g.E, p->thr_cols, st));
     }
-    JB_LAUNCHED(p, o->rows_out(g, p->bufA, p->tw_kn, ep, S * g.T * g.E, p->rpc_out, p->thr_rows, st));
+    JB_LAUNCHED(p, o->rows_out(g, p->bufA, p->tw_kn, ep, S * g.T * g.E, p->rpc_out, p->thr_rows, p->fast_rows, st));
     return 0;
 }
 
@@ -403,13 +419,13 @@ static int run_forward(jubik_plan* p, const double* x, int S, const JbEpi& ep, j
 static int run_adjoint(jubik_plan* p, const double* gin, const double* expo, int S, double* out, jb_stream_t st) {
     const JbGeom& g = p->g;
     const JbFftOps* o = p->ops;
-    JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.E, p->rpc_in, p->thr_rows, st));
+    JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.E, p->rpc_in, p->thr_rows, p->fast_rows, st));
     if (p->use_pipe) {
         JB_LAUNCHED(p, o->cols_pipe(g, true, p->src_adj, p->bufB, p->khat, p->tw_nk, S * g.T * g.E, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, S * g.T * g.E, p->thr_cols, st));
     }
-    JB_LAUNCHED(p, o->rows_adj_out(g, p->bufB, p->wgt, p->tw_kn, out, S * g.E, p->rpc_out, p->thr_rows, st));
+    JB_LAUNCHED(p, o->rows_adj_out(g, p->bufB, p->wgt, p->tw_kn, out, S * g.E, p->rpc_out, p->thr_rows, p->fast_rows, st));
     return 0;
 }
 

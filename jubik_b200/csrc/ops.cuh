@@ -3,24 +3,26 @@
 // table by length at plan creation.
 #pragma once
 #include "kernels.cuh"
+#include "rows_fast.cuh"
 #include "cols_pipe.cuh"
 
 struct JbFftOps {
     int L, R1, R2, CB;
     int ls;    // cd per real sequence in the exchange buffer
     int pipe;  // 1: cols_pipe (persistent TMA pipeline) is available for this length
+    // fast != 0 selects the low-overhead kernels of rows_fast.cuh (two-pass lengths, <= JB_MAXQ row-patches per row)
     cudaError_t (*rows_fwd)(const JbGeom&, const double* x, const double* wgt, const cd* tw_nk, cd* bufB,
-                            int planes, int rpc, int threads, jb_stream_t);
+                            int planes, int rpc, int threads, int fast, jb_stream_t);
     cudaError_t (*rows_adj_in)(const JbGeom&, const double* gin, const double* expo, const cd* tw_nk, cd* bufA,
-                               int planes, int rpc, int threads, jb_stream_t);
+                               int planes, int rpc, int threads, int fast, jb_stream_t);
     cudaError_t (*cols)(const JbGeom&, bool adj, const cd* in, cd* out, const cd* khat, const cd* tw_nk,
                         int planes, int threads, jb_stream_t);
     cudaError_t (*cols_pipe)(const JbGeom&, bool adj, const JbTileSrc& src, cd* out, const cd* khat, const cd* tw_nk,
                              int planes, int ctas, jb_stream_t);
     cudaError_t (*rows_out)(const JbGeom&, const cd* bufA, const cd* tw_kn, const JbEpi&, int planes, int rpc,
-                            int threads, jb_stream_t);
+                            int threads, int fast, jb_stream_t);
     cudaError_t (*rows_adj_out)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw_kn, double* grad,
-                                int planes, int rpc, int threads, jb_stream_t);
+                                int planes, int rpc, int threads, int fast, jb_stream_t);
     cudaError_t (*prep_rows)(const JbGeom&, const JbKsrc&, const cd* tw_nk, cd* scratch, int rpc, int threads,
                              jb_stream_t);
     cudaError_t (*prep_cols)(const JbGeom&, const cd* scratch, const double* sums, const cd* tw_nk, cd* khat,
@@ -45,19 +47,32 @@ struct JbOpsImpl {
             return (cudaError_t)1;
         }
     }
-    static size_t smem_rows_in(const JbGeom& g, int rpc) {
+    static size_t rowtab_bytes(int rpc) {
+        return jb_al16(sizeof(int) * rpc) + (sizeof(long long) + sizeof(double)) * (size_t)rpc * JB_MAXQ + 16;
+    }
+    static size_t smem_rows_in(const JbGeom& g, int rpc, int fast) {
         size_t B = (size_t)rpc * g.n;
+        if (fast) return jb_al16(B * FP::LS * sizeof(cd)) + rowtab_bytes(rpc);
         return jb_al16(B * FP::LS * sizeof(cd)) + sizeof(int) * (rpc + 2 * (size_t)rpc * g.n) + 16;
     }
     static cudaError_t rows_fwd(const JbGeom& g, const double* x, const double* wgt, const cd* tw_nk, cd* bufB,
-                                int planes, int rpc, int threads, jb_stream_t st) {
-        return jb_launch(k_rows_fwd<FP>, dim3(jb_cdiv(g.N, rpc), planes), dim3(threads), smem_rows_in(g, rpc), st,
-                         g, x, wgt, tw_nk, bufB, rpc);
+                                int planes, int rpc, int threads, int fast, jb_stream_t st) {
+        dim3 grid(jb_cdiv(g.N, rpc), planes);
+        if constexpr (FP::R2 > 1) {
+            if (fast) return jb_launch(k_rows_fwd2<FP>, grid, dim3(threads), smem_rows_in(g, rpc, 1), st, g, x, wgt,
+                                       tw_nk, bufB, rpc);
+        }
+        return jb_launch(k_rows_fwd<FP>, grid, dim3(threads), smem_rows_in(g, rpc, 0), st, g, x, wgt, tw_nk, bufB, rpc);
     }
     static cudaError_t rows_adj_in(const JbGeom& g, const double* gin, const double* expo, const cd* tw_nk,
-                                   cd* bufA, int planes, int rpc, int threads, jb_stream_t st) {
-        return jb_launch(k_rows_adj_in<FP>, dim3(jb_cdiv(g.N, rpc), planes), dim3(threads), smem_rows_in(g, rpc),
-                         st, g, gin, expo, tw_nk, bufA, rpc);
+                                   cd* bufA, int planes, int rpc, int threads, int fast, jb_stream_t st) {
+        dim3 grid(jb_cdiv(g.N, rpc), planes);
+        if constexpr (FP::R2 > 1) {
+            if (fast) return jb_launch(k_rows_adj_in2<FP>, grid, dim3(threads), smem_rows_in(g, rpc, 1), st, g, gin,
+                                       expo, tw_nk, bufA, rpc);
+        }
+        return jb_launch(k_rows_adj_in<FP>, grid, dim3(threads), smem_rows_in(g, rpc, 0), st, g, gin, expo, tw_nk,
+                         bufA, rpc);
     }
     static cudaError_t cols(const JbGeom& g, bool adj, const cd* in, cd* out, const cd* khat, const cd* tw_nk,
                             int planes, int threads, jb_stream_t st) {
@@ -67,20 +82,29 @@ struct JbOpsImpl {
         return jb_launch(k_cols<FP, CB, false>, grid, dim3(threads), smem, st, g, in, out, khat, tw_nk);
     }
     static cudaError_t rows_out(const JbGeom& g, const cd* bufA, const cd* tw_kn, const JbEpi& ep, int planes,
-                                int rpc, int threads, jb_stream_t st) {
+                                int rpc, int threads, int fast, jb_stream_t st) {
         size_t B = (size_t)rpc * g.n;
-        size_t smem = jb_al16(B * FP::LS * sizeof(cd)) + jb_al16(B * g.P * sizeof(double)) +
-                      jb_al16((size_t)threads * sizeof(double)) + sizeof(int) * (rpc + 2 * (size_t)rpc * g.n) + 16;
-        return jb_launch(k_rows_out<FP>, dim3(jb_cdiv(g.N, rpc), planes), dim3(threads), smem, st, g, bufA, tw_kn,
-                         ep, rpc);
+        dim3 grid(jb_cdiv(g.N, rpc), planes);
+        size_t common = jb_al16(B * FP::LS * sizeof(cd)) + jb_al16(B * g.P * sizeof(double)) +
+                        jb_al16((size_t)threads * sizeof(double));
+        if constexpr (FP::R2 > 1) {
+            if (fast) return jb_launch(k_rows_out2<FP>, grid, dim3(threads), common + rowtab_bytes(rpc), st, g, bufA,
+                                       tw_kn, ep, rpc);
+        }
+        size_t smem = common + sizeof(int) * (rpc + 2 * (size_t)rpc * g.n) + 16;
+        return jb_launch(k_rows_out<FP>, grid, dim3(threads), smem, st, g, bufA, tw_kn, ep, rpc);
     }
     static cudaError_t rows_adj_out(const JbGeom& g, const cd* bufB, const double* wgt, const cd* tw_kn,
-                                    double* grad, int planes, int rpc, int threads, jb_stream_t st) {
+                                    double* grad, int planes, int rpc, int threads, int fast, jb_stream_t st) {
         size_t B = (size_t)rpc * g.n;
-        size_t smem = jb_al16(B * FP::LS * sizeof(cd)) + jb_al16(B * g.w * sizeof(double)) +
-                      sizeof(int) * (rpc + 2 * (size_t)rpc * g.n) + 16;
-        return jb_launch(k_rows_adj_out<FP>, dim3(jb_cdiv(g.N, rpc), planes), dim3(threads), smem, st, g, bufB,
-                         wgt, tw_kn, grad, rpc);
+        dim3 grid(jb_cdiv(g.N, rpc), planes);
+        size_t common = jb_al16(B * FP::LS * sizeof(cd)) + jb_al16(B * g.w * sizeof(double));
+        if constexpr (FP::R2 > 1) {
+            if (fast) return jb_launch(k_rows_adj_out2<FP>, grid, dim3(threads), common + rowtab_bytes(rpc), st, g,
+                                       bufB, wgt, tw_kn, grad, rpc);
+        }
+        size_t smem = common + sizeof(int) * (rpc + 2 * (size_t)rpc * g.n) + 16;
+        return jb_launch(k_rows_adj_out<FP>, grid, dim3(threads), smem, st, g, bufB, wgt, tw_kn, grad, rpc);
     }
     static cudaError_t prep_rows(const JbGeom& g, const JbKsrc& ks, const cd* tw_nk, cd* scratch, int rpc,
                                  int threads, jb_stream_t st) {

@@ -1,0 +1,407 @@
+// rows_fast.cuh -- the four row kernels for two-pass transform lengths, written for low instruction
+// overhead: every per-item address is hoisted into a few base pointers, every per-element access is
+// `pointer + compile-time offset`, the direct/mirrored half-spectrum choice is resolved at compile time
+// (one run-time case per item), inter-pass twiddles come from two per-item seeds by recurrence, and the
+// row-patch lists are unrolled to JB_MAXQ entries.  Same maths and data layout as kernels.cuh (which
+// keeps the generic single-pass versions used by the tiny test lengths).
+#pragma once
+#include "kernels.cuh"
+
+#define JB_MAXQ 4  // row-patches j that can cover one image row: ceil(P/dx) (+1 with clamped offsets)
+
+// Hermitian half-spectrum element k = k1 + R1*K2 of a length-L real transform lives at index k when
+// 2k <= L, else at L-k conjugated.  For K2 fixed at compile time only 2*K2 == R2 depends on k1.
+template <class FP, int K2>
+JB_D bool jb_spec_direct(int k1) {
+    if constexpr (2 * K2 < FP::R2) return true;
+    else if constexpr (2 * K2 == FP::R2) return k1 == 0;
+    else return false;
+}
+
+// ---- shared pass bodies -------------------------------------------------------------------
+// r2c pass 1 tail: real radix-R1 butterfly, twiddle W_L^{n2 k1} (seeds W^{n2}, W^{2 n2}), store to the exchange buffer
+template <class FP>
+JB_D void jb_r2c_pass1(const double (&x)[FP::R1], cd* dst /* sm + b*LS + n2 */, cd w1, cd w2) {
+    constexpr int H1 = FP::H1, R2P = FP::R2P;
+    cd Y[H1];
+    rdft_fwd<FP::R1>(x, Y);
+    cd po = w1, pe = w2;
+    static_for<0, H1>([&](auto kk) {
+        constexpr int k1 = kk;
+        cd y = Y[k1];
+        if constexpr (k1 > 0) {
+            if constexpr (k1 & 1) { y = cd_mul(y, po); if constexpr (k1 + 2 < H1) po = cd_mul(po, w2); }
+            else { y = cd_mul(y, pe); if constexpr (k1 + 2 < H1) pe = cd_mul(pe, w2); }
+        }
+        dst[k1 * R2P] = y;
+    });
+}
+// r2c pass 2 head: load the k1-th row of the exchange buffer and transform over n2
+template <class FP>
+JB_D void jb_r2c_pass2(const cd* src /* sm + b*LS + k1*R2P */, cd (&u)[FP::R2]) {
+    static_for<0, FP::R2>([&](auto nn) { constexpr int n2 = nn; u[n2] = src[n2]; });
+    dft<FP::R2, -1>(u);
+}
+// c2r pass A tail: inverse radix-R2 over k2, twiddle W_L^{-n2 k1} (seeds W^{-k1}, W^{-2 k1}), store
+template <class FP>
+JB_D void jb_c2r_passA(cd (&u)[FP::R2], cd* dst /* sm + b*LS + k1*R2P */, cd w1, cd w2) {
+    dft<FP::R2, +1>(u);
+    cd po = w1, pe = w2;
+    static_for<0, FP::R2>([&](auto nn) {
+        constexpr int n2 = nn;
+        cd y = u[n2];
+        if constexpr (n2 > 0) {
+            if constexpr (n2 & 1) { y = cd_mul(y, po); if constexpr (n2 + 2 < FP::R2) po = cd_mul(po, w2); }
+            else { y = cd_mul(y, pe); if constexpr (n2 + 2 < FP::R2) pe = cd_mul(pe, w2); }
+        }
+        dst[n2] = y;
+    });
+}
+// c2r pass B head: gather the Hermitian k1 column and run the real inverse butterfly
+template <class FP>
+JB_D void jb_c2r_passB(const cd* src /* sm + b*LS + n2 */, double (&x)[FP::R1]) {
+    cd U[FP::H1];
+    static_for<0, FP::H1>([&](auto kk) { constexpr int k1 = kk; U[k1] = src[k1 * FP::R2P]; });
+    rdft_inv<FP::R1>(U, x);
+}
+
+// Row-patch table of the CTA's image rows in shared memory: for row rr, entry q: element offset of
+// (patch row-block j, row u) inside one plane of the spectrum buffer *excluding* the i*n*rows*PH term,
+// plus the window row weight.  cnt is clamped to JB_MAXQ (plan creation checks the geometry).
+struct JbRowTab {
+    int* cnt;        // [rpc]
+    long long* off;  // [rpc*JB_MAXQ]
+    double* wr;      // [rpc*JB_MAXQ]
+};
+JB_D size_t jb_rowtab_bytes(int rpc) {
+    return jb_align16(sizeof(int) * rpc) + sizeof(long long) * rpc * JB_MAXQ + sizeof(double) * rpc * JB_MAXQ;
+}
+JB_D JbRowTab jb_rowtab_at(unsigned char* p, int rpc) {
+    JbRowTab t;
+    t.cnt = reinterpret_cast<int*>(p);
+    t.off = reinterpret_cast<long long*>(p + jb_align16(sizeof(int) * rpc));
+    t.wr = reinterpret_cast<double*>(t.off + rpc * JB_MAXQ);
+    return t;
+}
+JB_D void jb_rowtab_build(const JbGeom& g, const JbRowTab& t, int r0, int rpc, int shift, int rows, const double* wgt) {
+    for (int rr = jb_tid(); rr < rpc; rr += jb_nthr()) {
+        int r = r0 + rr, c = 0;
+        if (r < g.N) {
+            for (int j = 0; j < g.n && c < JB_MAXQ; ++j) {
+                int u = r + shift - g.offs[j];
+                if (u >= 0 && u < rows) {
+                    t.off[rr * JB_MAXQ + c] = ((long long)j * rows + u) * g.PH;
+                    t.wr[rr * JB_MAXQ + c] = wgt ? wgt[u] : 1.0;
+                    ++c;
+                }
+            }
+        }
+        t.cnt[rr] = c;
+        for (int q = c; q < JB_MAXQ; ++q) { t.off[rr * JB_MAXQ + q] = 0; t.wr[rr * JB_MAXQ + q] = 0.0; }
+    }
+}
+
+// ------------------------------------------------------------ forward: sky rows -> spectra (r2c)
+// grid (ceil(N/rpc), S*E); dyn smem = B*LS*16 + rowtab.
+template <class FP>
+JB_GLOBAL void k_rows_fwd2(JbGeom g, const double* __restrict__ x, const double* __restrict__ wgt,
+                           const cd* __restrict__ tw_nk, cd* __restrict__ bufB, int rpc) {
+    constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
+    JB_SMEM(unsigned char, smraw);
+    const int n = g.n, N = g.N, m = g.m, w = g.w, hp = g.hp, PH = g.PH;
+    const int B = rpc * n;
+    cd* sm = reinterpret_cast<cd*>(smraw);
+    JbRowTab tab = jb_rowtab_at(smraw + jb_align16((size_t)B * LS * sizeof(cd)), rpc);
+    const int r0 = blockIdx.x * rpc, se = blockIdx.y;
+    jb_rowtab_build(g, tab, r0, rpc, hp, w, wgt);
+    const double* xp = x + (size_t)se * N * N;
+    for (int it = jb_tid(); it < B * R2; it += jb_nthr()) {
+        int b = it / R2, n2 = it - b * R2;
+        int rr = b / n, i = b - rr * n, r = r0 + rr;
+        // element p = R2*n1 + n2 of the zero-padded window row: q = p - m in [0,w), column c = offs[i]-hp+q in [0,N)
+        int q0 = n2 - m, c0 = g.offs[i] - hp + q0;
+        const double* px = xp + (size_t)(r < N ? r : 0) * N + c0;
+        const double* pw = wgt + q0;
+        double xv[R1];
+        static_for<0, R1>([&](auto nn) {
+            constexpr int n1 = nn;
+            int q = q0 + R2 * n1, c = c0 + R2 * n1;
+            bool ok = (r < N) && q >= 0 && q < w && c >= 0 && c < N;
+            xv[n1] = ok ? jb_ldg(px + R2 * n1) * jb_ldg(pw + R2 * n1) : 0.0;
+        });
+        jb_r2c_pass1<FP>(xv, sm + (size_t)b * LS + n2, jb_ldg(tw_nk + R2 + n2), jb_ldg(tw_nk + 2 * R2 + n2));
+    }
+    JB_SYNC();
+    const size_t plane = (size_t)se * n * n * w * PH;
+    for (int it = jb_tid(); it < B * H1; it += jb_nthr()) {
+        int b = it / H1, k1 = it - b * H1;
+        int rr = b / n, i = b - rr * n;
+        cd u[R2];
+        jb_r2c_pass2<FP>(sm + (size_t)b * LS + k1 * R2P, u);
+        const bool mirror_ok = (k1 != 0) && (2 * k1 != R1);
+        const int cnt = tab.cnt[rr];
+        cd* base = bufB + plane + (size_t)i * n * w * PH;
+        static_for<0, JB_MAXQ>([&](auto qq) {
+            constexpr int q = qq;
+            if (q < cnt) {
+                cd* pd = base + tab.off[rr * JB_MAXQ + q] + k1;       // direct:  + R1*k2
+                cd* pm = base + tab.off[rr * JB_MAXQ + q] + (L - k1); // mirror:  - R1*k2
+                const double wr = tab.wr[rr * JB_MAXQ + q];
+                static_for<0, R2>([&](auto kk) {
+                    constexpr int k2 = kk;
+                    cd v = cd_scale(u[k2], wr);
+                    if (jb_spec_direct<FP, k2>(k1)) pd[R1 * k2] = v;
+                    else if (mirror_ok) pm[-R1 * k2] = cd_conj(v);
+                });
+            }
+        });
+    }
+}
+
+// ------------------------------------------------------ adjoint: cotangent rows -> spectra (r2c)
+// grid (ceil(N/rpc), S*T*E)
+template <class FP>
+JB_GLOBAL void k_rows_adj_in2(JbGeom g, const double* __restrict__ gin, const double* __restrict__ expo,
+                              const cd* __restrict__ tw_nk, cd* __restrict__ bufA, int rpc) {
+    constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
+    JB_SMEM(unsigned char, smraw);
+    const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, P = g.P;
+    const int B = rpc * n;
+    cd* sm = reinterpret_cast<cd*>(smraw);
+    JbRowTab tab = jb_rowtab_at(smraw + jb_align16((size_t)B * LS * sizeof(cd)), rpc);
+    const int r0 = blockIdx.x * rpc, ste = blockIdx.y;
+    jb_rowtab_build(g, tab, r0, rpc, hp + m, P, nullptr);
+    const double* gp = gin + (size_t)ste * N * N;
+    const double* ep = expo ? expo + (size_t)(ste % (g.T * g.E)) * N * N : nullptr;
+    for (int it = jb_tid(); it < B * R2; it += jb_nthr()) {
+        int b = it / R2, n2 = it - b * R2;
+        int rr = b / n, i = b - rr * n, r = r0 + rr;
+        int c0 = g.offs[i] - hp - m + n2;
+        size_t rowoff = (size_t)(r < N ? r : 0) * N;
+        const double* pg = gp + rowoff + c0;
+        const double* pe = ep ? ep + rowoff + c0 : nullptr;
+        double xv[R1];
+        static_for<0, R1>([&](auto nn) {
+            constexpr int n1 = nn;
+            int p = n2 + R2 * n1, c = c0 + R2 * n1;
+            bool ok = (r < N) && p < P && c >= 0 && c < N;
+            double v = ok ? jb_ldg(pg + R2 * n1) : 0.0;
+            if (pe && ok) v *= jb_ldg(pe + R2 * n1);
+            xv[n1] = v;
+        });
+        jb_r2c_pass1<FP>(xv, sm + (size_t)b * LS + n2, jb_ldg(tw_nk + R2 + n2), jb_ldg(tw_nk + 2 * R2 + n2));
+    }
+    JB_SYNC();
+    const size_t plane = (size_t)ste * n * n * P * PH;
+    for (int it = jb_tid(); it < B * H1; it += jb_nthr()) {
+        int b = it / H1, k1 = it - b * H1;
+        int rr = b / n, i = b - rr * n;
+        cd u[R2];
+        jb_r2c_pass2<FP>(sm + (size_t)b * LS + k1 * R2P, u);
+        const bool mirror_ok = (k1 != 0) && (2 * k1 != R1);
+        const int cnt = tab.cnt[rr];
+        cd* base = bufA + plane + (size_t)i * n * P * PH;
+        static_for<0, JB_MAXQ>([&](auto qq) {
+            constexpr int q = qq;
+            if (q < cnt) {
+                cd* pd = base + tab.off[rr * JB_MAXQ + q] + k1;
+                cd* pm = base + tab.off[rr * JB_MAXQ + q] + (L - k1);
+                static_for<0, R2>([&](auto kk) {
+                    constexpr int k2 = kk;
+                    if (jb_spec_direct<FP, k2>(k1)) pd[R1 * k2] = u[k2];
+                    else if (mirror_ok) pm[-R1 * k2] = cd_conj(u[k2]);
+                });
+            }
+        });
+    }
+}
+
+// load the half-spectrum element (k1, K2) as the weighted sum over the row-patch table entries
+template <class FP, int K2, bool WEIGHTED>
+JB_D cd jb_sum_spec(const cd* const (&pd)[JB_MAXQ], const cd* const (&pm)[JB_MAXQ], const double (&wr)[JB_MAXQ],
+                    int cnt, int k1) {
+    cd acc = cd_make(0.0, 0.0);
+    const bool direct = jb_spec_direct<FP, K2>(k1);
+    static_for<0, JB_MAXQ>([&](auto qq) {
+        constexpr int q = qq;
+        if (q < cnt) {
+            cd v = direct ? pd[q][FP::R1 * K2] : pm[q][-FP::R1 * K2];
+            if (WEIGHTED) { acc.x += wr[q] * v.x; acc.y += wr[q] * v.y; }
+            else { acc.x += v.x; acc.y += v.y; }
+        }
+    });
+    if (!direct) acc.y = -acc.y;
+    return acc;
+}
+
+// --------------------------------------------- forward: spectra -> image rows (+ epilogue) (c2r)
+// grid (ceil(N/rpc), S*T*E)
+template <class FP>
+JB_GLOBAL void k_rows_out2(JbGeom g, const cd* __restrict__ bufA, const cd* __restrict__ tw_kn, JbEpi ep, int rpc) {
+    constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
+    JB_SMEM(unsigned char, smraw);
+    const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, P = g.P;
+    const int B = rpc * n;
+    size_t off = 0;
+    cd* sm = reinterpret_cast<cd*>(smraw);
+    off += jb_align16((size_t)B * LS * sizeof(cd));
+    double* tile = reinterpret_cast<double*>(smraw + off);
+    off += jb_align16((size_t)B * P * sizeof(double));
+    double* red = reinterpret_cast<double*>(smraw + off);
+    off += jb_align16((size_t)jb_nthr() * sizeof(double));
+    JbRowTab tab = jb_rowtab_at(smraw + off, rpc);
+    const int r0 = blockIdx.x * rpc, ste = blockIdx.y;
+    jb_rowtab_build(g, tab, r0, rpc, hp + m, P, nullptr);
+    JB_SYNC();
+    const cd* ab = bufA + (size_t)ste * n * n * P * PH;
+    for (int it = jb_tid(); it < B * H1; it += jb_nthr()) {
+        int b = it / H1, k1 = it - b * H1;
+        int rr = b / n, i = b - rr * n;
+        const int cnt = tab.cnt[rr];
+        const cd* base = ab + (size_t)i * n * P * PH;
+        const cd* pd[JB_MAXQ];
+        const cd* pm[JB_MAXQ];
+        double wr[JB_MAXQ];
+        static_for<0, JB_MAXQ>([&](auto qq) {
+            constexpr int q = qq;
+            pd[q] = base + tab.off[rr * JB_MAXQ + q] + k1;
+            pm[q] = base + tab.off[rr * JB_MAXQ + q] + (L - k1);
+            wr[q] = 1.0;
+        });
+        cd w1 = cd_conj(jb_ldg(tw_kn + R1 + k1)), w2 = cd_conj(jb_ldg(tw_kn + 2 * R1 + k1));
+        cd u[R2];
+        static_for<0, R2>([&](auto kk) { constexpr int k2 = kk; u[k2] = jb_sum_spec<FP, k2, false>(pd, pm, wr, cnt, k1); });
+        jb_c2r_passA<FP>(u, sm + (size_t)b * LS + k1 * R2P, w1, w2);
+    }
+    JB_SYNC();
+    for (int it = jb_tid(); it < B * R2; it += jb_nthr()) {
+        int b = it / R2, n2 = it - b * R2;
+        double xv[R1];
+        jb_c2r_passB<FP>(sm + (size_t)b * LS + n2, xv);
+        double* tp = tile + (size_t)b * P + n2;
+        static_for<0, R1>([&](auto nn) {
+            constexpr int n1 = nn;
+            if (R2 * n1 + n2 < P) tp[R2 * n1] = xv[n1];
+        });
+    }
+    JB_SYNC();
+    // overlap-add over column blocks i as a gather, then the epilogue
+    const int te = ste % (g.T * g.E);
+    const int shift = hp + m;
+    double esum = 0.0;
+    for (int idx = jb_tid(); idx < rpc * N; idx += jb_nthr()) {
+        int rr = idx / N, c = idx - rr * N, r = r0 + rr;
+        if (r >= N) continue;
+        double conv = 0.0;
+        const double* trow = tile + (size_t)rr * n * P + c + shift;
+        for (int i = 0; i < n; ++i) {
+            int p = c + shift - g.offs[i];
+            if (p >= 0 && p < P) conv += trow[(size_t)i * P - g.offs[i]];
+        }
+        size_t o = ((size_t)ste * N + r) * N + c;
+        size_t oe = ((size_t)te * N + r) * N + c;
+        if (ep.mode == JB_EPI_PSF) {
+            ep.out[o] = conv;
+        } else {
+            double ex = jb_ldg(ep.expo + oe);
+            if (ep.mode == JB_EPI_RESP) {
+                ep.out[o] = (ex != 0.0) ? ex * conv : 0.0;
+            } else if (ep.mode == JB_EPI_POISSON) {
+                double gout = 0.0;
+                if (ex != 0.0) {
+                    double lam = ex * conv, d = jb_ldg(ep.data + oe);
+                    esum += lam - d * log(lam);
+                    gout = ex * (1.0 - d / lam);
+                }
+                ep.out[o] = gout;
+            } else {
+                double gout = 0.0;
+                if (ex != 0.0) gout = ex * (ex * conv) / ep.lam[o];
+                ep.out[o] = gout;
+            }
+        }
+    }
+    if (ep.mode == JB_EPI_POISSON) {
+        double tot = jb_block_sum(esum, red);
+        if (jb_tid() == 0) ep.partial[(size_t)ste * gridDim.x + blockIdx.x] = tot;
+    }
+}
+
+// ------------------------------------ adjoint: spectra -> sky-gradient rows, summed over modules (c2r)
+// grid (ceil(N/rpc), S*E)
+template <class FP>
+JB_GLOBAL void k_rows_adj_out2(JbGeom g, const cd* __restrict__ bufB, const double* __restrict__ wgt,
+                               const cd* __restrict__ tw_kn, double* __restrict__ grad, int rpc) {
+    constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
+    JB_SMEM(unsigned char, smraw);
+    const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, w = g.w;
+    const int B = rpc * n;
+    size_t off = 0;
+    cd* sm = reinterpret_cast<cd*>(smraw);
+    off += jb_align16((size_t)B * LS * sizeof(cd));
+    double* tile = reinterpret_cast<double*>(smraw + off);
+    off += jb_align16((size_t)B * w * sizeof(double));
+    JbRowTab tab = jb_rowtab_at(smraw + off, rpc);
+    const int r0 = blockIdx.x * rpc, se = blockIdx.y;
+    const int s = se / g.E, e = se - s * g.E;
+    jb_rowtab_build(g, tab, r0, rpc, hp, w, wgt);
+    JB_SYNC();
+    const size_t plane_sz = (size_t)n * n * w * PH;
+    for (int it = jb_tid(); it < B * H1; it += jb_nthr()) {
+        int b = it / H1, k1 = it - b * H1;
+        int rr = b / n, i = b - rr * n;
+        const int cnt = tab.cnt[rr];
+        double wr[JB_MAXQ];
+        long long o[JB_MAXQ];
+        static_for<0, JB_MAXQ>([&](auto qq) {
+            constexpr int q = qq;
+            wr[q] = tab.wr[rr * JB_MAXQ + q];
+            o[q] = tab.off[rr * JB_MAXQ + q];
+        });
+        cd u[R2];
+        static_for<0, R2>([&](auto kk) { constexpr int k2 = kk; u[k2] = cd_make(0.0, 0.0); });
+        for (int t = 0; t < g.T; ++t) {
+            const cd* base = bufB + ((size_t)(s * g.T + t) * g.E + e) * plane_sz + (size_t)i * n * w * PH;
+            const cd* pd[JB_MAXQ];
+            const cd* pm[JB_MAXQ];
+            static_for<0, JB_MAXQ>([&](auto qq) {
+                constexpr int q = qq;
+                pd[q] = base + o[q] + k1;
+                pm[q] = base + o[q] + (L - k1);
+            });
+            static_for<0, R2>([&](auto kk) {
+                constexpr int k2 = kk;
+                cd v = jb_sum_spec<FP, k2, true>(pd, pm, wr, cnt, k1);
+                u[k2].x += v.x;
+                u[k2].y += v.y;
+            });
+        }
+        cd w1 = cd_conj(jb_ldg(tw_kn + R1 + k1)), w2 = cd_conj(jb_ldg(tw_kn + 2 * R1 + k1));
+        jb_c2r_passA<FP>(u, sm + (size_t)b * LS + k1 * R2P, w1, w2);
+    }
+    JB_SYNC();
+    for (int it = jb_tid(); it < B * R2; it += jb_nthr()) {
+        int b = it / R2, n2 = it - b * R2;
+        double xv[R1];
+        jb_c2r_passB<FP>(sm + (size_t)b * LS + n2, xv);
+        double* tp = tile + (size_t)b * w + (n2 - m);
+        const double* pw = wgt + (n2 - m);
+        static_for<0, R1>([&](auto nn) {
+            constexpr int n1 = nn;
+            int q = R2 * n1 + n2 - m;
+            if (q >= 0 && q < w) tp[R2 * n1] = xv[n1] * jb_ldg(pw + R2 * n1);
+        });
+    }
+    JB_SYNC();
+    for (int idx = jb_tid(); idx < rpc * N; idx += jb_nthr()) {
+        int rr = idx / N, c = idx - rr * N, r = r0 + rr;
+        if (r >= N) continue;
+        double acc = 0.0;
+        const double* trow = tile + (size_t)rr * n * w + c + hp;
+        for (int i = 0; i < n; ++i) {
+            int v = c + hp - g.offs[i];
+            if (v >= 0 && v < w) acc += trow[(size_t)i * w - g.offs[i]];
+        }
+        grad[((size_t)se * N + r) * N + c] = acc;
+    }
+}
