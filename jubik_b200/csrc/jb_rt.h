@@ -21,6 +21,7 @@
 #define JB_D __device__ __forceinline__
 #define JB_GLOBAL __global__
 #define JB_GLOBAL_S static __global__
+#define JB_LB(t, b) __launch_bounds__(t, b)
 #define JB_SMEM(T, name) extern __shared__ __align__(128) unsigned char jb_smem_raw_[]; \
                          T* name = reinterpret_cast<T*>(jb_smem_raw_)
 typedef cudaStream_t jb_stream_t;
@@ -57,6 +58,7 @@ inline cudaError_t jb_launch(K kern, dim3 grid, dim3 block, size_t smem, jb_stre
 #define JB_D inline
 #define JB_GLOBAL
 #define JB_GLOBAL_S static
+#define JB_LB(t, b)
 struct cd { double x, y; };
 struct dim3 {
     unsigned x, y, z;

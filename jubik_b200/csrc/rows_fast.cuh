@@ -104,7 +104,7 @@ JB_D void jb_rowtab_build(const JbGeom& g, const JbRowTab& t, int r0, int rpc, i
 // ------------------------------------------------------------ forward: sky rows -> spectra (r2c)
 // grid (ceil(N/rpc), S*E); dyn smem = B*LS*16 + rowtab.
 template <class FP>
-JB_GLOBAL void k_rows_fwd2(JbGeom g, const double* __restrict__ x, const double* __restrict__ wgt,
+JB_GLOBAL void JB_LB(256, 2) k_rows_fwd2(JbGeom g, const double* __restrict__ x, const double* __restrict__ wgt,
                            const cd* __restrict__ tw_nk, cd* __restrict__ bufB, int rpc) {
     constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
     JB_SMEM(unsigned char, smraw);
@@ -161,7 +161,7 @@ JB_GLOBAL void k_rows_fwd2(JbGeom g, const double* __restrict__ x, const double*
 // ------------------------------------------------------ adjoint: cotangent rows -> spectra (r2c)
 // grid (ceil(N/rpc), S*T*E)
 template <class FP>
-JB_GLOBAL void k_rows_adj_in2(JbGeom g, const double* __restrict__ gin, const double* __restrict__ expo,
+JB_GLOBAL void JB_LB(256, 2) k_rows_adj_in2(JbGeom g, const double* __restrict__ gin, const double* __restrict__ expo,
                               const cd* __restrict__ tw_nk, cd* __restrict__ bufA, int rpc) {
     constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
     JB_SMEM(unsigned char, smraw);
@@ -237,7 +237,7 @@ JB_D cd jb_sum_spec(const cd* const (&pd)[JB_MAXQ], const cd* const (&pm)[JB_MAX
 // --------------------------------------------- forward: spectra -> image rows (+ epilogue) (c2r)
 // grid (ceil(N/rpc), S*T*E)
 template <class FP>
-JB_GLOBAL void k_rows_out2(JbGeom g, const cd* __restrict__ bufA, const cd* __restrict__ tw_kn, JbEpi ep, int rpc) {
+JB_GLOBAL void JB_LB(256, 2) k_rows_out2(JbGeom g, const cd* __restrict__ bufA, const cd* __restrict__ tw_kn, JbEpi ep, int rpc) {
     constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
     JB_SMEM(unsigned char, smraw);
     const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, P = g.P;
@@ -330,7 +330,7 @@ JB_GLOBAL void k_rows_out2(JbGeom g, const cd* __restrict__ bufA, const cd* __re
 // ------------------------------------ adjoint: spectra -> sky-gradient rows, summed over modules (c2r)
 // grid (ceil(N/rpc), S*E)
 template <class FP>
-JB_GLOBAL void k_rows_adj_out2(JbGeom g, const cd* __restrict__ bufB, const double* __restrict__ wgt,
+JB_GLOBAL void JB_LB(256, 2) k_rows_adj_out2(JbGeom g, const cd* __restrict__ bufB, const double* __restrict__ wgt,
                                const cd* __restrict__ tw_kn, double* __restrict__ grad, int rpc) {
     constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
     JB_SMEM(unsigned char, smraw);
