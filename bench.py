@@ -8,8 +8,8 @@ Workload at N=1: BASELINE.json configs[1] ("C2", Chandra-like): 1024x1024 sky, 3
 spatially-variant PSF patches, margin 64, exposure + readout mask + Poisson likelihood, S=1, T=1.
 One step = one evaluation of (energy, d energy / d sky); sky-pixels = S*T*E*N^2.
 At N>1 every rank owns one VI sample of the same workload (weak scaling, sample sharding, SURVEY 8e);
-the per-sample energies and the sample-summed gradient are combined with NCCL all-reduces inside the
-timed region.
+the per-sample energies and the sample-summed gradient sit in one flat buffer that is combined with a
+SINGLE NCCL all-reduce inside the timed region.
 
 `value`  : device-resident throughput (inputs already in HBM), CUDA events, max over ranks.
 `e2e`    : the same metric through ResponsePlan.energy_and_grad_host (C ABI jubik_poisson_energy_and_grad_host)
@@ -190,12 +190,21 @@ def run_ours(args):
     del lam, truth
     flush = torch.empty(192 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 192 MiB > 126 MB L2
 
+    # one flat buffer = [sample-summed sky gradient (E,N,N) | energies of all world*S samples]: the partial
+    # log-likelihoods and the gradient are combined with a SINGLE NCCL all-reduce (north_star)
+    npx = E * N * N
+    flat = torch.zeros(npx + world * S, dtype=torch.float64, device=dev)
+    gbuf = flat[:npx].view(1, E, N, N) if S == 1 else torch.empty((S, E, N, N), dtype=torch.float64, device=dev)
+    ebuf = flat[npx + rank * S: npx + (rank + 1) * S]
+
     def step_device():
-        e, g = plan.energy_and_grad(x)
         if world > 1:
-            gsum = g.sum(0) if S > 1 else g[0]
-            dist.all_reduce(e)          # per-sample energies -> KL value
-            dist.all_reduce(gsum)       # sample-summed sky gradient (E,N,N)
+            flat[npx:].zero_()
+        e, g = plan.energy_and_grad(x, out_energy=ebuf, out_grad=gbuf)
+        if S > 1:
+            torch.sum(g, 0, out=flat[:npx].view(E, N, N))
+        if world > 1:
+            dist.all_reduce(flat)
         return e, g
 
     def barrier():

@@ -199,13 +199,17 @@ class ResponsePlan:
         import torch
         torch.cuda.current_stream(self.device).synchronize()
 
-    def energy_and_grad(self, x, need_grad=True):
-        """Poisson energy sum(lambda) - d.log(lambda) per sample and its gradient w.r.t. the sky."""
+    def energy_and_grad(self, x, need_grad=True, out_energy=None, out_grad=None):
+        """Poisson energy sum(lambda) - d.log(lambda) per sample and its gradient w.r.t. the sky.
+        out_energy (S,) / out_grad (S,E,N,N): optional preallocated contiguous float64 CUDA outputs (e.g. views
+        into one flat buffer that is then all-reduced in a single NCCL call)."""
         import torch
         x, sq = self._sky(x)
         S = x.shape[0]
-        energy = torch.empty((S,), dtype=torch.float64, device=self.device)
-        grad = torch.empty_like(x) if need_grad else None
+        energy = out_energy if out_energy is not None else torch.empty((S,), dtype=torch.float64, device=self.device)
+        grad = (out_grad if out_grad is not None else torch.empty_like(x)) if need_grad else None
+        if energy.numel() != S or not energy.is_contiguous() or (need_grad and (grad.numel() != x.numel() or not grad.is_contiguous())):
+            raise ValueError("output buffers must be contiguous and match (S,) / (S,E,N,N)")
         self.raw.call("jubik_poisson_energy_and_grad", C.c_void_p(x.data_ptr()), S, C.c_void_p(energy.data_ptr()),
                       C.c_void_p(grad.data_ptr()) if need_grad else None, self._stream())
         if sq:
