@@ -30,7 +30,7 @@ NVCC_FLAGS = [
 def fft_list():
     txt = open(os.path.join(CSRC, "fft_list.h")).read()
     return [tuple(int(v) for v in m.groups())
-            for m in re.finditer(r"X\((\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+)\)", txt)]
+            for m in re.finditer(r"X\((\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+)\)", txt)]
 
 
 def _sources_mtime():
@@ -59,10 +59,10 @@ def build(force=False, jobs=None, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     jobs = jobs or os.cpu_count() or 4
     tasks = []
-    for (L, r1, r2, cb, pipe) in fft_list():
+    for (L, r1, r2, cb, pipe, q1, q2, q3) in fft_list():
         obj = os.path.join(OBJ, "fft_%d.o" % L)
         cmd = [nvcc] + NVCC_FLAGS + ["-DJB_INST_L=%d" % L, "-DJB_INST_R1=%d" % r1, "-DJB_INST_R2=%d" % r2,
-                                    "-DJB_INST_CB=%d" % cb, "-DJB_INST_PIPE=%d" % pipe, "-c", os.path.join(CSRC, "fft_inst.cu"), "-o", obj]
+                                    "-DJB_INST_CB=%d" % cb, "-DJB_INST_PIPE=%d" % pipe, "-DJB_INST_Q1=%d" % q1, "-DJB_INST_Q2=%d" % q2, "-DJB_INST_Q3=%d" % q3, "-c", os.path.join(CSRC, "fft_inst.cu"), "-o", obj]
         tasks.append((cmd, obj))
     obj = os.path.join(OBJ, "capi.o")
     tasks.append(([nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "capi.cu"), "-o", obj], obj))

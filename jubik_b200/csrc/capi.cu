@@ -7,7 +7,7 @@
 #include <vector>
 #include <new>
 
-#define JB_X_DECL(L, R1, R2, CB, PIPE) JB_DECLARE_FFT(L)
+#define JB_X_DECL(L, R1, R2, CB, PIPE, Q1, Q2, Q3) JB_DECLARE_FFT(L)
 JB_FFT_LIST(JB_X_DECL)
 #undef JB_X_DECL
 
@@ -66,13 +66,13 @@ int make_tile_src(JbTileSrc* ts, const cd* base, size_t rows, int PH, int CB, in
 }
 
 const JbFftOps* find_ops(int L) {
-#define JB_X_FIND(LL, R1, R2, CB, PIPE) if (L == LL) return jb_fft_ops_##LL();
+#define JB_X_FIND(LL, R1, R2, CB, PIPE, Q1, Q2, Q3) if (L == LL) return jb_fft_ops_##LL();
     JB_FFT_LIST(JB_X_FIND)
 #undef JB_X_FIND
     return nullptr;
 }
 const int k_lengths[] = {
-#define JB_X_LEN(LL, R1, R2, CB, PIPE) LL,
+#define JB_X_LEN(LL, R1, R2, CB, PIPE, Q1, Q2, Q3) LL,
     JB_FFT_LIST(JB_X_LEN)
 #undef JB_X_LEN
 };
@@ -90,6 +90,8 @@ struct jubik_plan {
     cd* khat = nullptr;
     cd* tw_nk = nullptr;
     cd* tw_kn = nullptr;
+    cd* tw1 = nullptr;         // three-stage column pass: W_L^{m k1}  [k1*M + m]
+    cd* tw2 = nullptr;         //                          W_M^{n3 k2} [k2*R3 + n3]
     double* wgt = nullptr;
     double* expo = nullptr;    // (T,E,N,N) effective exposure, 0 == masked
     double* data = nullptr;    // (T,E,N,N)
@@ -137,7 +139,7 @@ int jubik_device_count(void) { return device_count(); }
 
 int jubik_plan_destroy(jubik_plan* p) {
     if (!p) return JUBIK_OK;
-    dev_free(p->khat); dev_free(p->tw_nk); dev_free(p->tw_kn); dev_free(p->wgt); dev_free(p->expo);
+    dev_free(p->khat); dev_free(p->tw_nk); dev_free(p->tw_kn); dev_free(p->tw1); dev_free(p->tw2); dev_free(p->wgt); dev_free(p->expo);
     dev_free(p->data); dev_free(p->bufA); dev_free(p->bufB); dev_free(p->gbuf); dev_free(p->lbuf);
     dev_free(p->partial); dev_free(p->xdev); dev_free(p->gdev); dev_free(p->edev);
     delete p;
@@ -316,7 +318,26 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
         p->fast_rows = (o->R2 > 1) && mx <= JB_MAXQ && !getenv("JUBIK_B200_ROWS_V1");
     }
     // ---- pipelined column pass: TMA views of the two spectrum workspaces
-    p->use_pipe = o->pipe && !getenv("JUBIK_B200_COLS_V1");
+    p->use_pipe = getenv("JUBIK_B200_COLS_V1") ? 0 : o->pipe;
+    if (p->use_pipe == 2) {
+        const int Q1 = o->q1, Q2 = o->q2, Q3 = o->q3, M = Q2 * Q3;
+        std::vector<cd> a((size_t)L), b((size_t)M);
+        const long double two_pi = 6.283185307179586476925286766559005768L;
+        for (int k1 = 0; k1 < Q1; ++k1)
+            for (int mm = 0; mm < M; ++mm) {
+                long double ang = -two_pi * (long double)(((long long)k1 * mm) % L) / (long double)L;
+                a[(size_t)k1 * M + mm] = cd_make((double)cosl(ang), (double)sinl(ang));
+            }
+        for (int k2 = 0; k2 < Q2; ++k2)
+            for (int n3 = 0; n3 < Q3; ++n3) {
+                long double ang = -two_pi * (long double)(((long long)k2 * n3) % M) / (long double)M;
+                b[(size_t)k2 * Q3 + n3] = cd_make((double)cosl(ang), (double)sinl(ang));
+            }
+        if (alloc(p, (void**)&p->tw1, L * sizeof(cd), "twiddles") || alloc(p, (void**)&p->tw2, M * sizeof(cd), "twiddles") ||
+            h2d(p->tw1, a.data(), L * sizeof(cd), st) || h2d(p->tw2, b.data(), M * sizeof(cd), st) || stream_sync(st)) {
+            cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "uploading three-stage twiddles failed");
+        }
+    }
     if (p->use_pipe) {
         std::string err;
         int brB = g.w < 64 ? g.w : 64, brA = g.P < 64 ? g.P : 64;
@@ -339,7 +360,7 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
         int items = prpc * (o->R2 > 1 ? (o->R2 > o->R1 / 2 + 1 ? o->R2 : o->R1 / 2 + 1) : 1);
         int thr = ((items + 31) / 32) * 32; if (thr < 32) thr = 32; if (thr > 256) thr = 256;
         cudaError_t e = o->prep_rows(g, ks, p->tw_nk, p->bufB, prpc, thr, st);
-        if (e == cudaSuccess) { ++p->launches; e = o->prep_cols(g, p->bufB, sums, p->tw_nk, p->khat, p->thr_cols, st); }
+        if (e == cudaSuccess) { ++p->launches; e = o->prep_cols(g, p->bufB, sums, p->use_pipe == 2 ? p->tw1 : p->tw_nk, p->tw2, p->khat, p->use_pipe == 2 ? 2 : 0, p->thr_cols, st); }
         if (e == cudaSuccess) ++p->launches;
         if (e != cudaSuccess || stream_sync(st)) { cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "PSF spectrum kernels -> " + cuda_msg(e)); }
     }
@@ -407,7 +428,7 @@ static int run_forward(jubik_plan* p, const double* x, int S, const JbEpi& ep, j
     const JbFftOps* o = p->ops;
     JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.E, p->rpc_in, p->thr_rows, p->fast_rows, st));
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, false, p->src_fwd, p->bufA, p->khat, p->tw_nk, S * g.T * g.E, p->n_sm, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, false, p->src_fwd, p->bufA, p->khat, p->use_pipe == 2 ? p->tw1 : p->tw_nk, p->tw2, S * g.T * g.E, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, S * g.T * g.E, p->thr_cols, st));
     }
@@ -421,7 +442,7 @@ static int run_adjoint(jubik_plan* p, const double* gin, const double* expo, int
     const JbFftOps* o = p->ops;
     JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.E, p->rpc_in, p->thr_rows, p->fast_rows, st));
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, true, p->src_adj, p->bufB, p->khat, p->tw_nk, S * g.T * g.E, p->n_sm, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, true, p->src_adj, p->bufB, p->khat, p->use_pipe == 2 ? p->tw1 : p->tw_nk, p->tw2, S * g.T * g.E, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, S * g.T * g.E, p->thr_cols, st));
     }

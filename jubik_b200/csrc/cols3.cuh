@@ -1,0 +1,271 @@
+// cols3.cuh -- column pass with a THREE-stage transform L = R1*R2*R3 (e.g. 384 = 8*6*8) on a CB-column tile.
+//
+// Why three light stages instead of two heavy ones: an FP64 butterfly of radix 24 keeps ~100 registers
+// live, so only 4-6 warps per SM could work at a time and the FP64 pipe (2 issue cycles per warp
+// instruction, long dependent latency) sat at ~25 %.  Radix 6/8 items need ~40 registers, every stage has
+// >= 384 independent items, and a 512-thread CTA keeps 4 warps per scheduler busy in every stage.
+//
+// Index maps (decimation in time), M = R2*R3:
+//   n = M*n1 + R3*n2 + n3          k = k1 + R1*(k2 + R2*k3)
+//   stage 1: DFT_R1 over n1, * W_L^{(R3 n2 + n3) k1}        rows {M*a + m}      in place
+//   stage 2: DFT_R2 over n2, * W_M^{n3 k2}                   rows {k1*M + R3*a + n3} in place
+//   stage 3: DFT_R3 over n3  -> X[k] at row k1*M + R3*k2 + k3; * K^ ; inverse DFT_R3 in the same registers
+//   then stages 2', 1' mirror 2, 1 with conjugated twiddles applied BEFORE the inverse butterflies.
+// K^ is stored per (module/energy, patch, strip) as [k3][k1*R2 + k2][b]: the register distribution of
+// stage 3, so the slice is contiguous (one 1-D bulk copy) and read conflict-free.
+#pragma once
+#include "cols_pipe.cuh"
+
+template <int L_, int R1_, int R2_, int R3_>
+struct Fft3 {
+    static constexpr int L = L_, R1 = R1_, R2 = R2_, R3 = R3_, M = R2_ * R3_;
+    static_assert(R1_ * R2_ * R3_ == L_, "L = R1*R2*R3");
+};
+
+#define JB_C3_THREADS 512
+
+// twiddle tables (host-built, uploaded once): tw1[k1*M + m] = W_L^{m k1}, tw2[k2*R3 + n3] = W_M^{n3 k2}
+template <class F3, int CB>
+struct Cols3 {
+    static constexpr int L = F3::L, R1 = F3::R1, R2 = F3::R2, R3 = F3::R3, M = F3::M;
+    static constexpr int I1 = M * CB, I2 = R1 * R3 * CB, I3 = R1 * R2 * CB;
+    static_assert(I1 <= JB_C3_THREADS && I2 <= JB_C3_THREADS && I3 <= JB_C3_THREADS, "one item per thread and stage");
+
+    // forward stage 1 with zero rows outside [vlo, vhi)
+    static JB_D void s1_fwd(cd* tile, const cd* tw1, int w, int vlo, int vhi) {
+        if (w >= I1) return;
+        const int m = w / CB, b = w - m * CB;
+        cd v[R1];
+        static_for<0, R1>([&](auto nn) {
+            constexpr int n1 = nn;
+            int p = M * n1 + m;
+            v[n1] = (p >= vlo && p < vhi) ? tile[p * CB + b] : cd_make(0.0, 0.0);
+        });
+        dft<R1, -1>(v);
+        static_for<0, R1>([&](auto kk) {
+            constexpr int k1 = kk;
+            cd y = v[k1];
+            if constexpr (k1 > 0) y = cd_mul(y, tw1[k1 * M + m]);
+            tile[(k1 * M + m) * CB + b] = y;
+        });
+    }
+    static JB_D void s2_fwd(cd* tile, const cd* tw2, int w) {
+        if (w >= I2) return;
+        const int c = w / CB, b = w - c * CB;   // c = k1*R3 + n3
+        const int k1 = c / R3, n3 = c - k1 * R3;
+        cd* base = tile + (size_t)(k1 * M + n3) * CB + b;
+        cd v[R2];
+        static_for<0, R2>([&](auto nn) { constexpr int n2 = nn; v[n2] = base[(R3 * n2) * CB]; });
+        dft<R2, -1>(v);
+        static_for<0, R2>([&](auto kk) {
+            constexpr int k2 = kk;
+            cd y = v[k2];
+            if constexpr (k2 > 0) y = cd_mul(y, tw2[k2 * R3 + n3]);
+            base[(R3 * k2) * CB] = y;
+        });
+    }
+    // stage 3 forward only (plan time): returns the spectrum values of this thread
+    static JB_D void s3_fwd(const cd* tile, int w, cd (&v)[R3]) {
+        const int c = w / CB, b = w - c * CB;   // c = k1*R2 + k2 ; rows R3*c + n3
+        const cd* base = tile + (size_t)(R3 * c) * CB + b;
+        static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; v[n3] = base[n3 * CB]; });
+        dft<R3, -1>(v);
+    }
+    // stage 3: forward, * K^ (conj for the adjoint), inverse -- the spectrum never leaves the registers
+    template <bool ADJ>
+    static JB_D void s3_mid(cd* tile, const cd* kh, int w) {
+        if (w >= I3) return;
+        const int c = w / CB, b = w - c * CB;
+        cd* base = tile + (size_t)(R3 * c) * CB + b;
+        cd v[R3];
+        static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; v[n3] = base[n3 * CB]; });
+        dft<R3, -1>(v);
+        static_for<0, R3>([&](auto kk) {
+            constexpr int k3 = kk;
+            cd kv = kh[k3 * I3 + w];
+            v[k3] = ADJ ? cd_mulc(v[k3], kv) : cd_mul(v[k3], kv);
+        });
+        dft<R3, +1>(v);
+        static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; base[n3 * CB] = v[n3]; });
+    }
+    static JB_D void s2_inv(cd* tile, const cd* tw2, int w) {
+        if (w >= I2) return;
+        const int c = w / CB, b = w - c * CB;
+        const int k1 = c / R3, n3 = c - k1 * R3;
+        cd* base = tile + (size_t)(k1 * M + n3) * CB + b;
+        cd v[R2];
+        static_for<0, R2>([&](auto kk) {
+            constexpr int k2 = kk;
+            cd y = base[(R3 * k2) * CB];
+            if constexpr (k2 > 0) y = cd_mulc(y, tw2[k2 * R3 + n3]);
+            v[k2] = y;
+        });
+        dft<R2, +1>(v);
+        static_for<0, R2>([&](auto nn) { constexpr int n2 = nn; base[(R3 * n2) * CB] = v[n2]; });
+    }
+    // inverse stage 1: load + conj twiddle (registers only); the caller may release the tile afterwards
+    static JB_D void s1_inv_load(const cd* tile, const cd* tw1, int w, cd (&v)[R1]) {
+        const int m = w / CB, b = w - m * CB;
+        static_for<0, R1>([&](auto kk) {
+            constexpr int k1 = kk;
+            cd y = tile[(k1 * M + m) * CB + b];
+            if constexpr (k1 > 0) y = cd_mulc(y, tw1[k1 * M + m]);
+            v[k1] = y;
+        });
+    }
+};
+
+// --------------------------------------------------------------------------------------------------------
+// Persistent TMA pipeline, 512 threads, 2-stage ring of (tile, K^ slice); thread 0 refills a slot as soon as
+// every warp has pulled its stage-1' operands out of it.  dynamic smem = 4*L*CB*16 + (L + M)*16 + 64.
+template <class F3, int CB, bool ADJ>
+JB_GLOBAL void JB_LB(JB_C3_THREADS, 1)
+k_cols3_pipe(const
+#ifndef JB_EMU
+             __grid_constant__
+#endif
+             JbTileSrc src, JbGeom g, cd* __restrict__ out, const cd* __restrict__ khat,
+             const cd* __restrict__ tw1g, const cd* __restrict__ tw2g, int planes) {
+    using C3 = Cols3<F3, CB>;
+    constexpr int L = F3::L, R1 = F3::R1, M = F3::M;
+    constexpr int TILE = L * CB;
+    JB_SMEM(unsigned char, smraw);
+    cd* tile0 = reinterpret_cast<cd*>(smraw);
+    cd* kh0 = tile0 + 2 * TILE;
+    cd* tw1 = kh0 + 2 * TILE;
+    cd* tw2 = tw1 + L;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tw2 + M);
+    const int nstrips = (g.PH + CB - 1) / CB;
+    const long nitems = (long)planes * g.n * g.n * nstrips;
+    const int tid = threadIdx.x;
+    const int PH = g.PH;
+    for (int i = tid; i < L; i += JB_C3_THREADS) tw1[i] = tw1g[i];
+    for (int i = tid; i < M; i += JB_C3_THREADS) tw2[i] = tw2g[i];
+#ifndef JB_EMU
+    auto issue_loads = [&](long item_, int s_) {
+        JbColItem ci = jb_col_item<L, CB, ADJ>(g, item_, nstrips);
+        cd* tile = tile0 + s_ * TILE;
+        const int BR = src.BR;
+        int nch = (ci.in_rows + BR - 1) / BR, issued = 0;
+        for (int c = 0; c < nch; ++c) {
+            int r0 = c * BR;
+            if (r0 + BR > ci.in_rows) r0 = ci.in_rows - BR;
+            int p0 = ci.in_p0 + r0;
+            if (p0 + BR > ci.vlo && p0 < ci.vhi) ++issued;
+        }
+        jb_mbar_expect_tx(&bars[s_], (uint32_t)(issued * BR * CB * sizeof(cd) + TILE * sizeof(cd)));
+        for (int c = 0; c < nch; ++c) {
+            int r0 = c * BR;
+            if (r0 + BR > ci.in_rows) r0 = ci.in_rows - BR;
+            int p0 = ci.in_p0 + r0;
+            if (p0 + BR > ci.vlo && p0 < ci.vhi)
+                jb_tma_load_2d(tile + (size_t)p0 * CB, &src.map, 2 * ci.strip * CB, (int)(ci.in_row0 + r0), &bars[s_]);
+        }
+        jb_bulk_load_1d(kh0 + s_ * TILE, khat + ci.k_off, (uint32_t)(TILE * sizeof(cd)), &bars[s_]);
+    };
+    if (tid == 0) {
+        jb_mbar_init(&bars[0], 1);
+        jb_mbar_init(&bars[1], 1);
+        jb_mbar_init(&bars[2], JB_C3_THREADS / 32);
+        jb_mbar_init(&bars[3], JB_C3_THREADS / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((long)blockIdx.x < nitems) issue_loads(blockIdx.x, 0);
+        if ((long)blockIdx.x + gridDim.x < nitems) issue_loads((long)blockIdx.x + gridDim.x, 1);
+    }
+#endif
+    JB_SYNC();
+    long item = blockIdx.x;
+    for (unsigned it = 0; item < nitems; ++it, item += gridDim.x) {
+        const int s = it & 1;
+        JbColItem ci = jb_col_item<L, CB, ADJ>(g, item, nstrips);
+        cd* tile = tile0 + s * TILE;
+        cd* kh = kh0 + s * TILE;
+#ifndef JB_EMU
+        jb_mbar_wait<false>(&bars[s], (it >> 1) & 1);
+#else
+        JB_SYNC();
+        for (int idx = tid; idx < ci.in_rows * CB; idx += JB_C3_THREADS) {
+            int r = idx / CB, b = idx - r * CB, col = ci.strip * CB + b;
+            tile[(size_t)(ci.in_p0 + r) * CB + b] = col < PH ? src.base[(ci.in_row0 + r) * PH + col] : cd_make(0.0, 0.0);
+        }
+        for (int idx = tid; idx < TILE; idx += JB_C3_THREADS) kh[idx] = khat[ci.k_off + idx];
+        JB_SYNC();
+#endif
+        C3::s1_fwd(tile, tw1, tid, ci.vlo, ci.vhi);
+        JB_SYNC();
+        C3::s2_fwd(tile, tw2, tid);
+        JB_SYNC();
+        C3::template s3_mid<ADJ>(tile, kh, tid);
+        JB_SYNC();
+        C3::s2_inv(tile, tw2, tid);
+        JB_SYNC();
+        {
+            const bool act = tid < C3::I1;
+            cd v[R1];
+            if (act) C3::s1_inv_load(tile, tw1, tid, v);
+#ifndef JB_EMU
+            jb_fence_proxy_async();
+            __syncwarp();
+            if ((tid & 31) == 0) jb_mbar_arrive(&bars[2 + s]);
+            if (tid == 0) {
+                long nxt = item + 2 * (long)gridDim.x;
+                if (nxt < nitems) {
+                    jb_mbar_wait<false>(&bars[2 + s], (it >> 1) & 1);
+                    issue_loads(nxt, s);
+                }
+            }
+#endif
+            if (act) {
+                dft<R1, +1>(v);
+                const int m = tid / CB, b = tid - m * CB;
+                const int colg = ci.strip * CB + b;
+                cd* ob = out + ci.out_off + colg + (long long)(m - ci.out_p0) * PH;
+                static_for<0, R1>([&](auto nn) {
+                    constexpr int n1 = nn;
+                    int p = M * n1 + m;
+                    if (colg < PH && p >= ci.out_p0 && p < ci.out_p0 + ci.out_rows) ob[(long long)(M * n1) * PH] = v[n1];
+                });
+            }
+        }
+    }
+}
+
+// plan time: forward 3-stage column transform of the PSF row spectra, normalised, stored as [k3][k1*R2+k2][b].
+// grid (nstrips, n*n, TE), block JB_C3_THREADS, dyn smem = L*CB*16 + (L+M)*16.
+template <class F3, int CB>
+JB_GLOBAL void JB_LB(JB_C3_THREADS, 1)
+k_prep_cols3(JbGeom g, const cd* __restrict__ scratch, const double* __restrict__ sums, const cd* __restrict__ tw1g,
+             const cd* __restrict__ tw2g, cd* __restrict__ khat) {
+    using C3 = Cols3<F3, CB>;
+    constexpr int L = F3::L, R3 = F3::R3, M = F3::M;
+    JB_SMEM(cd, tile);
+    cd* tw1 = tile + L * CB;
+    cd* tw2 = tw1 + L;
+    const int tid = threadIdx.x;
+    const int strip = blockIdx.x, k = blockIdx.y, te = blockIdx.z;
+    const int nn2 = g.n * g.n, PH = g.PH, dx = g.dx, w = g.w;
+    const int nstrips = gridDim.x, col0 = strip * CB;
+    const size_t pk = (size_t)te * nn2 + k;
+    const cd* ib = scratch + pk * w * PH;
+    cd* kb = khat + (pk * nstrips + strip) * ((size_t)L * CB);
+    for (int i = tid; i < L; i += JB_C3_THREADS) tw1[i] = tw1g[i];
+    for (int i = tid; i < M; i += JB_C3_THREADS) tw2[i] = tw2g[i];
+    // rows of the L-periodic prepared kernel: offset d in [0,dx) -> row d ; d in [-dx,0) -> row L+d ; scratch row q = d+dx
+    for (int idx = tid; idx < L * CB; idx += JB_C3_THREADS) {
+        int p = idx / CB, b = idx - p * CB, col = col0 + b, q = -1;
+        if (p < dx) q = p + dx;
+        else if (p >= L - dx) q = p - L + dx;
+        tile[idx] = (q >= 0 && col < PH) ? ib[(size_t)q * PH + col] : cd_make(0.0, 0.0);
+    }
+    JB_SYNC();
+    C3::s1_fwd(tile, tw1, tid, 0, L);
+    JB_SYNC();
+    C3::s2_fwd(tile, tw2, tid);
+    JB_SYNC();
+    if (tid < C3::I3) {
+        cd v[R3];
+        C3::s3_fwd(tile, tid, v);
+        const double scale = 1.0 / (sums[pk] * (double)L * (double)L);
+        static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; kb[k3 * C3::I3 + tid] = cd_scale(v[k3], scale); });
+    }
+}

@@ -4,12 +4,14 @@
 //   CB*16 B == 128 B rows), 0: the plain one-CTA-per-strip kernel.
 // The build (Makefile / __graft_entry__.build) compiles fft_inst.cu once per line.
 #pragma once
+// X(L, R1, R2, CB, PIPE, Q1, Q2, Q3): rows use L = R1*R2; PIPE = 0 plain column kernel, 1 two-pass TMA pipeline,
+// 2 three-stage TMA pipeline with L = Q1*Q2*Q3 (cols3.cuh).
 #define JB_FFT_LIST(X) \
-    X(20, 20, 1, 8, 0)    \
-    X(24, 24, 1, 8, 0)    \
-    X(28, 28, 1, 8, 0)    \
-    X(160, 16, 10, 8, 1)  \
-    X(336, 24, 14, 8, 1)  \
-    X(384, 24, 16, 8, 1)  \
-    X(640, 32, 20, 8, 0)  \
-    X(672, 28, 24, 8, 0)
+    X(20, 20, 1, 8, 0, 1, 1, 1)    \
+    X(24, 24, 1, 8, 0, 1, 1, 1)    \
+    X(28, 28, 1, 8, 0, 1, 1, 1)    \
+    X(160, 16, 10, 8, 2, 8, 5, 4)  \
+    X(336, 24, 14, 8, 2, 8, 6, 7)  \
+    X(384, 24, 16, 8, 2, 8, 6, 8)  \
+    X(640, 32, 20, 8, 0, 1, 1, 1)  \
+    X(672, 28, 24, 8, 0, 1, 1, 1)

@@ -5,11 +5,13 @@
 #include "kernels.cuh"
 #include "rows_fast.cuh"
 #include "cols_pipe.cuh"
+#include "cols3.cuh"
 
 struct JbFftOps {
     int L, R1, R2, CB;
     int ls;    // cd per real sequence in the exchange buffer
-    int pipe;  // 1: cols_pipe (persistent TMA pipeline) is available for this length
+    int pipe;  // 0: plain column kernel only; 1: two-pass TMA pipeline; 2: three-stage TMA pipeline (cols3.cuh)
+    int q1, q2, q3;  // three-stage factors (pipe == 2)
     // fast != 0 selects the low-overhead kernels of rows_fast.cuh (two-pass lengths, <= JB_MAXQ row-patches per row)
     cudaError_t (*rows_fwd)(const JbGeom&, const double* x, const double* wgt, const cd* tw_nk, cd* bufB,
                             int planes, int rpc, int threads, int fast, jb_stream_t);
@@ -17,33 +19,41 @@ struct JbFftOps {
                                int planes, int rpc, int threads, int fast, jb_stream_t);
     cudaError_t (*cols)(const JbGeom&, bool adj, const cd* in, cd* out, const cd* khat, const cd* tw_nk,
                         int planes, int threads, jb_stream_t);
-    cudaError_t (*cols_pipe)(const JbGeom&, bool adj, const JbTileSrc& src, cd* out, const cd* khat, const cd* tw_nk,
-                             int planes, int ctas, jb_stream_t);
+    // twa/twb: tw_nk/unused (pipe 1) or the stage-1/stage-2 tables tw1/tw2 (pipe 2)
+    cudaError_t (*cols_pipe)(const JbGeom&, bool adj, const JbTileSrc& src, cd* out, const cd* khat, const cd* twa,
+                             const cd* twb, int planes, int ctas, jb_stream_t);
     cudaError_t (*rows_out)(const JbGeom&, const cd* bufA, const cd* tw_kn, const JbEpi&, int planes, int rpc,
                             int threads, int fast, jb_stream_t);
     cudaError_t (*rows_adj_out)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw_kn, double* grad,
                                 int planes, int rpc, int threads, int fast, jb_stream_t);
     cudaError_t (*prep_rows)(const JbGeom&, const JbKsrc&, const cd* tw_nk, cd* scratch, int rpc, int threads,
                              jb_stream_t);
-    cudaError_t (*prep_cols)(const JbGeom&, const cd* scratch, const double* sums, const cd* tw_nk, cd* khat,
-                             int threads, jb_stream_t);
+    // layout 0: K^ in the two-pass register order (tw = tw_nk); layout 2: three-stage order (twa/twb = tw1/tw2)
+    cudaError_t (*prep_cols)(const JbGeom&, const cd* scratch, const double* sums, const cd* twa, const cd* twb,
+                             cd* khat, int layout, int threads, jb_stream_t);
 };
 
 inline int jb_cdiv(int a, int b) { return (a + b - 1) / b; }
 inline size_t jb_al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-template <class FP, int CB, int PIPE>
+template <class FP, int CB, int PIPE, class F3>
 struct JbOpsImpl {
     static cudaError_t cols_pipe(const JbGeom& g, bool adj, const JbTileSrc& src, cd* out, const cd* khat,
-                                 const cd* tw_nk, int planes, int ctas, jb_stream_t st) {
-        if constexpr (PIPE && FP::R2 > 1) {
+                                 const cd* twa, const cd* twb, int planes, int ctas, jb_stream_t st) {
+        if constexpr (PIPE == 2) {
+            size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd) + 64;
+            if (adj) return jb_launch(k_cols3_pipe<F3, CB, true>, dim3(ctas), dim3(JB_C3_THREADS), smem, st, src, g,
+                                      out, khat, twa, twb, planes);
+            return jb_launch(k_cols3_pipe<F3, CB, false>, dim3(ctas), dim3(JB_C3_THREADS), smem, st, src, g, out,
+                             khat, twa, twb, planes);
+        } else if constexpr (PIPE == 1 && FP::R2 > 1) {
             size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + 64;
             if (adj) return jb_launch(k_cols_pipe<FP, CB, true>, dim3(ctas), dim3(JB_PIPE_THREADS), smem, st, src, g,
-                                      out, khat, tw_nk, planes);
+                                      out, khat, twa, planes);
             return jb_launch(k_cols_pipe<FP, CB, false>, dim3(ctas), dim3(JB_PIPE_THREADS), smem, st, src, g, out,
-                             khat, tw_nk, planes);
+                             khat, twa, planes);
         } else {
-            (void)g; (void)adj; (void)src; (void)out; (void)khat; (void)tw_nk; (void)planes; (void)ctas; (void)st;
+            (void)g; (void)adj; (void)src; (void)out; (void)khat; (void)twa; (void)twb; (void)planes; (void)ctas; (void)st;
             return (cudaError_t)1;
         }
     }
@@ -112,20 +122,27 @@ struct JbOpsImpl {
         return jb_launch(k_prep_rows<FP>, dim3(jb_cdiv(g.w, rpc), ks.T * ks.E * g.n * g.n), dim3(threads), smem, st,
                          g, ks, tw_nk, scratch, rpc);
     }
-    static cudaError_t prep_cols(const JbGeom& g, const cd* scratch, const double* sums, const cd* tw_nk, cd* khat,
-                                 int threads, jb_stream_t st) {
+    static cudaError_t prep_cols(const JbGeom& g, const cd* scratch, const double* sums, const cd* twa, const cd* twb,
+                                 cd* khat, int layout, int threads, jb_stream_t st) {
         dim3 grid(jb_cdiv(g.PH, CB), g.n * g.n, g.T * g.E);
+        if constexpr (PIPE == 2) {
+            if (layout == 2) {
+                size_t smem3 = (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd);
+                return jb_launch(k_prep_cols3<F3, CB>, grid, dim3(JB_C3_THREADS), smem3, st, g, scratch, sums, twa, twb, khat);
+            }
+        }
         size_t smem = (FP::R2 == 1) ? 16 : (size_t)FP::L * CB * sizeof(cd);
-        return jb_launch(k_prep_cols<FP, CB>, grid, dim3(threads), smem, st, g, scratch, sums, tw_nk, khat);
+        return jb_launch(k_prep_cols<FP, CB>, grid, dim3(threads), smem, st, g, scratch, sums, twa, khat);
     }
     static const JbFftOps* table() {
-        static const JbFftOps t = {FP::L, FP::R1, FP::R2, CB, FP::LS, (PIPE && FP::R2 > 1) ? 1 : 0,
+        static const JbFftOps t = {FP::L, FP::R1, FP::R2, CB, FP::LS, (FP::R2 > 1) ? PIPE : 0, F3::R1, F3::R2, F3::R3,
                                    rows_fwd, rows_adj_in, cols, cols_pipe,
                                    rows_out, rows_adj_out, prep_rows, prep_cols};
         return &t;
     }
 };
 
-#define JB_DEFINE_FFT(LEN, R1, R2, CB, PIPE) \
-    const JbFftOps* jb_fft_ops_##LEN() { return JbOpsImpl<FftPlan<LEN, R1, R2>, CB, PIPE>::table(); }
+#define JB_DEFINE_FFT(LEN, R1, R2, CB, PIPE, Q1, Q2, Q3) \
+    const JbFftOps* jb_fft_ops_##LEN() { \
+        return JbOpsImpl<FftPlan<LEN, R1, R2>, CB, PIPE, Fft3<(PIPE == 2 ? LEN : 1), Q1, Q2, Q3>>::table(); }
 #define JB_DECLARE_FFT(LEN) const JbFftOps* jb_fft_ops_##LEN();

@@ -35,10 +35,10 @@ def build(force=False, lengths=None):
         return LIB
     os.makedirs(OUT, exist_ok=True)
     tasks = []
-    for (L, r1, r2, cb, pipe) in fft_list():
+    for (L, r1, r2, cb, pipe, q1, q2, q3) in fft_list():
         o = os.path.join(OUT, "fft_%d.o" % L)
         tasks.append((["g++"] + FLAGS + ["-DJB_INST_L=%d" % L, "-DJB_INST_R1=%d" % r1, "-DJB_INST_R2=%d" % r2,
-                                         "-DJB_INST_CB=%d" % cb, "-DJB_INST_PIPE=%d" % pipe, "-c", os.path.join(CSRC, "fft_inst.cu"), "-o", o], o))
+                                         "-DJB_INST_CB=%d" % cb, "-DJB_INST_PIPE=%d" % pipe, "-DJB_INST_Q1=%d" % q1, "-DJB_INST_Q2=%d" % q2, "-DJB_INST_Q3=%d" % q3, "-c", os.path.join(CSRC, "fft_inst.cu"), "-o", o], o))
     for name in ("capi.cu",):
         o = os.path.join(OUT, name + ".o")
         tasks.append((["g++"] + FLAGS + ["-c", os.path.join(CSRC, name), "-o", o], o))
