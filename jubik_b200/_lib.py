@@ -64,7 +64,7 @@ def bind(lib):
     lib.jubik_poisson_energy_and_grad.argtypes = [vp, vp, i, vp, vp, vp]
     lib.jubik_poisson_metric_apply.argtypes = [vp, vp, vp, i, vp, vp]
     lib.jubik_poisson_energy_and_grad_host.argtypes = [vp, vp, i, vp, vp, vp]
-    lib.jubik_poisson_profile.argtypes = [vp, vp, i, vp, vp, C.POINTER(C.c_float), vp]
+    lib.jubik_poisson_profile.argtypes = [vp, vp, i, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_int), vp]
     lib.jubik_measure_fp64_tflops.argtypes = [C.POINTER(d), vp]
     for name in EXPORTS:
         if name not in ("jubik_last_error", "jubik_plan_launch_count"):

@@ -106,6 +106,7 @@ struct jubik_plan {
     size_t bytes_khat = 0, bytes_ws = 0, bytes_total = 0;
     int nblk_out = 0;
     int use_pipe = 0, n_sm = 1;
+    int split_epi = 1, nblk_epi = 1;  // Poisson/metric epilogue as a separate elementwise kernel
     int fast_rows = 0;         // rows_fast.cuh kernels (two-pass length and <= JB_MAXQ row-patches per image row)
     JbTileSrc src_fwd, src_adj;  // TMA views of bufB / bufA for the pipelined column pass
     // per-kernel timing (jubik_poisson_profile): events recorded after every launch while enabled
@@ -295,7 +296,10 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
     size_t bB = STE * nn2 * (size_t)g.w * g.PH * sizeof(cd);
     size_t bG = STE * (size_t)N * N * sizeof(double);
     p->nblk_out = jb_cdiv(N, p->rpc_out);
-    size_t bP = STE * (size_t)p->nblk_out * sizeof(double);
+    p->split_epi = getenv("JUBIK_B200_FUSED_EPI") ? 0 : 1;
+    p->nblk_epi = jb_cdiv(N * N, 256 * 8);
+    if (p->nblk_epi > 1024) p->nblk_epi = 1024;
+    size_t bP = STE * (size_t)(p->nblk_out > p->nblk_epi ? p->nblk_out : p->nblk_epi) * sizeof(double);
     p->bytes_ws = bA + bB + bG + bP;
     if (alloc(p, (void**)&p->khat, p->bytes_khat, "PSF spectra") || alloc(p, (void**)&p->bufA, bA, "spectrum workspace A") ||
         alloc(p, (void**)&p->bufB, bB, "spectrum workspace B") || alloc(p, (void**)&p->gbuf, bG, "cotangent workspace") ||
@@ -482,20 +486,30 @@ int jubik_poisson_energy_and_grad(jubik_plan* p, const double* x, int S, double*
     if (!p->has_expo || !p->has_data) return fail(JUBIK_ERR_ARG, "plan needs exposures and data for the Poisson energy");
     const JbGeom& g = p->g;
     JbEpi ep; memset(&ep, 0, sizeof(ep));
-    ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
-    if (int rc = run_forward(p, x, S, ep, st)) return rc;
-    JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
-                             (const double*)p->partial, g.T * g.E * p->nblk_out, energy));
+    if (p->split_epi) {
+        // convolved planes first, then the Poisson epilogue as a separate full-occupancy elementwise pass
+        ep.mode = JB_EPI_PSF; ep.out = p->gbuf;
+        if (int rc = run_forward(p, x, S, ep, st)) return rc;
+        JB_LAUNCHED(p, jb_launch(k_poisson_epi, dim3(p->nblk_epi, S * g.T * g.E), dim3(256), 256 * sizeof(double), st,
+                                 p->gbuf, (const double*)p->expo, (const double*)p->data, g.T * g.E, g.N * g.N, p->partial));
+        JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
+                                 (const double*)p->partial, g.T * g.E * p->nblk_epi, energy));
+    } else {
+        ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
+        if (int rc = run_forward(p, x, S, ep, st)) return rc;
+        JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
+                                 (const double*)p->partial, g.T * g.E * p->nblk_out, energy));
+    }
     if (grad) return run_adjoint(p, p->gbuf, nullptr, S, grad, st);
     return JUBIK_OK;
 }
 
-// Same work as jubik_poisson_energy_and_grad with a CUDA event after every kernel; ms_out[0..6] =
-// rows_fwd, cols_fwd, rows_out(+Poisson), reduce, rows_adj_in, cols_adj, rows_adj_out.  Synchronises.
-int jubik_poisson_profile(jubik_plan* p, const double* x, int S, double* energy, double* grad, float* ms_out, void* stream_) {
+// Same work as jubik_poisson_energy_and_grad with a CUDA event after every kernel; ms_out[0..*n_out) in launch
+// order: rows_fwd, cols_fwd, rows_out, [poisson_epi,] reduce, rows_adj_in, cols_adj, rows_adj_out.  Synchronises.
+int jubik_poisson_profile(jubik_plan* p, const double* x, int S, double* energy, double* grad, float* ms_out, int* n_out, void* stream_) {
 #ifndef JB_EMU
     jb_stream_t st = (jb_stream_t)stream_;
-    if (!ms_out || !grad) return fail(JUBIK_ERR_ARG, "null pointer");
+    if (!ms_out || !grad || !n_out) return fail(JUBIK_ERR_ARG, "null pointer");
     for (int i = 0; i < 16; ++i) if (!p->prof_ev[i]) JB_CK(cudaEventCreate(&p->prof_ev[i]));
     p->prof_on = 1; p->prof_n = 0;
     jb_mark(p, st);
@@ -503,10 +517,11 @@ int jubik_poisson_profile(jubik_plan* p, const double* x, int S, double* energy,
     p->prof_on = 0;
     if (rc) return rc;
     JB_CK(cudaStreamSynchronize(st));
-    for (int i = 0; i + 1 < p->prof_n && i < 7; ++i) JB_CK(cudaEventElapsedTime(&ms_out[i], p->prof_ev[i], p->prof_ev[i + 1]));
+    for (int i = 0; i + 1 < p->prof_n && i < 12; ++i) JB_CK(cudaEventElapsedTime(&ms_out[i], p->prof_ev[i], p->prof_ev[i + 1]));
+    *n_out = p->prof_n - 1;
     return JUBIK_OK;
 #else
-    (void)p; (void)x; (void)S; (void)energy; (void)grad; (void)ms_out; (void)stream_;
+    (void)p; (void)x; (void)S; (void)energy; (void)grad; (void)ms_out; (void)n_out; (void)stream_;
     return fail(JUBIK_ERR_UNSUPPORTED, "profiling needs CUDA");
 #endif
 }
@@ -566,8 +581,15 @@ int jubik_poisson_metric_apply(jubik_plan* p, const double* x, const double* v, 
     JbEpi ep; memset(&ep, 0, sizeof(ep));
     ep.mode = JB_EPI_RESP; ep.out = p->lbuf; ep.expo = p->expo;
     if (int rc = run_forward(p, x, S, ep, st)) return rc;
-    ep.mode = JB_EPI_METRIC; ep.out = p->gbuf; ep.lam = p->lbuf;
-    if (int rc = run_forward(p, v, S, ep, st)) return rc;
+    if (p->split_epi) {
+        ep.mode = JB_EPI_PSF; ep.out = p->gbuf; ep.expo = nullptr;
+        if (int rc = run_forward(p, v, S, ep, st)) return rc;
+        JB_LAUNCHED(p, jb_launch(k_metric_epi, dim3(p->nblk_epi, S * g.T * g.E), dim3(256), 0, st, p->gbuf,
+                                 (const double*)p->expo, (const double*)p->lbuf, g.T * g.E, g.N * g.N));
+    } else {
+        ep.mode = JB_EPI_METRIC; ep.out = p->gbuf; ep.lam = p->lbuf;
+        if (int rc = run_forward(p, v, S, ep, st)) return rc;
+    }
     return run_adjoint(p, p->gbuf, nullptr, S, out, st);
 }
 

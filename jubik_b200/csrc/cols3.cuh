@@ -24,6 +24,15 @@ struct Fft3 {
 
 #define JB_C3_THREADS 512
 
+// what the compute threads need to know about a work item; written by thread 0 when it stages the item
+struct JbColInfo {
+    long long out_off;  // element offset of (row 0, column strip*CB) of this patch in the output buffer
+    int vlo, vhi;       // valid (in-image) input rows of the tile
+    int out_p0, out_rows;
+    int ncols;          // valid columns in this strip (PH - strip*CB, capped at CB)
+    int pad;
+};
+
 // twiddle tables (host-built, uploaded once): tw1[k1*M + m] = W_L^{m k1}, tw2[k2*R3 + n3] = W_M^{n3 k2}
 template <class F3, int CB>
 struct Cols3 {
@@ -135,15 +144,24 @@ k_cols3_pipe(const
     cd* tw1 = kh0 + 2 * TILE;
     cd* tw2 = tw1 + L;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tw2 + M);
+    JbColInfo* info = reinterpret_cast<JbColInfo*>(bars + 4);
     const int nstrips = (g.PH + CB - 1) / CB;
     const long nitems = (long)planes * g.n * g.n * nstrips;
     const int tid = threadIdx.x;
     const int PH = g.PH;
+    auto fill_info = [&](const JbColItem& ci, int s_) {
+        JbColInfo& f = info[s_];
+        f.out_off = (long long)ci.out_off + (long long)ci.strip * CB;
+        f.vlo = ci.vlo; f.vhi = ci.vhi; f.out_p0 = ci.out_p0; f.out_rows = ci.out_rows;
+        int nc = PH - ci.strip * CB;
+        f.ncols = nc < CB ? nc : CB;
+    };
     for (int i = tid; i < L; i += JB_C3_THREADS) tw1[i] = tw1g[i];
     for (int i = tid; i < M; i += JB_C3_THREADS) tw2[i] = tw2g[i];
 #ifndef JB_EMU
     auto issue_loads = [&](long item_, int s_) {
         JbColItem ci = jb_col_item<L, CB, ADJ>(g, item_, nstrips);
+        fill_info(ci, s_);  // ordered before the consumers' reads by the release/acquire of full[s_]
         cd* tile = tile0 + s_ * TILE;
         const int BR = src.BR;
         int nch = (ci.in_rows + BR - 1) / BR, issued = 0;
@@ -177,13 +195,14 @@ k_cols3_pipe(const
     long item = blockIdx.x;
     for (unsigned it = 0; item < nitems; ++it, item += gridDim.x) {
         const int s = it & 1;
-        JbColItem ci = jb_col_item<L, CB, ADJ>(g, item, nstrips);
         cd* tile = tile0 + s * TILE;
         cd* kh = kh0 + s * TILE;
 #ifndef JB_EMU
         jb_mbar_wait<false>(&bars[s], (it >> 1) & 1);
 #else
+        JbColItem ci = jb_col_item<L, CB, ADJ>(g, item, nstrips);
         JB_SYNC();
+        if (tid == 0) fill_info(ci, s);
         for (int idx = tid; idx < ci.in_rows * CB; idx += JB_C3_THREADS) {
             int r = idx / CB, b = idx - r * CB, col = ci.strip * CB + b;
             tile[(size_t)(ci.in_p0 + r) * CB + b] = col < PH ? src.base[(ci.in_row0 + r) * PH + col] : cd_make(0.0, 0.0);
@@ -191,7 +210,8 @@ k_cols3_pipe(const
         for (int idx = tid; idx < TILE; idx += JB_C3_THREADS) kh[idx] = khat[ci.k_off + idx];
         JB_SYNC();
 #endif
-        C3::s1_fwd(tile, tw1, tid, ci.vlo, ci.vhi);
+        const JbColInfo f = info[s];
+        C3::s1_fwd(tile, tw1, tid, f.vlo, f.vhi);
         JB_SYNC();
         C3::s2_fwd(tile, tw2, tid);
         JB_SYNC();
@@ -218,13 +238,16 @@ k_cols3_pipe(const
             if (act) {
                 dft<R1, +1>(v);
                 const int m = tid / CB, b = tid - m * CB;
-                const int colg = ci.strip * CB + b;
-                cd* ob = out + ci.out_off + colg + (long long)(m - ci.out_p0) * PH;
-                static_for<0, R1>([&](auto nn) {
-                    constexpr int n1 = nn;
-                    int p = M * n1 + m;
-                    if (colg < PH && p >= ci.out_p0 && p < ci.out_p0 + ci.out_rows) ob[(long long)(M * n1) * PH] = v[n1];
-                });
+                const int q0 = m - f.out_p0;            // output row of n1 = 0 (may be negative)
+                const long long stride = (long long)M * PH;
+                cd* ob = out + f.out_off + b + (long long)q0 * PH;
+                if (b < f.ncols) {
+                    static_for<0, R1>([&](auto nn) {
+                        constexpr int n1 = nn;
+                        int q = q0 + M * n1;
+                        if (q >= 0 && q < f.out_rows) ob[n1 * stride] = v[n1];
+                    });
+                }
             }
         }
     }

@@ -438,6 +438,46 @@ JB_GLOBAL void k_prep_cols(JbGeom g, const cd* __restrict__ scratch, const doubl
     cols_cfft<FP, CB, false>(sm, tw_nk, ld, mid, st);
 }
 
+// Poisson epilogue as its own full-occupancy elementwise pass (log + divide are ~100 FP64 instructions per
+// pixel: inside the low-occupancy row kernel they cost 4x more than here).  In place on the convolved planes:
+//   buf[s,t,e,:,:] = conv  ->  expo*(1 - d/lambda)  (0 where masked), lambda = expo*conv;
+//   partial[(s*TE + te)*nblk + blockIdx.x] = sum over this CTA's pixels of lambda - d log lambda.
+// grid (nblk, S*T*E), block 256.
+JB_GLOBAL_S void k_poisson_epi(double* __restrict__ buf, const double* __restrict__ expo, const double* __restrict__ data,
+                               int TE, int npix, double* __restrict__ partial) {
+    JB_SMEM(double, red);
+    const int ste = blockIdx.y, te = ste % TE;
+    double* b = buf + (size_t)ste * npix;
+    const double* ex = expo + (size_t)te * npix;
+    const double* dd = data + (size_t)te * npix;
+    double esum = 0.0;
+    for (int i = blockIdx.x * jb_nthr() + jb_tid(); i < npix; i += gridDim.x * jb_nthr()) {
+        double e = jb_ldg(ex + i), conv = b[i], gout = 0.0;
+        if (e != 0.0) {
+            double lam = e * conv, d = jb_ldg(dd + i);
+            esum += lam - d * log(lam);
+            gout = e * (1.0 - d / lam);
+        }
+        b[i] = gout;
+    }
+    double tot = jb_block_sum(esum, red);
+    if (jb_tid() == 0) partial[(size_t)ste * gridDim.x + blockIdx.x] = tot;
+}
+
+// metric epilogue: buf = conv(v)  ->  expo * (expo*conv) / lambda  (0 where masked)
+JB_GLOBAL_S void k_metric_epi(double* __restrict__ buf, const double* __restrict__ expo, const double* __restrict__ lam,
+                              int TE, int npix) {
+    const int ste = blockIdx.y, te = ste % TE;
+    double* b = buf + (size_t)ste * npix;
+    const double* ex = expo + (size_t)te * npix;
+    const double* lm = lam + (size_t)ste * npix;
+    for (int i = blockIdx.x * jb_nthr() + jb_tid(); i < npix; i += gridDim.x * jb_nthr()) {
+        double e = jb_ldg(ex + i), gout = 0.0;
+        if (e != 0.0) gout = e * (e * b[i]) / lm[i];
+        b[i] = gout;
+    }
+}
+
 // energy[s] = sum over (t,e) planes and row blocks of the per-CTA partials; one CTA per sample
 JB_GLOBAL_S void k_reduce_energy(const double* __restrict__ partial, int per_sample, double* __restrict__ energy) {
     JB_SMEM(double, red);

@@ -41,7 +41,7 @@ struct JbOpsImpl {
     static cudaError_t cols_pipe(const JbGeom& g, bool adj, const JbTileSrc& src, cd* out, const cd* khat,
                                  const cd* twa, const cd* twb, int planes, int ctas, jb_stream_t st) {
         if constexpr (PIPE == 2) {
-            size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd) + 64;
+            size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd) + 32 + 2 * sizeof(JbColInfo) + 32;
             if (adj) return jb_launch(k_cols3_pipe<F3, CB, true>, dim3(ctas), dim3(JB_C3_THREADS), smem, st, src, g,
                                       out, khat, twa, twb, planes);
             return jb_launch(k_cols3_pipe<F3, CB, false>, dim3(ctas), dim3(JB_C3_THREADS), smem, st, src, g, out,

@@ -236,7 +236,9 @@ class ResponsePlan:
                       C.c_void_p(energy_host.data_ptr()),
                       C.c_void_p(grad_host.data_ptr()) if grad_host is not None else None, self._stream())
 
-    KERNEL_NAMES = ("rows_fwd", "cols_fwd", "rows_out", "reduce", "rows_adj_in", "cols_adj", "rows_adj_out")
+    KERNEL_NAMES = {7: ("rows_fwd", "cols_fwd", "rows_out", "reduce", "rows_adj_in", "cols_adj", "rows_adj_out"),
+                    8: ("rows_fwd", "cols_fwd", "rows_out", "poisson_epi", "reduce", "rows_adj_in", "cols_adj",
+                        "rows_adj_out")}
 
     def profile(self, x):
         """energy_and_grad with a CUDA event after each kernel -> (energy, grad, {kernel: ms})."""
@@ -245,10 +247,12 @@ class ResponsePlan:
         S = x.shape[0]
         energy = torch.empty((S,), dtype=torch.float64, device=self.device)
         grad = torch.empty_like(x)
-        ms = (C.c_float * 7)()
+        ms = (C.c_float * 12)()
+        n = C.c_int(0)
         self.raw.call("jubik_poisson_profile", C.c_void_p(x.data_ptr()), S, C.c_void_p(energy.data_ptr()),
-                      C.c_void_p(grad.data_ptr()), ms, self._stream())
-        return energy, grad, dict(zip(self.KERNEL_NAMES, [float(v) for v in ms]))
+                      C.c_void_p(grad.data_ptr()), ms, C.byref(n), self._stream())
+        names = self.KERNEL_NAMES.get(n.value, tuple("k%d" % i for i in range(n.value)))
+        return energy, grad, dict(zip(names, [float(ms[i]) for i in range(n.value)]))
 
     @property
     def launch_count(self):
