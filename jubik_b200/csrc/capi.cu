@@ -33,10 +33,10 @@ std::string cuda_msg(cudaError_t) { return "emu"; }
 int device_count() { return 1; }
 #endif
 
-// 2-D fp64 TMA view of a (rows x PH) complex row-major buffer; box = CB columns x BR rows.
-int make_tile_src(JbTileSrc* ts, const cd* base, size_t rows, int PH, int CB, int BR, std::string* err) {
+// 3-D fp64 TMA view of a row-spectrum buffer (slabs, N, PH) complex: box = CB columns x BR rows x 1 slab.
+int make_tile_src(JbTileSrc* ts, const cd* base, size_t slabs, int N, int PH, int CB, int BR, std::string* err) {
     memset(ts, 0, sizeof(*ts));
-    ts->base = base; ts->PH = PH; ts->BR = BR;
+    ts->base = base; ts->PH = PH; ts->BR = BR; ts->N = N;
 #ifndef JB_EMU
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -51,16 +51,16 @@ int make_tile_src(JbTileSrc* ts, const cd* base, size_t rows, int PH, int CB, in
         }
         encode = (encode_fn)fn;
     }
-    cuuint64_t gdim[2] = {(cuuint64_t)2 * PH, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)PH * sizeof(cd)};
-    cuuint32_t box[2] = {(cuuint32_t)(2 * CB), (cuuint32_t)BR};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&ts->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gdim, gstr, box, estr,
+    cuuint64_t gdim[3] = {(cuuint64_t)2 * PH, (cuuint64_t)N, (cuuint64_t)slabs};
+    cuuint64_t gstr[2] = {(cuuint64_t)PH * sizeof(cd), (cuuint64_t)N * PH * sizeof(cd)};
+    cuuint32_t box[3] = {(cuuint32_t)(2 * CB), (cuuint32_t)BR, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&ts->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r); return 1; }
 #else
-    (void)rows; (void)CB; (void)err;
+    (void)slabs; (void)CB; (void)err;
 #endif
     return 0;
 }
@@ -95,8 +95,11 @@ struct jubik_plan {
     double* wgt = nullptr;
     double* expo = nullptr;    // (T,E,N,N) effective exposure, 0 == masked
     double* data = nullptr;    // (T,E,N,N)
-    cd* bufA = nullptr;        // (S_max*T*E, n^2, P, PH)
-    cd* bufB = nullptr;        // (S_max*T*E, n^2, w, PH)
+    // bufA: forward  column-pass output (STE, n^2, P, PH) -> rows_out;  adjoint row spectra rowsA (STE, n, N, PH)
+    // bufB: adjoint  column-pass output (STE, n^2, w, PH) -> rows_adj_out; forward row spectra rowsF (S*E, n, N, PH)
+    // (each direction uses one buffer as its de-duplicated input and the other as its per-patch output)
+    cd* bufA = nullptr;
+    cd* bufB = nullptr;
     double* gbuf = nullptr;    // (S_max,T,E,N,N) cotangent / lambda scratch
     double* lbuf = nullptr;    // (S_max,T,E,N,N) lambda for the metric (allocated on first use)
     double* partial = nullptr; // energy partials
@@ -345,8 +348,11 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
     if (p->use_pipe) {
         std::string err;
         int brB = g.w < 64 ? g.w : 64, brA = g.P < 64 ? g.P : 64;
-        if (make_tile_src(&p->src_fwd, p->bufB, STE * nn2 * (size_t)g.w, g.PH, o->CB, brB, &err) ||
-            make_tile_src(&p->src_adj, p->bufA, STE * nn2 * (size_t)g.P, g.PH, o->CB, brA, &err)) {
+        if (brB > N) brB = N;
+        if (brA > N) brA = N;
+        // the row-spectrum buffers (slabs = planes*n, N rows, PH) live in the first part of bufB (forward) / bufA (adjoint)
+        if (make_tile_src(&p->src_fwd, p->bufB, STE * (size_t)n, N, g.PH, o->CB, brB, &err) ||
+            make_tile_src(&p->src_adj, p->bufA, STE * (size_t)n, N, g.PH, o->CB, brA, &err)) {
             cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, err);
         }
 #ifndef JB_EMU
@@ -432,9 +438,9 @@ static int run_forward(jubik_plan* p, const double* x, int S, const JbEpi& ep, j
     const JbFftOps* o = p->ops;
     JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.E, p->rpc_in, p->thr_rows, p->fast_rows, st));
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, false, p->src_fwd, p->bufA, p->khat, p->use_pipe == 2 ? p->tw1 : p->tw_nk, p->tw2, S * g.T * g.E, p->n_sm, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, false, p->src_fwd, p->bufA, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.E, p->n_sm, st));
     } else {
-        JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, S * g.T * g.E, p->thr_cols, st));
+        JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, p->wgt, S * g.T * g.E, p->thr_cols, st));
     }
     JB_LAUNCHED(p, o->rows_out(g, p->bufA, p->tw_kn, ep, S * g.T * g.E, p->rpc_out, p->thr_rows, p->fast_rows, st));
     return 0;
@@ -446,9 +452,9 @@ static int run_adjoint(jubik_plan* p, const double* gin, const double* expo, int
     const JbFftOps* o = p->ops;
     JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.E, p->rpc_in, p->thr_rows, p->fast_rows, st));
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, true, p->src_adj, p->bufB, p->khat, p->use_pipe == 2 ? p->tw1 : p->tw_nk, p->tw2, S * g.T * g.E, p->n_sm, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, true, p->src_adj, p->bufB, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.E, p->n_sm, st));
     } else {
-        JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, S * g.T * g.E, p->thr_cols, st));
+        JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, p->wgt, S * g.T * g.E, p->thr_cols, st));
     }
     JB_LAUNCHED(p, o->rows_adj_out(g, p->bufB, p->wgt, p->tw_kn, out, S * g.E, p->rpc_out, p->thr_rows, p->fast_rows, st));
     return 0;

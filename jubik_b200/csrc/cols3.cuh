@@ -40,15 +40,21 @@ struct Cols3 {
     static constexpr int I1 = M * CB, I2 = R1 * R3 * CB, I3 = R1 * R2 * CB;
     static_assert(I1 <= JB_C3_THREADS && I2 <= JB_C3_THREADS && I3 <= JB_C3_THREADS, "one item per thread and stage");
 
-    // forward stage 1 with zero rows outside [vlo, vhi)
-    static JB_D void s1_fwd(cd* tile, const cd* tw1, int w, int vlo, int vhi) {
+    // forward stage 1 with zero rows outside [vlo, vhi); rw != nullptr: multiply tile row p by rw[p - p0]
+    // (the window row weight of the forward direction, convolve.py:88-90)
+    static JB_D void s1_fwd(cd* tile, const cd* tw1, int w, int vlo, int vhi, const double* rw, int p0) {
         if (w >= I1) return;
         const int m = w / CB, b = w - m * CB;
         cd v[R1];
         static_for<0, R1>([&](auto nn) {
             constexpr int n1 = nn;
             int p = M * n1 + m;
-            v[n1] = (p >= vlo && p < vhi) ? tile[p * CB + b] : cd_make(0.0, 0.0);
+            cd t = cd_make(0.0, 0.0);
+            if (p >= vlo && p < vhi) {
+                t = tile[p * CB + b];
+                if (rw) t = cd_scale(t, rw[p - p0]);
+            }
+            v[n1] = t;
         });
         dft<R1, -1>(v);
         static_for<0, R1>([&](auto kk) {
@@ -134,7 +140,7 @@ k_cols3_pipe(const
              __grid_constant__
 #endif
              JbTileSrc src, JbGeom g, cd* __restrict__ out, const cd* __restrict__ khat,
-             const cd* __restrict__ tw1g, const cd* __restrict__ tw2g, int planes) {
+             const cd* __restrict__ tw1g, const cd* __restrict__ tw2g, const double* __restrict__ wgt, int planes) {
     using C3 = Cols3<F3, CB>;
     constexpr int L = F3::L, R1 = F3::R1, M = F3::M;
     constexpr int TILE = L * CB;
@@ -145,6 +151,7 @@ k_cols3_pipe(const
     cd* tw2 = tw1 + L;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tw2 + M);
     JbColInfo* info = reinterpret_cast<JbColInfo*>(bars + 4);
+    double* rw = reinterpret_cast<double*>(info + 2);  // window row weights (forward direction only)
     const int nstrips = (g.PH + CB - 1) / CB;
     const long nitems = (long)planes * g.n * g.n * nstrips;
     const int tid = threadIdx.x;
@@ -158,6 +165,7 @@ k_cols3_pipe(const
     };
     for (int i = tid; i < L; i += JB_C3_THREADS) tw1[i] = tw1g[i];
     for (int i = tid; i < M; i += JB_C3_THREADS) tw2[i] = tw2g[i];
+    if (!ADJ) for (int i = tid; i < g.w; i += JB_C3_THREADS) rw[i] = wgt[i];
 #ifndef JB_EMU
     auto issue_loads = [&](long item_, int s_) {
         JbColItem ci = jb_col_item<L, CB, ADJ>(g, item_, nstrips);
@@ -177,7 +185,7 @@ k_cols3_pipe(const
             if (r0 + BR > ci.in_rows) r0 = ci.in_rows - BR;
             int p0 = ci.in_p0 + r0;
             if (p0 + BR > ci.vlo && p0 < ci.vhi)
-                jb_tma_load_2d(tile + (size_t)p0 * CB, &src.map, 2 * ci.strip * CB, (int)(ci.in_row0 + r0), &bars[s_]);
+                jb_tma_load_3d(tile + (size_t)p0 * CB, &src.map, 2 * ci.strip * CB, ci.row0 + r0, ci.in_slab, &bars[s_]);
         }
         jb_bulk_load_1d(kh0 + s_ * TILE, khat + ci.k_off, (uint32_t)(TILE * sizeof(cd)), &bars[s_]);
     };
@@ -204,14 +212,15 @@ k_cols3_pipe(const
         JB_SYNC();
         if (tid == 0) fill_info(ci, s);
         for (int idx = tid; idx < ci.in_rows * CB; idx += JB_C3_THREADS) {
-            int r = idx / CB, b = idx - r * CB, col = ci.strip * CB + b;
-            tile[(size_t)(ci.in_p0 + r) * CB + b] = col < PH ? src.base[(ci.in_row0 + r) * PH + col] : cd_make(0.0, 0.0);
+            int r = idx / CB, b = idx - r * CB, col = ci.strip * CB + b, ir = ci.row0 + r;
+            tile[(size_t)(ci.in_p0 + r) * CB + b] = (col < PH && ir >= 0 && ir < src.N)
+                ? src.base[((size_t)ci.in_slab * src.N + ir) * PH + col] : cd_make(0.0, 0.0);
         }
         for (int idx = tid; idx < TILE; idx += JB_C3_THREADS) kh[idx] = khat[ci.k_off + idx];
         JB_SYNC();
 #endif
         const JbColInfo f = info[s];
-        C3::s1_fwd(tile, tw1, tid, f.vlo, f.vhi);
+        C3::s1_fwd(tile, tw1, tid, f.vlo, f.vhi, ADJ ? nullptr : rw, g.m);
         JB_SYNC();
         C3::s2_fwd(tile, tw2, tid);
         JB_SYNC();
@@ -281,7 +290,7 @@ k_prep_cols3(JbGeom g, const cd* __restrict__ scratch, const double* __restrict_
         tile[idx] = (q >= 0 && col < PH) ? ib[(size_t)q * PH + col] : cd_make(0.0, 0.0);
     }
     JB_SYNC();
-    C3::s1_fwd(tile, tw1, tid, 0, L);
+    C3::s1_fwd(tile, tw1, tid, 0, L, nullptr, 0);
     JB_SYNC();
     C3::s2_fwd(tile, tw2, tid);
     JB_SYNC();

@@ -1,4 +1,5 @@
-// cols_pipe.cuh -- the column pass as a persistent, warp-specialised, TMA-fed pipeline (sm_100a).
+// cols_pipe.cuh -- building blocks of the column pass as a persistent TMA-fed pipeline (sm_100a): mbarrier /
+// cp.async.bulk wrappers, the tile source (3-D tensor map) and the per-item geometry.  The kernel is in cols3.cuh.
 //
 // One CTA per SM loops over (plane, patch, strip) work items.  Thread 0 stages, two items ahead,
 //   * the CB-column input tile of the patch's row spectra with cp.async.bulk.tensor.2d (TMA; columns
@@ -18,11 +19,14 @@
 
 struct JbTileSrc {
 #ifndef JB_EMU
-    CUtensorMap map;   // 2-D fp64 view: dim0 = 2*PH doubles (contiguous), dim1 = all rows of the buffer
+    CUtensorMap map;   // 3-D fp64 view of a row-spectrum buffer (planes*n, N, PH): dim0 = 2*PH doubles (contiguous),
+                       // dim1 = N image rows, dim2 = plane*n + i ; box = (2*CB, BR, 1).  Rows outside [0,N) and
+                       // columns beyond PH are zero-filled by the TMA unit.
 #endif
     const cd* base;    // same buffer, for the emulation build
     int PH;
     int BR;            // rows per TMA box
+    int N;
 };
 
 #define JB_PIPE_COMPUTE_THREADS 256
@@ -57,10 +61,10 @@ JB_D void jb_mbar_wait(uint64_t* b, uint32_t parity) {
         }
     } while (!done);
 }
-JB_D void jb_tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+JB_D void jb_tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(jb_smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(jb_smem_u32(bar))
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(jb_smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(jb_smem_u32(bar))
         : "memory");
 }
 JB_D void jb_bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -76,9 +80,10 @@ inline void jb_bar_compute() { JB_SYNC(); }
 
 // per-item geometry shared by producer and consumers
 struct JbColItem {
-    int strip, k, plane, te, j;
+    int strip, k, plane, te, j, i;
     int in_p0, in_rows, vlo, vhi, out_p0, out_rows;
-    size_t in_row0;   // first row of this patch in the input buffer (row units)
+    int row0;         // image row of tile row in_p0 (may be negative / run past N: zero rows)
+    int in_slab;      // in_plane*n + i : which (plane, column block) slab of the row-spectrum buffer
     size_t out_off;   // element offset of this patch in the output buffer
     size_t k_off;     // element offset of this (te, patch, strip) slice of K^
 };
@@ -92,200 +97,27 @@ JB_D JbColItem jb_col_item(const JbGeom& g, long item, int nstrips) {
     it.k = (int)(r % nn2);
     it.plane = (int)(r / nn2);
     it.j = it.k % g.n;
+    it.i = it.k / g.n;
     const int TE = g.T * g.E;
     const int s = it.plane / TE;
     it.te = it.plane - s * TE;
     const int e = it.te % g.E;
-    size_t in_plane;
+    int in_plane;
     if (!ADJ) {
         it.in_p0 = g.m; it.in_rows = g.w; it.out_p0 = 0; it.out_rows = g.P;
-        in_plane = (size_t)s * g.E + e;
-        int lo = g.hp - g.offs[it.j], hi = g.N + g.hp - g.offs[it.j];
-        it.vlo = g.m + (lo > 0 ? lo : 0);
-        it.vhi = g.m + (hi < g.w ? hi : g.w);
+        in_plane = s * g.E + e;
+        it.row0 = g.offs[it.j] - g.hp;
     } else {
         it.in_p0 = 0; it.in_rows = g.P; it.out_p0 = g.m; it.out_rows = g.w;
-        in_plane = (size_t)it.plane;
-        int lo = g.hp + g.m - g.offs[it.j], hi = g.N + g.hp + g.m - g.offs[it.j];
-        it.vlo = lo > 0 ? lo : 0;
-        it.vhi = hi < g.P ? hi : g.P;
+        in_plane = it.plane;
+        it.row0 = g.offs[it.j] - g.hp - g.m;
     }
-    it.in_row0 = (in_plane * nn2 + it.k) * (size_t)it.in_rows;
+    // tile rows whose image row lies in [0,N)
+    int lo = -it.row0, hi = g.N - it.row0;
+    it.vlo = it.in_p0 + (lo > 0 ? lo : 0);
+    it.vhi = it.in_p0 + (hi < it.in_rows ? hi : it.in_rows);
+    it.in_slab = in_plane * g.n + it.i;
     it.out_off = (((size_t)it.plane * nn2 + it.k) * (size_t)it.out_rows) * g.PH;
     it.k_off = (((size_t)it.te * nn2 + it.k) * nstrips + it.strip) * ((size_t)L * CB);
     return it;
-}
-
-// grid = min(items, SMs) persistent CTAs, block = JB_PIPE_THREADS, dynamic smem = 2*(2*L*CB*16) + 64.
-template <class FP, int CB, bool ADJ>
-JB_GLOBAL void
-#ifndef JB_EMU
-__maxnreg__(224)
-#endif
-k_cols_pipe(const
-#ifndef JB_EMU
-            __grid_constant__
-#endif
-            JbTileSrc src, JbGeom g, cd* __restrict__ out, const cd* __restrict__ khat,
-            const cd* __restrict__ tw_nk, int planes) {
-    constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2;
-    static_assert(R2 > 2 && R1 > 2, "the pipelined column pass is for two-pass lengths");
-    static_assert(R2 * CB <= JB_PIPE_COMPUTE_THREADS && R1 * CB <= JB_PIPE_COMPUTE_THREADS,
-                  "one work item per thread and pass (thread-constant twiddle seeds)");
-    constexpr int TILE = L * CB;  // cd per tile
-    JB_SMEM(unsigned char, smraw);
-    cd* tile0 = reinterpret_cast<cd*>(smraw);
-    cd* kh0 = tile0 + 2 * TILE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(kh0 + 2 * TILE);  // full[0], full[1], done[0], done[1]
-    const int nstrips = (g.PH + CB - 1) / CB;
-    const long nitems = (long)planes * g.n * g.n * nstrips;
-    const int tid = threadIdx.x;
-    const int PH = g.PH;
-
-#ifndef JB_EMU
-    // Thread 0 doubles as the producer: it stages item it+2 into a ring slot as soon as every warp has
-    // pulled its last operands of item it out of that slot (a separate producer warp would cost a whole
-    // 4-warp register allocation granule and cap the compute warps at 168 registers).
-    auto issue_loads = [&](long item_, int s_) {
-        JbColItem ci = jb_col_item<L, CB, ADJ>(g, item_, nstrips);
-        cd* tile = tile0 + s_ * TILE;
-        const int BR = src.BR;
-        int nch = (ci.in_rows + BR - 1) / BR, issued = 0;
-        for (int c = 0; c < nch; ++c) {  // row chunks of the input tile that intersect the in-image range
-            int r0 = c * BR;
-            if (r0 + BR > ci.in_rows) r0 = ci.in_rows - BR;
-            int p0 = ci.in_p0 + r0;
-            if (p0 + BR > ci.vlo && p0 < ci.vhi) ++issued;
-        }
-        jb_mbar_expect_tx(&bars[s_], (uint32_t)(issued * BR * CB * sizeof(cd) + TILE * sizeof(cd)));
-        for (int c = 0; c < nch; ++c) {
-            int r0 = c * BR;
-            if (r0 + BR > ci.in_rows) r0 = ci.in_rows - BR;
-            int p0 = ci.in_p0 + r0;
-            if (p0 + BR > ci.vlo && p0 < ci.vhi)
-                jb_tma_load_2d(tile + (size_t)p0 * CB, &src.map, 2 * ci.strip * CB, (int)(ci.in_row0 + r0), &bars[s_]);
-        }
-        jb_bulk_load_1d(kh0 + s_ * TILE, khat + ci.k_off, (uint32_t)(TILE * sizeof(cd)), &bars[s_]);
-    };
-    if (tid == 0) {
-        jb_mbar_init(&bars[0], 1);
-        jb_mbar_init(&bars[1], 1);
-        jb_mbar_init(&bars[2], JB_PIPE_THREADS / 32);
-        jb_mbar_init(&bars[3], JB_PIPE_THREADS / 32);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if ((long)blockIdx.x < nitems) issue_loads(blockIdx.x, 0);
-        if ((long)blockIdx.x + gridDim.x < nitems) issue_loads((long)blockIdx.x + gridDim.x, 1);
-    }
-    __syncthreads();
-#endif
-    // ---------------------------------------------------------------------- compute warps
-    // The thread <-> (n2 | k1) mapping is the same for every item, so the inter-pass twiddles
-    // W_L^{n2 k1} are generated from two thread-constant seeds by a two-chain recurrence
-    // (odd/even powers): no table loads on the critical path, error <= ~R/2 roundings.
-    cd p1w1 = cd_make(1.0, 0.0), p1w2 = p1w1, p2w1 = p1w1, p2w2 = p1w1;
-    {
-        int n2 = tid / CB, k1 = tid / CB;
-        if (n2 < R2) { p1w1 = tw_nk[1 * R2 + n2]; p1w2 = tw_nk[2 * R2 + n2]; }            // W^{n2}, W^{2 n2}
-        if (k1 < R1) { p2w1 = cd_conj(tw_nk[k1 * R2 + 1]); p2w2 = cd_conj(tw_nk[k1 * R2 + 2]); }  // W^{-k1}, W^{-2 k1}
-    }
-    long item = blockIdx.x;
-    for (unsigned it = 0; item < nitems; ++it, item += gridDim.x) {
-        const int s = it & 1;
-        JbColItem ci = jb_col_item<L, CB, ADJ>(g, item, nstrips);
-        cd* tile = tile0 + s * TILE;
-        const cd* kh = kh0 + s * TILE;
-#ifndef JB_EMU
-        jb_mbar_wait<false>(&bars[s], (it >> 1) & 1);
-#else
-        // emulation: synchronous staging of the same tiles (tests/emu only)
-        JB_SYNC();
-        for (int idx = tid; idx < ci.in_rows * CB; idx += JB_PIPE_COMPUTE_THREADS) {
-            int r = idx / CB, b = idx - r * CB, col = ci.strip * CB + b;
-            tile[(size_t)(ci.in_p0 + r) * CB + b] =
-                col < PH ? src.base[(ci.in_row0 + r) * PH + col] : cd_make(0.0, 0.0);
-        }
-        for (int idx = tid; idx < TILE; idx += JB_PIPE_COMPUTE_THREADS) const_cast<cd*>(kh)[idx] = khat[ci.k_off + idx];
-        JB_SYNC();
-#endif
-        // pass 1: forward radix-R1 over n1, in place (index set {R2*a + n2} is closed under the exchange)
-        for (int w = tid; w < R2 * CB; w += JB_PIPE_COMPUTE_THREADS) {
-            int n2 = w / CB, b = w - n2 * CB;
-            cd v[R1];
-            static_for<0, R1>([&](auto nn) {
-                constexpr int n1 = nn;
-                int p = R2 * n1 + n2;
-                v[n1] = (p >= ci.vlo && p < ci.vhi) ? tile[p * CB + b] : cd_make(0.0, 0.0);
-            });
-            dft<R1, -1>(v);
-            cd po = p1w1, pe = p1w2;  // W^{n2 k1} for odd / even k1
-            static_for<0, R1>([&](auto kk) {
-                constexpr int k1 = kk;
-                cd y = v[k1];
-                if constexpr (k1 > 0) {
-                    if constexpr (k1 & 1) { y = cd_mul(y, po); if constexpr (k1 + 2 < R1) po = cd_mul(po, p1w2); }
-                    else { y = cd_mul(y, pe); if constexpr (k1 + 2 < R1) pe = cd_mul(pe, p1w2); }
-                }
-                tile[(k1 * R2 + n2) * CB + b] = y;
-            });
-        }
-        jb_bar_compute();
-        // pass 2: forward radix-R2, spectrum multiply, inverse radix-R2, in place
-        for (int w = tid; w < R1 * CB; w += JB_PIPE_COMPUTE_THREADS) {
-            int k1 = w / CB, b = w - k1 * CB;
-            cd u[R2];
-            cd* col = tile + (size_t)(k1 * R2) * CB + b;
-            static_for<0, R2>([&](auto nn) { constexpr int n2 = nn; u[n2] = col[n2 * CB]; });
-            dft<R2, -1>(u);
-            static_for<0, R2>([&](auto kk) {
-                constexpr int k2 = kk;
-                cd kv = kh[(k2 * R1 + k1) * CB + b];
-                u[k2] = ADJ ? cd_mulc(u[k2], kv) : cd_mul(u[k2], kv);
-            });
-            dft<R2, +1>(u);
-            cd po = p2w1, pe = p2w2;  // W^{-k1 n2} for odd / even n2
-            static_for<0, R2>([&](auto nn) {
-                constexpr int n2 = nn;
-                cd y = u[n2];
-                if constexpr (n2 > 0) {
-                    if constexpr (n2 & 1) { y = cd_mul(y, po); if constexpr (n2 + 2 < R2) po = cd_mul(po, p2w2); }
-                    else { y = cd_mul(y, pe); if constexpr (n2 + 2 < R2) pe = cd_mul(pe, p2w2); }
-                }
-                col[n2 * CB] = y;
-            });
-        }
-        jb_bar_compute();
-        // pass B: inverse radix-R1; the stage is released as soon as its last read is in registers
-        constexpr int NB = (R2 * CB + JB_PIPE_COMPUTE_THREADS - 1) / JB_PIPE_COMPUTE_THREADS;
-        static_assert(NB == 1, "pass B assumes one item per thread (R2*CB <= compute threads)");
-        {
-            const int w = tid;
-            const bool act = w < R2 * CB;
-            int n2 = w / CB, b = w - n2 * CB;
-            cd v[R1];
-            if (act) static_for<0, R1>([&](auto kk) { constexpr int k1 = kk; v[k1] = tile[(k1 * R2 + n2) * CB + b]; });
-#ifndef JB_EMU
-            jb_fence_proxy_async();
-            __syncwarp();
-            if ((tid & 31) == 0) jb_mbar_arrive(&bars[2 + s]);
-            if (tid == 0) {
-                long nxt = item + 2 * (long)gridDim.x;
-                if (nxt < nitems) {
-                    jb_mbar_wait<false>(&bars[2 + s], (it >> 1) & 1);
-                    issue_loads(nxt, s);
-                }
-            }
-#endif
-            if (act) {
-                dft<R1, +1>(v);
-                const int colg = ci.strip * CB + b;
-                cd* ob = out + ci.out_off + colg;
-                static_for<0, R1>([&](auto nn) {
-                    constexpr int n1 = nn;
-                    int p = R2 * n1 + n2;
-                    if (colg < PH && p >= ci.out_p0 && p < ci.out_p0 + ci.out_rows)
-                        ob[(size_t)(p - ci.out_p0) * PH] = v[n1];
-                });
-            }
-        }
-    }
 }

@@ -13,7 +13,8 @@
 //   adjoint R^T : k_rows_adj_in (r2c of cotangent rows) -> k_cols (conj K^) -> k_rows_adj_out
 //                 (c2r + crop + weights + overlap-add gather, summed over modules)
 // Linearity is exploited twice: (1) the sky-row transform of window column-block i is shared by
-// the (<=2) row-patches j that contain the row -- one FFT, stored twice with the row weight;
+// the (<=2) row-patches j that contain the row -- one FFT, stored ONCE per (row, i); the column pass
+// reads overlapping row windows of that buffer and applies the row weight itself;
 // (2) the spectra of all row-patches j (and modules t, in the adjoint) that land on one output
 // row are summed BEFORE the inverse row transform -- one c2r per (row, i) instead of one per
 // patch row.  Overlap-add is a deterministic gather; no atomics, no memset.
@@ -61,22 +62,17 @@ JB_D void jb_build_jlist(const JbGeom& g, int r0, int rpc, int shift, int len, i
 JB_D size_t jb_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // ------------------------------------------------------------------ forward: sky rows -> spectra
-// grid (ceil(N/rpc), S*E).  x:(S,E,N,N).  bufB:(S*E, n*n, w, PH) rows u0 of the UN-padded window.
+// grid (ceil(N/rpc), S*E).  x:(S,E,N,N).  rowsF:(S*E, n, N, PH): r2c of the column-weighted, zero-padded window
+// row of column block i -- stored once per (row, i); the row weight is applied by the column pass.
 template <class FP>
 JB_GLOBAL void k_rows_fwd(JbGeom g, const double* __restrict__ x, const double* __restrict__ wgt,
-                          const cd* __restrict__ tw_nk, cd* __restrict__ bufB, int rpc) {
+                          const cd* __restrict__ tw_nk, cd* __restrict__ rowsF, int rpc) {
     JB_SMEM(unsigned char, smraw);
     const int B = rpc * g.n;
     cd* sm = reinterpret_cast<cd*>(smraw);
-    int* jcnt = reinterpret_cast<int*>(smraw + jb_align16((size_t)B * FP::LS * sizeof(cd)));
-    int* jj = jcnt + rpc;
-    int* ju = jj + rpc * g.n;
     const int r0 = blockIdx.x * rpc, se = blockIdx.y;
-    jb_build_jlist(g, r0, rpc, g.hp, g.w, jcnt, jj, ju);
-    JB_SYNC();
     const double* xp = x + (size_t)se * g.N * g.N;
     const int n = g.n, N = g.N, m = g.m, w = g.w, hp = g.hp, PH = g.PH;
-    const size_t nn2 = (size_t)n * n;
     auto ld = [&](int b, int p) -> double {
         int rr = b / n, i = b - rr * n, r = r0 + rr;
         int q = p - m;
@@ -85,32 +81,23 @@ JB_GLOBAL void k_rows_fwd(JbGeom g, const double* __restrict__ x, const double* 
         return jb_ldg(xp + (size_t)r * N + c) * jb_ldg(wgt + q);
     };
     auto st = [&](int b, int k, cd X) {
-        int rr = b / n, i = b - rr * n;
-        for (int q = 0; q < jcnt[rr]; ++q) {
-            int j = jj[rr * n + q], u0 = ju[rr * n + q];
-            double wr = jb_ldg(wgt + u0);
-            bufB[(((size_t)se * nn2 + (size_t)i * n + j) * w + u0) * PH + k] = cd_scale(X, wr);
-        }
+        int rr = b / n, i = b - rr * n, r = r0 + rr;
+        if (r < N) rowsF[(((size_t)se * n + i) * N + r) * PH + k] = X;
     };
     rows_r2c<FP>(sm, tw_nk, B, ld, st);
 }
 
 // ---------------------------------------------------------- adjoint: cotangent rows -> spectra
-// grid (ceil(N/rpc), S*T*E).  gin:(S,T,E,N,N) (optionally * expo).  bufA:(STE, n*n, P, PH).
+// grid (ceil(N/rpc), S*T*E).  gin:(S,T,E,N,N) (optionally * expo).  rowsA:(STE, n, N, PH): r2c of the P-wide
+// window of cotangent row r for column block i, stored once per (row, i).
 template <class FP>
 JB_GLOBAL void k_rows_adj_in(JbGeom g, const double* __restrict__ gin, const double* __restrict__ expo,
-                             const cd* __restrict__ tw_nk, cd* __restrict__ bufA, int rpc) {
+                             const cd* __restrict__ tw_nk, cd* __restrict__ rowsA, int rpc) {
     JB_SMEM(unsigned char, smraw);
     const int B = rpc * g.n;
     cd* sm = reinterpret_cast<cd*>(smraw);
-    int* jcnt = reinterpret_cast<int*>(smraw + jb_align16((size_t)B * FP::LS * sizeof(cd)));
-    int* jj = jcnt + rpc;
-    int* ju = jj + rpc * g.n;
     const int r0 = blockIdx.x * rpc, ste = blockIdx.y;
-    jb_build_jlist(g, r0, rpc, g.hp + g.m, g.P, jcnt, jj, ju);
-    JB_SYNC();
     const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, P = g.P;
-    const size_t nn2 = (size_t)n * n;
     const double* gp = gin + (size_t)ste * N * N;
     const double* ep = expo ? expo + (size_t)(ste % (g.T * g.E)) * N * N : nullptr;
     auto ld = [&](int b, int p) -> double {
@@ -122,11 +109,8 @@ JB_GLOBAL void k_rows_adj_in(JbGeom g, const double* __restrict__ gin, const dou
         return v;
     };
     auto st = [&](int b, int k, cd X) {
-        int rr = b / n, i = b - rr * n;
-        for (int q = 0; q < jcnt[rr]; ++q) {
-            int j = jj[rr * n + q], u = ju[rr * n + q];
-            bufA[(((size_t)ste * nn2 + (size_t)i * n + j) * P + u) * PH + k] = X;
-        }
+        int rr = b / n, i = b - rr * n, r = r0 + rr;
+        if (r < N) rowsA[(((size_t)ste * n + i) * N + r) * PH + k] = X;
     };
     rows_r2c<FP>(sm, tw_nk, B, ld, st);
 }
@@ -134,47 +118,47 @@ JB_GLOBAL void k_rows_adj_in(JbGeom g, const double* __restrict__ gin, const dou
 // --------------------------------------------------------------------------- column pass
 // grid (nstrips, n*n, planes).  One CTA owns CB spectrum columns of one patch: forward column FFT,
 // multiply by the resident PSF spectrum (conj for the adjoint), inverse column FFT.
-//   forward : in  bufB rows p-m for p in [m, m+w)  (plane s*E+e)   out bufA rows p in [0,P)
-//   adjoint : in  bufA rows p in [0,P)                              out bufB rows p-m, p in [m,m+w)
-// Rows whose image row lies outside [0,N) were never written by the row kernels and are read as 0.
+//   forward : in  rowsF[s*E+e][i] rows offs[j]-hp + (p-m),  p in [m, m+w), times the row weight wgt[p-m]
+//             out bufA rows p in [0,P)
+//   adjoint : in  rowsA[plane][i] rows offs[j]-hp-m + p,    p in [0,P)
+//             out bufB rows p-m, p in [m, m+w)
+// Window rows outside the image [0,N) are zero (the overlapping windows of neighbouring patches read the same
+// stored rows: nothing is duplicated in HBM).
 // Khat layout per (t,e,patch): [strip][k2][k1][b]  -- exactly the register distribution after the
 // forward transform, so the load is perfectly coalesced and needs no index arithmetic.
 template <class FP, int CB, bool ADJ>
 JB_GLOBAL void k_cols(JbGeom g, const cd* __restrict__ in, cd* __restrict__ out,
-                      const cd* __restrict__ khat, const cd* __restrict__ tw_nk) {
+                      const cd* __restrict__ khat, const cd* __restrict__ tw_nk, const double* __restrict__ wgt) {
     JB_SMEM(cd, sm);
     constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2;
     const int strip = blockIdx.x, k = blockIdx.y, plane = blockIdx.z;
     const int n = g.n, N = g.N, m = g.m, w = g.w, hp = g.hp, PH = g.PH, P = g.P;
-    const int j = k % n;
+    const int j = k % n, i = k / n;
     const int TE = g.T * g.E;
     const int s = plane / TE, te = plane - s * TE, e = te % g.E;
     const size_t nn2 = (size_t)n * n;
     const int nstrips = gridDim.x;
     const int col0 = strip * CB;
-    // image-row validity of patch rows
-    int in_p0, in_rows, vlo, vhi, out_p0, out_rows;
-    size_t in_plane, out_plane = plane;
+    int in_p0, in_rows, row0, out_p0, out_rows;
+    size_t in_plane;
     if (!ADJ) {
         in_p0 = m; in_rows = w; out_p0 = 0; out_rows = P;
         in_plane = (size_t)s * g.E + e;
-        int lo = hp - g.offs[j], hi = N + hp - g.offs[j];  // valid u0 range
-        vlo = m + (lo > 0 ? lo : 0);
-        vhi = m + (hi < w ? hi : w);
+        row0 = g.offs[j] - hp;
     } else {
         in_p0 = 0; in_rows = P; out_p0 = m; out_rows = w;
         in_plane = plane;
-        int lo = hp + m - g.offs[j], hi = N + hp + m - g.offs[j];
-        vlo = lo > 0 ? lo : 0;
-        vhi = hi < P ? hi : P;
+        row0 = g.offs[j] - hp - m;
     }
-    const cd* ib = in + ((in_plane * nn2 + k) * in_rows) * PH;
-    cd* ob = out + ((out_plane * nn2 + k) * out_rows) * PH;
+    const cd* ib = in + ((in_plane * n + i) * (size_t)N) * PH;
+    cd* ob = out + (((size_t)plane * nn2 + k) * out_rows) * PH;
     const cd* kb = khat + (((size_t)te * nn2 + k) * nstrips + strip) * ((size_t)L * CB);
     auto ld = [&](int p, int b) -> cd {
-        int col = col0 + b;
-        if (col >= PH || p < vlo || p >= vhi) return cd_make(0.0, 0.0);
-        return ib[(size_t)(p - in_p0) * PH + col];
+        int col = col0 + b, u = p - in_p0, r = row0 + u;
+        if (col >= PH || u < 0 || u >= in_rows || r < 0 || r >= N) return cd_make(0.0, 0.0);
+        cd v = ib[(size_t)r * PH + col];
+        if (!ADJ) v = cd_scale(v, jb_ldg(wgt + u));
+        return v;
     };
     auto mid = [&](int k1, int k2, int b, cd X) -> cd {
         cd kv = jb_ld_stream(kb + ((size_t)(k2 * R1 + k1)) * CB + b);

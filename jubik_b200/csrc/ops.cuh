@@ -18,10 +18,10 @@ struct JbFftOps {
     cudaError_t (*rows_adj_in)(const JbGeom&, const double* gin, const double* expo, const cd* tw_nk, cd* bufA,
                                int planes, int rpc, int threads, int fast, jb_stream_t);
     cudaError_t (*cols)(const JbGeom&, bool adj, const cd* in, cd* out, const cd* khat, const cd* tw_nk,
-                        int planes, int threads, jb_stream_t);
-    // twa/twb: tw_nk/unused (pipe 1) or the stage-1/stage-2 tables tw1/tw2 (pipe 2)
+                        const double* wgt, int planes, int threads, jb_stream_t);
+    // three-stage TMA pipeline (pipe == 2): twa/twb = stage-1/stage-2 twiddle tables
     cudaError_t (*cols_pipe)(const JbGeom&, bool adj, const JbTileSrc& src, cd* out, const cd* khat, const cd* twa,
-                             const cd* twb, int planes, int ctas, jb_stream_t);
+                             const cd* twb, const double* wgt, int planes, int ctas, jb_stream_t);
     cudaError_t (*rows_out)(const JbGeom&, const cd* bufA, const cd* tw_kn, const JbEpi&, int planes, int rpc,
                             int threads, int fast, jb_stream_t);
     cudaError_t (*rows_adj_out)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw_kn, double* grad,
@@ -39,21 +39,17 @@ inline size_t jb_al16(size_t x) { return (x + 15) & ~(size_t)15; }
 template <class FP, int CB, int PIPE, class F3>
 struct JbOpsImpl {
     static cudaError_t cols_pipe(const JbGeom& g, bool adj, const JbTileSrc& src, cd* out, const cd* khat,
-                                 const cd* twa, const cd* twb, int planes, int ctas, jb_stream_t st) {
+                                 const cd* twa, const cd* twb, const double* wgt, int planes, int ctas, jb_stream_t st) {
         if constexpr (PIPE == 2) {
-            size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd) + 32 + 2 * sizeof(JbColInfo) + 32;
+            size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd) + 32 +
+                          2 * sizeof(JbColInfo) + (size_t)g.w * sizeof(double) + 32;
             if (adj) return jb_launch(k_cols3_pipe<F3, CB, true>, dim3(ctas), dim3(JB_C3_THREADS), smem, st, src, g,
-                                      out, khat, twa, twb, planes);
+                                      out, khat, twa, twb, wgt, planes);
             return jb_launch(k_cols3_pipe<F3, CB, false>, dim3(ctas), dim3(JB_C3_THREADS), smem, st, src, g, out,
-                             khat, twa, twb, planes);
-        } else if constexpr (PIPE == 1 && FP::R2 > 1) {
-            size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + 64;
-            if (adj) return jb_launch(k_cols_pipe<FP, CB, true>, dim3(ctas), dim3(JB_PIPE_THREADS), smem, st, src, g,
-                                      out, khat, twa, planes);
-            return jb_launch(k_cols_pipe<FP, CB, false>, dim3(ctas), dim3(JB_PIPE_THREADS), smem, st, src, g, out,
-                             khat, twa, planes);
+                             khat, twa, twb, wgt, planes);
         } else {
-            (void)g; (void)adj; (void)src; (void)out; (void)khat; (void)twa; (void)twb; (void)planes; (void)ctas; (void)st;
+            (void)g; (void)adj; (void)src; (void)out; (void)khat; (void)twa; (void)twb; (void)wgt; (void)planes;
+            (void)ctas; (void)st;
             return (cudaError_t)1;
         }
     }
@@ -61,9 +57,9 @@ struct JbOpsImpl {
         return jb_al16(sizeof(int) * rpc) + (sizeof(long long) + sizeof(double)) * (size_t)rpc * JB_MAXQ + 16;
     }
     static size_t smem_rows_in(const JbGeom& g, int rpc, int fast) {
+        (void)fast;
         size_t B = (size_t)rpc * g.n;
-        if (fast) return jb_al16(B * FP::LS * sizeof(cd)) + rowtab_bytes(rpc);
-        return jb_al16(B * FP::LS * sizeof(cd)) + sizeof(int) * (rpc + 2 * (size_t)rpc * g.n) + 16;
+        return jb_al16(B * FP::LS * sizeof(cd)) + 16;
     }
     static cudaError_t rows_fwd(const JbGeom& g, const double* x, const double* wgt, const cd* tw_nk, cd* bufB,
                                 int planes, int rpc, int threads, int fast, jb_stream_t st) {
@@ -85,11 +81,11 @@ struct JbOpsImpl {
                          bufA, rpc);
     }
     static cudaError_t cols(const JbGeom& g, bool adj, const cd* in, cd* out, const cd* khat, const cd* tw_nk,
-                            int planes, int threads, jb_stream_t st) {
+                            const double* wgt, int planes, int threads, jb_stream_t st) {
         dim3 grid(jb_cdiv(g.PH, CB), g.n * g.n, planes);
         size_t smem = (FP::R2 == 1) ? 16 : (size_t)FP::L * CB * sizeof(cd);
-        if (adj) return jb_launch(k_cols<FP, CB, true>, grid, dim3(threads), smem, st, g, in, out, khat, tw_nk);
-        return jb_launch(k_cols<FP, CB, false>, grid, dim3(threads), smem, st, g, in, out, khat, tw_nk);
+        if (adj) return jb_launch(k_cols<FP, CB, true>, grid, dim3(threads), smem, st, g, in, out, khat, tw_nk, wgt);
+        return jb_launch(k_cols<FP, CB, false>, grid, dim3(threads), smem, st, g, in, out, khat, tw_nk, wgt);
     }
     static cudaError_t rows_out(const JbGeom& g, const cd* bufA, const cd* tw_kn, const JbEpi& ep, int planes,
                                 int rpc, int threads, int fast, jb_stream_t st) {
@@ -135,7 +131,7 @@ struct JbOpsImpl {
         return jb_launch(k_prep_cols<FP, CB>, grid, dim3(threads), smem, st, g, scratch, sums, twa, khat);
     }
     static const JbFftOps* table() {
-        static const JbFftOps t = {FP::L, FP::R1, FP::R2, CB, FP::LS, (FP::R2 > 1) ? PIPE : 0, F3::R1, F3::R2, F3::R3,
+        static const JbFftOps t = {FP::L, FP::R1, FP::R2, CB, FP::LS, (FP::R2 > 1 && PIPE == 2) ? 2 : 0, F3::R1, F3::R2, F3::R3,
                                    rows_fwd, rows_adj_in, cols, cols_pipe,
                                    rows_out, rows_adj_out, prep_rows, prep_cols};
         return &t;

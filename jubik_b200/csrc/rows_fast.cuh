@@ -101,19 +101,31 @@ JB_D void jb_rowtab_build(const JbGeom& g, const JbRowTab& t, int r0, int rpc, i
     }
 }
 
+// store the Hermitian half spectrum held as u[k2] = X[k1 + R1*k2] to one contiguous row (k = 0..L/2)
+template <class FP>
+JB_D void jb_store_half_row(cd* row, const cd (&u)[FP::R2], int k1) {
+    constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2;
+    const bool mirror_ok = (k1 != 0) && (2 * k1 != R1);
+    cd* pd = row + k1;        // direct:  + R1*k2
+    cd* pm = row + (L - k1);  // mirror:  - R1*k2
+    static_for<0, R2>([&](auto kk) {
+        constexpr int k2 = kk;
+        if (jb_spec_direct<FP, k2>(k1)) pd[R1 * k2] = u[k2];
+        else if (mirror_ok) pm[-R1 * k2] = cd_conj(u[k2]);
+    });
+}
+
 // ------------------------------------------------------------ forward: sky rows -> spectra (r2c)
-// grid (ceil(N/rpc), S*E); dyn smem = B*LS*16 + rowtab.
+// grid (ceil(N/rpc), S*E); dyn smem = B*LS*16.  rowsF:(S*E, n, N, PH), one row per (image row, column block).
 template <class FP>
 JB_GLOBAL void JB_LB(256, 2) k_rows_fwd2(JbGeom g, const double* __restrict__ x, const double* __restrict__ wgt,
-                           const cd* __restrict__ tw_nk, cd* __restrict__ bufB, int rpc) {
-    constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
+                           const cd* __restrict__ tw_nk, cd* __restrict__ rowsF, int rpc) {
+    constexpr int R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
     JB_SMEM(unsigned char, smraw);
     const int n = g.n, N = g.N, m = g.m, w = g.w, hp = g.hp, PH = g.PH;
     const int B = rpc * n;
     cd* sm = reinterpret_cast<cd*>(smraw);
-    JbRowTab tab = jb_rowtab_at(smraw + jb_align16((size_t)B * LS * sizeof(cd)), rpc);
     const int r0 = blockIdx.x * rpc, se = blockIdx.y;
-    jb_rowtab_build(g, tab, r0, rpc, hp, w, wgt);
     const double* xp = x + (size_t)se * N * N;
     for (int it = jb_tid(); it < B * R2; it += jb_nthr()) {
         int b = it / R2, n2 = it - b * R2;
@@ -132,45 +144,26 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_fwd2(JbGeom g, const double* __restrict__ x,
         jb_r2c_pass1<FP>(xv, sm + (size_t)b * LS + n2, jb_ldg(tw_nk + R2 + n2), jb_ldg(tw_nk + 2 * R2 + n2));
     }
     JB_SYNC();
-    const size_t plane = (size_t)se * n * n * w * PH;
     for (int it = jb_tid(); it < B * H1; it += jb_nthr()) {
         int b = it / H1, k1 = it - b * H1;
-        int rr = b / n, i = b - rr * n;
+        int rr = b / n, i = b - rr * n, r = r0 + rr;
         cd u[R2];
         jb_r2c_pass2<FP>(sm + (size_t)b * LS + k1 * R2P, u);
-        const bool mirror_ok = (k1 != 0) && (2 * k1 != R1);
-        const int cnt = tab.cnt[rr];
-        cd* base = bufB + plane + (size_t)i * n * w * PH;
-        static_for<0, JB_MAXQ>([&](auto qq) {
-            constexpr int q = qq;
-            if (q < cnt) {
-                cd* pd = base + tab.off[rr * JB_MAXQ + q] + k1;       // direct:  + R1*k2
-                cd* pm = base + tab.off[rr * JB_MAXQ + q] + (L - k1); // mirror:  - R1*k2
-                const double wr = tab.wr[rr * JB_MAXQ + q];
-                static_for<0, R2>([&](auto kk) {
-                    constexpr int k2 = kk;
-                    cd v = cd_scale(u[k2], wr);
-                    if (jb_spec_direct<FP, k2>(k1)) pd[R1 * k2] = v;
-                    else if (mirror_ok) pm[-R1 * k2] = cd_conj(v);
-                });
-            }
-        });
+        if (r < N) jb_store_half_row<FP>(rowsF + (((size_t)se * n + i) * N + r) * PH, u, k1);
     }
 }
 
 // ------------------------------------------------------ adjoint: cotangent rows -> spectra (r2c)
-// grid (ceil(N/rpc), S*T*E)
+// grid (ceil(N/rpc), S*T*E).  rowsA:(STE, n, N, PH)
 template <class FP>
 JB_GLOBAL void JB_LB(256, 2) k_rows_adj_in2(JbGeom g, const double* __restrict__ gin, const double* __restrict__ expo,
-                              const cd* __restrict__ tw_nk, cd* __restrict__ bufA, int rpc) {
-    constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
+                              const cd* __restrict__ tw_nk, cd* __restrict__ rowsA, int rpc) {
+    constexpr int R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
     JB_SMEM(unsigned char, smraw);
     const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, P = g.P;
     const int B = rpc * n;
     cd* sm = reinterpret_cast<cd*>(smraw);
-    JbRowTab tab = jb_rowtab_at(smraw + jb_align16((size_t)B * LS * sizeof(cd)), rpc);
     const int r0 = blockIdx.x * rpc, ste = blockIdx.y;
-    jb_rowtab_build(g, tab, r0, rpc, hp + m, P, nullptr);
     const double* gp = gin + (size_t)ste * N * N;
     const double* ep = expo ? expo + (size_t)(ste % (g.T * g.E)) * N * N : nullptr;
     for (int it = jb_tid(); it < B * R2; it += jb_nthr()) {
@@ -192,27 +185,12 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_adj_in2(JbGeom g, const double* __restrict__
         jb_r2c_pass1<FP>(xv, sm + (size_t)b * LS + n2, jb_ldg(tw_nk + R2 + n2), jb_ldg(tw_nk + 2 * R2 + n2));
     }
     JB_SYNC();
-    const size_t plane = (size_t)ste * n * n * P * PH;
     for (int it = jb_tid(); it < B * H1; it += jb_nthr()) {
         int b = it / H1, k1 = it - b * H1;
-        int rr = b / n, i = b - rr * n;
+        int rr = b / n, i = b - rr * n, r = r0 + rr;
         cd u[R2];
         jb_r2c_pass2<FP>(sm + (size_t)b * LS + k1 * R2P, u);
-        const bool mirror_ok = (k1 != 0) && (2 * k1 != R1);
-        const int cnt = tab.cnt[rr];
-        cd* base = bufA + plane + (size_t)i * n * P * PH;
-        static_for<0, JB_MAXQ>([&](auto qq) {
-            constexpr int q = qq;
-            if (q < cnt) {
-                cd* pd = base + tab.off[rr * JB_MAXQ + q] + k1;
-                cd* pm = base + tab.off[rr * JB_MAXQ + q] + (L - k1);
-                static_for<0, R2>([&](auto kk) {
-                    constexpr int k2 = kk;
-                    if (jb_spec_direct<FP, k2>(k1)) pd[R1 * k2] = u[k2];
-                    else if (mirror_ok) pm[-R1 * k2] = cd_conj(u[k2]);
-                });
-            }
-        });
+        if (r < N) jb_store_half_row<FP>(rowsA + (((size_t)ste * n + i) * N + r) * PH, u, k1);
     }
 }
 
