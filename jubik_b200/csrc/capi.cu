@@ -110,6 +110,7 @@ struct jubik_plan {
     int nblk_out = 0;
     int use_pipe = 0, n_sm = 1;
     int split_epi = 1, nblk_epi = 1;  // Poisson/metric epilogue as a separate elementwise kernel
+    int rows_pipe_out = 0, rows_pipe_adj = 0, qmax = 0;  // persistent bulk-copy-fed c2r kernels (rows_pipe.cuh)
     int fast_rows = 0;         // rows_fast.cuh kernels (two-pass length and <= JB_MAXQ row-patches per image row)
     JbTileSrc src_fwd, src_adj;  // TMA views of bufB / bufA for the pipelined column pass
     // per-kernel timing (jubik_poisson_profile): events recorded after every launch while enabled
@@ -323,6 +324,7 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
             mx = c1 > mx ? c1 : mx;
         }
         p->fast_rows = (o->R2 > 1) && mx <= JB_MAXQ && !getenv("JUBIK_B200_ROWS_V1");
+        p->qmax = mx;
     }
     // ---- pipelined column pass: TMA views of the two spectrum workspaces
     p->use_pipe = getenv("JUBIK_B200_COLS_V1") ? 0 : o->pipe;
@@ -344,6 +346,11 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
             h2d(p->tw1, a.data(), L * sizeof(cd), st) || h2d(p->tw2, b.data(), M * sizeof(cd), st) || stream_sync(st)) {
             cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "uploading three-stage twiddles failed");
         }
+    }
+    if (p->use_pipe && p->fast_rows && !getenv("JUBIK_B200_ROWS_V2")) {
+        const size_t smem_max = 227 * 1024;
+        p->rows_pipe_out = o->rows_out_pipe_smem(g, p->qmax) <= smem_max;
+        p->rows_pipe_adj = o->rows_adj_out_pipe_smem(g, p->qmax) <= smem_max;
     }
     if (p->use_pipe) {
         std::string err;
@@ -442,7 +449,11 @@ static int run_forward(jubik_plan* p, const double* x, int S, const JbEpi& ep, j
     } else {
         JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, p->wgt, S * g.T * g.E, p->thr_cols, st));
     }
-    JB_LAUNCHED(p, o->rows_out(g, p->bufA, p->tw_kn, ep, S * g.T * g.E, p->rpc_out, p->thr_rows, p->fast_rows, st));
+    if (p->rows_pipe_out && ep.mode != JB_EPI_POISSON) {
+        JB_LAUNCHED(p, o->rows_out_pipe(g, p->bufA, p->tw_kn, ep, S * g.T * g.E, p->qmax, p->n_sm, st));
+    } else {
+        JB_LAUNCHED(p, o->rows_out(g, p->bufA, p->tw_kn, ep, S * g.T * g.E, p->rpc_out, p->thr_rows, p->fast_rows, st));
+    }
     return 0;
 }
 
@@ -456,7 +467,11 @@ static int run_adjoint(jubik_plan* p, const double* gin, const double* expo, int
     } else {
         JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, p->wgt, S * g.T * g.E, p->thr_cols, st));
     }
-    JB_LAUNCHED(p, o->rows_adj_out(g, p->bufB, p->wgt, p->tw_kn, out, S * g.E, p->rpc_out, p->thr_rows, p->fast_rows, st));
+    if (p->rows_pipe_adj) {
+        JB_LAUNCHED(p, o->rows_adj_out_pipe(g, p->bufB, p->wgt, p->tw_kn, out, S * g.E, p->qmax, p->n_sm, st));
+    } else {
+        JB_LAUNCHED(p, o->rows_adj_out(g, p->bufB, p->wgt, p->tw_kn, out, S * g.E, p->rpc_out, p->thr_rows, p->fast_rows, st));
+    }
     return 0;
 }
 

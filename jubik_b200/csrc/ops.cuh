@@ -6,6 +6,7 @@
 #include "rows_fast.cuh"
 #include "cols_pipe.cuh"
 #include "cols3.cuh"
+#include "rows_pipe.cuh"
 
 struct JbFftOps {
     int L, R1, R2, CB;
@@ -26,6 +27,13 @@ struct JbFftOps {
                             int threads, int fast, jb_stream_t);
     cudaError_t (*rows_adj_out)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw_kn, double* grad,
                                 int planes, int rpc, int threads, int fast, jb_stream_t);
+    // persistent bulk-copy-fed c2r kernels (rows_pipe.cuh); *_smem returns the dynamic shared memory they need
+    size_t (*rows_out_pipe_smem)(const JbGeom&, int Q);
+    size_t (*rows_adj_out_pipe_smem)(const JbGeom&, int Q);
+    cudaError_t (*rows_out_pipe)(const JbGeom&, const cd* bufA, const cd* tw_kn, const JbEpi&, int planes, int Q,
+                                 int ctas, jb_stream_t);
+    cudaError_t (*rows_adj_out_pipe)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw_kn, double* grad,
+                                     int planes_se, int Q, int ctas, jb_stream_t);
     cudaError_t (*prep_rows)(const JbGeom&, const JbKsrc&, const cd* tw_nk, cd* scratch, int rpc, int threads,
                              jb_stream_t);
     // layout 0: K^ in the two-pass register order (tw = tw_nk); layout 2: three-stage order (twa/twb = tw1/tw2)
@@ -112,6 +120,38 @@ struct JbOpsImpl {
         size_t smem = common + sizeof(int) * (rpc + 2 * (size_t)rpc * g.n) + 16;
         return jb_launch(k_rows_adj_out<FP>, grid, dim3(threads), smem, st, g, bufB, wgt, tw_kn, grad, rpc);
     }
+    static size_t al128(size_t x) { return (x + 127) & ~(size_t)127; }
+    static size_t rows_out_pipe_smem(const JbGeom& g, int Q) {
+        if (FP::R2 == 1) return (size_t)1 << 30;
+        return al128(2 * (size_t)g.n * Q * g.PH * sizeof(cd)) + al128((size_t)g.n * FP::LS * sizeof(cd)) +
+               al128((size_t)g.n * g.P * sizeof(double)) + al128(JB_RP_THREADS * sizeof(double)) + 64 +
+               2 * sizeof(JbRowInfo) + 64;
+    }
+    static size_t rows_adj_out_pipe_smem(const JbGeom& g, int Q) {
+        if (FP::R2 == 1 || g.n * FP::H1 > JB_RP_THREADS) return (size_t)1 << 30;
+        return al128(2 * (size_t)g.n * Q * g.PH * sizeof(cd)) + al128((size_t)g.n * FP::LS * sizeof(cd)) +
+               al128((size_t)g.n * g.w * sizeof(double)) + 64 + 2 * sizeof(JbRowInfo) + 64;
+    }
+    static cudaError_t rows_out_pipe(const JbGeom& g, const cd* bufA, const cd* tw_kn, const JbEpi& ep, int planes,
+                                     int Q, int ctas, jb_stream_t st) {
+        if constexpr (FP::R2 > 1) {
+            return jb_launch(k_rows_out3<FP>, dim3(ctas), dim3(JB_RP_THREADS), rows_out_pipe_smem(g, Q), st, g, bufA,
+                             tw_kn, ep, planes, Q);
+        } else {
+            (void)g; (void)bufA; (void)tw_kn; (void)ep; (void)planes; (void)Q; (void)ctas; (void)st;
+            return (cudaError_t)1;
+        }
+    }
+    static cudaError_t rows_adj_out_pipe(const JbGeom& g, const cd* bufB, const double* wgt, const cd* tw_kn,
+                                         double* grad, int planes_se, int Q, int ctas, jb_stream_t st) {
+        if constexpr (FP::R2 > 1) {
+            return jb_launch(k_rows_adj_out3<FP>, dim3(ctas), dim3(JB_RP_THREADS), rows_adj_out_pipe_smem(g, Q), st, g,
+                             bufB, wgt, tw_kn, grad, planes_se, Q);
+        } else {
+            (void)g; (void)bufB; (void)wgt; (void)tw_kn; (void)grad; (void)planes_se; (void)Q; (void)ctas; (void)st;
+            return (cudaError_t)1;
+        }
+    }
     static cudaError_t prep_rows(const JbGeom& g, const JbKsrc& ks, const cd* tw_nk, cd* scratch, int rpc,
                                  int threads, jb_stream_t st) {
         size_t smem = jb_al16((size_t)rpc * FP::LS * sizeof(cd)) + 16;
@@ -133,7 +173,8 @@ struct JbOpsImpl {
     static const JbFftOps* table() {
         static const JbFftOps t = {FP::L, FP::R1, FP::R2, CB, FP::LS, (FP::R2 > 1 && PIPE == 2) ? 2 : 0, F3::R1, F3::R2, F3::R3,
                                    rows_fwd, rows_adj_in, cols, cols_pipe,
-                                   rows_out, rows_adj_out, prep_rows, prep_cols};
+                                   rows_out, rows_adj_out, rows_out_pipe_smem, rows_adj_out_pipe_smem, rows_out_pipe,
+                                   rows_adj_out_pipe, prep_rows, prep_cols};
         return &t;
     }
 };
