@@ -125,12 +125,12 @@ struct JbOpsImpl {
         if (FP::R2 == 1) return (size_t)1 << 30;
         return al128(2 * (size_t)g.n * Q * g.PH * sizeof(cd)) + al128((size_t)g.n * FP::LS * sizeof(cd)) +
                al128((size_t)g.n * g.P * sizeof(double)) + al128(JB_RP_THREADS * sizeof(double)) + 64 +
-               2 * sizeof(JbRowInfo) + 64;
+               2 * sizeof(JbRowInfo) + 2 * (size_t)g.N + 64;
     }
     static size_t rows_adj_out_pipe_smem(const JbGeom& g, int Q) {
         if (FP::R2 == 1 || g.n * FP::H1 > JB_RP_THREADS) return (size_t)1 << 30;
         return al128(2 * (size_t)g.n * Q * g.PH * sizeof(cd)) + al128((size_t)g.n * FP::LS * sizeof(cd)) +
-               al128((size_t)g.n * g.w * sizeof(double)) + 64 + 2 * sizeof(JbRowInfo) + 64;
+               al128((size_t)g.n * g.w * sizeof(double)) + 64 + 2 * sizeof(JbRowInfo) + 2 * (size_t)g.N + 64;
     }
     static cudaError_t rows_out_pipe(const JbGeom& g, const cd* bufA, const cd* tw_kn, const JbEpi& ep, int planes,
                                      int Q, int ctas, jb_stream_t st) {

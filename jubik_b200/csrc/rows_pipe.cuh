@@ -20,6 +20,20 @@ struct JbRowInfo {  // per ring stage: which spectrum rows were staged
 
 JB_D size_t jb_al128(size_t x) { return (x + 127) & ~(size_t)127; }
 
+// column blocks i whose window of `len` samples starting at offs[i]-shift covers image column c form a
+// contiguous range [lo, hi] (offs is non-decreasing); the same for every image row => tabulated once per CTA
+JB_D void jb_col_ranges(const JbGeom& g, int shift, int len, unsigned char* lo, unsigned char* hi) {
+    for (int c = threadIdx.x; c < g.N; c += JB_RP_THREADS) {
+        int l = g.n, h = -1;
+        for (int i = 0; i < g.n; ++i) {
+            int p = c + shift - g.offs[i];
+            if (p >= 0 && p < len) { if (i < l) l = i; h = i; }
+        }
+        lo[c] = (unsigned char)l;
+        hi[c] = (unsigned char)(h + 1);   // exclusive
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // forward: spectra -> image rows (+ epilogue).  grid = #SMs (persistent), block = JB_RP_THREADS.
 // item = plane*N + r.  bufA:(STE, n*n, P, PH).  Q = max row-patches per image row (<= JB_MAXQ).
@@ -43,9 +57,13 @@ k_rows_out3(JbGeom g, const cd* __restrict__ bufA, const cd* __restrict__ tw_kn,
     uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off);  // full[2], done[2]
     off += 64;
     JbRowInfo* info = reinterpret_cast<JbRowInfo*>(smraw + off);
+    off += 2 * sizeof(JbRowInfo);
+    unsigned char* clo = smraw + off;
+    unsigned char* chi = clo + N;
     const long nitems = (long)planes * N;
     const size_t nn2 = (size_t)n * n;
     const int shift = hp + m;
+    jb_col_ranges(g, shift, P, clo, chi);
 
     // stage the spectrum rows of `item` into ring slot s_ (called by all lanes of warp 0)
     auto stage_rows = [&](long item_, int s_) {
@@ -156,10 +174,8 @@ k_rows_out3(JbGeom g, const cd* __restrict__ bufA, const cd* __restrict__ tw_kn,
         for (int c = tid; c < N; c += JB_RP_THREADS) {
             double conv = 0.0;
             const double* trow = tile + c + shift;
-            for (int i = 0; i < n; ++i) {
-                int p = c + shift - g.offs[i];
-                if (p >= 0 && p < P) conv += trow[(size_t)i * P - g.offs[i]];
-            }
+            const int i1 = chi[c];
+            for (int i = clo[c]; i < i1; ++i) conv += trow[i * P - g.offs[i]];
             if (ep.mode == JB_EPI_PSF) {
                 ep.out[orow + c] = conv;
             } else {
@@ -211,6 +227,10 @@ k_rows_adj_out3(JbGeom g, const cd* __restrict__ bufB, const double* __restrict_
     uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off);
     off += 64;
     JbRowInfo* info = reinterpret_cast<JbRowInfo*>(smraw + off);
+    off += 2 * sizeof(JbRowInfo);
+    unsigned char* clo = smraw + off;
+    unsigned char* chi = clo + N;
+    jb_col_ranges(g, hp, w, clo, chi);
     const long nitems = (long)planes_se * N;
     const long nsteps_total = nitems * T;  // global step id = item*T + t ; this CTA owns items blockIdx.x + k*gridDim.x
     (void)nsteps_total;
@@ -341,10 +361,8 @@ k_rows_adj_out3(JbGeom g, const cd* __restrict__ bufB, const double* __restrict_
         for (int c = tid; c < N; c += JB_RP_THREADS) {
             double acc = 0.0;
             const double* trow = tile + c + hp;
-            for (int i = 0; i < n; ++i) {
-                int v = c + hp - g.offs[i];
-                if (v >= 0 && v < w) acc += trow[(size_t)i * w - g.offs[i]];
-            }
+            const int i1 = chi[c];
+            for (int i = clo[c]; i < i1; ++i) acc += trow[i * w - g.offs[i]];
             grow[c] = acc;
         }
     }

@@ -30,8 +30,9 @@ def test_emulated_kernels_match_reference_golden(golden_dir, name):
 
 
 @pytest.mark.parametrize("case", [
-    (120, 4, 10, 2, 2, 2, False, True),   # P=80 -> padded single... L=160 two-pass, compact PSF, S/T/E batching
-    (126, 4, 18, 1, 1, 1, True, False),   # N % n != 0, P = 98 -> needs compact? full support => must fail cleanly
+    (64, 4, 6, 2, 2, 2, False, True),     # P=44 -> padded L=160 (two-pass rows, three-stage TMA-pipelined columns in
+                                          # their emulated form), compact PSF, S/T/E batching
+    (62, 4, 9, 1, 1, 1, True, False),     # N % n != 0, P = 48 is not compiled and the PSF is wider than the margin => clean error
 ])
 def test_emulated_two_pass_fft_against_oracle(case):
     N, n, m, T, E, S, full, eff = case

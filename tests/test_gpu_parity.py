@@ -178,6 +178,7 @@ def test_full_size_chandra_adjointness_linearity_and_fd(torch_cuda):
     assert float(lin.abs().max()) / float(plan.psf(x).abs().max()) < 1e-12
     # Poisson data from the model itself, then FD of the energy along a random direction
     lam = plan.response(dev(torch, synth.sky(1, E, N, seed=5)))
+    torch.manual_seed(1234)
     d = torch.poisson(lam.clamp(min=0.0))[0]
     plan.set_data(d)
     e0, gr = plan.energy_and_grad(x)
@@ -187,7 +188,10 @@ def test_full_size_chandra_adjointness_linearity_and_fd(torch_cuda):
     em = plan.energy(x - eps * v)
     fd = float((ep - em).sum()) / (2 * eps)
     an = float(torch.vdot(gr.flatten(), v.flatten()))
-    assert abs(fd - an) / abs(an) < 1e-6
+    # the directional derivative along a random direction can be small by chance (E[lambda - d] = 0 near the
+    # truth), so the tolerance is relative to |g||v| as well as to |g.v|
+    scale = max(abs(an), 1e-4 * float(gr.norm() * v.norm()))
+    assert abs(fd - an) / scale < 1e-6
     # determinism: bitwise identical on repetition
     e1, gr1 = plan.energy_and_grad(x)
     assert torch.equal(e0, e1) and torch.equal(gr, gr1)
