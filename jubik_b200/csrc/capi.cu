@@ -117,6 +117,9 @@ struct jubik_plan {
     int prof_on = 0, prof_n = 0;
 #ifndef JB_EMU
     cudaEvent_t prof_ev[16] = {};
+    // host-buffer entry point: copy streams and per-energy-bin events (created on first use)
+    cudaStream_t st_in = nullptr, st_out = nullptr;
+    cudaEvent_t *ev_in = nullptr, *ev_c = nullptr, ev_start = nullptr;
 #endif
 };
 
@@ -147,6 +150,15 @@ int jubik_plan_destroy(jubik_plan* p) {
     dev_free(p->khat); dev_free(p->tw_nk); dev_free(p->tw_kn); dev_free(p->tw1); dev_free(p->tw2); dev_free(p->wgt); dev_free(p->expo);
     dev_free(p->data); dev_free(p->bufA); dev_free(p->bufB); dev_free(p->gbuf); dev_free(p->lbuf);
     dev_free(p->partial); dev_free(p->xdev); dev_free(p->gdev); dev_free(p->edev);
+#ifndef JB_EMU
+    if (p->st_in) {
+        for (int e = 0; e < p->g.E; ++e) { cudaEventDestroy(p->ev_in[e]); cudaEventDestroy(p->ev_c[e]); }
+        delete[] p->ev_in; delete[] p->ev_c;
+        cudaEventDestroy(p->ev_start);
+        cudaStreamDestroy(p->st_in); cudaStreamDestroy(p->st_out);
+    }
+    for (int i = 0; i < 16; ++i) if (p->prof_ev[i]) cudaEventDestroy(p->prof_ev[i]);
+#endif
     delete p;
     return JUBIK_OK;
 }
@@ -204,6 +216,7 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
     memset(&g, 0, sizeof(g));
     g.N = N; g.n = n; g.m = m; g.dx = dx; g.w = 2 * dx; g.hp = dx / 2; g.P = g.w + 2 * m;
     g.S = d->max_samples; g.T = d->n_modules; g.E = d->n_energy;
+    g.e0 = 0; g.Es = g.E;
     p->S_max = d->max_samples;
     // window starts with jax.lax.dynamic_slice clamping (convolve.py:55-57)
     {
@@ -440,39 +453,45 @@ static int check_call(jubik_plan* p, const void* a, const void* b, int S) {
 }
 
 // forward chain with the chosen epilogue
-static int run_forward(jubik_plan* p, const double* x, int S, const JbEpi& ep, jb_stream_t st) {
-    const JbGeom& g = p->g;
+// `g` may be a copy of p->g restricted to an energy-bin chunk (e0, Es)
+static int run_forward_g(jubik_plan* p, const JbGeom& g, const double* x, int S, const JbEpi& ep, jb_stream_t st) {
     const JbFftOps* o = p->ops;
-    JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.E, p->rpc_in, p->thr_rows, p->fast_rows, st));
+    JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.Es, p->rpc_in, p->thr_rows, p->fast_rows, st));
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, false, p->src_fwd, p->bufA, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.E, p->n_sm, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, false, p->src_fwd, p->bufA, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
     } else {
-        JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, p->wgt, S * g.T * g.E, p->thr_cols, st));
+        JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
     if (p->rows_pipe_out && ep.mode != JB_EPI_POISSON) {
-        JB_LAUNCHED(p, o->rows_out_pipe(g, p->bufA, p->tw_kn, ep, S * g.T * g.E, p->qmax, p->n_sm, st));
+        JB_LAUNCHED(p, o->rows_out_pipe(g, p->bufA, p->tw_kn, ep, S * g.T * g.Es, p->qmax, p->n_sm, st));
     } else {
-        JB_LAUNCHED(p, o->rows_out(g, p->bufA, p->tw_kn, ep, S * g.T * g.E, p->rpc_out, p->thr_rows, p->fast_rows, st));
+        JB_LAUNCHED(p, o->rows_out(g, p->bufA, p->tw_kn, ep, S * g.T * g.Es, p->rpc_out, p->thr_rows, p->fast_rows, st));
     }
     return 0;
 }
+static int run_forward(jubik_plan* p, const double* x, int S, const JbEpi& ep, jb_stream_t st) {
+    return run_forward_g(p, p->g, x, S, ep, st);
+}
 
 // adjoint chain; expo != nullptr multiplies the incoming cotangent by the effective exposure
-static int run_adjoint(jubik_plan* p, const double* gin, const double* expo, int S, double* out, jb_stream_t st) {
-    const JbGeom& g = p->g;
+static int run_adjoint_g(jubik_plan* p, const JbGeom& g, const double* gin, const double* expo, int S, double* out,
+                         jb_stream_t st) {
     const JbFftOps* o = p->ops;
-    JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.E, p->rpc_in, p->thr_rows, p->fast_rows, st));
+    JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.Es, p->rpc_in, p->thr_rows, p->fast_rows, st));
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, true, p->src_adj, p->bufB, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.E, p->n_sm, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, true, p->src_adj, p->bufB, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
     } else {
-        JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, p->wgt, S * g.T * g.E, p->thr_cols, st));
+        JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
     if (p->rows_pipe_adj) {
-        JB_LAUNCHED(p, o->rows_adj_out_pipe(g, p->bufB, p->wgt, p->tw_kn, out, S * g.E, p->qmax, p->n_sm, st));
+        JB_LAUNCHED(p, o->rows_adj_out_pipe(g, p->bufB, p->wgt, p->tw_kn, out, S * g.Es, p->qmax, p->n_sm, st));
     } else {
-        JB_LAUNCHED(p, o->rows_adj_out(g, p->bufB, p->wgt, p->tw_kn, out, S * g.E, p->rpc_out, p->thr_rows, p->fast_rows, st));
+        JB_LAUNCHED(p, o->rows_adj_out(g, p->bufB, p->wgt, p->tw_kn, out, S * g.Es, p->rpc_out, p->thr_rows, p->fast_rows, st));
     }
     return 0;
+}
+static int run_adjoint(jubik_plan* p, const double* gin, const double* expo, int S, double* out, jb_stream_t st) {
+    return run_adjoint_g(p, p->g, gin, expo, S, out, st);
 }
 
 int jubik_psf_apply(jubik_plan* p, const double* x, int S, double* out, void* stream_) {
@@ -512,7 +531,7 @@ int jubik_poisson_energy_and_grad(jubik_plan* p, const double* x, int S, double*
         ep.mode = JB_EPI_PSF; ep.out = p->gbuf;
         if (int rc = run_forward(p, x, S, ep, st)) return rc;
         JB_LAUNCHED(p, jb_launch(k_poisson_epi, dim3(p->nblk_epi, S * g.T * g.E), dim3(256), 256 * sizeof(double), st,
-                                 p->gbuf, (const double*)p->expo, (const double*)p->data, g.T * g.E, g.N * g.N, p->partial));
+                                 g, p->gbuf, (const double*)p->expo, (const double*)p->data, g.N * g.N, p->partial));
         JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
                                  (const double*)p->partial, g.T * g.E * p->nblk_epi, energy));
     } else {
@@ -605,8 +624,8 @@ int jubik_poisson_metric_apply(jubik_plan* p, const double* x, const double* v, 
     if (p->split_epi) {
         ep.mode = JB_EPI_PSF; ep.out = p->gbuf; ep.expo = nullptr;
         if (int rc = run_forward(p, v, S, ep, st)) return rc;
-        JB_LAUNCHED(p, jb_launch(k_metric_epi, dim3(p->nblk_epi, S * g.T * g.E), dim3(256), 0, st, p->gbuf,
-                                 (const double*)p->expo, (const double*)p->lbuf, g.T * g.E, g.N * g.N));
+        JB_LAUNCHED(p, jb_launch(k_metric_epi, dim3(p->nblk_epi, S * g.T * g.E), dim3(256), 0, st, g, p->gbuf,
+                                 (const double*)p->expo, (const double*)p->lbuf, g.N * g.N));
     } else {
         ep.mode = JB_EPI_METRIC; ep.out = p->gbuf; ep.lam = p->lbuf;
         if (int rc = run_forward(p, v, S, ep, st)) return rc;
@@ -618,13 +637,59 @@ int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, d
     jb_stream_t st = (jb_stream_t)stream_;
     if (int rc = check_call(p, xh, eh, S)) return rc;
     const JbGeom& g = p->g;
-    size_t bx = (size_t)p->S_max * g.E * g.N * g.N * sizeof(double);
+    const size_t npx = (size_t)g.N * g.N;
+    size_t bx = (size_t)p->S_max * g.E * npx * sizeof(double);
     if (!p->xdev) {
         if (alloc(p, (void**)&p->xdev, bx, "host-call staging x") || alloc(p, (void**)&p->gdev, bx, "host-call staging grad") ||
             alloc(p, (void**)&p->edev, p->S_max * sizeof(double), "host-call staging energy"))
             return JUBIK_ERR_ALLOC;
     }
-    size_t nx = (size_t)S * g.E * g.N * g.N * sizeof(double);
+    size_t nx = (size_t)S * g.E * npx * sizeof(double);
+#ifndef JB_EMU
+    // Energy bins are independent through the whole fused chain, so the call is pipelined per bin: the H2D copy
+    // of bin e+1 and the D2H copy of the gradient of bin e-1 overlap the kernels of bin e (three streams).
+    const bool chunked = gh && g.E > 1 && p->split_epi && p->has_expo && p->has_data && !getenv("JUBIK_B200_HOST_SERIAL");
+    if (chunked) {
+        if (!p->st_in) {
+            JB_CK(cudaStreamCreateWithFlags(&p->st_in, cudaStreamNonBlocking));
+            JB_CK(cudaStreamCreateWithFlags(&p->st_out, cudaStreamNonBlocking));
+            p->ev_in = new cudaEvent_t[g.E]; p->ev_c = new cudaEvent_t[g.E];
+            for (int e = 0; e < g.E; ++e) {
+                JB_CK(cudaEventCreateWithFlags(&p->ev_in[e], cudaEventDisableTiming));
+                JB_CK(cudaEventCreateWithFlags(&p->ev_c[e], cudaEventDisableTiming));
+            }
+            JB_CK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+        }
+        // the copy streams start after everything already queued on the caller's stream
+        JB_CK(cudaEventRecord(p->ev_start, st));
+        JB_CK(cudaStreamWaitEvent(p->st_in, p->ev_start, 0));
+        JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_start, 0));
+        const size_t pitch = (size_t)g.E * npx * sizeof(double), width = npx * sizeof(double);
+        for (int e = 0; e < g.E; ++e) {
+            JB_CK(cudaMemcpy2DAsync(p->xdev + e * npx, pitch, xh + e * npx, pitch, width, S, cudaMemcpyHostToDevice, p->st_in));
+            JB_CK(cudaEventRecord(p->ev_in[e], p->st_in));
+        }
+        for (int e = 0; e < g.E; ++e) {
+            JbGeom ge = g;
+            ge.e0 = e; ge.Es = 1;
+            JB_CK(cudaStreamWaitEvent(st, p->ev_in[e], 0));
+            JbEpi ep; memset(&ep, 0, sizeof(ep));
+            ep.mode = JB_EPI_PSF; ep.out = p->gbuf;
+            if (int rc = run_forward_g(p, ge, p->xdev, S, ep, st)) return rc;
+            JB_LAUNCHED(p, jb_launch(k_poisson_epi, dim3(p->nblk_epi, S * g.T), dim3(256), 256 * sizeof(double), st, ge,
+                                     p->gbuf, (const double*)p->expo, (const double*)p->data, (int)npx, p->partial));
+            if (int rc = run_adjoint_g(p, ge, p->gbuf, nullptr, S, p->gdev, st)) return rc;
+            JB_CK(cudaEventRecord(p->ev_c[e], st));
+            JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_c[e], 0));
+            JB_CK(cudaMemcpy2DAsync(gh + e * npx, pitch, p->gdev + e * npx, pitch, width, S, cudaMemcpyDeviceToHost, p->st_out));
+        }
+        JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
+                                 (const double*)p->partial, g.T * g.E * p->nblk_epi, p->edev));
+        if (d2h(eh, p->edev, S * sizeof(double), st)) return fail(JUBIK_ERR_CUDA, "D2H copy of energy failed");
+        if (stream_sync(st) || stream_sync(p->st_out)) return fail(JUBIK_ERR_CUDA, "stream synchronise failed");
+        return JUBIK_OK;
+    }
+#endif
     if (h2d(p->xdev, xh, nx, st)) return fail(JUBIK_ERR_CUDA, "H2D copy of x failed");
     if (int rc = jubik_poisson_energy_and_grad(p, p->xdev, S, p->edev, gh ? p->gdev : nullptr, stream_)) return rc;
     if (d2h(eh, p->edev, S * sizeof(double), st)) return fail(JUBIK_ERR_CUDA, "D2H copy of energy failed");

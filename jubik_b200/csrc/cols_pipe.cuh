@@ -95,17 +95,14 @@ JB_D JbColItem jb_col_item(const JbGeom& g, long item, int nstrips) {
     it.strip = (int)(item % nstrips);
     long r = item / nstrips;
     it.k = (int)(r % nn2);
-    it.plane = (int)(r / nn2);
+    int se;
+    jb_map_ste(g, (int)(r / nn2), it.plane, it.te, se);
     it.j = it.k % g.n;
     it.i = it.k / g.n;
-    const int TE = g.T * g.E;
-    const int s = it.plane / TE;
-    it.te = it.plane - s * TE;
-    const int e = it.te % g.E;
     int in_plane;
     if (!ADJ) {
         it.in_p0 = g.m; it.in_rows = g.w; it.out_p0 = 0; it.out_rows = g.P;
-        in_plane = s * g.E + e;
+        in_plane = se;
         it.row0 = g.offs[it.j] - g.hp;
     } else {
         it.in_p0 = 0; it.in_rows = g.P; it.out_p0 = g.m; it.out_rows = g.w;

@@ -30,8 +30,26 @@ struct JbGeom {
     int N, n, m, dx, w, hp, P;  // dx=int(N/n), w=2dx, hp=dx//2, P=w+2m  (convolve.py:43-51,104-105)
     int L, PH;                  // FFT length (>= P) and stored spectrum columns L/2+1
     int S, T, E;
+    int e0, Es;                 // energy-bin chunk processed by a launch: bins [e0, e0+Es) (whole range by default);
+                                // launches index planes over (S, T, Es) / (S, Es) and map to the true plane ids
     int offs[JB_MAXN];          // clamped window starts in the hp-padded frame (lax.dynamic_slice)
 };
+
+// launched plane index over (S, T, Es) -> ste = (s*T+t)*E+e, te = t*E+e, se = s*E+e
+JB_D void jb_map_ste(const JbGeom& g, int lp, int& ste, int& te, int& se) {
+    const int TEs = g.T * g.Es;
+    const int s = lp / TEs, r = lp - s * TEs;
+    const int t = r / g.Es, e = g.e0 + (r - t * g.Es);
+    ste = (s * g.T + t) * g.E + e;
+    te = t * g.E + e;
+    se = s * g.E + e;
+}
+// launched plane index over (S, Es) -> se (and s, e)
+JB_D int jb_map_se(const JbGeom& g, int lp, int& s, int& e) {
+    s = lp / g.Es;
+    e = g.e0 + (lp - s * g.Es);
+    return s * g.E + e;
+}
 
 enum { JB_EPI_PSF = 0, JB_EPI_RESP = 1, JB_EPI_POISSON = 2, JB_EPI_METRIC = 3 };
 
@@ -70,7 +88,8 @@ JB_GLOBAL void k_rows_fwd(JbGeom g, const double* __restrict__ x, const double* 
     JB_SMEM(unsigned char, smraw);
     const int B = rpc * g.n;
     cd* sm = reinterpret_cast<cd*>(smraw);
-    const int r0 = blockIdx.x * rpc, se = blockIdx.y;
+    int s_, e_;
+    const int r0 = blockIdx.x * rpc, se = jb_map_se(g, blockIdx.y, s_, e_);
     const double* xp = x + (size_t)se * g.N * g.N;
     const int n = g.n, N = g.N, m = g.m, w = g.w, hp = g.hp, PH = g.PH;
     auto ld = [&](int b, int p) -> double {
@@ -96,10 +115,12 @@ JB_GLOBAL void k_rows_adj_in(JbGeom g, const double* __restrict__ gin, const dou
     JB_SMEM(unsigned char, smraw);
     const int B = rpc * g.n;
     cd* sm = reinterpret_cast<cd*>(smraw);
-    const int r0 = blockIdx.x * rpc, ste = blockIdx.y;
+    int ste, te, se_;
+    jb_map_ste(g, blockIdx.y, ste, te, se_);
+    const int r0 = blockIdx.x * rpc;
     const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, P = g.P;
     const double* gp = gin + (size_t)ste * N * N;
-    const double* ep = expo ? expo + (size_t)(ste % (g.T * g.E)) * N * N : nullptr;
+    const double* ep = expo ? expo + (size_t)te * N * N : nullptr;
     auto ld = [&](int b, int p) -> double {
         int rr = b / n, i = b - rr * n, r = r0 + rr;
         int c = g.offs[i] - hp - m + p;
@@ -131,11 +152,11 @@ JB_GLOBAL void k_cols(JbGeom g, const cd* __restrict__ in, cd* __restrict__ out,
                       const cd* __restrict__ khat, const cd* __restrict__ tw_nk, const double* __restrict__ wgt) {
     JB_SMEM(cd, sm);
     constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2;
-    const int strip = blockIdx.x, k = blockIdx.y, plane = blockIdx.z;
+    const int strip = blockIdx.x, k = blockIdx.y;
+    int plane, te, se;
+    jb_map_ste(g, blockIdx.z, plane, te, se);
     const int n = g.n, N = g.N, m = g.m, w = g.w, hp = g.hp, PH = g.PH, P = g.P;
     const int j = k % n, i = k / n;
-    const int TE = g.T * g.E;
-    const int s = plane / TE, te = plane - s * TE, e = te % g.E;
     const size_t nn2 = (size_t)n * n;
     const int nstrips = gridDim.x;
     const int col0 = strip * CB;
@@ -143,7 +164,7 @@ JB_GLOBAL void k_cols(JbGeom g, const cd* __restrict__ in, cd* __restrict__ out,
     size_t in_plane;
     if (!ADJ) {
         in_p0 = m; in_rows = w; out_p0 = 0; out_rows = P;
-        in_plane = (size_t)s * g.E + e;
+        in_plane = (size_t)se;
         row0 = g.offs[j] - hp;
     } else {
         in_p0 = 0; in_rows = P; out_p0 = m; out_rows = w;
@@ -210,7 +231,9 @@ JB_GLOBAL void k_rows_out(JbGeom g, const cd* __restrict__ bufA, const cd* __res
     int* jcnt = reinterpret_cast<int*>(smraw + off);
     int* jj = jcnt + rpc;
     int* ju = jj + rpc * n;
-    const int r0 = blockIdx.x * rpc, ste = blockIdx.y;
+    int ste, te, se_;
+    jb_map_ste(g, blockIdx.y, ste, te, se_);
+    const int r0 = blockIdx.x * rpc;
     jb_build_jlist(g, r0, rpc, hp + m, P, jcnt, jj, ju);
     JB_SYNC();
     const size_t nn2 = (size_t)n * n;
@@ -229,7 +252,6 @@ JB_GLOBAL void k_rows_out(JbGeom g, const cd* __restrict__ bufA, const cd* __res
     };
     rows_c2r<FP>(sm, tw_kn, B, ld, st);
     JB_SYNC();
-    const int te = ste % (g.T * g.E);
     double esum = 0.0;
     for (int idx = jb_tid(); idx < rpc * N; idx += jb_nthr()) {
         int rr = idx / N, c = idx - rr * N, r = r0 + rr;
@@ -284,8 +306,8 @@ JB_GLOBAL void k_rows_adj_out(JbGeom g, const cd* __restrict__ bufB, const doubl
     int* jcnt = reinterpret_cast<int*>(smraw + off);
     int* jj = jcnt + rpc;
     int* ju = jj + rpc * n;
-    const int r0 = blockIdx.x * rpc, se = blockIdx.y;
-    const int s = se / g.E, e = se - s * g.E;
+    int s, e;
+    const int r0 = blockIdx.x * rpc, se = jb_map_se(g, blockIdx.y, s, e);
     jb_build_jlist(g, r0, rpc, hp, w, jcnt, jj, ju);
     JB_SYNC();
     const size_t nn2 = (size_t)n * n;
@@ -427,10 +449,11 @@ JB_GLOBAL void k_prep_cols(JbGeom g, const cd* __restrict__ scratch, const doubl
 //   buf[s,t,e,:,:] = conv  ->  expo*(1 - d/lambda)  (0 where masked), lambda = expo*conv;
 //   partial[(s*TE + te)*nblk + blockIdx.x] = sum over this CTA's pixels of lambda - d log lambda.
 // grid (nblk, S*T*E), block 256.
-JB_GLOBAL_S void k_poisson_epi(double* __restrict__ buf, const double* __restrict__ expo, const double* __restrict__ data,
-                               int TE, int npix, double* __restrict__ partial) {
+JB_GLOBAL_S void k_poisson_epi(JbGeom g, double* __restrict__ buf, const double* __restrict__ expo,
+                               const double* __restrict__ data, int npix, double* __restrict__ partial) {
     JB_SMEM(double, red);
-    const int ste = blockIdx.y, te = ste % TE;
+    int ste, te, se_;
+    jb_map_ste(g, blockIdx.y, ste, te, se_);
     double* b = buf + (size_t)ste * npix;
     const double* ex = expo + (size_t)te * npix;
     const double* dd = data + (size_t)te * npix;
@@ -449,9 +472,10 @@ JB_GLOBAL_S void k_poisson_epi(double* __restrict__ buf, const double* __restric
 }
 
 // metric epilogue: buf = conv(v)  ->  expo * (expo*conv) / lambda  (0 where masked)
-JB_GLOBAL_S void k_metric_epi(double* __restrict__ buf, const double* __restrict__ expo, const double* __restrict__ lam,
-                              int TE, int npix) {
-    const int ste = blockIdx.y, te = ste % TE;
+JB_GLOBAL_S void k_metric_epi(JbGeom g, double* __restrict__ buf, const double* __restrict__ expo,
+                              const double* __restrict__ lam, int npix) {
+    int ste, te, se_;
+    jb_map_ste(g, blockIdx.y, ste, te, se_);
     double* b = buf + (size_t)ste * npix;
     const double* ex = expo + (size_t)te * npix;
     const double* lm = lam + (size_t)ste * npix;

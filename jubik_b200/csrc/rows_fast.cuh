@@ -125,7 +125,8 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_fwd2(JbGeom g, const double* __restrict__ x,
     const int n = g.n, N = g.N, m = g.m, w = g.w, hp = g.hp, PH = g.PH;
     const int B = rpc * n;
     cd* sm = reinterpret_cast<cd*>(smraw);
-    const int r0 = blockIdx.x * rpc, se = blockIdx.y;
+    int s_, e_;
+    const int r0 = blockIdx.x * rpc, se = jb_map_se(g, blockIdx.y, s_, e_);
     const double* xp = x + (size_t)se * N * N;
     for (int it = jb_tid(); it < B * R2; it += jb_nthr()) {
         int b = it / R2, n2 = it - b * R2;
@@ -163,9 +164,11 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_adj_in2(JbGeom g, const double* __restrict__
     const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, P = g.P;
     const int B = rpc * n;
     cd* sm = reinterpret_cast<cd*>(smraw);
-    const int r0 = blockIdx.x * rpc, ste = blockIdx.y;
+    int ste, te, se_;
+    jb_map_ste(g, blockIdx.y, ste, te, se_);
+    const int r0 = blockIdx.x * rpc;
     const double* gp = gin + (size_t)ste * N * N;
-    const double* ep = expo ? expo + (size_t)(ste % (g.T * g.E)) * N * N : nullptr;
+    const double* ep = expo ? expo + (size_t)te * N * N : nullptr;
     for (int it = jb_tid(); it < B * R2; it += jb_nthr()) {
         int b = it / R2, n2 = it - b * R2;
         int rr = b / n, i = b - rr * n, r = r0 + rr;
@@ -228,7 +231,9 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_out2(JbGeom g, const cd* __restrict__ bufA, 
     double* red = reinterpret_cast<double*>(smraw + off);
     off += jb_align16((size_t)jb_nthr() * sizeof(double));
     JbRowTab tab = jb_rowtab_at(smraw + off, rpc);
-    const int r0 = blockIdx.x * rpc, ste = blockIdx.y;
+    int ste, te, se_;
+    jb_map_ste(g, blockIdx.y, ste, te, se_);
+    const int r0 = blockIdx.x * rpc;
     jb_rowtab_build(g, tab, r0, rpc, hp + m, P, nullptr);
     JB_SYNC();
     const cd* ab = bufA + (size_t)ste * n * n * P * PH;
@@ -264,7 +269,6 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_out2(JbGeom g, const cd* __restrict__ bufA, 
     }
     JB_SYNC();
     // overlap-add over column blocks i as a gather, then the epilogue
-    const int te = ste % (g.T * g.E);
     const int shift = hp + m;
     double esum = 0.0;
     for (int idx = jb_tid(); idx < rpc * N; idx += jb_nthr()) {
@@ -320,8 +324,8 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_adj_out2(JbGeom g, const cd* __restrict__ bu
     double* tile = reinterpret_cast<double*>(smraw + off);
     off += jb_align16((size_t)B * w * sizeof(double));
     JbRowTab tab = jb_rowtab_at(smraw + off, rpc);
-    const int r0 = blockIdx.x * rpc, se = blockIdx.y;
-    const int s = se / g.E, e = se - s * g.E;
+    int s, e;
+    const int r0 = blockIdx.x * rpc, se = jb_map_se(g, blockIdx.y, s, e);
     jb_rowtab_build(g, tab, r0, rpc, hp, w, wgt);
     JB_SYNC();
     const size_t plane_sz = (size_t)n * n * w * PH;

@@ -68,7 +68,9 @@ k_rows_out3(JbGeom g, const cd* __restrict__ bufA, const cd* __restrict__ tw_kn,
     // stage the spectrum rows of `item` into ring slot s_ (called by all lanes of warp 0)
     auto stage_rows = [&](long item_, int s_) {
         const int lane = tid & 31;
-        const int ste = (int)(item_ / N), r = (int)(item_ - (long)ste * N);
+        const int lp = (int)(item_ / N), r = (int)(item_ - (long)lp * N);
+        int ste, te_, se_;
+        jb_map_ste(g, lp, ste, te_, se_);
         int jl[JB_MAXQ], ul[JB_MAXQ], cnt = 0;
         for (int j = 0; j < n && cnt < JB_MAXQ; ++j) {
             int u = r + shift - g.offs[j];
@@ -116,7 +118,9 @@ k_rows_out3(JbGeom g, const cd* __restrict__ bufA, const cd* __restrict__ tw_kn,
     long item = blockIdx.x;
     for (unsigned it = 0; item < nitems; ++it, item += gridDim.x) {
         const int s = it & 1;
-        const int ste = (int)(item / N), r = (int)(item - (long)ste * N);
+        const int lp = (int)(item / N), r = (int)(item - (long)lp * N);
+        int ste, te, se_;
+        jb_map_ste(g, lp, ste, te, se_);
         const cd* spec = spec0 + (size_t)s * stage_cd;
 #ifndef JB_EMU
         jb_mbar_wait<false>(&bars[s], (it >> 1) & 1);
@@ -169,7 +173,6 @@ k_rows_out3(JbGeom g, const cd* __restrict__ bufA, const cd* __restrict__ tw_kn,
             });
         }
         JB_SYNC();
-        const int te = ste % (g.T * g.E);
         const size_t orow = ((size_t)ste * N + r) * N, erow = ((size_t)te * N + r) * N;
         for (int c = tid; c < N; c += JB_RP_THREADS) {
             double conv = 0.0;
@@ -243,8 +246,9 @@ k_rows_adj_out3(JbGeom g, const cd* __restrict__ bufB, const double* __restrict_
         const long it_ = ls_ / T;
         const int t = (int)(ls_ - it_ * T);
         const long item_ = blockIdx.x + it_ * (long)gridDim.x;
-        const int se = (int)(item_ / N), r = (int)(item_ - (long)se * N);
-        const int s_idx = se / g.E, e = se - s_idx * g.E;
+        const int lp = (int)(item_ / N), r = (int)(item_ - (long)lp * N);
+        int s_idx, e;
+        jb_map_se(g, lp, s_idx, e);
         int jl[JB_MAXQ], ul[JB_MAXQ], cnt = 0;
         for (int j = 0; j < n && cnt < JB_MAXQ; ++j) {
             int u = r + hp - g.offs[j];
@@ -293,7 +297,9 @@ k_rows_adj_out3(JbGeom g, const cd* __restrict__ bufB, const double* __restrict_
     long ls = 0;
     for (long it = 0; it < my_items; ++it) {
         const long item = blockIdx.x + it * (long)gridDim.x;
-        const int se = (int)(item / N), r = (int)(item - (long)se * N);
+        const int lp = (int)(item / N), r = (int)(item - (long)lp * N);
+        int s_i, e_i;
+        const int se = jb_map_se(g, lp, s_i, e_i);
         // pass A, accumulated over the modules t: each step consumes one ring slot
         cd u[R2];  // valid for w = tid < n*H1 (one item per thread; plan creation guarantees n*H1 <= threads)
         static_for<0, R2>([&](auto kk) { constexpr int k2 = kk; u[k2] = cd_make(0.0, 0.0); });
