@@ -172,6 +172,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
+        # the one collective is a ~25 MB fp64 all-reduce: on this NVSwitch box NCCL's ring beats its default (NVLS)
+        # choice at that size (106 vs 124 us measured at 8 ranks, tools/ar_bench.py)
+        os.environ.setdefault("NCCL_ALGO", "Ring")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N, n, m, T, E, desc = WORKLOADS[args.workload]
     S = args.samples_per_gpu

@@ -110,6 +110,7 @@ struct jubik_plan {
     int nblk_out = 0;
     int use_pipe = 0, n_sm = 1;
     int split_epi = 1, nblk_epi = 1;  // Poisson/metric epilogue as a separate elementwise kernel
+    int rows_r3_out = 0, rows_r3_adj = 0;  // packed-complex three-stage c2r kernels (rows3.cuh)
     int rows_pipe_out = 0, rows_pipe_adj = 0, qmax = 0;  // persistent bulk-copy-fed c2r kernels (rows_pipe.cuh)
     int fast_rows = 0;         // rows_fast.cuh kernels (two-pass length and <= JB_MAXQ row-patches per image row)
     JbTileSrc src_fwd, src_adj;  // TMA views of bufB / bufA for the pipelined column pass
@@ -364,6 +365,11 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
         const size_t smem_max = 227 * 1024;
         p->rows_pipe_out = o->rows_out_pipe_smem(g, p->qmax) <= smem_max;
         p->rows_pipe_adj = o->rows_adj_out_pipe_smem(g, p->qmax) <= smem_max;
+        if (p->use_pipe == 2 && !getenv("JUBIK_B200_ROWS_V3")) {
+            // two CTAs per SM: each may use half of the 227 KB (minus the 1 KB per-CTA reservation)
+            p->rows_r3_out = o->rows_out_r3_smem(g, p->qmax) <= smem_max / 2 - 1024;
+            p->rows_r3_adj = o->rows_adj_out_r3_smem(g, p->qmax) <= smem_max / 2 - 1024;
+        }
     }
     if (p->use_pipe) {
         std::string err;
@@ -462,7 +468,9 @@ static int run_forward_g(jubik_plan* p, const JbGeom& g, const double* x, int S,
     } else {
         JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
-    if (p->rows_pipe_out && ep.mode != JB_EPI_POISSON) {
+    if (p->rows_r3_out && ep.mode != JB_EPI_POISSON) {
+        JB_LAUNCHED(p, o->rows_out_r3(g, p->bufA, p->tw1, p->tw2, ep, S * g.T * g.Es, p->qmax, p->n_sm, st));
+    } else if (p->rows_pipe_out && ep.mode != JB_EPI_POISSON) {
         JB_LAUNCHED(p, o->rows_out_pipe(g, p->bufA, p->tw_kn, ep, S * g.T * g.Es, p->qmax, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->rows_out(g, p->bufA, p->tw_kn, ep, S * g.T * g.Es, p->rpc_out, p->thr_rows, p->fast_rows, st));
@@ -483,7 +491,9 @@ static int run_adjoint_g(jubik_plan* p, const JbGeom& g, const double* gin, cons
     } else {
         JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
-    if (p->rows_pipe_adj) {
+    if (p->rows_r3_adj) {
+        JB_LAUNCHED(p, o->rows_adj_out_r3(g, p->bufB, p->wgt, p->tw1, p->tw2, out, S * g.Es, p->qmax, p->n_sm, st));
+    } else if (p->rows_pipe_adj) {
         JB_LAUNCHED(p, o->rows_adj_out_pipe(g, p->bufB, p->wgt, p->tw_kn, out, S * g.Es, p->qmax, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->rows_adj_out(g, p->bufB, p->wgt, p->tw_kn, out, S * g.Es, p->rpc_out, p->thr_rows, p->fast_rows, st));

@@ -7,6 +7,7 @@
 #include "cols_pipe.cuh"
 #include "cols3.cuh"
 #include "rows_pipe.cuh"
+#include "rows3.cuh"
 
 struct JbFftOps {
     int L, R1, R2, CB;
@@ -34,6 +35,13 @@ struct JbFftOps {
                                  int ctas, jb_stream_t);
     cudaError_t (*rows_adj_out_pipe)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw_kn, double* grad,
                                      int planes_se, int Q, int ctas, jb_stream_t);
+    // packed-complex three-stage c2r kernels (rows3.cuh; need pipe == 2); *_smem returns a huge value if unusable
+    size_t (*rows_out_r3_smem)(const JbGeom&, int Q);
+    size_t (*rows_adj_out_r3_smem)(const JbGeom&, int Q);
+    cudaError_t (*rows_out_r3)(const JbGeom&, const cd* bufA, const cd* tw1, const cd* tw2, const JbEpi&, int planes,
+                               int Q, int ctas, jb_stream_t);
+    cudaError_t (*rows_adj_out_r3)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw1, const cd* tw2,
+                                   double* grad, int planes_se, int Q, int ctas, jb_stream_t);
     cudaError_t (*prep_rows)(const JbGeom&, const JbKsrc&, const cd* tw_nk, cd* scratch, int rpc, int threads,
                              jb_stream_t);
     // layout 0: K^ in the two-pass register order (tw = tw_nk); layout 2: three-stage order (twa/twb = tw1/tw2)
@@ -152,6 +160,42 @@ struct JbOpsImpl {
             return (cudaError_t)1;
         }
     }
+    static size_t rows_r3_common(const JbGeom& g, int Q, int width) {
+        if constexpr (PIPE == 2) {
+            const int NC = (g.n + 1) / 2, BP = F3::M * NC + 1;
+            if (F3::R1 * F3::R2 * NC > JB_R4_THREADS || F3::R1 * F3::R3 * NC > JB_R4_THREADS || F3::M * NC > JB_R4_THREADS ||
+                F3::L * NC > JB_R4_MAXEL * JB_R4_THREADS || g.n > 255 || g.N > JB_R4_MAXC * JB_R4_THREADS)
+                return (size_t)1 << 30;
+            (void)width;  // the real rows alias the complex tile
+            return al128((size_t)g.n * Q * g.PH * sizeof(cd)) + al128((size_t)F3::R1 * BP * sizeof(cd)) +
+                   al128((size_t)(F3::L + F3::M) * sizeof(cd)) + 64 + 2 * sizeof(JbRowInfo) + 2 * (size_t)g.N + 64;
+        } else {
+            (void)g; (void)Q; (void)width;
+            return (size_t)1 << 30;
+        }
+    }
+    static size_t rows_out_r3_smem(const JbGeom& g, int Q) { return rows_r3_common(g, Q, g.P); }
+    static size_t rows_adj_out_r3_smem(const JbGeom& g, int Q) { return rows_r3_common(g, Q, g.w); }
+    static cudaError_t rows_out_r3(const JbGeom& g, const cd* bufA, const cd* tw1, const cd* tw2, const JbEpi& ep,
+                                   int planes, int Q, int ctas, jb_stream_t st) {
+        if constexpr (PIPE == 2) {
+            return jb_launch(k_rows_out4<FP, F3>, dim3(ctas * JB_R4_CTAS_PER_SM), dim3(JB_R4_THREADS), rows_out_r3_smem(g, Q), st, g, bufA,
+                             tw1, tw2, ep, planes, Q);
+        } else {
+            (void)g; (void)bufA; (void)tw1; (void)tw2; (void)ep; (void)planes; (void)Q; (void)ctas; (void)st;
+            return (cudaError_t)1;
+        }
+    }
+    static cudaError_t rows_adj_out_r3(const JbGeom& g, const cd* bufB, const double* wgt, const cd* tw1, const cd* tw2,
+                                       double* grad, int planes_se, int Q, int ctas, jb_stream_t st) {
+        if constexpr (PIPE == 2) {
+            return jb_launch(k_rows_adj_out4<FP, F3>, dim3(ctas * JB_R4_CTAS_PER_SM), dim3(JB_R4_THREADS), rows_adj_out_r3_smem(g, Q), st, g,
+                             bufB, wgt, tw1, tw2, grad, planes_se, Q);
+        } else {
+            (void)g; (void)bufB; (void)wgt; (void)tw1; (void)tw2; (void)grad; (void)planes_se; (void)Q; (void)ctas; (void)st;
+            return (cudaError_t)1;
+        }
+    }
     static cudaError_t prep_rows(const JbGeom& g, const JbKsrc& ks, const cd* tw_nk, cd* scratch, int rpc,
                                  int threads, jb_stream_t st) {
         size_t smem = jb_al16((size_t)rpc * FP::LS * sizeof(cd)) + 16;
@@ -174,7 +218,8 @@ struct JbOpsImpl {
         static const JbFftOps t = {FP::L, FP::R1, FP::R2, CB, FP::LS, (FP::R2 > 1 && PIPE == 2) ? 2 : 0, F3::R1, F3::R2, F3::R3,
                                    rows_fwd, rows_adj_in, cols, cols_pipe,
                                    rows_out, rows_adj_out, rows_out_pipe_smem, rows_adj_out_pipe_smem, rows_out_pipe,
-                                   rows_adj_out_pipe, prep_rows, prep_cols};
+                                   rows_adj_out_pipe, rows_out_r3_smem, rows_adj_out_r3_smem, rows_out_r3, rows_adj_out_r3,
+                                   prep_rows, prep_cols};
         return &t;
     }
 };
