@@ -22,7 +22,9 @@ struct Fft3 {
     static_assert(R1_ * R2_ * R3_ == L_, "L = R1*R2*R3");
 };
 
-#define JB_C3_THREADS 512
+// threads per CTA = the widest stage (one work item per thread and stage), rounded up to whole warps; tiles of
+// <= 256 threads run two CTAs per SM so that one CTA's barrier/latency stalls overlap the other's butterflies
+JB_HD constexpr int jb_c3_max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
 
 // what the compute threads need to know about a work item; written by thread 0 when it stages the item
 struct JbColInfo {
@@ -38,7 +40,9 @@ template <class F3, int CB>
 struct Cols3 {
     static constexpr int L = F3::L, R1 = F3::R1, R2 = F3::R2, R3 = F3::R3, M = F3::M;
     static constexpr int I1 = M * CB, I2 = R1 * R3 * CB, I3 = R1 * R2 * CB;
-    static_assert(I1 <= JB_C3_THREADS && I2 <= JB_C3_THREADS && I3 <= JB_C3_THREADS, "one item per thread and stage");
+    static constexpr int THREADS = (jb_c3_max3(I1, I2, I3) + 31) / 32 * 32;
+    static constexpr int CPS = THREADS <= 256 ? 2 : 1;   // CTAs per SM the pipeline is sized for
+    static_assert(THREADS <= 1024, "one item per thread and stage");
 
     // forward stage 1 with zero rows outside [vlo, vhi); rw != nullptr: multiply tile row p by rw[p - p0]
     // (the window row weight of the forward direction, convolve.py:88-90)
@@ -134,7 +138,7 @@ struct Cols3 {
 // Persistent TMA pipeline, 512 threads, 2-stage ring of (tile, K^ slice); thread 0 refills a slot as soon as
 // every warp has pulled its stage-1' operands out of it.  dynamic smem = 4*L*CB*16 + (L + M)*16 + 64.
 template <class F3, int CB, bool ADJ>
-JB_GLOBAL void JB_LB(JB_C3_THREADS, 1)
+JB_GLOBAL void JB_LB((Cols3<F3, CB>::THREADS), (Cols3<F3, CB>::CPS))
 k_cols3_pipe(const
 #ifndef JB_EMU
              __grid_constant__
@@ -144,6 +148,7 @@ k_cols3_pipe(const
     using C3 = Cols3<F3, CB>;
     constexpr int L = F3::L, R1 = F3::R1, M = F3::M;
     constexpr int TILE = L * CB;
+    constexpr int JB_C3_THREADS = C3::THREADS;
     JB_SMEM(unsigned char, smraw);
     cd* tile0 = reinterpret_cast<cd*>(smraw);
     cd* kh0 = tile0 + 2 * TILE;
@@ -265,11 +270,12 @@ k_cols3_pipe(const
 // plan time: forward 3-stage column transform of the PSF row spectra, normalised, stored as [k3][k1*R2+k2][b].
 // grid (nstrips, n*n, TE), block JB_C3_THREADS, dyn smem = L*CB*16 + (L+M)*16.
 template <class F3, int CB>
-JB_GLOBAL void JB_LB(JB_C3_THREADS, 1)
+JB_GLOBAL void JB_LB((Cols3<F3, CB>::THREADS), 1)
 k_prep_cols3(JbGeom g, const cd* __restrict__ scratch, const double* __restrict__ sums, const cd* __restrict__ tw1g,
              const cd* __restrict__ tw2g, cd* __restrict__ khat) {
     using C3 = Cols3<F3, CB>;
     constexpr int L = F3::L, R3 = F3::R3, M = F3::M;
+    constexpr int JB_C3_THREADS = C3::THREADS;
     JB_SMEM(cd, tile);
     cd* tw1 = tile + L * CB;
     cd* tw2 = tw1 + L;

@@ -10,8 +10,8 @@
     X(20, 20, 1, 8, 0, 1, 1, 1)    \
     X(24, 24, 1, 8, 0, 1, 1, 1)    \
     X(28, 28, 1, 8, 0, 1, 1, 1)    \
-    X(160, 16, 10, 8, 2, 8, 5, 4)  \
-    X(336, 24, 14, 8, 2, 8, 6, 7)  \
-    X(384, 24, 16, 8, 2, 8, 6, 8)  \
-    X(640, 32, 20, 8, 0, 1, 1, 1)  \
-    X(672, 28, 24, 8, 0, 1, 1, 1)
+    X(160, 16, 10, 4, 2, 8, 5, 4)  \
+    X(336, 24, 14, 4, 2, 8, 6, 7)  \
+    X(384, 24, 16, 4, 2, 8, 6, 8)  \
+    X(640, 32, 20, 4, 2, 8, 8, 10)  \
+    X(672, 28, 24, 4, 2, 8, 7, 12)

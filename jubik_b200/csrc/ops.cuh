@@ -59,9 +59,9 @@ struct JbOpsImpl {
         if constexpr (PIPE == 2) {
             size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd) + 32 +
                           2 * sizeof(JbColInfo) + (size_t)g.w * sizeof(double) + 32;
-            if (adj) return jb_launch(k_cols3_pipe<F3, CB, true>, dim3(ctas), dim3(JB_C3_THREADS), smem, st, src, g,
+            if (adj) return jb_launch(k_cols3_pipe<F3, CB, true>, dim3(ctas * Cols3<F3, CB>::CPS), dim3(Cols3<F3, CB>::THREADS), smem, st, src, g,
                                       out, khat, twa, twb, wgt, planes);
-            return jb_launch(k_cols3_pipe<F3, CB, false>, dim3(ctas), dim3(JB_C3_THREADS), smem, st, src, g, out,
+            return jb_launch(k_cols3_pipe<F3, CB, false>, dim3(ctas * Cols3<F3, CB>::CPS), dim3(Cols3<F3, CB>::THREADS), smem, st, src, g, out,
                              khat, twa, twb, wgt, planes);
         } else {
             (void)g; (void)adj; (void)src; (void)out; (void)khat; (void)twa; (void)twb; (void)wgt; (void)planes;
@@ -208,7 +208,7 @@ struct JbOpsImpl {
         if constexpr (PIPE == 2) {
             if (layout == 2) {
                 size_t smem3 = (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd);
-                return jb_launch(k_prep_cols3<F3, CB>, grid, dim3(JB_C3_THREADS), smem3, st, g, scratch, sums, twa, twb, khat);
+                return jb_launch(k_prep_cols3<F3, CB>, grid, dim3(Cols3<F3, CB>::THREADS), smem3, st, g, scratch, sums, twa, twb, khat);
             }
         }
         size_t smem = (FP::R2 == 1) ? 16 : (size_t)FP::L * CB * sizeof(cd);

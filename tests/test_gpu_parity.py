@@ -198,6 +198,63 @@ def test_full_size_chandra_adjointness_linearity_and_fd(torch_cuda):
     plan.close()
 
 
+def test_full_size_erosita_like_c3_oracle_parity_and_adjointness(torch_cuda):
+    """BASELINE.json configs[2] at full size (7 modules x 3 bins, 1024^2, 10x10 patches, margin 64: N % n != 0,
+    P = 332 -> L = 336 padded transform, per-module effective areas): fused energy/gradient against the oracle
+    for every module and bin, plus dot-product adjointness of the full response."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    N, n, m, T, E, S = 1024, 10, 64, 7, 3, 1
+    dom, kern, cropped, expo, ea, x, R, d = build_case(N, n, m, T, E, S, False, True)
+    plan = jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
+                           eff_area=dev(torch, ea), pixel_area=synth.PIXEL_AREA, data=dev(torch, d),
+                           max_samples=S, cropped=True)
+    assert plan.info["L"] == 336 and plan.info["P"] == 332
+    xd = dev(torch, x)
+    e, gr = plan.energy_and_grad(xd)
+    eo, go = orc.energy_and_grad(R, d, x[0])
+    assert abs(float(e[0]) - eo) / abs(eo) < TOL
+    assert rel(gr[0].cpu().numpy(), go) < TOL
+    g = dev(torch, synth.direction((S, T, E, N, N)))
+    lhs = torch.vdot(g.flatten(), plan.response(xd).flatten())
+    rhs = torch.vdot(plan.response_T(g).flatten(), xd.flatten())
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-12
+    plan.close()
+
+
+def test_full_size_jwst_like_c4_oracle_parity_and_adjointness(torch_cuda):
+    """BASELINE.json configs[3] at full size (4096^2 sky, 16x16 patches, 128-px kernels = margin 64, P = 640):
+    forward PSF against the oracle, adjointness and the fused energy gradient's directional derivative."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    N, n, m, T, E, S = 4096, 16, 64, 1, 1, 1
+    dx = N // n
+    kern = synth.psf_cropped(T, n, E, dx, half_support=m)
+    expo = synth.exposure(T, E, N)
+    x = synth.sky(S, E, N)
+    plan = jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
+                           pixel_area=synth.PIXEL_AREA, max_samples=S, cropped=True)
+    assert plan.info["L"] == 640 and plan.info["exact_period"] == 1
+    xd = dev(torch, x)
+    y = plan.psf(xd)
+    yo = orc.linpatch_convolve(x[0], orc.Domain((E, N, N), synth.DIST), kern[0], n, m, cropped=True)
+    assert rel(y[0, 0].cpu().numpy(), yo) < TOL
+    g = dev(torch, synth.direction((S, T, E, N, N)))
+    lhs = torch.vdot(g.flatten(), plan.response(xd).flatten())
+    rhs = torch.vdot(plan.response_T(g).flatten(), xd.flatten())
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-12
+    lam = plan.response(dev(torch, synth.sky(1, E, N, seed=5)))
+    torch.manual_seed(7)
+    plan.set_data(torch.poisson(lam.clamp(min=0.0))[0])
+    e0, gr = plan.energy_and_grad(xd)
+    v = dev(torch, synth.direction((S, E, N, N), seed=9)) * xd
+    eps = 1e-4
+    fd = float((plan.energy(xd + eps * v) - plan.energy(xd - eps * v)).sum()) / (2 * eps)
+    an = float(torch.vdot(gr.flatten(), v.flatten()))
+    assert abs(fd - an) / max(abs(an), 1e-4 * float(gr.norm() * v.norm())) < 1e-6
+    plan.close()
+
+
 def test_error_behaviour_matches_reference(torch_cuda):
     import jubik_b200 as jb
     torch = torch_cuda
