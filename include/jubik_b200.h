@@ -105,7 +105,7 @@ int jubik_poisson_energy_and_grad_host(jubik_plan* plan, const double* x_host, i
                                        double* energy_host, double* grad_host, void* stream);
 
 /* Measurement helpers (bench.py): the energy+grad sequence with a CUDA event after every kernel,
- * ms_out[0..*n_out) (room for 12) in launch order = rows_fwd, cols_fwd, rows_out, [poisson_epi,] reduce,
+ * ms_out[0..*n_out) (room for 48) in launch order = rows_fwd, cols_fwd, rows_out, [poisson_epi,] reduce,
  * rows_adj_in, cols_adj, rows_adj_out (synchronises); and a DFMA micro-benchmark giving this device's FP64 FMA
  * throughput in TFLOP/s. */
 int jubik_poisson_profile(jubik_plan* plan, const double* x, int n_samples, double* energy, double* grad,

@@ -51,6 +51,9 @@ def _run(cmd, log):
 
 
 def build(force=False, jobs=None, verbose=False):
+    extra = os.environ.get("JUBIK_B200_NVCC_EXTRA", "").split()   # experiment hook, e.g. "-DJB_R5_SW=1"
+    if extra:
+        NVCC_FLAGS.extend(f for f in extra if f not in NVCC_FLAGS)
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: jubik_b200 needs the CUDA toolkit to build")

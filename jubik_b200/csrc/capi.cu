@@ -111,13 +111,18 @@ struct jubik_plan {
     int use_pipe = 0, n_sm = 1;
     int split_epi = 1, nblk_epi = 1;  // Poisson/metric epilogue as a separate elementwise kernel
     int rows_r3_out = 0, rows_r3_adj = 0;  // packed-complex three-stage c2r kernels (rows3.cuh)
+    int chunk_e = 0;                       // fused energy+gradient runs one energy bin at a time (L2 residency)
+    int rows5 = 0;                         // warp-private c2r kernels with the fused Poisson epilogue (rows5.cuh)
+    int* gtab_fwd = nullptr;               // rows5 overlap-add gather tables [gq][N]
+    int* gtab_adj = nullptr;
+    int gq_fwd = 0, gq_adj = 0;
     int rows_pipe_out = 0, rows_pipe_adj = 0, qmax = 0;  // persistent bulk-copy-fed c2r kernels (rows_pipe.cuh)
     int fast_rows = 0;         // rows_fast.cuh kernels (two-pass length and <= JB_MAXQ row-patches per image row)
     JbTileSrc src_fwd, src_adj;  // TMA views of bufB / bufA for the pipelined column pass
     // per-kernel timing (jubik_poisson_profile): events recorded after every launch while enabled
     int prof_on = 0, prof_n = 0;
 #ifndef JB_EMU
-    cudaEvent_t prof_ev[16] = {};
+    cudaEvent_t prof_ev[48] = {};
     // host-buffer entry point: copy streams and per-energy-bin events (created on first use)
     cudaStream_t st_in = nullptr, st_out = nullptr;
     cudaEvent_t *ev_in = nullptr, *ev_c = nullptr, ev_start = nullptr;
@@ -126,7 +131,7 @@ struct jubik_plan {
 
 static inline void jb_mark(jubik_plan* p, jb_stream_t st) {
 #ifndef JB_EMU
-    if (p->prof_on && p->prof_n < 16) cudaEventRecord(p->prof_ev[p->prof_n++], st);
+    if (p->prof_on && p->prof_n < 48) cudaEventRecord(p->prof_ev[p->prof_n++], st);
 #else
     (void)p; (void)st;
 #endif
@@ -150,7 +155,7 @@ int jubik_plan_destroy(jubik_plan* p) {
     if (!p) return JUBIK_OK;
     dev_free(p->khat); dev_free(p->tw_nk); dev_free(p->tw_kn); dev_free(p->tw1); dev_free(p->tw2); dev_free(p->wgt); dev_free(p->expo);
     dev_free(p->data); dev_free(p->bufA); dev_free(p->bufB); dev_free(p->gbuf); dev_free(p->lbuf);
-    dev_free(p->partial); dev_free(p->xdev); dev_free(p->gdev); dev_free(p->edev);
+    dev_free(p->partial); dev_free(p->gtab_fwd); dev_free(p->gtab_adj); dev_free(p->xdev); dev_free(p->gdev); dev_free(p->edev);
 #ifndef JB_EMU
     if (p->st_in) {
         for (int e = 0; e < p->g.E; ++e) { cudaEventDestroy(p->ev_in[e]); cudaEventDestroy(p->ev_c[e]); }
@@ -158,7 +163,7 @@ int jubik_plan_destroy(jubik_plan* p) {
         cudaEventDestroy(p->ev_start);
         cudaStreamDestroy(p->st_in); cudaStreamDestroy(p->st_out);
     }
-    for (int i = 0; i < 16; ++i) if (p->prof_ev[i]) cudaEventDestroy(p->prof_ev[i]);
+    for (int i = 0; i < 48; ++i) if (p->prof_ev[i]) cudaEventDestroy(p->prof_ev[i]);
 #endif
     delete p;
     return JUBIK_OK;
@@ -318,6 +323,7 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
     p->nblk_epi = jb_cdiv(N * N, 256 * 8);
     if (p->nblk_epi > 1024) p->nblk_epi = 1024;
     size_t bP = STE * (size_t)(p->nblk_out > p->nblk_epi ? p->nblk_out : p->nblk_epi) * sizeof(double);
+    if (bP < STE * (size_t)N * sizeof(double)) bP = STE * (size_t)N * sizeof(double);   // rows5: one partial per image row
     p->bytes_ws = bA + bB + bG + bP;
     if (alloc(p, (void**)&p->khat, p->bytes_khat, "PSF spectra") || alloc(p, (void**)&p->bufA, bA, "spectrum workspace A") ||
         alloc(p, (void**)&p->bufB, bB, "spectrum workspace B") || alloc(p, (void**)&p->gbuf, bG, "cotangent workspace") ||
@@ -371,6 +377,23 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
             p->rows_r3_adj = o->rows_adj_out_r3_smem(g, p->qmax) <= smem_max / 2 - 1024;
         }
     }
+    if (p->use_pipe == 2 && p->qmax <= JB_MAXQ && !getenv("JUBIK_B200_ROWS_V4"))
+        p->rows5 = o->rows5_smem(g) <= (size_t)227 * 1024 - 1024;
+    if (p->rows5) {
+        std::vector<int> tf((size_t)JB_MAXQ * N), ta((size_t)JB_MAXQ * N);
+        p->gq_fwd = o->rows5_gather(g, 0, JB_MAXQ, tf.data());
+        p->gq_adj = o->rows5_gather(g, 1, JB_MAXQ, ta.data());
+        if (p->gq_fwd < 1 || p->gq_adj < 1) {
+            p->rows5 = 0;
+        } else if (alloc(p, (void**)&p->gtab_fwd, tf.size() * sizeof(int), "gather table") ||
+                   alloc(p, (void**)&p->gtab_adj, ta.size() * sizeof(int), "gather table") ||
+                   h2d(p->gtab_fwd, tf.data(), tf.size() * sizeof(int), st) ||
+                   h2d(p->gtab_adj, ta.data(), ta.size() * sizeof(int), st) || stream_sync(st)) {
+            cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "uploading gather tables failed");
+        }
+    }
+    p->chunk_e = getenv("JUBIK_B200_CHUNK_E") ? 1 : 0;
+    if (p->rows5 && !getenv("JUBIK_B200_SPLIT_EPI")) { p->split_epi = 0; p->nblk_out = N; }   // fused epilogue: one partial per row
     if (p->use_pipe) {
         std::string err;
         int brB = g.w < 64 ? g.w : 64, brA = g.P < 64 ? g.P : 64;
@@ -468,7 +491,9 @@ static int run_forward_g(jubik_plan* p, const JbGeom& g, const double* x, int S,
     } else {
         JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
-    if (p->rows_r3_out && ep.mode != JB_EPI_POISSON) {
+    if (p->rows5) {
+        JB_LAUNCHED(p, o->rows5_fwd(g, p->bufA, p->tw1, p->tw2, p->gtab_fwd, p->gq_fwd, ep, S * g.T * g.Es, p->n_sm, st));
+    } else if (p->rows_r3_out && ep.mode != JB_EPI_POISSON) {
         JB_LAUNCHED(p, o->rows_out_r3(g, p->bufA, p->tw1, p->tw2, ep, S * g.T * g.Es, p->qmax, p->n_sm, st));
     } else if (p->rows_pipe_out && ep.mode != JB_EPI_POISSON) {
         JB_LAUNCHED(p, o->rows_out_pipe(g, p->bufA, p->tw_kn, ep, S * g.T * g.Es, p->qmax, p->n_sm, st));
@@ -491,7 +516,9 @@ static int run_adjoint_g(jubik_plan* p, const JbGeom& g, const double* gin, cons
     } else {
         JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
-    if (p->rows_r3_adj) {
+    if (p->rows5) {
+        JB_LAUNCHED(p, o->rows5_adj(g, p->bufB, p->wgt, p->tw1, p->tw2, p->gtab_adj, p->gq_adj, out, S * g.Es, p->n_sm, st));
+    } else if (p->rows_r3_adj) {
         JB_LAUNCHED(p, o->rows_adj_out_r3(g, p->bufB, p->wgt, p->tw1, p->tw2, out, S * g.Es, p->qmax, p->n_sm, st));
     } else if (p->rows_pipe_adj) {
         JB_LAUNCHED(p, o->rows_adj_out_pipe(g, p->bufB, p->wgt, p->tw_kn, out, S * g.Es, p->qmax, p->n_sm, st));
@@ -536,6 +563,20 @@ int jubik_poisson_energy_and_grad(jubik_plan* p, const double* x, int S, double*
     if (!p->has_expo || !p->has_data) return fail(JUBIK_ERR_ARG, "plan needs exposures and data for the Poisson energy");
     const JbGeom& g = p->g;
     JbEpi ep; memset(&ep, 0, sizeof(ep));
+    if (p->chunk_e && !p->split_epi && grad && g.E > 1) {
+        // one energy bin at a time, forward then adjoint: the bin's spectra (column-pass output -> row pass) and its
+        // cotangent plane are still L2-resident when the next kernel reads them
+        ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
+        for (int e = 0; e < g.E; ++e) {
+            JbGeom ge = g;
+            ge.e0 = e; ge.Es = 1;
+            if (int rc = run_forward_g(p, ge, x, S, ep, st)) return rc;
+            if (int rc = run_adjoint_g(p, ge, p->gbuf, nullptr, S, grad, st)) return rc;
+        }
+        JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
+                                 (const double*)p->partial, g.T * g.E * p->nblk_out, energy));
+        return JUBIK_OK;
+    }
     if (p->split_epi) {
         // convolved planes first, then the Poisson epilogue as a separate full-occupancy elementwise pass
         ep.mode = JB_EPI_PSF; ep.out = p->gbuf;
@@ -560,14 +601,14 @@ int jubik_poisson_profile(jubik_plan* p, const double* x, int S, double* energy,
 #ifndef JB_EMU
     jb_stream_t st = (jb_stream_t)stream_;
     if (!ms_out || !grad || !n_out) return fail(JUBIK_ERR_ARG, "null pointer");
-    for (int i = 0; i < 16; ++i) if (!p->prof_ev[i]) JB_CK(cudaEventCreate(&p->prof_ev[i]));
+    for (int i = 0; i < 48; ++i) if (!p->prof_ev[i]) JB_CK(cudaEventCreate(&p->prof_ev[i]));
     p->prof_on = 1; p->prof_n = 0;
     jb_mark(p, st);
     int rc = jubik_poisson_energy_and_grad(p, x, S, energy, grad, stream_);
     p->prof_on = 0;
     if (rc) return rc;
     JB_CK(cudaStreamSynchronize(st));
-    for (int i = 0; i + 1 < p->prof_n && i < 12; ++i) JB_CK(cudaEventElapsedTime(&ms_out[i], p->prof_ev[i], p->prof_ev[i + 1]));
+    for (int i = 0; i + 1 < p->prof_n && i < 47; ++i) JB_CK(cudaEventElapsedTime(&ms_out[i], p->prof_ev[i], p->prof_ev[i + 1]));
     *n_out = p->prof_n - 1;
     return JUBIK_OK;
 #else
@@ -658,7 +699,7 @@ int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, d
 #ifndef JB_EMU
     // Energy bins are independent through the whole fused chain, so the call is pipelined per bin: the H2D copy
     // of bin e+1 and the D2H copy of the gradient of bin e-1 overlap the kernels of bin e (three streams).
-    const bool chunked = gh && g.E > 1 && p->split_epi && p->has_expo && p->has_data && !getenv("JUBIK_B200_HOST_SERIAL");
+    const bool chunked = gh && g.E > 1 && (p->split_epi || p->rows5) && p->has_expo && p->has_data && !getenv("JUBIK_B200_HOST_SERIAL");
     if (chunked) {
         if (!p->st_in) {
             JB_CK(cudaStreamCreateWithFlags(&p->st_in, cudaStreamNonBlocking));
@@ -684,17 +725,22 @@ int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, d
             ge.e0 = e; ge.Es = 1;
             JB_CK(cudaStreamWaitEvent(st, p->ev_in[e], 0));
             JbEpi ep; memset(&ep, 0, sizeof(ep));
-            ep.mode = JB_EPI_PSF; ep.out = p->gbuf;
-            if (int rc = run_forward_g(p, ge, p->xdev, S, ep, st)) return rc;
-            JB_LAUNCHED(p, jb_launch(k_poisson_epi, dim3(p->nblk_epi, S * g.T), dim3(256), 256 * sizeof(double), st, ge,
-                                     p->gbuf, (const double*)p->expo, (const double*)p->data, (int)npx, p->partial));
+            if (p->split_epi) {
+                ep.mode = JB_EPI_PSF; ep.out = p->gbuf;
+                if (int rc = run_forward_g(p, ge, p->xdev, S, ep, st)) return rc;
+                JB_LAUNCHED(p, jb_launch(k_poisson_epi, dim3(p->nblk_epi, S * g.T), dim3(256), 256 * sizeof(double), st, ge,
+                                         p->gbuf, (const double*)p->expo, (const double*)p->data, (int)npx, p->partial));
+            } else {
+                ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
+                if (int rc = run_forward_g(p, ge, p->xdev, S, ep, st)) return rc;
+            }
             if (int rc = run_adjoint_g(p, ge, p->gbuf, nullptr, S, p->gdev, st)) return rc;
             JB_CK(cudaEventRecord(p->ev_c[e], st));
             JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_c[e], 0));
             JB_CK(cudaMemcpy2DAsync(gh + e * npx, pitch, p->gdev + e * npx, pitch, width, S, cudaMemcpyDeviceToHost, p->st_out));
         }
         JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
-                                 (const double*)p->partial, g.T * g.E * p->nblk_epi, p->edev));
+                                 (const double*)p->partial, g.T * g.E * (p->split_epi ? p->nblk_epi : p->nblk_out), p->edev));
         if (d2h(eh, p->edev, S * sizeof(double), st)) return fail(JUBIK_ERR_CUDA, "D2H copy of energy failed");
         if (stream_sync(st) || stream_sync(p->st_out)) return fail(JUBIK_ERR_CUDA, "stream synchronise failed");
         return JUBIK_OK;

@@ -38,6 +38,7 @@ JB_D void jb_st_stream(cd* p, cd v) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 #define JB_SYNC() __syncthreads()
+#define JB_SYNCWARP() __syncwarp()
 
 template <class K, class... A>
 inline cudaError_t jb_launch(K kern, dim3 grid, dim3 block, size_t smem, jb_stream_t st, A... args) {
@@ -76,6 +77,9 @@ extern thread_local jb_emu_ctx jb_ctx;
 #define gridDim (jb_ctx.gdim_)
 #define JB_SMEM(T, name) T* name = reinterpret_cast<T*>(jb_ctx.smem)
 #define JB_SYNC() jb_ctx.bar->arrive_and_wait()
+// emulated threads are not grouped in warps: a warp-level sync becomes a CTA-level one (callers keep the number
+// of warp syncs uniform across the CTA)
+#define JB_SYNCWARP() jb_ctx.bar->arrive_and_wait()
 typedef void* jb_stream_t;
 typedef int cudaError_t;
 #define cudaSuccess 0

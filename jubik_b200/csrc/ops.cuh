@@ -8,6 +8,8 @@
 #include "cols3.cuh"
 #include "rows_pipe.cuh"
 #include "rows3.cuh"
+#include "rows5.cuh"
+
 
 struct JbFftOps {
     int L, R1, R2, CB;
@@ -42,6 +44,13 @@ struct JbFftOps {
                                int Q, int ctas, jb_stream_t);
     cudaError_t (*rows_adj_out_r3)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw1, const cd* tw2,
                                    double* grad, int planes_se, int Q, int ctas, jb_stream_t);
+    // warp-private c2r kernels (rows5.cuh; need pipe == 2); fwd: ep.mode may be JB_EPI_POISSON (partials [STE][N])
+    size_t (*rows5_smem)(const JbGeom&);
+    int (*rows5_gather)(const JbGeom&, int adj, int maxq, int* host_tab);   // [maxq][N] table, returns slots used
+    cudaError_t (*rows5_fwd)(const JbGeom&, const cd* bufA, const cd* tw1, const cd* tw2, const int* gtab, int gq,
+                             const JbEpi&, int planes, int n_sm, jb_stream_t);
+    cudaError_t (*rows5_adj)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw1, const cd* tw2,
+                             const int* gtab, int gq, double* grad, int planes_se, int n_sm, jb_stream_t);
     cudaError_t (*prep_rows)(const JbGeom&, const JbKsrc&, const cd* tw_nk, cd* scratch, int rpc, int threads,
                              jb_stream_t);
     // layout 0: K^ in the two-pass register order (tw = tw_nk); layout 2: three-stage order (twa/twb = tw1/tw2)
@@ -196,6 +205,70 @@ struct JbOpsImpl {
             return (cudaError_t)1;
         }
     }
+    // sequences per warp: 1 for n <= 8 (CTAs of <= 4 warps, 28 warps per SM), else 2
+    static int rows5_sw(const JbGeom& g) { return (g.n + 1) / 2 <= 4 ? 1 : 2; }
+    static size_t rows5_smem(const JbGeom& g) {
+        if constexpr (PIPE == 2) {
+            const int sw = rows5_sw(g), NC = (g.n + 1) / 2, NW = (NC + sw - 1) / sw;
+            if (NW * 32 > 512) return (size_t)1 << 30;
+            return sw == 1 ? jb_rows5_smem<F3, 1>(g.n) : jb_rows5_smem<F3, 2>(g.n);
+        } else {
+            (void)g;
+            return (size_t)1 << 30;
+        }
+    }
+    static int rows5_gather(const JbGeom& g, int adj, int maxq, int* host_tab) {
+        if constexpr (PIPE == 2) {
+            return rows5_sw(g) == 1 ? jb_rows5_gather_table<F3, 1>(g, adj != 0, maxq, host_tab)
+                                    : jb_rows5_gather_table<F3, 2>(g, adj != 0, maxq, host_tab);
+        } else {
+            (void)g; (void)adj; (void)maxq; (void)host_tab;
+            return 0;
+        }
+    }
+    template <class K>
+    static int rows5_grid(K kern, int threads, size_t smem, long items, int n_sm) {
+        int per_sm = 1;
+#ifndef JB_EMU
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+#endif
+        long gsz = (long)per_sm * n_sm;
+        return (int)(gsz < items ? gsz : items);
+    }
+    template <int SW, bool ADJ>
+    static cudaError_t rows5_launch(const JbGeom& g, const cd* src, const double* wgt, const cd* tw1, const cd* tw2,
+                                    const int* gtab, int gq, const JbEpi& ep, double* grad, int planes, int n_sm,
+                                    jb_stream_t st) {
+        const int NC = (g.n + 1) / 2, NW = (NC + SW - 1) / SW;
+        const size_t smem = jb_rows5_smem<F3, SW>(g.n);
+        auto kern = k_rows_c2r5<F3, SW, ADJ>;
+        int grid = rows5_grid(kern, NW * 32, smem, (long)planes * g.N, n_sm);
+        return jb_launch(kern, dim3(grid), dim3(NW * 32), smem, st, g, src, tw1, tw2, wgt, gtab, gq, ep, grad, planes);
+    }
+    static cudaError_t rows5_fwd(const JbGeom& g, const cd* bufA, const cd* tw1, const cd* tw2, const int* gtab, int gq,
+                                 const JbEpi& ep, int planes, int n_sm, jb_stream_t st) {
+        if constexpr (PIPE == 2) {
+            if (rows5_sw(g) == 1)
+                return rows5_launch<1, false>(g, bufA, nullptr, tw1, tw2, gtab, gq, ep, nullptr, planes, n_sm, st);
+            return rows5_launch<2, false>(g, bufA, nullptr, tw1, tw2, gtab, gq, ep, nullptr, planes, n_sm, st);
+        } else {
+            (void)g; (void)bufA; (void)tw1; (void)tw2; (void)gtab; (void)gq; (void)ep; (void)planes; (void)n_sm; (void)st;
+            return (cudaError_t)1;
+        }
+    }
+    static cudaError_t rows5_adj(const JbGeom& g, const cd* bufB, const double* wgt, const cd* tw1, const cd* tw2,
+                                 const int* gtab, int gq, double* grad, int planes_se, int n_sm, jb_stream_t st) {
+        if constexpr (PIPE == 2) {
+            JbEpi ep; memset(&ep, 0, sizeof(ep));
+            if (rows5_sw(g) == 1)
+                return rows5_launch<1, true>(g, bufB, wgt, tw1, tw2, gtab, gq, ep, grad, planes_se, n_sm, st);
+            return rows5_launch<2, true>(g, bufB, wgt, tw1, tw2, gtab, gq, ep, grad, planes_se, n_sm, st);
+        } else {
+            (void)g; (void)bufB; (void)wgt; (void)tw1; (void)tw2; (void)gtab; (void)gq; (void)grad; (void)planes_se; (void)n_sm; (void)st;
+            return (cudaError_t)1;
+        }
+    }
     static cudaError_t prep_rows(const JbGeom& g, const JbKsrc& ks, const cd* tw_nk, cd* scratch, int rpc,
                                  int threads, jb_stream_t st) {
         size_t smem = jb_al16((size_t)rpc * FP::LS * sizeof(cd)) + 16;
@@ -219,7 +292,7 @@ struct JbOpsImpl {
                                    rows_fwd, rows_adj_in, cols, cols_pipe,
                                    rows_out, rows_adj_out, rows_out_pipe_smem, rows_adj_out_pipe_smem, rows_out_pipe,
                                    rows_adj_out_pipe, rows_out_r3_smem, rows_adj_out_r3_smem, rows_out_r3, rows_adj_out_r3,
-                                   prep_rows, prep_cols};
+                                   rows5_smem, rows5_gather, rows5_fwd, rows5_adj, prep_rows, prep_cols};
         return &t;
     }
 };

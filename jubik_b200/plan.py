@@ -247,12 +247,20 @@ class ResponsePlan:
         S = x.shape[0]
         energy = torch.empty((S,), dtype=torch.float64, device=self.device)
         grad = torch.empty_like(x)
-        ms = (C.c_float * 12)()
+        ms = (C.c_float * 48)()
         n = C.c_int(0)
         self.raw.call("jubik_poisson_profile", C.c_void_p(x.data_ptr()), S, C.c_void_p(energy.data_ptr()),
                       C.c_void_p(grad.data_ptr()), ms, C.byref(n), self._stream())
+        vals = [float(ms[i]) for i in range(n.value)]
+        E = self.info["E"]
+        if n.value == 6 * E + 1 and n.value not in self.KERNEL_NAMES:
+            # one energy bin at a time: (rows_fwd, cols_fwd, rows_out, rows_adj_in, cols_adj, rows_adj_out) x E, reduce
+            per = ("rows_fwd", "cols_fwd", "rows_out", "rows_adj_in", "cols_adj", "rows_adj_out")
+            out = {k: sum(vals[6 * e + i] for e in range(E)) for i, k in enumerate(per)}
+            out["reduce"] = vals[-1]
+            return energy, grad, out
         names = self.KERNEL_NAMES.get(n.value, tuple("k%d" % i for i in range(n.value)))
-        return energy, grad, dict(zip(names, [float(ms[i]) for i in range(n.value)]))
+        return energy, grad, dict(zip(names, vals))
 
     @property
     def launch_count(self):
