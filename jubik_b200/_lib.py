@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libjubik_b200.so")
+# JUBIK_B200_LIB: development hook to load a differently tuned build of the same CUDA library (tools/build_variant.py)
+LIB_PATH = os.environ.get("JUBIK_B200_LIB") or os.path.join(HERE, "libjubik_b200.so")
 
 KERNEL_FULL, KERNEL_CROPPED = 0, 1
 DATA_F64, DATA_I64 = 0, 1

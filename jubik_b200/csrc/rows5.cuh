@@ -16,6 +16,13 @@
 #pragma once
 #include "rows3.cuh"
 
+#ifndef JB_R5_B
+#define JB_R5_B 3     // spectrum elements x row-patches whose loads a lane keeps in flight (per sequence)
+#endif
+#ifndef JB_R5_CPS
+#define JB_R5_CPS 6   // CTAs per SM the SW = 1 kernel is register-limited to
+#endif
+
 template <class F3, int SW>
 struct Rows5 {
     static constexpr int L = F3::L, R1 = F3::R1, R2 = F3::R2, R3 = F3::R3, M = F3::M;
@@ -166,60 +173,86 @@ inline int jb_rows5_gather_table(const JbGeom& g, bool adj, int maxq, int* tab) 
 
 // one image row: summation over the covering row-patches (x modules) and assembly of the warp's SW sequences
 //   pbase[s][0/1] : row 0 of column blocks ia / ib of the first source plane; tstride: elements between modules (ADJ)
-// All loads of one spectrum element (SW sequences x 2 rows x cnt row-patches) are issued before the first use, so a
-// warp pays one DRAM round trip per element (the loads are volatile asm: the compiler keeps this order).
+// CNT (row-patches covering the row) is a compile-time constant and the loads of EG consecutive spectrum elements
+// (EG x SW sequences x 2 rows x CNT row-patches) are all issued before the first use, so a warp pays one DRAM
+// round trip per EG elements (the loads are volatile asm: the compiler keeps this order).
+template <class F3, int SW, bool ADJ, int CNT, int EG>
+JB_D void jb_rows5_assemble_c(cd* tile, const cd* const (&pbase)[SW][2], const bool (&has)[SW][2], size_t tstride, int T,
+                              const int (&rowoff)[JB_MAXQ], const double (&wr)[JB_MAXQ],
+                              const unsigned* __restrict__ atab, int lane) {
+    using R = Rows5<F3, SW>;
+    constexpr int NG = (R::NE + EG - 1) / EG;
+#pragma unroll 1
+    for (int gi = 0; gi < NG; ++gi) {
+        const int e0 = gi * EG;
+        cd xa[EG][SW], xb[EG][SW];
+        static_for<0, EG>([&](auto ee) {
+            static_for<0, SW>([&](auto ss) { xa[ee][ss] = cd_make(0.0, 0.0); xb[ee][ss] = cd_make(0.0, 0.0); });
+        });
+        size_t toff = lane + 32 * e0;
+        for (int t = 0; t < T; ++t, toff += tstride) {
+            cd va[EG][SW][CNT], vb[EG][SW][CNT];
+            static_for<0, EG>([&](auto ee) {
+                constexpr int e = ee;
+                if (lane + 32 * (e0 + e) < R::PHL) {
+                    static_for<0, SW>([&](auto ss) {
+                        constexpr int s = ss;
+                        static_for<0, CNT>([&](auto qq) {
+                            constexpr int q = qq;
+                            va[e][s][q] = jb_ld_stream(pbase[s][0] + toff + 32 * e + rowoff[q]);
+                            vb[e][s][q] = jb_ld_stream(pbase[s][1] + toff + 32 * e + rowoff[q]);
+                        });
+                    });
+                }
+            });
+            static_for<0, EG>([&](auto ee) {
+                constexpr int e = ee;
+                if (lane + 32 * (e0 + e) < R::PHL) {
+                    static_for<0, SW>([&](auto ss) {
+                        constexpr int s = ss;
+                        static_for<0, CNT>([&](auto qq) {
+                            constexpr int q = qq;
+                            if (ADJ) {
+                                xa[e][s].x += wr[q] * va[e][s][q].x; xa[e][s].y += wr[q] * va[e][s][q].y;
+                                xb[e][s].x += wr[q] * vb[e][s][q].x; xb[e][s].y += wr[q] * vb[e][s][q].y;
+                            } else {
+                                xa[e][s] = cd_add(xa[e][s], va[e][s][q]); xb[e][s] = cd_add(xb[e][s], vb[e][s][q]);
+                            }
+                        });
+                    });
+                }
+            });
+        }
+        static_for<0, EG>([&](auto ee) {
+            constexpr int e = ee;
+            const int k = lane + 32 * (e0 + e);
+            if (k < R::PHL) {
+                const unsigned ad = atab[(e0 + e) * 32 + lane];
+                const int adk = (int)(ad & 0xffffu), adm = (int)(ad >> 16);
+                static_for<0, SW>([&](auto ss) {
+                    constexpr int s = ss;
+                    if (has[s][0]) {
+                        cd a = xa[e][s], b = has[s][1] ? xb[e][s] : cd_make(0.0, 0.0);
+                        cd* ts = tile + s * R::SEQ;
+                        ts[adk] = cd_make(a.x - b.y, a.y + b.x);
+                        if (adm != 0xffff) ts[adm] = cd_make(a.x + b.y, b.x - a.y);
+                    }
+                });
+            }
+        });
+    }
+}
+
+// loads in flight per lane and round trip: EG * SW * 2 * CNT, kept at <= 16 (64 registers)
 template <class F3, int SW, bool ADJ>
 JB_D void jb_rows5_assemble(cd* tile, const cd* const (&pbase)[SW][2], const bool (&has)[SW][2], size_t tstride, int T,
                             int cnt, const int (&rowoff)[JB_MAXQ], const double (&wr)[JB_MAXQ],
                             const unsigned* __restrict__ atab, int lane) {
-    using R = Rows5<F3, SW>;
-#pragma unroll 1
-    for (int e = 0; e < R::NE; ++e) {
-        const int k = lane + 32 * e;
-        if (k < R::PHL) {
-            const unsigned ad = atab[e * 32 + lane];
-            const int adk = (int)(ad & 0xffffu), adm = (int)(ad >> 16);
-            cd xa[SW], xb[SW];
-            static_for<0, SW>([&](auto ss) { constexpr int s = ss; xa[s] = cd_make(0.0, 0.0); xb[s] = xa[s]; });
-            size_t toff = k;
-            for (int t = 0; t < T; ++t, toff += tstride) {
-                cd va[SW][JB_MAXQ], vb[SW][JB_MAXQ];
-                static_for<0, SW>([&](auto ss) {
-                    constexpr int s = ss;
-                    static_for<0, JB_MAXQ>([&](auto qq) {
-                        constexpr int q = qq;
-                        if (q < cnt) {
-                            va[s][q] = jb_ld_stream(pbase[s][0] + toff + rowoff[q]);
-                            vb[s][q] = jb_ld_stream(pbase[s][1] + toff + rowoff[q]);
-                        }
-                    });
-                });
-                static_for<0, SW>([&](auto ss) {
-                    constexpr int s = ss;
-                    static_for<0, JB_MAXQ>([&](auto qq) {
-                        constexpr int q = qq;
-                        if (q < cnt) {
-                            if (ADJ) {
-                                xa[s].x += wr[q] * va[s][q].x; xa[s].y += wr[q] * va[s][q].y;
-                                xb[s].x += wr[q] * vb[s][q].x; xb[s].y += wr[q] * vb[s][q].y;
-                            } else {
-                                xa[s] = cd_add(xa[s], va[s][q]); xb[s] = cd_add(xb[s], vb[s][q]);
-                            }
-                        }
-                    });
-                });
-            }
-            static_for<0, SW>([&](auto ss) {
-                constexpr int s = ss;
-                if (has[s][0]) {
-                    cd a = xa[s], b = has[s][1] ? xb[s] : cd_make(0.0, 0.0);
-                    cd* ts = tile + s * R::SEQ;
-                    ts[adk] = cd_make(a.x - b.y, a.y + b.x);
-                    if (adm != 0xffff) ts[adm] = cd_make(a.x + b.y, b.x - a.y);
-                }
-            });
-        }
-    }
+    constexpr int B = JB_R5_B / SW;   // EG * CNT budget
+    if (cnt == 1) jb_rows5_assemble_c<F3, SW, ADJ, 1, (B >= 4 ? 4 : B)>(tile, pbase, has, tstride, T, rowoff, wr, atab, lane);
+    else if (cnt == 2) jb_rows5_assemble_c<F3, SW, ADJ, 2, (B / 2 >= 1 ? B / 2 : 1)>(tile, pbase, has, tstride, T, rowoff, wr, atab, lane);
+    else if (cnt == 3) jb_rows5_assemble_c<F3, SW, ADJ, 3, (B / 3 >= 1 ? B / 3 : 1)>(tile, pbase, has, tstride, T, rowoff, wr, atab, lane);
+    else if (cnt == 4) jb_rows5_assemble_c<F3, SW, ADJ, 4, (B / 4 >= 1 ? B / 4 : 1)>(tile, pbase, has, tstride, T, rowoff, wr, atab, lane);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -231,7 +264,7 @@ JB_D void jb_rows5_assemble(cd* tile, const cd* const (&pbase)[SW][2], const boo
 template <class F3, int SW, bool ADJ>
 // SW = 1: one sequence per warp, CTAs of <= 4 warps (n <= 8), 72 registers so that 7 CTAs = 28 warps fit an SM;
 // SW = 2: two sequences per warp for wider patch grids (up to 16 warps per CTA)
-JB_GLOBAL void JB_LB((SW == 1 ? 128 : 512), (SW == 1 ? 6 : 1))
+JB_GLOBAL void JB_LB((SW == 1 ? 128 : 512), (SW == 1 ? JB_R5_CPS : 1))
 k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, const cd* __restrict__ tw2,
             const double* __restrict__ wgt, const int* __restrict__ gtab, int GQ, JbEpi ep, double* __restrict__ grad,
             int planes) {
