@@ -111,6 +111,7 @@ struct jubik_plan {
     int use_pipe = 0, n_sm = 1;
     int split_epi = 1, nblk_epi = 1;  // Poisson/metric epilogue as a separate elementwise kernel
     int rows_r3_out = 0, rows_r3_adj = 0;  // packed-complex three-stage c2r kernels (rows3.cuh)
+    int sweep = 0;                         // column pass accumulates over the row-patches (cols3.cuh SWEEP + rows5 presum)
     int chunk_e = 0;                       // fused energy+gradient runs one energy bin at a time (L2 residency)
     int rows5 = 0;                         // warp-private c2r kernels with the fused Poisson epilogue (rows5.cuh)
     int* gtab_fwd = nullptr;               // rows5 overlap-add gather tables [gq][N]
@@ -393,6 +394,9 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
         }
     }
     p->chunk_e = getenv("JUBIK_B200_CHUNK_E") ? 1 : 0;
+    // measured on B200 (C2): the read-add-write costs the column pass more (+48 us per direction) than the row pass
+    // gains from reading one summed row (-22 / -13 us), so the sweep stays an opt-in experiment
+    p->sweep = (p->rows5 && getenv("JUBIK_B200_SWEEP")) ? 1 : 0;
     if (p->rows5 && !getenv("JUBIK_B200_SPLIT_EPI")) { p->split_epi = 0; p->nblk_out = N; }   // fused epilogue: one partial per row
     if (p->use_pipe) {
         std::string err;
@@ -487,12 +491,12 @@ static int run_forward_g(jubik_plan* p, const JbGeom& g, const double* x, int S,
     const JbFftOps* o = p->ops;
     JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.Es, p->rpc_in, p->thr_rows, p->fast_rows, st));
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, false, p->src_fwd, p->bufA, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, false, p->sweep, p->src_fwd, p->bufA, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
     if (p->rows5) {
-        JB_LAUNCHED(p, o->rows5_fwd(g, p->bufA, p->tw1, p->tw2, p->gtab_fwd, p->gq_fwd, ep, S * g.T * g.Es, p->n_sm, st));
+        JB_LAUNCHED(p, o->rows5_fwd(g, p->bufA, p->tw1, p->tw2, p->gtab_fwd, p->gq_fwd, ep, p->sweep, S * g.T * g.Es, p->n_sm, st));
     } else if (p->rows_r3_out && ep.mode != JB_EPI_POISSON) {
         JB_LAUNCHED(p, o->rows_out_r3(g, p->bufA, p->tw1, p->tw2, ep, S * g.T * g.Es, p->qmax, p->n_sm, st));
     } else if (p->rows_pipe_out && ep.mode != JB_EPI_POISSON) {
@@ -512,12 +516,12 @@ static int run_adjoint_g(jubik_plan* p, const JbGeom& g, const double* gin, cons
     const JbFftOps* o = p->ops;
     JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.Es, p->rpc_in, p->thr_rows, p->fast_rows, st));
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, true, p->src_adj, p->bufB, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, true, p->sweep, p->src_adj, p->bufB, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
     if (p->rows5) {
-        JB_LAUNCHED(p, o->rows5_adj(g, p->bufB, p->wgt, p->tw1, p->tw2, p->gtab_adj, p->gq_adj, out, S * g.Es, p->n_sm, st));
+        JB_LAUNCHED(p, o->rows5_adj(g, p->bufB, p->wgt, p->tw1, p->tw2, p->gtab_adj, p->gq_adj, out, p->sweep, S * g.Es, p->n_sm, st));
     } else if (p->rows_r3_adj) {
         JB_LAUNCHED(p, o->rows_adj_out_r3(g, p->bufB, p->wgt, p->tw1, p->tw2, out, S * g.Es, p->qmax, p->n_sm, st));
     } else if (p->rows_pipe_adj) {

@@ -32,6 +32,9 @@ struct JbColInfo {
     int vlo, vhi;       // valid (in-image) input rows of the tile
     int out_p0, out_rows;
     int ncols;          // valid columns in this strip (PH - strip*CB, capped at CB)
+    int row_base;       // sweep mode: image row of output row 0 of this patch (may be negative)
+    long long sw_off;   // sweep mode: element offset of (slab, image row 0, column strip*CB) in the summed buffer
+    int rmw_end;        // sweep mode: image rows < rmw_end were already written by the previous patch of the chain
     int pad;
 };
 
@@ -137,7 +140,12 @@ struct Cols3 {
 // --------------------------------------------------------------------------------------------------------
 // Persistent TMA pipeline, 512 threads, 2-stage ring of (tile, K^ slice); thread 0 refills a slot as soon as
 // every warp has pulled its stage-1' operands out of it.  dynamic smem = 4*L*CB*16 + (L + M)*16 + 64.
-template <class F3, int CB, bool ADJ>
+// SWEEP: a CTA walks whole column chains (plane, column block i, strip) through the row-patches j = 0..n-1 and
+// ACCUMULATES the patch outputs that land on the same image row into one summed buffer (planes*n, N, PH) -- plain
+// store on first touch, read-add-write (L2-resident, written by this CTA one item earlier) otherwise; fixed order
+// j ascending, so the sums are reproducible.  The adjoint applies the window row weight before accumulating.  The
+// row pass then reads ONE spectrum row per (image row, i) instead of one per covering patch.
+template <class F3, int CB, bool ADJ, bool SWEEP>
 JB_GLOBAL void JB_LB((Cols3<F3, CB>::THREADS), (Cols3<F3, CB>::CPS))
 k_cols3_pipe(const
 #ifndef JB_EMU
@@ -159,18 +167,39 @@ k_cols3_pipe(const
     double* rw = reinterpret_cast<double*>(info + 2);  // window row weights (forward direction only)
     const int nstrips = (g.PH + CB - 1) / CB;
     const long nitems = (long)planes * g.n * g.n * nstrips;
+    const long nchains = (long)planes * g.n * nstrips;
     const int tid = threadIdx.x;
     const int PH = g.PH;
+    // local iteration -> global item ((plane*n*n + i*n + j)*nstrips + strip), -1 past the end
+    auto item_of = [&](long it_) -> long {
+        if (!SWEEP) {
+            long v = (long)blockIdx.x + it_ * (long)gridDim.x;
+            return v < nitems ? v : -1;
+        }
+        const long c = (long)blockIdx.x + (it_ / g.n) * (long)gridDim.x;
+        if (c >= nchains) return -1;
+        const int j = (int)(it_ % g.n), strip = (int)(c % nstrips);
+        const long r = c / nstrips;
+        const int i = (int)(r % g.n);
+        const long pl = r / g.n;
+        return ((pl * g.n + i) * g.n + j) * nstrips + strip;
+    };
     auto fill_info = [&](const JbColItem& ci, int s_) {
         JbColInfo& f = info[s_];
         f.out_off = (long long)ci.out_off + (long long)ci.strip * CB;
         f.vlo = ci.vlo; f.vhi = ci.vhi; f.out_p0 = ci.out_p0; f.out_rows = ci.out_rows;
         int nc = PH - ci.strip * CB;
         f.ncols = nc < CB ? nc : CB;
+        if (SWEEP) {
+            const int back = ADJ ? g.hp : g.hp + g.m;    // image row of output row 0 = offs[j] - back
+            f.row_base = g.offs[ci.j] - back;
+            f.sw_off = ((long long)(ci.plane * g.n + ci.i) * g.N) * PH + (long long)ci.strip * CB;
+            f.rmw_end = ci.j > 0 ? g.offs[ci.j - 1] - back + ci.out_rows : -(1 << 30);
+        }
     };
     for (int i = tid; i < L; i += JB_C3_THREADS) tw1[i] = tw1g[i];
     for (int i = tid; i < M; i += JB_C3_THREADS) tw2[i] = tw2g[i];
-    if (!ADJ) for (int i = tid; i < g.w; i += JB_C3_THREADS) rw[i] = wgt[i];
+    if (!ADJ || SWEEP) for (int i = tid; i < g.w; i += JB_C3_THREADS) rw[i] = wgt[i];
 #ifndef JB_EMU
     auto issue_loads = [&](long item_, int s_) {
         JbColItem ci = jb_col_item<L, CB, ADJ>(g, item_, nstrips);
@@ -200,13 +229,14 @@ k_cols3_pipe(const
         jb_mbar_init(&bars[2], JB_C3_THREADS / 32);
         jb_mbar_init(&bars[3], JB_C3_THREADS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if ((long)blockIdx.x < nitems) issue_loads(blockIdx.x, 0);
-        if ((long)blockIdx.x + gridDim.x < nitems) issue_loads((long)blockIdx.x + gridDim.x, 1);
+        if (item_of(0) >= 0) issue_loads(item_of(0), 0);
+        if (item_of(1) >= 0) issue_loads(item_of(1), 1);
     }
 #endif
     JB_SYNC();
-    long item = blockIdx.x;
-    for (unsigned it = 0; item < nitems; ++it, item += gridDim.x) {
+    for (unsigned it = 0;; ++it) {
+        const long item = item_of(it);
+        if (item < 0) break;
         const int s = it & 1;
         cd* tile = tile0 + s * TILE;
         cd* kh = kh0 + s * TILE;
@@ -242,28 +272,52 @@ k_cols3_pipe(const
             __syncwarp();
             if ((tid & 31) == 0) jb_mbar_arrive(&bars[2 + s]);
             if (tid == 0) {
-                long nxt = item + 2 * (long)gridDim.x;
-                if (nxt < nitems) {
+                long nxt = item_of((long)it + 2);
+                if (nxt >= 0) {
                     jb_mbar_wait<false>(&bars[2 + s], (it >> 1) & 1);
                     issue_loads(nxt, s);
                 }
             }
 #endif
             if (act) {
-                dft<R1, +1>(v);
                 const int m = tid / CB, b = tid - m * CB;
                 const int q0 = m - f.out_p0;            // output row of n1 = 0 (may be negative)
-                const long long stride = (long long)M * PH;
-                cd* ob = out + f.out_off + b + (long long)q0 * PH;
-                if (b < f.ncols) {
+                if (SWEEP) {
+                    cd* ob = out + f.sw_off + b;
+                    cd old[R1];
+                    // previous partial sums first (L2 hits), so that their latency hides behind the last butterfly
                     static_for<0, R1>([&](auto nn) {
                         constexpr int n1 = nn;
-                        int q = q0 + M * n1;
-                        if (q >= 0 && q < f.out_rows) ob[n1 * stride] = v[n1];
+                        const int q = q0 + M * n1, r = f.row_base + q;
+                        old[n1] = cd_make(0.0, 0.0);
+                        if (b < f.ncols && q >= 0 && q < f.out_rows && r >= 0 && r < g.N && r < f.rmw_end)
+                            old[n1] = jb_ld_cg(ob + (long long)r * PH);
                     });
+                    dft<R1, +1>(v);
+                    static_for<0, R1>([&](auto nn) {
+                        constexpr int n1 = nn;
+                        const int q = q0 + M * n1, r = f.row_base + q;
+                        if (b < f.ncols && q >= 0 && q < f.out_rows && r >= 0 && r < g.N) {
+                            cd y = v[n1];
+                            if (ADJ) y = cd_scale(y, rw[q]);
+                            ob[(long long)r * PH] = cd_add(old[n1], y);
+                        }
+                    });
+                } else {
+                    dft<R1, +1>(v);
+                    const long long stride = (long long)M * PH;
+                    cd* ob = out + f.out_off + b + (long long)q0 * PH;
+                    if (b < f.ncols) {
+                        static_for<0, R1>([&](auto nn) {
+                            constexpr int n1 = nn;
+                            int q = q0 + M * n1;
+                            if (q >= 0 && q < f.out_rows) ob[n1 * stride] = v[n1];
+                        });
+                    }
                 }
             }
         }
+        // (the stage barriers of the next item order this item's stores before the next read-add-write)
     }
 }
 

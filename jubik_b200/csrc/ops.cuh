@@ -24,8 +24,9 @@ struct JbFftOps {
     cudaError_t (*cols)(const JbGeom&, bool adj, const cd* in, cd* out, const cd* khat, const cd* tw_nk,
                         const double* wgt, int planes, int threads, jb_stream_t);
     // three-stage TMA pipeline (pipe == 2): twa/twb = stage-1/stage-2 twiddle tables
-    cudaError_t (*cols_pipe)(const JbGeom&, bool adj, const JbTileSrc& src, cd* out, const cd* khat, const cd* twa,
-                             const cd* twb, const double* wgt, int planes, int ctas, jb_stream_t);
+    // sweep != 0: outputs accumulated over the row-patches into (planes*n, N, PH) (cols3.cuh)
+    cudaError_t (*cols_pipe)(const JbGeom&, bool adj, int sweep, const JbTileSrc& src, cd* out, const cd* khat,
+                             const cd* twa, const cd* twb, const double* wgt, int planes, int ctas, jb_stream_t);
     cudaError_t (*rows_out)(const JbGeom&, const cd* bufA, const cd* tw_kn, const JbEpi&, int planes, int rpc,
                             int threads, int fast, jb_stream_t);
     cudaError_t (*rows_adj_out)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw_kn, double* grad,
@@ -47,10 +48,11 @@ struct JbFftOps {
     // warp-private c2r kernels (rows5.cuh; need pipe == 2); fwd: ep.mode may be JB_EPI_POISSON (partials [STE][N])
     size_t (*rows5_smem)(const JbGeom&);
     int (*rows5_gather)(const JbGeom&, int adj, int maxq, int* host_tab);   // [maxq][N] table, returns slots used
+    // presum != 0: the source is the column pass's summed buffer (planes*n, N, PH) (sweep mode)
     cudaError_t (*rows5_fwd)(const JbGeom&, const cd* bufA, const cd* tw1, const cd* tw2, const int* gtab, int gq,
-                             const JbEpi&, int planes, int n_sm, jb_stream_t);
+                             const JbEpi&, int presum, int planes, int n_sm, jb_stream_t);
     cudaError_t (*rows5_adj)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw1, const cd* tw2,
-                             const int* gtab, int gq, double* grad, int planes_se, int n_sm, jb_stream_t);
+                             const int* gtab, int gq, double* grad, int presum, int planes_se, int n_sm, jb_stream_t);
     cudaError_t (*prep_rows)(const JbGeom&, const JbKsrc&, const cd* tw_nk, cd* scratch, int rpc, int threads,
                              jb_stream_t);
     // layout 0: K^ in the two-pass register order (tw = tw_nk); layout 2: three-stage order (twa/twb = tw1/tw2)
@@ -63,18 +65,25 @@ inline size_t jb_al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 template <class FP, int CB, int PIPE, class F3>
 struct JbOpsImpl {
-    static cudaError_t cols_pipe(const JbGeom& g, bool adj, const JbTileSrc& src, cd* out, const cd* khat,
+    static cudaError_t cols_pipe(const JbGeom& g, bool adj, int sweep, const JbTileSrc& src, cd* out, const cd* khat,
                                  const cd* twa, const cd* twb, const double* wgt, int planes, int ctas, jb_stream_t st) {
         if constexpr (PIPE == 2) {
             size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd) + 32 +
                           2 * sizeof(JbColInfo) + (size_t)g.w * sizeof(double) + 32;
-            if (adj) return jb_launch(k_cols3_pipe<F3, CB, true>, dim3(ctas * Cols3<F3, CB>::CPS), dim3(Cols3<F3, CB>::THREADS), smem, st, src, g,
-                                      out, khat, twa, twb, wgt, planes);
-            return jb_launch(k_cols3_pipe<F3, CB, false>, dim3(ctas * Cols3<F3, CB>::CPS), dim3(Cols3<F3, CB>::THREADS), smem, st, src, g, out,
-                             khat, twa, twb, wgt, planes);
+            const dim3 grid(ctas * Cols3<F3, CB>::CPS), block(Cols3<F3, CB>::THREADS);
+            if (sweep) {
+                if (adj) return jb_launch(k_cols3_pipe<F3, CB, true, true>, grid, block, smem, st, src, g, out, khat, twa,
+                                          twb, wgt, planes);
+                return jb_launch(k_cols3_pipe<F3, CB, false, true>, grid, block, smem, st, src, g, out, khat, twa, twb,
+                                 wgt, planes);
+            }
+            if (adj) return jb_launch(k_cols3_pipe<F3, CB, true, false>, grid, block, smem, st, src, g, out, khat, twa,
+                                      twb, wgt, planes);
+            return jb_launch(k_cols3_pipe<F3, CB, false, false>, grid, block, smem, st, src, g, out, khat, twa, twb, wgt,
+                             planes);
         } else {
-            (void)g; (void)adj; (void)src; (void)out; (void)khat; (void)twa; (void)twb; (void)wgt; (void)planes;
-            (void)ctas; (void)st;
+            (void)g; (void)adj; (void)sweep; (void)src; (void)out; (void)khat; (void)twa; (void)twb; (void)wgt;
+            (void)planes; (void)ctas; (void)st;
             return (cudaError_t)1;
         }
     }
@@ -238,34 +247,36 @@ struct JbOpsImpl {
     }
     template <int SW, bool ADJ>
     static cudaError_t rows5_launch(const JbGeom& g, const cd* src, const double* wgt, const cd* tw1, const cd* tw2,
-                                    const int* gtab, int gq, const JbEpi& ep, double* grad, int planes, int n_sm,
-                                    jb_stream_t st) {
+                                    const int* gtab, int gq, const JbEpi& ep, double* grad, int presum, int planes,
+                                    int n_sm, jb_stream_t st) {
         const int NC = (g.n + 1) / 2, NW = (NC + SW - 1) / SW;
         const size_t smem = jb_rows5_smem<F3, SW>(g.n);
         auto kern = k_rows_c2r5<F3, SW, ADJ>;
         int grid = rows5_grid(kern, NW * 32, smem, (long)planes * g.N, n_sm);
-        return jb_launch(kern, dim3(grid), dim3(NW * 32), smem, st, g, src, tw1, tw2, wgt, gtab, gq, ep, grad, planes);
+        return jb_launch(kern, dim3(grid), dim3(NW * 32), smem, st, g, src, tw1, tw2, wgt, gtab, gq, ep, grad, presum,
+                         planes);
     }
     static cudaError_t rows5_fwd(const JbGeom& g, const cd* bufA, const cd* tw1, const cd* tw2, const int* gtab, int gq,
-                                 const JbEpi& ep, int planes, int n_sm, jb_stream_t st) {
+                                 const JbEpi& ep, int presum, int planes, int n_sm, jb_stream_t st) {
         if constexpr (PIPE == 2) {
             if (rows5_sw(g) == 1)
-                return rows5_launch<1, false>(g, bufA, nullptr, tw1, tw2, gtab, gq, ep, nullptr, planes, n_sm, st);
-            return rows5_launch<2, false>(g, bufA, nullptr, tw1, tw2, gtab, gq, ep, nullptr, planes, n_sm, st);
+                return rows5_launch<1, false>(g, bufA, nullptr, tw1, tw2, gtab, gq, ep, nullptr, presum, planes, n_sm, st);
+            return rows5_launch<2, false>(g, bufA, nullptr, tw1, tw2, gtab, gq, ep, nullptr, presum, planes, n_sm, st);
         } else {
-            (void)g; (void)bufA; (void)tw1; (void)tw2; (void)gtab; (void)gq; (void)ep; (void)planes; (void)n_sm; (void)st;
+            (void)g; (void)bufA; (void)tw1; (void)tw2; (void)gtab; (void)gq; (void)ep; (void)presum; (void)planes; (void)n_sm; (void)st;
             return (cudaError_t)1;
         }
     }
     static cudaError_t rows5_adj(const JbGeom& g, const cd* bufB, const double* wgt, const cd* tw1, const cd* tw2,
-                                 const int* gtab, int gq, double* grad, int planes_se, int n_sm, jb_stream_t st) {
+                                 const int* gtab, int gq, double* grad, int presum, int planes_se, int n_sm,
+                                 jb_stream_t st) {
         if constexpr (PIPE == 2) {
             JbEpi ep; memset(&ep, 0, sizeof(ep));
             if (rows5_sw(g) == 1)
-                return rows5_launch<1, true>(g, bufB, wgt, tw1, tw2, gtab, gq, ep, grad, planes_se, n_sm, st);
-            return rows5_launch<2, true>(g, bufB, wgt, tw1, tw2, gtab, gq, ep, grad, planes_se, n_sm, st);
+                return rows5_launch<1, true>(g, bufB, wgt, tw1, tw2, gtab, gq, ep, grad, presum, planes_se, n_sm, st);
+            return rows5_launch<2, true>(g, bufB, wgt, tw1, tw2, gtab, gq, ep, grad, presum, planes_se, n_sm, st);
         } else {
-            (void)g; (void)bufB; (void)wgt; (void)tw1; (void)tw2; (void)gtab; (void)gq; (void)grad; (void)planes_se; (void)n_sm; (void)st;
+            (void)g; (void)bufB; (void)wgt; (void)tw1; (void)tw2; (void)gtab; (void)gq; (void)grad; (void)presum; (void)planes_se; (void)n_sm; (void)st;
             return (cudaError_t)1;
         }
     }

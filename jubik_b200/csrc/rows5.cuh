@@ -267,7 +267,7 @@ template <class F3, int SW, bool ADJ>
 JB_GLOBAL void JB_LB((SW == 1 ? 128 : 512), (SW == 1 ? JB_R5_CPS : 1))
 k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, const cd* __restrict__ tw2,
             const double* __restrict__ wgt, const int* __restrict__ gtab, int GQ, JbEpi ep, double* __restrict__ grad,
-            int planes) {
+            int presum, int planes) {
     using R = Rows5<F3, SW>;
     JB_SMEM(unsigned char, smraw);
     const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH;
@@ -278,12 +278,14 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
     int* itab = reinterpret_cast<int*>(atab + R::NE * 32);
     double* red = reinterpret_cast<double*>(itab + R::NR * 32);
     cd* tile = tiles + (size_t)wid * SW * R::SEQ;
-    const int ROWS = ADJ ? g.w : g.P;            // rows per patch in src
+    const int ROWS = ADJ ? g.w : g.P;            // rows per patch (window length)
     const int shift = ADJ ? hp : hp + m;         // u = r + shift - offs[j]
     const int p0 = ADJ ? m : 0;                  // valid window samples [p0, p0 + ROWS)
     const size_t nn2 = (size_t)n * n;
-    const size_t plane_sz = nn2 * ROWS * PH;
-    const size_t istride = (size_t)n * ROWS * PH;
+    // source layout: per-patch rows (planes, n*n, ROWS, PH), or -- presum -- the column pass's buffer of spectra
+    // already summed over the covering row-patches (and row-weighted in the adjoint): (planes*n, N, PH)
+    const size_t plane_sz = presum ? (size_t)n * N * PH : nn2 * ROWS * PH;
+    const size_t istride = presum ? (size_t)N * PH : (size_t)n * ROWS * PH;
     for (int i = tid; i < R::NE * 32; i += NT) {
         int k = i;   // e*32 + lane == frequency
         unsigned lo = (k < R::PHL) ? (unsigned)R::addr_of_freq(k) : 0u;
@@ -317,6 +319,7 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
                 ++cnt;
             }
         }
+        if (presum && cnt > 0) { cnt = 1; rowoff[0] = r * PH; wr[0] = 1.0; }
         int ste = 0, te = 0, se = 0, T = 1;
         const cd* plane0;
         size_t tstride = 0;
