@@ -36,6 +36,7 @@ struct JbColInfo {
     long long sw_off;   // sweep mode: element offset of (slab, image row 0, column strip*CB) in the summed buffer
     int rmw_end;        // sweep mode: image rows < rmw_end were already written by the previous patch of the chain
     int pad;
+    long long k_off;    // element offset of this item's K^ slice (direct-load mode)
 };
 
 // twiddle tables (host-built, uploaded once): tw1[k1*M + m] = W_L^{m k1}, tw2[k2*R3 + n3] = W_M^{n3 k2}
@@ -45,6 +46,7 @@ struct Cols3 {
     static constexpr int I1 = M * CB, I2 = R1 * R3 * CB, I3 = R1 * R2 * CB;
     static constexpr int THREADS = (jb_c3_max3(I1, I2, I3) + 31) / 32 * 32;
     static constexpr int CPS = THREADS <= 256 ? 2 : 1;   // CTAs per SM the pipeline is sized for
+    static constexpr int CPS_KD = THREADS <= 256 ? 3 : 1; // ... when K^ is read straight from L2 (no staging ring)
     static_assert(THREADS <= 1024, "one item per thread and stage");
 
     // forward stage 1 with zero rows outside [vlo, vhi); rw != nullptr: multiply tile row p by rw[p - p0]
@@ -94,17 +96,20 @@ struct Cols3 {
         dft<R3, -1>(v);
     }
     // stage 3: forward, * K^ (conj for the adjoint), inverse -- the spectrum never leaves the registers
-    template <bool ADJ>
+    // KD: kh is the slice in GLOBAL memory (L2-warm thanks to the producer's prefetch): the loads are issued first
+    // and land while the forward butterfly runs
+    template <bool ADJ, bool KD = false>
     static JB_D void s3_mid(cd* tile, const cd* kh, int w) {
         if (w >= I3) return;
         const int c = w / CB, b = w - c * CB;
         cd* base = tile + (size_t)(R3 * c) * CB + b;
-        cd v[R3];
+        cd v[R3], kq[KD ? R3 : 1];
+        if (KD) static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; kq[KD ? k3 : 0] = jb_ld_nc(kh + k3 * I3 + w); });
         static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; v[n3] = base[n3 * CB]; });
         dft<R3, -1>(v);
         static_for<0, R3>([&](auto kk) {
             constexpr int k3 = kk;
-            cd kv = kh[k3 * I3 + w];
+            cd kv = KD ? kq[KD ? k3 : 0] : kh[k3 * I3 + w];
             v[k3] = ADJ ? cd_mulc(v[k3], kv) : cd_mul(v[k3], kv);
         });
         dft<R3, +1>(v);
@@ -145,8 +150,10 @@ struct Cols3 {
 // store on first touch, read-add-write (L2-resident, written by this CTA one item earlier) otherwise; fixed order
 // j ascending, so the sums are reproducible.  The adjoint applies the window row weight before accumulating.  The
 // row pass then reads ONE spectrum row per (image row, i) instead of one per covering patch.
-template <class F3, int CB, bool ADJ, bool SWEEP>
-JB_GLOBAL void JB_LB((Cols3<F3, CB>::THREADS), (Cols3<F3, CB>::CPS))
+// KD: no K^ staging ring -- thread 0 prefetches the slice into L2 two items ahead and the stage-3 threads load it
+// straight into registers; the shared memory saved lets a third CTA (24 warps) share the SM.
+template <class F3, int CB, bool ADJ, bool SWEEP, bool KD = false>
+JB_GLOBAL void JB_LB((Cols3<F3, CB>::THREADS), (KD ? Cols3<F3, CB>::CPS_KD : Cols3<F3, CB>::CPS))
 k_cols3_pipe(const
 #ifndef JB_EMU
              __grid_constant__
@@ -160,7 +167,7 @@ k_cols3_pipe(const
     JB_SMEM(unsigned char, smraw);
     cd* tile0 = reinterpret_cast<cd*>(smraw);
     cd* kh0 = tile0 + 2 * TILE;
-    cd* tw1 = kh0 + 2 * TILE;
+    cd* tw1 = kh0 + (KD ? 0 : 2 * TILE);
     cd* tw2 = tw1 + L;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tw2 + M);
     JbColInfo* info = reinterpret_cast<JbColInfo*>(bars + 4);
@@ -190,6 +197,7 @@ k_cols3_pipe(const
         f.vlo = ci.vlo; f.vhi = ci.vhi; f.out_p0 = ci.out_p0; f.out_rows = ci.out_rows;
         int nc = PH - ci.strip * CB;
         f.ncols = nc < CB ? nc : CB;
+        f.k_off = (long long)ci.k_off;
         if (SWEEP) {
             const int back = ADJ ? g.hp : g.hp + g.m;    // image row of output row 0 = offs[j] - back
             f.row_base = g.offs[ci.j] - back;
@@ -213,7 +221,7 @@ k_cols3_pipe(const
             int p0 = ci.in_p0 + r0;
             if (p0 + BR > ci.vlo && p0 < ci.vhi) ++issued;
         }
-        jb_mbar_expect_tx(&bars[s_], (uint32_t)(issued * BR * CB * sizeof(cd) + TILE * sizeof(cd)));
+        jb_mbar_expect_tx(&bars[s_], (uint32_t)(issued * BR * CB * sizeof(cd) + (KD ? 0 : TILE * sizeof(cd))));
         for (int c = 0; c < nch; ++c) {
             int r0 = c * BR;
             if (r0 + BR > ci.in_rows) r0 = ci.in_rows - BR;
@@ -221,7 +229,8 @@ k_cols3_pipe(const
             if (p0 + BR > ci.vlo && p0 < ci.vhi)
                 jb_tma_load_3d(tile + (size_t)p0 * CB, &src.map, 2 * ci.strip * CB, ci.row0 + r0, ci.in_slab, &bars[s_]);
         }
-        jb_bulk_load_1d(kh0 + s_ * TILE, khat + ci.k_off, (uint32_t)(TILE * sizeof(cd)), &bars[s_]);
+        if (KD) jb_bulk_prefetch_l2(khat + ci.k_off, (uint32_t)(TILE * sizeof(cd)));
+        else jb_bulk_load_1d(kh0 + s_ * TILE, khat + ci.k_off, (uint32_t)(TILE * sizeof(cd)), &bars[s_]);
     };
     if (tid == 0) {
         jb_mbar_init(&bars[0], 1);
@@ -239,7 +248,7 @@ k_cols3_pipe(const
         if (item < 0) break;
         const int s = it & 1;
         cd* tile = tile0 + s * TILE;
-        cd* kh = kh0 + s * TILE;
+        const cd* kh = KD ? nullptr : kh0 + s * TILE;
 #ifndef JB_EMU
         jb_mbar_wait<false>(&bars[s], (it >> 1) & 1);
 #else
@@ -251,15 +260,16 @@ k_cols3_pipe(const
             tile[(size_t)(ci.in_p0 + r) * CB + b] = (col < PH && ir >= 0 && ir < src.N)
                 ? src.base[((size_t)ci.in_slab * src.N + ir) * PH + col] : cd_make(0.0, 0.0);
         }
-        for (int idx = tid; idx < TILE; idx += JB_C3_THREADS) kh[idx] = khat[ci.k_off + idx];
+        if (!KD) for (int idx = tid; idx < TILE; idx += JB_C3_THREADS) kh0[s * TILE + idx] = khat[ci.k_off + idx];
         JB_SYNC();
 #endif
         const JbColInfo f = info[s];
+        if (KD) kh = khat + f.k_off;
         C3::s1_fwd(tile, tw1, tid, f.vlo, f.vhi, ADJ ? nullptr : rw, g.m);
         JB_SYNC();
         C3::s2_fwd(tile, tw2, tid);
         JB_SYNC();
-        C3::template s3_mid<ADJ>(tile, kh, tid);
+        C3::template s3_mid<ADJ, KD>(tile, kh, tid);
         JB_SYNC();
         C3::s2_inv(tile, tw2, tid);
         JB_SYNC();

@@ -72,6 +72,10 @@ JB_D void jb_bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* 
                  ::"r"(jb_smem_u32(dst)), "l"(src), "r"(bytes), "r"(jb_smem_u32(bar))
                  : "memory");
 }
+// warm L2 with a contiguous global range (no shared-memory destination, no completion tracking)
+JB_D void jb_bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 JB_D void jb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 JB_D void jb_bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(JB_PIPE_COMPUTE_THREADS) : "memory"); }
 #else

@@ -34,6 +34,12 @@ JB_D cd jb_ld_stream(const cd* p) {
     asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
+// read-only 128-bit load that does not allocate in L1 (data used once per CTA)
+JB_D cd jb_ld_nc(const cd* p) {
+    cd v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
 // L2-only (no L1 allocation) load: data another thread of this CTA wrote a moment ago
 JB_D cd jb_ld_cg(const cd* p) {
     cd v;
@@ -92,6 +98,7 @@ typedef int cudaError_t;
 template <class T> inline T jb_ldg(const T* p) { return *p; }
 inline cd jb_ld_stream(const cd* p) { return *p; }
 inline cd jb_ld_cg(const cd* p) { return *p; }
+inline cd jb_ld_nc(const cd* p) { return *p; }
 inline void jb_st_stream(cd* p, cd v) { *p = v; }
 inline cd make_double2(double x, double y) { return cd{x, y}; }
 

@@ -71,6 +71,16 @@ struct JbOpsImpl {
             size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd) + 32 +
                           2 * sizeof(JbColInfo) + (size_t)g.w * sizeof(double) + 32;
             const dim3 grid(ctas * Cols3<F3, CB>::CPS), block(Cols3<F3, CB>::THREADS);
+#ifdef JB_COLS_KD
+            if (!sweep) {   // K^ straight from L2, three CTAs per SM
+                const dim3 grid3(ctas * Cols3<F3, CB>::CPS_KD);
+                const size_t smem3 = smem - 2 * (size_t)FP::L * CB * sizeof(cd);
+                if (adj) return jb_launch(k_cols3_pipe<F3, CB, true, false, true>, grid3, block, smem3, st, src, g, out,
+                                          khat, twa, twb, wgt, planes);
+                return jb_launch(k_cols3_pipe<F3, CB, false, false, true>, grid3, block, smem3, st, src, g, out, khat,
+                                 twa, twb, wgt, planes);
+            }
+#endif
             if (sweep) {
                 if (adj) return jb_launch(k_cols3_pipe<F3, CB, true, true>, grid, block, smem, st, src, g, out, khat, twa,
                                           twb, wgt, planes);
@@ -251,10 +261,15 @@ struct JbOpsImpl {
                                     int n_sm, jb_stream_t st) {
         const int NC = (g.n + 1) / 2, NW = (NC + SW - 1) / SW;
         const size_t smem = jb_rows5_smem<F3, SW>(g.n);
-        auto kern = k_rows_c2r5<F3, SW, ADJ>;
-        int grid = rows5_grid(kern, NW * 32, smem, (long)planes * g.N, n_sm);
-        return jb_launch(kern, dim3(grid), dim3(NW * 32), smem, st, g, src, tw1, tw2, wgt, gtab, gq, ep, grad, presum,
-                         planes);
+        auto go = [&](auto kern) {
+            int grid = rows5_grid(kern, NW * 32, smem, (long)planes * g.N, n_sm);
+            return jb_launch(kern, dim3(grid), dim3(NW * 32), smem, st, g, src, tw1, tw2, wgt, gtab, gq, ep, grad, planes);
+        };
+        if constexpr (!ADJ) {
+            if (ep.mode == JB_EPI_POISSON)
+                return presum ? go(k_rows_c2r5<F3, SW, false, true, true>) : go(k_rows_c2r5<F3, SW, false, false, true>);
+        }
+        return presum ? go(k_rows_c2r5<F3, SW, ADJ, true, false>) : go(k_rows_c2r5<F3, SW, ADJ, false, false>);
     }
     static cudaError_t rows5_fwd(const JbGeom& g, const cd* bufA, const cd* tw1, const cd* tw2, const int* gtab, int gq,
                                  const JbEpi& ep, int presum, int planes, int n_sm, jb_stream_t st) {

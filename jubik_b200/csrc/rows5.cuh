@@ -261,13 +261,16 @@ JB_D void jb_rows5_assemble(cd* tile, const cd* const (&pbase)[SW][2], const boo
 //   adjoint (ADJ = true) : src = bufB ((S,T,E), n*n, w, PH); items = planes*N over launched (S,Es) planes; the
 //                          spectra of all modules are summed before the transform; out = grad (S,E,N,N).
 //   gtab: gather table [GQ][N] (jb_rows5_gather_table).
-template <class F3, int SW, bool ADJ>
-// SW = 1: one sequence per warp, CTAs of <= 4 warps (n <= 8), 72 registers so that 7 CTAs = 28 warps fit an SM;
-// SW = 2: two sequences per warp for wider patch grids (up to 16 warps per CTA)
+// SW = 1: one sequence per warp, CTAs of <= 4 warps (n <= 8), 80 registers so that 6 CTAs = 24 warps fit an SM;
+// SW = 2: two sequences per warp for wider patch grids (up to 16 warps per CTA).
+// PRESUM: the source is the column pass's summed buffer (sweep mode).
+// POIS: the fused Poisson energy/cotangent epilogue is compiled in (its log/divide raise the register pressure).
+template <class F3, int SW, bool ADJ, bool PRESUM, bool POIS>
 JB_GLOBAL void JB_LB((SW == 1 ? 128 : 512), (SW == 1 ? JB_R5_CPS : 1))
 k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, const cd* __restrict__ tw2,
             const double* __restrict__ wgt, const int* __restrict__ gtab, int GQ, JbEpi ep, double* __restrict__ grad,
-            int presum, int planes) {
+            int planes) {
+    constexpr bool presum = PRESUM;
     using R = Rows5<F3, SW>;
     JB_SMEM(unsigned char, smraw);
     const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH;
@@ -370,7 +373,7 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
                     if (ex != 0.0) o = ex * conv;
                 } else if (ep.mode == JB_EPI_METRIC) {
                     if (ex != 0.0) o = ex * (ex * conv) / ep.lam[orow + c];
-                } else {  // JB_EPI_POISSON: energy partial + cotangent expo * (1 - d / lambda)
+                } else if (POIS) {  // JB_EPI_POISSON: energy partial + cotangent expo * (1 - d / lambda)
                     if (ex != 0.0) {
                         const double lam = ex * conv, d = jb_ldg(ep.data + erow + c);
                         esum += lam - d * log(lam);
@@ -380,7 +383,7 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
                 ep.out[orow + c] = o;
             }
         }
-        if (!ADJ && ep.mode == JB_EPI_POISSON) {
+        if (!ADJ && POIS) {
             double tot = jb_block_sum(esum, red);   // fixed-order tree; ends with a block barrier
             if (tid == 0) ep.partial[(size_t)ste * N + r] = tot;
         } else {

@@ -255,6 +255,28 @@ def test_full_size_jwst_like_c4_oracle_parity_and_adjointness(torch_cuda):
     plan.close()
 
 
+def test_sweep_mode_matches_oracle(torch_cuda, monkeypatch):
+    """Opt-in column-pass sweep (accumulation over the row-patches inside the column kernel, rows5 reading the
+    pre-summed spectra): same numbers as the oracle, forward / transpose / fused energy+gradient."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    monkeypatch.setenv("JUBIK_B200_SWEEP", "1")
+    case = (768, 6, 64, 2, 1, 1, False, True)
+    N, n, m, T, E, S, full, eff = case
+    dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
+    plan = jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
+                           eff_area=dev(torch, ea), pixel_area=synth.PIXEL_AREA, data=dev(torch, d), max_samples=S,
+                           cropped=cropped)
+    xd = dev(torch, x)
+    g = synth.direction((S, T, E, N, N))
+    assert rel(plan.psf(xd).cpu().numpy(), np.stack([R.psf(x[s]) for s in range(S)])) < TOL
+    assert rel(plan.response_T(dev(torch, g)).cpu().numpy(), np.stack([R.dense_T(g[s]) for s in range(S)])) < TOL
+    e, gr = plan.energy_and_grad(xd)
+    eo, go = orc.energy_and_grad(R, d, x[0])
+    assert abs(float(e[0]) - eo) / abs(eo) < TOL and rel(gr[0].cpu().numpy(), go) < TOL
+    plan.close()
+
+
 def test_error_behaviour_matches_reference(torch_cuda):
     import jubik_b200 as jb
     torch = torch_cuda
