@@ -19,6 +19,10 @@
  *                              sum(lambda) - d.log(lambda) -- erosita_likelihood.py:85-89,
  *                              chandra_likelihood.py:37, formula demos/x-ray-imaging.py:313
  *   jubik_poisson_metric_apply R^T diag(1/lambda) R v  (Fisher metric NIFTy builds by linearize+transpose)
+ *   jubik_poisson_left_sqrt_metric   R^T (t / sqrt(lambda)): Poissonian left_sqrt_metric pulled back through R,
+ *                              what NIFTy's geoVI/MGVI sample draws apply
+ *   jubik_poisson_energy_and_grad_logsky   the same value_and_grad with the sky-model tail x = exp(log_sky)
+ *                              (jubik/sky_models.py:340-341) and its VJP grad * x folded in
  *
  * Conventions: every array pointer is a DEVICE pointer to contiguous C-order memory (float64 unless
  * stated); `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous
@@ -99,6 +103,12 @@ int jubik_poisson_energy_and_grad(jubik_plan* plan, const double* x, int n_sampl
 /* out = R^T diag(1/(R x)) R v ; x,v,out:(S,E,N,N) */
 int jubik_poisson_metric_apply(jubik_plan* plan, const double* x, const double* v, int n_samples,
                                double* out, void* stream);
+/* out = R^T (t / sqrt(R x)) ; x,out:(S,E,N,N), t:(S,T,E,N,N) (masked pixels of t are ignored) */
+int jubik_poisson_left_sqrt_metric(jubik_plan* plan, const double* x, const double* t, int n_samples,
+                                   double* out, void* stream);
+/* log_sky:(S,E,N,N) -> energy of x = exp(log_sky) and d energy / d log_sky = grad_x * x */
+int jubik_poisson_energy_and_grad_logsky(jubik_plan* plan, const double* log_sky, int n_samples,
+                                         double* energy, double* grad, void* stream);
 /* Same as jubik_poisson_energy_and_grad with HOST buffers (pinned or pageable): H2D of x, the kernels,
  * D2H of energy and grad, all on `stream`, then a stream synchronise.  This is the end-to-end call. */
 int jubik_poisson_energy_and_grad_host(jubik_plan* plan, const double* x_host, int n_samples,

@@ -22,6 +22,7 @@ EXPORTS = [
     "jubik_plan_launch_count", "jubik_psf_apply", "jubik_psf_apply_T", "jubik_response_apply",
     "jubik_response_apply_T", "jubik_poisson_energy_and_grad", "jubik_poisson_metric_apply",
     "jubik_poisson_energy_and_grad_host", "jubik_poisson_profile", "jubik_measure_fp64_tflops",
+    "jubik_poisson_left_sqrt_metric", "jubik_poisson_energy_and_grad_logsky",
 ]
 
 

@@ -200,4 +200,12 @@ class PoissonLikelihood:
     def metric(self, x, v):
         return self.plan.metric(x, v)
 
+    def left_sqrt_metric(self, x, t):
+        """R^T (t / sqrt(R x)) for a dense data-space tangent t ([S,] T, E, N, N); masked pixels are ignored."""
+        return self.plan.left_sqrt_metric(x, t)
+
+    def value_and_grad_logsky(self, log_sky):
+        """value_and_grad with respect to log_sky, sky = exp(log_sky) (jubik/sky_models.py:340-341)."""
+        return self.plan.energy_and_grad_logsky(log_sky)
+
     __call__ = energy

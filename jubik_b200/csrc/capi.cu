@@ -103,6 +103,7 @@ struct jubik_plan {
     double* gbuf = nullptr;    // (S_max,T,E,N,N) cotangent / lambda scratch
     double* lbuf = nullptr;    // (S_max,T,E,N,N) lambda for the metric (allocated on first use)
     double* partial = nullptr; // energy partials
+    double* xexp = nullptr;    // exp(log sky) of the sky-model tail entry point (allocated on first use)
     double* xdev = nullptr;    // staging for the host-buffer entry point (allocated on first use)
     double* gdev = nullptr;
     double* edev = nullptr;
@@ -156,7 +157,7 @@ int jubik_plan_destroy(jubik_plan* p) {
     if (!p) return JUBIK_OK;
     dev_free(p->khat); dev_free(p->tw_nk); dev_free(p->tw_kn); dev_free(p->tw1); dev_free(p->tw2); dev_free(p->wgt); dev_free(p->expo);
     dev_free(p->data); dev_free(p->bufA); dev_free(p->bufB); dev_free(p->gbuf); dev_free(p->lbuf);
-    dev_free(p->partial); dev_free(p->gtab_fwd); dev_free(p->gtab_adj); dev_free(p->xdev); dev_free(p->gdev); dev_free(p->edev);
+    dev_free(p->xexp); dev_free(p->partial); dev_free(p->gtab_fwd); dev_free(p->gtab_adj); dev_free(p->xdev); dev_free(p->gdev); dev_free(p->edev);
 #ifndef JB_EMU
     if (p->st_in) {
         for (int e = 0; e < p->g.E; ++e) { cudaEventDestroy(p->ev_in[e]); cudaEventDestroy(p->ev_c[e]); }
@@ -686,6 +687,39 @@ int jubik_poisson_metric_apply(jubik_plan* p, const double* x, const double* v, 
         if (int rc = run_forward(p, v, S, ep, st)) return rc;
     }
     return run_adjoint(p, p->gbuf, nullptr, S, out, st);
+}
+
+int jubik_poisson_left_sqrt_metric(jubik_plan* p, const double* x, const double* t, int S, double* out, void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (int rc = check_call(p, x, out, S)) return rc;
+    if (!t) return fail(JUBIK_ERR_ARG, "null array pointer");
+    if (!p->has_expo) return fail(JUBIK_ERR_ARG, "plan was created without exposures");
+    const JbGeom& g = p->g;
+    if (!p->lbuf) {
+        size_t bG = (size_t)p->S_max * g.T * g.E * g.N * g.N * sizeof(double);
+        if (int rc = alloc(p, (void**)&p->lbuf, bG, "lambda workspace")) return rc;
+    }
+    JbEpi ep; memset(&ep, 0, sizeof(ep));
+    ep.mode = JB_EPI_RESP; ep.out = p->lbuf; ep.expo = p->expo;
+    if (int rc = run_forward(p, x, S, ep, st)) return rc;
+    JB_LAUNCHED(p, jb_launch(k_lsm_epi, dim3(p->nblk_epi, S * g.T * g.E), dim3(256), 0, st, g, t, (const double*)p->expo,
+                             (const double*)p->lbuf, p->gbuf, g.N * g.N));
+    return run_adjoint(p, p->gbuf, nullptr, S, out, st);
+}
+
+int jubik_poisson_energy_and_grad_logsky(jubik_plan* p, const double* log_sky, int S, double* energy, double* grad,
+                                         void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (int rc = check_call(p, log_sky, energy, S)) return rc;
+    const JbGeom& g = p->g;
+    const size_t cnt = (size_t)S * g.E * g.N * g.N;
+    if (!p->xexp) {
+        if (int rc = alloc(p, (void**)&p->xexp, (size_t)p->S_max * g.E * g.N * g.N * sizeof(double), "exp(log sky) workspace")) return rc;
+    }
+    JB_LAUNCHED(p, jb_launch(k_exp, dim3(1184), dim3(256), 0, st, log_sky, p->xexp, cnt));
+    if (int rc = jubik_poisson_energy_and_grad(p, p->xexp, S, energy, grad, stream_)) return rc;
+    if (grad) JB_LAUNCHED(p, jb_launch(k_mul_inplace, dim3(1184), dim3(256), 0, st, grad, (const double*)p->xexp, cnt));
+    return JUBIK_OK;
 }
 
 int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, double* eh, double* gh, void* stream_) {

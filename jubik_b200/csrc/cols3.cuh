@@ -44,7 +44,11 @@ template <class F3, int CB>
 struct Cols3 {
     static constexpr int L = F3::L, R1 = F3::R1, R2 = F3::R2, R3 = F3::R3, M = F3::M;
     static constexpr int I1 = M * CB, I2 = R1 * R3 * CB, I3 = R1 * R2 * CB;
-    static constexpr int THREADS = (jb_c3_max3(I1, I2, I3) + 31) / 32 * 32;
+    // WL ("warp-local middle"): the R2*R3-point sub-transform of one k1 (stage 2, stage 3 * K^ * stage 3', stage 2')
+    // for all CB columns fits one warp, so warp k1 runs those three stages with warp-level syncs only and the
+    // item needs two block barriers instead of five
+    static constexpr bool WL = (R3 * CB <= 32) && (R2 * CB <= 32);
+    static constexpr int THREADS = WL ? (jb_c3_max3(I1, 32 * R1, 0) + 31) / 32 * 32 : (jb_c3_max3(I1, I2, I3) + 31) / 32 * 32;
     static constexpr int CPS = THREADS <= 256 ? 2 : 1;   // CTAs per SM the pipeline is sized for
     static constexpr int CPS_KD = THREADS <= 256 ? 3 : 1; // ... when K^ is read straight from L2 (no staging ring)
     static_assert(THREADS <= 1024, "one item per thread and stage");
@@ -119,6 +123,53 @@ struct Cols3 {
         if (w >= I2) return;
         const int c = w / CB, b = w - c * CB;
         const int k1 = c / R3, n3 = c - k1 * R3;
+        cd* base = tile + (size_t)(k1 * M + n3) * CB + b;
+        cd v[R2];
+        static_for<0, R2>([&](auto kk) {
+            constexpr int k2 = kk;
+            cd y = base[(R3 * k2) * CB];
+            if constexpr (k2 > 0) y = cd_mulc(y, tw2[k2 * R3 + n3]);
+            v[k2] = y;
+        });
+        dft<R2, +1>(v);
+        static_for<0, R2>([&](auto nn) { constexpr int n2 = nn; base[(R3 * n2) * CB] = v[n2]; });
+    }
+    // ---- warp-local variants: warp k1, lane = (n3 or k2)*CB + b
+    static JB_D void s2_fwd_w(cd* tile, const cd* tw2, int k1, int lane) {
+        if (lane >= R3 * CB) return;
+        const int n3 = lane / CB, b = lane - n3 * CB;
+        cd* base = tile + (size_t)(k1 * M + n3) * CB + b;
+        cd v[R2];
+        static_for<0, R2>([&](auto nn) { constexpr int n2 = nn; v[n2] = base[(R3 * n2) * CB]; });
+        dft<R2, -1>(v);
+        static_for<0, R2>([&](auto kk) {
+            constexpr int k2 = kk;
+            cd y = v[k2];
+            if constexpr (k2 > 0) y = cd_mul(y, tw2[k2 * R3 + n3]);
+            base[(R3 * k2) * CB] = y;
+        });
+    }
+    template <bool ADJ, bool KD = false>
+    static JB_D void s3_mid_w(cd* tile, const cd* kh, int k1, int lane) {
+        if (lane >= R2 * CB) return;
+        const int w = k1 * (R2 * CB) + lane;          // = (k1*R2 + k2)*CB + b : the K^ slice index of s3_mid
+        const int c = w / CB, b = w - c * CB;
+        cd* base = tile + (size_t)(R3 * c) * CB + b;
+        cd v[R3], kq[KD ? R3 : 1];
+        if (KD) static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; kq[KD ? k3 : 0] = jb_ld_nc(kh + k3 * I3 + w); });
+        static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; v[n3] = base[n3 * CB]; });
+        dft<R3, -1>(v);
+        static_for<0, R3>([&](auto kk) {
+            constexpr int k3 = kk;
+            cd kv = KD ? kq[KD ? k3 : 0] : kh[k3 * I3 + w];
+            v[k3] = ADJ ? cd_mulc(v[k3], kv) : cd_mul(v[k3], kv);
+        });
+        dft<R3, +1>(v);
+        static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; base[n3 * CB] = v[n3]; });
+    }
+    static JB_D void s2_inv_w(cd* tile, const cd* tw2, int k1, int lane) {
+        if (lane >= R3 * CB) return;
+        const int n3 = lane / CB, b = lane - n3 * CB;
         cd* base = tile + (size_t)(k1 * M + n3) * CB + b;
         cd v[R2];
         static_for<0, R2>([&](auto kk) {
@@ -267,12 +318,22 @@ k_cols3_pipe(const
         if (KD) kh = khat + f.k_off;
         C3::s1_fwd(tile, tw1, tid, f.vlo, f.vhi, ADJ ? nullptr : rw, g.m);
         JB_SYNC();
-        C3::s2_fwd(tile, tw2, tid);
-        JB_SYNC();
-        C3::template s3_mid<ADJ, KD>(tile, kh, tid);
-        JB_SYNC();
-        C3::s2_inv(tile, tw2, tid);
-        JB_SYNC();
+        if constexpr (C3::WL) {
+            const int k1 = tid >> 5, lane = tid & 31;
+            if (k1 < F3::R1) C3::s2_fwd_w(tile, tw2, k1, lane);
+            JB_SYNCWARP();
+            if (k1 < F3::R1) C3::template s3_mid_w<ADJ, KD>(tile, kh, k1, lane);
+            JB_SYNCWARP();
+            if (k1 < F3::R1) C3::s2_inv_w(tile, tw2, k1, lane);
+            JB_SYNC();
+        } else {
+            C3::s2_fwd(tile, tw2, tid);
+            JB_SYNC();
+            C3::template s3_mid<ADJ, KD>(tile, kh, tid);
+            JB_SYNC();
+            C3::s2_inv(tile, tw2, tid);
+            JB_SYNC();
+        }
         {
             const bool act = tid < C3::I1;
             cd v[R1];

@@ -486,6 +486,31 @@ JB_GLOBAL_S void k_metric_epi(JbGeom g, double* __restrict__ buf, const double* 
     }
 }
 
+// left-sqrt-metric epilogue: out = expo * t / sqrt(lambda)  (0 where masked); NIFTy's Poissonian left_sqrt_metric
+// t / sqrt(lambda) pulled back through R, the expo factor being R^T's exposure multiply
+JB_GLOBAL_S void k_lsm_epi(JbGeom g, const double* __restrict__ t, const double* __restrict__ expo,
+                           const double* __restrict__ lam, double* __restrict__ out, int npix) {
+    int ste, te, se_;
+    jb_map_ste(g, blockIdx.y, ste, te, se_);
+    const double* tp = t + (size_t)ste * npix;
+    const double* ex = expo + (size_t)te * npix;
+    const double* lm = lam + (size_t)ste * npix;
+    double* o = out + (size_t)ste * npix;
+    for (int i = blockIdx.x * jb_nthr() + jb_tid(); i < npix; i += gridDim.x * jb_nthr()) {
+        double e = jb_ldg(ex + i), v = 0.0;
+        if (e != 0.0) v = e * tp[i] / sqrt(lm[i]);
+        o[i] = v;
+    }
+}
+
+// sky-model tail (sky_models.py:340-341): x = exp(log_sky); and its VJP grad_log_sky = grad_x * x
+JB_GLOBAL_S void k_exp(const double* __restrict__ s, double* __restrict__ x, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * jb_nthr() + jb_tid(); i < n; i += (size_t)gridDim.x * jb_nthr()) x[i] = exp(s[i]);
+}
+JB_GLOBAL_S void k_mul_inplace(double* __restrict__ a, const double* __restrict__ b, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * jb_nthr() + jb_tid(); i < n; i += (size_t)gridDim.x * jb_nthr()) a[i] *= b[i];
+}
+
 // energy[s] = sum over (t,e) planes and row blocks of the per-CTA partials; one CTA per sample
 JB_GLOBAL_S void k_reduce_energy(const double* __restrict__ partial, int per_sample, double* __restrict__ energy) {
     JB_SMEM(double, red);

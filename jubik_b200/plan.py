@@ -229,6 +229,26 @@ class ResponsePlan:
                       C.c_void_p(out.data_ptr()), self._stream())
         return out[0] if sq else out
 
+    def left_sqrt_metric(self, x, t):
+        """R^T (t / sqrt(R x)): the Poissonian left-sqrt-metric pulled back to the sky (t in data space (S,T,E,N,N))."""
+        import torch
+        x, sq = self._sky(x)
+        t, _ = self._det(t)
+        out = torch.empty_like(x)
+        self.raw.call("jubik_poisson_left_sqrt_metric", C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()), x.shape[0],
+                      C.c_void_p(out.data_ptr()), self._stream())
+        return out[0] if sq else out
+
+    def energy_and_grad_logsky(self, log_sky):
+        """Fused value + gradient with respect to log_sky, sky = exp(log_sky) (sky_models.py:340-341)."""
+        import torch
+        s, sq = self._sky(log_sky)
+        energy = torch.empty((s.shape[0],), dtype=torch.float64, device=self.device)
+        grad = torch.empty_like(s)
+        self.raw.call("jubik_poisson_energy_and_grad_logsky", C.c_void_p(s.data_ptr()), s.shape[0],
+                      C.c_void_p(energy.data_ptr()), C.c_void_p(grad.data_ptr()), self._stream())
+        return (energy[0], grad[0]) if sq else (energy, grad)
+
     def energy_and_grad_host(self, x_host, energy_host, grad_host):
         """End-to-end call on HOST tensors (pinned for full PCIe speed): H2D, kernels, D2H, sync."""
         S = x_host.shape[0] if x_host.dim() == 4 else 1

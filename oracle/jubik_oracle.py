@@ -386,5 +386,20 @@ def metric_apply(resp: Response, x, v):
     return resp.dense_T(w)
 
 
+def left_sqrt_metric(resp: Response, x, t):
+    """Poissonian left_sqrt_metric t / sqrt(lambda) (NIFTy) pulled back through R."""
+    lam = resp.dense(x)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        w = np.where(resp.mask, 0.0, np.asarray(t, dtype=np.float64) / np.sqrt(lam))
+    return resp.dense_T(w)
+
+
+def energy_and_grad_logsky(resp: Response, data_dense, log_sky):
+    """value_and_grad with the sky-model tail sky = exp(log_sky) (jubik/sky_models.py:340-341)."""
+    x = np.exp(np.asarray(log_sky, dtype=np.float64))
+    h, g = energy_and_grad(resp, data_dense, x)
+    return h, g * x
+
+
 def default_workers():
     return os.cpu_count() or 1

@@ -105,6 +105,14 @@ def test_oracle_parity_all_entry_points(torch_cuda, case):
     v = synth.direction((S, E, N, N), seed=9)
     mo = np.stack([orc.metric_apply(R, x[s], v[s]) for s in range(S)])
     assert rel(plan.metric(xd, dev(torch, v)).cpu().numpy(), mo) < TOL
+    # left-sqrt-metric and the log-sky tail
+    lo = np.stack([orc.left_sqrt_metric(R, x[s], g[s]) for s in range(S)])
+    assert rel(plan.left_sqrt_metric(xd, gd).cpu().numpy(), lo) < TOL
+    ls = np.log(x)
+    el, gl = plan.energy_and_grad_logsky(dev(torch, ls))
+    elo, glo = zip(*[orc.energy_and_grad_logsky(R, d, ls[s]) for s in range(S)])
+    assert np.abs((el.cpu().numpy() - np.array(elo)) / np.array(elo)).max() < TOL
+    assert rel(gl.cpu().numpy(), np.stack(glo)) < TOL
     # host-buffer end-to-end entry point gives the same numbers
     xh = torch.as_tensor(x).pin_memory()
     eh = torch.empty((S,), dtype=torch.float64).pin_memory()
