@@ -47,7 +47,13 @@ struct Cols3 {
     // WL ("warp-local middle"): the R2*R3-point sub-transform of one k1 (stage 2, stage 3 * K^ * stage 3', stage 2')
     // for all CB columns fits one warp, so warp k1 runs those three stages with warp-level syncs only and the
     // item needs two block barriers instead of five
+    // Measured on B200 (r1): no gain at L = 384 (158 -> 158 us) and a loss at L = 336 (idle lanes), i.e. block
+    // barriers are not what limits this kernel -- kept behind JB_COLS_WL for the record.
+#ifdef JB_COLS_WL
     static constexpr bool WL = (R3 * CB <= 32) && (R2 * CB <= 32);
+#else
+    static constexpr bool WL = false;
+#endif
     static constexpr int THREADS = WL ? (jb_c3_max3(I1, 32 * R1, 0) + 31) / 32 * 32 : (jb_c3_max3(I1, I2, I3) + 31) / 32 * 32;
     static constexpr int CPS = THREADS <= 256 ? 2 : 1;   // CTAs per SM the pipeline is sized for
     static constexpr int CPS_KD = THREADS <= 256 ? 3 : 1; // ... when K^ is read straight from L2 (no staging ring)
