@@ -19,6 +19,15 @@
 #ifndef JB_R5_B
 #define JB_R5_B 3     // spectrum elements x row-patches whose loads a lane keeps in flight (per sequence)
 #endif
+#ifndef JB_R5_GU
+#define JB_R5_GU 1    // unroll factor of the gather / epilogue pixel loop
+#endif
+#ifndef JB_R5_AU
+#define JB_R5_AU 1    // unroll factor of the assembly loop over spectrum-element groups
+#endif
+#ifndef JB_R5_PF
+#define JB_R5_PF 0    // 1: prefetch the next row's sources into L2 (measured slower on B200: 122 -> 134 us, 72 -> 76 us)
+#endif
 #ifndef JB_R5_CPS
 #define JB_R5_CPS 6   // CTAs per SM the SW = 1 kernel is register-limited to
 #endif
@@ -182,7 +191,8 @@ JB_D void jb_rows5_assemble_c(cd* tile, const cd* const (&pbase)[SW][2], const b
                               const unsigned* __restrict__ atab, int lane) {
     using R = Rows5<F3, SW>;
     constexpr int NG = (R::NE + EG - 1) / EG;
-#pragma unroll 1
+    constexpr int AU = JB_R5_AU;
+#pragma unroll AU
     for (int gi = 0; gi < NG; ++gi) {
         const int e0 = gi * EG;
         cd xa[EG][SW], xb[EG][SW];
@@ -343,6 +353,40 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
             pbase[s][0] = plane0 + (size_t)(has[s][0] ? ia : 0) * istride;
             pbase[s][1] = plane0 + (size_t)(has[s][1] ? ia + 1 : 0) * istride;
         });
+#if !defined(JB_EMU) && JB_R5_PF
+        // warm L2 with the NEXT row's sources (one bulk prefetch per source row, no registers / shared memory): the
+        // seven dependent load round trips of that row then cost an L2 hit instead of a DRAM access each
+        {
+            const long nxt = item + gridDim.x;
+            if (nxt < nitems) {
+                const int lp2 = (int)(nxt / N), r2 = (int)(nxt - (long)lp2 * N);
+                const cd* pl2;
+                if (!ADJ) {
+                    int a_, b_, c_;
+                    jb_map_ste(g, lp2, a_, b_, c_);
+                    pl2 = src + (size_t)a_ * plane_sz;
+                } else {
+                    int s2_, e2_;
+                    jb_map_se(g, lp2, s2_, e2_);
+                    pl2 = src + ((size_t)(s2_ * g.T) * g.E + e2_) * plane_sz;
+                }
+                // lane -> (sequence s, row a/b, module t, candidate row-patch j): at most SW*2*T*n work items
+                const int per = 2 * n;
+                for (int idx = lane; idx < SW * per * T; idx += 32) {
+                    const int t = idx / (SW * per), rem = idx - t * (SW * per);
+                    const int s = rem / per, rem2 = rem - s * per, ab = rem2 / n, j = rem2 - ab * n;
+                    const int ia = 2 * (wid * SW + s) + ab;
+                    const int u = r2 + shift - g.offs[j];
+                    if (ia < n && u >= 0 && u < ROWS) {
+                        const cd* ps = pl2 + (size_t)t * tstride + (size_t)ia * istride +
+                                       (presum ? (size_t)r2 * PH : ((size_t)j * ROWS + u) * PH);
+                        if (!presum || j == 0 || r2 + shift - g.offs[j - 1] >= ROWS || true)
+                            jb_bulk_prefetch_l2(ps, (uint32_t)(PH * sizeof(cd)));
+                    }
+                }
+            }
+        }
+#endif
         jb_rows5_assemble<F3, SW, ADJ>(tile, pbase, has, tstride, T, cnt, rowoff, wr, atab, lane);
         JB_SYNCWARP();
         R::s3(tile, itab, lane);
@@ -356,6 +400,8 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
         double esum = 0.0;
         const size_t orow = ADJ ? ((size_t)se * N + r) * N : ((size_t)ste * N + r) * N;
         const size_t erow = ((size_t)te * N + r) * N;
+        constexpr int GU = JB_R5_GU;
+#pragma unroll GU
         for (int c = tid; c < N; c += NT) {
             double conv = 0.0;
             static_for<0, JB_MAXQ>([&](auto qq) {
