@@ -289,11 +289,21 @@ def run_ours(args):
         # column pass, forward: read w rows, read the resident spectrum (L*PH), write P rows, all complex128
         cols_bytes = S * T * E * n * n * (w + P + L) * PH * 16
         cols_s = kms["cols_fwd"] * 1e-3
+        # DRAM bytes of the same kernel from the committed `ncu --set full` capture (profiles/*_traffic.json)
+        traffic = None
+        try:
+            import glob
+            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1]
+            tj = json.load(open(tf))
+            if tj.get("workload") == args.workload and S == 1:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         b_alg, f_alg = alg_bytes_flops(N, n, m, T, E, S)
         t_step = t_dev / args.steps
         roof = {"bound": "hbm", "kernel": "k_cols (forward column pass: FFT * K^ * IFFT)",
                 "achieved": cols_bytes / cols_s / 1e9, "peak": hbm, "unit": "GB/s",
-                "frac": cols_bytes / cols_s / 1e9 / hbm, "peak_source": hbm_src, "traffic": None,
+                "frac": cols_bytes / cols_s / 1e9 / hbm, "peak_source": hbm_src, "traffic": traffic,
                 "algorithmic_bytes_per_launch": cols_bytes, "launch_ms": kms["cols_fwd"],
                 "kernel_ms": kms,
                 "path": {"B_alg_bytes": b_alg, "F_alg_flops": f_alg,
