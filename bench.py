@@ -6,8 +6,10 @@
 
 Workload at N=1: BASELINE.json configs[1] ("C2", Chandra-like): 1024x1024 sky, 3 energy bins, 8x8
 spatially-variant PSF patches, margin 64, exposure + readout mask + Poisson likelihood, S=1, T=1.
-One step = one evaluation of (energy, d energy / d sky); sky-pixels = S*T*E*N^2.
-At N>1 every rank owns one VI sample of the same workload (weak scaling, sample sharding, SURVEY 8e);
+One step = one evaluation of (energy[s], d energy[s] / d sky[s]) for the S samples of the rank; sky-pixels =
+S*T*E*N^2.
+Every rank (also at N=1) evaluates `--samples-per-gpu` posterior samples of that workload per step (default 2, the
+per-GPU share of BASELINE.json configs[4]: 16 geoVI samples over 8 GPUs) -- weak scaling, sample sharding (SURVEY 8e);
 the per-sample energies and the sample-summed gradient sit in one flat buffer that is combined with a
 SINGLE NCCL all-reduce inside the timed region.
 
@@ -295,7 +297,7 @@ def run_ours(args):
             import glob
             tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1]
             tj = json.load(open(tf))
-            if tj.get("workload") == args.workload and S == 1:
+            if tj.get("workload") == args.workload and tj.get("samples", 1) == S:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except Exception:
             pass
@@ -337,7 +339,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--samples-per-gpu", type=int, default=1)
+    ap.add_argument("--samples-per-gpu", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

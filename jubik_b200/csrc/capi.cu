@@ -117,6 +117,7 @@ struct jubik_plan {
     int rows5 = 0;                         // warp-private c2r kernels with the fused Poisson epilogue (rows5.cuh)
     int* gtab_fwd = nullptr;               // rows5 overlap-add gather tables [gq][N]
     int* gtab_adj = nullptr;
+    unsigned* counter = nullptr;           // last-CTA-done counter of the fused energy reduction
     int gq_fwd = 0, gq_adj = 0;
     int rows_pipe_out = 0, rows_pipe_adj = 0, qmax = 0;  // persistent bulk-copy-fed c2r kernels (rows_pipe.cuh)
     int fast_rows = 0;         // rows_fast.cuh kernels (two-pass length and <= JB_MAXQ row-patches per image row)
@@ -157,7 +158,7 @@ int jubik_plan_destroy(jubik_plan* p) {
     if (!p) return JUBIK_OK;
     dev_free(p->khat); dev_free(p->tw_nk); dev_free(p->tw_kn); dev_free(p->tw1); dev_free(p->tw2); dev_free(p->wgt); dev_free(p->expo);
     dev_free(p->data); dev_free(p->bufA); dev_free(p->bufB); dev_free(p->gbuf); dev_free(p->lbuf);
-    dev_free(p->xexp); dev_free(p->partial); dev_free(p->gtab_fwd); dev_free(p->gtab_adj); dev_free(p->xdev); dev_free(p->gdev); dev_free(p->edev);
+    dev_free(p->counter); dev_free(p->xexp); dev_free(p->partial); dev_free(p->gtab_fwd); dev_free(p->gtab_adj); dev_free(p->xdev); dev_free(p->gdev); dev_free(p->edev);
 #ifndef JB_EMU
     if (p->st_in) {
         for (int e = 0; e < p->g.E; ++e) { cudaEventDestroy(p->ev_in[e]); cudaEventDestroy(p->ev_c[e]); }
@@ -184,6 +185,7 @@ static void choose_launch_shapes(jubik_plan* p) {
     // rows kernels: aim for >= 8 sequences per CTA, <= 256 threads; items per pass ~ B*R2 and B*(R1/2+1)
     int rpc = 1;
     while (rpc * g.n < 8 && rpc < g.N) rpc *= 2;
+    if (const char* ev = getenv("JUBIK_B200_RPC")) { int v = atoi(ev); if (v >= 1 && v <= 8) rpc = v; }   // tuning hook
     p->rpc_in = p->rpc_out = rpc;
     int B = rpc * g.n;
     int items = B * (o->R2 > 1 ? (o->R2 > o->R1 / 2 + 1 ? o->R2 : o->R1 / 2 + 1) : 1);
@@ -399,6 +401,13 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
     // gains from reading one summed row (-22 / -13 us), so the sweep stays an opt-in experiment
     p->sweep = (p->rows5 && getenv("JUBIK_B200_SWEEP")) ? 1 : 0;
     if (p->rows5 && !getenv("JUBIK_B200_SPLIT_EPI")) { p->split_epi = 0; p->nblk_out = N; }   // fused epilogue: one partial per row
+    if (p->rows5 && !p->split_epi && !getenv("JUBIK_B200_SEPARATE_REDUCE")) {
+        unsigned zero = 0;
+        if (alloc(p, (void**)&p->counter, sizeof(unsigned), "reduction counter") || h2d(p->counter, &zero, sizeof(zero), st) ||
+            stream_sync(st)) {
+            cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "allocating the reduction counter failed");
+        }
+    }
     if (p->use_pipe) {
         std::string err;
         int brB = g.w < 64 ? g.w : 64, brA = g.P < 64 ? g.P : 64;
@@ -575,11 +584,15 @@ int jubik_poisson_energy_and_grad(jubik_plan* p, const double* x, int S, double*
         for (int e = 0; e < g.E; ++e) {
             JbGeom ge = g;
             ge.e0 = e; ge.Es = 1;
+            if (p->counter && e == g.E - 1) {
+                ep.energy = energy; ep.counter = p->counter; ep.n_samples = S; ep.per_sample = g.T * g.E * p->nblk_out;
+            }
             if (int rc = run_forward_g(p, ge, x, S, ep, st)) return rc;
             if (int rc = run_adjoint_g(p, ge, p->gbuf, nullptr, S, grad, st)) return rc;
         }
-        JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
-                                 (const double*)p->partial, g.T * g.E * p->nblk_out, energy));
+        if (!p->counter)
+            JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
+                                     (const double*)p->partial, g.T * g.E * p->nblk_out, energy));
         return JUBIK_OK;
     }
     if (p->split_epi) {
@@ -592,9 +605,13 @@ int jubik_poisson_energy_and_grad(jubik_plan* p, const double* x, int S, double*
                                  (const double*)p->partial, g.T * g.E * p->nblk_epi, energy));
     } else {
         ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
+        if (p->counter) {
+            ep.energy = energy; ep.counter = p->counter; ep.n_samples = S; ep.per_sample = g.T * g.E * p->nblk_out;
+        }
         if (int rc = run_forward(p, x, S, ep, st)) return rc;
-        JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
-                                 (const double*)p->partial, g.T * g.E * p->nblk_out, energy));
+        if (!p->counter)
+            JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
+                                     (const double*)p->partial, g.T * g.E * p->nblk_out, energy));
     }
     if (grad) return run_adjoint(p, p->gbuf, nullptr, S, grad, st);
     return JUBIK_OK;
@@ -770,6 +787,9 @@ int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, d
                                          p->gbuf, (const double*)p->expo, (const double*)p->data, (int)npx, p->partial));
             } else {
                 ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
+                if (p->counter && e == g.E - 1) {
+                    ep.energy = p->edev; ep.counter = p->counter; ep.n_samples = S; ep.per_sample = g.T * g.E * p->nblk_out;
+                }
                 if (int rc = run_forward_g(p, ge, p->xdev, S, ep, st)) return rc;
             }
             if (int rc = run_adjoint_g(p, ge, p->gbuf, nullptr, S, p->gdev, st)) return rc;
@@ -777,8 +797,9 @@ int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, d
             JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_c[e], 0));
             JB_CK(cudaMemcpy2DAsync(gh + e * npx, pitch, p->gdev + e * npx, pitch, width, S, cudaMemcpyDeviceToHost, p->st_out));
         }
-        JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
-                                 (const double*)p->partial, g.T * g.E * (p->split_epi ? p->nblk_epi : p->nblk_out), p->edev));
+        if (p->split_epi || !p->counter)
+            JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
+                                     (const double*)p->partial, g.T * g.E * (p->split_epi ? p->nblk_epi : p->nblk_out), p->edev));
         if (d2h(eh, p->edev, S * sizeof(double), st)) return fail(JUBIK_ERR_CUDA, "D2H copy of energy failed");
         if (stream_sync(st) || stream_sync(p->st_out)) return fail(JUBIK_ERR_CUDA, "stream synchronise failed");
         return JUBIK_OK;

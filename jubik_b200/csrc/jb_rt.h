@@ -51,6 +51,13 @@ JB_D void jb_st_stream(cd* p, cd v) {
 }
 #define JB_SYNC() __syncthreads()
 #define JB_SYNCWARP() __syncwarp()
+JB_D unsigned jb_atomic_inc(unsigned* p) { return atomicAdd(p, 1u); }
+JB_D void jb_threadfence() { __threadfence(); }
+JB_D double jb_ld_cg_f64(const double* p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
 
 template <class K, class... A>
 inline cudaError_t jb_launch(K kern, dim3 grid, dim3 block, size_t smem, jb_stream_t st, A... args) {
@@ -98,6 +105,9 @@ typedef int cudaError_t;
 template <class T> inline T jb_ldg(const T* p) { return *p; }
 inline cd jb_ld_stream(const cd* p) { return *p; }
 inline cd jb_ld_cg(const cd* p) { return *p; }
+inline unsigned jb_atomic_inc(unsigned* p) { return (*p)++; }   // emulated CTAs run one after the other
+inline void jb_threadfence() {}
+inline double jb_ld_cg_f64(const double* p) { return *p; }
 inline cd jb_ld_nc(const cd* p) { return *p; }
 inline void jb_st_stream(cd* p, cd v) { *p = v; }
 inline cd make_double2(double x, double y) { return cd{x, y}; }

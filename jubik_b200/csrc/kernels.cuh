@@ -60,6 +60,10 @@ struct JbEpi {
     const double* lam;    // (S,T,E,N,N) for JB_EPI_METRIC
     double* out;          // (S,T,E,N,N)
     double* partial;      // per-CTA energy partials, [STE][gridDim.x]
+    // fused final reduction (rows5, JB_EPI_POISSON): the last CTA to finish sums the partials in a fixed order
+    double* energy;       // (S,) or nullptr (no fused reduction in this launch)
+    unsigned* counter;    // zero-initialised device counter, reset by the last CTA
+    int n_samples, per_sample;
 };
 
 // Row-patch list of an image row: all j with u = r + shift - offs[j] in [0, len).

@@ -436,4 +436,25 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
             JB_SYNC();   // the gather has read the tiles before the next row is assembled into them
         }
     }
+    if (!ADJ && POIS && ep.energy) {
+        // fused final reduction: the last CTA to get here sums all per-row partials in a fixed order
+        JB_SYNC();
+        if (tid == 0) {
+            jb_threadfence();
+            red[0] = (jb_atomic_inc(ep.counter) == gridDim.x - 1) ? 1.0 : 0.0;
+        }
+        JB_SYNC();
+        const bool last = red[0] != 0.0;
+        JB_SYNC();
+        if (last) {
+            jb_threadfence();
+            for (int s = 0; s < ep.n_samples; ++s) {
+                double acc = 0.0;
+                for (int i = tid; i < ep.per_sample; i += NT) acc += jb_ld_cg_f64(ep.partial + (size_t)s * ep.per_sample + i);
+                double tot = jb_block_sum(acc, red);
+                if (tid == 0) ep.energy[s] = tot;
+            }
+            if (tid == 0) *ep.counter = 0u;
+        }
+    }
 }

@@ -256,7 +256,8 @@ class ResponsePlan:
                       C.c_void_p(energy_host.data_ptr()),
                       C.c_void_p(grad_host.data_ptr()) if grad_host is not None else None, self._stream())
 
-    KERNEL_NAMES = {7: ("rows_fwd", "cols_fwd", "rows_out", "reduce", "rows_adj_in", "cols_adj", "rows_adj_out"),
+    KERNEL_NAMES = {6: ("rows_fwd", "cols_fwd", "rows_out", "rows_adj_in", "cols_adj", "rows_adj_out"),
+                    7: ("rows_fwd", "cols_fwd", "rows_out", "reduce", "rows_adj_in", "cols_adj", "rows_adj_out"),
                     8: ("rows_fwd", "cols_fwd", "rows_out", "poisson_epi", "reduce", "rows_adj_in", "cols_adj",
                         "rows_adj_out")}
 
@@ -273,11 +274,12 @@ class ResponsePlan:
                       C.c_void_p(grad.data_ptr()), ms, C.byref(n), self._stream())
         vals = [float(ms[i]) for i in range(n.value)]
         E = self.info["E"]
-        if n.value == 6 * E + 1 and n.value not in self.KERNEL_NAMES:
+        if n.value in (6 * E, 6 * E + 1) and n.value not in self.KERNEL_NAMES:
             # one energy bin at a time: (rows_fwd, cols_fwd, rows_out, rows_adj_in, cols_adj, rows_adj_out) x E, reduce
             per = ("rows_fwd", "cols_fwd", "rows_out", "rows_adj_in", "cols_adj", "rows_adj_out")
             out = {k: sum(vals[6 * e + i] for e in range(E)) for i, k in enumerate(per)}
-            out["reduce"] = vals[-1]
+            if n.value == 6 * E + 1:
+                out["reduce"] = vals[-1]
             return energy, grad, out
         names = self.KERNEL_NAMES.get(n.value, tuple("k%d" % i for i in range(n.value)))
         return energy, grad, dict(zip(names, vals))

@@ -263,6 +263,43 @@ def test_full_size_jwst_like_c4_oracle_parity_and_adjointness(torch_cuda):
     plan.close()
 
 
+def test_full_size_geovi_batch_c5_per_gpu_share(torch_cuda):
+    """BASELINE.json configs[4], the share of ONE GPU (2 of the 16 posterior samples x 7 modules x 3 bins at 2048^2,
+    10x10 patches, margin 128: P = 664 -> L = 672): sample batching is bitwise the same as one sample at a time,
+    adjointness of the batched response, and a finite-difference check of the fused gradient."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    N, n, m, T, E, S = 2048, 10, 128, 7, 3, 2
+    dx = N // n
+    kern = synth.psf_cropped(T, n, E, dx, half_support=m)
+    expo = synth.exposure(T, E, N)
+    ea = synth.eff_area(T, E)
+    plan = jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
+                           eff_area=dev(torch, ea), pixel_area=synth.PIXEL_AREA, max_samples=S, cropped=True)
+    del kern
+    assert plan.info["L"] == 672 and plan.info["P"] == 664
+    x = dev(torch, synth.sky(S, E, N))
+    lam = plan.response(dev(torch, synth.sky(1, E, N, seed=5)))
+    torch.manual_seed(11)
+    plan.set_data(torch.poisson(lam.clamp(min=0.0))[0])
+    del lam
+    e, gr = plan.energy_and_grad(x)
+    for s in range(S):
+        es, gs = plan.energy_and_grad(x[s:s + 1])
+        assert torch.equal(es[0], e[s]) and torch.equal(gs[0], gr[s])
+    g = dev(torch, synth.direction((S, T, E, N, N)))
+    lhs = torch.vdot(g.flatten(), plan.response(x).flatten())
+    rhs = torch.vdot(plan.response_T(g).flatten(), x.flatten())
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-12
+    del g
+    v = dev(torch, synth.direction((S, E, N, N), seed=9)) * x
+    eps = 1e-4
+    fd = float((plan.energy(x + eps * v) - plan.energy(x - eps * v)).sum()) / (2 * eps)
+    an = float(torch.vdot(gr.flatten(), v.flatten()))
+    assert abs(fd - an) / max(abs(an), 1e-4 * float(gr.norm() * v.norm())) < 1e-6
+    plan.close()
+
+
 def test_sweep_mode_matches_oracle(torch_cuda, monkeypatch):
     """Opt-in column-pass sweep (accumulation over the row-patches inside the column kernel, rows5 reading the
     pre-summed spectra): same numbers as the oracle, forward / transpose / fused energy+gradient."""
