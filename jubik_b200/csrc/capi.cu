@@ -401,7 +401,9 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
     // gains from reading one summed row (-22 / -13 us), so the sweep stays an opt-in experiment
     p->sweep = (p->rows5 && getenv("JUBIK_B200_SWEEP")) ? 1 : 0;
     if (p->rows5 && !getenv("JUBIK_B200_SPLIT_EPI")) { p->split_epi = 0; p->nblk_out = N; }   // fused epilogue: one partial per row
-    if (p->rows5 && !p->split_epi && !getenv("JUBIK_B200_SEPARATE_REDUCE")) {
+    // fused final reduction (last CTA of the forward c2r kernel sums the partials): measured equal to the separate
+    // 8 us k_reduce_energy launch (the lone last CTA adds the same tail), so it stays opt-in
+    if (p->rows5 && !p->split_epi && getenv("JUBIK_B200_FUSED_REDUCE")) {
         unsigned zero = 0;
         if (alloc(p, (void**)&p->counter, sizeof(unsigned), "reduction counter") || h2d(p->counter, &zero, sizeof(zero), st) ||
             stream_sync(st)) {
