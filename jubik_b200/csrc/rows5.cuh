@@ -28,6 +28,9 @@
 #ifndef JB_R5_PF
 #define JB_R5_PF 0    // 1: prefetch the next row's sources into L2 (measured slower on B200: 122 -> 134 us, 72 -> 76 us)
 #endif
+#ifndef JB_R5_REV
+#define JB_R5_REV 0   // 1: walk the image rows in descending order (L2 reuse of the column pass's last output; measured neutral)
+#endif
 #ifndef JB_R5_CPS
 #define JB_R5_CPS 6   // CTAs per SM the SW = 1 kernel is register-limited to
 #endif
@@ -315,7 +318,10 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
     });
     JB_SYNC();
     const long nitems = (long)planes * N;
-    for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    for (long it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
+        // walk the rows in DESCENDING order: the column pass wrote the planes in ascending order, so the last plane
+        // is still (partly) L2-resident when this kernel starts -- consume it first instead of evicting it
+        const long item = JB_R5_REV ? nitems - 1 - it_ : it_;
         const int lp = (int)(item / N), r = (int)(item - (long)lp * N);
         // ---- sources of this row (uniform over the CTA)
         int rowoff[JB_MAXQ];
@@ -357,8 +363,8 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
         // warm L2 with the NEXT row's sources (one bulk prefetch per source row, no registers / shared memory): the
         // seven dependent load round trips of that row then cost an L2 hit instead of a DRAM access each
         {
-            const long nxt = item + gridDim.x;
-            if (nxt < nitems) {
+            const long nxt = JB_R5_REV ? item - (long)gridDim.x : item + (long)gridDim.x;
+            if (nxt >= 0 && nxt < nitems) {
                 const int lp2 = (int)(nxt / N), r2 = (int)(nxt - (long)lp2 * N);
                 const cd* pl2;
                 if (!ADJ) {
