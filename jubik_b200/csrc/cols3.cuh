@@ -58,51 +58,73 @@ struct Cols3 {
     static constexpr int CPS = THREADS <= 256 ? 2 : 1;   // CTAs per SM the pipeline is sized for
     static constexpr int CPS_KD = THREADS <= 256 ? 3 : 1; // ... when K^ is read straight from L2 (no staging ring)
     static_assert(THREADS <= 1024, "one item per thread and stage");
+    // SWZ: with 4-column tiles two stage-3 items of one quarter-warp (rows 8c + n3 and 8c + 8 + n3) hit the same
+    // banks.  Between the first forward stage and the last inverse stage the tile is therefore kept row-swizzled,
+    // physical row = row ^ ((row >> 3) & 1): neighbouring 8-row groups swap their even/odd rows, every stage stays
+    // on the same pair of rows per lane pair, and stage 3 becomes conflict-free (ncu r1h: 19 % of the column pass's
+    // shared-memory wavefronts were replays).  Row parities follow from M % 16 == 0 and R3 == 8.
+    // Measured on B200: conflict-free, yet SLOWER (158 -> 165 us): the extra address arithmetic costs more than the
+    // replays -- the kernel is bound by per-warp instruction latency, not by shared-memory bandwidth.  Opt-in.
+#ifdef JB_COLS_SWZ
+    static constexpr bool SWZ = !WL && (R3 == 8) && (CB == 4) && (M % 16 == 0);
+#else
+    static constexpr bool SWZ = false;
+#endif
+    static JB_HD int swz_off(int par, int odd) { return SWZ ? par * (1 - 2 * odd) * CB : 0; }   // element offset of the swap
 
     // forward stage 1 with zero rows outside [vlo, vhi); rw != nullptr: multiply tile row p by rw[p - p0]
     // (the window row weight of the forward direction, convolve.py:88-90)
     static JB_D void s1_fwd(cd* tile, const cd* tw1, int w, int vlo, int vhi, const double* rw, int p0) {
-        if (w >= I1) return;
+        const bool act = w < I1;
         const int m = w / CB, b = w - m * CB;
         cd v[R1];
-        static_for<0, R1>([&](auto nn) {
-            constexpr int n1 = nn;
-            int p = M * n1 + m;
-            cd t = cd_make(0.0, 0.0);
-            if (p >= vlo && p < vhi) {
-                t = tile[p * CB + b];
-                if (rw) t = cd_scale(t, rw[p - p0]);
-            }
-            v[n1] = t;
-        });
-        dft<R1, -1>(v);
-        static_for<0, R1>([&](auto kk) {
-            constexpr int k1 = kk;
-            cd y = v[k1];
-            if constexpr (k1 > 0) y = cd_mul(y, tw1[k1 * M + m]);
-            tile[(k1 * M + m) * CB + b] = y;
-        });
+        if (act) {
+            static_for<0, R1>([&](auto nn) {
+                constexpr int n1 = nn;
+                int p = M * n1 + m;
+                cd t = cd_make(0.0, 0.0);
+                if (p >= vlo && p < vhi) {
+                    t = tile[p * CB + b];
+                    if (rw) t = cd_scale(t, rw[p - p0]);
+                }
+                v[n1] = t;
+            });
+            dft<R1, -1>(v);
+        }
+        if (SWZ) JB_SYNCWARP();   // the swapped destination row is an input row of a neighbouring lane of this warp
+        if (act) {
+            const int so = swz_off((m >> 3) & 1, m & 1);
+            static_for<0, R1>([&](auto kk) {
+                constexpr int k1 = kk;
+                cd y = v[k1];
+                if constexpr (k1 > 0) y = cd_mul(y, tw1[k1 * M + m]);
+                tile[(k1 * M + m) * CB + b + so] = y;
+            });
+        }
     }
     static JB_D void s2_fwd(cd* tile, const cd* tw2, int w) {
         if (w >= I2) return;
         const int c = w / CB, b = w - c * CB;   // c = k1*R3 + n3
         const int k1 = c / R3, n3 = c - k1 * R3;
         cd* base = tile + (size_t)(k1 * M + n3) * CB + b;
+        const int p0 = ((k1 * M + n3) >> 3) & 1;
+        const int so[2] = {swz_off(p0, n3 & 1), swz_off(1 - p0, n3 & 1)};   // even / odd n2 (R3 == 8 rows per step)
         cd v[R2];
-        static_for<0, R2>([&](auto nn) { constexpr int n2 = nn; v[n2] = base[(R3 * n2) * CB]; });
+        static_for<0, R2>([&](auto nn) { constexpr int n2 = nn; v[n2] = base[(R3 * n2) * CB + so[n2 & 1]]; });
         dft<R2, -1>(v);
         static_for<0, R2>([&](auto kk) {
             constexpr int k2 = kk;
             cd y = v[k2];
             if constexpr (k2 > 0) y = cd_mul(y, tw2[k2 * R3 + n3]);
-            base[(R3 * k2) * CB] = y;
+            base[(R3 * k2) * CB + so[k2 & 1]] = y;
         });
     }
     // stage 3 forward only (plan time): returns the spectrum values of this thread
     static JB_D void s3_fwd(const cd* tile, int w, cd (&v)[R3]) {
         const int c = w / CB, b = w - c * CB;   // c = k1*R2 + k2 ; rows R3*c + n3
         const cd* base = tile + (size_t)(R3 * c) * CB + b;
-        static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; v[n3] = base[n3 * CB]; });
+        const int par = c & 1;
+        static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; v[n3] = base[n3 * CB + swz_off(par, n3 & 1)]; });
         dft<R3, -1>(v);
     }
     // stage 3: forward, * K^ (conj for the adjoint), inverse -- the spectrum never leaves the registers
@@ -113,9 +135,10 @@ struct Cols3 {
         if (w >= I3) return;
         const int c = w / CB, b = w - c * CB;
         cd* base = tile + (size_t)(R3 * c) * CB + b;
+        const int par = c & 1;
         cd v[R3], kq[KD ? R3 : 1];
         if (KD) static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; kq[KD ? k3 : 0] = jb_ld_nc(kh + k3 * I3 + w); });
-        static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; v[n3] = base[n3 * CB]; });
+        static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; v[n3] = base[n3 * CB + swz_off(par, n3 & 1)]; });
         dft<R3, -1>(v);
         static_for<0, R3>([&](auto kk) {
             constexpr int k3 = kk;
@@ -123,22 +146,24 @@ struct Cols3 {
             v[k3] = ADJ ? cd_mulc(v[k3], kv) : cd_mul(v[k3], kv);
         });
         dft<R3, +1>(v);
-        static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; base[n3 * CB] = v[n3]; });
+        static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; base[n3 * CB + swz_off(par, n3 & 1)] = v[n3]; });
     }
     static JB_D void s2_inv(cd* tile, const cd* tw2, int w) {
         if (w >= I2) return;
         const int c = w / CB, b = w - c * CB;
         const int k1 = c / R3, n3 = c - k1 * R3;
         cd* base = tile + (size_t)(k1 * M + n3) * CB + b;
+        const int p0 = ((k1 * M + n3) >> 3) & 1;
+        const int so[2] = {swz_off(p0, n3 & 1), swz_off(1 - p0, n3 & 1)};
         cd v[R2];
         static_for<0, R2>([&](auto kk) {
             constexpr int k2 = kk;
-            cd y = base[(R3 * k2) * CB];
+            cd y = base[(R3 * k2) * CB + so[k2 & 1]];
             if constexpr (k2 > 0) y = cd_mulc(y, tw2[k2 * R3 + n3]);
             v[k2] = y;
         });
         dft<R2, +1>(v);
-        static_for<0, R2>([&](auto nn) { constexpr int n2 = nn; base[(R3 * n2) * CB] = v[n2]; });
+        static_for<0, R2>([&](auto nn) { constexpr int n2 = nn; base[(R3 * n2) * CB + so[n2 & 1]] = v[n2]; });
     }
     // ---- warp-local variants: warp k1, lane = (n3 or k2)*CB + b
     static JB_D void s2_fwd_w(cd* tile, const cd* tw2, int k1, int lane) {
@@ -190,9 +215,10 @@ struct Cols3 {
     // inverse stage 1: load + conj twiddle (registers only); the caller may release the tile afterwards
     static JB_D void s1_inv_load(const cd* tile, const cd* tw1, int w, cd (&v)[R1]) {
         const int m = w / CB, b = w - m * CB;
+        const int so = swz_off((m >> 3) & 1, m & 1);
         static_for<0, R1>([&](auto kk) {
             constexpr int k1 = kk;
-            cd y = tile[(k1 * M + m) * CB + b];
+            cd y = tile[(k1 * M + m) * CB + b + so];
             if constexpr (k1 > 0) y = cd_mulc(y, tw1[k1 * M + m]);
             v[k1] = y;
         });
@@ -278,16 +304,27 @@ k_cols3_pipe(const
             int p0 = ci.in_p0 + r0;
             if (p0 + BR > ci.vlo && p0 < ci.vhi) ++issued;
         }
+#ifdef JB_ABL_NOTILE
+        issued = 0;
+#endif
+#ifdef JB_ABL_NOKHAT
+        jb_mbar_expect_tx(&bars[s_], (uint32_t)(issued * BR * CB * sizeof(cd)));
+#else
         jb_mbar_expect_tx(&bars[s_], (uint32_t)(issued * BR * CB * sizeof(cd) + (KD ? 0 : TILE * sizeof(cd))));
+#endif
         for (int c = 0; c < nch; ++c) {
             int r0 = c * BR;
             if (r0 + BR > ci.in_rows) r0 = ci.in_rows - BR;
             int p0 = ci.in_p0 + r0;
+#ifndef JB_ABL_NOTILE
             if (p0 + BR > ci.vlo && p0 < ci.vhi)
                 jb_tma_load_3d(tile + (size_t)p0 * CB, &src.map, 2 * ci.strip * CB, ci.row0 + r0, ci.in_slab, &bars[s_]);
+#endif
         }
+#ifndef JB_ABL_NOKHAT
         if (KD) jb_bulk_prefetch_l2(khat + ci.k_off, (uint32_t)(TILE * sizeof(cd)));
         else jb_bulk_load_1d(kh0 + s_ * TILE, khat + ci.k_off, (uint32_t)(TILE * sizeof(cd)), &bars[s_]);
+#endif
     };
     if (tid == 0) {
         jb_mbar_init(&bars[0], 1);
@@ -322,6 +359,7 @@ k_cols3_pipe(const
 #endif
         const JbColInfo f = info[s];
         if (KD) kh = khat + f.k_off;
+#ifndef JB_ABL_NOCOMPUTE
         C3::s1_fwd(tile, tw1, tid, f.vlo, f.vhi, ADJ ? nullptr : rw, g.m);
         JB_SYNC();
         if constexpr (C3::WL) {
@@ -340,6 +378,7 @@ k_cols3_pipe(const
             C3::s2_inv(tile, tw2, tid);
             JB_SYNC();
         }
+#endif
         {
             const bool act = tid < C3::I1;
             cd v[R1];
@@ -381,10 +420,16 @@ k_cols3_pipe(const
                         }
                     });
                 } else {
+#ifndef JB_ABL_NOCOMPUTE
                     dft<R1, +1>(v);
+#endif
                     const long long stride = (long long)M * PH;
                     cd* ob = out + f.out_off + b + (long long)q0 * PH;
+#ifdef JB_ABL_NOSTORE
+                    if (b < f.ncols && v[0].x == 1.2345e300) {
+#else
                     if (b < f.ncols) {
+#endif
                         static_for<0, R1>([&](auto nn) {
                             constexpr int n1 = nn;
                             int q = q0 + M * n1;
