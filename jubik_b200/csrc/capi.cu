@@ -112,6 +112,7 @@ struct jubik_plan {
     int use_pipe = 0, n_sm = 1;
     int split_epi = 1, nblk_epi = 1;  // Poisson/metric epilogue as a separate elementwise kernel
     int rows_r3_out = 0, rows_r3_adj = 0;  // packed-complex three-stage c2r kernels (rows3.cuh)
+    int rows6 = 0;                         // warp-private r2c kernels (rows6.cuh)
     int sweep = 0;                         // column pass accumulates over the row-patches (cols3.cuh SWEEP + rows5 presum)
     int chunk_e = 0;                       // fused energy+gradient runs one energy bin at a time (L2 residency)
     int rows5 = 0;                         // warp-private c2r kernels with the fused Poisson epilogue (rows5.cuh)
@@ -397,6 +398,9 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
         }
     }
     p->chunk_e = getenv("JUBIK_B200_CHUNK_E") ? 1 : 0;
+    // warp-private r2c kernels: parity-tested, but measured slower than the two-pass kernels of rows_fast.cuh on B200
+    // (forward 69 vs 36 us -- the two-pass kernel skips the zero padding --, adjoint 58 vs 57 us): opt-in
+    p->rows6 = (p->rows5 && getenv("JUBIK_B200_ROWS_R2C_V6") && o->rows6_smem(g) <= (size_t)227 * 1024 - 1024) ? 1 : 0;
     // measured on B200 (C2): the read-add-write costs the column pass more (+48 us per direction) than the row pass
     // gains from reading one summed row (-22 / -13 us), so the sweep stays an opt-in experiment
     p->sweep = (p->rows5 && getenv("JUBIK_B200_SWEEP")) ? 1 : 0;
@@ -501,7 +505,11 @@ static int check_call(jubik_plan* p, const void* a, const void* b, int S) {
 // `g` may be a copy of p->g restricted to an energy-bin chunk (e0, Es)
 static int run_forward_g(jubik_plan* p, const JbGeom& g, const double* x, int S, const JbEpi& ep, jb_stream_t st) {
     const JbFftOps* o = p->ops;
-    JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.Es, p->rpc_in, p->thr_rows, p->fast_rows, st));
+    if (p->rows6) {
+        JB_LAUNCHED(p, o->rows6(g, 0, x, nullptr, p->wgt, p->tw1, p->tw2, p->bufB, S * g.Es, p->n_sm, st));
+    } else {
+        JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.Es, p->rpc_in, p->thr_rows, p->fast_rows, st));
+    }
     if (p->use_pipe) {
         JB_LAUNCHED(p, o->cols_pipe(g, false, p->sweep, p->src_fwd, p->bufA, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
     } else {
@@ -526,7 +534,11 @@ static int run_forward(jubik_plan* p, const double* x, int S, const JbEpi& ep, j
 static int run_adjoint_g(jubik_plan* p, const JbGeom& g, const double* gin, const double* expo, int S, double* out,
                          jb_stream_t st) {
     const JbFftOps* o = p->ops;
-    JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.Es, p->rpc_in, p->thr_rows, p->fast_rows, st));
+    if (p->rows6) {
+        JB_LAUNCHED(p, o->rows6(g, 1, gin, expo, p->wgt, p->tw1, p->tw2, p->bufA, S * g.T * g.Es, p->n_sm, st));
+    } else {
+        JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.Es, p->rpc_in, p->thr_rows, p->fast_rows, st));
+    }
     if (p->use_pipe) {
         JB_LAUNCHED(p, o->cols_pipe(g, true, p->sweep, p->src_adj, p->bufB, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
     } else {

@@ -9,6 +9,7 @@
 #include "rows_pipe.cuh"
 #include "rows3.cuh"
 #include "rows5.cuh"
+#include "rows6.cuh"
 
 
 struct JbFftOps {
@@ -53,6 +54,10 @@ struct JbFftOps {
                              const JbEpi&, int presum, int planes, int n_sm, jb_stream_t);
     cudaError_t (*rows5_adj)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw1, const cd* tw2,
                              const int* gtab, int gq, double* grad, int presum, int planes_se, int n_sm, jb_stream_t);
+    // warp-private r2c kernels (rows6.cuh; need pipe == 2): adj = 0 sky rows -> rowsF, adj = 1 cotangent rows -> rowsA
+    size_t (*rows6_smem)(const JbGeom&);
+    cudaError_t (*rows6)(const JbGeom&, int adj, const double* in, const double* expo, const double* wgt, const cd* tw1,
+                         const cd* tw2, cd* out, int planes, int n_sm, jb_stream_t);
     cudaError_t (*prep_rows)(const JbGeom&, const JbKsrc&, const cd* tw_nk, cd* scratch, int rpc, int threads,
                              jb_stream_t);
     // layout 0: K^ in the two-pass register order (tw = tw_nk); layout 2: three-stage order (twa/twb = tw1/tw2)
@@ -295,6 +300,39 @@ struct JbOpsImpl {
             return (cudaError_t)1;
         }
     }
+    static size_t rows6_smem(const JbGeom& g) {
+        if constexpr (PIPE == 2) {
+            const int sw = rows5_sw(g), NC = (g.n + 1) / 2, NW = (NC + sw - 1) / sw;
+            if (NW * 32 > 512 || F3::L > 65535) return (size_t)1 << 30;
+            return sw == 1 ? jb_rows6_smem<F3, 1>(g.n, g.N) : jb_rows6_smem<F3, 2>(g.n, g.N);
+        } else {
+            (void)g;
+            return (size_t)1 << 30;
+        }
+    }
+    template <int SW, bool ADJ>
+    static cudaError_t rows6_launch(const JbGeom& g, const double* in, const double* expo, const double* wgt,
+                                    const cd* tw1, const cd* tw2, cd* out, int planes, int n_sm, jb_stream_t st) {
+        const int NC = (g.n + 1) / 2, NW = (NC + SW - 1) / SW;
+        const size_t smem = jb_rows6_smem<F3, SW>(g.n, g.N);
+        auto kern = k_rows_r2c6<F3, SW, ADJ>;
+        int grid = rows5_grid(kern, NW * 32, smem, (long)planes * g.N, n_sm);
+        return jb_launch(kern, dim3(grid), dim3(NW * 32), smem, st, g, in, expo, wgt, tw1, tw2, out, planes);
+    }
+    static cudaError_t rows6(const JbGeom& g, int adj, const double* in, const double* expo, const double* wgt,
+                             const cd* tw1, const cd* tw2, cd* out, int planes, int n_sm, jb_stream_t st) {
+        if constexpr (PIPE == 2) {
+            if (rows5_sw(g) == 1) {
+                if (adj) return rows6_launch<1, true>(g, in, expo, wgt, tw1, tw2, out, planes, n_sm, st);
+                return rows6_launch<1, false>(g, in, expo, wgt, tw1, tw2, out, planes, n_sm, st);
+            }
+            if (adj) return rows6_launch<2, true>(g, in, expo, wgt, tw1, tw2, out, planes, n_sm, st);
+            return rows6_launch<2, false>(g, in, expo, wgt, tw1, tw2, out, planes, n_sm, st);
+        } else {
+            (void)g; (void)adj; (void)in; (void)expo; (void)wgt; (void)tw1; (void)tw2; (void)out; (void)planes; (void)n_sm; (void)st;
+            return (cudaError_t)1;
+        }
+    }
     static cudaError_t prep_rows(const JbGeom& g, const JbKsrc& ks, const cd* tw_nk, cd* scratch, int rpc,
                                  int threads, jb_stream_t st) {
         size_t smem = jb_al16((size_t)rpc * FP::LS * sizeof(cd)) + 16;
@@ -318,7 +356,7 @@ struct JbOpsImpl {
                                    rows_fwd, rows_adj_in, cols, cols_pipe,
                                    rows_out, rows_adj_out, rows_out_pipe_smem, rows_adj_out_pipe_smem, rows_out_pipe,
                                    rows_adj_out_pipe, rows_out_r3_smem, rows_adj_out_r3_smem, rows_out_r3, rows_adj_out_r3,
-                                   rows5_smem, rows5_gather, rows5_fwd, rows5_adj, prep_rows, prep_cols};
+                                   rows5_smem, rows5_gather, rows5_fwd, rows5_adj, rows6_smem, rows6, prep_rows, prep_cols};
         return &t;
     }
 };

@@ -300,13 +300,18 @@ def test_full_size_geovi_batch_c5_per_gpu_share(torch_cuda):
     plan.close()
 
 
-def test_sweep_mode_matches_oracle(torch_cuda, monkeypatch):
-    """Opt-in column-pass sweep (accumulation over the row-patches inside the column kernel, rows5 reading the
-    pre-summed spectra): same numbers as the oracle, forward / transpose / fused energy+gradient."""
+@pytest.mark.parametrize("flag", ["JUBIK_B200_SWEEP", "JUBIK_B200_ROWS_R2C_V6", "JUBIK_B200_FUSED_REDUCE",
+                                  "JUBIK_B200_CHUNK_E"])
+def test_optin_kernel_variants_match_oracle(torch_cuda, monkeypatch, flag):
+    """The measured-but-not-default kernel variants stay parity-green."""
+    _variant_parity(torch_cuda, monkeypatch, flag)
+
+
+def _variant_parity(torch_cuda, monkeypatch, flag):
     import jubik_b200 as jb
     torch = torch_cuda
-    monkeypatch.setenv("JUBIK_B200_SWEEP", "1")
-    case = (768, 6, 64, 2, 1, 1, False, True)
+    monkeypatch.setenv(flag, "1")
+    case = (768, 6, 64, 2, 2, 1, False, True)
     N, n, m, T, E, S, full, eff = case
     dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
     plan = jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
