@@ -11,6 +11,11 @@ sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")
 from jubik_b200 import build as b  # noqa: E402
 
 tag, L, extra = sys.argv[1], int(sys.argv[2]), sys.argv[3:]
+cb_override = None
+for a in list(extra):
+    if a.startswith("--cb="):
+        cb_override = int(a[5:])
+        extra.remove(a)
 b.build()
 out = os.path.join(b.HERE, "_variants")
 os.makedirs(out, exist_ok=True)
@@ -18,6 +23,8 @@ objs = []
 for (l, r1, r2, cb, pipe, q1, q2, q3) in b.fft_list():
     o = os.path.join(b.OBJ, "fft_%d.o" % l)
     if l == L:
+        if cb_override:
+            cb = cb_override
         o = os.path.join(out, "fft_%d_%s.o" % (l, tag))
         cmd = ["nvcc"] + b.NVCC_FLAGS + extra + ["-DJB_INST_L=%d" % l, "-DJB_INST_R1=%d" % r1, "-DJB_INST_R2=%d" % r2,
                                                 "-DJB_INST_CB=%d" % cb, "-DJB_INST_PIPE=%d" % pipe, "-DJB_INST_Q1=%d" % q1,
