@@ -162,7 +162,7 @@ int jubik_plan_destroy(jubik_plan* p) {
     dev_free(p->counter); dev_free(p->xexp); dev_free(p->partial); dev_free(p->gtab_fwd); dev_free(p->gtab_adj); dev_free(p->xdev); dev_free(p->gdev); dev_free(p->edev);
 #ifndef JB_EMU
     if (p->st_in) {
-        for (int e = 0; e < p->g.E; ++e) { cudaEventDestroy(p->ev_in[e]); cudaEventDestroy(p->ev_c[e]); }
+        for (int e = 0; e < p->S_max * p->g.E; ++e) { cudaEventDestroy(p->ev_in[e]); cudaEventDestroy(p->ev_c[e]); }
         delete[] p->ev_in; delete[] p->ev_c;
         cudaEventDestroy(p->ev_start);
         cudaStreamDestroy(p->st_in); cudaStreamDestroy(p->st_out);
@@ -768,13 +768,14 @@ int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, d
 #ifndef JB_EMU
     // Energy bins are independent through the whole fused chain, so the call is pipelined per bin: the H2D copy
     // of bin e+1 and the D2H copy of the gradient of bin e-1 overlap the kernels of bin e (three streams).
-    const bool chunked = gh && g.E > 1 && (p->split_epi || p->rows5) && p->has_expo && p->has_data && !getenv("JUBIK_B200_HOST_SERIAL");
+    const bool chunked = gh && (g.E > 1 || (S > 1 && !p->split_epi)) && (p->split_epi || p->rows5) && p->has_expo && p->has_data && !getenv("JUBIK_B200_HOST_SERIAL");
     if (chunked) {
+        const int nev = p->S_max * g.E;
         if (!p->st_in) {
             JB_CK(cudaStreamCreateWithFlags(&p->st_in, cudaStreamNonBlocking));
             JB_CK(cudaStreamCreateWithFlags(&p->st_out, cudaStreamNonBlocking));
-            p->ev_in = new cudaEvent_t[g.E]; p->ev_c = new cudaEvent_t[g.E];
-            for (int e = 0; e < g.E; ++e) {
+            p->ev_in = new cudaEvent_t[nev]; p->ev_c = new cudaEvent_t[nev];
+            for (int e = 0; e < nev; ++e) {
                 JB_CK(cudaEventCreateWithFlags(&p->ev_in[e], cudaEventDisableTiming));
                 JB_CK(cudaEventCreateWithFlags(&p->ev_c[e], cudaEventDisableTiming));
             }
@@ -784,36 +785,54 @@ int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, d
         JB_CK(cudaEventRecord(p->ev_start, st));
         JB_CK(cudaStreamWaitEvent(p->st_in, p->ev_start, 0));
         JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_start, 0));
-        const size_t pitch = (size_t)g.E * npx * sizeof(double), width = npx * sizeof(double);
-        for (int e = 0; e < g.E; ++e) {
-            JB_CK(cudaMemcpy2DAsync(p->xdev + e * npx, pitch, xh + e * npx, pitch, width, S, cudaMemcpyHostToDevice, p->st_in));
-            JB_CK(cudaEventRecord(p->ev_in[e], p->st_in));
-        }
-        for (int e = 0; e < g.E; ++e) {
-            JbGeom ge = g;
-            ge.e0 = e; ge.Es = 1;
-            JB_CK(cudaStreamWaitEvent(st, p->ev_in[e], 0));
-            JbEpi ep; memset(&ep, 0, sizeof(ep));
-            if (p->split_epi) {
+        if (!p->split_epi) {
+            // one (sample, energy bin) plane per chunk: only the first plane's H2D and the last plane's D2H are exposed
+            const size_t plane_b = npx * sizeof(double);
+            for (int c = 0; c < S * g.E; ++c) {
+                JB_CK(cudaMemcpyAsync(p->xdev + (size_t)c * npx, xh + (size_t)c * npx, plane_b, cudaMemcpyHostToDevice, p->st_in));
+                JB_CK(cudaEventRecord(p->ev_in[c], p->st_in));
+            }
+            for (int si = 0; si < S; ++si)
+                for (int e = 0; e < g.E; ++e) {
+                    const int c = si * g.E + e;
+                    JbGeom ge = g;
+                    ge.e0 = e; ge.Es = 1;
+                    JB_CK(cudaStreamWaitEvent(st, p->ev_in[c], 0));
+                    JbEpi ep; memset(&ep, 0, sizeof(ep));
+                    ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data;
+                    ep.partial = p->partial + (size_t)si * g.T * g.E * p->nblk_out;
+                    // the chunk runs as "sample 0" of a one-sample batch on this sample's slices of x / grad / partials
+                    if (int rc = run_forward_g(p, ge, p->xdev + (size_t)si * g.E * npx, 1, ep, st)) return rc;
+                    if (int rc = run_adjoint_g(p, ge, p->gbuf, nullptr, 1, p->gdev + (size_t)si * g.E * npx, st)) return rc;
+                    JB_CK(cudaEventRecord(p->ev_c[c], st));
+                    JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_c[c], 0));
+                    JB_CK(cudaMemcpyAsync(gh + (size_t)c * npx, p->gdev + (size_t)c * npx, plane_b, cudaMemcpyDeviceToHost, p->st_out));
+                }
+            JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
+                                     (const double*)p->partial, g.T * g.E * p->nblk_out, p->edev));
+        } else {
+            const size_t pitch = (size_t)g.E * npx * sizeof(double), width = npx * sizeof(double);
+            for (int e = 0; e < g.E; ++e) {
+                JB_CK(cudaMemcpy2DAsync(p->xdev + e * npx, pitch, xh + e * npx, pitch, width, S, cudaMemcpyHostToDevice, p->st_in));
+                JB_CK(cudaEventRecord(p->ev_in[e], p->st_in));
+            }
+            for (int e = 0; e < g.E; ++e) {
+                JbGeom ge = g;
+                ge.e0 = e; ge.Es = 1;
+                JB_CK(cudaStreamWaitEvent(st, p->ev_in[e], 0));
+                JbEpi ep; memset(&ep, 0, sizeof(ep));
                 ep.mode = JB_EPI_PSF; ep.out = p->gbuf;
                 if (int rc = run_forward_g(p, ge, p->xdev, S, ep, st)) return rc;
                 JB_LAUNCHED(p, jb_launch(k_poisson_epi, dim3(p->nblk_epi, S * g.T), dim3(256), 256 * sizeof(double), st, ge,
                                          p->gbuf, (const double*)p->expo, (const double*)p->data, (int)npx, p->partial));
-            } else {
-                ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
-                if (p->counter && e == g.E - 1) {
-                    ep.energy = p->edev; ep.counter = p->counter; ep.n_samples = S; ep.per_sample = g.T * g.E * p->nblk_out;
-                }
-                if (int rc = run_forward_g(p, ge, p->xdev, S, ep, st)) return rc;
+                if (int rc = run_adjoint_g(p, ge, p->gbuf, nullptr, S, p->gdev, st)) return rc;
+                JB_CK(cudaEventRecord(p->ev_c[e], st));
+                JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_c[e], 0));
+                JB_CK(cudaMemcpy2DAsync(gh + e * npx, pitch, p->gdev + e * npx, pitch, width, S, cudaMemcpyDeviceToHost, p->st_out));
             }
-            if (int rc = run_adjoint_g(p, ge, p->gbuf, nullptr, S, p->gdev, st)) return rc;
-            JB_CK(cudaEventRecord(p->ev_c[e], st));
-            JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_c[e], 0));
-            JB_CK(cudaMemcpy2DAsync(gh + e * npx, pitch, p->gdev + e * npx, pitch, width, S, cudaMemcpyDeviceToHost, p->st_out));
-        }
-        if (p->split_epi || !p->counter)
             JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
-                                     (const double*)p->partial, g.T * g.E * (p->split_epi ? p->nblk_epi : p->nblk_out), p->edev));
+                                     (const double*)p->partial, g.T * g.E * p->nblk_epi, p->edev));
+        }
         if (d2h(eh, p->edev, S * sizeof(double), st)) return fail(JUBIK_ERR_CUDA, "D2H copy of energy failed");
         if (stream_sync(st) || stream_sync(p->st_out)) return fail(JUBIK_ERR_CUDA, "stream synchronise failed");
         return JUBIK_OK;
