@@ -109,6 +109,16 @@ int jubik_poisson_left_sqrt_metric(jubik_plan* plan, const double* x, const doub
 /* log_sky:(S,E,N,N) -> energy of x = exp(log_sky) and d energy / d log_sky = grad_x * x */
 int jubik_poisson_energy_and_grad_logsky(jubik_plan* plan, const double* log_sky, int n_samples,
                                          double* energy, double* grad, void* stream);
+/* Stand-alone helpers of the reference's public API (no plan needed; device pointers, fp64):
+ *   jubik_slice_patches    jubik/convolve.py:28-63: x (lead,h,w) -> out (n*n, lead, 2dx+2dr, 2dy+2dr), patch k = i*n+j at
+ *                          row offset j*dx, column offset i*dy of the dx//2-padded array (dynamic_slice clamping)
+ *   jubik_slice_patches_T  its exact transpose (jax.linear_transpose): patches -> (lead,h,w), deterministic gather
+ *   jubik_convolve         jubik/convolve.py:148-176: dvol * Re ifftn(fftn(x) * fftn(y)) over the last two axes, evaluated
+ *                          as a direct circular sum (n0*n1 <= 256*256); x_lead == 1 is the broadcasting branch :167-171 */
+int jubik_slice_patches(const double* x, int lead, int h, int w, int n_patches, int dr, double* out, void* stream);
+int jubik_slice_patches_T(const double* patches, int lead, int h, int w, int n_patches, int dr, double* out, void* stream);
+int jubik_convolve(const double* x, const double* y, int lead, int x_lead, int n0, int n1, double dvol, double* out,
+                   void* stream);
 /* Same as jubik_poisson_energy_and_grad with HOST buffers (pinned or pageable): H2D of x, the kernels,
  * D2H of energy and grad, all on `stream`, then a stream synchronise.  This is the end-to-end call. */
 int jubik_poisson_energy_and_grad_host(jubik_plan* plan, const double* x_host, int n_samples,

@@ -23,6 +23,7 @@ EXPORTS = [
     "jubik_response_apply_T", "jubik_poisson_energy_and_grad", "jubik_poisson_metric_apply",
     "jubik_poisson_energy_and_grad_host", "jubik_poisson_profile", "jubik_measure_fp64_tflops",
     "jubik_poisson_left_sqrt_metric", "jubik_poisson_energy_and_grad_logsky",
+    "jubik_slice_patches", "jubik_slice_patches_T", "jubik_convolve",
 ]
 
 
@@ -68,6 +69,11 @@ def bind(lib):
     lib.jubik_poisson_energy_and_grad_host.argtypes = [vp, vp, i, vp, vp, vp]
     lib.jubik_poisson_profile.argtypes = [vp, vp, i, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_int), vp]
     lib.jubik_measure_fp64_tflops.argtypes = [C.POINTER(d), vp]
+    lib.jubik_poisson_left_sqrt_metric.argtypes = [vp, vp, vp, i, vp, vp]
+    lib.jubik_poisson_energy_and_grad_logsky.argtypes = [vp, vp, i, vp, vp, vp]
+    lib.jubik_slice_patches.argtypes = [vp, i, i, i, i, i, vp, vp]
+    lib.jubik_slice_patches_T.argtypes = [vp, i, i, i, i, i, vp, vp]
+    lib.jubik_convolve.argtypes = [vp, vp, i, i, i, i, d, vp, vp]
     for name in EXPORTS:
         if name not in ("jubik_last_error", "jubik_plan_launch_count"):
             getattr(lib, name).restype = i

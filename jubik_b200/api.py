@@ -5,6 +5,8 @@ the reference's own:
 
     Domain                      jubik/data.py:19-29
     linpatch_convolve           jubik/convolve.py:66-145
+    slice_patches / _T          jubik/convolve.py:28-63 (+ its jax.linear_transpose, :141-143)
+    convolve                    jubik/convolve.py:148-176
     build_exposure_function     jubik/response.py:12-45
     build_readout_function      jubik/response.py:48-112
     build_psf_operator          instruments/erosita/erosita_response.py:206-212 (psf_op), chandra :127-130
@@ -18,6 +20,7 @@ reference also exposes separately).  There is no CPU path.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import NamedTuple
 
 from .plan import ResponsePlan
@@ -87,6 +90,85 @@ def linpatch_convolve(x, domain, kernel, n_patches_per_axis, margin):
         _PLAN_CACHE[key] = plan
     y = plan.psf(x.reshape((E, N, N)))[0]
     return y.reshape(lead + (N, N))
+
+
+def _stream_ptr(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def slice_patches(x, shape, n_patches_per_axis, additional_margin):
+    """Drop-in for jubik.convolve.slice_patches (convolve.py:28-63): (..., H, W) -> (n*n, ..., 2dx+2dr, 2dy+2dr)."""
+    torch = _torch()
+    from ._lib import load, check
+    lib = load()
+    x = _as_cuda(x)
+    h, w = int(shape[-2]), int(shape[-1])
+    n, dr = int(n_patches_per_axis), int(additional_margin)
+    lead = tuple(x.shape[:-2])
+    nl = 1
+    for v in lead:
+        nl *= v
+    dx, dy = int((h - 2 * dr) / n), int((w - 2 * dr) / n)
+    out = torch.empty((n * n,) + lead + (2 * dx + 2 * dr, 2 * dy + 2 * dr), dtype=torch.float64, device=x.device)
+    check(lib, lib.jubik_slice_patches(C.c_void_p(x.data_ptr()), max(nl, 1), h, w, n, dr, C.c_void_p(out.data_ptr()),
+                                       _stream_ptr(torch)))
+    return out
+
+
+def slice_patches_T(patches, shape, n_patches_per_axis, additional_margin):
+    """Exact transpose of slice_patches (what jax.linear_transpose yields, convolve.py:141-143)."""
+    torch = _torch()
+    from ._lib import load, check
+    lib = load()
+    patches = _as_cuda(patches)
+    h, w = int(shape[-2]), int(shape[-1])
+    n, dr = int(n_patches_per_axis), int(additional_margin)
+    lead = tuple(patches.shape[1:-2])
+    nl = 1
+    for v in lead:
+        nl *= v
+    out = torch.empty(lead + (h, w), dtype=torch.float64, device=patches.device)
+    check(lib, lib.jubik_slice_patches_T(C.c_void_p(patches.data_ptr()), max(nl, 1), h, w, n, dr,
+                                         C.c_void_p(out.data_ptr()), _stream_ptr(torch)))
+    return out
+
+
+def convolve(x, y, domain, axes):
+    """Drop-in for jubik.convolve (convolve.py:148-176): dvol * Re ifftn(fftn(x) * fftn(y)) over the last two axes,
+    including the broadcasting branch (y.ndim > x.ndim) and its console message.  Stand-alone calls use a direct
+    circular sum on the GPU (arrays up to 256x256); the FFT pipeline is the ResponsePlan / linpatch_convolve path."""
+    torch = _torch()
+    from ._lib import load, check
+    lib = load()
+    x = _as_cuda(x)
+    y = _as_cuda(y, x.device)
+    nd = max(x.dim(), y.dim())
+    if sorted(a % nd if a >= 0 else a + nd for a in axes) != [nd - 2, nd - 1] and sorted(axes) != [-2, -1]:
+        raise NotImplementedError("convolve: only the last two axes are supported")
+    dvol = 1.0
+    for a in axes:
+        dvol *= float(domain.distances[a])
+    n0, n1 = int(y.shape[-2]), int(y.shape[-1])
+    if tuple(x.shape[-2:]) != (n0, n1):
+        raise ValueError("convolve: the last two axes of both arrays must agree")
+    if y.dim() > x.dim():
+        print("kernel_shape:", tuple(x.shape))
+        print("signal_shape:", tuple(y.shape))
+        print("Dimension Inconsistency. Broadcasting PSFs")
+        if x.dim() != 2:
+            raise NotImplementedError("convolve: broadcasting is supported for a 2-D kernel")
+        x_lead = 1
+    else:
+        if tuple(x.shape) != tuple(y.shape):
+            raise ValueError("convolve: shapes must agree")
+        x_lead = None
+    lead = 1
+    for v in y.shape[:-2]:
+        lead *= v
+    out = torch.empty_like(y)
+    check(lib, lib.jubik_convolve(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), lead, lead if x_lead is None else 1,
+                                  n0, n1, dvol, C.c_void_p(out.data_ptr()), _stream_ptr(torch)))
+    return out
 
 
 def build_exposure_function(exposures, exposure_cut=None):

@@ -753,6 +753,117 @@ int jubik_poisson_energy_and_grad_logsky(jubik_plan* p, const double* log_sky, i
     return JUBIK_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Stand-alone versions of the reference's public helpers (jubik/convolve.py:28-63 slice_patches and its
+// jax.linear_transpose, :148-176 convolve).  The fused path above never materialises the patches; these exist so
+// that callers of ju.slice_patches / ju.convolve find the same functions.
+
+struct JbSliceGeom { int lead, h, w, n, dr, dx, dy, sx, sy, hx, hy; };
+
+static int slice_geom(JbSliceGeom& q, int lead, int h, int w, int n, int dr) {
+    if (lead < 1 || h < 1 || w < 1 || n < 1 || dr < 0) return fail(JUBIK_ERR_ARG, "slice_patches: bad shape");
+    q.lead = lead; q.h = h; q.w = w; q.n = n; q.dr = dr;
+    q.dx = (h - 2 * dr) / n; q.dy = (w - 2 * dr) / n;          // int() truncation, convolve.py:43-44
+    if (q.dx < 1 || q.dy < 1) return fail(JUBIK_ERR_ARG, "slice_patches: more patches than pixels");
+    q.sx = 2 * q.dx + 2 * dr; q.sy = 2 * q.dy + 2 * dr;
+    q.hx = q.dx / 2; q.hy = q.dy / 2;
+    if (q.sx > h + 2 * q.hx || q.sy > w + 2 * q.hy) return fail(JUBIK_ERR_ARG, "slice_patches: window larger than the padded array");
+    return 0;
+}
+// window start with lax.dynamic_slice clamping (convolve.py:55-57)
+JB_HD int jb_slice_off(int j, int d, int frame, int size) {
+    int o = j * d;
+    if (o > frame - size) o = frame - size;
+    return o < 0 ? 0 : o;
+}
+
+// out (n*n, lead, sx, sy): patch k = i*n + j <- padded x rows offx[j].., columns offy[i]..
+JB_GLOBAL_S void k_slice_patches(JbSliceGeom q, const double* __restrict__ x, double* __restrict__ out) {
+    const size_t per = (size_t)q.sx * q.sy, tot = (size_t)q.n * q.n * q.lead * per;
+    for (size_t idx = (size_t)blockIdx.x * jb_nthr() + jb_tid(); idx < tot; idx += (size_t)gridDim.x * jb_nthr()) {
+        size_t r = idx;
+        const int c = (int)(r % q.sy); r /= q.sy;
+        const int a = (int)(r % q.sx); r /= q.sx;
+        const int l = (int)(r % q.lead);
+        const int k = (int)(r / q.lead), i = k / q.n, j = k - i * q.n;
+        const int row = jb_slice_off(j, q.dx, q.h + 2 * q.hx, q.sx) + a - q.hx;
+        const int col = jb_slice_off(i, q.dy, q.w + 2 * q.hy, q.sy) + c - q.hy;
+        out[idx] = (row >= 0 && row < q.h && col >= 0 && col < q.w) ? x[((size_t)l * q.h + row) * q.w + col] : 0.0;
+    }
+}
+// transpose as a gather: out (lead, h, w) <- sum over the patches covering the pixel, fixed order k ascending
+JB_GLOBAL_S void k_slice_patches_T(JbSliceGeom q, const double* __restrict__ patches, double* __restrict__ out) {
+    const size_t tot = (size_t)q.lead * q.h * q.w, per = (size_t)q.sx * q.sy;
+    for (size_t idx = (size_t)blockIdx.x * jb_nthr() + jb_tid(); idx < tot; idx += (size_t)gridDim.x * jb_nthr()) {
+        size_t r = idx;
+        const int col = (int)(r % q.w); r /= q.w;
+        const int row = (int)(r % q.h);
+        const int l = (int)(r / q.h);
+        double acc = 0.0;
+        for (int i = 0; i < q.n; ++i) {
+            const int c = col + q.hy - jb_slice_off(i, q.dy, q.w + 2 * q.hy, q.sy);
+            if (c < 0 || c >= q.sy) continue;
+            for (int j = 0; j < q.n; ++j) {
+                const int a = row + q.hx - jb_slice_off(j, q.dx, q.h + 2 * q.hx, q.sx);
+                if (a < 0 || a >= q.sx) continue;
+                acc += patches[((size_t)(i * q.n + j) * q.lead + l) * per + (size_t)a * q.sy + c];
+            }
+        }
+        out[idx] = acc;
+    }
+}
+// dvol * (x circularly convolved with y) over the last two axes by direct summation (== Re ifftn(fftn x * fftn y) for
+// real inputs); x: (x_lead, n0, n1) with x_lead in {lead, 1} (1 = the reference's broadcasting branch), y, out: (lead, n0, n1)
+JB_GLOBAL_S void k_convolve_direct(const double* __restrict__ x, const double* __restrict__ y, int lead, int x_lead, int n0,
+                                   int n1, double dvol, double* __restrict__ out) {
+    const size_t tot = (size_t)lead * n0 * n1;
+    for (size_t idx = (size_t)blockIdx.x * jb_nthr() + jb_tid(); idx < tot; idx += (size_t)gridDim.x * jb_nthr()) {
+        size_t r = idx;
+        const int j = (int)(r % n1); r /= n1;
+        const int i = (int)(r % n0);
+        const int l = (int)(r / n0);
+        const double* xp = x + (size_t)(x_lead == 1 ? 0 : l) * n0 * n1;
+        const double* yp = y + (size_t)l * n0 * n1;
+        double acc = 0.0;
+        for (int a = 0; a < n0; ++a) {
+            int ia = i - a; if (ia < 0) ia += n0;
+            for (int b = 0; b < n1; ++b) {
+                int jb = j - b; if (jb < 0) jb += n1;
+                acc += xp[(size_t)a * n1 + b] * yp[(size_t)ia * n1 + jb];
+            }
+        }
+        out[idx] = dvol * acc;
+    }
+}
+
+int jubik_slice_patches(const double* x, int lead, int h, int w, int n_patches, int dr, double* out, void* stream_) {
+    if (!x || !out) return fail(JUBIK_ERR_ARG, "null array pointer");
+    if (device_count() < 1) return fail(JUBIK_ERR_CUDA, "no CUDA device: jubik_b200 has no CPU fallback");
+    JbSliceGeom q;
+    if (int rc = slice_geom(q, lead, h, w, n_patches, dr)) return rc;
+    JB_CK(jb_launch(k_slice_patches, dim3(1184), dim3(256), 0, (jb_stream_t)stream_, q, x, out));
+    return JUBIK_OK;
+}
+int jubik_slice_patches_T(const double* patches, int lead, int h, int w, int n_patches, int dr, double* out, void* stream_) {
+    if (!patches || !out) return fail(JUBIK_ERR_ARG, "null array pointer");
+    if (device_count() < 1) return fail(JUBIK_ERR_CUDA, "no CUDA device: jubik_b200 has no CPU fallback");
+    JbSliceGeom q;
+    if (int rc = slice_geom(q, lead, h, w, n_patches, dr)) return rc;
+    JB_CK(jb_launch(k_slice_patches_T, dim3(1184), dim3(256), 0, (jb_stream_t)stream_, q, patches, out));
+    return JUBIK_OK;
+}
+int jubik_convolve(const double* x, const double* y, int lead, int x_lead, int n0, int n1, double dvol, double* out,
+                   void* stream_) {
+    if (!x || !y || !out) return fail(JUBIK_ERR_ARG, "null array pointer");
+    if (device_count() < 1) return fail(JUBIK_ERR_CUDA, "no CUDA device: jubik_b200 has no CPU fallback");
+    if (lead < 1 || n0 < 1 || n1 < 1 || (x_lead != lead && x_lead != 1)) return fail(JUBIK_ERR_ARG, "convolve: bad shape");
+    if ((size_t)n0 * n1 > (size_t)256 * 256)
+        return fail(JUBIK_ERR_UNSUPPORTED, "stand-alone convolve uses direct summation (<= 256x256); the FFT path is "
+                                           "jubik_plan_create + jubik_psf_apply");
+    JB_CK(jb_launch(k_convolve_direct, dim3(1184), dim3(128), 0, (jb_stream_t)stream_, x, y, lead, x_lead, n0, n1, dvol, out));
+    return JUBIK_OK;
+}
+
 int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, double* eh, double* gh, void* stream_) {
     jb_stream_t st = (jb_stream_t)stream_;
     if (int rc = check_call(p, xh, eh, S)) return rc;

@@ -327,6 +327,39 @@ def _variant_parity(torch_cuda, monkeypatch, flag):
     plan.close()
 
 
+def test_standalone_slice_patches_and_convolve_match_reference_golden(torch_cuda, golden_dir, capsys):
+    """The stand-alone public helpers against outputs of the reference's own source (tests/golden/make_golden.py):
+    slice_patches (test/test_slice_patches.py fixture, incl. dynamic_slice clamping), its linear transpose, and
+    convolve with its broadcasting branch (test/test_convolve.py)."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    z = np.load(os.path.join(golden_dir, "slice_patches.npz"))
+    sp = jb.slice_patches(dev(torch, z["a"]), (36, 36), 16, 2).cpu().numpy()
+    assert sp.shape == z["sp"].shape and np.array_equal(sp, z["sp"])
+    spT = jb.slice_patches_T(dev(torch, z["b"]), (36, 36), 16, 2).cpu().numpy()
+    assert np.allclose(spT, z["spT"], rtol=0, atol=1e-13)
+    assert np.array_equal(jb.slice_patches(dev(torch, z["a2"]), (15, 15), 5, 0).cpu().numpy(), z["sp2"])
+    # adjointness with a leading axis (test_slice_patches.py:55-66)
+    a = synth.direction((3, 36, 36), seed=21)
+    b = synth.direction((256, 3, 8, 8), seed=22)
+    lhs = np.vdot(b, jb.slice_patches(dev(torch, a), (36, 36), 16, 2).cpu().numpy())
+    rhs = np.vdot(jb.slice_patches_T(dev(torch, b), (36, 36), 16, 2).cpu().numpy(), a)
+    assert abs(lhs - rhs) / abs(lhs) < 1e-13
+    c = np.load(os.path.join(golden_dir, "convolve.npz"))
+    dom = jb.Domain(tuple(c["sig"].shape), tuple(c["distances"]))
+    c1 = jb.convolve(dev(torch, c["ker"]), dev(torch, c["sig"]), dom, axes=(-2, -1)).cpu().numpy()
+    assert rel(c1, c["c1"]) < 1e-12
+    capsys.readouterr()
+    c2 = jb.convolve(dev(torch, c["ker2"]), dev(torch, c["sig"]), dom, axes=(-2, -1)).cpu().numpy()
+    assert "Dimension Inconsistency. Broadcasting PSFs" in capsys.readouterr().out
+    assert c2.shape == c["sig"].shape and rel(c2, c["c2"]) < 1e-12
+    # delta kernel => identity (test_convolve.py:32-41)
+    k = np.zeros((4, 4)); k[0, 0] = 1.0
+    sig = np.random.default_rng(0).normal(size=(4, 4))
+    res = jb.convolve(dev(torch, k), dev(torch, sig), jb.Domain((4, 4), (1.0, 1.0)), axes=(-2, -1)).cpu().numpy()
+    np.testing.assert_allclose(res, sig, rtol=1e-10, atol=1e-10)
+
+
 def test_error_behaviour_matches_reference(torch_cuda):
     import jubik_b200 as jb
     torch = torch_cuda
