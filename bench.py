@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- fused forward + VJP of response + Poisson log-likelihood, fp64, in sky-pixels/s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C1|C3s]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C1|C3s|C3|C4]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU)
 
 Workload at N=1: BASELINE.json configs[1] ("C2", Chandra-like): 1024x1024 sky, 3 energy bins, 8x8
@@ -43,6 +43,11 @@ WORKLOADS = {
     "C2": (1024, 8, 64, 1, 3, "C2 Chandra-like: 1024x1024 sky, 3 energy bins, 8x8 PSF patches, margin 64, "
                               "exposure + mask + Poisson fwd+VJP"),
     "C3s": (1020, 10, 64, 2, 3, "C3-like slice: 1020x1020 sky, 2 modules x 3 bins, 10x10 PSF patches, margin 64"),
+    # the other single-GPU configurations of BASELINE.json (parity-test cases; benched on request for DESIGN.md section 4)
+    "C3": (1024, 10, 64, 7, 3, "C3 eROSITA-like: 7 telescope modules x 3 energy bins, 1024x1024 sky, 10x10 PSF patches, "
+                               "margin 64 (P=332 -> L=336), per-module exposure/readout masks"),
+    "C4": (4096, 16, 64, 1, 1, "C4 JWST-like: 4096x4096 sky, 16x16 PSF patches with 128-px kernels (margin 64, P=640), "
+                               "single filter"),
 }
 
 
@@ -170,6 +175,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything a library writes to fd 1 (NCCL prints its version banner there)
+    # is sent to stderr instead, and the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
@@ -202,7 +212,18 @@ def run_ours(args):
     gbuf = flat[:npx].view(1, E, N, N) if S == 1 else torch.empty((S, E, N, N), dtype=torch.float64, device=dev)
     ebuf = flat[npx + rank * S: npx + (rank + 1) * S]
 
+    # default: the whole step -- kernels, the fold of the rank's samples into `flat` and the ONE ncclAllReduce -- is a
+    # single C-ABI call (jubik_poisson_energy_and_grad_sharded) on one stream; the library owns the NCCL communicator
+    # (torch.distributed only hands the ncclUniqueId around).  JUBIK_B200_TORCH_ALLREDUCE=1 keeps the collective in torch.
+    via_torch = os.environ.get("JUBIK_B200_TORCH_ALLREDUCE") == "1"
+    comm = None
+    if world > 1 and not via_torch:
+        comm = jb.Communicator.from_torch_distributed()
+    glocal = gbuf if S > 1 else None     # per-sample gradients of this rank (S == 1: the gradient lands in flat directly)
+
     def step_device():
+        if not via_torch:
+            return plan.energy_and_grad_sharded(x, comm, jb.SHARD_SAMPLES, flat=flat, grad_local=glocal)
         if world > 1:
             flat[npx:].zero_()
         e, g = plan.energy_and_grad(x, out_energy=ebuf, out_grad=gbuf)
@@ -320,14 +341,19 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": desc, "N": N, "n_patches": n, "margin": m, "T": T, "E": E,
                            "samples_per_gpu": S, "fft_length": L, "parallelism": "sample-sharded x%d" % world,
+                           "collective": ("torch.distributed all_reduce" if via_torch else
+                                          "one ncclAllReduce of [sum-grad | energies] issued inside the C-ABI call")
+                           if world > 1 else "none",
                            "l2": "flushed (192 MiB write) between timed iterations; working set %.0f MB > L2"
                                  % (info["bytes_total"] / 1e6)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": t_e2e / args.steps * 1e3},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cb}
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
+        if comm is not None:
+            comm.close()
         dist.destroy_process_group()
     return 0
 

@@ -124,6 +124,31 @@ int jubik_convolve(const double* x, const double* y, int lead, int x_lead, int n
 int jubik_poisson_energy_and_grad_host(jubik_plan* plan, const double* x_host, int n_samples,
                                        double* energy_host, double* grad_host, void* stream);
 
+/* Multi-GPU variants (one process per GPU).  The reference has no multi-device path: its VI driver maps the
+ * likelihood over posterior samples on one device (jft.optimize_kl, erosita_likelihood.py:85-89 under jax.vmap) and sums
+ * the telescope modules inside one callable (erosita_response.py:209-212).  These entry points shard exactly those two
+ * axes and combine the partial log-likelihoods and gradients with ONE ncclAllReduce(sum, fp64) of `flat` on `stream`:
+ *   JUBIK_SHARD_SAMPLES  every rank evaluates its own S samples of a replicated plan.
+ *       flat = [ sum over ALL samples of d energy / d sky  (E,N,N) | energies (n_ranks, S) ]
+ *       grad_local (S,E,N,N) receives this rank's per-sample gradients (NULL: not wanted).
+ *   JUBIK_SHARD_MODULES  every rank holds a plan of its own modules (T_local) and evaluates the same S samples.
+ *       flat = [ d energy / d sky (S,E,N,N) | energies (S) ], both summed over ranks; grad_local must be NULL.
+ * jubik_sharded_flat_size gives the element count of `flat`.  comm == NULL runs the single-rank path (no collective).
+ * NCCL is bound with dlopen("libnccl.so.2") at the first jubik_comm_* call; jubik_comm_create wraps ncclCommInitRank on
+ * the current device with a 128-byte ncclUniqueId from jubik_comm_unique_id (rank 0) that the caller distributes;
+ * jubik_comm_adopt wraps an ncclComm_t the caller already owns (it is not destroyed by jubik_comm_destroy). */
+typedef struct jubik_comm jubik_comm;
+enum { JUBIK_SHARD_SAMPLES = 0, JUBIK_SHARD_MODULES = 1 };
+int jubik_comm_unique_id(void* id128_out);
+int jubik_comm_create(jubik_comm** comm, const void* id128, int rank, int n_ranks);
+int jubik_comm_adopt(jubik_comm** comm, void* nccl_comm);
+int jubik_comm_destroy(jubik_comm* comm);
+int jubik_comm_rank(const jubik_comm* comm);
+int jubik_comm_size(const jubik_comm* comm);
+long long jubik_sharded_flat_size(const jubik_plan* plan, const jubik_comm* comm, int shard_mode, int n_samples);
+int jubik_poisson_energy_and_grad_sharded(jubik_plan* plan, jubik_comm* comm, int shard_mode, const double* x,
+                                          int n_samples, double* grad_local, double* flat, void* stream);
+
 /* Measurement helpers (bench.py): the energy+grad sequence with a CUDA event after every kernel,
  * ms_out[0..*n_out) (room for 48) in launch order = rows_fwd, cols_fwd, rows_out, [poisson_epi,] reduce,
  * rows_adj_in, cols_adj, rows_adj_out (synchronises); and a DFMA micro-benchmark giving this device's FP64 FMA

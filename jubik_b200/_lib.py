@@ -24,7 +24,10 @@ EXPORTS = [
     "jubik_poisson_energy_and_grad_host", "jubik_poisson_profile", "jubik_measure_fp64_tflops",
     "jubik_poisson_left_sqrt_metric", "jubik_poisson_energy_and_grad_logsky",
     "jubik_slice_patches", "jubik_slice_patches_T", "jubik_convolve",
+    "jubik_comm_unique_id", "jubik_comm_create", "jubik_comm_adopt", "jubik_comm_destroy", "jubik_comm_rank",
+    "jubik_comm_size", "jubik_sharded_flat_size", "jubik_poisson_energy_and_grad_sharded",
 ]
+SHARD_SAMPLES, SHARD_MODULES = 0, 1
 
 
 class PlanDesc(C.Structure):
@@ -74,8 +77,17 @@ def bind(lib):
     lib.jubik_slice_patches.argtypes = [vp, i, i, i, i, i, vp, vp]
     lib.jubik_slice_patches_T.argtypes = [vp, i, i, i, i, i, vp, vp]
     lib.jubik_convolve.argtypes = [vp, vp, i, i, i, i, d, vp, vp]
+    lib.jubik_comm_unique_id.argtypes = [vp]
+    lib.jubik_comm_create.argtypes = [C.POINTER(vp), vp, i, i]
+    lib.jubik_comm_adopt.argtypes = [C.POINTER(vp), vp]
+    lib.jubik_comm_destroy.argtypes = [vp]
+    lib.jubik_comm_rank.argtypes = [vp]
+    lib.jubik_comm_size.argtypes = [vp]
+    lib.jubik_sharded_flat_size.argtypes = [vp, vp, i, i]
+    lib.jubik_sharded_flat_size.restype = C.c_longlong
+    lib.jubik_poisson_energy_and_grad_sharded.argtypes = [vp, vp, i, vp, i, vp, vp, vp]
     for name in EXPORTS:
-        if name not in ("jubik_last_error", "jubik_plan_launch_count"):
+        if name not in ("jubik_last_error", "jubik_plan_launch_count", "jubik_sharded_flat_size"):
             getattr(lib, name).restype = i
     return lib
 

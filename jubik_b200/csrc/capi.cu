@@ -958,3 +958,170 @@ int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, d
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Multi-GPU variants: the fused evaluation followed by ONE ncclAllReduce of a flat buffer on
+// the caller's stream.  NCCL is bound at run time (dlopen of the libnccl.so.2 already in the process -- torch's or
+// jax's -- or the system one): the library has no link-time NCCL dependency and single-GPU users never load it.
+#ifndef JB_EMU
+#include <dlfcn.h>
+namespace {
+struct JbNcclId { char internal[128]; };          // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128)
+typedef void* jb_nccl_comm_t;
+struct JbNccl {
+    void* h = nullptr;
+    int (*GetUniqueId)(JbNcclId*) = nullptr;
+    int (*CommInitRank)(jb_nccl_comm_t*, int, JbNcclId, int) = nullptr;
+    int (*CommDestroy)(jb_nccl_comm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, jb_nccl_comm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*CommCount)(jb_nccl_comm_t, int*) = nullptr;
+    int (*CommUserRank)(jb_nccl_comm_t, int*) = nullptr;
+};
+JbNccl g_nccl;
+int nccl_load() {
+    if (g_nccl.h) return 0;
+    const char* names[] = {getenv("JUBIK_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* nm : names) {
+        if (!nm || !*nm) continue;
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(JUBIK_ERR_UNSUPPORTED, std::string("NCCL not found (libnccl.so.2): ") + (dlerror() ? dlerror() : ""));
+    JbNccl t; t.h = h;
+    t.GetUniqueId = (decltype(t.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    t.CommInitRank = (decltype(t.CommInitRank))dlsym(h, "ncclCommInitRank");
+    t.CommDestroy = (decltype(t.CommDestroy))dlsym(h, "ncclCommDestroy");
+    t.AllReduce = (decltype(t.AllReduce))dlsym(h, "ncclAllReduce");
+    t.GetErrorString = (decltype(t.GetErrorString))dlsym(h, "ncclGetErrorString");
+    t.CommCount = (decltype(t.CommCount))dlsym(h, "ncclCommCount");
+    t.CommUserRank = (decltype(t.CommUserRank))dlsym(h, "ncclCommUserRank");
+    if (!t.GetUniqueId || !t.CommInitRank || !t.CommDestroy || !t.AllReduce || !t.GetErrorString || !t.CommCount || !t.CommUserRank)
+        return fail(JUBIK_ERR_UNSUPPORTED, "libnccl lacks a required symbol");
+    g_nccl = t;
+    return 0;
+}
+int nccl_fail(const char* what, int rc) {
+    return fail(JUBIK_ERR_CUDA, std::string(what) + " -> NCCL error " + std::to_string(rc) + ": " + g_nccl.GetErrorString(rc));
+}
+}  // namespace
+#endif
+
+struct jubik_comm {
+    void* nccl = nullptr;   // ncclComm_t
+    int rank = 0, n_ranks = 1, owned = 0;
+};
+
+extern "C" {
+
+int jubik_comm_unique_id(void* id_out) {
+#ifndef JB_EMU
+    if (!id_out) return fail(JUBIK_ERR_ARG, "null pointer");
+    if (int rc = nccl_load()) return rc;
+    if (int rc = g_nccl.GetUniqueId((JbNcclId*)id_out)) return nccl_fail("ncclGetUniqueId", rc);
+    return JUBIK_OK;
+#else
+    (void)id_out;
+    return fail(JUBIK_ERR_UNSUPPORTED, "no NCCL in the emulation build");
+#endif
+}
+
+int jubik_comm_create(jubik_comm** out, const void* id, int rank, int n_ranks) {
+#ifndef JB_EMU
+    if (!out || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(JUBIK_ERR_ARG, "bad communicator arguments");
+    if (int rc = nccl_load()) return rc;
+    JbNcclId nid;
+    memcpy(&nid, id, sizeof(nid));
+    jb_nccl_comm_t c = nullptr;
+    if (int rc = g_nccl.CommInitRank(&c, n_ranks, nid, rank)) return nccl_fail("ncclCommInitRank", rc);
+    jubik_comm* m = new (std::nothrow) jubik_comm();
+    if (!m) return fail(JUBIK_ERR_ALLOC, "out of host memory");
+    m->nccl = c; m->rank = rank; m->n_ranks = n_ranks; m->owned = 1;
+    *out = m;
+    return JUBIK_OK;
+#else
+    (void)out; (void)id; (void)rank; (void)n_ranks;
+    return fail(JUBIK_ERR_UNSUPPORTED, "no NCCL in the emulation build");
+#endif
+}
+
+int jubik_comm_adopt(jubik_comm** out, void* nccl_comm) {
+#ifndef JB_EMU
+    if (!out || !nccl_comm) return fail(JUBIK_ERR_ARG, "null pointer");
+    if (int rc = nccl_load()) return rc;
+    jubik_comm* m = new (std::nothrow) jubik_comm();
+    if (!m) return fail(JUBIK_ERR_ALLOC, "out of host memory");
+    m->nccl = nccl_comm; m->owned = 0;
+    int rc = g_nccl.CommCount(nccl_comm, &m->n_ranks);
+    if (!rc) rc = g_nccl.CommUserRank(nccl_comm, &m->rank);
+    if (rc) { delete m; return nccl_fail("ncclCommCount/ncclCommUserRank", rc); }
+    *out = m;
+    return JUBIK_OK;
+#else
+    (void)out; (void)nccl_comm;
+    return fail(JUBIK_ERR_UNSUPPORTED, "no NCCL in the emulation build");
+#endif
+}
+
+int jubik_comm_destroy(jubik_comm* c) {
+    if (!c) return JUBIK_OK;
+#ifndef JB_EMU
+    if (c->owned && c->nccl && g_nccl.h) g_nccl.CommDestroy(c->nccl);
+#endif
+    delete c;
+    return JUBIK_OK;
+}
+
+int jubik_comm_rank(const jubik_comm* c) { return c ? c->rank : 0; }
+int jubik_comm_size(const jubik_comm* c) { return c ? c->n_ranks : 1; }
+
+long long jubik_sharded_flat_size(const jubik_plan* p, const jubik_comm* c, int shard_mode, int S) {
+    if (!p || S < 1) return -1;
+    const long long npx = (long long)p->g.E * p->g.N * p->g.N;
+    const int R = c ? c->n_ranks : 1;
+    if (shard_mode == JUBIK_SHARD_SAMPLES) return npx + (long long)R * S;
+    if (shard_mode == JUBIK_SHARD_MODULES) return (long long)S * npx + S;
+    return -1;
+}
+
+int jubik_poisson_energy_and_grad_sharded(jubik_plan* p, jubik_comm* c, int shard_mode, const double* x, int S,
+                                          double* grad_local, double* flat, void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (int rc = check_call(p, x, flat, S)) return rc;
+    const JbGeom& g = p->g;
+    const size_t npx = (size_t)g.E * g.N * g.N;
+    const int R = c ? c->n_ranks : 1, rank = c ? c->rank : 0;
+    size_t count = 0;
+    if (shard_mode == JUBIK_SHARD_MODULES) {
+        // this rank's modules only: partial energies (S) and partial gradients (S,E,N,N) land in flat and are summed
+        count = (size_t)S * npx + S;
+        if (int rc = jubik_poisson_energy_and_grad(p, x, S, flat + (size_t)S * npx, flat, stream_)) return rc;
+        if (grad_local) return fail(JUBIK_ERR_ARG, "module sharding has no per-rank gradient output (pass NULL)");
+    } else if (shard_mode == JUBIK_SHARD_SAMPLES) {
+        count = npx + (size_t)R * S;
+        double* gl = grad_local;
+        if (!gl && S > 1) {
+            if (!p->gdev) {
+                if (int rc = alloc(p, (void**)&p->gdev, (size_t)p->S_max * npx * sizeof(double), "per-sample gradient staging")) return rc;
+            }
+            gl = p->gdev;
+        }
+        if (!gl) gl = flat;   // one local sample and no per-sample output wanted: the gradient is written in place
+        if (int rc = jubik_poisson_energy_and_grad(p, x, S, flat + npx + (size_t)rank * S, gl, stream_)) return rc;
+        JB_LAUNCHED(p, jb_launch(k_fold_samples, dim3(1184), dim3(256), 0, st, (const double*)(gl == flat ? nullptr : gl), S, npx,
+                                 flat, rank * S, R * S));
+    } else {
+        return fail(JUBIK_ERR_ARG, "unknown shard mode");
+    }
+#ifndef JB_EMU
+    if (c && c->nccl) {   // also for a one-rank communicator (NCCL treats it as an in-place copy)
+        if (int rc = g_nccl.AllReduce(flat, flat, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl, st))
+            return nccl_fail("ncclAllReduce", rc);
+    }
+#endif
+    (void)count;
+    return JUBIK_OK;
+}
+
+}  // extern "C"

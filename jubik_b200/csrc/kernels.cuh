@@ -515,6 +515,27 @@ JB_GLOBAL_S void k_mul_inplace(double* __restrict__ a, const double* __restrict_
     for (size_t i = (size_t)blockIdx.x * jb_nthr() + jb_tid(); i < n; i += (size_t)gridDim.x * jb_nthr()) a[i] *= b[i];
 }
 
+// sample-sharded multi-GPU evaluation: flat = [ sum_s grad[s] (npx) | energies of all ranks' samples (nslots) ].
+// This rank's energies were already written into its slots [slot0, slot0+S) by k_reduce_energy; the other slots are
+// zeroed here so that ONE all-reduce(sum) of `flat` delivers the sample-summed gradient and every energy.
+// grad == nullptr: the gradient of the single local sample already sits in flat (only the slots are cleared).
+JB_GLOBAL_S void k_fold_samples(const double* __restrict__ grad, int S, size_t npx, double* __restrict__ flat, int slot0,
+                                int nslots) {
+    const size_t t0 = (size_t)blockIdx.x * jb_nthr() + jb_tid(), nt = (size_t)gridDim.x * jb_nthr();
+    if (grad) {
+        const cd* g2 = reinterpret_cast<const cd*>(grad);   // 128-bit accesses
+        cd* f2 = reinterpret_cast<cd*>(flat);
+        const size_t h = npx / 2;   // npx = E*N*N with N even
+        for (size_t i = t0; i < h; i += nt) {
+            cd a = g2[i];
+            for (int s = 1; s < S; ++s) { cd b = g2[(size_t)s * h + i]; a.x += b.x; a.y += b.y; }   // fixed order
+            f2[i] = a;
+        }
+    }
+    for (size_t j = t0; j < (size_t)nslots; j += nt)
+        if ((int)j < slot0 || (int)j >= slot0 + S) flat[npx + j] = 0.0;
+}
+
 // energy[s] = sum over (t,e) planes and row blocks of the per-CTA partials; one CTA per sample
 JB_GLOBAL_S void k_reduce_energy(const double* __restrict__ partial, int per_sample, double* __restrict__ energy) {
     JB_SMEM(double, red);

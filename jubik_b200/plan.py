@@ -219,6 +219,42 @@ class ResponsePlan:
     def energy(self, x):
         return self.energy_and_grad(x, need_grad=False)[0]
 
+    def flat_size(self, comm, n_samples, shard_mode=_lib.SHARD_SAMPLES):
+        """Element count of the flat all-reduce buffer of energy_and_grad_sharded (jubik_sharded_flat_size)."""
+        n = int(self.raw.lib.jubik_sharded_flat_size(self.raw.handle, comm.handle if comm is not None else None,
+                                                     int(shard_mode), int(n_samples)))
+        if n < 0:
+            raise ValueError("bad shard mode / sample count")
+        return n
+
+    def energy_and_grad_sharded(self, x, comm, shard_mode=_lib.SHARD_SAMPLES, flat=None, grad_local=None):
+        """Multi-GPU fused evaluation: this rank's share of the work, then ONE ncclAllReduce of `flat` on the current
+        stream (jubik_poisson_energy_and_grad_sharded).  comm: Communicator or None (single rank, no collective).
+          SHARD_SAMPLES: x = this rank's (S,E,N,N) samples -> (energies (n_ranks,S), sample-summed gradient (E,N,N));
+                         grad_local (S,E,N,N), if given, receives the per-sample gradients of this rank.
+          SHARD_MODULES: the plan holds this rank's modules, x is replicated -> (energies (S,), gradient (S,E,N,N)).
+        The returned tensors are views into `flat`."""
+        import torch
+        x, _ = self._sky(x)
+        S = x.shape[0]
+        n = self.flat_size(comm, S, shard_mode)
+        if flat is None:
+            flat = torch.empty((n,), dtype=torch.float64, device=self.device)
+        if flat.numel() != n or not flat.is_contiguous() or flat.dtype != torch.float64 or not flat.is_cuda:
+            raise ValueError("flat must be a contiguous float64 CUDA tensor of %d elements" % n)
+        if grad_local is not None and (grad_local.numel() != x.numel() or not grad_local.is_contiguous()):
+            raise ValueError("grad_local must be contiguous (S,E,N,N)")
+        self.raw.call("jubik_poisson_energy_and_grad_sharded", comm.handle if comm is not None else None,
+                      int(shard_mode), C.c_void_p(x.data_ptr()), S,
+                      C.c_void_p(grad_local.data_ptr()) if grad_local is not None else None,
+                      C.c_void_p(flat.data_ptr()), self._stream())
+        npx = self.E * self.N * self.N
+        if shard_mode == _lib.SHARD_SAMPLES:
+            R = comm.size if comm is not None else 1
+            return flat[npx:].view(R, S), flat[:npx].view(self.E, self.N, self.N)
+        return flat[S * npx:], flat[:S * npx].view(S, self.E, self.N, self.N)
+
+
     def metric(self, x, v):
         """Fisher metric pulled back through R:  R^T diag(1/(R x)) R v."""
         import torch
@@ -299,3 +335,44 @@ def measure_fp64_tflops():
     out = C.c_double()
     check(lib, lib.jubik_measure_fp64_tflops(C.byref(out), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     return out.value
+
+
+class Communicator:
+    """jubik_comm*: an NCCL communicator owned by libjubik_b200.so (one rank per process / GPU).
+
+    `Communicator.from_torch_distributed()` creates the ncclUniqueId on rank 0, distributes it through the already
+    initialised torch.distributed group (any backend -- plumbing only) and calls ncclCommInitRank on the current
+    CUDA device.  The all-reduce itself is issued by the C library, on the stream of the fused evaluation."""
+
+    def __init__(self, unique_id: bytes, rank: int, world: int):
+        self.lib = _lib.load()
+        self.handle = C.c_void_p()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        check(self.lib, self.lib.jubik_comm_create(C.byref(self.handle), buf, int(rank), int(world)))
+        self.rank, self.size = int(rank), int(world)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        lib = _lib.load()
+        buf = C.create_string_buffer(128)
+        check(lib, lib.jubik_comm_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, group=None):
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return cls(box[0], rank, world)
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.jubik_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

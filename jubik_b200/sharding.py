@@ -13,6 +13,10 @@ independent in the forward direction.  Two partitions are provided:
 
 The collective is NCCL over NVLink when the tensors are CUDA tensors and gloo in the CPU tests; the compute
 object is anything with energy_and_grad(x) -> (energy (S,), grad (S,E,N,N)) -- ResponsePlan in production.
+
+`NcclShardedLikelihood` is the production form of both partitions: the fused evaluation AND the single
+ncclAllReduce of one flat buffer are issued by libjubik_b200.so on the same stream
+(jubik_poisson_energy_and_grad_sharded); torch.distributed only distributes the ncclUniqueId.
 """
 from __future__ import annotations
 
@@ -83,3 +87,30 @@ class ModuleShardedLikelihood:
         self.dist.all_reduce(e, group=self.group)
         self.dist.all_reduce(g, group=self.group)
         return e, g
+
+
+class NcclShardedLikelihood:
+    """Sample- or module-sharded Poisson likelihood with the collective inside the C ABI.
+
+    mode "samples": `plan` is replicated, every rank passes its own (S_local,E,N,N) block of samples (equal S_local
+                    on every rank, contiguous blocks: rank r owns samples [r*S_local, (r+1)*S_local)).
+                    energy_and_grad -> (energies of all samples (world*S_local,), sample-summed gradient (E,N,N)).
+    mode "modules": `plan` holds this rank's modules (kernel[mine], exposure[mine], data[mine]); x is replicated.
+                    energy_and_grad -> (energies (S,), gradient (S,E,N,N)), both summed over ranks."""
+
+    def __init__(self, plan, mode="samples", comm=None, group=None):
+        from . import _lib
+        from .plan import Communicator
+        self.plan = plan
+        self.mode = {"samples": _lib.SHARD_SAMPLES, "modules": _lib.SHARD_MODULES}[mode]
+        self.comm = comm if comm is not None else Communicator.from_torch_distributed(group)
+        self.flat = None
+
+    def energy_and_grad(self, x, grad_local=None):
+        S = x.shape[0] if x.dim() == 4 else 1
+        n = self.plan.flat_size(self.comm, S, self.mode)
+        if self.flat is None or self.flat.numel() != n:
+            import torch
+            self.flat = torch.empty((n,), dtype=torch.float64, device=self.plan.device)
+        e, g = self.plan.energy_and_grad_sharded(x, self.comm, self.mode, flat=self.flat, grad_local=grad_local)
+        return e.reshape(-1), g

@@ -90,3 +90,13 @@ class EmuPlan:
         out = np.empty_like(x4)
         self.raw.call("jubik_poisson_metric_apply", _p(x4), _p(v4), x4.shape[0], _p(out), None)
         return out[0] if sq else out
+
+    def energy_and_grad_sharded(self, x, shard_mode, want_local=False):
+        """Single-rank path of jubik_poisson_energy_and_grad_sharded (comm = NULL: no collective)."""
+        x4 = np.ascontiguousarray(x, dtype=np.float64)
+        S = x4.shape[0]
+        n = int(self.raw.lib.jubik_sharded_flat_size(self.raw.handle, None, int(shard_mode), S))
+        flat = np.full((n,), np.nan)
+        gl = np.empty_like(x4) if want_local else None
+        self.raw.call("jubik_poisson_energy_and_grad_sharded", None, int(shard_mode), _p(x4), S, _p(gl), _p(flat), None)
+        return flat, gl

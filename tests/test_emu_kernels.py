@@ -64,3 +64,34 @@ def test_emulated_two_pass_fft_against_oracle(case):
     assert rel(gr, np.stack(go)) < TOL
     v = synth.direction((S, E, N, N), seed=9)
     assert rel(p.metric(x, v), np.stack([orc.metric_apply(R, x[s], v[s]) for s in range(S)])) < TOL
+
+
+def test_emulated_sharded_entry_point_single_rank():
+    """jubik_poisson_energy_and_grad_sharded without a communicator: layout of the flat all-reduce buffer,
+    the sample fold kernel (fixed summation order) and the module-sharded in-place layout."""
+    from jubik_b200 import _lib
+    N, n, m, T, E, S = 64, 4, 6, 2, 2, 3
+    dx = N // n
+    kern = synth.psf_cropped(T, n, E, dx, half_support=m)
+    expo = synth.exposure(T, E, N)
+    x = synth.sky(S, E, N)
+    R = orc.Response(orc.Domain((E, N, N), synth.DIST), kern, n, m, expo, 500.0, synth.PIXEL_AREA, cropped=True)
+    d = synth.counts_from(R.dense(synth.sky(1, E, N, seed=5)[0]))
+    p = EmuPlan(kern, N, n, m, exposure=expo, exposure_cut=500.0, pixel_area=synth.PIXEL_AREA, data=d,
+                max_samples=S, cropped=True, fft_length=160)
+    eo, go = zip(*[orc.energy_and_grad(R, d, x[s]) for s in range(S)])
+    eo, go = np.array(eo), np.stack(go)
+    npx = E * N * N
+    for want_local in (True, False):
+        flat, gl = p.energy_and_grad_sharded(x, _lib.SHARD_SAMPLES, want_local)
+        assert flat.shape == (npx + S,)
+        assert np.abs((flat[npx:] - eo) / eo).max() < TOL
+        assert rel(flat[:npx].reshape(E, N, N), go.sum(0)) < TOL
+        if want_local:
+            assert rel(gl, go) < TOL
+    flat, _ = p.energy_and_grad_sharded(x[:1], _lib.SHARD_SAMPLES)       # one local sample: gradient written in place
+    assert rel(flat[:npx].reshape(E, N, N), go[0]) < TOL and abs(flat[npx] - eo[0]) / abs(eo[0]) < TOL
+    flat, _ = p.energy_and_grad_sharded(x, _lib.SHARD_MODULES)
+    assert flat.shape == (S * npx + S,)
+    assert rel(flat[:S * npx].reshape(S, E, N, N), go) < TOL
+    assert np.abs((flat[S * npx:] - eo) / eo).max() < TOL

@@ -374,3 +374,91 @@ def test_error_behaviour_matches_reference(torch_cuda):
                         exposure_cut=-1.0)
     with pytest.raises(jb.JubikError):  # non-smooth P with a PSF wider than the margin
         jb.ResponsePlan(torch.ones((1, 16, 1, 64, 64), dtype=torch.float64, device="cuda"), 64, 4, 5)
+
+
+def test_sharded_entry_point_with_one_rank_nccl_communicator(torch_cuda):
+    """jubik_poisson_energy_and_grad_sharded through a real (one-rank) NCCL communicator created by the C library:
+    dlopen of libnccl, ncclCommInitRank, the fold kernel and an in-place ncclAllReduce on the plan's stream."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    case = (240, 4, 10, 2, 2, 3, False, True)
+    N, n, m, T, E, S, full, eff = case
+    dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
+    plan = jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
+                           eff_area=dev(torch, ea), pixel_area=synth.PIXEL_AREA, data=dev(torch, d), max_samples=S,
+                           cropped=cropped)
+    comm = jb.Communicator(jb.Communicator.unique_id(), 0, 1)
+    assert comm.size == 1 and comm.rank == 0
+    xd = dev(torch, x)
+    e0, g0 = plan.energy_and_grad(xd)
+    gl = torch.empty_like(xd)
+    e, g = plan.energy_and_grad_sharded(xd, comm, jb.SHARD_SAMPLES, grad_local=gl)
+    assert e.shape == (1, S) and torch.equal(e[0], e0) and torch.equal(gl, g0)
+    eo, go = zip(*[orc.energy_and_grad(R, d, x[s]) for s in range(S)])
+    assert rel(g.cpu().numpy(), np.stack(go).sum(0)) < TOL
+    assert torch.equal(g, (g0[0] + g0[1]) + g0[2])        # fixed summation order
+    e1, g1 = plan.energy_and_grad_sharded(xd[:1], None, jb.SHARD_SAMPLES)       # no communicator, gradient in place
+    assert torch.equal(e1[0], e0[:1]) and torch.equal(g1, g0[0])
+    em, gm = plan.energy_and_grad_sharded(xd, comm, jb.SHARD_MODULES)
+    assert torch.equal(em, e0) and torch.equal(gm, g0)
+    comm.close()
+    plan.close()
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    import jubik_b200 as jb
+    from jubik_b200.sharding import NcclShardedLikelihood, owned
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)       # plumbing for the ncclUniqueId only
+    case = (240, 4, 10, 2, 2, 4, False, True)
+    N, n, m, T, E, S, full, eff = case
+    dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
+
+    def mk(tsel, smax):
+        return jb.ResponsePlan(torch.as_tensor(kern[tsel]).cuda(), N, n, m, exposure=torch.as_tensor(expo[tsel]).cuda(),
+                               exposure_cut=500.0, eff_area=torch.as_tensor(ea[tsel]).cuda(),
+                               pixel_area=synth.PIXEL_AREA, data=torch.as_tensor(d[tsel]).cuda(), max_samples=smax,
+                               cropped=cropped)
+    comm = jb.Communicator.from_torch_distributed()
+    sl = S // world
+    lh = NcclShardedLikelihood(mk(list(range(T)), sl), "samples", comm=comm)
+    e_s, g_s = lh.energy_and_grad(torch.as_tensor(x[rank * sl:(rank + 1) * sl]).cuda())
+    lm = NcclShardedLikelihood(mk(owned(T, rank, world), S), "modules", comm=comm)
+    e_m, g_m = lm.energy_and_grad(torch.as_tensor(x).cuda())
+    torch.cuda.synchronize()
+    if rank == 0:
+        q.put((e_s.cpu().numpy(), g_s.cpu().numpy(), e_m.cpu().numpy(), g_m.cpu().numpy()))
+    dist.barrier()
+    comm.close()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_nccl_sharding_matches_oracle(torch_cuda):
+    """Two ranks, two GPUs: sample sharding and module sharding with the ncclAllReduce issued by the C library."""
+    import socket
+    torch = torch_cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    e_s, g_s, e_m, g_m = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    case = (240, 4, 10, 2, 2, 4, False, True)
+    dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
+    eo, go = zip(*[orc.energy_and_grad(R, d, x[s]) for s in range(4)])
+    eo, go = np.array(eo), np.stack(go)
+    assert np.abs((e_s - eo) / eo).max() < TOL and rel(g_s, go.sum(0)) < TOL
+    assert np.abs((e_m - eo) / eo).max() < TOL and rel(g_m, go) < TOL
