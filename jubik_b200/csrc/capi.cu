@@ -3,6 +3,7 @@
 #include "ops.cuh"
 #include "fft_list.h"
 #include "../../include/jubik_b200.h"
+#include <algorithm>
 #include <string>
 #include <vector>
 #include <new>
@@ -123,12 +124,16 @@ struct jubik_plan {
     int rows_pipe_out = 0, rows_pipe_adj = 0, qmax = 0;  // persistent bulk-copy-fed c2r kernels (rows_pipe.cuh)
     int fast_rows = 0;         // rows_fast.cuh kernels (two-pass length and <= JB_MAXQ row-patches per image row)
     JbTileSrc src_fwd, src_adj;  // TMA views of bufB / bufA for the pipelined column pass
+    // second spectrum workspace (one sample) of the host-buffer entry point's second compute stream (first use)
+    cd* bufA2 = nullptr;
+    cd* bufB2 = nullptr;
+    JbTileSrc src_fwd2, src_adj2;
     // per-kernel timing (jubik_poisson_profile): events recorded after every launch while enabled
     int prof_on = 0, prof_n = 0;
 #ifndef JB_EMU
     cudaEvent_t prof_ev[48] = {};
     // host-buffer entry point: copy streams and per-energy-bin events (created on first use)
-    cudaStream_t st_in = nullptr, st_out = nullptr;
+    cudaStream_t st_in = nullptr, st_out = nullptr, st_c2 = nullptr;
     cudaEvent_t *ev_in = nullptr, *ev_c = nullptr, ev_start = nullptr;
 #endif
 };
@@ -158,14 +163,14 @@ int jubik_device_count(void) { return device_count(); }
 int jubik_plan_destroy(jubik_plan* p) {
     if (!p) return JUBIK_OK;
     dev_free(p->khat); dev_free(p->tw_nk); dev_free(p->tw_kn); dev_free(p->tw1); dev_free(p->tw2); dev_free(p->wgt); dev_free(p->expo);
-    dev_free(p->data); dev_free(p->bufA); dev_free(p->bufB); dev_free(p->gbuf); dev_free(p->lbuf);
+    dev_free(p->data); dev_free(p->bufA); dev_free(p->bufB); dev_free(p->bufA2); dev_free(p->bufB2); dev_free(p->gbuf); dev_free(p->lbuf);
     dev_free(p->counter); dev_free(p->xexp); dev_free(p->partial); dev_free(p->gtab_fwd); dev_free(p->gtab_adj); dev_free(p->xdev); dev_free(p->gdev); dev_free(p->edev);
 #ifndef JB_EMU
     if (p->st_in) {
         for (int e = 0; e < p->S_max * p->g.E; ++e) { cudaEventDestroy(p->ev_in[e]); cudaEventDestroy(p->ev_c[e]); }
         delete[] p->ev_in; delete[] p->ev_c;
         cudaEventDestroy(p->ev_start);
-        cudaStreamDestroy(p->st_in); cudaStreamDestroy(p->st_out);
+        cudaStreamDestroy(p->st_in); cudaStreamDestroy(p->st_out); if (p->st_c2) cudaStreamDestroy(p->st_c2);
     }
     for (int i = 0; i < 48; ++i) if (p->prof_ev[i]) cudaEventDestroy(p->prof_ev[i]);
 #endif
@@ -885,6 +890,7 @@ int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, d
         if (!p->st_in) {
             JB_CK(cudaStreamCreateWithFlags(&p->st_in, cudaStreamNonBlocking));
             JB_CK(cudaStreamCreateWithFlags(&p->st_out, cudaStreamNonBlocking));
+            JB_CK(cudaStreamCreateWithFlags(&p->st_c2, cudaStreamNonBlocking));
             p->ev_in = new cudaEvent_t[nev]; p->ev_c = new cudaEvent_t[nev];
             for (int e = 0; e < nev; ++e) {
                 JB_CK(cudaEventCreateWithFlags(&p->ev_in[e], cudaEventDisableTiming));
@@ -903,22 +909,54 @@ int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, d
                 JB_CK(cudaMemcpyAsync(p->xdev + (size_t)c * npx, xh + (size_t)c * npx, plane_b, cudaMemcpyHostToDevice, p->st_in));
                 JB_CK(cudaEventRecord(p->ev_in[c], p->st_in));
             }
+            // Planes alternate between two compute streams: a one-plane launch leaves the persistent kernels with a
+            // ragged last wave (1024 rows on 888 resident CTAs), which the other stream's plane fills.  A plane uses
+            // workspace slab e, so it also waits for the previous plane with the same e (other stream when E is odd).
+            bool two = !getenv("JUBIK_B200_HOST_ONE_STREAM") && S * g.E > 1 && p->use_pipe;
+            if (two && !p->bufA2) {
+                // the two streams' planes are in different phases at the same time, and the forward / adjoint layouts of
+                // one buffer alias across energy bins: the second stream gets its own pair of spectrum buffers
+                const size_t TE1 = (size_t)g.T * g.E, nn2 = (size_t)g.n * g.n;
+                const int brB = std::min(std::min(g.w, 64), g.N), brA = std::min(std::min(g.P, 64), g.N);
+                std::string err;
+                if (alloc(p, (void**)&p->bufA2, TE1 * nn2 * (size_t)g.P * g.PH * sizeof(cd), "second spectrum workspace A") ||
+                    alloc(p, (void**)&p->bufB2, TE1 * nn2 * (size_t)g.w * g.PH * sizeof(cd), "second spectrum workspace B"))
+                    return JUBIK_ERR_ALLOC;
+                if (make_tile_src(&p->src_fwd2, p->bufB2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brB, &err) ||
+                    make_tile_src(&p->src_adj2, p->bufA2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brA, &err))
+                    return fail(JUBIK_ERR_CUDA, err);
+            }
+            if (two) JB_CK(cudaStreamWaitEvent(p->st_c2, p->ev_start, 0));
+            // kernel arguments are captured at launch, so the second stream's launches simply see the plan with its
+            // workspace pointers exchanged while they are enqueued
+            auto swap_ws = [&]() {
+                std::swap(p->bufA, p->bufA2); std::swap(p->bufB, p->bufB2);
+                std::swap(p->src_fwd, p->src_fwd2); std::swap(p->src_adj, p->src_adj2);
+            };
+            int last_c2 = -1;
             for (int si = 0; si < S; ++si)
                 for (int e = 0; e < g.E; ++e) {
                     const int c = si * g.E + e;
+                    jb_stream_t cs = (two && (c & 1)) ? (jb_stream_t)p->st_c2 : st;
+                    if (cs != st) last_c2 = c;
                     JbGeom ge = g;
                     ge.e0 = e; ge.Es = 1;
-                    JB_CK(cudaStreamWaitEvent(st, p->ev_in[c], 0));
+                    JB_CK(cudaStreamWaitEvent(cs, p->ev_in[c], 0));
+                    if (two && c >= g.E) JB_CK(cudaStreamWaitEvent(cs, p->ev_c[c - g.E], 0));
                     JbEpi ep; memset(&ep, 0, sizeof(ep));
                     ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data;
                     ep.partial = p->partial + (size_t)si * g.T * g.E * p->nblk_out;
                     // the chunk runs as "sample 0" of a one-sample batch on this sample's slices of x / grad / partials
-                    if (int rc = run_forward_g(p, ge, p->xdev + (size_t)si * g.E * npx, 1, ep, st)) return rc;
-                    if (int rc = run_adjoint_g(p, ge, p->gbuf, nullptr, 1, p->gdev + (size_t)si * g.E * npx, st)) return rc;
-                    JB_CK(cudaEventRecord(p->ev_c[c], st));
+                    if (cs != st) swap_ws();
+                    int rc = run_forward_g(p, ge, p->xdev + (size_t)si * g.E * npx, 1, ep, cs);
+                    if (!rc) rc = run_adjoint_g(p, ge, p->gbuf, nullptr, 1, p->gdev + (size_t)si * g.E * npx, cs);
+                    if (cs != st) swap_ws();
+                    if (rc) return rc;
+                    JB_CK(cudaEventRecord(p->ev_c[c], cs));
                     JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_c[c], 0));
                     JB_CK(cudaMemcpyAsync(gh + (size_t)c * npx, p->gdev + (size_t)c * npx, plane_b, cudaMemcpyDeviceToHost, p->st_out));
                 }
+            if (last_c2 >= 0) JB_CK(cudaStreamWaitEvent(st, p->ev_c[last_c2], 0));   // join before the energy reduction
             JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
                                      (const double*)p->partial, g.T * g.E * p->nblk_out, p->edev));
         } else {
