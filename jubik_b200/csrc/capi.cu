@@ -4,6 +4,7 @@
 #include "fft_list.h"
 #include "../../include/jubik_b200.h"
 #include <algorithm>
+#include <functional>
 #include <string>
 #include <vector>
 #include <new>
@@ -116,6 +117,8 @@ struct jubik_plan {
     int rows6 = 0;                         // warp-private r2c kernels (rows6.cuh)
     int sweep = 0;                         // column pass accumulates over the row-patches (cols3.cuh SWEEP + rows5 presum)
     int chunk_e = 0;                       // fused energy+gradient runs one energy bin at a time (L2 residency)
+    int cols_pp = 0;                       // column pass as an anti-phase pair of groups per SM (cols3_pp.cuh)
+    int dev_planes = 0;                    // ... one (sample, bin) plane at a time on two alternating streams
     int rows5 = 0;                         // warp-private c2r kernels with the fused Poisson epilogue (rows5.cuh)
     int* gtab_fwd = nullptr;               // rows5 overlap-add gather tables [gq][N]
     int* gtab_adj = nullptr;
@@ -403,6 +406,8 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
         }
     }
     p->chunk_e = getenv("JUBIK_B200_CHUNK_E") ? 1 : 0;
+    p->dev_planes = getenv("JUBIK_B200_DEV_PLANES") ? 1 : 0;
+    p->cols_pp = (!p->sweep && getenv("JUBIK_B200_COLS_PP")) ? 1 : 0;
     // warp-private r2c kernels: parity-tested, but measured slower than the two-pass kernels of rows_fast.cuh on B200
     // (forward 69 vs 36 us -- the two-pass kernel skips the zero padding --, adjoint 58 vs 57 us): opt-in
     p->rows6 = (p->rows5 && getenv("JUBIK_B200_ROWS_R2C_V6") && o->rows6_smem(g) <= (size_t)227 * 1024 - 1024) ? 1 : 0;
@@ -516,7 +521,7 @@ static int run_forward_g(jubik_plan* p, const JbGeom& g, const double* x, int S,
         JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.Es, p->rpc_in, p->thr_rows, p->fast_rows, st));
     }
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, false, p->sweep, p->src_fwd, p->bufA, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, false, p->cols_pp ? 2 : p->sweep, p->src_fwd, p->bufA, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
@@ -545,7 +550,7 @@ static int run_adjoint_g(jubik_plan* p, const JbGeom& g, const double* gin, cons
         JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.Es, p->rpc_in, p->thr_rows, p->fast_rows, st));
     }
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, true, p->sweep, p->src_adj, p->bufB, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, true, p->cols_pp ? 2 : p->sweep, p->src_adj, p->bufB, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
@@ -590,12 +595,99 @@ int jubik_response_apply_T(jubik_plan* p, const double* gin, int S, double* out,
     return run_adjoint(p, gin, p->expo, S, out, (jb_stream_t)stream_);
 }
 
+#ifndef JB_EMU
+// streams / events of the plane-pipelined call forms (first use)
+static int ensure_plane_streams(jubik_plan* p) {
+    if (p->st_in) return 0;
+    const int nev = p->S_max * p->g.E;
+    JB_CK(cudaStreamCreateWithFlags(&p->st_in, cudaStreamNonBlocking));
+    JB_CK(cudaStreamCreateWithFlags(&p->st_out, cudaStreamNonBlocking));
+    JB_CK(cudaStreamCreateWithFlags(&p->st_c2, cudaStreamNonBlocking));
+    p->ev_in = new cudaEvent_t[nev]; p->ev_c = new cudaEvent_t[nev];
+    for (int e = 0; e < nev; ++e) {
+        JB_CK(cudaEventCreateWithFlags(&p->ev_in[e], cudaEventDisableTiming));
+        JB_CK(cudaEventCreateWithFlags(&p->ev_c[e], cudaEventDisableTiming));
+    }
+    JB_CK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+    return 0;
+}
+// The two compute streams' planes are in different phases at the same time, and the forward / adjoint layouts of one
+// spectrum buffer alias across energy bins: the second stream gets its own pair of buffers (one sample's worth).
+static int ensure_second_workspace(jubik_plan* p) {
+    if (p->bufA2) return 0;
+    const JbGeom& g = p->g;
+    const size_t TE1 = (size_t)g.T * g.E, nn2 = (size_t)g.n * g.n;
+    const int brB = std::min(std::min(g.w, 64), g.N), brA = std::min(std::min(g.P, 64), g.N);
+    std::string err;
+    if (alloc(p, (void**)&p->bufA2, TE1 * nn2 * (size_t)g.P * g.PH * sizeof(cd), "second spectrum workspace A") ||
+        alloc(p, (void**)&p->bufB2, TE1 * nn2 * (size_t)g.w * g.PH * sizeof(cd), "second spectrum workspace B"))
+        return JUBIK_ERR_ALLOC;
+    if (make_tile_src(&p->src_fwd2, p->bufB2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brB, &err) ||
+        make_tile_src(&p->src_adj2, p->bufA2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brA, &err))
+        return fail(JUBIK_ERR_CUDA, err);
+    return 0;
+}
+// kernel arguments are captured at launch, so the second stream's launches simply see the plan with its workspace
+// pointers exchanged while they are enqueued
+static void swap_workspace(jubik_plan* p) {
+    std::swap(p->bufA, p->bufA2); std::swap(p->bufB, p->bufB2);
+    std::swap(p->src_fwd, p->src_fwd2); std::swap(p->src_adj, p->src_adj2);
+}
+// Fused energy + gradient as (sample, energy bin) planes alternating between the caller's stream and a second one
+// (device-resident form of the host entry point's pipeline).  wait_in: per-plane events to wait for (H2D), or null;
+// after_plane(c, stream): hook after a plane's kernels were enqueued (the host path issues the D2H there).
+static int run_planes_two_streams(jubik_plan* p, const double* x, int S, double* grad, bool two, bool wait_in,
+                                  jb_stream_t st, const std::function<int(int)>& after_plane) {
+    const JbGeom& g = p->g;
+    const size_t npx = (size_t)g.N * g.N;
+    if (two) JB_CK(cudaStreamWaitEvent(p->st_c2, p->ev_start, 0));
+    int last_c2 = -1;
+    for (int si = 0; si < S; ++si)
+        for (int e = 0; e < g.E; ++e) {
+            const int c = si * g.E + e;
+            jb_stream_t cs = (two && (c & 1)) ? (jb_stream_t)p->st_c2 : st;
+            if (cs != st) last_c2 = c;
+            JbGeom ge = g;
+            ge.e0 = e; ge.Es = 1;
+            if (wait_in) JB_CK(cudaStreamWaitEvent(cs, p->ev_in[c], 0));
+            // a plane uses workspace slab e: wait for the previous plane with the same e (other stream when E is odd)
+            if (two && c >= g.E) JB_CK(cudaStreamWaitEvent(cs, p->ev_c[c - g.E], 0));
+            JbEpi ep; memset(&ep, 0, sizeof(ep));
+            ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data;
+            ep.partial = p->partial + (size_t)si * g.T * g.E * p->nblk_out;
+            // the chunk runs as "sample 0" of a one-sample batch on this sample's slices of x / grad / partials
+            if (cs != st) swap_workspace(p);
+            int rc = run_forward_g(p, ge, x + (size_t)si * g.E * npx, 1, ep, cs);
+            if (!rc) rc = run_adjoint_g(p, ge, p->gbuf, nullptr, 1, grad + (size_t)si * g.E * npx, cs);
+            if (cs != st) swap_workspace(p);
+            if (rc) return rc;
+            JB_CK(cudaEventRecord(p->ev_c[c], cs));
+            if (int rc2 = after_plane(c)) return rc2;
+        }
+    if (last_c2 >= 0) JB_CK(cudaStreamWaitEvent(st, p->ev_c[last_c2], 0));   // join before the energy reduction
+    return 0;
+}
+#endif
+
 int jubik_poisson_energy_and_grad(jubik_plan* p, const double* x, int S, double* energy, double* grad, void* stream_) {
     jb_stream_t st = (jb_stream_t)stream_;
     if (int rc = check_call(p, x, energy, S)) return rc;
     if (!p->has_expo || !p->has_data) return fail(JUBIK_ERR_ARG, "plan needs exposures and data for the Poisson energy");
     const JbGeom& g = p->g;
     JbEpi ep; memset(&ep, 0, sizeof(ep));
+#ifndef JB_EMU
+    if (p->dev_planes && grad && !p->split_epi && p->rows5 && p->use_pipe && !p->counter && S * g.E > 1 && !p->prof_on) {
+        // JUBIK_B200_DEV_PLANES=1 (experiment): one (sample, energy bin) plane at a time on two alternating streams,
+        // so that a plane's spectra are still L2-resident when its next kernel reads them
+        if (int rc = ensure_plane_streams(p)) return rc;
+        if (int rc = ensure_second_workspace(p)) return rc;
+        JB_CK(cudaEventRecord(p->ev_start, st));
+        if (int rc = run_planes_two_streams(p, x, S, grad, true, false, st, [](int) { return 0; })) return rc;
+        JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
+                                 (const double*)p->partial, g.T * g.E * p->nblk_out, energy));
+        return JUBIK_OK;
+    }
+#endif
     if (p->chunk_e && !p->split_epi && grad && g.E > 1) {
         // one energy bin at a time, forward then adjoint: the bin's spectra (column-pass output -> row pass) and its
         // cotangent plane are still L2-resident when the next kernel reads them
@@ -886,18 +978,7 @@ int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, d
     // of bin e+1 and the D2H copy of the gradient of bin e-1 overlap the kernels of bin e (three streams).
     const bool chunked = gh && (g.E > 1 || (S > 1 && !p->split_epi)) && (p->split_epi || p->rows5) && p->has_expo && p->has_data && !getenv("JUBIK_B200_HOST_SERIAL");
     if (chunked) {
-        const int nev = p->S_max * g.E;
-        if (!p->st_in) {
-            JB_CK(cudaStreamCreateWithFlags(&p->st_in, cudaStreamNonBlocking));
-            JB_CK(cudaStreamCreateWithFlags(&p->st_out, cudaStreamNonBlocking));
-            JB_CK(cudaStreamCreateWithFlags(&p->st_c2, cudaStreamNonBlocking));
-            p->ev_in = new cudaEvent_t[nev]; p->ev_c = new cudaEvent_t[nev];
-            for (int e = 0; e < nev; ++e) {
-                JB_CK(cudaEventCreateWithFlags(&p->ev_in[e], cudaEventDisableTiming));
-                JB_CK(cudaEventCreateWithFlags(&p->ev_c[e], cudaEventDisableTiming));
-            }
-            JB_CK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
-        }
+        if (int rc = ensure_plane_streams(p)) return rc;
         // the copy streams start after everything already queued on the caller's stream
         JB_CK(cudaEventRecord(p->ev_start, st));
         JB_CK(cudaStreamWaitEvent(p->st_in, p->ev_start, 0));
@@ -910,53 +991,15 @@ int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, d
                 JB_CK(cudaEventRecord(p->ev_in[c], p->st_in));
             }
             // Planes alternate between two compute streams: a one-plane launch leaves the persistent kernels with a
-            // ragged last wave (1024 rows on 888 resident CTAs), which the other stream's plane fills.  A plane uses
-            // workspace slab e, so it also waits for the previous plane with the same e (other stream when E is odd).
-            bool two = !getenv("JUBIK_B200_HOST_ONE_STREAM") && S * g.E > 1 && p->use_pipe;
-            if (two && !p->bufA2) {
-                // the two streams' planes are in different phases at the same time, and the forward / adjoint layouts of
-                // one buffer alias across energy bins: the second stream gets its own pair of spectrum buffers
-                const size_t TE1 = (size_t)g.T * g.E, nn2 = (size_t)g.n * g.n;
-                const int brB = std::min(std::min(g.w, 64), g.N), brA = std::min(std::min(g.P, 64), g.N);
-                std::string err;
-                if (alloc(p, (void**)&p->bufA2, TE1 * nn2 * (size_t)g.P * g.PH * sizeof(cd), "second spectrum workspace A") ||
-                    alloc(p, (void**)&p->bufB2, TE1 * nn2 * (size_t)g.w * g.PH * sizeof(cd), "second spectrum workspace B"))
-                    return JUBIK_ERR_ALLOC;
-                if (make_tile_src(&p->src_fwd2, p->bufB2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brB, &err) ||
-                    make_tile_src(&p->src_adj2, p->bufA2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brA, &err))
-                    return fail(JUBIK_ERR_CUDA, err);
-            }
-            if (two) JB_CK(cudaStreamWaitEvent(p->st_c2, p->ev_start, 0));
-            // kernel arguments are captured at launch, so the second stream's launches simply see the plan with its
-            // workspace pointers exchanged while they are enqueued
-            auto swap_ws = [&]() {
-                std::swap(p->bufA, p->bufA2); std::swap(p->bufB, p->bufB2);
-                std::swap(p->src_fwd, p->src_fwd2); std::swap(p->src_adj, p->src_adj2);
+            // ragged last wave (1024 rows on 888 resident CTAs), which the other stream's plane fills.
+            const bool two = !getenv("JUBIK_B200_HOST_ONE_STREAM") && S * g.E > 1 && p->use_pipe;
+            if (two) { if (int rc = ensure_second_workspace(p)) return rc; }
+            auto d2h_plane = [&](int c) -> int {
+                JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_c[c], 0));
+                JB_CK(cudaMemcpyAsync(gh + (size_t)c * npx, p->gdev + (size_t)c * npx, plane_b, cudaMemcpyDeviceToHost, p->st_out));
+                return 0;
             };
-            int last_c2 = -1;
-            for (int si = 0; si < S; ++si)
-                for (int e = 0; e < g.E; ++e) {
-                    const int c = si * g.E + e;
-                    jb_stream_t cs = (two && (c & 1)) ? (jb_stream_t)p->st_c2 : st;
-                    if (cs != st) last_c2 = c;
-                    JbGeom ge = g;
-                    ge.e0 = e; ge.Es = 1;
-                    JB_CK(cudaStreamWaitEvent(cs, p->ev_in[c], 0));
-                    if (two && c >= g.E) JB_CK(cudaStreamWaitEvent(cs, p->ev_c[c - g.E], 0));
-                    JbEpi ep; memset(&ep, 0, sizeof(ep));
-                    ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data;
-                    ep.partial = p->partial + (size_t)si * g.T * g.E * p->nblk_out;
-                    // the chunk runs as "sample 0" of a one-sample batch on this sample's slices of x / grad / partials
-                    if (cs != st) swap_ws();
-                    int rc = run_forward_g(p, ge, p->xdev + (size_t)si * g.E * npx, 1, ep, cs);
-                    if (!rc) rc = run_adjoint_g(p, ge, p->gbuf, nullptr, 1, p->gdev + (size_t)si * g.E * npx, cs);
-                    if (cs != st) swap_ws();
-                    if (rc) return rc;
-                    JB_CK(cudaEventRecord(p->ev_c[c], cs));
-                    JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_c[c], 0));
-                    JB_CK(cudaMemcpyAsync(gh + (size_t)c * npx, p->gdev + (size_t)c * npx, plane_b, cudaMemcpyDeviceToHost, p->st_out));
-                }
-            if (last_c2 >= 0) JB_CK(cudaStreamWaitEvent(st, p->ev_c[last_c2], 0));   // join before the energy reduction
+            if (int rc = run_planes_two_streams(p, p->xdev, S, p->gdev, two, true, st, d2h_plane)) return rc;
             JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
                                      (const double*)p->partial, g.T * g.E * p->nblk_out, p->edev));
         } else {

@@ -6,6 +6,7 @@
 #include "rows_fast.cuh"
 #include "cols_pipe.cuh"
 #include "cols3.cuh"
+#include "cols3_pp.cuh"
 #include "rows_pipe.cuh"
 #include "rows3.cuh"
 #include "rows5.cuh"
@@ -84,6 +85,20 @@ struct JbOpsImpl {
                                           khat, twa, twb, wgt, planes);
                 return jb_launch(k_cols3_pipe<F3, CB, false, false, true>, grid3, block, smem3, st, src, g, out, khat,
                                  twa, twb, wgt, planes);
+            }
+#endif
+#ifndef JB_EMU
+            if (sweep == 2) {   // anti-phase pair of groups in one CTA per SM (cols3_pp.cuh); falls through for wide tiles
+                if constexpr (Cols3<F3, CB>::CPS == 2) {
+                    const size_t smem2 = 8 * (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd) + 64 +
+                                         4 * sizeof(JbColInfo) + (size_t)g.w * sizeof(double) + 32;
+                    const dim3 grid2(ctas), block2(2 * Cols3<F3, CB>::THREADS);
+                    if (adj) return jb_launch(k_cols3_pp<F3, CB, true>, grid2, block2, smem2, st, src, g, out, khat, twa, twb,
+                                              wgt, planes);
+                    return jb_launch(k_cols3_pp<F3, CB, false>, grid2, block2, smem2, st, src, g, out, khat, twa, twb, wgt,
+                                     planes);
+                }
+                sweep = 0;
             }
 #endif
             if (sweep) {

@@ -301,7 +301,7 @@ def test_full_size_geovi_batch_c5_per_gpu_share(torch_cuda):
 
 
 @pytest.mark.parametrize("flag", ["JUBIK_B200_SWEEP", "JUBIK_B200_ROWS_R2C_V6", "JUBIK_B200_FUSED_REDUCE",
-                                  "JUBIK_B200_CHUNK_E"])
+                                  "JUBIK_B200_CHUNK_E", "JUBIK_B200_DEV_PLANES", "JUBIK_B200_COLS_PP"])
 def test_optin_kernel_variants_match_oracle(torch_cuda, monkeypatch, flag):
     """The measured-but-not-default kernel variants stay parity-green."""
     _variant_parity(torch_cuda, monkeypatch, flag)
@@ -325,6 +325,31 @@ def _variant_parity(torch_cuda, monkeypatch, flag):
     eo, go = orc.energy_and_grad(R, d, x[0])
     assert abs(float(e[0]) - eo) / abs(eo) < TOL and rel(gr[0].cpu().numpy(), go) < TOL
     plan.close()
+
+
+def test_plane_pipelined_device_path_is_bitwise_equal_to_batched(torch_cuda, monkeypatch):
+    """JUBIK_B200_DEV_PLANES: (sample, bin) planes alternating between two streams with two workspaces give exactly
+    the batched call's numbers (same kernels, same summation order), call after call."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    case = (512, 4, 64, 2, 3, 2, False, True)
+    N, n, m, T, E, S, full, eff = case
+    dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
+
+    def mk():
+        return jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
+                               eff_area=dev(torch, ea), pixel_area=synth.PIXEL_AREA, data=dev(torch, d), max_samples=S,
+                               cropped=cropped)
+    xd = dev(torch, x)
+    p0 = mk()
+    e0, g0 = p0.energy_and_grad(xd)
+    monkeypatch.setenv("JUBIK_B200_DEV_PLANES", "1")
+    p1 = mk()
+    for _ in range(3):
+        e1, g1 = p1.energy_and_grad(xd)
+        assert torch.equal(e0, e1) and torch.equal(g0, g1)
+    p0.close()
+    p1.close()
 
 
 def test_standalone_slice_patches_and_convolve_match_reference_golden(torch_cuda, golden_dir, capsys):
