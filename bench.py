@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- fused forward + VJP of response + Poisson log-likelihood, fp64, in sky-pixels/s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C1|C3s|C3|C4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C1|C3s|C3|C4|C5g]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU)
 
 Workload at N=1: BASELINE.json configs[1] ("C2", Chandra-like): 1024x1024 sky, 3 energy bins, 8x8
@@ -46,6 +46,8 @@ WORKLOADS = {
     # the other single-GPU configurations of BASELINE.json (parity-test cases; benched on request for DESIGN.md section 4)
     "C3": (1024, 10, 64, 7, 3, "C3 eROSITA-like: 7 telescope modules x 3 energy bins, 1024x1024 sky, 10x10 PSF patches, "
                                "margin 64 (P=332 -> L=336), per-module exposure/readout masks"),
+    "C5g": (2048, 10, 128, 7, 3, "C5 geoVI batch, one GPU's share (2 of 16 samples with --samples-per-gpu 2): 7 telescope modules "
+                                 "x 3 energy bins at 2048x2048, 10x10 PSF patches, margin 128 (P=664 -> L=672)"),
     "C4": (4096, 16, 64, 1, 1, "C4 JWST-like: 4096x4096 sky, 16x16 PSF patches with 128-px kernels (margin 64, P=640), "
                                "single filter"),
 }
