@@ -125,9 +125,47 @@ struct JbOpsImpl {
         size_t B = (size_t)rpc * g.n;
         return jb_al16(B * FP::LS * sizeof(cd)) + 16;
     }
+    // persistent prefetching r2c kernel (k_rows_in_pf): used when it fits at least two CTAs per SM; JUBIK_B200_ROWS_IN_V2=1
+    // keeps the one-row-per-CTA kernels
+    template <bool ADJ>
+    static bool rows_in_pf(const JbGeom& g, const double* in, const double* wgt, const cd* tw_nk, cd* out, int planes,
+                           int threads, jb_stream_t st, cudaError_t* err) {
+        if constexpr (FP::R2 > 1) {
+            const bool off = getenv("JUBIK_B200_ROWS_IN_V2") != nullptr;
+            const size_t smem = jb_al16((size_t)g.n * FP::LS * sizeof(cd)) + 2 * (size_t)g.N * sizeof(double) +
+                                (ADJ ? 0 : (size_t)g.w * sizeof(double));
+            if (off || (g.N & 1) || smem > 110 * 1024) return false;
+            int per_sm = 1, n_sm = 148;
+#ifndef JB_EMU
+            static int cache_thr = -1, cache_cps = 1, cache_sm = 148;
+            static size_t cache_smem = 0;
+            if (cache_thr != threads || cache_smem != smem) {
+                int dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&cache_sm, cudaDevAttrMultiProcessorCount, dev);
+                if (smem > 48 * 1024)
+                    cudaFuncSetAttribute(k_rows_in_pf<FP, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cache_cps, k_rows_in_pf<FP, ADJ>, threads, smem) != cudaSuccess ||
+                    cache_cps < 1) { cudaGetLastError(); cache_cps = 1; }
+                cache_thr = threads; cache_smem = smem;
+            }
+            per_sm = cache_cps; n_sm = cache_sm;
+#endif
+            long ctas = (long)per_sm * n_sm;
+            const long total = (long)planes * g.N;
+            if (ctas > total) ctas = total;
+            *err = jb_launch(k_rows_in_pf<FP, ADJ>, dim3((unsigned)ctas), dim3(threads), smem, st, g, in, wgt, tw_nk, out, planes);
+            return true;
+        } else {
+            (void)g; (void)in; (void)wgt; (void)tw_nk; (void)out; (void)planes; (void)threads; (void)st; (void)err;
+            return false;
+        }
+    }
     static cudaError_t rows_fwd(const JbGeom& g, const double* x, const double* wgt, const cd* tw_nk, cd* bufB,
                                 int planes, int rpc, int threads, int fast, jb_stream_t st) {
         dim3 grid(jb_cdiv(g.N, rpc), planes);
+        cudaError_t e2;
+        if (fast && rows_in_pf<false>(g, x, wgt, tw_nk, bufB, planes, threads, st, &e2)) return e2;
         if constexpr (FP::R2 > 1) {
             if (fast) return jb_launch(k_rows_fwd2<FP>, grid, dim3(threads), smem_rows_in(g, rpc, 1), st, g, x, wgt,
                                        tw_nk, bufB, rpc);
@@ -137,6 +175,8 @@ struct JbOpsImpl {
     static cudaError_t rows_adj_in(const JbGeom& g, const double* gin, const double* expo, const cd* tw_nk,
                                    cd* bufA, int planes, int rpc, int threads, int fast, jb_stream_t st) {
         dim3 grid(jb_cdiv(g.N, rpc), planes);
+        cudaError_t e2;
+        if (fast && !expo && rows_in_pf<true>(g, gin, nullptr, tw_nk, bufA, planes, threads, st, &e2)) return e2;
         if constexpr (FP::R2 > 1) {
             if (fast) return jb_launch(k_rows_adj_in2<FP>, grid, dim3(threads), smem_rows_in(g, rpc, 1), st, g, gin,
                                        expo, tw_nk, bufA, rpc);

@@ -197,6 +197,95 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_adj_in2(JbGeom g, const double* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Persistent r2c row kernel with the NEXT image row prefetched into shared memory (cp.async, no registers held).
+// ncu of k_rows_fwd2 / k_rows_adj_in2 (r1o): 58 % of the stall samples sit on the first use of the 24 strided global
+// loads of pass 1 and 10 % on EXIT (stores draining) -- four one-row CTAs per SM cannot hide a DRAM round trip.  Here a
+// CTA walks the (plane, image row) list with a stride of gridDim.x; while it transforms row k the 8 KB of row k+1 land
+// in the other half of a two-slot ring, and pass 1 reads its window elements from shared memory.
+//   ADJ = false: sky rows, window weights, w-wide windows at offs[i]-hp            -> rowsF (S*E, n, N, PH)
+//   ADJ = true : cotangent rows (exposure already folded in), P-wide windows       -> rowsA (STE, n, N, PH)
+// dyn smem = n*LS*16 (exchange) + 2*N*8 (row ring) + w*8 (window weights, forward only).
+#ifndef JB_EMU
+JB_D void jb_cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+JB_D void jb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+JB_D void jb_cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+#else
+inline void jb_cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+inline void jb_cp_async_commit() {}
+inline void jb_cp_async_wait1() {}
+#endif
+
+template <class FP, bool ADJ>
+JB_GLOBAL void JB_LB(256, 2) k_rows_in_pf(JbGeom g, const double* __restrict__ in, const double* __restrict__ wgt,
+                                          const cd* __restrict__ tw_nk, cd* __restrict__ rows, int planes) {
+    constexpr int R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
+    JB_SMEM(unsigned char, smraw);
+    const int n = g.n, N = g.N, m = g.m, w = g.w, hp = g.hp, PH = g.PH, P = g.P;
+    cd* sm = reinterpret_cast<cd*>(smraw);
+    double* ring = reinterpret_cast<double*>(smraw + jb_align16((size_t)n * LS * sizeof(cd)));
+    double* wsm = ring + 2 * (size_t)N;      // window weights (forward): read once per CTA, ordered by the first barrier
+    if (!ADJ) for (int q = jb_tid(); q < w; q += jb_nthr()) wsm[q] = wgt[q];
+    const int total = planes * N;
+    auto plane_of = [&](int lp) -> int {   // launched plane -> plane index of the input / output buffers
+        int a, b2, c2;
+        if (ADJ) { jb_map_ste(g, lp, a, b2, c2); return a; }
+        return jb_map_se(g, lp, a, b2);
+    };
+    auto prefetch = [&](int idx, int slot) {
+        const int lp = idx / N, r = idx - lp * N;
+        const double* src = in + ((size_t)plane_of(lp) * N + r) * N;
+        double* dst = ring + (size_t)slot * N;
+        for (int c = 2 * jb_tid(); c < N; c += 2 * jb_nthr()) jb_cp_async16(dst + c, src + c);
+    };
+    int idx = blockIdx.x;
+    if (idx < total) prefetch(idx, 0);
+    jb_cp_async_commit();
+    for (int k = 0; idx < total; idx += gridDim.x, ++k) {
+        const int nxt = idx + gridDim.x;
+        if (nxt < total) prefetch(nxt, (k + 1) & 1);
+        jb_cp_async_commit();
+        jb_cp_async_wait1();          // this thread's copies of the current row have landed ...
+        JB_SYNC();                    // ... and so have everybody else's
+        const double* row = ring + (size_t)(k & 1) * N;
+        const int lp = idx / N, r = idx - lp * N;
+        const int pl = plane_of(lp);
+        for (int it = jb_tid(); it < n * R2; it += jb_nthr()) {
+            const int i = it / R2, n2 = it - i * R2;
+            double xv[R1];
+            if (!ADJ) {
+                // element p = R2*n1 + n2 of the zero-padded window row: q = p - m in [0,w), column c = offs[i]-hp+q
+                const int q0 = n2 - m, c0 = g.offs[i] - hp + q0;
+                static_for<0, R1>([&](auto nn) {
+                    constexpr int n1 = nn;
+                    const int q = q0 + R2 * n1, c = c0 + R2 * n1;
+                    const bool ok = q >= 0 && q < w && c >= 0 && c < N;
+                    xv[n1] = ok ? row[c] * wsm[q] : 0.0;
+                });
+            } else {
+                const int c0 = g.offs[i] - hp - m + n2;
+                static_for<0, R1>([&](auto nn) {
+                    constexpr int n1 = nn;
+                    const int p = n2 + R2 * n1, c = c0 + R2 * n1;
+                    const bool ok = p < P && c >= 0 && c < N;
+                    xv[n1] = ok ? row[c] : 0.0;
+                });
+            }
+            jb_r2c_pass1<FP>(xv, sm + (size_t)i * LS + n2, jb_ldg(tw_nk + R2 + n2), jb_ldg(tw_nk + 2 * R2 + n2));
+        }
+        JB_SYNC();
+        for (int it = jb_tid(); it < n * H1; it += jb_nthr()) {
+            const int i = it / H1, k1 = it - i * H1;
+            cd u[R2];
+            jb_r2c_pass2<FP>(sm + (size_t)i * LS + k1 * R2P, u);
+            jb_store_half_row<FP>(rows + (((size_t)pl * n + i) * N + r) * PH, u, k1);
+        }
+        JB_SYNC();   // exchange buffer and ring slot k&1 are free for the next round
+    }
+}
+
 // load the half-spectrum element (k1, K2) as the weighted sum over the row-patch table entries
 template <class FP, int K2, bool WEIGHTED>
 JB_D cd jb_sum_spec(const cd* const (&pd)[JB_MAXQ], const cd* const (&pm)[JB_MAXQ], const double (&wr)[JB_MAXQ],

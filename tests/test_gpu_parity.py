@@ -301,7 +301,7 @@ def test_full_size_geovi_batch_c5_per_gpu_share(torch_cuda):
 
 
 @pytest.mark.parametrize("flag", ["JUBIK_B200_SWEEP", "JUBIK_B200_ROWS_R2C_V6", "JUBIK_B200_FUSED_REDUCE",
-                                  "JUBIK_B200_CHUNK_E", "JUBIK_B200_DEV_PLANES", "JUBIK_B200_COLS_PP"])
+                                  "JUBIK_B200_CHUNK_E", "JUBIK_B200_DEV_PLANES", "JUBIK_B200_COLS_PP", "JUBIK_B200_ROWS_IN_V2"])
 def test_optin_kernel_variants_match_oracle(torch_cuda, monkeypatch, flag):
     """The measured-but-not-default kernel variants stay parity-green."""
     _variant_parity(torch_cuda, monkeypatch, flag)
