@@ -130,6 +130,7 @@ struct jubik_plan {
     // second spectrum workspace (one sample) of the host-buffer entry point's second compute stream (first use)
     cd* bufA2 = nullptr;
     cd* bufB2 = nullptr;
+    double* gbuf2 = nullptr;
     JbTileSrc src_fwd2, src_adj2;
     // per-kernel timing (jubik_poisson_profile): events recorded after every launch while enabled
     int prof_on = 0, prof_n = 0;
@@ -166,7 +167,7 @@ int jubik_device_count(void) { return device_count(); }
 int jubik_plan_destroy(jubik_plan* p) {
     if (!p) return JUBIK_OK;
     dev_free(p->khat); dev_free(p->tw_nk); dev_free(p->tw_kn); dev_free(p->tw1); dev_free(p->tw2); dev_free(p->wgt); dev_free(p->expo);
-    dev_free(p->data); dev_free(p->bufA); dev_free(p->bufB); dev_free(p->bufA2); dev_free(p->bufB2); dev_free(p->gbuf); dev_free(p->lbuf);
+    dev_free(p->data); dev_free(p->bufA); dev_free(p->bufB); dev_free(p->bufA2); dev_free(p->bufB2); dev_free(p->gbuf2); dev_free(p->gbuf); dev_free(p->lbuf);
     dev_free(p->counter); dev_free(p->xexp); dev_free(p->partial); dev_free(p->gtab_fwd); dev_free(p->gtab_adj); dev_free(p->xdev); dev_free(p->gdev); dev_free(p->edev);
 #ifndef JB_EMU
     if (p->st_in) {
@@ -620,7 +621,8 @@ static int ensure_second_workspace(jubik_plan* p) {
     const int brB = std::min(std::min(g.w, 64), g.N), brA = std::min(std::min(g.P, 64), g.N);
     std::string err;
     if (alloc(p, (void**)&p->bufA2, TE1 * nn2 * (size_t)g.P * g.PH * sizeof(cd), "second spectrum workspace A") ||
-        alloc(p, (void**)&p->bufB2, TE1 * nn2 * (size_t)g.w * g.PH * sizeof(cd), "second spectrum workspace B"))
+        alloc(p, (void**)&p->bufB2, TE1 * nn2 * (size_t)g.w * g.PH * sizeof(cd), "second spectrum workspace B") ||
+        alloc(p, (void**)&p->gbuf2, TE1 * (size_t)g.N * g.N * sizeof(double), "second cotangent workspace"))
         return JUBIK_ERR_ALLOC;
     if (make_tile_src(&p->src_fwd2, p->bufB2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brB, &err) ||
         make_tile_src(&p->src_adj2, p->bufA2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brA, &err))
@@ -632,6 +634,7 @@ static int ensure_second_workspace(jubik_plan* p) {
 static void swap_workspace(jubik_plan* p) {
     std::swap(p->bufA, p->bufA2); std::swap(p->bufB, p->bufB2);
     std::swap(p->src_fwd, p->src_fwd2); std::swap(p->src_adj, p->src_adj2);
+    std::swap(p->gbuf, p->gbuf2);
 }
 // Fused energy + gradient as (sample, energy bin) planes alternating between the caller's stream and a second one
 // (device-resident form of the host entry point's pipeline).  wait_in: per-plane events to wait for (H2D), or null;
@@ -641,29 +644,38 @@ static int run_planes_two_streams(jubik_plan* p, const double* x, int S, double*
     const JbGeom& g = p->g;
     const size_t npx = (size_t)g.N * g.N;
     if (two) JB_CK(cudaStreamWaitEvent(p->st_c2, p->ev_start, 0));
-    int last_c2 = -1;
-    for (int si = 0; si < S; ++si)
-        for (int e = 0; e < g.E; ++e) {
-            const int c = si * g.E + e;
-            jb_stream_t cs = (two && (c & 1)) ? (jb_stream_t)p->st_c2 : st;
-            if (cs != st) last_c2 = c;
-            JbGeom ge = g;
-            ge.e0 = e; ge.Es = 1;
-            if (wait_in) JB_CK(cudaStreamWaitEvent(cs, p->ev_in[c], 0));
-            // a plane uses workspace slab e: wait for the previous plane with the same e (other stream when E is odd)
-            if (two && c >= g.E) JB_CK(cudaStreamWaitEvent(cs, p->ev_c[c - g.E], 0));
-            JbEpi ep; memset(&ep, 0, sizeof(ep));
-            ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data;
-            ep.partial = p->partial + (size_t)si * g.T * g.E * p->nblk_out;
-            // the chunk runs as "sample 0" of a one-sample batch on this sample's slices of x / grad / partials
-            if (cs != st) swap_workspace(p);
-            int rc = run_forward_g(p, ge, x + (size_t)si * g.E * npx, 1, ep, cs);
-            if (!rc) rc = run_adjoint_g(p, ge, p->gbuf, nullptr, 1, grad + (size_t)si * g.E * npx, cs);
-            if (cs != st) swap_workspace(p);
-            if (rc) return rc;
-            JB_CK(cudaEventRecord(p->ev_c[c], cs));
-            if (int rc2 = after_plane(c)) return rc2;
+    // Chunks of one or two consecutive energy bins of one sample: the first and the last plane travel alone (their
+    // H2D / D2H copies are the exposed ones), the planes in between pair up so that the persistent kernels see fuller
+    // waves.  With two streams every stream owns its spectrum buffers AND its cotangent scratch, so chunks on
+    // different streams never touch the same memory; chunks on one stream are ordered by the stream.
+    const int nplanes = S * g.E;
+    const bool pair_up = two && !getenv("JUBIK_B200_HOST_SINGLE_PLANES");
+    int last_c2 = -1, k = 0;
+    for (int c = 0; c < nplanes; ++k) {
+        const int si = c / g.E, e = c - si * g.E;
+        int len = 1;
+        if (pair_up && c > 0 && e + 1 < g.E && c + 1 < nplanes - 1) len = 2;
+        jb_stream_t cs = (two && (k & 1)) ? (jb_stream_t)p->st_c2 : st;
+        const int cl = c + len - 1;     // last plane of the chunk: its event stands for the chunk
+        if (cs != st) last_c2 = cl;
+        JbGeom ge = g;
+        ge.e0 = e; ge.Es = len;
+        if (wait_in) for (int q = c; q <= cl; ++q) JB_CK(cudaStreamWaitEvent(cs, p->ev_in[q], 0));
+        JbEpi ep; memset(&ep, 0, sizeof(ep));
+        if (cs != st) swap_workspace(p);
+        ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data;
+        ep.partial = p->partial + (size_t)si * g.T * g.E * p->nblk_out;
+        // the chunk runs as "sample 0" of a one-sample batch on this sample's slices of x / grad / partials
+        int rc = run_forward_g(p, ge, x + (size_t)si * g.E * npx, 1, ep, cs);
+        if (!rc) rc = run_adjoint_g(p, ge, p->gbuf, nullptr, 1, grad + (size_t)si * g.E * npx, cs);
+        if (cs != st) swap_workspace(p);
+        if (rc) return rc;
+        for (int q = c; q <= cl; ++q) {
+            JB_CK(cudaEventRecord(p->ev_c[q], cs));
+            if (int rc2 = after_plane(q)) return rc2;
         }
+        c += len;
+    }
     if (last_c2 >= 0) JB_CK(cudaStreamWaitEvent(st, p->ev_c[last_c2], 0));   // join before the energy reduction
     return 0;
 }
