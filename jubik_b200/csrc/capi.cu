@@ -644,12 +644,13 @@ static int run_planes_two_streams(jubik_plan* p, const double* x, int S, double*
     const JbGeom& g = p->g;
     const size_t npx = (size_t)g.N * g.N;
     if (two) JB_CK(cudaStreamWaitEvent(p->st_c2, p->ev_start, 0));
-    // Chunks of one or two consecutive energy bins of one sample: the first and the last plane travel alone (their
-    // H2D / D2H copies are the exposed ones), the planes in between pair up so that the persistent kernels see fuller
-    // waves.  With two streams every stream owns its spectrum buffers AND its cotangent scratch, so chunks on
-    // different streams never touch the same memory; chunks on one stream are ordered by the stream.
+    // One (sample, energy bin) plane per chunk.  With two streams every stream owns its spectrum buffers AND its
+    // cotangent scratch, so chunks on different streams never touch the same memory; chunks on one stream are ordered
+    // by the stream.  JUBIK_B200_HOST_PAIR_PLANES=1 pairs up the planes between the first and the last one (fuller
+    // waves for the persistent kernels) -- measured slower end to end (1.88 vs 1.61 ms at C2, S = 2: the coarser
+    // chunks start later and return their gradients later), kept as a tested option.
     const int nplanes = S * g.E;
-    const bool pair_up = two && !getenv("JUBIK_B200_HOST_SINGLE_PLANES");
+    const bool pair_up = two && getenv("JUBIK_B200_HOST_PAIR_PLANES");
     int last_c2 = -1, k = 0;
     for (int c = 0; c < nplanes; ++k) {
         const int si = c / g.E, e = c - si * g.E;

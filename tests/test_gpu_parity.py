@@ -347,10 +347,13 @@ def test_plane_pipelined_device_path_is_bitwise_equal_to_batched(torch_cuda, mon
     xh = torch.as_tensor(x).pin_memory()
     eh = torch.empty((S,), dtype=torch.float64).pin_memory()
     gh = torch.empty_like(xh).pin_memory()
-    for _ in range(2):
-        gh.zero_()
-        p0.energy_and_grad_host(xh, eh, gh)
-        assert torch.equal(eh, e0.cpu()) and torch.equal(gh, g0.cpu())
+    for pair in (False, True):
+        if pair:
+            monkeypatch.setenv("JUBIK_B200_HOST_PAIR_PLANES", "1")     # chunks of two bins (Es = 2 of E = 3)
+        for _ in range(2):
+            gh.zero_()
+            p0.energy_and_grad_host(xh, eh, gh)
+            assert torch.equal(eh, e0.cpu()) and torch.equal(gh, g0.cpu())
     monkeypatch.setenv("JUBIK_B200_DEV_PLANES", "1")
     p1 = mk()
     for _ in range(3):
