@@ -285,7 +285,12 @@ struct JbOpsImpl {
         }
     }
     // sequences per warp: 1 for n <= 8 (CTAs of <= 4 warps, 28 warps per SM), else 2
-    static int rows5_sw(const JbGeom& g) { return (g.n + 1) / 2 <= 4 ? 1 : 2; }
+    // sequences per warp of the c2r kernels: one for up to 8 packed pairs (n <= 16; more than 4 warps: the WIDE form)
+    static int rows5_sw(const JbGeom& g) {
+        if (getenv("JUBIK_B200_ROWS5_SW2")) return (g.n + 1) / 2 <= 4 ? 1 : 2;   // previous rule (tuning record)
+        return (g.n + 1) / 2 <= 8 ? 1 : 2;
+    }
+    static int rows6_sw(const JbGeom& g) { return (g.n + 1) / 2 <= 4 ? 1 : 2; }   // r2c v6 kernels: CTAs of <= 4 warps
     static size_t rows5_smem(const JbGeom& g) {
         if constexpr (PIPE == 2) {
             const int sw = rows5_sw(g), NC = (g.n + 1) / 2, NW = (NC + sw - 1) / sw;
@@ -325,6 +330,15 @@ struct JbOpsImpl {
             int grid = rows5_grid(kern, NW * 32, smem, (long)planes * g.N, n_sm);
             return jb_launch(kern, dim3(grid), dim3(NW * 32), smem, st, g, src, tw1, tw2, wgt, gtab, gq, ep, grad, planes);
         };
+        if constexpr (SW == 1) {
+            if (NW > 4) {   // 5..8 warps per CTA
+                if constexpr (!ADJ) {
+                    if (ep.mode == JB_EPI_POISSON)
+                        return presum ? go(k_rows_c2r5<F3, 1, false, true, true, true>) : go(k_rows_c2r5<F3, 1, false, false, true, true>);
+                }
+                return presum ? go(k_rows_c2r5<F3, 1, ADJ, true, false, true>) : go(k_rows_c2r5<F3, 1, ADJ, false, false, true>);
+            }
+        }
         if constexpr (!ADJ) {
             if (ep.mode == JB_EPI_POISSON)
                 return presum ? go(k_rows_c2r5<F3, SW, false, true, true>) : go(k_rows_c2r5<F3, SW, false, false, true>);
@@ -357,7 +371,7 @@ struct JbOpsImpl {
     }
     static size_t rows6_smem(const JbGeom& g) {
         if constexpr (PIPE == 2) {
-            const int sw = rows5_sw(g), NC = (g.n + 1) / 2, NW = (NC + sw - 1) / sw;
+            const int sw = rows6_sw(g), NC = (g.n + 1) / 2, NW = (NC + sw - 1) / sw;
             if (NW * 32 > 512 || F3::L > 65535) return (size_t)1 << 30;
             return sw == 1 ? jb_rows6_smem<F3, 1>(g.n, g.N) : jb_rows6_smem<F3, 2>(g.n, g.N);
         } else {
@@ -377,7 +391,7 @@ struct JbOpsImpl {
     static cudaError_t rows6(const JbGeom& g, int adj, const double* in, const double* expo, const double* wgt,
                              const cd* tw1, const cd* tw2, cd* out, int planes, int n_sm, jb_stream_t st) {
         if constexpr (PIPE == 2) {
-            if (rows5_sw(g) == 1) {
+            if (rows6_sw(g) == 1) {
                 if (adj) return rows6_launch<1, true>(g, in, expo, wgt, tw1, tw2, out, planes, n_sm, st);
                 return rows6_launch<1, false>(g, in, expo, wgt, tw1, tw2, out, planes, n_sm, st);
             }

@@ -278,8 +278,11 @@ JB_D void jb_rows5_assemble(cd* tile, const cd* const (&pbase)[SW][2], const boo
 // SW = 2: two sequences per warp for wider patch grids (up to 16 warps per CTA).
 // PRESUM: the source is the column pass's summed buffer (sweep mode).
 // POIS: the fused Poisson energy/cotangent epilogue is compiled in (its log/divide raise the register pressure).
-template <class F3, int SW, bool ADJ, bool PRESUM, bool POIS>
-JB_GLOBAL void JB_LB((SW == 1 ? 128 : 512), (SW == 1 ? JB_R5_CPS : 1))
+// WIDE (SW = 1 only): CTAs of 5..8 warps (patch grids of 9..16 per axis, e.g. the 10x10 of the eROSITA-like configs):
+// still one sequence per warp and 80 registers, so that e.g. 3 CTAs x 5 warps share an SM at L = 672 where the
+// SW = 2 form (3 warps per CTA, 110-128 registers) keeps 9 warps resident.
+template <class F3, int SW, bool ADJ, bool PRESUM, bool POIS, bool WIDE = false>
+JB_GLOBAL void JB_LB((SW == 1 ? (WIDE ? 256 : 128) : 512), (SW == 1 ? (WIDE ? 3 : JB_R5_CPS) : 1))
 k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, const cd* __restrict__ tw2,
             const double* __restrict__ wgt, const int* __restrict__ gtab, int GQ, JbEpi ep, double* __restrict__ grad,
             int planes) {
