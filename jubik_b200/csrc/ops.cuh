@@ -134,7 +134,9 @@ struct JbOpsImpl {
             const bool off = getenv("JUBIK_B200_ROWS_IN_V2") != nullptr;
             const size_t smem = jb_al16((size_t)g.n * FP::LS * sizeof(cd)) + 2 * (size_t)g.N * sizeof(double) +
                                 (ADJ ? 0 : (size_t)g.w * sizeof(double));
-            if (off || (g.N & 1) || smem > 110 * 1024) return false;
+            size_t lim = 110 * 1024;     // two CTAs per SM; JUBIK_B200_ROWS_IN_PF_KB overrides (tuning hook, <= 226)
+            if (const char* ev = getenv("JUBIK_B200_ROWS_IN_PF_KB")) { int v = atoi(ev); if (v >= 16 && v <= 226) lim = (size_t)v * 1024; }
+            if (off || (g.N & 1) || smem > lim) return false;
             int per_sm = 1, n_sm = 148;
 #ifndef JB_EMU
             static int cache_thr = -1, cache_cps = 1, cache_sm = 148;
