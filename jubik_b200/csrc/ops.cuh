@@ -125,7 +125,7 @@ struct JbOpsImpl {
         size_t B = (size_t)rpc * g.n;
         return jb_al16(B * FP::LS * sizeof(cd)) + 16;
     }
-    // persistent prefetching r2c kernel (k_rows_in_pf): used when it fits at least two CTAs per SM; JUBIK_B200_ROWS_IN_V2=1
+    // persistent prefetching r2c kernel (k_rows_in_pf): used when its exchange buffer + row ring fit an SM; JUBIK_B200_ROWS_IN_V2=1
     // keeps the one-row-per-CTA kernels
     template <bool ADJ>
     static bool rows_in_pf(const JbGeom& g, const double* in, const double* wgt, const cd* tw_nk, cd* out, int planes,
@@ -134,7 +134,8 @@ struct JbOpsImpl {
             const bool off = getenv("JUBIK_B200_ROWS_IN_V2") != nullptr;
             const size_t smem = jb_al16((size_t)g.n * FP::LS * sizeof(cd)) + 2 * (size_t)g.N * sizeof(double) +
                                 (ADJ ? 0 : (size_t)g.w * sizeof(double));
-            size_t lim = 110 * 1024;     // two CTAs per SM; JUBIK_B200_ROWS_IN_PF_KB overrides (tuning hook, <= 226)
+            size_t lim = 200 * 1024;     // one CTA per SM is still a win (C4: cotangent rows 0.41 -> 0.16 ms, r1x);
+                                         // JUBIK_B200_ROWS_IN_PF_KB overrides (tuning hook, <= 226)
             if (const char* ev = getenv("JUBIK_B200_ROWS_IN_PF_KB")) { int v = atoi(ev); if (v >= 16 && v <= 226) lim = (size_t)v * 1024; }
             if (off || (g.N & 1) || smem > lim) return false;
             int per_sm = 1, n_sm = 148;
