@@ -6,7 +6,7 @@ Importing the package does not need a GPU; every compute entry point does and ra
 """
 from ._lib import JubikError, load as load_library  # noqa: F401
 from .api import (Domain, PoissonLikelihood, Vector, build_exposure_function, build_psf_operator,  # noqa: F401
-                  build_readout_function, build_response, convolve, linpatch_convolve, slice_patches,
+                  build_readout_function, build_response, convolve, integrate, linpatch_convolve, slice_patches,
                   slice_patches_T)
 from .plan import Communicator, ResponsePlan  # noqa: F401
 from ._lib import SHARD_MODULES, SHARD_SAMPLES  # noqa: F401

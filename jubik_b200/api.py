@@ -7,6 +7,7 @@ the reference's own:
     linpatch_convolve           jubik/convolve.py:66-145
     slice_patches / _T          jubik/convolve.py:28-63 (+ its jax.linear_transpose, :141-143)
     convolve                    jubik/convolve.py:148-176
+    integrate                   jubik/convolve.py:179-184 (host code at set-up time in the reference too)
     build_exposure_function     jubik/response.py:12-45
     build_readout_function      jubik/response.py:48-112
     build_psf_operator          instruments/erosita/erosita_response.py:206-212 (psf_op), chandra :127-130
@@ -169,6 +170,21 @@ def convolve(x, y, domain, axes):
     check(lib, lib.jubik_convolve(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), lead, lead if x_lead is None else 1,
                                   n0, n1, dvol, C.c_void_p(out.data_ptr()), _stream_ptr(torch)))
     return out
+
+
+def integrate(x, domain, axes):
+    """Drop-in for jubik.convolve.integrate (convolve.py:179-184): dvol * sum over `axes`.  Set-up-time host code in
+    the reference (NumPy; used once to normalise the Chandra PSF, chandra_response.py:123): NumPy arrays are summed
+    with NumPy, torch tensors (any device) with torch -- no kernel of ours is involved."""
+    axes = tuple(axes)
+    dvol = 1.0
+    for i in axes:
+        dvol *= float(domain.distances[i])
+    torch = _torch()
+    if isinstance(x, torch.Tensor):
+        return dvol * torch.sum(x, dim=axes)
+    import numpy as np
+    return dvol * np.sum(x, axis=axes)
 
 
 def build_exposure_function(exposures, exposure_cut=None):

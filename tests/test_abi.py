@@ -74,3 +74,14 @@ def test_product_package_never_touches_oracle_or_emulation():
                 assert "libjubik_emu" not in txt, f
     code = "import sys; import jubik_b200; assert not any(m.startswith('oracle') for m in sys.modules)"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_integrate_mirror_known_answer():
+    """jubik.convolve.integrate (convolve.py:179-184; reference test test_convolve.py:23-29) in the host mirror."""
+    import numpy as np
+    import torch
+    import jubik_b200 as jb
+    dom = jb.Domain(shape=(3, 4), distances=(0.5, 0.25))
+    assert jb.integrate(np.ones((3, 4)), dom, axes=(0, 1)) == 3 * 4 * 0.5 * 0.25
+    t = jb.integrate(torch.ones((2, 3, 4), dtype=torch.float64), jb.Domain((2, 3, 4), (1.0, 0.5, 0.25)), axes=(-2, -1))
+    assert t.shape == (2,) and float(t[0]) == 3 * 4 * 0.5 * 0.25
