@@ -85,3 +85,14 @@ def test_integrate_mirror_known_answer():
     assert jb.integrate(np.ones((3, 4)), dom, axes=(0, 1)) == 3 * 4 * 0.5 * 0.25
     t = jb.integrate(torch.ones((2, 3, 4), dtype=torch.float64), jb.Domain((2, 3, 4), (1.0, 0.5, 0.25)), axes=(-2, -1))
     assert t.shape == (2,) and float(t[0]) == 3 * 4 * 0.5 * 0.25
+
+
+def test_hot_kernels_use_tma_bulk_copies_and_fp64_pipe(lib_path):
+    """SASS evidence (B200_PROFILING.md): the column pass is fed by TMA tensor loads and bulk copies on mbarriers
+    (UTMALDG / UBLKCP / SYNCS), the r2c row kernels prefetch with cp.async (LDGSTS), and the arithmetic is FP64."""
+    obj = os.path.join(ROOT, "jubik_b200", "_build", "fft_384.o")
+    assert os.path.exists(obj)
+    sass = subprocess.run(["cuobjdump", "-sass", obj], stdout=subprocess.PIPE, text=True).stdout
+    for mnemonic in ("UTMALDG.3D", "UBLKCP", "SYNCS.ARRIVE.TRANS64", "LDGSTS.E.BYPASS.128", "DFMA", "DADD"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA" not in sass and "UTCHMMA" not in sass      # no tensor-core path: FP64 FFT / stencil work
