@@ -128,12 +128,12 @@ struct JbOpsImpl {
     // persistent prefetching r2c kernel (k_rows_in_pf): used when its exchange buffer + row ring fit an SM; JUBIK_B200_ROWS_IN_V2=1
     // keeps the one-row-per-CTA kernels
     template <bool ADJ>
-    static bool rows_in_pf(const JbGeom& g, const double* in, const double* wgt, const cd* tw_nk, cd* out, int planes,
+    static bool rows_in_pf(const JbGeom& g, const double* in, const double* aux, const cd* tw_nk, cd* out, int planes,
                            int threads, jb_stream_t st, cudaError_t* err) {
         if constexpr (FP::R2 > 1) {
             const bool off = getenv("JUBIK_B200_ROWS_IN_V2") != nullptr;
             const size_t smem = jb_al16((size_t)g.n * FP::LS * sizeof(cd)) + 2 * (size_t)g.N * sizeof(double) +
-                                (ADJ ? 0 : (size_t)g.w * sizeof(double));
+                                (ADJ ? (aux ? 2 * (size_t)g.N * sizeof(double) : 0) : (size_t)g.w * sizeof(double));
             size_t lim = 200 * 1024;     // one CTA per SM is still a win (C4: cotangent rows 0.41 -> 0.16 ms, r1x);
                                          // JUBIK_B200_ROWS_IN_PF_KB overrides (tuning hook, <= 226)
             if (const char* ev = getenv("JUBIK_B200_ROWS_IN_PF_KB")) { int v = atoi(ev); if (v >= 16 && v <= 226) lim = (size_t)v * 1024; }
@@ -157,10 +157,10 @@ struct JbOpsImpl {
             long ctas = (long)per_sm * n_sm;
             const long total = (long)planes * g.N;
             if (ctas > total) ctas = total;
-            *err = jb_launch(k_rows_in_pf<FP, ADJ>, dim3((unsigned)ctas), dim3(threads), smem, st, g, in, wgt, tw_nk, out, planes);
+            *err = jb_launch(k_rows_in_pf<FP, ADJ>, dim3((unsigned)ctas), dim3(threads), smem, st, g, in, aux, tw_nk, out, planes);
             return true;
         } else {
-            (void)g; (void)in; (void)wgt; (void)tw_nk; (void)out; (void)planes; (void)threads; (void)st; (void)err;
+            (void)g; (void)in; (void)aux; (void)tw_nk; (void)out; (void)planes; (void)threads; (void)st; (void)err;
             return false;
         }
     }
@@ -179,7 +179,7 @@ struct JbOpsImpl {
                                    cd* bufA, int planes, int rpc, int threads, int fast, jb_stream_t st) {
         dim3 grid(jb_cdiv(g.N, rpc), planes);
         cudaError_t e2;
-        if (fast && !expo && rows_in_pf<true>(g, gin, nullptr, tw_nk, bufA, planes, threads, st, &e2)) return e2;
+        if (fast && rows_in_pf<true>(g, gin, expo, tw_nk, bufA, planes, threads, st, &e2)) return e2;
         if constexpr (FP::R2 > 1) {
             if (fast) return jb_launch(k_rows_adj_in2<FP>, grid, dim3(threads), smem_rows_in(g, rpc, 1), st, g, gin,
                                        expo, tw_nk, bufA, rpc);

@@ -205,7 +205,7 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_adj_in2(JbGeom g, const double* __restrict__
 // in the other half of a two-slot ring, and pass 1 reads its window elements from shared memory.
 //   ADJ = false: sky rows, window weights, w-wide windows at offs[i]-hp            -> rowsF (S*E, n, N, PH)
 //   ADJ = true : cotangent rows (exposure already folded in), P-wide windows       -> rowsA (STE, n, N, PH)
-// dyn smem = n*LS*16 (exchange) + 2*N*8 (row ring) + w*8 (window weights, forward only).
+// dyn smem = n*LS*16 (exchange) + 2*N*8 (row ring) + w*8 (forward: window weights) or 2*N*8 (adjoint with exposure).
 #ifndef JB_EMU
 JB_D void jb_cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
@@ -219,26 +219,37 @@ inline void jb_cp_async_wait1() {}
 #endif
 
 template <class FP, bool ADJ>
-JB_GLOBAL void JB_LB(256, 2) k_rows_in_pf(JbGeom g, const double* __restrict__ in, const double* __restrict__ wgt,
+JB_GLOBAL void JB_LB(256, 2) k_rows_in_pf(JbGeom g, const double* __restrict__ in, const double* __restrict__ aux,
                                           const cd* __restrict__ tw_nk, cd* __restrict__ rows, int planes) {
+    // aux: forward = window weights (w); adjoint = effective exposure (T,E,N,N) to multiply the cotangent with, or null
     constexpr int R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
     JB_SMEM(unsigned char, smraw);
     const int n = g.n, N = g.N, m = g.m, w = g.w, hp = g.hp, PH = g.PH, P = g.P;
     cd* sm = reinterpret_cast<cd*>(smraw);
     double* ring = reinterpret_cast<double*>(smraw + jb_align16((size_t)n * LS * sizeof(cd)));
-    double* wsm = ring + 2 * (size_t)N;      // window weights (forward): read once per CTA, ordered by the first barrier
-    if (!ADJ) for (int q = jb_tid(); q < w; q += jb_nthr()) wsm[q] = wgt[q];
+    double* ext = ring + 2 * (size_t)N;      // forward: window weights (w); adjoint with exposure: its two-slot row ring
+    const bool with_expo = ADJ && aux != nullptr;
+    if (!ADJ) for (int q = jb_tid(); q < w; q += jb_nthr()) ext[q] = aux[q];   // ordered by the first barrier
     const int total = planes * N;
-    auto plane_of = [&](int lp) -> int {   // launched plane -> plane index of the input / output buffers
+    // launched plane -> plane index of the input / output buffers (and of the exposure)
+    auto plane_of = [&](int lp, int& te) -> int {
         int a, b2, c2;
-        if (ADJ) { jb_map_ste(g, lp, a, b2, c2); return a; }
+        if (ADJ) { jb_map_ste(g, lp, a, b2, c2); te = b2; return a; }
+        te = 0;
         return jb_map_se(g, lp, a, b2);
     };
     auto prefetch = [&](int idx, int slot) {
         const int lp = idx / N, r = idx - lp * N;
-        const double* src = in + ((size_t)plane_of(lp) * N + r) * N;
+        int te;
+        const int pl = plane_of(lp, te);
+        const double* src = in + ((size_t)pl * N + r) * N;
         double* dst = ring + (size_t)slot * N;
         for (int c = 2 * jb_tid(); c < N; c += 2 * jb_nthr()) jb_cp_async16(dst + c, src + c);
+        if (with_expo) {
+            const double* src2 = aux + ((size_t)te * N + r) * N;
+            double* dst2 = ext + (size_t)slot * N;
+            for (int c = 2 * jb_tid(); c < N; c += 2 * jb_nthr()) jb_cp_async16(dst2 + c, src2 + c);
+        }
     };
     int idx = blockIdx.x;
     if (idx < total) prefetch(idx, 0);
@@ -250,8 +261,10 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_in_pf(JbGeom g, const double* __restrict__ i
         jb_cp_async_wait1();          // this thread's copies of the current row have landed ...
         JB_SYNC();                    // ... and so have everybody else's
         const double* row = ring + (size_t)(k & 1) * N;
+        const double* erow = ext + (size_t)(k & 1) * N;
         const int lp = idx / N, r = idx - lp * N;
-        const int pl = plane_of(lp);
+        int te_;
+        const int pl = plane_of(lp, te_);
         for (int it = jb_tid(); it < n * R2; it += jb_nthr()) {
             const int i = it / R2, n2 = it - i * R2;
             double xv[R1];
@@ -262,7 +275,7 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_in_pf(JbGeom g, const double* __restrict__ i
                     constexpr int n1 = nn;
                     const int q = q0 + R2 * n1, c = c0 + R2 * n1;
                     const bool ok = q >= 0 && q < w && c >= 0 && c < N;
-                    xv[n1] = ok ? row[c] * wsm[q] : 0.0;
+                    xv[n1] = ok ? row[c] * ext[q] : 0.0;
                 });
             } else {
                 const int c0 = g.offs[i] - hp - m + n2;
@@ -270,7 +283,9 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_in_pf(JbGeom g, const double* __restrict__ i
                     constexpr int n1 = nn;
                     const int p = n2 + R2 * n1, c = c0 + R2 * n1;
                     const bool ok = p < P && c >= 0 && c < N;
-                    xv[n1] = ok ? row[c] : 0.0;
+                    double v = ok ? row[c] : 0.0;
+                    if (with_expo && ok) v *= erow[c];
+                    xv[n1] = v;
                 });
             }
             jb_r2c_pass1<FP>(xv, sm + (size_t)i * LS + n2, jb_ldg(tw_nk + R2 + n2), jb_ldg(tw_nk + 2 * R2 + n2));
