@@ -27,7 +27,9 @@
  * Conventions: every array pointer is a DEVICE pointer to contiguous C-order memory (float64 unless
  * stated); `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous
  * on that stream; return value 0 = ok, otherwise an error code whose text is jubik_last_error().
- * No allocation happens after plan creation.  A plan owns one workspace: use one plan per stream.
+ * No allocation happens after plan creation, except on the FIRST call of an entry point that needs extra staging
+ * (host-buffer call: device copies of x / grad and the second stream's workspace; metric: lambda scratch; log-sky:
+ * exp(log_sky); sharded call without grad_local: per-sample gradients).  A plan owns one workspace: use one plan per stream.
  * There is no CPU fallback: without a CUDA device every entry point fails.
  */
 #ifndef JUBIK_B200_H
