@@ -10,8 +10,9 @@ One step = one evaluation of (energy[s], d energy[s] / d sky[s]) for the S sampl
 S*T*E*N^2.
 Every rank (also at N=1) evaluates `--samples-per-gpu` posterior samples of that workload per step (default 2, the
 per-GPU share of BASELINE.json configs[4]: 16 geoVI samples over 8 GPUs) -- weak scaling, sample sharding (SURVEY 8e);
-the per-sample energies and the sample-summed gradient sit in one flat buffer that is combined with a
-SINGLE NCCL all-reduce inside the timed region.
+one step is ONE C-ABI call (jubik_poisson_energy_and_grad_sharded): the seven kernels, the fold of the rank's samples
+into a flat buffer [sample-summed gradient | per-sample energies of all ranks] and a SINGLE ncclAllReduce of that buffer,
+issued by the library on its own NCCL communicator, all on one stream inside the timed region.
 
 `value`  : device-resident throughput (inputs already in HBM), CUDA events, max over ranks.
 `e2e`    : the same metric through ResponsePlan.energy_and_grad_host (C ABI jubik_poisson_energy_and_grad_host)
