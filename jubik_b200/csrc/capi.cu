@@ -131,6 +131,7 @@ struct jubik_plan {
     cd* bufA2 = nullptr;
     cd* bufB2 = nullptr;
     double* gbuf2 = nullptr;
+    int ws2_ready = 0;
     JbTileSrc src_fwd2, src_adj2;
     // per-kernel timing (jubik_poisson_profile): events recorded after every launch while enabled
     int prof_on = 0, prof_n = 0;
@@ -615,18 +616,19 @@ static int ensure_plane_streams(jubik_plan* p) {
 // The two compute streams' planes are in different phases at the same time, and the forward / adjoint layouts of one
 // spectrum buffer alias across energy bins: the second stream gets its own pair of buffers (one sample's worth).
 static int ensure_second_workspace(jubik_plan* p) {
-    if (p->bufA2) return 0;
+    if (p->ws2_ready) return 0;
     const JbGeom& g = p->g;
     const size_t TE1 = (size_t)g.T * g.E, nn2 = (size_t)g.n * g.n;
     const int brB = std::min(std::min(g.w, 64), g.N), brA = std::min(std::min(g.P, 64), g.N);
     std::string err;
-    if (alloc(p, (void**)&p->bufA2, TE1 * nn2 * (size_t)g.P * g.PH * sizeof(cd), "second spectrum workspace A") ||
-        alloc(p, (void**)&p->bufB2, TE1 * nn2 * (size_t)g.w * g.PH * sizeof(cd), "second spectrum workspace B") ||
-        alloc(p, (void**)&p->gbuf2, TE1 * (size_t)g.N * g.N * sizeof(double), "second cotangent workspace"))
+    if ((!p->bufA2 && alloc(p, (void**)&p->bufA2, TE1 * nn2 * (size_t)g.P * g.PH * sizeof(cd), "second spectrum workspace A")) ||
+        (!p->bufB2 && alloc(p, (void**)&p->bufB2, TE1 * nn2 * (size_t)g.w * g.PH * sizeof(cd), "second spectrum workspace B")) ||
+        (!p->gbuf2 && alloc(p, (void**)&p->gbuf2, TE1 * (size_t)g.N * g.N * sizeof(double), "second cotangent workspace")))
         return JUBIK_ERR_ALLOC;
     if (make_tile_src(&p->src_fwd2, p->bufB2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brB, &err) ||
         make_tile_src(&p->src_adj2, p->bufA2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brA, &err))
         return fail(JUBIK_ERR_CUDA, err);
+    p->ws2_ready = 1;
     return 0;
 }
 // kernel arguments are captured at launch, so the second stream's launches simply see the plan with its workspace
