@@ -10,5 +10,6 @@ from .api import (Domain, PoissonLikelihood, Vector, build_exposure_function, bu
                   slice_patches_T)
 from .plan import Communicator, ResponsePlan  # noqa: F401
 from ._lib import SHARD_MODULES, SHARD_SAMPLES  # noqa: F401
+from . import sharding  # noqa: F401
 
 __version__ = "0.1.0"
