@@ -27,9 +27,10 @@
  * Conventions: every array pointer is a DEVICE pointer to contiguous C-order memory (float64 unless
  * stated); `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous
  * on that stream; return value 0 = ok, otherwise an error code whose text is jubik_last_error().
- * No allocation happens after plan creation, except on the FIRST call of an entry point that needs extra staging
- * (host-buffer call: device copies of x / grad and the second stream's workspace; metric: lambda scratch; log-sky:
- * exp(log_sky); sharded call without grad_local: per-sample gradients).  A plan owns one workspace: use one plan per stream.
+ * No allocation happens after plan creation: the staging of the optional entry points (host-buffer call, metric,
+ * sharded call) is requested with jubik_plan_desc.flags and allocated by jubik_plan_create (the one exception is
+ * jubik_plan_set_data on a plan created without data, which allocates the counts plane once).  Kernel selection is a
+ * pure function of the descriptor -- no environment variables.  A plan owns one workspace: use one plan per stream.
  * There is no CPU fallback: without a CUDA device every entry point fails.
  */
 #ifndef JUBIK_B200_H
@@ -47,6 +48,14 @@ enum { JUBIK_KERNEL_FULL = 0,    /* (T, n*n, E, N, N) origin-centred, as psf_int
        JUBIK_KERNEL_CROPPED = 1  /* (T, n*n, E, 2dx, 2dx) centred = what convolve.py:107-111 extracts */ };
 enum { JUBIK_DATA_F64 = 0, JUBIK_DATA_I64 = 1 };
 
+/* Optional staging, allocated at plan creation (no allocation happens afterwards).  An entry point whose staging was
+ * not requested fails with JUBIK_ERR_ARG. */
+enum { JUBIK_PLAN_HOST_CALL = 1,  /* jubik_poisson_energy_and_grad_host: device copies of x / grad / energy, copy streams,
+                                     and the second compute stream's workspace (one sample's worth of spectra)          */
+       JUBIK_PLAN_METRIC = 2,     /* jubik_poisson_set_point / metric / left-sqrt-metric: (S,T,E,N,N) linearisation point */
+       JUBIK_PLAN_SHARDED = 4     /* jubik_poisson_energy_and_grad_sharded: per-sample gradient staging (used when
+                                     grad_local is NULL) and the collective's stream                                     */ };
+
 enum { JUBIK_OK = 0, JUBIK_ERR_ARG = 1, JUBIK_ERR_UNSUPPORTED = 2, JUBIK_ERR_CUDA = 3, JUBIK_ERR_ALLOC = 4 };
 
 typedef struct jubik_plan_desc {
@@ -60,7 +69,7 @@ typedef struct jubik_plan_desc {
     int32_t data_dtype;        /* JUBIK_DATA_*                                                  */
     int32_t has_exposure_cut;  /* 0: exposure_cut=None                                          */
     int32_t fft_length;        /* 0 = choose; otherwise force this transform length (>= P)      */
-    int32_t reserved;
+    int32_t flags;             /* JUBIK_PLAN_*: which optional staging the plan allocates        */
     double d0, d1;             /* pixel distances (domain.distances[-2:]); cancel analytically   */
     double exposure_cut;
     double pixel_area;         /* x * pixel_area in R (1.0 if unused)                            */
@@ -75,6 +84,10 @@ typedef struct jubik_plan_info {
     int32_t exact_period;      /* 1: circular period == P (reference semantics for any PSF support) */
     int32_t psf_half_support;  /* max |offset| with a non-zero PSF value                            */
     int32_t fft_r1, fft_r2, col_block;
+    int32_t alias_fold;        /* 1: L > P with a PSF wider than the margin: linear convolution folded modulo P     */
+    int32_t alias_ext;         /* rows / columns at either end of the P-window that alias (half-support - margin)   */
+    int32_t fast_path;         /* 1: TMA column pipeline + warp-private c2r rows; 0: generic kernels                */
+    int32_t flags;             /* the descriptor's JUBIK_PLAN_* flags                                               */
     size_t bytes_khat, bytes_workspace, bytes_total;
 } jubik_plan_info;
 
@@ -90,6 +103,11 @@ int jubik_plan_destroy(jubik_plan* plan);
 int jubik_plan_get_info(const jubik_plan* plan, jubik_plan_info* info);
 /* (re)bind the observed counts, dense (T,E,N,N) */
 int jubik_plan_set_data(jubik_plan* plan, const void* data, int data_dtype, void* stream);
+/* Replace the PSF kernels of an existing plan (same geometry): redoes convolve.py:104-131 + the kernel FFT into the
+ * resident spectra without reallocating.  This is the eROSITA call form R(x, k) with the kernel as a dynamic argument
+ * (erosita_response.py:349-350, erosita_likelihood.py:73-83): the binding calls it only when k actually changed.
+ * Fails with JUBIK_ERR_UNSUPPORTED if the new PSF's support no longer fits the plan's transform length. Synchronises. */
+int jubik_plan_set_kernel(jubik_plan* plan, const double* kernel, int kernel_layout, void* stream);
 /* kernels launched through this plan so far (bench.py's gpu_launches) */
 long long jubik_plan_launch_count(const jubik_plan* plan);
 
@@ -108,7 +126,16 @@ int jubik_poisson_metric_apply(jubik_plan* plan, const double* x, const double* 
 /* out = R^T (t / sqrt(R x)) ; x,out:(S,E,N,N), t:(S,T,E,N,N) (masked pixels of t are ignored) */
 int jubik_poisson_left_sqrt_metric(jubik_plan* plan, const double* x, const double* t, int n_samples,
                                    double* out, void* stream);
-/* log_sky:(S,E,N,N) -> energy of x = exp(log_sky) and d energy / d log_sky = grad_x * x */
+/* The same two operators with a CACHED linearisation point: NIFTy's CG applies the metric 60-70 times per sample at a
+ * fixed position (lin_maxiter, demos/configs/eROSITA_demo.yaml:161).  jubik_poisson_set_point runs one forward pass
+ * and stores expo^2 / lambda(x) (S,T,E,N,N); each *_at_point call is then one forward + one adjoint pass (metric) or one
+ * adjoint pass (left-sqrt-metric).  The two calls above are set_point followed by the matching *_at_point call.
+ * Needs JUBIK_PLAN_METRIC. */
+int jubik_poisson_set_point(jubik_plan* plan, const double* x, int n_samples, void* stream);
+int jubik_poisson_metric_apply_at_point(jubik_plan* plan, const double* v, int n_samples, double* out, void* stream);
+int jubik_poisson_left_sqrt_metric_at_point(jubik_plan* plan, const double* t, int n_samples, double* out, void* stream);
+/* log_sky:(S,E,N,N) -> energy of x = exp(log_sky) and d energy / d log_sky = grad_x * x.  The exp is taken by the r2c
+ * row kernel on load and the product by the c2r row kernel on store: no extra pass over the sky. */
 int jubik_poisson_energy_and_grad_logsky(jubik_plan* plan, const double* log_sky, int n_samples,
                                          double* energy, double* grad, void* stream);
 /* Stand-alone helpers of the reference's public API (no plan needed; device pointers, fp64):

@@ -15,10 +15,12 @@ LIB_PATH = os.environ.get("JUBIK_B200_LIB") or os.path.join(HERE, "libjubik_b200
 
 KERNEL_FULL, KERNEL_CROPPED = 0, 1
 DATA_F64, DATA_I64 = 0, 1
+PLAN_HOST_CALL, PLAN_METRIC, PLAN_SHARDED = 1, 2, 4
 
 EXPORTS = [
     "jubik_last_error", "jubik_version", "jubik_fft_length_supported", "jubik_device_count",
-    "jubik_plan_create", "jubik_plan_destroy", "jubik_plan_get_info", "jubik_plan_set_data",
+    "jubik_plan_create", "jubik_plan_destroy", "jubik_plan_get_info", "jubik_plan_set_data", "jubik_plan_set_kernel",
+    "jubik_poisson_set_point", "jubik_poisson_metric_apply_at_point", "jubik_poisson_left_sqrt_metric_at_point",
     "jubik_plan_launch_count", "jubik_psf_apply", "jubik_psf_apply_T", "jubik_response_apply",
     "jubik_response_apply_T", "jubik_poisson_energy_and_grad", "jubik_poisson_metric_apply",
     "jubik_poisson_energy_and_grad_host", "jubik_poisson_profile", "jubik_measure_fp64_tflops",
@@ -35,7 +37,7 @@ class PlanDesc(C.Structure):
         ("n0", C.c_int32), ("n1", C.c_int32), ("n_energy", C.c_int32), ("n_modules", C.c_int32),
         ("max_samples", C.c_int32), ("n_patches", C.c_int32), ("margin", C.c_int32),
         ("kernel_layout", C.c_int32), ("data_dtype", C.c_int32), ("has_exposure_cut", C.c_int32),
-        ("fft_length", C.c_int32), ("reserved", C.c_int32),
+        ("fft_length", C.c_int32), ("flags", C.c_int32),
         ("d0", C.c_double), ("d1", C.c_double), ("exposure_cut", C.c_double), ("pixel_area", C.c_double),
         ("kernel", C.c_void_p), ("exposure", C.c_void_p), ("eff_area", C.c_void_p), ("data", C.c_void_p),
     ]
@@ -44,7 +46,7 @@ class PlanDesc(C.Structure):
 class PlanInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in
                 ("N", "n", "m", "dx", "w", "P", "L", "PH", "S_max", "T", "E", "exact_period",
-                 "psf_half_support", "fft_r1", "fft_r2", "col_block")] + \
+                 "psf_half_support", "fft_r1", "fft_r2", "col_block", "alias_fold", "alias_ext", "fast_path", "flags")] + \
                [("bytes_khat", C.c_size_t), ("bytes_workspace", C.c_size_t), ("bytes_total", C.c_size_t)]
 
 
@@ -63,6 +65,10 @@ def bind(lib):
     lib.jubik_plan_destroy.argtypes = [vp]
     lib.jubik_plan_get_info.argtypes = [vp, C.POINTER(PlanInfo)]
     lib.jubik_plan_set_data.argtypes = [vp, vp, i, vp]
+    lib.jubik_plan_set_kernel.argtypes = [vp, vp, i, vp]
+    lib.jubik_poisson_set_point.argtypes = [vp, vp, i, vp]
+    lib.jubik_poisson_metric_apply_at_point.argtypes = [vp, vp, i, vp, vp]
+    lib.jubik_poisson_left_sqrt_metric_at_point.argtypes = [vp, vp, i, vp, vp]
     lib.jubik_plan_launch_count.argtypes = [vp]
     lib.jubik_plan_launch_count.restype = C.c_longlong
     for name in ("jubik_psf_apply", "jubik_psf_apply_T", "jubik_response_apply", "jubik_response_apply_T"):

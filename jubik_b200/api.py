@@ -65,31 +65,69 @@ def _as_cuda(a, device=None):
 _PLAN_CACHE = {}
 
 
+class _CachedPsf:
+    """One cached linpatch plan: the plan, the device kernel it was built from (kept alive, so its address cannot be
+    recycled for a different PSF) and the identity/version of the caller's object for the cheap hit test."""
+
+    def __init__(self, plan, kern_dev, src):
+        self.plan, self.kern_dev = plan, kern_dev
+        self.remember(src)
+
+    def remember(self, src):
+        torch = _torch()
+        self.src_id = id(src)
+        self.src_version = src._version if isinstance(src, torch.Tensor) else None
+        self.src_ref = src if isinstance(src, torch.Tensor) else None   # pins id(src) for tensors
+
+    def same_object(self, src):
+        return self.src_ref is not None and src is self.src_ref and src._version == self.src_version
+
+
 def linpatch_convolve(x, domain, kernel, n_patches_per_axis, margin):
     """Drop-in for jubik.linpatch_convolve (convolve.py:66-145).
 
-    x: (..., N, N); kernel: (n*n, ..., N, N) origin-centred, same leading axes as x.  A plan (PSF spectra)
-    is built per distinct kernel tensor and cached; hot loops should hold a plan via build_psf_operator.
+    x: (..., N, N); kernel: (n*n, ..., N, N) origin-centred, same leading axes as x.  One plan (PSF spectra) is cached
+    per geometry.  A call with the same kernel tensor (same object, unmodified) or a kernel of equal CONTENT reuses the
+    resident spectra; any other kernel re-runs the PSF preparation on the device (jubik_plan_set_kernel), so two
+    different PSFs of the same shape can never be confused.  Hot loops should hold a plan via build_psf_operator.
     """
     if not isinstance(domain, Domain):
         raise ValueError("domain has to be an instance of jubik.Domain")
     torch = _torch()
+    from ._lib import JubikError
     x = _as_cuda(x)
-    kernel = _as_cuda(kernel, x.device)
+    kern_dev = _as_cuda(kernel, x.device)
     N = domain.shape[-1]
     lead = tuple(x.shape[:-2])
     E = 1
     for s in lead:
         E *= s
-    key = (kernel.data_ptr(), kernel._version, tuple(kernel.shape), N, n_patches_per_axis, margin, x.device.index)
-    plan = _PLAN_CACHE.get(key)
-    if plan is None:
-        k5 = kernel.reshape((1, kernel.shape[0], E) + tuple(kernel.shape[-2:]))
+    key = (tuple(kern_dev.shape), N, n_patches_per_axis, margin, x.device.index, tuple(domain.distances[-2:]))
+    k5 = kern_dev.reshape((1, kern_dev.shape[0], E) + tuple(kern_dev.shape[-2:])).contiguous()
+
+    def private(t):
+        # the cache's copy must not alias the caller's tensor: an in-place update of that tensor would otherwise change
+        # both sides of the content comparison below
+        shares = isinstance(kernel, torch.Tensor) and t.untyped_storage().data_ptr() == kernel.untyped_storage().data_ptr()
+        return t.clone() if shares else t
+    ent = _PLAN_CACHE.get(key)
+    if ent is not None and not ent.same_object(kernel):
+        if not torch.equal(ent.kern_dev, k5):
+            try:
+                ent.plan.set_kernel(k5, cropped=False)
+                ent.kern_dev = private(k5)
+            except JubikError:      # the new PSF's support does not fit the cached transform length
+                ent.plan.close()
+                del _PLAN_CACHE[key]
+                ent = None
+        if ent is not None:
+            ent.remember(kernel)
+    if ent is None:
         plan = ResponsePlan(k5, N, n_patches_per_axis, margin, distances=tuple(domain.distances[-2:]))
         if len(_PLAN_CACHE) >= 4:
-            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE))).close()
-        _PLAN_CACHE[key] = plan
-    y = plan.psf(x.reshape((E, N, N)))[0]
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE))).plan.close()
+        ent = _PLAN_CACHE[key] = _CachedPsf(plan, private(k5), kernel)
+    y = ent.plan.psf(x.reshape((E, N, N)))[0]
     return y.reshape(lead + (N, N))
 
 

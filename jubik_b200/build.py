@@ -33,12 +33,21 @@ def fft_list():
             for m in re.finditer(r"X\((\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+)\)", txt)]
 
 
-def _sources_mtime():
-    newest = 0.0
+STAMP = os.path.join(OBJ, "sources.sha256")
+
+
+def _sources_digest(flags):
+    """sha256 over every source/header that goes into the library plus the compiler flags: the rebuild decision
+    follows the CONTENT (an mtime comparison breaks on checkouts and on the copy that travels to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256()
     for root in (CSRC, os.path.join(HERE, "..", "include")):
-        for f in os.listdir(root):
-            newest = max(newest, os.path.getmtime(os.path.join(root, f)))
-    return newest
+        for f in sorted(os.listdir(root)):
+            h.update(f.encode())
+            with open(os.path.join(root, f), "rb") as fh:
+                h.update(fh.read())
+    h.update(" ".join(flags).encode())
+    return h.hexdigest()
 
 
 def _run(cmd, log):
@@ -57,7 +66,8 @@ def build(force=False, jobs=None, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: jubik_b200 needs the CUDA toolkit to build")
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _sources_mtime():
+    digest = _sources_digest(NVCC_FLAGS)
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     jobs = jobs or os.cpu_count() or 4
@@ -77,6 +87,8 @@ def build(force=False, jobs=None, verbose=False):
                 print(out)
     objs = [o for _, o in tasks]
     _run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"], os.path.join(OBJ, "link.log"))
+    with open(STAMP, "w") as fh:
+        fh.write(digest + "\n")
     return LIB
 
 

@@ -83,10 +83,11 @@ const int k_lengths[] = {
 struct jubik_plan {
     JbGeom g;
     const JbFftOps* ops = nullptr;
-    int S_max = 0;
+    int S_max = 0, flags = 0;
     int exact = 0, support = 0;
     int has_expo = 0, has_data = 0;
-    int rpc_in = 1, rpc_out = 1, thr_rows = 128, thr_cols = 128;
+    int point_S = 0;           // samples of the cached linearisation point (0: none)
+    int rpc = 1, thr_rows = 128, thr_cols = 128;
     long long launches = 0;
     // device memory
     cd* khat = nullptr;
@@ -97,37 +98,31 @@ struct jubik_plan {
     double* wgt = nullptr;
     double* expo = nullptr;    // (T,E,N,N) effective exposure, 0 == masked
     double* data = nullptr;    // (T,E,N,N)
-    // bufA: forward  column-pass output (STE, n^2, P, PH) -> rows_out;  adjoint row spectra rowsA (STE, n, N, PH)
+    double* psums = nullptr;   // (T*E*n*n) PSF sums and half-supports: plan creation and jubik_plan_set_kernel
+    int* psupp = nullptr;
+    // bufA: forward  column-pass output (STE, n^2, P or L, PH) -> rows_out;  adjoint row spectra rowsA (STE, n, N, PH)
     // bufB: adjoint  column-pass output (STE, n^2, w, PH) -> rows_adj_out; forward row spectra rowsF (S*E, n, N, PH)
     // (each direction uses one buffer as its de-duplicated input and the other as its per-patch output)
     cd* bufA = nullptr;
     cd* bufB = nullptr;
-    double* gbuf = nullptr;    // (S_max,T,E,N,N) cotangent / lambda scratch
-    double* lbuf = nullptr;    // (S_max,T,E,N,N) lambda for the metric (allocated on first use)
+    double* gbuf = nullptr;    // (S_max,T,E,N,N) cotangent scratch
+    double* fac = nullptr;     // (S_max,T,E,N,N) expo^2 / lambda at the linearisation point (JUBIK_PLAN_METRIC)
     double* partial = nullptr; // energy partials
-    double* xexp = nullptr;    // exp(log sky) of the sky-model tail entry point (allocated on first use)
-    double* xdev = nullptr;    // staging for the host-buffer entry point (allocated on first use)
+    double* xdev = nullptr;    // staging of the host-buffer entry point (JUBIK_PLAN_HOST_CALL)
     double* gdev = nullptr;
     double* edev = nullptr;
+    double* gstage = nullptr;  // per-sample gradients of the sharded call without grad_local (JUBIK_PLAN_SHARDED)
     size_t bytes_khat = 0, bytes_ws = 0, bytes_total = 0;
     int nblk_out = 0;
     int use_pipe = 0, n_sm = 1;
-    int split_epi = 1, nblk_epi = 1;  // Poisson/metric epilogue as a separate elementwise kernel
-    int rows_r3_out = 0, rows_r3_adj = 0;  // packed-complex three-stage c2r kernels (rows3.cuh)
-    int rows6 = 0;                         // warp-private r2c kernels (rows6.cuh)
-    int sweep = 0;                         // column pass accumulates over the row-patches (cols3.cuh SWEEP + rows5 presum)
-    int chunk_e = 0;                       // fused energy+gradient runs one energy bin at a time (L2 residency)
-    int cols_pp = 0;                       // column pass as an anti-phase pair of groups per SM (cols3_pp.cuh)
-    int dev_planes = 0;                    // ... one (sample, bin) plane at a time on two alternating streams
     int rows5 = 0;                         // warp-private c2r kernels with the fused Poisson epilogue (rows5.cuh)
     int* gtab_fwd = nullptr;               // rows5 overlap-add gather tables [gq][N]
     int* gtab_adj = nullptr;
-    unsigned* counter = nullptr;           // last-CTA-done counter of the fused energy reduction
     int gq_fwd = 0, gq_adj = 0;
-    int rows_pipe_out = 0, rows_pipe_adj = 0, qmax = 0;  // persistent bulk-copy-fed c2r kernels (rows_pipe.cuh)
-    int fast_rows = 0;         // rows_fast.cuh kernels (two-pass length and <= JB_MAXQ row-patches per image row)
+    int qmax = 0;
+    int fast_rows = 0;         // rows_fast.cuh kernels (two-pass length, <= JB_MAXQ row-patches per image row, no alias fold)
     JbTileSrc src_fwd, src_adj;  // TMA views of bufB / bufA for the pipelined column pass
-    // second spectrum workspace (one sample) of the host-buffer entry point's second compute stream (first use)
+    // second spectrum workspace (one sample) of the host-buffer entry point's second compute stream
     cd* bufA2 = nullptr;
     cd* bufB2 = nullptr;
     double* gbuf2 = nullptr;
@@ -137,9 +132,10 @@ struct jubik_plan {
     int prof_on = 0, prof_n = 0;
 #ifndef JB_EMU
     cudaEvent_t prof_ev[48] = {};
-    // host-buffer entry point: copy streams and per-energy-bin events (created on first use)
-    cudaStream_t st_in = nullptr, st_out = nullptr, st_c2 = nullptr;
-    cudaEvent_t *ev_in = nullptr, *ev_c = nullptr, ev_start = nullptr;
+    // host-buffer entry point: copy streams and per-plane events; sharded call: the collective's stream
+    cudaStream_t st_in = nullptr, st_out = nullptr, st_c2 = nullptr, st_comm = nullptr;
+    cudaEvent_t *ev_in = nullptr, *ev_c = nullptr, ev_start = nullptr, *ev_bin = nullptr, ev_comm = nullptr;
+    int n_ev = 0;
 #endif
 };
 
@@ -161,22 +157,29 @@ static inline void jb_mark(jubik_plan* p, jb_stream_t st) {
 extern "C" {
 
 const char* jubik_last_error(void) { return g_err.c_str(); }
-int jubik_version(void) { return 100; }
+int jubik_version(void) { return 200; }
 int jubik_fft_length_supported(int length) { return find_ops(length) != nullptr; }
 int jubik_device_count(void) { return device_count(); }
 
 int jubik_plan_destroy(jubik_plan* p) {
     if (!p) return JUBIK_OK;
-    dev_free(p->khat); dev_free(p->tw_nk); dev_free(p->tw_kn); dev_free(p->tw1); dev_free(p->tw2); dev_free(p->wgt); dev_free(p->expo);
-    dev_free(p->data); dev_free(p->bufA); dev_free(p->bufB); dev_free(p->bufA2); dev_free(p->bufB2); dev_free(p->gbuf2); dev_free(p->gbuf); dev_free(p->lbuf);
-    dev_free(p->counter); dev_free(p->xexp); dev_free(p->partial); dev_free(p->gtab_fwd); dev_free(p->gtab_adj); dev_free(p->xdev); dev_free(p->gdev); dev_free(p->edev);
+    void* bufs[] = {p->khat, p->tw_nk, p->tw_kn, p->tw1, p->tw2, p->wgt, p->expo, p->data, p->psums, p->psupp, p->bufA, p->bufB,
+                    p->bufA2, p->bufB2, p->gbuf2, p->gbuf, p->fac, p->partial, p->gtab_fwd, p->gtab_adj, p->xdev, p->gdev,
+                    p->edev, p->gstage};
+    for (void* b : bufs) dev_free(b);
 #ifndef JB_EMU
-    if (p->st_in) {
-        for (int e = 0; e < p->S_max * p->g.E; ++e) { cudaEventDestroy(p->ev_in[e]); cudaEventDestroy(p->ev_c[e]); }
-        delete[] p->ev_in; delete[] p->ev_c;
-        cudaEventDestroy(p->ev_start);
-        cudaStreamDestroy(p->st_in); cudaStreamDestroy(p->st_out); if (p->st_c2) cudaStreamDestroy(p->st_c2);
+    for (int e = 0; e < p->n_ev; ++e) {
+        if (p->ev_in && p->ev_in[e]) cudaEventDestroy(p->ev_in[e]);
+        if (p->ev_c && p->ev_c[e]) cudaEventDestroy(p->ev_c[e]);
     }
+    delete[] p->ev_in; delete[] p->ev_c;
+    if (p->ev_bin) { for (int e = 0; e < p->g.E; ++e) if (p->ev_bin[e]) cudaEventDestroy(p->ev_bin[e]); delete[] p->ev_bin; }
+    if (p->ev_start) cudaEventDestroy(p->ev_start);
+    if (p->ev_comm) cudaEventDestroy(p->ev_comm);
+    if (p->st_in) cudaStreamDestroy(p->st_in);
+    if (p->st_out) cudaStreamDestroy(p->st_out);
+    if (p->st_c2) cudaStreamDestroy(p->st_c2);
+    if (p->st_comm) cudaStreamDestroy(p->st_comm);
     for (int i = 0; i < 48; ++i) if (p->prof_ev[i]) cudaEventDestroy(p->prof_ev[i]);
 #endif
     delete p;
@@ -184,8 +187,10 @@ int jubik_plan_destroy(jubik_plan* p) {
 }
 
 static int alloc(jubik_plan* p, void** ptr, size_t bytes, const char* what) {
-    if (dev_malloc(ptr, bytes)) return fail(JUBIK_ERR_ALLOC, std::string("device allocation failed for ") + what +
-                                                                 " (" + std::to_string(bytes) + " bytes)");
+    if (dev_malloc(ptr, bytes)) {
+        *ptr = nullptr;
+        return fail(JUBIK_ERR_ALLOC, std::string("device allocation failed for ") + what + " (" + std::to_string(bytes) + " bytes)");
+    }
     p->bytes_total += bytes;
     return 0;
 }
@@ -196,8 +201,7 @@ static void choose_launch_shapes(jubik_plan* p) {
     // rows kernels: aim for >= 8 sequences per CTA, <= 256 threads; items per pass ~ B*R2 and B*(R1/2+1)
     int rpc = 1;
     while (rpc * g.n < 8 && rpc < g.N) rpc *= 2;
-    if (const char* ev = getenv("JUBIK_B200_RPC")) { int v = atoi(ev); if (v >= 1 && v <= 8) rpc = v; }   // tuning hook
-    p->rpc_in = p->rpc_out = rpc;
+    p->rpc = rpc;
     int B = rpc * g.n;
     int items = B * (o->R2 > 1 ? (o->R2 > o->R1 / 2 + 1 ? o->R2 : o->R1 / 2 + 1) : 1);
     int thr = ((items + 31) / 32) * 32;
@@ -209,6 +213,115 @@ static void choose_launch_shapes(jubik_plan* p) {
     if (ct < 32) ct = 32;
     if (ct > 128) ct = 128;
     p->thr_cols = ct;
+}
+
+// PSF sums and half-supports of every (module, energy, patch) -> p->psums / p->psupp; p->support = the largest
+static int psf_stats(jubik_plan* p, const JbKsrc& ks, jb_stream_t st) {
+    const JbGeom& g = p->g;
+    const size_t nn2 = (size_t)g.n * g.n, TE = (size_t)g.T * g.E;
+    JB_CK(jb_launch(k_prep_sum, dim3((unsigned)nn2, (unsigned)TE), dim3(256), 256 * sizeof(double), st, g, ks, p->psums, p->psupp));
+    ++p->launches;
+    std::vector<int> hs(TE * nn2);
+    if (d2h(hs.data(), p->psupp, hs.size() * sizeof(int), st) || stream_sync(st)) return fail(JUBIK_ERR_CUDA, "reading PSF support failed");
+    int mx = 0;
+    for (int v : hs) mx = v > mx ? v : mx;
+    p->support = mx;
+    return 0;
+}
+
+// PSF spectra: rows r2c -> columns FFT -> normalise -> resident in the column pass's register order (convolve.py:104-131
+// + the kernel FFT of :165, hoisted out of the per-call path).  bufB is the scratch for the row spectra.
+static int psf_spectra(jubik_plan* p, const JbKsrc& ks, jb_stream_t st) {
+    const JbGeom& g = p->g;
+    const JbFftOps* o = p->ops;
+    const int prpc = 8;
+    int items = prpc * (o->R2 > 1 ? (o->R2 > o->R1 / 2 + 1 ? o->R2 : o->R1 / 2 + 1) : 1);
+    int thr = ((items + 31) / 32) * 32; if (thr < 32) thr = 32; if (thr > 256) thr = 256;
+    JB_CK(o->prep_rows(g, ks, p->tw_nk, p->bufB, prpc, thr, st));
+    ++p->launches;
+    JB_CK(o->prep_cols(g, p->bufB, p->psums, p->use_pipe == 2 ? p->tw1 : p->tw_nk, p->tw2, p->khat, p->use_pipe == 2 ? 2 : 0, p->thr_cols, st));
+    ++p->launches;
+    return 0;
+}
+
+#ifndef JB_EMU
+// streams / events of the plane-pipelined host call and of the overlapped collective
+static int ensure_plane_streams(jubik_plan* p) {
+    if (p->st_in) return 0;
+    const int nev = p->S_max * p->g.E;
+    JB_CK(cudaStreamCreateWithFlags(&p->st_in, cudaStreamNonBlocking));
+    JB_CK(cudaStreamCreateWithFlags(&p->st_out, cudaStreamNonBlocking));
+    JB_CK(cudaStreamCreateWithFlags(&p->st_c2, cudaStreamNonBlocking));
+    p->ev_in = new cudaEvent_t[nev](); p->ev_c = new cudaEvent_t[nev]();
+    p->n_ev = nev;
+    for (int e = 0; e < nev; ++e) {
+        JB_CK(cudaEventCreateWithFlags(&p->ev_in[e], cudaEventDisableTiming));
+        JB_CK(cudaEventCreateWithFlags(&p->ev_c[e], cudaEventDisableTiming));
+    }
+    if (!p->ev_start) JB_CK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+    return 0;
+}
+static int ensure_comm_stream(jubik_plan* p) {
+    if (p->st_comm) return 0;
+    JB_CK(cudaStreamCreateWithFlags(&p->st_comm, cudaStreamNonBlocking));
+    p->ev_bin = new cudaEvent_t[p->g.E]();
+    for (int e = 0; e < p->g.E; ++e) JB_CK(cudaEventCreateWithFlags(&p->ev_bin[e], cudaEventDisableTiming));
+    JB_CK(cudaEventCreateWithFlags(&p->ev_comm, cudaEventDisableTiming));
+    if (!p->ev_start) JB_CK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+    return 0;
+}
+// The two compute streams' planes are in different phases at the same time, and the forward / adjoint layouts of one
+// spectrum buffer alias across energy bins: the second stream gets its own pair of buffers (one sample's worth).
+static int ensure_second_workspace(jubik_plan* p) {
+    if (p->ws2_ready) return 0;
+    const JbGeom& g = p->g;
+    const size_t TE1 = (size_t)g.T * g.E, nn2 = (size_t)g.n * g.n;
+    const int brB = std::min(std::min(g.w, 64), g.N), brA = std::min(std::min(g.P, 64), g.N);
+    const size_t orows = g.fold ? g.L : g.P;
+    std::string err;
+    if ((!p->bufA2 && alloc(p, (void**)&p->bufA2, TE1 * nn2 * orows * g.PH * sizeof(cd), "second spectrum workspace A")) ||
+        (!p->bufB2 && alloc(p, (void**)&p->bufB2, TE1 * nn2 * (size_t)g.w * g.PH * sizeof(cd), "second spectrum workspace B")) ||
+        (!p->gbuf2 && alloc(p, (void**)&p->gbuf2, TE1 * (size_t)g.N * g.N * sizeof(double), "second cotangent workspace")))
+        return JUBIK_ERR_ALLOC;
+    if (p->use_pipe && (make_tile_src(&p->src_fwd2, p->bufB2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brB, &err) ||
+                        make_tile_src(&p->src_adj2, p->bufA2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brA, &err)))
+        return fail(JUBIK_ERR_CUDA, err);
+    p->ws2_ready = 1;
+    return 0;
+}
+#endif
+
+// Transform length.  P compiled in: the period is exactly P (reference semantics for any PSF).  Otherwise a larger
+// compiled length: the padded linear convolution when the PSF half-support s <= m, else (L >= w + 2s) the linear
+// convolution folded modulo P (alias fold, kernels.cuh).
+static int choose_length(const JbGeom& g, int support, int forced, int* L_out, int* fold_out, int* ext_out) {
+    const int need_fold = g.w + 2 * support;
+    int L = 0, fold = 0;
+    if (forced > 0) {
+        if (forced < g.P) return fail(JUBIK_ERR_ARG, "fft_length < P = 2*int(N/n) + 2*margin");
+        if (!find_ops(forced)) return fail(JUBIK_ERR_UNSUPPORTED, "fft_length " + std::to_string(forced) + " is not compiled in");
+        L = forced;
+        if (L != g.P && support > g.m) {
+            if (L < need_fold)
+                return fail(JUBIK_ERR_ARG, "fft_length " + std::to_string(L) + " is too short for the alias fold: the PSF half-support (" +
+                            std::to_string(support) + ") exceeds the margin, which needs L >= w + 2*support = " + std::to_string(need_fold));
+            fold = 1;
+        }
+    } else if (find_ops(g.P)) {
+        L = g.P;
+    } else if (support <= g.m) {
+        for (int c : k_lengths) if (c >= g.P && (L == 0 || c < L)) L = c;
+        if (!L) return fail(JUBIK_ERR_UNSUPPORTED, "no compiled FFT length >= P = " + std::to_string(g.P));
+    } else {
+        for (int c : k_lengths) if (c >= need_fold && c >= g.P && (L == 0 || c < L)) L = c;
+        if (!L)
+            return fail(JUBIK_ERR_UNSUPPORTED, "P = " + std::to_string(g.P) + " is not a compiled FFT length, the PSF half-support (" +
+                        std::to_string(support) + ") exceeds the margin (" + std::to_string(g.m) + "), and no compiled length >= w + 2*support = " +
+                        std::to_string(need_fold) + " exists for the period-P alias fold");
+        fold = 1;
+    }
+    *L_out = L; *fold_out = fold; *ext_out = fold ? support - g.m : 0;
+    return 0;
 }
 
 int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_) {
@@ -233,12 +346,15 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
     if (N - 2 * dx < 2) return fail(JUBIK_ERR_ARG, "kernel crop (N-2dx)//2 must be >= 1");
     jubik_plan* p = new (std::nothrow) jubik_plan();
     if (!p) return fail(JUBIK_ERR_ALLOC, "host allocation failed");
+    // every early return below goes through this guard: the plan owns all its temporaries, so nothing leaks
+    struct Guard { jubik_plan* p; ~Guard() { if (p) jubik_plan_destroy(p); } } guard{p};
     JbGeom& g = p->g;
     memset(&g, 0, sizeof(g));
     g.N = N; g.n = n; g.m = m; g.dx = dx; g.w = 2 * dx; g.hp = dx / 2; g.P = g.w + 2 * m;
     g.S = d->max_samples; g.T = d->n_modules; g.E = d->n_energy;
     g.e0 = 0; g.Es = g.E;
     p->S_max = d->max_samples;
+    p->flags = d->flags;
     // window starts with jax.lax.dynamic_slice clamping (convolve.py:55-57)
     {
         int frame = N + 2 * g.hp;
@@ -251,46 +367,16 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
     }
     const size_t nn2 = (size_t)n * n, TE = (size_t)g.T * g.E, STE = TE * p->S_max;
     int rc = 0;
-#define JB_TRY(expr) do { rc = (expr); if (rc) { jubik_plan_destroy(p); return rc; } } while (0)
-#define JB_TRYCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { jubik_plan_destroy(p); \
-        return fail(JUBIK_ERR_CUDA, std::string(#call) + " -> " + cuda_msg(e_)); } ++p->launches; } while (0)
+#define JB_TRY(expr) do { rc = (expr); if (rc) return rc; } while (0)
 
     // ---- PSF sums + support (decides the transform length)
     JbKsrc ks;
     ks.ptr = d->kernel; ks.cropped = (d->kernel_layout == JUBIK_KERNEL_CROPPED); ks.T = g.T; ks.E = g.E;
-    double* sums = nullptr;
-    int* supp = nullptr;
-    JB_TRY(alloc(p, (void**)&sums, TE * nn2 * sizeof(double), "psf sums"));
-    if (dev_malloc((void**)&supp, TE * nn2 * sizeof(int))) { dev_free(sums); jubik_plan_destroy(p); return fail(JUBIK_ERR_ALLOC, "psf support"); }
-    auto cleanup_tmp = [&]() { dev_free(sums); dev_free(supp); };
-    {
-        cudaError_t e = jb_launch(k_prep_sum, dim3((unsigned)nn2, (unsigned)TE), dim3(256), 256 * sizeof(double), st, g, ks, sums, supp);
-        if (e != cudaSuccess) { cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "k_prep_sum -> " + cuda_msg(e)); }
-        ++p->launches;
-        std::vector<int> hs(TE * nn2);
-        if (d2h(hs.data(), supp, hs.size() * sizeof(int), st) || stream_sync(st)) { cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "reading PSF support failed"); }
-        int mx = 0;
-        for (int v : hs) mx = v > mx ? v : mx;
-        p->support = mx;
-    }
-    // ---- transform length: exact period P if compiled in; else (compact PSF only) the next larger length
+    JB_TRY(alloc(p, (void**)&p->psums, TE * nn2 * sizeof(double), "psf sums"));
+    JB_TRY(alloc(p, (void**)&p->psupp, TE * nn2 * sizeof(int), "psf support"));
+    JB_TRY(psf_stats(p, ks, st));
     int L = 0;
-    if (d->fft_length > 0) {
-        if (d->fft_length < g.P) { cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_ARG, "fft_length < P = 2*int(N/n) + 2*margin"); }
-        if (!find_ops(d->fft_length)) { cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_UNSUPPORTED, "fft_length " + std::to_string(d->fft_length) + " is not compiled in"); }
-        L = d->fft_length;
-    } else if (find_ops(g.P)) {
-        L = g.P;
-    } else {
-        for (int c : k_lengths) if (c >= g.P && (L == 0 || c < L)) L = c;
-    }
-    if (L == 0) { cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_UNSUPPORTED, "no compiled FFT length >= P = " + std::to_string(g.P)); }
-    if (L != g.P && p->support > m) {
-        cleanup_tmp(); jubik_plan_destroy(p);
-        return fail(JUBIK_ERR_UNSUPPORTED, "P = " + std::to_string(g.P) + " is not a compiled FFT length and the PSF half-support (" +
-                    std::to_string(p->support) + ") exceeds the margin (" + std::to_string(m) +
-                    "): the reference's period-P wrap-around cannot be reproduced with a padded transform");
-    }
+    JB_TRY(choose_length(g, p->support, d->fft_length, &L, &g.fold, &g.ext));
     p->exact = (L == g.P);
     g.L = L; g.PH = L / 2 + 1;
     p->ops = find_ops(L);
@@ -323,29 +409,27 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
         }
         JB_TRY(alloc(p, (void**)&p->wgt, g.w * sizeof(double), "weights"));
         if (h2d(p->tw_nk, a.data(), L * sizeof(cd), st) || h2d(p->tw_kn, b.data(), L * sizeof(cd), st) ||
-            h2d(p->wgt, wv.data(), g.w * sizeof(double), st) || stream_sync(st)) {
-            cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "uploading twiddles failed");
-        }
+            h2d(p->wgt, wv.data(), g.w * sizeof(double), st) || stream_sync(st))
+            return fail(JUBIK_ERR_CUDA, "uploading twiddles failed");
     }
     // ---- workspace
     const size_t nstrips = (size_t)jb_cdiv(g.PH, o->CB);
+    const size_t orows = g.fold ? (size_t)L : (size_t)g.P;    // rows per patch of the forward column-pass output
     p->bytes_khat = TE * nn2 * nstrips * (size_t)L * o->CB * sizeof(cd);
-    size_t bA = STE * nn2 * (size_t)g.P * g.PH * sizeof(cd);
+    size_t bA = STE * nn2 * orows * g.PH * sizeof(cd);
     size_t bB = STE * nn2 * (size_t)g.w * g.PH * sizeof(cd);
     size_t bG = STE * (size_t)N * N * sizeof(double);
-    p->nblk_out = jb_cdiv(N, p->rpc_out);
-    p->split_epi = getenv("JUBIK_B200_FUSED_EPI") ? 0 : 1;
-    p->nblk_epi = jb_cdiv(N * N, 256 * 8);
-    if (p->nblk_epi > 1024) p->nblk_epi = 1024;
-    size_t bP = STE * (size_t)(p->nblk_out > p->nblk_epi ? p->nblk_out : p->nblk_epi) * sizeof(double);
-    if (bP < STE * (size_t)N * sizeof(double)) bP = STE * (size_t)N * sizeof(double);   // rows5: one partial per image row
+    size_t bP = STE * (size_t)N * sizeof(double);   // one energy partial per image row at most
     p->bytes_ws = bA + bB + bG + bP;
-    if (alloc(p, (void**)&p->khat, p->bytes_khat, "PSF spectra") || alloc(p, (void**)&p->bufA, bA, "spectrum workspace A") ||
-        alloc(p, (void**)&p->bufB, bB, "spectrum workspace B") || alloc(p, (void**)&p->gbuf, bG, "cotangent workspace") ||
-        alloc(p, (void**)&p->partial, bP, "energy partials")) {
-        std::string msg = g_err; cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_ALLOC, msg);
-    }
-    // ---- low-overhead row kernels need at most JB_MAXQ row-patches covering any image row
+    JB_TRY(alloc(p, (void**)&p->khat, p->bytes_khat, "PSF spectra"));
+    JB_TRY(alloc(p, (void**)&p->bufA, bA, "spectrum workspace A"));
+    JB_TRY(alloc(p, (void**)&p->bufB, bB, "spectrum workspace B"));
+    JB_TRY(alloc(p, (void**)&p->gbuf, bG, "cotangent workspace"));
+    JB_TRY(alloc(p, (void**)&p->partial, bP, "energy partials"));
+    // ---- which kernels: the fast path (TMA column pipeline + warp-private c2r rows + prefetching r2c rows) needs a
+    // three-stage length, at most JB_MAXQ row-patches covering any image row and no alias fold; everything else runs
+    // the generic kernels of kernels.cuh (same maths, any geometry).  No environment switches: the plan is a pure
+    // function of its descriptor.
     {
         int mx = 0;
         for (int r = 0; r < N; ++r) {
@@ -358,11 +442,10 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
             mx = c0 > mx ? c0 : mx;
             mx = c1 > mx ? c1 : mx;
         }
-        p->fast_rows = (o->R2 > 1) && mx <= JB_MAXQ && !getenv("JUBIK_B200_ROWS_V1");
         p->qmax = mx;
+        p->fast_rows = (o->R2 > 1) && mx <= JB_MAXQ && !g.fold;
     }
-    // ---- pipelined column pass: TMA views of the two spectrum workspaces
-    p->use_pipe = getenv("JUBIK_B200_COLS_V1") ? 0 : o->pipe;
+    p->use_pipe = g.fold ? 0 : o->pipe;
     if (p->use_pipe == 2) {
         const int Q1 = o->q1, Q2 = o->q2, Q3 = o->q3, M = Q2 * Q3;
         std::vector<cd> a((size_t)L), b((size_t)M);
@@ -377,22 +460,12 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
                 long double ang = -two_pi * (long double)(((long long)k2 * n3) % M) / (long double)M;
                 b[(size_t)k2 * Q3 + n3] = cd_make((double)cosl(ang), (double)sinl(ang));
             }
-        if (alloc(p, (void**)&p->tw1, L * sizeof(cd), "twiddles") || alloc(p, (void**)&p->tw2, M * sizeof(cd), "twiddles") ||
-            h2d(p->tw1, a.data(), L * sizeof(cd), st) || h2d(p->tw2, b.data(), M * sizeof(cd), st) || stream_sync(st)) {
-            cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "uploading three-stage twiddles failed");
-        }
+        JB_TRY(alloc(p, (void**)&p->tw1, L * sizeof(cd), "twiddles"));
+        JB_TRY(alloc(p, (void**)&p->tw2, M * sizeof(cd), "twiddles"));
+        if (h2d(p->tw1, a.data(), L * sizeof(cd), st) || h2d(p->tw2, b.data(), M * sizeof(cd), st) || stream_sync(st))
+            return fail(JUBIK_ERR_CUDA, "uploading three-stage twiddles failed");
     }
-    if (p->use_pipe && p->fast_rows && !getenv("JUBIK_B200_ROWS_V2")) {
-        const size_t smem_max = 227 * 1024;
-        p->rows_pipe_out = o->rows_out_pipe_smem(g, p->qmax) <= smem_max;
-        p->rows_pipe_adj = o->rows_adj_out_pipe_smem(g, p->qmax) <= smem_max;
-        if (p->use_pipe == 2 && !getenv("JUBIK_B200_ROWS_V3")) {
-            // two CTAs per SM: each may use half of the 227 KB (minus the 1 KB per-CTA reservation)
-            p->rows_r3_out = o->rows_out_r3_smem(g, p->qmax) <= smem_max / 2 - 1024;
-            p->rows_r3_adj = o->rows_adj_out_r3_smem(g, p->qmax) <= smem_max / 2 - 1024;
-        }
-    }
-    if (p->use_pipe == 2 && p->qmax <= JB_MAXQ && !getenv("JUBIK_B200_ROWS_V4"))
+    if (p->use_pipe == 2 && p->qmax <= JB_MAXQ)
         p->rows5 = o->rows5_smem(g) <= (size_t)227 * 1024 - 1024;
     if (p->rows5) {
         std::vector<int> tf((size_t)JB_MAXQ * N), ta((size_t)JB_MAXQ * N);
@@ -400,32 +473,18 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
         p->gq_adj = o->rows5_gather(g, 1, JB_MAXQ, ta.data());
         if (p->gq_fwd < 1 || p->gq_adj < 1) {
             p->rows5 = 0;
-        } else if (alloc(p, (void**)&p->gtab_fwd, tf.size() * sizeof(int), "gather table") ||
-                   alloc(p, (void**)&p->gtab_adj, ta.size() * sizeof(int), "gather table") ||
-                   h2d(p->gtab_fwd, tf.data(), tf.size() * sizeof(int), st) ||
-                   h2d(p->gtab_adj, ta.data(), ta.size() * sizeof(int), st) || stream_sync(st)) {
-            cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "uploading gather tables failed");
+        } else {
+            JB_TRY(alloc(p, (void**)&p->gtab_fwd, tf.size() * sizeof(int), "gather table"));
+            JB_TRY(alloc(p, (void**)&p->gtab_adj, ta.size() * sizeof(int), "gather table"));
+            if (h2d(p->gtab_fwd, tf.data(), tf.size() * sizeof(int), st) ||
+                h2d(p->gtab_adj, ta.data(), ta.size() * sizeof(int), st) || stream_sync(st))
+                return fail(JUBIK_ERR_CUDA, "uploading gather tables failed");
         }
     }
-    p->chunk_e = getenv("JUBIK_B200_CHUNK_E") ? 1 : 0;
-    p->dev_planes = getenv("JUBIK_B200_DEV_PLANES") ? 1 : 0;
-    p->cols_pp = (!p->sweep && getenv("JUBIK_B200_COLS_PP")) ? 1 : 0;
-    // warp-private r2c kernels: parity-tested, but measured slower than the two-pass kernels of rows_fast.cuh on B200
-    // (forward 69 vs 36 us -- the two-pass kernel skips the zero padding --, adjoint 58 vs 57 us): opt-in
-    p->rows6 = (p->rows5 && getenv("JUBIK_B200_ROWS_R2C_V6") && o->rows6_smem(g) <= (size_t)227 * 1024 - 1024) ? 1 : 0;
-    // measured on B200 (C2): the read-add-write costs the column pass more (+48 us per direction) than the row pass
-    // gains from reading one summed row (-22 / -13 us), so the sweep stays an opt-in experiment
-    p->sweep = (p->rows5 && getenv("JUBIK_B200_SWEEP")) ? 1 : 0;
-    if (p->rows5 && !getenv("JUBIK_B200_SPLIT_EPI")) { p->split_epi = 0; p->nblk_out = N; }   // fused epilogue: one partial per row
-    // fused final reduction (last CTA of the forward c2r kernel sums the partials): measured equal to the separate
-    // 8 us k_reduce_energy launch (the lone last CTA adds the same tail), so it stays opt-in
-    if (p->rows5 && !p->split_epi && getenv("JUBIK_B200_FUSED_REDUCE")) {
-        unsigned zero = 0;
-        if (alloc(p, (void**)&p->counter, sizeof(unsigned), "reduction counter") || h2d(p->counter, &zero, sizeof(zero), st) ||
-            stream_sync(st)) {
-            cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "allocating the reduction counter failed");
-        }
-    }
+    p->nblk_out = p->rows5 ? N : jb_cdiv(N, p->rpc);
+    if (!p->rows5 && o->rows_generic_smem(g, p->rpc, p->thr_rows) > (size_t)227 * 1024)
+        return fail(JUBIK_ERR_UNSUPPORTED, "this geometry needs the generic row kernels (alias fold, or a transform length without the "
+                                           "three-stage pipeline) and their shared-memory tile exceeds 227 KB: use fewer patches per axis");
     if (p->use_pipe) {
         std::string err;
         int brB = g.w < 64 ? g.w : 64, brA = g.P < 64 ? g.P : 64;
@@ -433,45 +492,76 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
         if (brA > N) brA = N;
         // the row-spectrum buffers (slabs = planes*n, N rows, PH) live in the first part of bufB (forward) / bufA (adjoint)
         if (make_tile_src(&p->src_fwd, p->bufB, STE * (size_t)n, N, g.PH, o->CB, brB, &err) ||
-            make_tile_src(&p->src_adj, p->bufA, STE * (size_t)n, N, g.PH, o->CB, brA, &err)) {
-            cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, err);
-        }
+            make_tile_src(&p->src_adj, p->bufA, STE * (size_t)n, N, g.PH, o->CB, brA, &err))
+            return fail(JUBIK_ERR_CUDA, err);
+    }
 #ifndef JB_EMU
+    {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         p->n_sm = sms > 0 ? sms : 148;
+    }
 #else
-        p->n_sm = 2;
+    p->n_sm = 2;
+#endif
+    JB_TRY(psf_spectra(p, ks, st));
+    if (stream_sync(st)) return fail(JUBIK_ERR_CUDA, "PSF spectrum kernels failed");
+    // ---- optional staging, all of it allocated HERE (no allocation after plan creation)
+    if (p->flags & JUBIK_PLAN_METRIC) JB_TRY(alloc(p, (void**)&p->fac, bG, "metric linearisation point"));
+    if (p->flags & JUBIK_PLAN_SHARDED)
+        JB_TRY(alloc(p, (void**)&p->gstage, (size_t)p->S_max * g.E * N * N * sizeof(double), "per-sample gradient staging"));
+    if (p->flags & JUBIK_PLAN_HOST_CALL) {
+        const size_t bx = (size_t)p->S_max * g.E * N * N * sizeof(double);
+        JB_TRY(alloc(p, (void**)&p->xdev, bx, "host-call staging x"));
+        JB_TRY(alloc(p, (void**)&p->gdev, bx, "host-call staging grad"));
+        JB_TRY(alloc(p, (void**)&p->edev, p->S_max * sizeof(double), "host-call staging energy"));
+#ifndef JB_EMU
+        JB_TRY(ensure_plane_streams(p));
+        if (p->S_max * g.E > 1) JB_TRY(ensure_second_workspace(p));
 #endif
     }
-    // ---- PSF spectra: rows r2c -> columns FFT -> normalise -> resident in k_cols' register order
-    {
-        int prpc = 8;
-        int items = prpc * (o->R2 > 1 ? (o->R2 > o->R1 / 2 + 1 ? o->R2 : o->R1 / 2 + 1) : 1);
-        int thr = ((items + 31) / 32) * 32; if (thr < 32) thr = 32; if (thr > 256) thr = 256;
-        cudaError_t e = o->prep_rows(g, ks, p->tw_nk, p->bufB, prpc, thr, st);
-        if (e == cudaSuccess) { ++p->launches; e = o->prep_cols(g, p->bufB, sums, p->use_pipe == 2 ? p->tw1 : p->tw_nk, p->tw2, p->khat, p->use_pipe == 2 ? 2 : 0, p->thr_cols, st); }
-        if (e == cudaSuccess) ++p->launches;
-        if (e != cudaSuccess || stream_sync(st)) { cleanup_tmp(); jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "PSF spectrum kernels -> " + cuda_msg(e)); }
-    }
-    p->bytes_total -= TE * nn2 * sizeof(double);
-    cleanup_tmp();
+#ifndef JB_EMU
+    if (p->flags & JUBIK_PLAN_SHARDED) JB_TRY(ensure_comm_stream(p));
+#endif
     // ---- exposure / mask / data
     if (d->exposure) {
         size_t tot = TE * (size_t)N * N;
         JB_TRY(alloc(p, (void**)&p->expo, tot * sizeof(double), "exposure"));
-        JB_TRYCK(jb_launch(k_prep_expo, dim3(592), dim3(256), 0, st, d->exposure, d->eff_area, d->exposure_cut,
-                           (int)(d->has_exposure_cut != 0), d->pixel_area, (size_t)N * N, tot, p->expo));
+        cudaError_t e = jb_launch(k_prep_expo, dim3(592), dim3(256), 0, st, d->exposure, d->eff_area, d->exposure_cut,
+                                  (int)(d->has_exposure_cut != 0), d->pixel_area, (size_t)N * N, tot, p->expo);
+        if (e != cudaSuccess) return fail(JUBIK_ERR_CUDA, "k_prep_expo -> " + cuda_msg(e));
+        ++p->launches;
         p->has_expo = 1;
     }
-    if (d->data) {
-        rc = jubik_plan_set_data(p, d->data, d->data_dtype, stream_);
-        if (rc) { jubik_plan_destroy(p); return rc; }
-    }
-    if (stream_sync(st)) { jubik_plan_destroy(p); return fail(JUBIK_ERR_CUDA, "plan creation: stream sync failed"); }
+    if (d->data) JB_TRY(jubik_plan_set_data(p, d->data, d->data_dtype, stream_));
+    if (stream_sync(st)) return fail(JUBIK_ERR_CUDA, "plan creation: stream sync failed");
+    guard.p = nullptr;
     *out = p;
     return JUBIK_OK;
+}
+
+int jubik_plan_set_kernel(jubik_plan* p, const double* kernel, int kernel_layout, void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (!p || !kernel) return fail(JUBIK_ERR_ARG, "null plan/kernel");
+    JbGeom& g = p->g;
+    JbKsrc ks;
+    ks.ptr = kernel; ks.cropped = (kernel_layout == JUBIK_KERNEL_CROPPED); ks.T = g.T; ks.E = g.E;
+    const int old_support = p->support;
+    if (int rc = psf_stats(p, ks, st)) return rc;
+    if (!p->exact) {
+        // a padded transform stays exact only while the new PSF fits the plan's choice
+        const bool ok = g.fold ? (g.L >= g.w + 2 * p->support) : (p->support <= g.m);
+        if (!ok) {
+            const int s_new = p->support;
+            p->support = old_support;
+            return fail(JUBIK_ERR_UNSUPPORTED, "the new PSF's half-support (" + std::to_string(s_new) + ") does not fit this plan's "
+                        "transform length " + std::to_string(g.L) + " (P = " + std::to_string(g.P) + "): create a new plan");
+        }
+        if (g.fold) g.ext = p->support > g.m ? p->support - g.m : 0;
+    }
+    p->point_S = 0;    // a cached linearisation point belongs to the old response
+    return psf_spectra(p, ks, st);
 }
 
 int jubik_plan_set_data(jubik_plan* p, const void* data, int dtype, void* stream_) {
@@ -500,6 +590,9 @@ int jubik_plan_get_info(const jubik_plan* p, jubik_plan_info* i) {
     i->N = g.N; i->n = g.n; i->m = g.m; i->dx = g.dx; i->w = g.w; i->P = g.P; i->L = g.L; i->PH = g.PH;
     i->S_max = p->S_max; i->T = g.T; i->E = g.E; i->exact_period = p->exact; i->psf_half_support = p->support;
     i->fft_r1 = p->ops->R1; i->fft_r2 = p->ops->R2; i->col_block = p->ops->CB;
+    i->alias_fold = g.fold; i->alias_ext = g.ext;
+    i->fast_path = (p->use_pipe == 2 && p->rows5 && p->fast_rows) ? 1 : 0;
+    i->flags = p->flags;
     i->bytes_khat = p->bytes_khat; i->bytes_workspace = p->bytes_ws; i->bytes_total = p->bytes_total;
     return JUBIK_OK;
 }
@@ -513,62 +606,47 @@ static int check_call(jubik_plan* p, const void* a, const void* b, int S) {
     return 0;
 }
 
-// forward chain with the chosen epilogue
-// `g` may be a copy of p->g restricted to an energy-bin chunk (e0, Es)
-static int run_forward_g(jubik_plan* p, const JbGeom& g, const double* x, int S, const JbEpi& ep, jb_stream_t st) {
+// forward chain with the chosen epilogue; `g` may be a copy of p->g restricted to an energy-bin chunk (e0, Es);
+// exp_in: x holds log_sky and the r2c row kernel forms exp(log_sky) on the fly
+static int run_forward_g(jubik_plan* p, const JbGeom& g, const double* x, int S, const JbEpi& ep, int exp_in, jb_stream_t st) {
     const JbFftOps* o = p->ops;
-    if (p->rows6) {
-        JB_LAUNCHED(p, o->rows6(g, 0, x, nullptr, p->wgt, p->tw1, p->tw2, p->bufB, S * g.Es, p->n_sm, st));
-    } else {
-        JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.Es, p->rpc_in, p->thr_rows, p->fast_rows, st));
-    }
+    JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.Es, p->rpc, p->thr_rows, p->fast_rows, exp_in, st));
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, false, p->cols_pp ? 2 : p->sweep, p->src_fwd, p->bufA, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, false, p->src_fwd, p->bufA, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
     if (p->rows5) {
-        JB_LAUNCHED(p, o->rows5_fwd(g, p->bufA, p->tw1, p->tw2, p->gtab_fwd, p->gq_fwd, ep, p->sweep, S * g.T * g.Es, p->n_sm, st));
-    } else if (p->rows_r3_out && ep.mode != JB_EPI_POISSON) {
-        JB_LAUNCHED(p, o->rows_out_r3(g, p->bufA, p->tw1, p->tw2, ep, S * g.T * g.Es, p->qmax, p->n_sm, st));
-    } else if (p->rows_pipe_out && ep.mode != JB_EPI_POISSON) {
-        JB_LAUNCHED(p, o->rows_out_pipe(g, p->bufA, p->tw_kn, ep, S * g.T * g.Es, p->qmax, p->n_sm, st));
+        JB_LAUNCHED(p, o->rows5_fwd(g, p->bufA, p->tw1, p->tw2, p->gtab_fwd, p->gq_fwd, ep, S * g.T * g.Es, p->n_sm, st));
     } else {
-        JB_LAUNCHED(p, o->rows_out(g, p->bufA, p->tw_kn, ep, S * g.T * g.Es, p->rpc_out, p->thr_rows, p->fast_rows, st));
+        JB_LAUNCHED(p, o->rows_out(g, p->bufA, p->tw_kn, ep, S * g.T * g.Es, p->rpc, p->thr_rows, p->fast_rows, st));
     }
     return 0;
 }
 static int run_forward(jubik_plan* p, const double* x, int S, const JbEpi& ep, jb_stream_t st) {
-    return run_forward_g(p, p->g, x, S, ep, st);
+    return run_forward_g(p, p->g, x, S, ep, 0, st);
 }
 
-// adjoint chain; expo != nullptr multiplies the incoming cotangent by the effective exposure
+// adjoint chain; expo != nullptr multiplies the incoming cotangent by the effective exposure; logsky != nullptr
+// multiplies the outgoing gradient by exp(log_sky) (VJP of the sky-model tail)
 static int run_adjoint_g(jubik_plan* p, const JbGeom& g, const double* gin, const double* expo, int S, double* out,
-                         jb_stream_t st) {
+                         const double* logsky, jb_stream_t st) {
     const JbFftOps* o = p->ops;
-    if (p->rows6) {
-        JB_LAUNCHED(p, o->rows6(g, 1, gin, expo, p->wgt, p->tw1, p->tw2, p->bufA, S * g.T * g.Es, p->n_sm, st));
-    } else {
-        JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.Es, p->rpc_in, p->thr_rows, p->fast_rows, st));
-    }
+    JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.Es, p->rpc, p->thr_rows, p->fast_rows, st));
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, true, p->cols_pp ? 2 : p->sweep, p->src_adj, p->bufB, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, true, p->src_adj, p->bufB, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
     if (p->rows5) {
-        JB_LAUNCHED(p, o->rows5_adj(g, p->bufB, p->wgt, p->tw1, p->tw2, p->gtab_adj, p->gq_adj, out, p->sweep, S * g.Es, p->n_sm, st));
-    } else if (p->rows_r3_adj) {
-        JB_LAUNCHED(p, o->rows_adj_out_r3(g, p->bufB, p->wgt, p->tw1, p->tw2, out, S * g.Es, p->qmax, p->n_sm, st));
-    } else if (p->rows_pipe_adj) {
-        JB_LAUNCHED(p, o->rows_adj_out_pipe(g, p->bufB, p->wgt, p->tw_kn, out, S * g.Es, p->qmax, p->n_sm, st));
+        JB_LAUNCHED(p, o->rows5_adj(g, p->bufB, p->wgt, p->tw1, p->tw2, p->gtab_adj, p->gq_adj, out, logsky, S * g.Es, p->n_sm, st));
     } else {
-        JB_LAUNCHED(p, o->rows_adj_out(g, p->bufB, p->wgt, p->tw_kn, out, S * g.Es, p->rpc_out, p->thr_rows, p->fast_rows, st));
+        JB_LAUNCHED(p, o->rows_adj_out(g, p->bufB, p->wgt, p->tw_kn, out, logsky, S * g.Es, p->rpc, p->thr_rows, p->fast_rows, st));
     }
     return 0;
 }
 static int run_adjoint(jubik_plan* p, const double* gin, const double* expo, int S, double* out, jb_stream_t st) {
-    return run_adjoint_g(p, p->g, gin, expo, S, out, st);
+    return run_adjoint_g(p, p->g, gin, expo, S, out, nullptr, st);
 }
 
 int jubik_psf_apply(jubik_plan* p, const double* x, int S, double* out, void* stream_) {
@@ -597,40 +675,35 @@ int jubik_response_apply_T(jubik_plan* p, const double* gin, int S, double* out,
     return run_adjoint(p, gin, p->expo, S, out, (jb_stream_t)stream_);
 }
 
+static int reduce_energy(jubik_plan* p, int S, double* energy, jb_stream_t st) {
+    JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st, (const double*)p->partial,
+                             p->g.T * p->g.E * p->nblk_out, energy));
+    return 0;
+}
+
+// fused energy + gradient of sum(lambda) - d log(lambda); logsky: x holds log_sky (exp on load, * exp(log_sky) on store)
+static int energy_and_grad_impl(jubik_plan* p, const double* x, int S, double* energy, double* grad, bool logsky, jb_stream_t st) {
+    if (!p->has_expo || !p->has_data) return fail(JUBIK_ERR_ARG, "plan needs exposures and data for the Poisson energy");
+    JbEpi ep; memset(&ep, 0, sizeof(ep));
+    ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
+    if (int rc = run_forward_g(p, p->g, x, S, ep, logsky ? 1 : 0, st)) return rc;
+    if (int rc = reduce_energy(p, S, energy, st)) return rc;
+    if (grad) return run_adjoint_g(p, p->g, p->gbuf, nullptr, S, grad, logsky ? x : nullptr, st);
+    return JUBIK_OK;
+}
+
+int jubik_poisson_energy_and_grad(jubik_plan* p, const double* x, int S, double* energy, double* grad, void* stream_) {
+    if (int rc = check_call(p, x, energy, S)) return rc;
+    return energy_and_grad_impl(p, x, S, energy, grad, false, (jb_stream_t)stream_);
+}
+
+int jubik_poisson_energy_and_grad_logsky(jubik_plan* p, const double* log_sky, int S, double* energy, double* grad,
+                                         void* stream_) {
+    if (int rc = check_call(p, log_sky, energy, S)) return rc;
+    return energy_and_grad_impl(p, log_sky, S, energy, grad, true, (jb_stream_t)stream_);
+}
+
 #ifndef JB_EMU
-// streams / events of the plane-pipelined call forms (first use)
-static int ensure_plane_streams(jubik_plan* p) {
-    if (p->st_in) return 0;
-    const int nev = p->S_max * p->g.E;
-    JB_CK(cudaStreamCreateWithFlags(&p->st_in, cudaStreamNonBlocking));
-    JB_CK(cudaStreamCreateWithFlags(&p->st_out, cudaStreamNonBlocking));
-    JB_CK(cudaStreamCreateWithFlags(&p->st_c2, cudaStreamNonBlocking));
-    p->ev_in = new cudaEvent_t[nev]; p->ev_c = new cudaEvent_t[nev];
-    for (int e = 0; e < nev; ++e) {
-        JB_CK(cudaEventCreateWithFlags(&p->ev_in[e], cudaEventDisableTiming));
-        JB_CK(cudaEventCreateWithFlags(&p->ev_c[e], cudaEventDisableTiming));
-    }
-    JB_CK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
-    return 0;
-}
-// The two compute streams' planes are in different phases at the same time, and the forward / adjoint layouts of one
-// spectrum buffer alias across energy bins: the second stream gets its own pair of buffers (one sample's worth).
-static int ensure_second_workspace(jubik_plan* p) {
-    if (p->ws2_ready) return 0;
-    const JbGeom& g = p->g;
-    const size_t TE1 = (size_t)g.T * g.E, nn2 = (size_t)g.n * g.n;
-    const int brB = std::min(std::min(g.w, 64), g.N), brA = std::min(std::min(g.P, 64), g.N);
-    std::string err;
-    if ((!p->bufA2 && alloc(p, (void**)&p->bufA2, TE1 * nn2 * (size_t)g.P * g.PH * sizeof(cd), "second spectrum workspace A")) ||
-        (!p->bufB2 && alloc(p, (void**)&p->bufB2, TE1 * nn2 * (size_t)g.w * g.PH * sizeof(cd), "second spectrum workspace B")) ||
-        (!p->gbuf2 && alloc(p, (void**)&p->gbuf2, TE1 * (size_t)g.N * g.N * sizeof(double), "second cotangent workspace")))
-        return JUBIK_ERR_ALLOC;
-    if (make_tile_src(&p->src_fwd2, p->bufB2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brB, &err) ||
-        make_tile_src(&p->src_adj2, p->bufA2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brA, &err))
-        return fail(JUBIK_ERR_CUDA, err);
-    p->ws2_ready = 1;
-    return 0;
-}
 // kernel arguments are captured at launch, so the second stream's launches simply see the plan with its workspace
 // pointers exchanged while they are enqueued
 static void swap_workspace(jubik_plan* p) {
@@ -638,9 +711,8 @@ static void swap_workspace(jubik_plan* p) {
     std::swap(p->src_fwd, p->src_fwd2); std::swap(p->src_adj, p->src_adj2);
     std::swap(p->gbuf, p->gbuf2);
 }
-// Fused energy + gradient as (sample, energy bin) planes alternating between the caller's stream and a second one
-// (device-resident form of the host entry point's pipeline).  wait_in: per-plane events to wait for (H2D), or null;
-// after_plane(c, stream): hook after a plane's kernels were enqueued (the host path issues the D2H there).
+// Fused energy + gradient as (sample, energy bin) planes alternating between the caller's stream and a second one.
+// wait_in: wait for the per-plane H2D events; after_plane(c): hook after a plane's kernels were enqueued (D2H).
 static int run_planes_two_streams(jubik_plan* p, const double* x, int S, double* grad, bool two, bool wait_in,
                                   jb_stream_t st, const std::function<int(int)>& after_plane) {
     const JbGeom& g = p->g;
@@ -648,107 +720,39 @@ static int run_planes_two_streams(jubik_plan* p, const double* x, int S, double*
     if (two) JB_CK(cudaStreamWaitEvent(p->st_c2, p->ev_start, 0));
     // One (sample, energy bin) plane per chunk.  With two streams every stream owns its spectrum buffers AND its
     // cotangent scratch, so chunks on different streams never touch the same memory; chunks on one stream are ordered
-    // by the stream.  JUBIK_B200_HOST_PAIR_PLANES=1 pairs up the planes between the first and the last one (fuller
-    // waves for the persistent kernels) -- measured slower end to end (1.88 vs 1.61 ms at C2, S = 2: the coarser
-    // chunks start later and return their gradients later), kept as a tested option.
+    // by the stream.
     const int nplanes = S * g.E;
-    const bool pair_up = two && getenv("JUBIK_B200_HOST_PAIR_PLANES");
-    int last_c2 = -1, k = 0;
-    for (int c = 0; c < nplanes; ++k) {
+    int last_c2 = -1;
+    for (int c = 0; c < nplanes; ++c) {
         const int si = c / g.E, e = c - si * g.E;
-        int len = 1;
-        if (pair_up && c > 0 && e + 1 < g.E && c + 1 < nplanes - 1) len = 2;
-        jb_stream_t cs = (two && (k & 1)) ? (jb_stream_t)p->st_c2 : st;
-        const int cl = c + len - 1;     // last plane of the chunk: its event stands for the chunk
-        if (cs != st) last_c2 = cl;
+        jb_stream_t cs = (two && (c & 1)) ? (jb_stream_t)p->st_c2 : st;
+        if (cs != st) last_c2 = c;
         JbGeom ge = g;
-        ge.e0 = e; ge.Es = len;
-        if (wait_in) for (int q = c; q <= cl; ++q) JB_CK(cudaStreamWaitEvent(cs, p->ev_in[q], 0));
+        ge.e0 = e; ge.Es = 1;
+        if (wait_in) JB_CK(cudaStreamWaitEvent(cs, p->ev_in[c], 0));
         JbEpi ep; memset(&ep, 0, sizeof(ep));
         if (cs != st) swap_workspace(p);
         ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data;
         ep.partial = p->partial + (size_t)si * g.T * g.E * p->nblk_out;
         // the chunk runs as "sample 0" of a one-sample batch on this sample's slices of x / grad / partials
-        int rc = run_forward_g(p, ge, x + (size_t)si * g.E * npx, 1, ep, cs);
-        if (!rc) rc = run_adjoint_g(p, ge, p->gbuf, nullptr, 1, grad + (size_t)si * g.E * npx, cs);
+        int rc = run_forward_g(p, ge, x + (size_t)si * g.E * npx, 1, ep, 0, cs);
+        if (!rc) rc = run_adjoint_g(p, ge, p->gbuf, nullptr, 1, grad + (size_t)si * g.E * npx, nullptr, cs);
         if (cs != st) swap_workspace(p);
         if (rc) return rc;
-        for (int q = c; q <= cl; ++q) {
-            JB_CK(cudaEventRecord(p->ev_c[q], cs));
-            if (int rc2 = after_plane(q)) return rc2;
-        }
-        c += len;
+        JB_CK(cudaEventRecord(p->ev_c[c], cs));
+        if (int rc2 = after_plane(c)) return rc2;
     }
     if (last_c2 >= 0) JB_CK(cudaStreamWaitEvent(st, p->ev_c[last_c2], 0));   // join before the energy reduction
     return 0;
 }
 #endif
 
-int jubik_poisson_energy_and_grad(jubik_plan* p, const double* x, int S, double* energy, double* grad, void* stream_) {
-    jb_stream_t st = (jb_stream_t)stream_;
-    if (int rc = check_call(p, x, energy, S)) return rc;
-    if (!p->has_expo || !p->has_data) return fail(JUBIK_ERR_ARG, "plan needs exposures and data for the Poisson energy");
-    const JbGeom& g = p->g;
-    JbEpi ep; memset(&ep, 0, sizeof(ep));
-#ifndef JB_EMU
-    if (p->dev_planes && grad && !p->split_epi && p->rows5 && p->use_pipe && !p->counter && S * g.E > 1 && !p->prof_on) {
-        // JUBIK_B200_DEV_PLANES=1 (experiment): one (sample, energy bin) plane at a time on two alternating streams,
-        // so that a plane's spectra are still L2-resident when its next kernel reads them
-        if (int rc = ensure_plane_streams(p)) return rc;
-        if (int rc = ensure_second_workspace(p)) return rc;
-        JB_CK(cudaEventRecord(p->ev_start, st));
-        if (int rc = run_planes_two_streams(p, x, S, grad, true, false, st, [](int) { return 0; })) return rc;
-        JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
-                                 (const double*)p->partial, g.T * g.E * p->nblk_out, energy));
-        return JUBIK_OK;
-    }
-#endif
-    if (p->chunk_e && !p->split_epi && grad && g.E > 1) {
-        // one energy bin at a time, forward then adjoint: the bin's spectra (column-pass output -> row pass) and its
-        // cotangent plane are still L2-resident when the next kernel reads them
-        ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
-        for (int e = 0; e < g.E; ++e) {
-            JbGeom ge = g;
-            ge.e0 = e; ge.Es = 1;
-            if (p->counter && e == g.E - 1) {
-                ep.energy = energy; ep.counter = p->counter; ep.n_samples = S; ep.per_sample = g.T * g.E * p->nblk_out;
-            }
-            if (int rc = run_forward_g(p, ge, x, S, ep, st)) return rc;
-            if (int rc = run_adjoint_g(p, ge, p->gbuf, nullptr, S, grad, st)) return rc;
-        }
-        if (!p->counter)
-            JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
-                                     (const double*)p->partial, g.T * g.E * p->nblk_out, energy));
-        return JUBIK_OK;
-    }
-    if (p->split_epi) {
-        // convolved planes first, then the Poisson epilogue as a separate full-occupancy elementwise pass
-        ep.mode = JB_EPI_PSF; ep.out = p->gbuf;
-        if (int rc = run_forward(p, x, S, ep, st)) return rc;
-        JB_LAUNCHED(p, jb_launch(k_poisson_epi, dim3(p->nblk_epi, S * g.T * g.E), dim3(256), 256 * sizeof(double), st,
-                                 g, p->gbuf, (const double*)p->expo, (const double*)p->data, g.N * g.N, p->partial));
-        JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
-                                 (const double*)p->partial, g.T * g.E * p->nblk_epi, energy));
-    } else {
-        ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
-        if (p->counter) {
-            ep.energy = energy; ep.counter = p->counter; ep.n_samples = S; ep.per_sample = g.T * g.E * p->nblk_out;
-        }
-        if (int rc = run_forward(p, x, S, ep, st)) return rc;
-        if (!p->counter)
-            JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
-                                     (const double*)p->partial, g.T * g.E * p->nblk_out, energy));
-    }
-    if (grad) return run_adjoint(p, p->gbuf, nullptr, S, grad, st);
-    return JUBIK_OK;
-}
-
 // Same work as jubik_poisson_energy_and_grad with a CUDA event after every kernel; ms_out[0..*n_out) in launch
-// order: rows_fwd, cols_fwd, rows_out, [poisson_epi,] reduce, rows_adj_in, cols_adj, rows_adj_out.  Synchronises.
+// order: rows_fwd, cols_fwd, rows_out, reduce, rows_adj_in, cols_adj, rows_adj_out.  Synchronises.
 int jubik_poisson_profile(jubik_plan* p, const double* x, int S, double* energy, double* grad, float* ms_out, int* n_out, void* stream_) {
 #ifndef JB_EMU
     jb_stream_t st = (jb_stream_t)stream_;
-    if (!ms_out || !grad || !n_out) return fail(JUBIK_ERR_ARG, "null pointer");
+    if (!p || !ms_out || !grad || !n_out) return fail(JUBIK_ERR_ARG, "null pointer");
     for (int i = 0; i < 48; ++i) if (!p->prof_ev[i]) JB_CK(cudaEventCreate(&p->prof_ev[i]));
     p->prof_on = 1; p->prof_n = 0;
     jb_mark(p, st);
@@ -807,62 +811,52 @@ int jubik_measure_fp64_tflops(double* tflops_out, void* stream_) {
 #endif
 }
 
-int jubik_poisson_metric_apply(jubik_plan* p, const double* x, const double* v, int S, double* out, void* stream_) {
-    jb_stream_t st = (jb_stream_t)stream_;
-    if (int rc = check_call(p, x, out, S)) return rc;
-    if (!v) return fail(JUBIK_ERR_ARG, "null array pointer");
+// ---- Fisher metric of the Poisson likelihood pulled back through R, with a cached linearisation point.
+// NIFTy's CG holds the position fixed for 60-70 metric applies per sample (eROSITA_demo.yaml:161): set_point runs ONE
+// forward pass that stores fac = expo^2 / lambda(x0) (0 where masked); every apply is then one forward (epilogue
+// out = fac * conv(v)) and one adjoint.
+int jubik_poisson_set_point(jubik_plan* p, const double* x, int S, void* stream_) {
+    if (int rc = check_call(p, x, x, S)) return rc;
     if (!p->has_expo) return fail(JUBIK_ERR_ARG, "plan was created without exposures");
-    const JbGeom& g = p->g;
-    if (!p->lbuf) {
-        size_t bG = (size_t)p->S_max * g.T * g.E * g.N * g.N * sizeof(double);
-        if (int rc = alloc(p, (void**)&p->lbuf, bG, "lambda workspace")) return rc;
-    }
+    if (!p->fac) return fail(JUBIK_ERR_ARG, "plan was created without JUBIK_PLAN_METRIC (no linearisation-point buffer)");
     JbEpi ep; memset(&ep, 0, sizeof(ep));
-    ep.mode = JB_EPI_RESP; ep.out = p->lbuf; ep.expo = p->expo;
-    if (int rc = run_forward(p, x, S, ep, st)) return rc;
-    if (p->split_epi) {
-        ep.mode = JB_EPI_PSF; ep.out = p->gbuf; ep.expo = nullptr;
-        if (int rc = run_forward(p, v, S, ep, st)) return rc;
-        JB_LAUNCHED(p, jb_launch(k_metric_epi, dim3(p->nblk_epi, S * g.T * g.E), dim3(256), 0, st, g, p->gbuf,
-                                 (const double*)p->expo, (const double*)p->lbuf, g.N * g.N));
-    } else {
-        ep.mode = JB_EPI_METRIC; ep.out = p->gbuf; ep.lam = p->lbuf;
-        if (int rc = run_forward(p, v, S, ep, st)) return rc;
-    }
+    ep.mode = JB_EPI_MFAC; ep.out = p->fac; ep.expo = p->expo;
+    if (int rc = run_forward(p, x, S, ep, (jb_stream_t)stream_)) return rc;
+    p->point_S = S;
+    return JUBIK_OK;
+}
+
+int jubik_poisson_metric_apply_at_point(jubik_plan* p, const double* v, int S, double* out, void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (int rc = check_call(p, v, out, S)) return rc;
+    if (!p->fac || p->point_S < 1) return fail(JUBIK_ERR_ARG, "no linearisation point: call jubik_poisson_set_point first");
+    if (S != p->point_S) return fail(JUBIK_ERR_ARG, "n_samples differs from the linearisation point's");
+    JbEpi ep; memset(&ep, 0, sizeof(ep));
+    ep.mode = JB_EPI_METRIC; ep.out = p->gbuf; ep.fac = p->fac;
+    if (int rc = run_forward(p, v, S, ep, st)) return rc;
     return run_adjoint(p, p->gbuf, nullptr, S, out, st);
+}
+
+int jubik_poisson_left_sqrt_metric_at_point(jubik_plan* p, const double* t, int S, double* out, void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (int rc = check_call(p, t, out, S)) return rc;
+    if (!p->fac || p->point_S < 1) return fail(JUBIK_ERR_ARG, "no linearisation point: call jubik_poisson_set_point first");
+    if (S != p->point_S) return fail(JUBIK_ERR_ARG, "n_samples differs from the linearisation point's");
+    const size_t cnt = (size_t)S * p->g.T * p->g.E * p->g.N * p->g.N;
+    JB_LAUNCHED(p, jb_launch(k_lsm_epi, dim3(1184), dim3(256), 0, st, t, (const double*)p->fac, p->gbuf, cnt));
+    return run_adjoint(p, p->gbuf, nullptr, S, out, st);
+}
+
+int jubik_poisson_metric_apply(jubik_plan* p, const double* x, const double* v, int S, double* out, void* stream_) {
+    if (!v) return fail(JUBIK_ERR_ARG, "null array pointer");
+    if (int rc = jubik_poisson_set_point(p, x, S, stream_)) return rc;
+    return jubik_poisson_metric_apply_at_point(p, v, S, out, stream_);
 }
 
 int jubik_poisson_left_sqrt_metric(jubik_plan* p, const double* x, const double* t, int S, double* out, void* stream_) {
-    jb_stream_t st = (jb_stream_t)stream_;
-    if (int rc = check_call(p, x, out, S)) return rc;
     if (!t) return fail(JUBIK_ERR_ARG, "null array pointer");
-    if (!p->has_expo) return fail(JUBIK_ERR_ARG, "plan was created without exposures");
-    const JbGeom& g = p->g;
-    if (!p->lbuf) {
-        size_t bG = (size_t)p->S_max * g.T * g.E * g.N * g.N * sizeof(double);
-        if (int rc = alloc(p, (void**)&p->lbuf, bG, "lambda workspace")) return rc;
-    }
-    JbEpi ep; memset(&ep, 0, sizeof(ep));
-    ep.mode = JB_EPI_RESP; ep.out = p->lbuf; ep.expo = p->expo;
-    if (int rc = run_forward(p, x, S, ep, st)) return rc;
-    JB_LAUNCHED(p, jb_launch(k_lsm_epi, dim3(p->nblk_epi, S * g.T * g.E), dim3(256), 0, st, g, t, (const double*)p->expo,
-                             (const double*)p->lbuf, p->gbuf, g.N * g.N));
-    return run_adjoint(p, p->gbuf, nullptr, S, out, st);
-}
-
-int jubik_poisson_energy_and_grad_logsky(jubik_plan* p, const double* log_sky, int S, double* energy, double* grad,
-                                         void* stream_) {
-    jb_stream_t st = (jb_stream_t)stream_;
-    if (int rc = check_call(p, log_sky, energy, S)) return rc;
-    const JbGeom& g = p->g;
-    const size_t cnt = (size_t)S * g.E * g.N * g.N;
-    if (!p->xexp) {
-        if (int rc = alloc(p, (void**)&p->xexp, (size_t)p->S_max * g.E * g.N * g.N * sizeof(double), "exp(log sky) workspace")) return rc;
-    }
-    JB_LAUNCHED(p, jb_launch(k_exp, dim3(1184), dim3(256), 0, st, log_sky, p->xexp, cnt));
-    if (int rc = jubik_poisson_energy_and_grad(p, p->xexp, S, energy, grad, stream_)) return rc;
-    if (grad) JB_LAUNCHED(p, jb_launch(k_mul_inplace, dim3(1184), dim3(256), 0, st, grad, (const double*)p->xexp, cnt));
-    return JUBIK_OK;
+    if (int rc = jubik_poisson_set_point(p, x, S, stream_)) return rc;
+    return jubik_poisson_left_sqrt_metric_at_point(p, t, S, out, stream_);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -979,67 +973,33 @@ int jubik_convolve(const double* x, const double* y, int lead, int x_lead, int n
 int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, double* eh, double* gh, void* stream_) {
     jb_stream_t st = (jb_stream_t)stream_;
     if (int rc = check_call(p, xh, eh, S)) return rc;
+    if (!p->xdev) return fail(JUBIK_ERR_ARG, "plan was created without JUBIK_PLAN_HOST_CALL (no staging buffers for host arrays)");
+    if (!p->has_expo || !p->has_data) return fail(JUBIK_ERR_ARG, "plan needs exposures and data for the Poisson energy");
     const JbGeom& g = p->g;
     const size_t npx = (size_t)g.N * g.N;
-    size_t bx = (size_t)p->S_max * g.E * npx * sizeof(double);
-    if (!p->xdev) {
-        if (alloc(p, (void**)&p->xdev, bx, "host-call staging x") || alloc(p, (void**)&p->gdev, bx, "host-call staging grad") ||
-            alloc(p, (void**)&p->edev, p->S_max * sizeof(double), "host-call staging energy"))
-            return JUBIK_ERR_ALLOC;
-    }
     size_t nx = (size_t)S * g.E * npx * sizeof(double);
 #ifndef JB_EMU
-    // Energy bins are independent through the whole fused chain, so the call is pipelined per bin: the H2D copy
-    // of bin e+1 and the D2H copy of the gradient of bin e-1 overlap the kernels of bin e (three streams).
-    const bool chunked = gh && (g.E > 1 || (S > 1 && !p->split_epi)) && (p->split_epi || p->rows5) && p->has_expo && p->has_data && !getenv("JUBIK_B200_HOST_SERIAL");
-    if (chunked) {
-        if (int rc = ensure_plane_streams(p)) return rc;
+    // (sample, energy bin) planes are independent through the whole fused chain, so the call is pipelined per plane:
+    // the H2D copy of plane c+1 and the D2H copy of the gradient of plane c-1 overlap the kernels of plane c.
+    if (gh && S * g.E > 1) {
         // the copy streams start after everything already queued on the caller's stream
         JB_CK(cudaEventRecord(p->ev_start, st));
         JB_CK(cudaStreamWaitEvent(p->st_in, p->ev_start, 0));
         JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_start, 0));
-        if (!p->split_epi) {
-            // one (sample, energy bin) plane per chunk: only the first plane's H2D and the last plane's D2H are exposed
-            const size_t plane_b = npx * sizeof(double);
-            for (int c = 0; c < S * g.E; ++c) {
-                JB_CK(cudaMemcpyAsync(p->xdev + (size_t)c * npx, xh + (size_t)c * npx, plane_b, cudaMemcpyHostToDevice, p->st_in));
-                JB_CK(cudaEventRecord(p->ev_in[c], p->st_in));
-            }
-            // Planes alternate between two compute streams: a one-plane launch leaves the persistent kernels with a
-            // ragged last wave (1024 rows on 888 resident CTAs), which the other stream's plane fills.
-            const bool two = !getenv("JUBIK_B200_HOST_ONE_STREAM") && S * g.E > 1 && p->use_pipe;
-            if (two) { if (int rc = ensure_second_workspace(p)) return rc; }
-            auto d2h_plane = [&](int c) -> int {
-                JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_c[c], 0));
-                JB_CK(cudaMemcpyAsync(gh + (size_t)c * npx, p->gdev + (size_t)c * npx, plane_b, cudaMemcpyDeviceToHost, p->st_out));
-                return 0;
-            };
-            if (int rc = run_planes_two_streams(p, p->xdev, S, p->gdev, two, true, st, d2h_plane)) return rc;
-            JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
-                                     (const double*)p->partial, g.T * g.E * p->nblk_out, p->edev));
-        } else {
-            const size_t pitch = (size_t)g.E * npx * sizeof(double), width = npx * sizeof(double);
-            for (int e = 0; e < g.E; ++e) {
-                JB_CK(cudaMemcpy2DAsync(p->xdev + e * npx, pitch, xh + e * npx, pitch, width, S, cudaMemcpyHostToDevice, p->st_in));
-                JB_CK(cudaEventRecord(p->ev_in[e], p->st_in));
-            }
-            for (int e = 0; e < g.E; ++e) {
-                JbGeom ge = g;
-                ge.e0 = e; ge.Es = 1;
-                JB_CK(cudaStreamWaitEvent(st, p->ev_in[e], 0));
-                JbEpi ep; memset(&ep, 0, sizeof(ep));
-                ep.mode = JB_EPI_PSF; ep.out = p->gbuf;
-                if (int rc = run_forward_g(p, ge, p->xdev, S, ep, st)) return rc;
-                JB_LAUNCHED(p, jb_launch(k_poisson_epi, dim3(p->nblk_epi, S * g.T), dim3(256), 256 * sizeof(double), st, ge,
-                                         p->gbuf, (const double*)p->expo, (const double*)p->data, (int)npx, p->partial));
-                if (int rc = run_adjoint_g(p, ge, p->gbuf, nullptr, S, p->gdev, st)) return rc;
-                JB_CK(cudaEventRecord(p->ev_c[e], st));
-                JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_c[e], 0));
-                JB_CK(cudaMemcpy2DAsync(gh + e * npx, pitch, p->gdev + e * npx, pitch, width, S, cudaMemcpyDeviceToHost, p->st_out));
-            }
-            JB_LAUNCHED(p, jb_launch(k_reduce_energy, dim3(S), dim3(256), 256 * sizeof(double), st,
-                                     (const double*)p->partial, g.T * g.E * p->nblk_epi, p->edev));
+        const size_t plane_b = npx * sizeof(double);
+        for (int c = 0; c < S * g.E; ++c) {
+            JB_CK(cudaMemcpyAsync(p->xdev + (size_t)c * npx, xh + (size_t)c * npx, plane_b, cudaMemcpyHostToDevice, p->st_in));
+            JB_CK(cudaEventRecord(p->ev_in[c], p->st_in));
         }
+        // Planes alternate between two compute streams: a one-plane launch leaves the persistent kernels with a
+        // ragged last wave (1024 rows on 888 resident CTAs), which the other stream's plane fills.
+        auto d2h_plane = [&](int c) -> int {
+            JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_c[c], 0));
+            JB_CK(cudaMemcpyAsync(gh + (size_t)c * npx, p->gdev + (size_t)c * npx, plane_b, cudaMemcpyDeviceToHost, p->st_out));
+            return 0;
+        };
+        if (int rc = run_planes_two_streams(p, p->xdev, S, p->gdev, p->ws2_ready != 0, true, st, d2h_plane)) return rc;
+        if (int rc = reduce_energy(p, S, p->edev, st)) return rc;
         if (d2h(eh, p->edev, S * sizeof(double), st)) return fail(JUBIK_ERR_CUDA, "D2H copy of energy failed");
         if (stream_sync(st) || stream_sync(p->st_out)) return fail(JUBIK_ERR_CUDA, "stream synchronise failed");
         return JUBIK_OK;
@@ -1185,28 +1145,60 @@ int jubik_poisson_energy_and_grad_sharded(jubik_plan* p, jubik_comm* c, int shar
                                           double* grad_local, double* flat, void* stream_) {
     jb_stream_t st = (jb_stream_t)stream_;
     if (int rc = check_call(p, x, flat, S)) return rc;
+    if (!p->has_expo || !p->has_data) return fail(JUBIK_ERR_ARG, "plan needs exposures and data for the Poisson energy");
     const JbGeom& g = p->g;
-    const size_t npx = (size_t)g.E * g.N * g.N;
+    const size_t npl = (size_t)g.N * g.N, npx = (size_t)g.E * npl;
     const int R = c ? c->n_ranks : 1, rank = c ? c->rank : 0;
     size_t count = 0;
     if (shard_mode == JUBIK_SHARD_MODULES) {
         // this rank's modules only: partial energies (S) and partial gradients (S,E,N,N) land in flat and are summed
+        if (grad_local) return fail(JUBIK_ERR_ARG, "module sharding has no per-rank gradient output (pass NULL)");
         count = (size_t)S * npx + S;
         if (int rc = jubik_poisson_energy_and_grad(p, x, S, flat + (size_t)S * npx, flat, stream_)) return rc;
-        if (grad_local) return fail(JUBIK_ERR_ARG, "module sharding has no per-rank gradient output (pass NULL)");
     } else if (shard_mode == JUBIK_SHARD_SAMPLES) {
         count = npx + (size_t)R * S;
         double* gl = grad_local;
         if (!gl && S > 1) {
-            if (!p->gdev) {
-                if (int rc = alloc(p, (void**)&p->gdev, (size_t)p->S_max * npx * sizeof(double), "per-sample gradient staging")) return rc;
-            }
-            gl = p->gdev;
+            if (!p->gstage) return fail(JUBIK_ERR_ARG, "plan was created without JUBIK_PLAN_SHARDED: pass grad_local (S,E,N,N) "
+                                                       "or create the plan with the flag");
+            gl = p->gstage;
         }
         if (!gl) gl = flat;   // one local sample and no per-sample output wanted: the gradient is written in place
-        if (int rc = jubik_poisson_energy_and_grad(p, x, S, flat + npx + (size_t)rank * S, gl, stream_)) return rc;
+        double* eslot = flat + npx + (size_t)rank * S;
+#ifndef JB_EMU
+        if (c && c->nccl && R > 1 && g.E > 1 && p->st_comm) {
+            // Overlapped collective: one energy bin at a time; as soon as the sample-summed gradient of bin e is folded
+            // into flat, its all-reduce is issued on the collective's stream while the kernels of bin e+1 run.  Only the
+            // last bin's all-reduce (which also carries the energies, contiguous behind it) is exposed.
+            JbEpi ep; memset(&ep, 0, sizeof(ep));
+            ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
+            JB_CK(cudaEventRecord(p->ev_start, st));
+            JB_CK(cudaStreamWaitEvent(p->st_comm, p->ev_start, 0));
+            for (int e = 0; e < g.E; ++e) {
+                JbGeom ge = g;
+                ge.e0 = e; ge.Es = 1;
+                if (int rc = run_forward_g(p, ge, x, S, ep, 0, st)) return rc;
+                if (e == g.E - 1) { if (int rc = reduce_energy(p, S, eslot, st)) return rc; }
+                if (int rc = run_adjoint_g(p, ge, p->gbuf, nullptr, S, gl, nullptr, st)) return rc;
+                const bool last = e == g.E - 1;
+                JB_LAUNCHED(p, jb_launch(k_fold_samples, dim3(592), dim3(256), 0, st,
+                                         (const double*)(gl == flat ? nullptr : gl + (size_t)e * npl), S, npl, npx,
+                                         flat + (size_t)e * npl, last ? flat + npx : nullptr, rank * S, R * S));
+                JB_CK(cudaEventRecord(p->ev_bin[e], st));
+                JB_CK(cudaStreamWaitEvent(p->st_comm, p->ev_bin[e], 0));
+                double* seg = flat + (size_t)e * npl;
+                const size_t cnt = last ? npl + (size_t)R * S : npl;
+                if (int rc = g_nccl.AllReduce(seg, seg, cnt, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl, p->st_comm))
+                    return nccl_fail("ncclAllReduce", rc);
+            }
+            JB_CK(cudaEventRecord(p->ev_comm, p->st_comm));
+            JB_CK(cudaStreamWaitEvent(st, p->ev_comm, 0));
+            return JUBIK_OK;
+        }
+#endif
+        if (int rc = jubik_poisson_energy_and_grad(p, x, S, eslot, gl, stream_)) return rc;
         JB_LAUNCHED(p, jb_launch(k_fold_samples, dim3(1184), dim3(256), 0, st, (const double*)(gl == flat ? nullptr : gl), S, npx,
-                                 flat, rank * S, R * S));
+                                 npx, flat, flat + npx, rank * S, R * S));
     } else {
         return fail(JUBIK_ERR_ARG, "unknown shard mode");
     }

@@ -235,8 +235,8 @@ struct Cols3 {
 // row pass then reads ONE spectrum row per (image row, i) instead of one per covering patch.
 // KD: no K^ staging ring -- thread 0 prefetches the slice into L2 two items ahead and the stage-3 threads load it
 // straight into registers; the shared memory saved lets a third CTA (24 warps) share the SM.
-template <class F3, int CB, bool ADJ, bool SWEEP, bool KD = false>
-JB_GLOBAL void JB_LB((Cols3<F3, CB>::THREADS), (KD ? Cols3<F3, CB>::CPS_KD : Cols3<F3, CB>::CPS))
+template <class F3, int CB, bool ADJ>
+JB_GLOBAL void JB_LB((Cols3<F3, CB>::THREADS), (Cols3<F3, CB>::CPS))
 k_cols3_pipe(const
 #ifndef JB_EMU
              __grid_constant__
@@ -247,6 +247,7 @@ k_cols3_pipe(const
     constexpr int L = F3::L, R1 = F3::R1, M = F3::M;
     constexpr int TILE = L * CB;
     constexpr int JB_C3_THREADS = C3::THREADS;
+    constexpr bool SWEEP = false, KD = false;   // round-1 experiments (column-chain accumulation, K^ straight from L2): see DESIGN.md
     JB_SMEM(unsigned char, smraw);
     cd* tile0 = reinterpret_cast<cd*>(smraw);
     cd* kh0 = tile0 + 2 * TILE;

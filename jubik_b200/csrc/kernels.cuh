@@ -32,8 +32,31 @@ struct JbGeom {
     int S, T, E;
     int e0, Es;                 // energy-bin chunk processed by a launch: bins [e0, e0+Es) (whole range by default);
                                 // launches index planes over (S, T, Es) / (S, Es) and map to the true plane ids
+    int fold, ext;              // period-P alias fold (L > P and PSF half-support s > m): ext = s - m rows/columns at either
+                                // end of the P-window alias onto [P, P+ext) / [L-ext, L) of the length-L transform
     int offs[JB_MAXN];          // clamped window starts in the hp-padded frame (lax.dynamic_slice)
 };
+
+// Period-P alias fold (hard part 2; reference semantics jubik/convolve.py:92-131,165-176: the convolution is
+// CIRCULAR with period P, so PSF tails beyond the margin wrap around).  With a transform length L >= w + 2s the length-L
+// result is the LINEAR convolution (no wrap), laid out circularly: positions [-ext, 0) sit at [L-ext, L) and positions
+// [P, P+ext) follow the window.  The period-P result is out[t] = lin[t] + lin[t+P] (t < ext) + lin[t-P] (t >= P-ext);
+// the transpose feeds the periodic extension of the P-window.  jb_fold_src maps a length-L position p to the window
+// position it aliases (or -1 if p lies in the unused gap): p in [0,P) -> p, [P,P+ext) -> p-P, [L-ext,L) -> p-L+P.
+JB_HD int jb_fold_src(const JbGeom& g, int p) {
+    if (p < g.P) return p;
+    if (!g.fold) return -1;
+    if (p < g.P + g.ext) return p - g.P;
+    if (p >= g.L - g.ext) return p - g.L + g.P;
+    return -1;
+}
+// second length-L position that folds onto window position t (-1: none)
+JB_HD int jb_fold_alias(const JbGeom& g, int t) {
+    if (!g.fold) return -1;
+    if (t < g.ext) return t + g.P;
+    if (t >= g.P - g.ext) return t - g.P + g.L;
+    return -1;
+}
 
 // launched plane index over (S, T, Es) -> ste = (s*T+t)*E+e, te = t*E+e, se = s*E+e
 JB_D void jb_map_ste(const JbGeom& g, int lp, int& ste, int& te, int& se) {
@@ -51,30 +74,47 @@ JB_D int jb_map_se(const JbGeom& g, int lp, int& s, int& e) {
     return s * g.E + e;
 }
 
-enum { JB_EPI_PSF = 0, JB_EPI_RESP = 1, JB_EPI_POISSON = 2, JB_EPI_METRIC = 3 };
+// Epilogues of the forward chain (conv = linpatch_convolve(x)[s,t,e,r,c], ex = effective exposure, 0 == masked):
+//   PSF      out = conv                                      (psf_func)
+//   RESP     out = ex * conv                                 (R, dense)
+//   POISSON  out = ex * (1 - d / lambda), lambda = ex * conv; energy partial += lambda - d log lambda
+//   MFAC     out = ex / conv = ex^2 / lambda                 (linearisation point of the metric, jubik_poisson_set_point)
+//   METRIC   out = fac * conv, fac = ex^2 / lambda(x0)       (R^T-ready  ex * (R v) / lambda)
+enum { JB_EPI_PSF = 0, JB_EPI_RESP = 1, JB_EPI_POISSON = 2, JB_EPI_METRIC = 3, JB_EPI_MFAC = 4 };
 
 struct JbEpi {
     int mode;
     const double* expo;   // (T,E,N,N) thresholded exposure * eff_area * pixel_area ; 0 == masked
     const double* data;   // (T,E,N,N) counts as fp64
-    const double* lam;    // (S,T,E,N,N) for JB_EPI_METRIC
+    const double* fac;    // (S,T,E,N,N) for JB_EPI_METRIC: ex^2 / lambda at the linearisation point, 0 == masked
     double* out;          // (S,T,E,N,N)
     double* partial;      // per-CTA energy partials, [STE][gridDim.x]
-    // fused final reduction (rows5, JB_EPI_POISSON): the last CTA to finish sums the partials in a fixed order
-    double* energy;       // (S,) or nullptr (no fused reduction in this launch)
-    unsigned* counter;    // zero-initialised device counter, reset by the last CTA
-    int n_samples, per_sample;
 };
 
+// one pixel of the non-Poisson epilogues
+JB_D double jb_epi_pixel(const JbEpi& ep, double conv, size_t o, size_t oe) {
+    if (ep.mode == JB_EPI_PSF) return conv;
+    if (ep.mode == JB_EPI_METRIC) return jb_ldg(ep.fac + o) * conv;
+    const double ex = jb_ldg(ep.expo + oe);
+    if (ex == 0.0) return 0.0;
+    return ep.mode == JB_EPI_RESP ? ex * conv : ex / conv;
+}
+
 // Row-patch list of an image row: all j with u = r + shift - offs[j] in [0, len).
-// Stored in shared memory as (j, u) pairs; cnt <= n.
-JB_D void jb_build_jlist(const JbGeom& g, int r0, int rpc, int shift, int len, int* jcnt, int* jj, int* ju) {
+// Stored in shared memory as (j, row) pairs, 2n slots per image row; `row` is the row inside the patch's block of the
+// spectrum buffer.  fold (forward direction only): the aliased row of the same patch is a second source.
+JB_D void jb_build_jlist(const JbGeom& g, int r0, int rpc, int shift, int len, bool fold, int* jcnt, int* jj, int* ju) {
+    const int cap = 2 * g.n;
     for (int rr = jb_tid(); rr < rpc; rr += jb_nthr()) {
         int r = r0 + rr, c = 0;
         if (r < g.N) {
             for (int j = 0; j < g.n; ++j) {
                 int u = r + shift - g.offs[j];
-                if (u >= 0 && u < len) { jj[rr * g.n + c] = j; ju[rr * g.n + c] = u; ++c; }
+                if (u >= 0 && u < len) {
+                    jj[rr * cap + c] = j; ju[rr * cap + c] = u; ++c;
+                    int a = fold ? jb_fold_alias(g, u) : -1;
+                    if (a >= 0) { jj[rr * cap + c] = j; ju[rr * cap + c] = a; ++c; }
+                }
             }
         }
         jcnt[rr] = c;
@@ -88,7 +128,7 @@ JB_D size_t jb_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 // row of column block i -- stored once per (row, i); the row weight is applied by the column pass.
 template <class FP>
 JB_GLOBAL void k_rows_fwd(JbGeom g, const double* __restrict__ x, const double* __restrict__ wgt,
-                          const cd* __restrict__ tw_nk, cd* __restrict__ rowsF, int rpc) {
+                          const cd* __restrict__ tw_nk, cd* __restrict__ rowsF, int rpc, int exp_in) {
     JB_SMEM(unsigned char, smraw);
     const int B = rpc * g.n;
     cd* sm = reinterpret_cast<cd*>(smraw);
@@ -101,7 +141,9 @@ JB_GLOBAL void k_rows_fwd(JbGeom g, const double* __restrict__ x, const double* 
         int q = p - m;
         int c = g.offs[i] - hp + q;
         if (r >= N || q < 0 || q >= w || c < 0 || c >= N) return 0.0;
-        return jb_ldg(xp + (size_t)r * N + c) * jb_ldg(wgt + q);
+        double v = jb_ldg(xp + (size_t)r * N + c);
+        if (exp_in) v = exp(v);      // sky-model tail x = exp(log_sky) (sky_models.py:340-341)
+        return v * jb_ldg(wgt + q);
     };
     auto st = [&](int b, int k, cd X) {
         int rr = b / n, i = b - rr * n, r = r0 + rr;
@@ -122,13 +164,14 @@ JB_GLOBAL void k_rows_adj_in(JbGeom g, const double* __restrict__ gin, const dou
     int ste, te, se_;
     jb_map_ste(g, blockIdx.y, ste, te, se_);
     const int r0 = blockIdx.x * rpc;
-    const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, P = g.P;
+    const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH;
     const double* gp = gin + (size_t)ste * N * N;
     const double* ep = expo ? expo + (size_t)te * N * N : nullptr;
     auto ld = [&](int b, int p) -> double {
         int rr = b / n, i = b - rr * n, r = r0 + rr;
-        int c = g.offs[i] - hp - m + p;
-        if (r >= N || p >= P || c < 0 || c >= N) return 0.0;
+        const int ps = jb_fold_src(g, p);       // window position (periodic extension under the alias fold)
+        int c = g.offs[i] - hp - m + ps;
+        if (r >= N || ps < 0 || c < 0 || c >= N) return 0.0;
         double v = jb_ldg(gp + (size_t)r * N + c);
         if (ep) v *= jb_ldg(ep + (size_t)r * N + c);
         return v;
@@ -167,7 +210,7 @@ JB_GLOBAL void k_cols(JbGeom g, const cd* __restrict__ in, cd* __restrict__ out,
     int in_p0, in_rows, row0, out_p0, out_rows;
     size_t in_plane;
     if (!ADJ) {
-        in_p0 = m; in_rows = w; out_p0 = 0; out_rows = P;
+        in_p0 = m; in_rows = w; out_p0 = 0; out_rows = g.fold ? L : P;   // fold: all L rows go out, the row pass sums the aliases
         in_plane = (size_t)se;
         row0 = g.offs[j] - hp;
     } else {
@@ -179,7 +222,9 @@ JB_GLOBAL void k_cols(JbGeom g, const cd* __restrict__ in, cd* __restrict__ out,
     cd* ob = out + (((size_t)plane * nn2 + k) * out_rows) * PH;
     const cd* kb = khat + (((size_t)te * nn2 + k) * nstrips + strip) * ((size_t)L * CB);
     auto ld = [&](int p, int b) -> cd {
-        int col = col0 + b, u = p - in_p0, r = row0 + u;
+        int col = col0 + b, u = p - in_p0;
+        if (ADJ) u = jb_fold_src(g, p);          // periodic extension of the P cotangent rows under the alias fold
+        int r = row0 + u;
         if (col >= PH || u < 0 || u >= in_rows || r < 0 || r >= N) return cd_make(0.0, 0.0);
         cd v = ib[(size_t)r * PH + col];
         if (!ADJ) v = cd_scale(v, jb_ldg(wgt + u));
@@ -227,32 +272,34 @@ JB_GLOBAL void k_rows_out(JbGeom g, const cd* __restrict__ bufA, const cd* __res
     const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, P = g.P;
     size_t off = 0;
     cd* sm = reinterpret_cast<cd*>(smraw);
+    const int TW = g.fold ? FP::L : P;       // real samples kept per sequence; OR = rows per patch in bufA
+    const int OR = TW;
     off += jb_align16((size_t)B * FP::LS * sizeof(cd));
     double* tile = reinterpret_cast<double*>(smraw + off);
-    off += jb_align16((size_t)B * P * sizeof(double));
+    off += jb_align16((size_t)B * TW * sizeof(double));
     double* red = reinterpret_cast<double*>(smraw + off);
     off += jb_align16((size_t)jb_nthr() * sizeof(double));
     int* jcnt = reinterpret_cast<int*>(smraw + off);
     int* jj = jcnt + rpc;
-    int* ju = jj + rpc * n;
+    int* ju = jj + 2 * rpc * n;
     int ste, te, se_;
     jb_map_ste(g, blockIdx.y, ste, te, se_);
     const int r0 = blockIdx.x * rpc;
-    jb_build_jlist(g, r0, rpc, hp + m, P, jcnt, jj, ju);
+    jb_build_jlist(g, r0, rpc, hp + m, P, g.fold != 0, jcnt, jj, ju);
     JB_SYNC();
     const size_t nn2 = (size_t)n * n;
-    const cd* ab = bufA + (size_t)ste * nn2 * P * PH;
+    const cd* ab = bufA + (size_t)ste * nn2 * OR * PH;
     auto ld = [&](int b, int k) -> cd {
         int rr = b / n, i = b - rr * n;
         cd acc = cd_make(0.0, 0.0);
         for (int q = 0; q < jcnt[rr]; ++q) {
-            int j = jj[rr * n + q], u = ju[rr * n + q];
-            acc = cd_add(acc, ab[(((size_t)i * n + j) * P + u) * PH + k]);
+            int j = jj[rr * 2 * n + q], u = ju[rr * 2 * n + q];
+            acc = cd_add(acc, ab[(((size_t)i * n + j) * OR + u) * PH + k]);
         }
         return acc;
     };
     auto st = [&](int b, int p, double v) {
-        if (p < P) tile[(size_t)b * P + p] = v;
+        if (p < TW) tile[(size_t)b * TW + p] = v;
     };
     rows_c2r<FP>(sm, tw_kn, B, ld, st);
     JB_SYNC();
@@ -263,29 +310,25 @@ JB_GLOBAL void k_rows_out(JbGeom g, const cd* __restrict__ bufA, const cd* __res
         double conv = 0.0;
         for (int i = 0; i < n; ++i) {
             int p = c - (g.offs[i] - hp - m);
-            if (p >= 0 && p < P) conv += tile[(size_t)(rr * n + i) * P + p];
+            if (p >= 0 && p < P) {
+                conv += tile[(size_t)(rr * n + i) * TW + p];
+                const int a = jb_fold_alias(g, p);
+                if (a >= 0) conv += tile[(size_t)(rr * n + i) * TW + a];
+            }
         }
         size_t o = ((size_t)ste * N + r) * N + c;
         size_t oe = ((size_t)te * N + r) * N + c;
-        if (ep.mode == JB_EPI_PSF) {
-            ep.out[o] = conv;
-        } else {
-            double ex = jb_ldg(ep.expo + oe);
-            if (ep.mode == JB_EPI_RESP) {
-                ep.out[o] = (ex != 0.0) ? ex * conv : 0.0;
-            } else if (ep.mode == JB_EPI_POISSON) {
-                double gout = 0.0;
-                if (ex != 0.0) {
-                    double lam = ex * conv, d = jb_ldg(ep.data + oe);
-                    esum += lam - d * log(lam);
-                    gout = ex * (1.0 - d / lam);
-                }
-                ep.out[o] = gout;
-            } else {  // JB_EPI_METRIC: R^T-ready  ex * (R v) / lambda
-                double gout = 0.0;
-                if (ex != 0.0) gout = ex * (ex * conv) / ep.lam[o];
-                ep.out[o] = gout;
+        if (ep.mode == JB_EPI_POISSON) {
+            const double ex = jb_ldg(ep.expo + oe);
+            double gout = 0.0;
+            if (ex != 0.0) {
+                double lam = ex * conv, d = jb_ldg(ep.data + oe);
+                esum += lam - d * log(lam);
+                gout = ex * (1.0 - d / lam);
             }
+            ep.out[o] = gout;
+        } else {
+            ep.out[o] = jb_epi_pixel(ep, conv, o, oe);
         }
     }
     if (ep.mode == JB_EPI_POISSON) {
@@ -298,7 +341,8 @@ JB_GLOBAL void k_rows_out(JbGeom g, const cd* __restrict__ bufA, const cd* __res
 // grid (ceil(N/rpc), S*E).  bufB:(STE, n*n, w, PH).  grad:(S,E,N,N).
 template <class FP>
 JB_GLOBAL void k_rows_adj_out(JbGeom g, const cd* __restrict__ bufB, const double* __restrict__ wgt,
-                              const cd* __restrict__ tw_kn, double* __restrict__ grad, int rpc) {
+                              const cd* __restrict__ tw_kn, double* __restrict__ grad, const double* __restrict__ logsky,
+                              int rpc) {
     JB_SMEM(unsigned char, smraw);
     const int B = rpc * g.n;
     const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, w = g.w;
@@ -309,10 +353,10 @@ JB_GLOBAL void k_rows_adj_out(JbGeom g, const cd* __restrict__ bufB, const doubl
     off += jb_align16((size_t)B * w * sizeof(double));
     int* jcnt = reinterpret_cast<int*>(smraw + off);
     int* jj = jcnt + rpc;
-    int* ju = jj + rpc * n;
+    int* ju = jj + 2 * rpc * n;
     int s, e;
     const int r0 = blockIdx.x * rpc, se = jb_map_se(g, blockIdx.y, s, e);
-    jb_build_jlist(g, r0, rpc, hp, w, jcnt, jj, ju);
+    jb_build_jlist(g, r0, rpc, hp, w, false, jcnt, jj, ju);
     JB_SYNC();
     const size_t nn2 = (size_t)n * n;
     auto ld = [&](int b, int k) -> cd {
@@ -321,7 +365,7 @@ JB_GLOBAL void k_rows_adj_out(JbGeom g, const cd* __restrict__ bufB, const doubl
         for (int t = 0; t < g.T; ++t) {
             const cd* bb = bufB + ((size_t)(s * g.T + t) * g.E + e) * nn2 * w * PH;
             for (int q = 0; q < jcnt[rr]; ++q) {
-                int j = jj[rr * n + q], u0 = ju[rr * n + q];
+                int j = jj[rr * 2 * n + q], u0 = ju[rr * 2 * n + q];
                 double wr = jb_ldg(wgt + u0);
                 cd v = bb[(((size_t)i * n + j) * w + u0) * PH + k];
                 acc.x += wr * v.x;
@@ -344,7 +388,9 @@ JB_GLOBAL void k_rows_adj_out(JbGeom g, const cd* __restrict__ bufB, const doubl
             int v = c - (g.offs[i] - hp);
             if (v >= 0 && v < w) acc += tile[(size_t)(rr * n + i) * w + v];
         }
-        grad[((size_t)se * N + r) * N + c] = acc;
+        const size_t o = ((size_t)se * N + r) * N + c;
+        if (logsky) acc *= exp(jb_ldg(logsky + o));   // VJP of x = exp(log_sky): d/dlog_sky = grad_x * x
+        grad[o] = acc;
     }
 }
 
@@ -448,92 +494,38 @@ JB_GLOBAL void k_prep_cols(JbGeom g, const cd* __restrict__ scratch, const doubl
     cols_cfft<FP, CB, false>(sm, tw_nk, ld, mid, st);
 }
 
-// Poisson epilogue as its own full-occupancy elementwise pass (log + divide are ~100 FP64 instructions per
-// pixel: inside the low-occupancy row kernel they cost 4x more than here).  In place on the convolved planes:
-//   buf[s,t,e,:,:] = conv  ->  expo*(1 - d/lambda)  (0 where masked), lambda = expo*conv;
-//   partial[(s*TE + te)*nblk + blockIdx.x] = sum over this CTA's pixels of lambda - d log lambda.
-// grid (nblk, S*T*E), block 256.
-JB_GLOBAL_S void k_poisson_epi(JbGeom g, double* __restrict__ buf, const double* __restrict__ expo,
-                               const double* __restrict__ data, int npix, double* __restrict__ partial) {
-    JB_SMEM(double, red);
-    int ste, te, se_;
-    jb_map_ste(g, blockIdx.y, ste, te, se_);
-    double* b = buf + (size_t)ste * npix;
-    const double* ex = expo + (size_t)te * npix;
-    const double* dd = data + (size_t)te * npix;
-    double esum = 0.0;
-    for (int i = blockIdx.x * jb_nthr() + jb_tid(); i < npix; i += gridDim.x * jb_nthr()) {
-        double e = jb_ldg(ex + i), conv = b[i], gout = 0.0;
-        if (e != 0.0) {
-            double lam = e * conv, d = jb_ldg(dd + i);
-            esum += lam - d * log(lam);
-            gout = e * (1.0 - d / lam);
-        }
-        b[i] = gout;
-    }
-    double tot = jb_block_sum(esum, red);
-    if (jb_tid() == 0) partial[(size_t)ste * gridDim.x + blockIdx.x] = tot;
-}
-
-// metric epilogue: buf = conv(v)  ->  expo * (expo*conv) / lambda  (0 where masked)
-JB_GLOBAL_S void k_metric_epi(JbGeom g, double* __restrict__ buf, const double* __restrict__ expo,
-                              const double* __restrict__ lam, int npix) {
-    int ste, te, se_;
-    jb_map_ste(g, blockIdx.y, ste, te, se_);
-    double* b = buf + (size_t)ste * npix;
-    const double* ex = expo + (size_t)te * npix;
-    const double* lm = lam + (size_t)ste * npix;
-    for (int i = blockIdx.x * jb_nthr() + jb_tid(); i < npix; i += gridDim.x * jb_nthr()) {
-        double e = jb_ldg(ex + i), gout = 0.0;
-        if (e != 0.0) gout = e * (e * b[i]) / lm[i];
-        b[i] = gout;
+// left-sqrt-metric epilogue: out = ex * t / sqrt(lambda) = sqrt(fac) * t with fac = ex^2 / lambda (0 where masked);
+// NIFTy's Poissonian left_sqrt_metric t / sqrt(lambda) pulled back through R, the ex factor being
+// R^T's exposure multiply
+JB_GLOBAL_S void k_lsm_epi(const double* __restrict__ t, const double* __restrict__ fac, double* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * jb_nthr() + jb_tid(); i < n; i += (size_t)gridDim.x * jb_nthr()) {
+        const double f = fac[i];
+        out[i] = (f != 0.0) ? sqrt(f) * t[i] : 0.0;
     }
 }
 
-// left-sqrt-metric epilogue: out = expo * t / sqrt(lambda)  (0 where masked); NIFTy's Poissonian left_sqrt_metric
-// t / sqrt(lambda) pulled back through R, the expo factor being R^T's exposure multiply
-JB_GLOBAL_S void k_lsm_epi(JbGeom g, const double* __restrict__ t, const double* __restrict__ expo,
-                           const double* __restrict__ lam, double* __restrict__ out, int npix) {
-    int ste, te, se_;
-    jb_map_ste(g, blockIdx.y, ste, te, se_);
-    const double* tp = t + (size_t)ste * npix;
-    const double* ex = expo + (size_t)te * npix;
-    const double* lm = lam + (size_t)ste * npix;
-    double* o = out + (size_t)ste * npix;
-    for (int i = blockIdx.x * jb_nthr() + jb_tid(); i < npix; i += gridDim.x * jb_nthr()) {
-        double e = jb_ldg(ex + i), v = 0.0;
-        if (e != 0.0) v = e * tp[i] / sqrt(lm[i]);
-        o[i] = v;
-    }
-}
-
-// sky-model tail (sky_models.py:340-341): x = exp(log_sky); and its VJP grad_log_sky = grad_x * x
-JB_GLOBAL_S void k_exp(const double* __restrict__ s, double* __restrict__ x, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * jb_nthr() + jb_tid(); i < n; i += (size_t)gridDim.x * jb_nthr()) x[i] = exp(s[i]);
-}
-JB_GLOBAL_S void k_mul_inplace(double* __restrict__ a, const double* __restrict__ b, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * jb_nthr() + jb_tid(); i < n; i += (size_t)gridDim.x * jb_nthr()) a[i] *= b[i];
-}
-
-// sample-sharded multi-GPU evaluation: flat = [ sum_s grad[s] (npx) | energies of all ranks' samples (nslots) ].
-// This rank's energies were already written into its slots [slot0, slot0+S) by k_reduce_energy; the other slots are
-// zeroed here so that ONE all-reduce(sum) of `flat` delivers the sample-summed gradient and every energy.
-// grad == nullptr: the gradient of the single local sample already sits in flat (only the slots are cleared).
-JB_GLOBAL_S void k_fold_samples(const double* __restrict__ grad, int S, size_t npx, double* __restrict__ flat, int slot0,
-                                int nslots) {
+// sample-sharded multi-GPU evaluation: flat = [ sum_s grad[s] (E,N,N) | energies of all ranks' samples (nslots) ].
+// Folds `cnt` gradient elements of the S local samples (element i of sample s at grad[s*sstride + i]) into dst[0..cnt) in a
+// fixed order.  This rank's energies were already written into its slots [slot0, slot0+S) of `slots` by k_reduce_energy;
+// the other slots are zeroed here so that ONE all-reduce(sum) delivers the sample-summed gradient and every energy.
+// grad == nullptr: the gradient of the single local sample already sits in dst; slots == nullptr: leave the energies alone
+// (the per-energy-bin calls of the overlapped collective clear them with the last bin only).
+JB_GLOBAL_S void k_fold_samples(const double* __restrict__ grad, int S, size_t cnt, size_t sstride, double* __restrict__ dst,
+                                double* __restrict__ slots, int slot0, int nslots) {
     const size_t t0 = (size_t)blockIdx.x * jb_nthr() + jb_tid(), nt = (size_t)gridDim.x * jb_nthr();
     if (grad) {
-        const cd* g2 = reinterpret_cast<const cd*>(grad);   // 128-bit accesses
-        cd* f2 = reinterpret_cast<cd*>(flat);
-        const size_t h = npx / 2;   // npx = E*N*N with N even
+        const cd* g2 = reinterpret_cast<const cd*>(grad);   // 128-bit accesses (cnt and sstride are multiples of N*N, N even)
+        cd* f2 = reinterpret_cast<cd*>(dst);
+        const size_t h = cnt / 2, hs = sstride / 2;
         for (size_t i = t0; i < h; i += nt) {
             cd a = g2[i];
-            for (int s = 1; s < S; ++s) { cd b = g2[(size_t)s * h + i]; a.x += b.x; a.y += b.y; }   // fixed order
+            for (int s = 1; s < S; ++s) { cd b = g2[(size_t)s * hs + i]; a.x += b.x; a.y += b.y; }   // fixed order
             f2[i] = a;
         }
     }
-    for (size_t j = t0; j < (size_t)nslots; j += nt)
-        if ((int)j < slot0 || (int)j >= slot0 + S) flat[npx + j] = 0.0;
+    if (slots)
+        for (size_t j = t0; j < (size_t)nslots; j += nt)
+            if ((int)j < slot0 || (int)j >= slot0 + S) slots[j] = 0.0;
 }
 
 // energy[s] = sum over (t,e) planes and row blocks of the per-CTA partials; one CTA per sample

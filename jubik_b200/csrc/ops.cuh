@@ -6,59 +6,39 @@
 #include "rows_fast.cuh"
 #include "cols_pipe.cuh"
 #include "cols3.cuh"
-#include "cols3_pp.cuh"
-#include "rows_pipe.cuh"
-#include "rows3.cuh"
 #include "rows5.cuh"
-#include "rows6.cuh"
 
 
 struct JbFftOps {
     int L, R1, R2, CB;
     int ls;    // cd per real sequence in the exchange buffer
-    int pipe;  // 0: plain column kernel only; 1: two-pass TMA pipeline; 2: three-stage TMA pipeline (cols3.cuh)
+    int pipe;  // 0: plain column kernel only; 2: three-stage TMA pipeline (cols3.cuh)
     int q1, q2, q3;  // three-stage factors (pipe == 2)
-    // fast != 0 selects the low-overhead kernels of rows_fast.cuh (two-pass lengths, <= JB_MAXQ row-patches per row)
+    // fast != 0 selects the low-overhead kernels of rows_fast.cuh (two-pass lengths, <= JB_MAXQ row-patches per row,
+    // no alias fold); fast == 0 the generic kernels of kernels.cuh (any geometry, period-P alias fold)
     cudaError_t (*rows_fwd)(const JbGeom&, const double* x, const double* wgt, const cd* tw_nk, cd* bufB,
-                            int planes, int rpc, int threads, int fast, jb_stream_t);
+                            int planes, int rpc, int threads, int fast, int exp_in, jb_stream_t);
     cudaError_t (*rows_adj_in)(const JbGeom&, const double* gin, const double* expo, const cd* tw_nk, cd* bufA,
                                int planes, int rpc, int threads, int fast, jb_stream_t);
     cudaError_t (*cols)(const JbGeom&, bool adj, const cd* in, cd* out, const cd* khat, const cd* tw_nk,
                         const double* wgt, int planes, int threads, jb_stream_t);
     // three-stage TMA pipeline (pipe == 2): twa/twb = stage-1/stage-2 twiddle tables
-    // sweep != 0: outputs accumulated over the row-patches into (planes*n, N, PH) (cols3.cuh)
-    cudaError_t (*cols_pipe)(const JbGeom&, bool adj, int sweep, const JbTileSrc& src, cd* out, const cd* khat,
+    cudaError_t (*cols_pipe)(const JbGeom&, bool adj, const JbTileSrc& src, cd* out, const cd* khat,
                              const cd* twa, const cd* twb, const double* wgt, int planes, int ctas, jb_stream_t);
     cudaError_t (*rows_out)(const JbGeom&, const cd* bufA, const cd* tw_kn, const JbEpi&, int planes, int rpc,
                             int threads, int fast, jb_stream_t);
     cudaError_t (*rows_adj_out)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw_kn, double* grad,
-                                int planes, int rpc, int threads, int fast, jb_stream_t);
-    // persistent bulk-copy-fed c2r kernels (rows_pipe.cuh); *_smem returns the dynamic shared memory they need
-    size_t (*rows_out_pipe_smem)(const JbGeom&, int Q);
-    size_t (*rows_adj_out_pipe_smem)(const JbGeom&, int Q);
-    cudaError_t (*rows_out_pipe)(const JbGeom&, const cd* bufA, const cd* tw_kn, const JbEpi&, int planes, int Q,
-                                 int ctas, jb_stream_t);
-    cudaError_t (*rows_adj_out_pipe)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw_kn, double* grad,
-                                     int planes_se, int Q, int ctas, jb_stream_t);
-    // packed-complex three-stage c2r kernels (rows3.cuh; need pipe == 2); *_smem returns a huge value if unusable
-    size_t (*rows_out_r3_smem)(const JbGeom&, int Q);
-    size_t (*rows_adj_out_r3_smem)(const JbGeom&, int Q);
-    cudaError_t (*rows_out_r3)(const JbGeom&, const cd* bufA, const cd* tw1, const cd* tw2, const JbEpi&, int planes,
-                               int Q, int ctas, jb_stream_t);
-    cudaError_t (*rows_adj_out_r3)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw1, const cd* tw2,
-                                   double* grad, int planes_se, int Q, int ctas, jb_stream_t);
+                                const double* logsky, int planes, int rpc, int threads, int fast, jb_stream_t);
+    // dynamic shared memory of the generic row kernels (plan creation rejects geometries beyond 227 KB)
+    size_t (*rows_generic_smem)(const JbGeom&, int rpc, int threads);
     // warp-private c2r kernels (rows5.cuh; need pipe == 2); fwd: ep.mode may be JB_EPI_POISSON (partials [STE][N])
     size_t (*rows5_smem)(const JbGeom&);
     int (*rows5_gather)(const JbGeom&, int adj, int maxq, int* host_tab);   // [maxq][N] table, returns slots used
-    // presum != 0: the source is the column pass's summed buffer (planes*n, N, PH) (sweep mode)
     cudaError_t (*rows5_fwd)(const JbGeom&, const cd* bufA, const cd* tw1, const cd* tw2, const int* gtab, int gq,
-                             const JbEpi&, int presum, int planes, int n_sm, jb_stream_t);
+                             const JbEpi&, int planes, int n_sm, jb_stream_t);
     cudaError_t (*rows5_adj)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw1, const cd* tw2,
-                             const int* gtab, int gq, double* grad, int presum, int planes_se, int n_sm, jb_stream_t);
-    // warp-private r2c kernels (rows6.cuh; need pipe == 2): adj = 0 sky rows -> rowsF, adj = 1 cotangent rows -> rowsA
-    size_t (*rows6_smem)(const JbGeom&);
-    cudaError_t (*rows6)(const JbGeom&, int adj, const double* in, const double* expo, const double* wgt, const cd* tw1,
-                         const cd* tw2, cd* out, int planes, int n_sm, jb_stream_t);
+                             const int* gtab, int gq, double* grad, const double* logsky, int planes_se, int n_sm,
+                             jb_stream_t);
     cudaError_t (*prep_rows)(const JbGeom&, const JbKsrc&, const cd* tw_nk, cd* scratch, int rpc, int threads,
                              jb_stream_t);
     // layout 0: K^ in the two-pass register order (tw = tw_nk); layout 2: three-stage order (twa/twb = tw1/tw2)
@@ -71,48 +51,17 @@ inline size_t jb_al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 template <class FP, int CB, int PIPE, class F3>
 struct JbOpsImpl {
-    static cudaError_t cols_pipe(const JbGeom& g, bool adj, int sweep, const JbTileSrc& src, cd* out, const cd* khat,
+    static cudaError_t cols_pipe(const JbGeom& g, bool adj, const JbTileSrc& src, cd* out, const cd* khat,
                                  const cd* twa, const cd* twb, const double* wgt, int planes, int ctas, jb_stream_t st) {
         if constexpr (PIPE == 2) {
             size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd) + 32 +
                           2 * sizeof(JbColInfo) + (size_t)g.w * sizeof(double) + 32;
             const dim3 grid(ctas * Cols3<F3, CB>::CPS), block(Cols3<F3, CB>::THREADS);
-#ifdef JB_COLS_KD
-            if (!sweep) {   // K^ straight from L2, three CTAs per SM
-                const dim3 grid3(ctas * Cols3<F3, CB>::CPS_KD);
-                const size_t smem3 = smem - 2 * (size_t)FP::L * CB * sizeof(cd);
-                if (adj) return jb_launch(k_cols3_pipe<F3, CB, true, false, true>, grid3, block, smem3, st, src, g, out,
-                                          khat, twa, twb, wgt, planes);
-                return jb_launch(k_cols3_pipe<F3, CB, false, false, true>, grid3, block, smem3, st, src, g, out, khat,
-                                 twa, twb, wgt, planes);
-            }
-#endif
-#ifndef JB_EMU
-            if (sweep == 2) {   // anti-phase pair of groups in one CTA per SM (cols3_pp.cuh); falls through for wide tiles
-                if constexpr (Cols3<F3, CB>::CPS == 2) {
-                    const size_t smem2 = 8 * (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd) + 64 +
-                                         4 * sizeof(JbColInfo) + (size_t)g.w * sizeof(double) + 32;
-                    const dim3 grid2(ctas), block2(2 * Cols3<F3, CB>::THREADS);
-                    if (adj) return jb_launch(k_cols3_pp<F3, CB, true>, grid2, block2, smem2, st, src, g, out, khat, twa, twb,
-                                              wgt, planes);
-                    return jb_launch(k_cols3_pp<F3, CB, false>, grid2, block2, smem2, st, src, g, out, khat, twa, twb, wgt,
-                                     planes);
-                }
-                sweep = 0;
-            }
-#endif
-            if (sweep) {
-                if (adj) return jb_launch(k_cols3_pipe<F3, CB, true, true>, grid, block, smem, st, src, g, out, khat, twa,
-                                          twb, wgt, planes);
-                return jb_launch(k_cols3_pipe<F3, CB, false, true>, grid, block, smem, st, src, g, out, khat, twa, twb,
-                                 wgt, planes);
-            }
-            if (adj) return jb_launch(k_cols3_pipe<F3, CB, true, false>, grid, block, smem, st, src, g, out, khat, twa,
-                                      twb, wgt, planes);
-            return jb_launch(k_cols3_pipe<F3, CB, false, false>, grid, block, smem, st, src, g, out, khat, twa, twb, wgt,
-                             planes);
+            if (adj) return jb_launch(k_cols3_pipe<F3, CB, true>, grid, block, smem, st, src, g, out, khat, twa, twb, wgt,
+                                      planes);
+            return jb_launch(k_cols3_pipe<F3, CB, false>, grid, block, smem, st, src, g, out, khat, twa, twb, wgt, planes);
         } else {
-            (void)g; (void)adj; (void)sweep; (void)src; (void)out; (void)khat; (void)twa; (void)twb; (void)wgt;
+            (void)g; (void)adj; (void)src; (void)out; (void)khat; (void)twa; (void)twb; (void)wgt;
             (void)planes; (void)ctas; (void)st;
             return (cudaError_t)1;
         }
@@ -120,24 +69,34 @@ struct JbOpsImpl {
     static size_t rowtab_bytes(int rpc) {
         return jb_al16(sizeof(int) * rpc) + (sizeof(long long) + sizeof(double)) * (size_t)rpc * JB_MAXQ + 16;
     }
-    static size_t smem_rows_in(const JbGeom& g, int rpc, int fast) {
-        (void)fast;
+    static size_t smem_rows_in(const JbGeom& g, int rpc) {
         size_t B = (size_t)rpc * g.n;
         return jb_al16(B * FP::LS * sizeof(cd)) + 16;
     }
-    // persistent prefetching r2c kernel (k_rows_in_pf): used when its exchange buffer + row ring fit an SM; JUBIK_B200_ROWS_IN_V2=1
-    // keeps the one-row-per-CTA kernels
+    // generic c2r kernels: exchange buffer + real tile (TW wide) + reduction scratch + row-patch lists (2n per row)
+    static size_t smem_rows_out_generic(const JbGeom& g, int rpc, int threads) {
+        size_t B = (size_t)rpc * g.n;
+        const int TW = g.fold ? g.L : g.P;
+        return jb_al16(B * FP::LS * sizeof(cd)) + jb_al16(B * TW * sizeof(double)) + jb_al16((size_t)threads * sizeof(double)) +
+               sizeof(int) * (rpc + 4 * (size_t)rpc * g.n) + 16;
+    }
+    static size_t smem_rows_adj_out_generic(const JbGeom& g, int rpc) {
+        size_t B = (size_t)rpc * g.n;
+        return jb_al16(B * FP::LS * sizeof(cd)) + jb_al16(B * g.w * sizeof(double)) + sizeof(int) * (rpc + 4 * (size_t)rpc * g.n) + 16;
+    }
+    static size_t rows_generic_smem(const JbGeom& g, int rpc, int threads) {
+        size_t a = smem_rows_out_generic(g, rpc, threads), b = smem_rows_adj_out_generic(g, rpc), c = smem_rows_in(g, rpc);
+        return a > b ? (a > c ? a : c) : (b > c ? b : c);
+    }
+    // persistent prefetching r2c kernel (k_rows_in_pf): used when its exchange buffer + row ring fit an SM
     template <bool ADJ>
     static bool rows_in_pf(const JbGeom& g, const double* in, const double* aux, const cd* tw_nk, cd* out, int planes,
-                           int threads, jb_stream_t st, cudaError_t* err) {
+                           int threads, int exp_in, jb_stream_t st, cudaError_t* err) {
         if constexpr (FP::R2 > 1) {
-            const bool off = getenv("JUBIK_B200_ROWS_IN_V2") != nullptr;
             const size_t smem = jb_al16((size_t)g.n * FP::LS * sizeof(cd)) + 2 * (size_t)g.N * sizeof(double) +
                                 (ADJ ? (aux ? 2 * (size_t)g.N * sizeof(double) : 0) : (size_t)g.w * sizeof(double));
-            size_t lim = 200 * 1024;     // one CTA per SM is still a win (C4: cotangent rows 0.41 -> 0.16 ms, r1x);
-                                         // JUBIK_B200_ROWS_IN_PF_KB overrides (tuning hook, <= 226)
-            if (const char* ev = getenv("JUBIK_B200_ROWS_IN_PF_KB")) { int v = atoi(ev); if (v >= 16 && v <= 226) lim = (size_t)v * 1024; }
-            if (off || (g.N & 1) || smem > lim) return false;
+            const size_t lim = 200 * 1024;   // one CTA per SM is still a win (C4: cotangent rows 0.41 -> 0.16 ms, r1x)
+            if ((g.N & 1) || smem > lim) return false;
             int per_sm = 1, n_sm = 148;
 #ifndef JB_EMU
             static int cache_thr = -1, cache_cps = 1, cache_sm = 148;
@@ -157,35 +116,26 @@ struct JbOpsImpl {
             long ctas = (long)per_sm * n_sm;
             const long total = (long)planes * g.N;
             if (ctas > total) ctas = total;
-            *err = jb_launch(k_rows_in_pf<FP, ADJ>, dim3((unsigned)ctas), dim3(threads), smem, st, g, in, aux, tw_nk, out, planes);
+            *err = jb_launch(k_rows_in_pf<FP, ADJ>, dim3((unsigned)ctas), dim3(threads), smem, st, g, in, aux, tw_nk, out, planes, exp_in);
             return true;
         } else {
-            (void)g; (void)in; (void)aux; (void)tw_nk; (void)out; (void)planes; (void)threads; (void)st; (void)err;
+            (void)g; (void)in; (void)aux; (void)tw_nk; (void)out; (void)planes; (void)threads; (void)exp_in; (void)st; (void)err;
             return false;
         }
     }
     static cudaError_t rows_fwd(const JbGeom& g, const double* x, const double* wgt, const cd* tw_nk, cd* bufB,
-                                int planes, int rpc, int threads, int fast, jb_stream_t st) {
+                                int planes, int rpc, int threads, int fast, int exp_in, jb_stream_t st) {
         dim3 grid(jb_cdiv(g.N, rpc), planes);
         cudaError_t e2;
-        if (fast && rows_in_pf<false>(g, x, wgt, tw_nk, bufB, planes, threads, st, &e2)) return e2;
-        if constexpr (FP::R2 > 1) {
-            if (fast) return jb_launch(k_rows_fwd2<FP>, grid, dim3(threads), smem_rows_in(g, rpc, 1), st, g, x, wgt,
-                                       tw_nk, bufB, rpc);
-        }
-        return jb_launch(k_rows_fwd<FP>, grid, dim3(threads), smem_rows_in(g, rpc, 0), st, g, x, wgt, tw_nk, bufB, rpc);
+        if (fast && rows_in_pf<false>(g, x, wgt, tw_nk, bufB, planes, threads, exp_in, st, &e2)) return e2;
+        return jb_launch(k_rows_fwd<FP>, grid, dim3(threads), smem_rows_in(g, rpc), st, g, x, wgt, tw_nk, bufB, rpc, exp_in);
     }
     static cudaError_t rows_adj_in(const JbGeom& g, const double* gin, const double* expo, const cd* tw_nk,
                                    cd* bufA, int planes, int rpc, int threads, int fast, jb_stream_t st) {
         dim3 grid(jb_cdiv(g.N, rpc), planes);
         cudaError_t e2;
-        if (fast && rows_in_pf<true>(g, gin, expo, tw_nk, bufA, planes, threads, st, &e2)) return e2;
-        if constexpr (FP::R2 > 1) {
-            if (fast) return jb_launch(k_rows_adj_in2<FP>, grid, dim3(threads), smem_rows_in(g, rpc, 1), st, g, gin,
-                                       expo, tw_nk, bufA, rpc);
-        }
-        return jb_launch(k_rows_adj_in<FP>, grid, dim3(threads), smem_rows_in(g, rpc, 0), st, g, gin, expo, tw_nk,
-                         bufA, rpc);
+        if (fast && rows_in_pf<true>(g, gin, expo, tw_nk, bufA, planes, threads, 0, st, &e2)) return e2;
+        return jb_launch(k_rows_adj_in<FP>, grid, dim3(threads), smem_rows_in(g, rpc), st, g, gin, expo, tw_nk, bufA, rpc);
     }
     static cudaError_t cols(const JbGeom& g, bool adj, const cd* in, cd* out, const cd* khat, const cd* tw_nk,
                             const double* wgt, int planes, int threads, jb_stream_t st) {
@@ -198,102 +148,32 @@ struct JbOpsImpl {
                                 int rpc, int threads, int fast, jb_stream_t st) {
         size_t B = (size_t)rpc * g.n;
         dim3 grid(jb_cdiv(g.N, rpc), planes);
-        size_t common = jb_al16(B * FP::LS * sizeof(cd)) + jb_al16(B * g.P * sizeof(double)) +
-                        jb_al16((size_t)threads * sizeof(double));
         if constexpr (FP::R2 > 1) {
-            if (fast) return jb_launch(k_rows_out2<FP>, grid, dim3(threads), common + rowtab_bytes(rpc), st, g, bufA,
-                                       tw_kn, ep, rpc);
+            if (fast) {
+                size_t common = jb_al16(B * FP::LS * sizeof(cd)) + jb_al16(B * g.P * sizeof(double)) +
+                                jb_al16((size_t)threads * sizeof(double));
+                return jb_launch(k_rows_out2<FP>, grid, dim3(threads), common + rowtab_bytes(rpc), st, g, bufA, tw_kn, ep, rpc);
+            }
         }
-        size_t smem = common + sizeof(int) * (rpc + 2 * (size_t)rpc * g.n) + 16;
-        return jb_launch(k_rows_out<FP>, grid, dim3(threads), smem, st, g, bufA, tw_kn, ep, rpc);
+        return jb_launch(k_rows_out<FP>, grid, dim3(threads), smem_rows_out_generic(g, rpc, threads), st, g, bufA, tw_kn, ep, rpc);
     }
     static cudaError_t rows_adj_out(const JbGeom& g, const cd* bufB, const double* wgt, const cd* tw_kn,
-                                    double* grad, int planes, int rpc, int threads, int fast, jb_stream_t st) {
+                                    double* grad, const double* logsky, int planes, int rpc, int threads, int fast,
+                                    jb_stream_t st) {
         size_t B = (size_t)rpc * g.n;
         dim3 grid(jb_cdiv(g.N, rpc), planes);
-        size_t common = jb_al16(B * FP::LS * sizeof(cd)) + jb_al16(B * g.w * sizeof(double));
         if constexpr (FP::R2 > 1) {
-            if (fast) return jb_launch(k_rows_adj_out2<FP>, grid, dim3(threads), common + rowtab_bytes(rpc), st, g,
-                                       bufB, wgt, tw_kn, grad, rpc);
+            if (fast) {
+                size_t common = jb_al16(B * FP::LS * sizeof(cd)) + jb_al16(B * g.w * sizeof(double));
+                return jb_launch(k_rows_adj_out2<FP>, grid, dim3(threads), common + rowtab_bytes(rpc), st, g,
+                                 bufB, wgt, tw_kn, grad, logsky, rpc);
+            }
         }
-        size_t smem = common + sizeof(int) * (rpc + 2 * (size_t)rpc * g.n) + 16;
-        return jb_launch(k_rows_adj_out<FP>, grid, dim3(threads), smem, st, g, bufB, wgt, tw_kn, grad, rpc);
+        return jb_launch(k_rows_adj_out<FP>, grid, dim3(threads), smem_rows_adj_out_generic(g, rpc), st, g, bufB, wgt, tw_kn,
+                         grad, logsky, rpc);
     }
-    static size_t al128(size_t x) { return (x + 127) & ~(size_t)127; }
-    static size_t rows_out_pipe_smem(const JbGeom& g, int Q) {
-        if (FP::R2 == 1) return (size_t)1 << 30;
-        return al128(2 * (size_t)g.n * Q * g.PH * sizeof(cd)) + al128((size_t)g.n * FP::LS * sizeof(cd)) +
-               al128((size_t)g.n * g.P * sizeof(double)) + al128(JB_RP_THREADS * sizeof(double)) + 64 +
-               2 * sizeof(JbRowInfo) + 2 * (size_t)g.N + 64;
-    }
-    static size_t rows_adj_out_pipe_smem(const JbGeom& g, int Q) {
-        if (FP::R2 == 1 || g.n * FP::H1 > JB_RP_THREADS) return (size_t)1 << 30;
-        return al128(2 * (size_t)g.n * Q * g.PH * sizeof(cd)) + al128((size_t)g.n * FP::LS * sizeof(cd)) +
-               al128((size_t)g.n * g.w * sizeof(double)) + 64 + 2 * sizeof(JbRowInfo) + 2 * (size_t)g.N + 64;
-    }
-    static cudaError_t rows_out_pipe(const JbGeom& g, const cd* bufA, const cd* tw_kn, const JbEpi& ep, int planes,
-                                     int Q, int ctas, jb_stream_t st) {
-        if constexpr (FP::R2 > 1) {
-            return jb_launch(k_rows_out3<FP>, dim3(ctas), dim3(JB_RP_THREADS), rows_out_pipe_smem(g, Q), st, g, bufA,
-                             tw_kn, ep, planes, Q);
-        } else {
-            (void)g; (void)bufA; (void)tw_kn; (void)ep; (void)planes; (void)Q; (void)ctas; (void)st;
-            return (cudaError_t)1;
-        }
-    }
-    static cudaError_t rows_adj_out_pipe(const JbGeom& g, const cd* bufB, const double* wgt, const cd* tw_kn,
-                                         double* grad, int planes_se, int Q, int ctas, jb_stream_t st) {
-        if constexpr (FP::R2 > 1) {
-            return jb_launch(k_rows_adj_out3<FP>, dim3(ctas), dim3(JB_RP_THREADS), rows_adj_out_pipe_smem(g, Q), st, g,
-                             bufB, wgt, tw_kn, grad, planes_se, Q);
-        } else {
-            (void)g; (void)bufB; (void)wgt; (void)tw_kn; (void)grad; (void)planes_se; (void)Q; (void)ctas; (void)st;
-            return (cudaError_t)1;
-        }
-    }
-    static size_t rows_r3_common(const JbGeom& g, int Q, int width) {
-        if constexpr (PIPE == 2) {
-            const int NC = (g.n + 1) / 2, BP = F3::M * NC + 1;
-            if (F3::R1 * F3::R2 * NC > JB_R4_THREADS || F3::R1 * F3::R3 * NC > JB_R4_THREADS || F3::M * NC > JB_R4_THREADS ||
-                F3::L * NC > JB_R4_MAXEL * JB_R4_THREADS || g.n > 255 || g.N > JB_R4_MAXC * JB_R4_THREADS)
-                return (size_t)1 << 30;
-            (void)width;  // the real rows alias the complex tile
-            return al128((size_t)g.n * Q * g.PH * sizeof(cd)) + al128((size_t)F3::R1 * BP * sizeof(cd)) +
-                   al128((size_t)(F3::L + F3::M) * sizeof(cd)) + 64 + 2 * sizeof(JbRowInfo) + 2 * (size_t)g.N + 64;
-        } else {
-            (void)g; (void)Q; (void)width;
-            return (size_t)1 << 30;
-        }
-    }
-    static size_t rows_out_r3_smem(const JbGeom& g, int Q) { return rows_r3_common(g, Q, g.P); }
-    static size_t rows_adj_out_r3_smem(const JbGeom& g, int Q) { return rows_r3_common(g, Q, g.w); }
-    static cudaError_t rows_out_r3(const JbGeom& g, const cd* bufA, const cd* tw1, const cd* tw2, const JbEpi& ep,
-                                   int planes, int Q, int ctas, jb_stream_t st) {
-        if constexpr (PIPE == 2) {
-            return jb_launch(k_rows_out4<FP, F3>, dim3(ctas * JB_R4_CTAS_PER_SM), dim3(JB_R4_THREADS), rows_out_r3_smem(g, Q), st, g, bufA,
-                             tw1, tw2, ep, planes, Q);
-        } else {
-            (void)g; (void)bufA; (void)tw1; (void)tw2; (void)ep; (void)planes; (void)Q; (void)ctas; (void)st;
-            return (cudaError_t)1;
-        }
-    }
-    static cudaError_t rows_adj_out_r3(const JbGeom& g, const cd* bufB, const double* wgt, const cd* tw1, const cd* tw2,
-                                       double* grad, int planes_se, int Q, int ctas, jb_stream_t st) {
-        if constexpr (PIPE == 2) {
-            return jb_launch(k_rows_adj_out4<FP, F3>, dim3(ctas * JB_R4_CTAS_PER_SM), dim3(JB_R4_THREADS), rows_adj_out_r3_smem(g, Q), st, g,
-                             bufB, wgt, tw1, tw2, grad, planes_se, Q);
-        } else {
-            (void)g; (void)bufB; (void)wgt; (void)tw1; (void)tw2; (void)grad; (void)planes_se; (void)Q; (void)ctas; (void)st;
-            return (cudaError_t)1;
-        }
-    }
-    // sequences per warp: 1 for n <= 8 (CTAs of <= 4 warps, 28 warps per SM), else 2
     // sequences per warp of the c2r kernels: one for up to 8 packed pairs (n <= 16; more than 4 warps: the WIDE form)
-    static int rows5_sw(const JbGeom& g) {
-        if (getenv("JUBIK_B200_ROWS5_SW2")) return (g.n + 1) / 2 <= 4 ? 1 : 2;   // previous rule (tuning record)
-        return (g.n + 1) / 2 <= 8 ? 1 : 2;
-    }
-    static int rows6_sw(const JbGeom& g) { return (g.n + 1) / 2 <= 4 ? 1 : 2; }   // r2c v6 kernels: CTAs of <= 4 warps
+    static int rows5_sw(const JbGeom& g) { return (g.n + 1) / 2 <= 8 ? 1 : 2; }
     static size_t rows5_smem(const JbGeom& g) {
         if constexpr (PIPE == 2) {
             const int sw = rows5_sw(g), NC = (g.n + 1) / 2, NW = (NC + sw - 1) / sw;
@@ -325,83 +205,43 @@ struct JbOpsImpl {
     }
     template <int SW, bool ADJ>
     static cudaError_t rows5_launch(const JbGeom& g, const cd* src, const double* wgt, const cd* tw1, const cd* tw2,
-                                    const int* gtab, int gq, const JbEpi& ep, double* grad, int presum, int planes,
-                                    int n_sm, jb_stream_t st) {
+                                    const int* gtab, int gq, const JbEpi& ep, double* grad, const double* logsky,
+                                    int planes, int n_sm, jb_stream_t st) {
         const int NC = (g.n + 1) / 2, NW = (NC + SW - 1) / SW;
         const size_t smem = jb_rows5_smem<F3, SW>(g.n);
         auto go = [&](auto kern) {
             int grid = rows5_grid(kern, NW * 32, smem, (long)planes * g.N, n_sm);
-            return jb_launch(kern, dim3(grid), dim3(NW * 32), smem, st, g, src, tw1, tw2, wgt, gtab, gq, ep, grad, planes);
+            return jb_launch(kern, dim3(grid), dim3(NW * 32), smem, st, g, src, tw1, tw2, wgt, gtab, gq, ep, grad, logsky, planes);
         };
+        // heavy = transcendental epilogue: forward Poisson energy/cotangent, adjoint * exp(log_sky)
+        const bool heavy = ADJ ? (logsky != nullptr) : (ep.mode == JB_EPI_POISSON);
         if constexpr (SW == 1) {
-            if (NW > 4) {   // 5..8 warps per CTA
-                if constexpr (!ADJ) {
-                    if (ep.mode == JB_EPI_POISSON)
-                        return presum ? go(k_rows_c2r5<F3, 1, false, true, true, true>) : go(k_rows_c2r5<F3, 1, false, false, true, true>);
-                }
-                return presum ? go(k_rows_c2r5<F3, 1, ADJ, true, false, true>) : go(k_rows_c2r5<F3, 1, ADJ, false, false, true>);
-            }
+            if (NW > 4)   // 5..8 warps per CTA
+                return heavy ? go(k_rows_c2r5<F3, 1, ADJ, true, true>) : go(k_rows_c2r5<F3, 1, ADJ, false, true>);
         }
-        if constexpr (!ADJ) {
-            if (ep.mode == JB_EPI_POISSON)
-                return presum ? go(k_rows_c2r5<F3, SW, false, true, true>) : go(k_rows_c2r5<F3, SW, false, false, true>);
-        }
-        return presum ? go(k_rows_c2r5<F3, SW, ADJ, true, false>) : go(k_rows_c2r5<F3, SW, ADJ, false, false>);
+        return heavy ? go(k_rows_c2r5<F3, SW, ADJ, true>) : go(k_rows_c2r5<F3, SW, ADJ, false>);
     }
     static cudaError_t rows5_fwd(const JbGeom& g, const cd* bufA, const cd* tw1, const cd* tw2, const int* gtab, int gq,
-                                 const JbEpi& ep, int presum, int planes, int n_sm, jb_stream_t st) {
+                                 const JbEpi& ep, int planes, int n_sm, jb_stream_t st) {
         if constexpr (PIPE == 2) {
             if (rows5_sw(g) == 1)
-                return rows5_launch<1, false>(g, bufA, nullptr, tw1, tw2, gtab, gq, ep, nullptr, presum, planes, n_sm, st);
-            return rows5_launch<2, false>(g, bufA, nullptr, tw1, tw2, gtab, gq, ep, nullptr, presum, planes, n_sm, st);
+                return rows5_launch<1, false>(g, bufA, nullptr, tw1, tw2, gtab, gq, ep, nullptr, nullptr, planes, n_sm, st);
+            return rows5_launch<2, false>(g, bufA, nullptr, tw1, tw2, gtab, gq, ep, nullptr, nullptr, planes, n_sm, st);
         } else {
-            (void)g; (void)bufA; (void)tw1; (void)tw2; (void)gtab; (void)gq; (void)ep; (void)presum; (void)planes; (void)n_sm; (void)st;
+            (void)g; (void)bufA; (void)tw1; (void)tw2; (void)gtab; (void)gq; (void)ep; (void)planes; (void)n_sm; (void)st;
             return (cudaError_t)1;
         }
     }
     static cudaError_t rows5_adj(const JbGeom& g, const cd* bufB, const double* wgt, const cd* tw1, const cd* tw2,
-                                 const int* gtab, int gq, double* grad, int presum, int planes_se, int n_sm,
+                                 const int* gtab, int gq, double* grad, const double* logsky, int planes_se, int n_sm,
                                  jb_stream_t st) {
         if constexpr (PIPE == 2) {
             JbEpi ep; memset(&ep, 0, sizeof(ep));
             if (rows5_sw(g) == 1)
-                return rows5_launch<1, true>(g, bufB, wgt, tw1, tw2, gtab, gq, ep, grad, presum, planes_se, n_sm, st);
-            return rows5_launch<2, true>(g, bufB, wgt, tw1, tw2, gtab, gq, ep, grad, presum, planes_se, n_sm, st);
+                return rows5_launch<1, true>(g, bufB, wgt, tw1, tw2, gtab, gq, ep, grad, logsky, planes_se, n_sm, st);
+            return rows5_launch<2, true>(g, bufB, wgt, tw1, tw2, gtab, gq, ep, grad, logsky, planes_se, n_sm, st);
         } else {
-            (void)g; (void)bufB; (void)wgt; (void)tw1; (void)tw2; (void)gtab; (void)gq; (void)grad; (void)presum; (void)planes_se; (void)n_sm; (void)st;
-            return (cudaError_t)1;
-        }
-    }
-    static size_t rows6_smem(const JbGeom& g) {
-        if constexpr (PIPE == 2) {
-            const int sw = rows6_sw(g), NC = (g.n + 1) / 2, NW = (NC + sw - 1) / sw;
-            if (NW * 32 > 512 || F3::L > 65535) return (size_t)1 << 30;
-            return sw == 1 ? jb_rows6_smem<F3, 1>(g.n, g.N) : jb_rows6_smem<F3, 2>(g.n, g.N);
-        } else {
-            (void)g;
-            return (size_t)1 << 30;
-        }
-    }
-    template <int SW, bool ADJ>
-    static cudaError_t rows6_launch(const JbGeom& g, const double* in, const double* expo, const double* wgt,
-                                    const cd* tw1, const cd* tw2, cd* out, int planes, int n_sm, jb_stream_t st) {
-        const int NC = (g.n + 1) / 2, NW = (NC + SW - 1) / SW;
-        const size_t smem = jb_rows6_smem<F3, SW>(g.n, g.N);
-        auto kern = k_rows_r2c6<F3, SW, ADJ>;
-        int grid = rows5_grid(kern, NW * 32, smem, (long)planes * g.N, n_sm);
-        return jb_launch(kern, dim3(grid), dim3(NW * 32), smem, st, g, in, expo, wgt, tw1, tw2, out, planes);
-    }
-    static cudaError_t rows6(const JbGeom& g, int adj, const double* in, const double* expo, const double* wgt,
-                             const cd* tw1, const cd* tw2, cd* out, int planes, int n_sm, jb_stream_t st) {
-        if constexpr (PIPE == 2) {
-            if (rows6_sw(g) == 1) {
-                if (adj) return rows6_launch<1, true>(g, in, expo, wgt, tw1, tw2, out, planes, n_sm, st);
-                return rows6_launch<1, false>(g, in, expo, wgt, tw1, tw2, out, planes, n_sm, st);
-            }
-            if (adj) return rows6_launch<2, true>(g, in, expo, wgt, tw1, tw2, out, planes, n_sm, st);
-            return rows6_launch<2, false>(g, in, expo, wgt, tw1, tw2, out, planes, n_sm, st);
-        } else {
-            (void)g; (void)adj; (void)in; (void)expo; (void)wgt; (void)tw1; (void)tw2; (void)out; (void)planes; (void)n_sm; (void)st;
+            (void)g; (void)bufB; (void)wgt; (void)tw1; (void)tw2; (void)gtab; (void)gq; (void)grad; (void)logsky; (void)planes_se; (void)n_sm; (void)st;
             return (cudaError_t)1;
         }
     }
@@ -425,10 +265,8 @@ struct JbOpsImpl {
     }
     static const JbFftOps* table() {
         static const JbFftOps t = {FP::L, FP::R1, FP::R2, CB, FP::LS, (FP::R2 > 1 && PIPE == 2) ? 2 : 0, F3::R1, F3::R2, F3::R3,
-                                   rows_fwd, rows_adj_in, cols, cols_pipe,
-                                   rows_out, rows_adj_out, rows_out_pipe_smem, rows_adj_out_pipe_smem, rows_out_pipe,
-                                   rows_adj_out_pipe, rows_out_r3_smem, rows_adj_out_r3_smem, rows_out_r3, rows_adj_out_r3,
-                                   rows5_smem, rows5_gather, rows5_fwd, rows5_adj, rows6_smem, rows6, prep_rows, prep_cols};
+                                   rows_fwd, rows_adj_in, cols, cols_pipe, rows_out, rows_adj_out, rows_generic_smem,
+                                   rows5_smem, rows5_gather, rows5_fwd, rows5_adj, prep_rows, prep_cols};
         return &t;
     }
 };

@@ -1,8 +1,8 @@
 // rows5.cuh -- the two c2r row kernels (spectra -> image rows) with WARP-PRIVATE transforms.
 //
-// rows3.cuh ran one CTA-wide transform per image row: six block barriers around stages of one radix-8 butterfly
-// per thread, a single warp issuing the bulk copies, and an assembly stage that was mostly address arithmetic
-// (ncu r1f: 33 M warp instructions of which 7 M FP64, FP64 pipe 13 %, DRAM 27 %).  Here every warp owns SW packed
+// An earlier generation (round 1, rows3.cuh, removed) ran one CTA-wide transform per image row: six block barriers
+// around stages of one radix-8 butterfly per thread, a single warp issuing the bulk copies, and an assembly stage that
+// was mostly address arithmetic (ncu r1f: 33 M warp instructions of which 7 M FP64, FP64 pipe 13 %, DRAM 27 %).  Here every warp owns SW packed
 // complex sequences Z = X_a + i X_b (two Hermitian row spectra each, columns blocks i = 2c, 2c+1 of one image row):
 //   * the lanes read the <= JB_MAXQ covering row-patches (x modules in the adjoint) straight from HBM with
 //     coalesced 128-bit loads (no staging buffer, no mbarrier), sum them in registers and scatter Z[k], Z[L-k]
@@ -14,7 +14,8 @@
 //     cotangent) and the coalesced store.
 // A CTA = ceil(ceil(n/2)/SW) warps = one image row per iteration; many small CTAs per SM hide the load latency.
 #pragma once
-#include "rows3.cuh"
+#include "rows_fast.cuh"
+#include "cols3.cuh"
 
 #ifndef JB_R5_B
 #define JB_R5_B 3     // spectrum elements x row-patches whose loads a lane keeps in flight (per sequence)
@@ -24,12 +25,6 @@
 #endif
 #ifndef JB_R5_AU
 #define JB_R5_AU 1    // unroll factor of the assembly loop over spectrum-element groups
-#endif
-#ifndef JB_R5_PF
-#define JB_R5_PF 0    // 1: prefetch the next row's sources into L2 (measured slower on B200: 122 -> 134 us, 72 -> 76 us)
-#endif
-#ifndef JB_R5_REV
-#define JB_R5_REV 0   // 1: walk the image rows in descending order (L2 reuse of the column pass's last output; measured neutral)
 #endif
 #ifndef JB_R5_CPS
 #define JB_R5_CPS 6   // CTAs per SM the SW = 1 kernel is register-limited to
@@ -280,17 +275,16 @@ JB_D void jb_rows5_assemble(cd* tile, const cd* const (&pbase)[SW][2], const boo
 //   gtab: gather table [GQ][N] (jb_rows5_gather_table).
 // SW = 1: one sequence per warp, CTAs of <= 4 warps (n <= 8), 80 registers so that 6 CTAs = 24 warps fit an SM;
 // SW = 2: two sequences per warp for wider patch grids (up to 16 warps per CTA).
-// PRESUM: the source is the column pass's summed buffer (sweep mode).
-// POIS: the fused Poisson energy/cotangent epilogue is compiled in (its log/divide raise the register pressure).
+// POIS: the transcendental epilogue is compiled in (it raises the register pressure, so the plain variants stay lean):
+//   forward -- the fused Poisson energy / cotangent (log, divide); adjoint -- the VJP of the sky-model tail, * exp(log_sky).
 // WIDE (SW = 1 only): CTAs of 5..8 warps (patch grids of 9..16 per axis, e.g. the 10x10 of the eROSITA-like configs):
 // still one sequence per warp and 80 registers, so that e.g. 3 CTAs x 5 warps share an SM at L = 672 where the
 // SW = 2 form (3 warps per CTA, 110-128 registers) keeps 9 warps resident.
-template <class F3, int SW, bool ADJ, bool PRESUM, bool POIS, bool WIDE = false>
+template <class F3, int SW, bool ADJ, bool POIS, bool WIDE = false>
 JB_GLOBAL void JB_LB((SW == 1 ? (WIDE ? 256 : 128) : 512), (SW == 1 ? (WIDE ? 3 : JB_R5_CPS) : 1))
 k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, const cd* __restrict__ tw2,
             const double* __restrict__ wgt, const int* __restrict__ gtab, int GQ, JbEpi ep, double* __restrict__ grad,
-            int planes) {
-    constexpr bool presum = PRESUM;
+            const double* __restrict__ logsky, int planes) {
     using R = Rows5<F3, SW>;
     JB_SMEM(unsigned char, smraw);
     const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH;
@@ -305,10 +299,9 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
     const int shift = ADJ ? hp : hp + m;         // u = r + shift - offs[j]
     const int p0 = ADJ ? m : 0;                  // valid window samples [p0, p0 + ROWS)
     const size_t nn2 = (size_t)n * n;
-    // source layout: per-patch rows (planes, n*n, ROWS, PH), or -- presum -- the column pass's buffer of spectra
-    // already summed over the covering row-patches (and row-weighted in the adjoint): (planes*n, N, PH)
-    const size_t plane_sz = presum ? (size_t)n * N * PH : nn2 * ROWS * PH;
-    const size_t istride = presum ? (size_t)N * PH : (size_t)n * ROWS * PH;
+    // source layout: per-patch rows (planes, n*n, ROWS, PH)
+    const size_t plane_sz = nn2 * ROWS * PH;
+    const size_t istride = (size_t)n * ROWS * PH;
     for (int i = tid; i < R::NE * 32; i += NT) {
         int k = i;   // e*32 + lane == frequency
         unsigned lo = (k < R::PHL) ? (unsigned)R::addr_of_freq(k) : 0u;
@@ -326,9 +319,7 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
     JB_SYNC();
     const long nitems = (long)planes * N;
     for (long it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
-        // walk the rows in DESCENDING order: the column pass wrote the planes in ascending order, so the last plane
-        // is still (partly) L2-resident when this kernel starts -- consume it first instead of evicting it
-        const long item = JB_R5_REV ? nitems - 1 - it_ : it_;
+        const long item = it_;
         const int lp = (int)(item / N), r = (int)(item - (long)lp * N);
         // ---- sources of this row (uniform over the CTA)
         int rowoff[JB_MAXQ];
@@ -345,7 +336,6 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
                 ++cnt;
             }
         }
-        if (presum && cnt > 0) { cnt = 1; rowoff[0] = r * PH; wr[0] = 1.0; }
         int ste = 0, te = 0, se = 0, T = 1;
         const cd* plane0;
         size_t tstride = 0;
@@ -366,44 +356,10 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
             pbase[s][0] = plane0 + (size_t)(has[s][0] ? ia : 0) * istride;
             pbase[s][1] = plane0 + (size_t)(has[s][1] ? ia + 1 : 0) * istride;
         });
-#if !defined(JB_EMU) && JB_R5_PF
-        // warm L2 with the NEXT row's sources (one bulk prefetch per source row, no registers / shared memory): the
-        // seven dependent load round trips of that row then cost an L2 hit instead of a DRAM access each
-        {
-            const long nxt = JB_R5_REV ? item - (long)gridDim.x : item + (long)gridDim.x;
-            if (nxt >= 0 && nxt < nitems) {
-                const int lp2 = (int)(nxt / N), r2 = (int)(nxt - (long)lp2 * N);
-                const cd* pl2;
-                if (!ADJ) {
-                    int a_, b_, c_;
-                    jb_map_ste(g, lp2, a_, b_, c_);
-                    pl2 = src + (size_t)a_ * plane_sz;
-                } else {
-                    int s2_, e2_;
-                    jb_map_se(g, lp2, s2_, e2_);
-                    pl2 = src + ((size_t)(s2_ * g.T) * g.E + e2_) * plane_sz;
-                }
-                // lane -> (sequence s, row a/b, module t, candidate row-patch j): at most SW*2*T*n work items
-                const int per = 2 * n;
-                for (int idx = lane; idx < SW * per * T; idx += 32) {
-                    const int t = idx / (SW * per), rem = idx - t * (SW * per);
-                    const int s = rem / per, rem2 = rem - s * per, ab = rem2 / n, j = rem2 - ab * n;
-                    const int ia = 2 * (wid * SW + s) + ab;
-                    const int u = r2 + shift - g.offs[j];
-                    if (ia < n && u >= 0 && u < ROWS) {
-                        const cd* ps = pl2 + (size_t)t * tstride + (size_t)ia * istride +
-                                       (presum ? (size_t)r2 * PH : ((size_t)j * ROWS + u) * PH);
-                        if (!presum || j == 0 || r2 + shift - g.offs[j - 1] >= ROWS || true)
-                            jb_bulk_prefetch_l2(ps, (uint32_t)(PH * sizeof(cd)));
-                    }
-                }
-            }
-        }
-#endif
 #if !defined(JB_EMU) && JB_R5_EPF
         // the epilogue's operands (exposure, counts / lambda of this image row: N*8 bytes each) are independent of the
         // transform: one bulk L2 prefetch each now, so that the pixel loop behind the block barrier finds them in L2
-        if (!ADJ && POIS && tid == 0 && ep.mode == JB_EPI_POISSON) {
+        if (!ADJ && POIS && tid == 0) {
             jb_bulk_prefetch_l2(ep.expo + ((size_t)te * N + r) * N, (uint32_t)(N * sizeof(double)));
             jb_bulk_prefetch_l2(ep.data + ((size_t)te * N + r) * N, (uint32_t)(N * sizeof(double)));
         }
@@ -430,24 +386,19 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
                 if (q < GQ) conv += tr[jb_ldg(gtab + q * N + c)];
             });
             if (ADJ) {
+                if (POIS) conv *= exp(jb_ldg(logsky + orow + c));   // VJP of x = exp(log_sky) (sky_models.py:340-341)
                 grad[orow + c] = conv;
-            } else if (ep.mode == JB_EPI_PSF) {
-                ep.out[orow + c] = conv;
-            } else {
+            } else if (POIS) {  // JB_EPI_POISSON: energy partial + cotangent expo * (1 - d / lambda)
                 const double ex = jb_ldg(ep.expo + erow + c);
                 double o = 0.0;
-                if (ep.mode == JB_EPI_RESP) {
-                    if (ex != 0.0) o = ex * conv;
-                } else if (ep.mode == JB_EPI_METRIC) {
-                    if (ex != 0.0) o = ex * (ex * conv) / ep.lam[orow + c];
-                } else if (POIS) {  // JB_EPI_POISSON: energy partial + cotangent expo * (1 - d / lambda)
-                    if (ex != 0.0) {
-                        const double lam = ex * conv, d = jb_ldg(ep.data + erow + c);
-                        esum += lam - d * log(lam);
-                        o = ex * (1.0 - d / lam);
-                    }
+                if (ex != 0.0) {
+                    const double lam = ex * conv, d = jb_ldg(ep.data + erow + c);
+                    esum += lam - d * log(lam);
+                    o = ex * (1.0 - d / lam);
                 }
                 ep.out[orow + c] = o;
+            } else {
+                ep.out[orow + c] = jb_epi_pixel(ep, conv, orow + c, erow + c);
             }
         }
         if (!ADJ && POIS) {
@@ -455,27 +406,6 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
             if (tid == 0) ep.partial[(size_t)ste * N + r] = tot;
         } else {
             JB_SYNC();   // the gather has read the tiles before the next row is assembled into them
-        }
-    }
-    if (!ADJ && POIS && ep.energy) {
-        // fused final reduction: the last CTA to get here sums all per-row partials in a fixed order
-        JB_SYNC();
-        if (tid == 0) {
-            jb_threadfence();
-            red[0] = (jb_atomic_inc(ep.counter) == gridDim.x - 1) ? 1.0 : 0.0;
-        }
-        JB_SYNC();
-        const bool last = red[0] != 0.0;
-        JB_SYNC();
-        if (last) {
-            jb_threadfence();
-            for (int s = 0; s < ep.n_samples; ++s) {
-                double acc = 0.0;
-                for (int i = tid; i < ep.per_sample; i += NT) acc += jb_ld_cg_f64(ep.partial + (size_t)s * ep.per_sample + i);
-                double tot = jb_block_sum(acc, red);
-                if (tid == 0) ep.energy[s] = tot;
-            }
-            if (tid == 0) *ep.counter = 0u;
         }
     }
 }

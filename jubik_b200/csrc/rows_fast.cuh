@@ -115,91 +115,9 @@ JB_D void jb_store_half_row(cd* row, const cd (&u)[FP::R2], int k1) {
     });
 }
 
-// ------------------------------------------------------------ forward: sky rows -> spectra (r2c)
-// grid (ceil(N/rpc), S*E); dyn smem = B*LS*16.  rowsF:(S*E, n, N, PH), one row per (image row, column block).
-template <class FP>
-JB_GLOBAL void JB_LB(256, 2) k_rows_fwd2(JbGeom g, const double* __restrict__ x, const double* __restrict__ wgt,
-                           const cd* __restrict__ tw_nk, cd* __restrict__ rowsF, int rpc) {
-    constexpr int R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
-    JB_SMEM(unsigned char, smraw);
-    const int n = g.n, N = g.N, m = g.m, w = g.w, hp = g.hp, PH = g.PH;
-    const int B = rpc * n;
-    cd* sm = reinterpret_cast<cd*>(smraw);
-    int s_, e_;
-    const int r0 = blockIdx.x * rpc, se = jb_map_se(g, blockIdx.y, s_, e_);
-    const double* xp = x + (size_t)se * N * N;
-    for (int it = jb_tid(); it < B * R2; it += jb_nthr()) {
-        int b = it / R2, n2 = it - b * R2;
-        int rr = b / n, i = b - rr * n, r = r0 + rr;
-        // element p = R2*n1 + n2 of the zero-padded window row: q = p - m in [0,w), column c = offs[i]-hp+q in [0,N)
-        int q0 = n2 - m, c0 = g.offs[i] - hp + q0;
-        const double* px = xp + (size_t)(r < N ? r : 0) * N + c0;
-        const double* pw = wgt + q0;
-        double xv[R1];
-        static_for<0, R1>([&](auto nn) {
-            constexpr int n1 = nn;
-            int q = q0 + R2 * n1, c = c0 + R2 * n1;
-            bool ok = (r < N) && q >= 0 && q < w && c >= 0 && c < N;
-            xv[n1] = ok ? jb_ldg(px + R2 * n1) * jb_ldg(pw + R2 * n1) : 0.0;
-        });
-        jb_r2c_pass1<FP>(xv, sm + (size_t)b * LS + n2, jb_ldg(tw_nk + R2 + n2), jb_ldg(tw_nk + 2 * R2 + n2));
-    }
-    JB_SYNC();
-    for (int it = jb_tid(); it < B * H1; it += jb_nthr()) {
-        int b = it / H1, k1 = it - b * H1;
-        int rr = b / n, i = b - rr * n, r = r0 + rr;
-        cd u[R2];
-        jb_r2c_pass2<FP>(sm + (size_t)b * LS + k1 * R2P, u);
-        if (r < N) jb_store_half_row<FP>(rowsF + (((size_t)se * n + i) * N + r) * PH, u, k1);
-    }
-}
-
-// ------------------------------------------------------ adjoint: cotangent rows -> spectra (r2c)
-// grid (ceil(N/rpc), S*T*E).  rowsA:(STE, n, N, PH)
-template <class FP>
-JB_GLOBAL void JB_LB(256, 2) k_rows_adj_in2(JbGeom g, const double* __restrict__ gin, const double* __restrict__ expo,
-                              const cd* __restrict__ tw_nk, cd* __restrict__ rowsA, int rpc) {
-    constexpr int R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
-    JB_SMEM(unsigned char, smraw);
-    const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, P = g.P;
-    const int B = rpc * n;
-    cd* sm = reinterpret_cast<cd*>(smraw);
-    int ste, te, se_;
-    jb_map_ste(g, blockIdx.y, ste, te, se_);
-    const int r0 = blockIdx.x * rpc;
-    const double* gp = gin + (size_t)ste * N * N;
-    const double* ep = expo ? expo + (size_t)te * N * N : nullptr;
-    for (int it = jb_tid(); it < B * R2; it += jb_nthr()) {
-        int b = it / R2, n2 = it - b * R2;
-        int rr = b / n, i = b - rr * n, r = r0 + rr;
-        int c0 = g.offs[i] - hp - m + n2;
-        size_t rowoff = (size_t)(r < N ? r : 0) * N;
-        const double* pg = gp + rowoff + c0;
-        const double* pe = ep ? ep + rowoff + c0 : nullptr;
-        double xv[R1];
-        static_for<0, R1>([&](auto nn) {
-            constexpr int n1 = nn;
-            int p = n2 + R2 * n1, c = c0 + R2 * n1;
-            bool ok = (r < N) && p < P && c >= 0 && c < N;
-            double v = ok ? jb_ldg(pg + R2 * n1) : 0.0;
-            if (pe && ok) v *= jb_ldg(pe + R2 * n1);
-            xv[n1] = v;
-        });
-        jb_r2c_pass1<FP>(xv, sm + (size_t)b * LS + n2, jb_ldg(tw_nk + R2 + n2), jb_ldg(tw_nk + 2 * R2 + n2));
-    }
-    JB_SYNC();
-    for (int it = jb_tid(); it < B * H1; it += jb_nthr()) {
-        int b = it / H1, k1 = it - b * H1;
-        int rr = b / n, i = b - rr * n, r = r0 + rr;
-        cd u[R2];
-        jb_r2c_pass2<FP>(sm + (size_t)b * LS + k1 * R2P, u);
-        if (r < N) jb_store_half_row<FP>(rowsA + (((size_t)ste * n + i) * N + r) * PH, u, k1);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // Persistent r2c row kernel with the NEXT image row prefetched into shared memory (cp.async, no registers held).
-// ncu of k_rows_fwd2 / k_rows_adj_in2 (r1o): 58 % of the stall samples sit on the first use of the 24 strided global
+// ncu of the one-row-per-CTA predecessors (r1o): 58 % of the stall samples sit on the first use of the 24 strided global
 // loads of pass 1 and 10 % on EXIT (stores draining) -- four one-row CTAs per SM cannot hide a DRAM round trip.  Here a
 // CTA walks the (plane, image row) list with a stride of gridDim.x; while it transforms row k the 8 KB of row k+1 land
 // in the other half of a two-slot ring, and pass 1 reads its window elements from shared memory.
@@ -220,8 +138,9 @@ inline void jb_cp_async_wait1() {}
 
 template <class FP, bool ADJ>
 JB_GLOBAL void JB_LB(256, 2) k_rows_in_pf(JbGeom g, const double* __restrict__ in, const double* __restrict__ aux,
-                                          const cd* __restrict__ tw_nk, cd* __restrict__ rows, int planes) {
+                                          const cd* __restrict__ tw_nk, cd* __restrict__ rows, int planes, int exp_in) {
     // aux: forward = window weights (w); adjoint = effective exposure (T,E,N,N) to multiply the cotangent with, or null
+    // exp_in (forward): the input rows are log_sky; x = exp(log_sky) is formed in the shared-memory ring (sky_models.py:340-341)
     constexpr int R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
     JB_SMEM(unsigned char, smraw);
     const int n = g.n, N = g.N, m = g.m, w = g.w, hp = g.hp, PH = g.PH, P = g.P;
@@ -260,8 +179,12 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_in_pf(JbGeom g, const double* __restrict__ i
         jb_cp_async_commit();
         jb_cp_async_wait1();          // this thread's copies of the current row have landed ...
         JB_SYNC();                    // ... and so have everybody else's
-        const double* row = ring + (size_t)(k & 1) * N;
+        double* row = ring + (size_t)(k & 1) * N;
         const double* erow = ext + (size_t)(k & 1) * N;
+        if (!ADJ && exp_in) {
+            for (int c = jb_tid(); c < N; c += jb_nthr()) row[c] = exp(row[c]);
+            JB_SYNC();
+        }
         const int lp = idx / N, r = idx - lp * N;
         int te_;
         const int pl = plane_of(lp, te_);
@@ -386,25 +309,17 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_out2(JbGeom g, const cd* __restrict__ bufA, 
         }
         size_t o = ((size_t)ste * N + r) * N + c;
         size_t oe = ((size_t)te * N + r) * N + c;
-        if (ep.mode == JB_EPI_PSF) {
-            ep.out[o] = conv;
-        } else {
-            double ex = jb_ldg(ep.expo + oe);
-            if (ep.mode == JB_EPI_RESP) {
-                ep.out[o] = (ex != 0.0) ? ex * conv : 0.0;
-            } else if (ep.mode == JB_EPI_POISSON) {
-                double gout = 0.0;
-                if (ex != 0.0) {
-                    double lam = ex * conv, d = jb_ldg(ep.data + oe);
-                    esum += lam - d * log(lam);
-                    gout = ex * (1.0 - d / lam);
-                }
-                ep.out[o] = gout;
-            } else {
-                double gout = 0.0;
-                if (ex != 0.0) gout = ex * (ex * conv) / ep.lam[o];
-                ep.out[o] = gout;
+        if (ep.mode == JB_EPI_POISSON) {
+            const double ex = jb_ldg(ep.expo + oe);
+            double gout = 0.0;
+            if (ex != 0.0) {
+                double lam = ex * conv, d = jb_ldg(ep.data + oe);
+                esum += lam - d * log(lam);
+                gout = ex * (1.0 - d / lam);
             }
+            ep.out[o] = gout;
+        } else {
+            ep.out[o] = jb_epi_pixel(ep, conv, o, oe);
         }
     }
     if (ep.mode == JB_EPI_POISSON) {
@@ -417,7 +332,8 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_out2(JbGeom g, const cd* __restrict__ bufA, 
 // grid (ceil(N/rpc), S*E)
 template <class FP>
 JB_GLOBAL void JB_LB(256, 2) k_rows_adj_out2(JbGeom g, const cd* __restrict__ bufB, const double* __restrict__ wgt,
-                               const cd* __restrict__ tw_kn, double* __restrict__ grad, int rpc) {
+                               const cd* __restrict__ tw_kn, double* __restrict__ grad, const double* __restrict__ logsky,
+                               int rpc) {
     constexpr int L = FP::L, R1 = FP::R1, R2 = FP::R2, H1 = FP::H1, LS = FP::LS, R2P = FP::R2P;
     JB_SMEM(unsigned char, smraw);
     const int n = g.n, N = g.N, m = g.m, hp = g.hp, PH = g.PH, w = g.w;
@@ -488,6 +404,8 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_adj_out2(JbGeom g, const cd* __restrict__ bu
             int v = c + hp - g.offs[i];
             if (v >= 0 && v < w) acc += trow[(size_t)i * w - g.offs[i]];
         }
-        grad[((size_t)se * N + r) * N + c] = acc;
+        const size_t o = ((size_t)se * N + r) * N + c;
+        if (logsky) acc *= exp(jb_ldg(logsky + o));
+        grad[o] = acc;
     }
 }

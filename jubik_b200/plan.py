@@ -34,6 +34,8 @@ class RawPlan:
             pass
 
     def call(self, name, *args):
+        if not self.handle:
+            raise _lib.JubikError("plan is closed")
         check(self.lib, getattr(self.lib, name)(self.handle, *args))
 
     @property
@@ -43,7 +45,7 @@ class RawPlan:
 
 def make_desc(N, E, T, n_patches, margin, kernel_ptr, cropped, max_samples=1, exposure_ptr=None,
               exposure_cut=None, eff_area_ptr=None, pixel_area=1.0, data_ptr=None, data_is_int=False,
-              distances=(1.0, 1.0), fft_length=0, N1=None):
+              distances=(1.0, 1.0), fft_length=0, N1=None, flags=0):
     d = PlanDesc()
     d.n0, d.n1 = int(N), int(N if N1 is None else N1)
     d.n_energy, d.n_modules, d.max_samples = int(E), int(T), int(max_samples)
@@ -53,6 +55,7 @@ def make_desc(N, E, T, n_patches, margin, kernel_ptr, cropped, max_samples=1, ex
     d.has_exposure_cut = 0 if exposure_cut is None else 1
     d.exposure_cut = 0.0 if exposure_cut is None else float(exposure_cut)
     d.fft_length = int(fft_length)
+    d.flags = int(flags)
     d.d0, d.d1 = float(distances[0]), float(distances[1])
     d.pixel_area = float(pixel_area)
     d.kernel = kernel_ptr
@@ -70,11 +73,14 @@ class ResponsePlan:
     exposure : (T, E, N, N) raw exposures or None (PSF-only plan); thresholded with exposure_cut
                exactly like response.py:37-40 / :85-87 (mask == thresholded exposure == 0).
     data     : (T, E, N, N) dense counts (int64 or float64) or None.
+    host_call / metric / sharded : which optional staging the plan allocates at creation (JUBIK_PLAN_* flags of
+               include/jubik_b200.h): the host-buffer entry point, the metric's cached linearisation point, and the
+               sharded entry point's per-sample gradient staging + collective stream.  Nothing is allocated later.
     """
 
     def __init__(self, kernel, N, n_patches, margin, exposure=None, exposure_cut=None, eff_area=None,
                  pixel_area=1.0, data=None, max_samples=1, cropped=False, distances=(1.0, 1.0),
-                 fft_length=0):
+                 fft_length=0, host_call=False, metric=True, sharded=False):
         import torch
         lib = _lib.load()
         if not (kernel.is_cuda and kernel.dtype == torch.float64):
@@ -112,10 +118,14 @@ class ResponsePlan:
             keep.append(data)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
+            flags = ((_lib.PLAN_HOST_CALL if host_call else 0) | (_lib.PLAN_METRIC if (metric and exposure is not None) else 0) |
+                     (_lib.PLAN_SHARDED if sharded else 0))
             desc = make_desc(N, E, T, n_patches, margin, kernel.data_ptr(), cropped, max_samples, eptr,
-                             exposure_cut, fptr, pixel_area, dptr, data_is_int, distances, fft_length)
+                             exposure_cut, fptr, pixel_area, dptr, data_is_int, distances, fft_length, flags=flags)
             self.raw = RawPlan(lib, desc, stream)
         self.info = self.raw.info
+        self.cropped = bool(cropped)
+        self.n_patches, self.margin = int(n_patches), int(margin)
         del keep
 
     def _prep_data(self, data):
@@ -137,10 +147,21 @@ class ResponsePlan:
         import torch
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _sky(self, x):
+    def _call(self, name, *args):
+        """One C-ABI call with the plan's device current (a process may hold plans on several GPUs)."""
         import torch
-        if not (x.is_cuda and x.dtype == torch.float64):
-            raise TypeError("input must be a float64 CUDA tensor")
+        with torch.cuda.device(self.device):
+            self.raw.call(name, *args, self._stream())
+
+    def _on_device(self, t, what):
+        import torch
+        if not (t.is_cuda and t.dtype == torch.float64):
+            raise TypeError("%s must be a float64 CUDA tensor" % what)
+        if t.device != self.device:
+            raise ValueError("%s lives on %s but the plan on %s" % (what, t.device, self.device))
+
+    def _sky(self, x):
+        self._on_device(x, "input")
         squeeze = x.dim() == 3
         if squeeze:
             x = x.unsqueeze(0)
@@ -151,9 +172,7 @@ class ResponsePlan:
         return x.contiguous(), squeeze
 
     def _det(self, g):
-        import torch
-        if not (g.is_cuda and g.dtype == torch.float64):
-            raise TypeError("input must be a float64 CUDA tensor")
+        self._on_device(g, "input")
         squeeze = g.dim() == 4
         if squeeze:
             g = g.unsqueeze(0)
@@ -167,14 +186,14 @@ class ResponsePlan:
         import torch
         x, sq = self._sky(x)
         out = torch.empty((x.shape[0], self.T, self.E, self.N, self.N), dtype=torch.float64, device=self.device)
-        self.raw.call(name, C.c_void_p(x.data_ptr()), x.shape[0], C.c_void_p(out.data_ptr()), self._stream())
+        self._call(name, C.c_void_p(x.data_ptr()), x.shape[0], C.c_void_p(out.data_ptr()))
         return out[0] if sq else out
 
     def _adj(self, name, g):
         import torch
         g, sq = self._det(g)
         out = torch.empty((g.shape[0], self.E, self.N, self.N), dtype=torch.float64, device=self.device)
-        self.raw.call(name, C.c_void_p(g.data_ptr()), g.shape[0], C.c_void_p(out.data_ptr()), self._stream())
+        self._call(name, C.c_void_p(g.data_ptr()), g.shape[0], C.c_void_p(out.data_ptr()))
         return out[0] if sq else out
 
     # ---------------------------------------------------------------------------------- calls
@@ -194,10 +213,25 @@ class ResponsePlan:
 
     def set_data(self, data):
         data, is_int = self._prep_data(data)
-        self.raw.call("jubik_plan_set_data", C.c_void_p(data.data_ptr()),
-                      _lib.DATA_I64 if is_int else _lib.DATA_F64, self._stream())
+        self._call("jubik_plan_set_data", C.c_void_p(data.data_ptr()), _lib.DATA_I64 if is_int else _lib.DATA_F64)
         import torch
         torch.cuda.current_stream(self.device).synchronize()
+
+    def set_kernel(self, kernel, cropped=None):
+        """Replace the PSF kernels (same geometry) -- the dynamic-kernel call form R(x, k) of the eROSITA response
+        (erosita_response.py:349-350).  Redoes the PSF preparation and its FFT into the resident spectra."""
+        import torch
+        cropped = self.cropped if cropped is None else bool(cropped)
+        self._on_device(kernel, "kernel")
+        kernel = kernel.contiguous()
+        dx = int(self.N / self.n_patches)
+        exp = (self.T, self.n_patches ** 2, self.E) + ((2 * dx, 2 * dx) if cropped else (self.N, self.N))
+        if tuple(kernel.shape) != exp:
+            raise ValueError("kernel should have shape %s" % (exp,))
+        self._call("jubik_plan_set_kernel", C.c_void_p(kernel.data_ptr()), _lib.KERNEL_CROPPED if cropped else _lib.KERNEL_FULL)
+        info = PlanInfo()
+        check(self.raw.lib, self.raw.lib.jubik_plan_get_info(self.raw.handle, C.byref(info)))
+        self.info = self.raw.info = {k: getattr(info, k) for k, _ in PlanInfo._fields_}
 
     def energy_and_grad(self, x, need_grad=True, out_energy=None, out_grad=None):
         """Poisson energy sum(lambda) - d.log(lambda) per sample and its gradient w.r.t. the sky.
@@ -210,8 +244,11 @@ class ResponsePlan:
         grad = (out_grad if out_grad is not None else torch.empty_like(x)) if need_grad else None
         if energy.numel() != S or not energy.is_contiguous() or (need_grad and (grad.numel() != x.numel() or not grad.is_contiguous())):
             raise ValueError("output buffers must be contiguous and match (S,) / (S,E,N,N)")
-        self.raw.call("jubik_poisson_energy_and_grad", C.c_void_p(x.data_ptr()), S, C.c_void_p(energy.data_ptr()),
-                      C.c_void_p(grad.data_ptr()) if need_grad else None, self._stream())
+        self._on_device(energy, "out_energy")
+        if need_grad:
+            self._on_device(grad, "out_grad")
+        self._call("jubik_poisson_energy_and_grad", C.c_void_p(x.data_ptr()), S, C.c_void_p(energy.data_ptr()),
+                   C.c_void_p(grad.data_ptr()) if need_grad else None)
         if sq:
             return energy[0], (grad[0] if need_grad else None)
         return energy, grad
@@ -244,10 +281,11 @@ class ResponsePlan:
             raise ValueError("flat must be a contiguous float64 CUDA tensor of %d elements" % n)
         if grad_local is not None and (grad_local.numel() != x.numel() or not grad_local.is_contiguous()):
             raise ValueError("grad_local must be contiguous (S,E,N,N)")
-        self.raw.call("jubik_poisson_energy_and_grad_sharded", comm.handle if comm is not None else None,
-                      int(shard_mode), C.c_void_p(x.data_ptr()), S,
-                      C.c_void_p(grad_local.data_ptr()) if grad_local is not None else None,
-                      C.c_void_p(flat.data_ptr()), self._stream())
+        self._on_device(flat, "flat")
+        self._call("jubik_poisson_energy_and_grad_sharded", comm.handle if comm is not None else None,
+                   int(shard_mode), C.c_void_p(x.data_ptr()), S,
+                   C.c_void_p(grad_local.data_ptr()) if grad_local is not None else None,
+                   C.c_void_p(flat.data_ptr()))
         npx = self.E * self.N * self.N
         if shard_mode == _lib.SHARD_SAMPLES:
             R = comm.size if comm is not None else 1
@@ -260,9 +298,11 @@ class ResponsePlan:
         import torch
         x, sq = self._sky(x)
         v, _ = self._sky(v)
+        if v.shape != x.shape:
+            raise ValueError("x and v must have the same shape")
         out = torch.empty_like(x)
-        self.raw.call("jubik_poisson_metric_apply", C.c_void_p(x.data_ptr()), C.c_void_p(v.data_ptr()), x.shape[0],
-                      C.c_void_p(out.data_ptr()), self._stream())
+        self._call("jubik_poisson_metric_apply", C.c_void_p(x.data_ptr()), C.c_void_p(v.data_ptr()), x.shape[0],
+                   C.c_void_p(out.data_ptr()))
         return out[0] if sq else out
 
     def left_sqrt_metric(self, x, t):
@@ -270,9 +310,34 @@ class ResponsePlan:
         import torch
         x, sq = self._sky(x)
         t, _ = self._det(t)
+        if t.shape[0] != x.shape[0]:
+            raise ValueError("x and t must have the same number of samples")
         out = torch.empty_like(x)
-        self.raw.call("jubik_poisson_left_sqrt_metric", C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()), x.shape[0],
-                      C.c_void_p(out.data_ptr()), self._stream())
+        self._call("jubik_poisson_left_sqrt_metric", C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()), x.shape[0],
+                   C.c_void_p(out.data_ptr()))
+        return out[0] if sq else out
+
+    def set_point(self, x):
+        """Cache the linearisation point of the metric: one forward pass stores expo^2 / (R x).  NIFTy's CG applies the
+        metric 60-70 times per sample at a fixed position (eROSITA_demo.yaml:161)."""
+        x, _ = self._sky(x)
+        self._call("jubik_poisson_set_point", C.c_void_p(x.data_ptr()), x.shape[0])
+        self._point_S = x.shape[0]
+
+    def metric_at_point(self, v):
+        """R^T diag(1/lambda(x0)) R v at the point of the last set_point: one forward + one adjoint pass."""
+        import torch
+        v, sq = self._sky(v)
+        out = torch.empty_like(v)
+        self._call("jubik_poisson_metric_apply_at_point", C.c_void_p(v.data_ptr()), v.shape[0], C.c_void_p(out.data_ptr()))
+        return out[0] if sq else out
+
+    def left_sqrt_metric_at_point(self, t):
+        """R^T (t / sqrt(lambda(x0))) at the point of the last set_point: one adjoint pass."""
+        import torch
+        t, sq = self._det(t)
+        out = torch.empty((t.shape[0], self.E, self.N, self.N), dtype=torch.float64, device=self.device)
+        self._call("jubik_poisson_left_sqrt_metric_at_point", C.c_void_p(t.data_ptr()), t.shape[0], C.c_void_p(out.data_ptr()))
         return out[0] if sq else out
 
     def energy_and_grad_logsky(self, log_sky):
@@ -281,21 +346,30 @@ class ResponsePlan:
         s, sq = self._sky(log_sky)
         energy = torch.empty((s.shape[0],), dtype=torch.float64, device=self.device)
         grad = torch.empty_like(s)
-        self.raw.call("jubik_poisson_energy_and_grad_logsky", C.c_void_p(s.data_ptr()), s.shape[0],
-                      C.c_void_p(energy.data_ptr()), C.c_void_p(grad.data_ptr()), self._stream())
+        self._call("jubik_poisson_energy_and_grad_logsky", C.c_void_p(s.data_ptr()), s.shape[0],
+                   C.c_void_p(energy.data_ptr()), C.c_void_p(grad.data_ptr()))
         return (energy[0], grad[0]) if sq else (energy, grad)
 
     def energy_and_grad_host(self, x_host, energy_host, grad_host):
-        """End-to-end call on HOST tensors (pinned for full PCIe speed): H2D, kernels, D2H, sync."""
+        """End-to-end call on HOST tensors (pinned for full PCIe speed): H2D, kernels, D2H, sync.
+        x_host ([S,]E,N,N), energy_host (S,), grad_host like x_host or None: float64 CPU, contiguous."""
+        import torch
         S = x_host.shape[0] if x_host.dim() == 4 else 1
-        self.raw.call("jubik_poisson_energy_and_grad_host", C.c_void_p(x_host.data_ptr()), S,
-                      C.c_void_p(energy_host.data_ptr()),
-                      C.c_void_p(grad_host.data_ptr()) if grad_host is not None else None, self._stream())
+        if S > self.S_max:
+            raise ValueError("more samples than the plan's max_samples")
+        want = S * self.E * self.N * self.N
+        for name, t, numel in (("x_host", x_host, want), ("energy_host", energy_host, S), ("grad_host", grad_host, want)):
+            if t is None and name == "grad_host":
+                continue
+            if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous():
+                raise TypeError("%s must be a contiguous float64 CPU tensor" % name)
+            if t.numel() != numel:
+                raise ValueError("%s has %d elements, expected %d" % (name, t.numel(), numel))
+        self._call("jubik_poisson_energy_and_grad_host", C.c_void_p(x_host.data_ptr()), S,
+                   C.c_void_p(energy_host.data_ptr()),
+                   C.c_void_p(grad_host.data_ptr()) if grad_host is not None else None)
 
-    KERNEL_NAMES = {6: ("rows_fwd", "cols_fwd", "rows_out", "rows_adj_in", "cols_adj", "rows_adj_out"),
-                    7: ("rows_fwd", "cols_fwd", "rows_out", "reduce", "rows_adj_in", "cols_adj", "rows_adj_out"),
-                    8: ("rows_fwd", "cols_fwd", "rows_out", "poisson_epi", "reduce", "rows_adj_in", "cols_adj",
-                        "rows_adj_out")}
+    KERNEL_NAMES = {7: ("rows_fwd", "cols_fwd", "rows_out", "reduce", "rows_adj_in", "cols_adj", "rows_adj_out")}
 
     def profile(self, x):
         """energy_and_grad with a CUDA event after each kernel -> (energy, grad, {kernel: ms})."""
@@ -306,17 +380,10 @@ class ResponsePlan:
         grad = torch.empty_like(x)
         ms = (C.c_float * 48)()
         n = C.c_int(0)
-        self.raw.call("jubik_poisson_profile", C.c_void_p(x.data_ptr()), S, C.c_void_p(energy.data_ptr()),
-                      C.c_void_p(grad.data_ptr()), ms, C.byref(n), self._stream())
+        with torch.cuda.device(self.device):
+            self.raw.call("jubik_poisson_profile", C.c_void_p(x.data_ptr()), S, C.c_void_p(energy.data_ptr()),
+                          C.c_void_p(grad.data_ptr()), ms, C.byref(n), self._stream())
         vals = [float(ms[i]) for i in range(n.value)]
-        E = self.info["E"]
-        if n.value in (6 * E, 6 * E + 1) and n.value not in self.KERNEL_NAMES:
-            # one energy bin at a time: (rows_fwd, cols_fwd, rows_out, rows_adj_in, cols_adj, rows_adj_out) x E, reduce
-            per = ("rows_fwd", "cols_fwd", "rows_out", "rows_adj_in", "cols_adj", "rows_adj_out")
-            out = {k: sum(vals[6 * e + i] for e in range(E)) for i, k in enumerate(per)}
-            if n.value == 6 * E + 1:
-                out["reduce"] = vals[-1]
-            return energy, grad, out
         names = self.KERNEL_NAMES.get(n.value, tuple("k%d" % i for i in range(n.value)))
         return energy, grad, dict(zip(names, vals))
 

@@ -51,14 +51,20 @@ class SampleShardedLikelihood:
         """x_local: this rank's samples (len(mine),E,N,N).
         Returns (energies of ALL samples (S,), sample-summed gradient (E,N,N) or the local gradients)."""
         import torch
-        e_loc, g_loc = self.plan.energy_and_grad(x_local)
-        e_all = torch.zeros((self.S,), dtype=e_loc.dtype, device=e_loc.device)
+        if x_local.shape[0] != len(self.mine):
+            raise ValueError("x_local holds %d samples but this rank owns %d" % (x_local.shape[0], len(self.mine)))
+        e_all = torch.zeros((self.S,), dtype=x_local.dtype, device=x_local.device)
         if len(self.mine):
+            e_loc, g_loc = self.plan.energy_and_grad(x_local)
             e_all[self.mine] = e_loc
+        else:
+            # a rank without samples (n_samples < world) contributes zeros but still enters every collective
+            g_loc = torch.zeros((0,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
         self.dist.all_reduce(e_all, group=self.group)
         if not reduce_grad:
             return e_all, g_loc
-        g_sum = g_loc.sum(0) if len(self.mine) else torch.zeros(g_loc.shape[1:], dtype=g_loc.dtype, device=g_loc.device)
+        g_sum = g_loc.sum(0) if len(self.mine) else torch.zeros(tuple(x_local.shape[1:]), dtype=x_local.dtype,
+                                                                 device=x_local.device)
         self.dist.all_reduce(g_sum, group=self.group)
         return e_all, g_sum
 
@@ -105,9 +111,32 @@ class NcclShardedLikelihood:
         self.mode = {"samples": _lib.SHARD_SAMPLES, "modules": _lib.SHARD_MODULES}[mode]
         self.comm = comm if comm is not None else Communicator.from_torch_distributed(group)
         self.flat = None
+        self.group = group
+        self._checked = None
+
+    def _check_uniform(self, S):
+        """Every rank must pass the same number of samples: the all-reduce count depends on it, and a mismatch would
+        hang or corrupt the collective.  Checked once per distinct S through torch.distributed (plumbing only)."""
+        if self._checked == S:
+            return
+        try:
+            import torch.distributed as dist
+            live = dist.is_available() and dist.is_initialized()
+        except Exception:
+            live = False
+        if live and self.comm.size > 1:
+            box = [None] * dist.get_world_size(self.group)
+            dist.all_gather_object(box, int(S), group=self.group)
+            if len(set(box)) != 1:
+                raise ValueError("NcclShardedLikelihood: ranks passed different sample counts %s" % (box,))
+        self._checked = S
 
     def energy_and_grad(self, x, grad_local=None):
         S = x.shape[0] if x.dim() == 4 else 1
+        if S < 1:
+            raise ValueError("NcclShardedLikelihood needs at least one sample per rank (use SampleShardedLikelihood "
+                             "for ragged partitions)")
+        self._check_uniform(S)
         n = self.plan.flat_size(self.comm, S, self.mode)
         if self.flat is None or self.flat.numel() != n:
             import torch

@@ -28,7 +28,7 @@ def _p(a):
 
 class EmuPlan:
     def __init__(self, kernel, N, n, m, exposure=None, exposure_cut=None, eff_area=None, pixel_area=1.0,
-                 data=None, max_samples=1, cropped=False, fft_length=0):
+                 data=None, max_samples=1, cropped=False, fft_length=0, flags=None):
         kernel = np.ascontiguousarray(kernel, dtype=np.float64)
         self.T, _, self.E = kernel.shape[:3]
         self.N, self.S_max = N, max_samples
@@ -41,7 +41,8 @@ class EmuPlan:
         desc = make_desc(N, self.E, self.T, n, m, kernel.ctypes.data, cropped, max_samples,
                          None if exposure is None else exposure.ctypes.data, exposure_cut,
                          None if eff_area is None else eff_area.ctypes.data, pixel_area,
-                         None if data is None else data.ctypes.data, is_int, fft_length=fft_length)
+                         None if data is None else data.ctypes.data, is_int, fft_length=fft_length,
+                         flags=(_lib.PLAN_METRIC | _lib.PLAN_SHARDED | _lib.PLAN_HOST_CALL) if flags is None else flags)
         self.raw = RawPlan(emu_lib(), desc, 0)
         self.info = self.raw.info
 
@@ -90,6 +91,43 @@ class EmuPlan:
         out = np.empty_like(x4)
         self.raw.call("jubik_poisson_metric_apply", _p(x4), _p(v4), x4.shape[0], _p(out), None)
         return out[0] if sq else out
+
+    def energy_and_grad_logsky(self, ls):
+        ls = np.ascontiguousarray(ls, dtype=np.float64)
+        sq = ls.ndim == 3
+        x4 = ls[None] if sq else ls
+        e = np.empty((x4.shape[0],))
+        g = np.empty_like(x4)
+        self.raw.call("jubik_poisson_energy_and_grad_logsky", _p(x4), x4.shape[0], _p(e), _p(g), None)
+        return (e[0], g[0]) if sq else (e, g)
+
+    def left_sqrt_metric(self, x, t):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        out = np.empty_like(x)
+        self.raw.call("jubik_poisson_left_sqrt_metric", _p(x), _p(t), x.shape[0], _p(out), None)
+        return out
+
+    def set_point(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self.raw.call("jubik_poisson_set_point", _p(x), x.shape[0], None)
+
+    def metric_at_point(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        out = np.empty_like(v)
+        self.raw.call("jubik_poisson_metric_apply_at_point", _p(v), v.shape[0], _p(out), None)
+        return out
+
+    def set_kernel(self, kernel, cropped):
+        kernel = np.ascontiguousarray(kernel, dtype=np.float64)
+        self.raw.call("jubik_plan_set_kernel", _p(kernel), _lib.KERNEL_CROPPED if cropped else _lib.KERNEL_FULL, None)
+
+    def energy_and_grad_host(self, x):
+        x4 = np.ascontiguousarray(x, dtype=np.float64)
+        e = np.empty((x4.shape[0],))
+        g = np.empty_like(x4)
+        self.raw.call("jubik_poisson_energy_and_grad_host", _p(x4), x4.shape[0], _p(e), _p(g), None)
+        return e, g
 
     def energy_and_grad_sharded(self, x, shard_mode, want_local=False):
         """Single-rank path of jubik_poisson_energy_and_grad_sharded (comm = NULL: no collective)."""

@@ -73,6 +73,10 @@ def _linear_transpose(fun, primal, cache=True):
     psize = int(np.prod(pshape))
     key = _closure_key(fun, pshape) if cache else None
     mat = _MATRIX_CACHE.get(key) if cache else None
+    if mat is None and psize > 20000:
+        mat = _gather_matrix(fun, pshape)       # large primal: exact matrix of a pure gather from ONE probe call
+        if mat is not None and cache:
+            _MATRIX_CACHE[key] = mat
     if mat is None:
         cols = []
         e = np.zeros(psize)
@@ -88,6 +92,28 @@ def _linear_transpose(fun, primal, cache=True):
         ct = np.asarray(ct, dtype=np.float64).reshape(-1)
         return ((mat @ ct).reshape(pshape),)
     return transposed
+
+
+def _gather_matrix(fun, pshape):
+    """Matrix of a linear map that is a pure GATHER (every output element is one input element or a padded zero),
+    e.g. the reference's slice_patches: apply the function once to the array of (flat index + 1); the output then
+    names the source of every output element.  Verified on a random vector before use (exact equality), so nothing
+    about the function is assumed: if it is not a gather the caller falls back to the basis-vector construction."""
+    import scipy.sparse as sp
+    psize = int(np.prod(pshape))
+    probe = np.arange(1, psize + 1, dtype=np.float64).reshape(pshape)
+    z = np.asarray(fun(probe)).reshape(-1)
+    zi = np.rint(z).astype(np.int64)
+    if not np.array_equal(zi.astype(np.float64), z) or zi.min() < 0 or zi.max() > psize:
+        return None
+    r = np.random.default_rng(123).normal(size=pshape)
+    want = np.asarray(fun(r)).reshape(-1)
+    got = np.where(zi > 0, r.reshape(-1)[np.maximum(zi - 1, 0)], 0.0)
+    if not np.array_equal(want, got):
+        return None
+    rows = np.nonzero(zi > 0)[0]
+    m = sp.csr_matrix((np.ones(rows.size), (rows, zi[rows] - 1)), shape=(z.size, psize))   # M: primal -> output
+    return m.T.tocsr()                                                                     # row k = image of basis k
 
 
 def _install_stand_ins():
@@ -184,6 +210,42 @@ def main():
                                cache=False)(g)[0]
         np.savez_compressed(os.path.join(OUT, name + ".npz"), x=x, kernel=kern, n=n, m=m,
                             distances=np.array(dom.distances), y=y, g=g, yT=yT)
+        print(name, y.shape, float(np.abs(y).max()))
+
+    # ---- the PRODUCTION pipelines pinned to the reference source directly: full-size geometries whose P is
+    # a compiled three-stage length, and small geometries that need the period-P alias fold.  Kernels come from
+    # tests/synth.py seeds (regenerated by the tests), so only x / y (/ g, yT) are stored.
+    sys.path.insert(0, os.path.abspath(os.path.join(OUT, "..", "..")))
+    from tests import synth
+    big = {
+        # name: (N, n, m, sig)                      P    what it pins
+        "lp_N256_n4_m16_wide": (256, 4, 16, (3.0, 12.0)),   # 160  BASELINE configs[0] (C1), PSF tails wrap around the period
+        "lp_N512_n4_m32_wide": (512, 4, 32, (4.0, 20.0)),   # 320  Chandra demo: sdim 512, npatch 4, margfrac 0.062 (chandra_demo.yaml:13,44-45)
+        "lp_N512_n8_m32_wide": (512, 8, 32, (4.0, 20.0)),   # 192  eROSITA demo: sdim 512, npatch 8 (eROSITA_demo.yaml:35-36,48)
+    }
+    for name, (N, n, m, sig) in big.items():
+        kern = synth.psf_full(1, n, 1, N, seed=1, sig=sig)[0]
+        x = synth.sky(1, 1, N, seed=0)[0]
+        dom = Domain((1, N, N), synth.DIST)
+        y = np.asarray(conv.linpatch_convolve(x, dom, kern, n, m))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), N=N, n=n, m=m, sig=np.array(sig), y=y,
+                            distances=np.array(dom.distances))
+        print(name, y.shape, float(np.abs(y).max()))
+    fold = {
+        # name: (E, N, n, m, sig): P is NOT a compiled length and the PSF half-support (dx) exceeds the margin
+        "lp_N62_n4_m9_fold": (1, 62, 4, 9, (2.0, 8.0)),     # P = 48 -> L = 96, ext = 6
+        "lp_N100_n5_m7_fold": (2, 100, 5, 7, (2.0, 10.0)),  # P = 54 -> L = 96, ext = 13
+    }
+    for name, (E, N, n, m, sig) in fold.items():
+        rng = np.random.default_rng(sum(map(ord, name)))
+        kern = synth.psf_full(1, n, E, N, seed=1, sig=sig)[0]
+        x = 5e-4 * np.exp(0.5 * rng.normal(size=(E, N, N)))
+        dom = Domain((E, N, N), synth.DIST)
+        y = np.asarray(conv.linpatch_convolve(x, dom, kern, n, m))
+        g = rng.normal(size=(E, N, N))
+        yT = _linear_transpose(lambda a: conv.linpatch_convolve(a, dom, kern, n, m), x, cache=False)(g)[0]
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), x=x, n=n, m=m, sig=np.array(sig), y=y, g=g, yT=yT,
+                            distances=np.array(dom.distances))
         print(name, y.shape, float(np.abs(y).max()))
 
     # slice_patches and its jax.linear_transpose, the fixture of test/test_slice_patches.py

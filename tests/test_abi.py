@@ -41,10 +41,26 @@ def test_library_contains_sm100a_code(lib_path):
 def test_supported_lengths_and_versions(lib_path):
     from jubik_b200 import _lib
     lib = _lib.load(require_device=False)
-    assert lib.jubik_version() >= 100
+    assert lib.jubik_version() >= 200
     for L in (160, 336, 384, 640, 672):     # P of BASELINE configs C1..C5 (332 -> 336, 664 -> 672)
         assert lib.jubik_fft_length_supported(L) == 1
+    for L in (192, 320):                    # the reference's shipped demos: 512^2 / 8x8 and 4x4, margfrac 0.062
+        assert lib.jubik_fft_length_supported(L) == 1     # (demos/configs/eROSITA_demo.yaml:35-36,48; chandra_demo.yaml:13,44-45)
+    for L in (96, 128, 256, 448, 512, 768, 896, 1024):
+        assert lib.jubik_fft_length_supported(L) == 1
     assert lib.jubik_fft_length_supported(332) == 0
+
+
+def test_kernel_selection_reads_no_environment():
+    """The plan is a pure function of its descriptor: no getenv on the product path.  The one
+    environment hook left names the NCCL library file to dlopen."""
+    csrc = os.path.join(ROOT, "jubik_b200", "csrc")
+    hits = []
+    for f in os.listdir(csrc):
+        for ln, line in enumerate(open(os.path.join(csrc, f)), 1):
+            if "getenv" in line:
+                hits.append((f, ln, line.strip()))
+    assert all("JUBIK_B200_NCCL_LIB" in h[2] for h in hits), hits
 
 
 @pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -29,10 +29,25 @@ def test_emulated_kernels_match_reference_golden(golden_dir, name):
     assert rel(p.psf_T(z["g"][None]), z["yT"]) < TOL
 
 
+@pytest.mark.parametrize("name", ["lp_N62_n4_m9_fold", "lp_N100_n5_m7_fold"])
+def test_emulated_alias_fold_matches_reference_golden(golden_dir, name):
+    """Period-P alias fold (P not a compiled length, PSF wider than the margin) against the reference source's output."""
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    x, n, m = z["x"], int(z["n"]), int(z["m"])
+    E, N = x.shape[0], x.shape[-1]
+    kern = synth.psf_full(1, n, E, N, seed=1, sig=tuple(z["sig"]))
+    p = EmuPlan(kern, N, n, m)
+    assert p.info["alias_fold"] == 1 and p.info["L"] == 96 and p.info["alias_ext"] == N // n - m
+    assert rel(p.psf(x)[0], z["y"]) < TOL
+    assert rel(p.psf_T(z["g"][None]), z["yT"]) < TOL
+
+
 @pytest.mark.parametrize("case", [
     (64, 4, 6, 2, 2, 2, False, True),     # P=44 -> padded L=160 (two-pass rows, three-stage TMA-pipelined columns in
                                           # their emulated form), compact PSF, S/T/E batching
-    (62, 4, 9, 1, 1, 1, True, False),     # N % n != 0, P = 48 is not compiled and the PSF is wider than the margin => clean error
+    (62, 4, 9, 1, 1, 1, True, False),     # N % n != 0, P = 48 is not compiled and the PSF is wider than the margin (half-support
+                                          # 15 > 9): period-P alias fold on L = 160 >= w + 2*support = 60
+    (64, 4, 3, 2, 1, 2, True, True),      # P = 38, full support 16 > 3: wide alias bands (ext = 13), T/S batching
 ])
 def test_emulated_two_pass_fft_against_oracle(case):
     N, n, m, T, E, S, full, eff = case
@@ -44,18 +59,17 @@ def test_emulated_two_pass_fft_against_oracle(case):
         kern, cropped = synth.psf_cropped(T, n, E, dx, half_support=m), True
     expo = synth.exposure(T, E, N)
     ea = synth.eff_area(T, E) if eff else None
-    if full:
-        from jubik_b200 import JubikError
-        with pytest.raises(JubikError, match="half-support"):
-            EmuPlan(kern, N, n, m, exposure=expo, exposure_cut=500.0, cropped=cropped)
-        return
     x = synth.sky(S, E, N)
     R = orc.Response(dom, kern, n, m, expo, 500.0, synth.PIXEL_AREA, eff_area=ea, cropped=cropped)
     d = synth.counts_from(R.dense(synth.sky(1, E, N, seed=5)[0]))
     p = EmuPlan(kern, N, n, m, exposure=expo, exposure_cut=500.0, eff_area=ea, pixel_area=synth.PIXEL_AREA,
                 data=d, max_samples=S, cropped=cropped, fft_length=160)
     assert p.info["L"] == 160 and p.info["exact_period"] == 0
+    assert p.info["alias_fold"] == (1 if full else 0)
+    if full:
+        assert p.info["alias_ext"] == dx - m and p.info["fast_path"] == 0
     g = synth.direction((S, T, E, N, N))
+    assert rel(p.psf_T(g), np.stack([R.psf_T(g[s]) for s in range(S)])) < TOL
     assert rel(p.psf(x), np.stack([R.psf(x[s]) for s in range(S)])) < TOL
     assert rel(p.response_T(g), np.stack([R.dense_T(g[s]) for s in range(S)])) < TOL
     e, gr = p.energy_and_grad(x)
@@ -63,7 +77,22 @@ def test_emulated_two_pass_fft_against_oracle(case):
     assert np.abs((e - np.array(eo)) / np.array(eo)).max() < TOL
     assert rel(gr, np.stack(go)) < TOL
     v = synth.direction((S, E, N, N), seed=9)
-    assert rel(p.metric(x, v), np.stack([orc.metric_apply(R, x[s], v[s]) for s in range(S)])) < TOL
+    mo = np.stack([orc.metric_apply(R, x[s], v[s]) for s in range(S)])
+    assert rel(p.metric(x, v), mo) < TOL
+    # cached linearisation point: set_point once, then any number of applies
+    p.set_point(x)
+    assert rel(p.metric_at_point(v), mo) < TOL
+    v2 = synth.direction((S, E, N, N), seed=10)
+    assert rel(p.metric_at_point(v2), np.stack([orc.metric_apply(R, x[s], v2[s]) for s in range(S)])) < TOL
+    assert rel(p.left_sqrt_metric(x, g), np.stack([orc.left_sqrt_metric(R, x[s], g[s]) for s in range(S)])) < TOL
+    # sky-model tail fused into the row kernels (exp on load, * exp(log_sky) on store)
+    ls = np.log(x)
+    el, gl = p.energy_and_grad_logsky(ls)
+    elo, glo = zip(*[orc.energy_and_grad_logsky(R, d, ls[s]) for s in range(S)])
+    assert np.abs((el - np.array(elo)) / np.array(elo)).max() < TOL
+    assert rel(gl, np.stack(glo)) < TOL
+    eh, gh = p.energy_and_grad_host(x)
+    assert np.array_equal(eh, e) and np.array_equal(gh, gr)
 
 
 def test_emulated_sharded_entry_point_single_rank():

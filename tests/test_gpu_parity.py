@@ -54,6 +54,50 @@ def test_golden_linpatch_forward_and_transpose(torch_cuda, golden_dir, name):
     plan.close()
 
 
+WIDE = ["lp_N256_n4_m16_wide", "lp_N512_n4_m32_wide", "lp_N512_n8_m32_wide"]
+
+
+@pytest.mark.parametrize("name", WIDE)
+def test_golden_production_pipeline_vs_reference_source(torch_cuda, golden_dir, name):
+    """The PRODUCTION kernels (TMA column pipeline, warp-private c2r rows, prefetching r2c rows; P = 160 / 320 / 192 are
+    three-stage lengths) against forward outputs of the reference's own convolve.py -- BASELINE configs[0] and the two
+    shipped demo geometries (512^2, npatch 4 / 8, margfrac 0.062: chandra_demo.yaml:13,44-45, eROSITA_demo.yaml:35-36,48)
+    with PSFs whose tails wrap around the period (full-support kernels in the reference layout)."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    N, n, m = int(z["N"]), int(z["n"]), int(z["m"])
+    kern = synth.psf_full(1, n, 1, N, seed=1, sig=tuple(z["sig"]))
+    x = synth.sky(1, 1, N, seed=0)[0]
+    plan = jb.ResponsePlan(dev(torch, kern), N, n, m)
+    assert plan.info["exact_period"] == 1 and plan.info["fast_path"] == 1 and plan.info["psf_half_support"] > m
+    assert rel(plan.psf(dev(torch, x))[0].cpu().numpy(), z["y"]) < TOL
+    # the transpose through the same kernels is the exact adjoint of that forward
+    g = dev(torch, synth.direction((1, 1, 1, N, N)))
+    xd = dev(torch, x[None])
+    lhs = torch.vdot(g.flatten(), plan.psf(xd).flatten())
+    rhs = torch.vdot(plan.psf_T(g).flatten(), xd.flatten())
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-12
+    plan.close()
+
+
+@pytest.mark.parametrize("name", ["lp_N62_n4_m9_fold", "lp_N100_n5_m7_fold"])
+def test_golden_alias_fold_vs_reference_source(torch_cuda, golden_dir, name):
+    """P is not a compiled length and the PSF is wider than the margin: linear convolution on L >= w + 2*support folded
+    modulo P, forward and transpose against the reference source's outputs."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    x, n, m = z["x"], int(z["n"]), int(z["m"])
+    E, N = x.shape[0], x.shape[-1]
+    kern = synth.psf_full(1, n, E, N, seed=1, sig=tuple(z["sig"]))
+    plan = jb.ResponsePlan(dev(torch, kern), N, n, m)
+    assert plan.info["alias_fold"] == 1 and plan.info["exact_period"] == 0 and plan.info["alias_ext"] == N // n - m
+    assert rel(plan.psf(dev(torch, x))[0].cpu().numpy(), z["y"]) < TOL
+    assert rel(plan.psf_T(dev(torch, z["g"][None])).cpu().numpy(), z["yT"]) < TOL
+    plan.close()
+
+
 # (N, n, m, T, E, S, full_support, eff_area)  -> FFT length exercised
 CASES = [
     (256, 4, 16, 1, 1, 1, True, False),    # C1: P=160 exact period, full-support PSF wraps around
@@ -64,6 +108,10 @@ CASES = [
     (768, 6, 64, 2, 1, 1, False, True),    # P=384, more patches, two modules
     (1024, 4, 64, 1, 1, 1, False, False),  # C4 patch geometry: P=640
     (816, 4, 128, 1, 1, 1, False, False),  # C5 patch geometry: P=664 -> L=672
+    (512, 8, 32, 2, 2, 2, True, True),     # eROSITA demo geometry: P=192 exact, full support, S/T/E batching
+    (512, 4, 32, 1, 3, 1, True, False),    # Chandra demo geometry: P=320 exact, full support, 3 bins
+    (408, 4, 64, 1, 2, 1, True, False),    # C3 patch geometry with a FULL-support PSF: P=332, alias fold on L=448
+    (1024, 8, 126, 1, 1, 1, False, False), # P=508 -> L=512 padded; (2048/16 patch geometry, odd demo margin)
 ]
 
 
@@ -90,7 +138,9 @@ def test_oracle_parity_all_entry_points(torch_cuda, case):
     dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
     plan = jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
                            eff_area=None if ea is None else dev(torch, ea), pixel_area=synth.PIXEL_AREA,
-                           data=dev(torch, d), max_samples=S, cropped=cropped)
+                           data=dev(torch, d), max_samples=S, cropped=cropped, host_call=True)
+    if full and plan.info["P"] != plan.info["L"]:
+        assert plan.info["alias_fold"] == 1 and plan.info["L"] >= plan.info["w"] + 2 * plan.info["psf_half_support"]
     xd = dev(torch, x)
     g = synth.direction((S, T, E, N, N))
     gd = dev(torch, g)
@@ -108,6 +158,13 @@ def test_oracle_parity_all_entry_points(torch_cuda, case):
     # left-sqrt-metric and the log-sky tail
     lo = np.stack([orc.left_sqrt_metric(R, x[s], g[s]) for s in range(S)])
     assert rel(plan.left_sqrt_metric(xd, gd).cpu().numpy(), lo) < TOL
+    # cached linearisation point (what NIFTy's CG does: one position, many applies)
+    plan.set_point(xd)
+    v2 = synth.direction((S, E, N, N), seed=10)
+    assert rel(plan.metric_at_point(dev(torch, v)).cpu().numpy(), mo) < TOL
+    assert rel(plan.metric_at_point(dev(torch, v2)).cpu().numpy(),
+               np.stack([orc.metric_apply(R, x[s], v2[s]) for s in range(S)])) < TOL
+    assert rel(plan.left_sqrt_metric_at_point(gd).cpu().numpy(), lo) < TOL
     ls = np.log(x)
     el, gl = plan.energy_and_grad_logsky(dev(torch, ls))
     elo, glo = zip(*[orc.energy_and_grad_logsky(R, d, ls[s]) for s in range(S)])
@@ -300,67 +357,171 @@ def test_full_size_geovi_batch_c5_per_gpu_share(torch_cuda):
     plan.close()
 
 
-@pytest.mark.parametrize("flag", ["JUBIK_B200_SWEEP", "JUBIK_B200_ROWS_R2C_V6", "JUBIK_B200_FUSED_REDUCE",
-                                  "JUBIK_B200_CHUNK_E", "JUBIK_B200_DEV_PLANES", "JUBIK_B200_COLS_PP", "JUBIK_B200_ROWS_IN_V2"])
-def test_optin_kernel_variants_match_oracle(torch_cuda, monkeypatch, flag):
-    """The measured-but-not-default kernel variants stay parity-green."""
-    _variant_parity(torch_cuda, monkeypatch, flag)
-
-
-def _variant_parity(torch_cuda, monkeypatch, flag):
-    import jubik_b200 as jb
-    torch = torch_cuda
-    monkeypatch.setenv(flag, "1")
-    case = (768, 6, 64, 2, 2, 1, False, True)
-    N, n, m, T, E, S, full, eff = case
-    dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
-    plan = jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
-                           eff_area=dev(torch, ea), pixel_area=synth.PIXEL_AREA, data=dev(torch, d), max_samples=S,
-                           cropped=cropped)
-    xd = dev(torch, x)
-    g = synth.direction((S, T, E, N, N))
-    assert rel(plan.psf(xd).cpu().numpy(), np.stack([R.psf(x[s]) for s in range(S)])) < TOL
-    assert rel(plan.response_T(dev(torch, g)).cpu().numpy(), np.stack([R.dense_T(g[s]) for s in range(S)])) < TOL
-    e, gr = plan.energy_and_grad(xd)
-    eo, go = orc.energy_and_grad(R, d, x[0])
-    assert abs(float(e[0]) - eo) / abs(eo) < TOL and rel(gr[0].cpu().numpy(), go) < TOL
-    plan.close()
-
-
-def test_plane_pipelined_device_path_is_bitwise_equal_to_batched(torch_cuda, monkeypatch):
-    """JUBIK_B200_DEV_PLANES: (sample, bin) planes alternating between two streams with two workspaces give exactly
-    the batched call's numbers (same kernels, same summation order), call after call."""
+def test_host_buffer_entry_point_is_bitwise_equal_to_device_call(torch_cuda):
+    """jubik_poisson_energy_and_grad_host: (sample, bin) planes alternating between two streams with two workspaces give
+    exactly the batched device call's numbers (same kernels, same summation order), call after call; and the entry
+    point refuses to run on a plan that was created without its staging (no allocation after plan creation)."""
     import jubik_b200 as jb
     torch = torch_cuda
     case = (512, 4, 64, 2, 3, 2, False, True)
     N, n, m, T, E, S, full, eff = case
     dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
 
-    def mk():
+    def mk(**kw):
         return jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
                                eff_area=dev(torch, ea), pixel_area=synth.PIXEL_AREA, data=dev(torch, d), max_samples=S,
-                               cropped=cropped)
+                               cropped=cropped, **kw)
     xd = dev(torch, x)
-    p0 = mk()
+    p0 = mk(host_call=True)
     e0, g0 = p0.energy_and_grad(xd)
-    # the host-buffer entry point runs the same pipeline (chunks of one or two energy bins on two streams) with copies
     xh = torch.as_tensor(x).pin_memory()
     eh = torch.empty((S,), dtype=torch.float64).pin_memory()
     gh = torch.empty_like(xh).pin_memory()
-    for pair in (False, True):
-        if pair:
-            monkeypatch.setenv("JUBIK_B200_HOST_PAIR_PLANES", "1")     # chunks of two bins (Es = 2 of E = 3)
-        for _ in range(2):
-            gh.zero_()
-            p0.energy_and_grad_host(xh, eh, gh)
-            assert torch.equal(eh, e0.cpu()) and torch.equal(gh, g0.cpu())
-    monkeypatch.setenv("JUBIK_B200_DEV_PLANES", "1")
-    p1 = mk()
     for _ in range(3):
-        e1, g1 = p1.energy_and_grad(xd)
-        assert torch.equal(e0, e1) and torch.equal(g0, g1)
+        gh.zero_()
+        p0.energy_and_grad_host(xh, eh, gh)
+        assert torch.equal(eh, e0.cpu()) and torch.equal(gh, g0.cpu())
+    with pytest.raises((TypeError, ValueError)):            # undersized / wrong-device buffers are rejected in Python
+        p0.energy_and_grad_host(xh, eh[:1], gh)
+    with pytest.raises((TypeError, ValueError)):
+        p0.energy_and_grad_host(xd, eh, gh)
+    bytes_before = p0.info["bytes_total"]
+    p1 = mk()
+    assert p1.info["bytes_total"] < bytes_before
+    with pytest.raises(jb.JubikError, match="JUBIK_PLAN_HOST_CALL"):
+        p1.energy_and_grad_host(xh, eh, gh)
     p0.close()
     p1.close()
+
+
+def test_set_kernel_and_linpatch_cache_never_confuse_two_psfs(torch_cuda):
+    """The eROSITA call form has the kernel as a DYNAMIC argument (erosita_response.py:349-350): jubik_plan_set_kernel
+    swaps the PSF of a live plan, and linpatch_convolve called with two different NumPy kernels of identical shape
+    (fresh device temporaries that may reuse one address -- ADVICE r1) returns two different, correct results."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    N, n, m, E = 256, 4, 16, 1
+    dom_o = orc.Domain((E, N, N), synth.DIST)
+    dom = jb.Domain(dom_o.shape, dom_o.distances)
+    k1 = synth.psf_full(1, n, E, N, seed=1)[0]
+    k2 = synth.psf_full(1, n, E, N, seed=77, sig=(2.0, 9.0))[0]
+    x = synth.sky(1, E, N)[0]
+    y1 = orc.linpatch_convolve(x, dom_o, k1, n, m)
+    y2 = orc.linpatch_convolve(x, dom_o, k2, n, m)
+    assert rel(y1, y2) > 1e-3
+    for _ in range(2):
+        assert rel(jb.linpatch_convolve(x, dom, k1, n, m).cpu().numpy(), y1) < TOL
+        assert rel(jb.linpatch_convolve(x, dom, k2, n, m).cpu().numpy(), y2) < TOL
+    kd = dev(torch, k1)
+    assert rel(jb.linpatch_convolve(dev(torch, x), dom, kd, n, m).cpu().numpy(), y1) < TOL
+    kd.copy_(dev(torch, k2))          # same tensor object, new content
+    assert rel(jb.linpatch_convolve(dev(torch, x), dom, kd, n, m).cpu().numpy(), y2) < TOL
+    plan = jb.ResponsePlan(dev(torch, k1[None]), N, n, m)
+    assert rel(plan.psf(dev(torch, x))[0].cpu().numpy(), y1) < TOL
+    plan.set_kernel(dev(torch, k2[None]))
+    assert rel(plan.psf(dev(torch, x))[0].cpu().numpy(), y2) < TOL
+    # padded length: a new PSF that no longer fits the plan's transform length is refused, not approximated
+    N2, n2, m2 = 240, 4, 10       # P = 140 -> L = 160 with a compact PSF
+    kc = synth.psf_cropped(1, n2, 1, N2 // n2, half_support=m2)
+    p2 = jb.ResponsePlan(dev(torch, kc), N2, n2, m2, cropped=True)
+    assert p2.info["L"] == 160 and p2.info["alias_fold"] == 0
+    with pytest.raises(jb.JubikError, match="create a new plan"):
+        p2.set_kernel(dev(torch, synth.psf_cropped(1, n2, 1, N2 // n2, half_support=None, sig=(4.0, 20.0))))
+    plan.close()
+    p2.close()
+
+
+def test_exact_benchmark_config_c2_two_samples_oracle_parity(torch_cuda):
+    """The configuration bench.py --workload C2 times (1024^2, 8x8 patches, margin 64, E=3, TWO samples -- the n <= 8 form
+    of the c2r kernels) against the ORACLE: energy, gradient, psf and response_T (this exact config had
+    only self-consistency checks)."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    case = (1024, 8, 64, 1, 3, 2, False, False)
+    N, n, m, T, E, S, full, eff = case
+    dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
+    plan = jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
+                           pixel_area=synth.PIXEL_AREA, data=dev(torch, d), max_samples=S, cropped=True)
+    assert plan.info["L"] == 384 and plan.info["fast_path"] == 1
+    xd = dev(torch, x)
+    e, gr = plan.energy_and_grad(xd)
+    eo, go = zip(*[orc.energy_and_grad(R, d, x[s]) for s in range(S)])
+    assert np.abs((e.cpu().numpy() - np.array(eo)) / np.array(eo)).max() < TOL
+    assert rel(gr.cpu().numpy(), np.stack(go)) < TOL
+    assert rel(plan.psf(xd).cpu().numpy(), np.stack([R.psf(x[s]) for s in range(S)])) < TOL
+    g = synth.direction((S, T, E, N, N))
+    assert rel(plan.response_T(dev(torch, g)).cpu().numpy(), np.stack([R.dense_T(g[s]) for s in range(S)])) < TOL
+    plan.close()
+
+
+def test_c5_plane_and_c4_energy_gradient_oracle_parity(torch_cuda):
+    """One (module, bin) plane of the C5 share (2048^2, 10x10 patches, margin 128: P = 664 -> L = 672, the WIDE c2r form)
+    and C4 (4096^2, 16x16, P = 640): fused energy + gradient against the oracle at full image size."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    for case, L in (((2048, 10, 128, 1, 1, 1, False, True), 672), ((4096, 16, 64, 1, 1, 1, False, False), 640)):
+        N, n, m, T, E, S, full, eff = case
+        dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
+        plan = jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
+                               eff_area=None if ea is None else dev(torch, ea), pixel_area=synth.PIXEL_AREA,
+                               data=dev(torch, d), max_samples=S, cropped=True)
+        assert plan.info["L"] == L and plan.info["fast_path"] == 1
+        e, gr = plan.energy_and_grad(dev(torch, x))
+        eo, go = orc.energy_and_grad(R, d, x[0])
+        assert abs(float(e[0]) - eo) / abs(eo) < TOL
+        assert rel(gr[0].cpu().numpy(), go) < TOL
+        plan.close()
+        del kern, expo, x, R, d
+
+
+def test_full_size_c3_with_full_support_psf_alias_fold(torch_cuda):
+    """BASELINE configs[2] geometry (1024^2, 10x10 patches, margin 64: P = 332 = 4*83 is not a smooth length) with a PSF
+    that fills the whole 2dx crop (half-support 102 > 64): the reference's period-332 wrap-around is reproduced by the
+    alias fold on L = 448.  Two modules, one bin (the oracle's cost is per plane)."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    N, n, m, T, E, S = 1024, 10, 64, 2, 1, 1
+    dx = N // n
+    kern = synth.psf_cropped(T, n, E, dx, half_support=None, sig=(4.0, 25.0))
+    expo = synth.exposure(T, E, N)
+    ea = synth.eff_area(T, E)
+    x = synth.sky(S, E, N)
+    R = orc.Response(orc.Domain((E, N, N), synth.DIST), kern, n, m, expo, 500.0, synth.PIXEL_AREA, eff_area=ea, cropped=True)
+    d = synth.counts_from(R.dense(synth.sky(1, E, N, seed=5)[0]))
+    plan = jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0, eff_area=dev(torch, ea),
+                           pixel_area=synth.PIXEL_AREA, data=dev(torch, d), max_samples=S, cropped=True)
+    assert plan.info["P"] == 332 and plan.info["alias_fold"] == 1 and plan.info["L"] == 448
+    xd = dev(torch, x)
+    assert rel(plan.psf(xd)[0].cpu().numpy(), R.psf(x[0])) < TOL
+    e, gr = plan.energy_and_grad(xd)
+    eo, go = orc.energy_and_grad(R, d, x[0])
+    assert abs(float(e[0]) - eo) / abs(eo) < TOL and rel(gr[0].cpu().numpy(), go) < TOL
+    # the padded transform WITHOUT the fold is what the reference does not compute: it must differ visibly
+    compact = synth.psf_cropped(T, n, E, dx, half_support=m, sig=(4.0, 25.0))
+    Rc = orc.Response(orc.Domain((E, N, N), synth.DIST), compact, n, m, expo, 500.0, synth.PIXEL_AREA, eff_area=ea, cropped=True)
+    assert rel(Rc.psf(x[0]), R.psf(x[0])) > 1e-3
+    plan.close()
+
+
+def test_edge_cases_of_survey_appendix_a(torch_cuda):
+    """A5: an all-zero kernel makes the reference divide by zero (NaN output); the CUDA path mirrors that (NaN, no crash).
+    A12: lambda <= 0 on an unmasked pixel gives a NaN / inf energy in the reference (log of a non-positive number);
+    mirrored: a non-positive sky yields a non-finite energy instead of a silently wrong number."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    N, n, m = 256, 4, 16
+    kern = synth.psf_full(1, n, 1, N)
+    kern[0, 5] = 0.0                                     # one patch with an all-zero PSF
+    y = jb.ResponsePlan(dev(torch, kern), N, n, m).psf(dev(torch, synth.sky(1, 1, N)[0]))
+    assert bool(torch.isnan(y).any())
+    yo = orc.linpatch_convolve(synth.sky(1, 1, N)[0], orc.Domain((1, N, N), synth.DIST), kern[0], n, m)
+    assert np.array_equal(np.isnan(yo), np.isnan(y[0].cpu().numpy()))
+    case = (256, 4, 16, 1, 1, 1, True, False)
+    dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
+    plan = jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
+                           pixel_area=synth.PIXEL_AREA, data=dev(torch, d))
+    e = plan.energy(dev(torch, -x))
+    assert not bool(torch.isfinite(e).all())
 
 
 def test_standalone_slice_patches_and_convolve_match_reference_golden(torch_cuda, golden_dir, capsys):
@@ -408,8 +569,13 @@ def test_error_behaviour_matches_reference(torch_cuda):
     with pytest.raises(jb.JubikError):  # negative cut, response.py:37-39
         jb.ResponsePlan(k[None], 32, 4, 4, exposure=torch.ones((1, 1, 32, 32), dtype=torch.float64, device="cuda"),
                         exposure_cut=-1.0)
-    with pytest.raises(jb.JubikError):  # non-smooth P with a PSF wider than the margin
-        jb.ResponsePlan(torch.ones((1, 16, 1, 64, 64), dtype=torch.float64, device="cuda"), 64, 4, 5)
+    # non-smooth P (42) with a PSF wider than the margin: served by the alias fold since r2 (was JUBIK_ERR_UNSUPPORTED)
+    p = jb.ResponsePlan(torch.ones((1, 16, 1, 64, 64), dtype=torch.float64, device="cuda"), 64, 4, 5)
+    assert p.info["alias_fold"] == 1
+    with pytest.raises(jb.JubikError, match="fft_length"):   # a forced length that is too short for the fold
+        jb.ResponsePlan(torch.ones((1, 16, 1, 64, 64), dtype=torch.float64, device="cuda"), 64, 4, 5, fft_length=96 // 2 + 0)
+    with pytest.raises(ValueError):     # an input on the wrong device / a CPU tensor never reaches the C ABI
+        p.psf(torch.zeros((1, 64, 64), dtype=torch.float64))
 
 
 def test_sharded_entry_point_with_one_rank_nccl_communicator(torch_cuda):
@@ -422,7 +588,7 @@ def test_sharded_entry_point_with_one_rank_nccl_communicator(torch_cuda):
     dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
     plan = jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
                            eff_area=dev(torch, ea), pixel_area=synth.PIXEL_AREA, data=dev(torch, d), max_samples=S,
-                           cropped=cropped)
+                           cropped=cropped, sharded=True)
     comm = jb.Communicator(jb.Communicator.unique_id(), 0, 1)
     assert comm.size == 1 and comm.rank == 0
     xd = dev(torch, x)
@@ -457,7 +623,7 @@ def _nccl_worker(rank, world, port, q):
         return jb.ResponsePlan(torch.as_tensor(kern[tsel]).cuda(), N, n, m, exposure=torch.as_tensor(expo[tsel]).cuda(),
                                exposure_cut=500.0, eff_area=torch.as_tensor(ea[tsel]).cuda(),
                                pixel_area=synth.PIXEL_AREA, data=torch.as_tensor(d[tsel]).cuda(), max_samples=smax,
-                               cropped=cropped)
+                               cropped=cropped, sharded=True)
     comm = jb.Communicator.from_torch_distributed()
     sl = S // world
     lh = NcclShardedLikelihood(mk(list(range(T)), sl), "samples", comm=comm)

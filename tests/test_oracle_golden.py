@@ -29,6 +29,35 @@ def test_linpatch_matches_reference_source(golden_dir, name):
     assert rel(orc.linpatch_convolve(z["x"], dom, cut, n, m, cropped=True), z["y"]) < 1e-13
 
 
+WIDE = ["lp_N256_n4_m16_wide", "lp_N512_n4_m32_wide", "lp_N512_n8_m32_wide"]
+FOLD = ["lp_N62_n4_m9_fold", "lp_N100_n5_m7_fold"]
+
+
+@pytest.mark.parametrize("name", WIDE)
+def test_linpatch_production_geometries_match_reference_source(golden_dir, name):
+    """C1 and the reference's two shipped demo geometries (512^2, 4x4 / 8x8, margfrac 0.062) with PSFs whose tails
+    wrap around the period: forward output of the reference's own convolve.py; kernels regenerated from the seed."""
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    N, n, m = int(z["N"]), int(z["n"]), int(z["m"])
+    kern = synth.psf_full(1, n, 1, N, seed=1, sig=tuple(z["sig"]))[0]
+    x = synth.sky(1, 1, N, seed=0)[0]
+    dom = orc.Domain((1, N, N), tuple(z["distances"]))
+    assert rel(orc.linpatch_convolve(x, dom, kern, n, m), z["y"]) < 1e-13
+    cut = orc.crop_kernel(kern, dom.shape, n)
+    assert rel(orc.linpatch_convolve(x, dom, cut, n, m, cropped=True), z["y"]) < 1e-13
+
+
+@pytest.mark.parametrize("name", FOLD)
+def test_linpatch_wide_psf_on_non_smooth_period_matches_reference_source(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    x, n, m = z["x"], int(z["n"]), int(z["m"])
+    E, N = x.shape[0], x.shape[-1]
+    kern = synth.psf_full(1, n, E, N, seed=1, sig=tuple(z["sig"]))[0]
+    dom = orc.Domain(tuple(x.shape), tuple(z["distances"]))
+    assert rel(orc.linpatch_convolve(x, dom, kern, n, m), z["y"]) < 1e-13
+    assert rel(orc.linpatch_convolve_T(z["g"], dom, kern, n, m), z["yT"]) < 1e-13
+
+
 def test_slice_patches_matches_reference_source(golden_dir):
     z = np.load(os.path.join(golden_dir, "slice_patches.npz"))
     sp = orc.slice_patches(z["a"], (36, 36), 16, 2)

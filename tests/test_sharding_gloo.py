@@ -43,8 +43,11 @@ def _worker(rank, world, port, q):
     mine = owned(T, rank, world)
     lm = ModuleShardedLikelihood(OraclePlan(mine), T)
     e_m, g_m = lm.energy_and_grad(x)
+    # fewer samples than ranks: the rank that owns nothing must still enter both collectives
+    l1 = SampleShardedLikelihood(OraclePlan(list(range(T))), 1)
+    e_1, g_1 = l1.energy_and_grad(l1.local(x[:1]))
     if rank == 0:
-        q.put((e_s.numpy(), g_s.numpy(), e_m.numpy(), g_m.numpy()))
+        q.put((e_s.numpy(), g_s.numpy(), e_m.numpy(), g_m.numpy(), e_1.numpy(), g_1.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -59,7 +62,7 @@ def test_sample_and_module_sharding_world2():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    e_s, g_s, e_m, g_m = q.get(timeout=240)
+    e_s, g_s, e_m, g_m, e_1, g_1 = q.get(timeout=240)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -67,6 +70,7 @@ def test_sample_and_module_sharding_world2():
     e, g = ref.energy_and_grad(torch.as_tensor(synth.sky(S, E, N)))
     assert np.allclose(e_s, e.numpy(), rtol=1e-13) and np.allclose(g_s, g.numpy().sum(0), rtol=1e-12, atol=1e-12)
     assert np.allclose(e_m, e.numpy(), rtol=1e-13) and np.allclose(g_m, g.numpy(), rtol=1e-12, atol=1e-12)
+    assert np.allclose(e_1, e.numpy()[:1], rtol=1e-13) and np.allclose(g_1, g.numpy()[0], rtol=1e-12, atol=1e-12)
 
 
 def test_partition_helpers():
