@@ -1,26 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- fused forward + VJP of response + Poisson log-likelihood, fp64, in sky-pixels/s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C1|C3s|C3|C4|C5g]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C5|C1|C2|C3|C4]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU)
 
-Workload at N=1: BASELINE.json configs[1] ("C2", Chandra-like): 1024x1024 sky, 3 energy bins, 8x8
-spatially-variant PSF patches, margin 64, exposure + readout mask + Poisson likelihood, S=1, T=1.
-One step = one evaluation of (energy[s], d energy[s] / d sky[s]) for the S samples of the rank; sky-pixels =
-S*T*E*N^2.
-Every rank (also at N=1) evaluates `--samples-per-gpu` posterior samples of that workload per step (default 2, the
-per-GPU share of BASELINE.json configs[4]: 16 geoVI samples over 8 GPUs) -- weak scaling, sample sharding;
-one step is ONE C-ABI call (jubik_poisson_energy_and_grad_sharded): the seven kernels, the fold of the rank's samples
-into a flat buffer [sample-summed gradient | per-sample energies of all ranks] and a SINGLE ncclAllReduce of that buffer,
-issued by the library on its own NCCL communicator, all on one stream inside the timed region.
+Default workload: BASELINE.json configs[4] ("C5", the configuration the metric "... at 1/2/4/8 B200" is quoted on, and
+the largest one): 16 posterior samples x 7 telescope modules x 3 energy bins at 2048x2048, 10x10 PSF patches, margin 128.
+The job is FIXED (strong scaling): N ranks evaluate 16/N samples each, in chunks of two (the plan's workspace holds two
+samples; one GPU loops over 8 chunks).  One step = ONE C-ABI call per rank (jubik_poisson_energy_and_grad_sharded): the
+kernels of every chunk, the fold of the rank's samples into a flat buffer [sample-summed gradient | energies of all
+samples] and the NCCL all-reduce of that buffer (issued by the library, one energy bin at a time so that it overlaps
+the next bin's kernels).  sky-pixels per step = samples * T * E * N^2.  --workload selects the other
+BASELINE configurations (C1..C4, their own sample counts).
 
 `value`  : device-resident throughput (inputs already in HBM), CUDA events, max over ranks.
-`e2e`    : the same metric through ResponsePlan.energy_and_grad_host (C ABI jubik_poisson_energy_and_grad_host)
-           with pinned HOST buffers: H2D of x and D2H of energy+gradient inside the timed region.
-`roofline`: dominant kernel (column pass k_cols, forward direction) -- algorithmic bytes / live CUDA-event
-           duration against MEASURED_PEAKS.json hbm_gbs; whole-path HBM and FP64 fractions alongside.
-`cpu_baseline`: the NumPy/scipy oracle (the reference's op sequence; jax is not installable here) timed on
-           this box's host cores on a bounded sample.  --impl reference prints that arm alone.
+`e2e`    : the same operation through jubik_poisson_energy_and_grad_sharded_host with pinned HOST buffers: H2D of every
+           sample and D2H of [gradient | energies] inside the timed region.
+`roofline`: SURVEY 8(d) whole-path fraction against the binding roof (FP64 pipe, measured DFMA peak) with the HBM
+           fraction beside it; `dominant_kernel` = the forward column pass against its compulsory bytes (the resident
+           PSF spectra it must read); per-kernel durations measured live with CUDA events.
+`parity` : N = 1: one (module, bin) plane of the workload against the CPU oracle; N > 1: rank 0 re-evaluates all samples
+           alone and compares with the all-reduced result.
+`cpu_baseline`: the NumPy/scipy oracle (the reference's op sequence; jax is not installable here) timed on this box's
+           host cores on one (module, bin) plane of the workload (N = 1 only).  --impl reference prints that arm alone.
 """
 import argparse
 import json
@@ -33,39 +35,38 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core
+if "--impl" in sys.argv and "reference" in sys.argv:
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 import numpy as np  # noqa: E402
 
 METRIC = "fwd+VJP response+loglik sky-pixels/s (fp64)"
 UNIT = "sky-pixels/s"
 
 WORKLOADS = {
-    # name: (N, n, m, T, E, description)
-    "C1": (256, 4, 16, 1, 1, "C1: 256x256 sky, 4x4 PSF patches, margin 16, 1 energy bin"),
-    "C2": (1024, 8, 64, 1, 3, "C2 Chandra-like: 1024x1024 sky, 3 energy bins, 8x8 PSF patches, margin 64, "
-                              "exposure + mask + Poisson fwd+VJP"),
-    "C3s": (1020, 10, 64, 2, 3, "C3-like slice: 1020x1020 sky, 2 modules x 3 bins, 10x10 PSF patches, margin 64"),
-    # the other single-GPU configurations of BASELINE.json (parity-test cases; benched on request for DESIGN.md section 4)
-    "C3": (1024, 10, 64, 7, 3, "C3 eROSITA-like: 7 telescope modules x 3 energy bins, 1024x1024 sky, 10x10 PSF patches, "
-                               "margin 64 (P=332 -> L=336), per-module exposure/readout masks"),
-    "C5g": (2048, 10, 128, 7, 3, "C5 geoVI batch, one GPU's share (2 of 16 samples with --samples-per-gpu 2): 7 telescope modules "
-                                 "x 3 energy bins at 2048x2048, 10x10 PSF patches, margin 128 (P=664 -> L=672)"),
-    "C4": (4096, 16, 64, 1, 1, "C4 JWST-like: 4096x4096 sky, 16x16 PSF patches with 128-px kernels (margin 64, P=640), "
-                               "single filter"),
+    # name: (N, n, m, T, E, samples of the job, samples per chunk, description)
+    "C1": (256, 4, 16, 1, 1, 1, 1, "C1: 256x256 sky, 4x4 PSF patches, margin 16, 1 energy bin"),
+    "C2": (1024, 8, 64, 1, 3, 2, 2, "C2 Chandra-like: 1024x1024 sky, 3 energy bins, 8x8 PSF patches, margin 64, "
+                                    "exposure + mask + Poisson fwd+VJP, 2 samples"),
+    "C3": (1024, 10, 64, 7, 3, 1, 1, "C3 eROSITA-like: 7 telescope modules x 3 energy bins, 1024x1024 sky, 10x10 PSF "
+                                     "patches, margin 64 (P=332 -> L=336), per-module exposure/readout masks"),
+    "C4": (4096, 16, 64, 1, 1, 1, 1, "C4 JWST-like: 4096x4096 sky, 16x16 PSF patches with 128-px kernels (margin 64, "
+                                     "P=640), single filter"),
+    "C5": (2048, 10, 128, 7, 3, 16, 2, "C5 geoVI batch: 16 posterior samples x 7 telescope modules x 3 energy bins at "
+                                       "2048x2048, 10x10 PSF patches, margin 128 (P=664 -> L=672), sample-sharded"),
 }
 
 
-def make_inputs(wl, S, seed_shift=0):
-    from tests import synth
-    N, n, m, T, E, _ = WORKLOADS[wl]
-    dx = N // n
-    kern = synth.psf_cropped(T, n, E, dx, half_support=m)
-    expo = synth.exposure(T, E, N)
-    x = synth.sky(S, E, N, seed=0 + seed_shift)
-    return kern, expo, x
+def config_of(wl):
+    """The workload keys both arms print (identical dicts: the driver's same_config check)."""
+    N, n, m, T, E, S, chunk, desc = WORKLOADS[wl]
+    return {"workload": desc, "name": wl, "N": N, "n_patches": n, "margin": m, "T": T, "E": E, "samples": S}
 
 
 def alg_bytes_flops(N, n, m, T, E, S):
-    """compulsory HBM bytes and textbook FFT flops of one fused fwd+VJP evaluation."""
+    """compulsory HBM bytes and textbook FFT flops of one fused fwd+VJP evaluation of S samples."""
     dx = N // n
     P = 2 * dx + 2 * m
     khat = n * n * P * (P // 2 + 1) * 16
@@ -75,46 +76,56 @@ def alg_bytes_flops(N, n, m, T, E, S):
 
 
 # ----------------------------------------------------------------------------------- CPU arm
-def cpu_arm(wl, steps, warmup, bounded_bins=1):
-    """Oracle (reference op sequence: c2c fftn x2 + ifftn, kernel prep every call, gather/scatter) on the host
-    cores.  One step = fwd+VJP on `bounded_bins` energy bin(s) of the workload, T=1, S=1."""
-    from oracle import jubik_oracle as orc
-    from tests import synth
-    N, n, m, T, E, desc = WORKLOADS[wl]
-    Eb = min(bounded_bins, E)
-    cores = os.cpu_count() or 1
-    orc.set_workers(cores)
-    dx = N // n
-    kern = synth.psf_cropped(1, n, Eb, dx, half_support=m)
-    expo = synth.exposure(1, Eb, N)
-    x = synth.sky(1, Eb, N)[0]
-    dom = orc.Domain((Eb, N, N), synth.DIST)
-    R = orc.Response(dom, kern, n, m, expo, 500.0, synth.PIXEL_AREA, cropped=True)
-    d = synth.counts_from(R.dense(synth.sky(1, Eb, N, seed=5)[0]))
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        orc.energy_and_grad(R, d, x)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    px = Eb * N * N
-    tot = sum(times)
-    return {"value": px * len(times) / tot, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d of %d energy bin(s) of %s, T=1, S=1 per step; NumPy/scipy.fft oracle with workers=%d; "
-                      "%d steps, %.2f s/step" % (Eb, E, wl, cores, len(times), tot / len(times))}, tot / len(times)
+class CpuPlane:
+    """One (module 0, bin 0) plane of the workload at full image size on the oracle (reference op sequence: c2c fftn
+    x2 + ifftn, kernel prep every call, gather/scatter) -- the bounded sample of the CPU arm, and the parity probe."""
+
+    def __init__(self, wl):
+        from oracle import jubik_oracle as orc
+        from tests import synth
+        self.orc = orc
+        N, n, m, T, E, S, chunk, desc = WORKLOADS[wl]
+        self.wl, self.N, self.n, self.m = wl, N, n, m
+        self.cores = os.cpu_count() or 1
+        orc.set_workers(self.cores)
+        dx = N // n
+        self.kern = synth.psf_cropped(1, n, 1, dx, half_support=m)
+        self.expo = synth.exposure(1, 1, N)
+        self.x = synth.sky(1, 1, N)[0]
+        dom = orc.Domain((1, N, N), synth.DIST)
+        self.R = orc.Response(dom, self.kern, n, m, self.expo, 500.0, synth.PIXEL_AREA, cropped=True)
+        self.d = synth.counts_from(self.R.dense(synth.sky(1, 1, N, seed=5)[0]))
+        self.sample = "one (module, energy bin) plane of %s at %dx%d (of T=%d x E=%d x %d samples) per step" % (
+            wl, N, N, T, E, S)
+
+    def step(self):
+        return self.orc.energy_and_grad(self.R, self.d, self.x)
+
+    def time(self, steps, warmup):
+        times = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            self.step()
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+        tot = sum(times)
+        px = self.N * self.N
+        cb = {"value": px * len(times) / tot, "unit": UNIT, "cores": self.cores, "kind": "port",
+              "sample": self.sample + "; NumPy/scipy.fft oracle with workers=%d; %d steps, %.2f s/step"
+                        % (self.cores, len(times), tot / len(times))}
+        return cb, tot / len(times)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    N, n, m, T, E, desc = WORKLOADS[args.workload]
-    cb, s_per_step = cpu_arm(args.workload, args.steps, args.warmup)
+    cb, s_per_step = CpuPlane(args.workload).time(args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "N": N, "n_patches": n, "margin": m, "T": T, "E": E, "S": 1},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_of(args.workload),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -169,6 +180,19 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------- GPU arm
+def make_inputs(wl):
+    from tests import synth
+    N, n, m, T, E, S, chunk, _ = WORKLOADS[wl]
+    return synth.psf_cropped(T, n, E, N // n, half_support=m), synth.exposure(T, E, N)
+
+
+def sample_skies(wl, first, count):
+    """Skies of the job's samples [first, first+count): one seed per global sample index."""
+    from tests import synth
+    N, n, m, T, E, S, chunk, _ = WORKLOADS[wl]
+    return np.concatenate([synth.sky(1, E, N, seed=1000 + s) for s in range(first, first + count)], axis=0)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -187,54 +211,40 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
-        # the one collective is a ~25 MB fp64 all-reduce: on this NVSwitch box NCCL's ring beats its default (NVLS)
-        # choice at that size (106 vs 124 us measured at 8 ranks, tools/ar_bench.py)
-        os.environ.setdefault("NCCL_ALGO", "Ring")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    N, n, m, T, E, desc = WORKLOADS[args.workload]
-    S = args.samples_per_gpu
-    kern, expo, x_np = make_inputs(args.workload, S, seed_shift=100 * rank)
+    N, n, m, T, E, S_job, chunk, desc = WORKLOADS[args.workload]
+    if args.samples:
+        S_job = args.samples
+    if S_job % world:
+        raise SystemExit("the job's %d samples do not divide over %d ranks" % (S_job, world))
+    S = S_job // world                   # this rank's samples
+    chunk = min(chunk, S)
     dev = torch.device("cuda", local)
+    kern, expo = make_inputs(args.workload)
     kern_d = torch.as_tensor(kern).to(dev)
     expo_d = torch.as_tensor(expo).to(dev)
+    del kern, expo
     plan = jb.ResponsePlan(kern_d, N, n, m, exposure=expo_d, exposure_cut=500.0, pixel_area=16.0,
-                           max_samples=S, cropped=True)
+                           max_samples=chunk, cropped=True, host_call=True, sharded=True, metric=False)
     del kern_d
-    x = torch.as_tensor(x_np).to(dev)
-    truth = torch.as_tensor(make_inputs(args.workload, 1, seed_shift=5)[2]).to(dev)
+    from tests import synth
+    truth = torch.as_tensor(synth.sky(1, E, N, seed=5)).to(dev)
     lam = plan.response(truth)[0]
     torch.manual_seed(3)
     plan.set_data(torch.poisson(lam.clamp(min=0.0)))
     del lam, truth
+    x_np = sample_skies(args.workload, rank * S, S)
+    x = torch.as_tensor(x_np).to(dev)
     flush = torch.empty(192 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 192 MiB > 126 MB L2
 
     # one flat buffer = [sample-summed sky gradient (E,N,N) | energies of all world*S samples]: the partial
-    # log-likelihoods and the gradient are combined with a SINGLE NCCL all-reduce (north_star)
+    # log-likelihoods and the gradient are combined by the library's NCCL all-reduce (north_star)
     npx = E * N * N
     flat = torch.zeros(npx + world * S, dtype=torch.float64, device=dev)
-    gbuf = flat[:npx].view(1, E, N, N) if S == 1 else torch.empty((S, E, N, N), dtype=torch.float64, device=dev)
-    ebuf = flat[npx + rank * S: npx + (rank + 1) * S]
-
-    # default: the whole step -- kernels, the fold of the rank's samples into `flat` and the ONE ncclAllReduce -- is a
-    # single C-ABI call (jubik_poisson_energy_and_grad_sharded) on one stream; the library owns the NCCL communicator
-    # (torch.distributed only hands the ncclUniqueId around).  JUBIK_B200_TORCH_ALLREDUCE=1 keeps the collective in torch.
-    via_torch = os.environ.get("JUBIK_B200_TORCH_ALLREDUCE") == "1"
-    comm = None
-    if world > 1 and not via_torch:
-        comm = jb.Communicator.from_torch_distributed()
-    glocal = gbuf if S > 1 else None     # per-sample gradients of this rank (S == 1: the gradient lands in flat directly)
+    comm = jb.Communicator.from_torch_distributed() if world > 1 else None
 
     def step_device():
-        if not via_torch:
-            return plan.energy_and_grad_sharded(x, comm, jb.SHARD_SAMPLES, flat=flat, grad_local=glocal)
-        if world > 1:
-            flat[npx:].zero_()
-        e, g = plan.energy_and_grad(x, out_energy=ebuf, out_grad=gbuf)
-        if S > 1:
-            torch.sum(g, 0, out=flat[:npx].view(E, N, N))
-        if world > 1:
-            dist.all_reduce(flat)
-        return e, g
+        return plan.energy_and_grad_sharded(x, comm, jb.SHARD_SAMPLES, flat=flat)
 
     def barrier():
         if world > 1:
@@ -262,25 +272,21 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev = float(tt)
-    px_step = world * S * T * E * N * N
+    px_step = S_job * T * E * N * N
     value = px_step * args.steps / t_dev
+    res_dev = flat.clone()
 
-    # ---- end to end through the host-buffer C-ABI call (pinned host memory)
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory): the same operation, same reduction
     xh = torch.as_tensor(x_np).pin_memory()
-    eh = torch.empty((S,), dtype=torch.float64).pin_memory()
-    gh = torch.empty_like(xh).pin_memory()
+    fh = torch.empty((npx + world * S,), dtype=torch.float64).pin_memory()
     for _ in range(3):
-        plan.energy_and_grad_host(xh, eh, gh)
+        plan.energy_and_grad_sharded_host(xh, comm, fh)
     barrier()
-    t0 = time.perf_counter()
     e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in e2e_ev:
         flush.zero_()
         a.record()
-        plan.energy_and_grad_host(xh, eh, gh)
-        if world > 1:
-            et = eh.to(dev, non_blocking=True)
-            dist.all_reduce(et)
+        plan.energy_and_grad_sharded_host(xh, comm, fh)
         b.record()
     barrier()
     t_e2e = sum(a.elapsed_time(b) for a, b in e2e_ev) * 1e-3
@@ -289,16 +295,47 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_e2e = float(tt)
     e2e_value = px_step * args.steps / t_e2e
-    h2d = xh.numel() * 8
-    d2h = gh.numel() * 8 + eh.numel() * 8
+    h2d = xh.numel() * 8 * world
+    d2h = fh.numel() * 8 * world
+    e2e_same = bool(torch.equal(fh, res_dev.cpu()))   # host form == device form, bit for bit
 
-    line = None
+    # ---- parity leg
+    parity = {"checked": False}
+    cpu = None
+    if world > 1:
+        # rank 0 evaluates ALL samples alone (chunked, no communicator) and compares with the all-reduced result
+        if rank == 0:
+            xa = torch.as_tensor(sample_skies(args.workload, 0, S_job)).to(dev)
+            fl1 = torch.zeros(npx + S_job, dtype=torch.float64, device=dev)
+            plan.energy_and_grad_sharded(xa, None, jb.SHARD_SAMPLES, flat=fl1)
+            g_err = float((fl1[:npx] - res_dev[:npx]).abs().max() / fl1[:npx].abs().max())
+            e_err = float(((fl1[npx:] - res_dev[npx:]) / fl1[npx:]).abs().max())
+            parity = {"checked": True, "ok": bool(g_err < 1e-11 and e_err < 1e-12 and e2e_same),
+                      "what": "all-reduced [sum-gradient | energies] of %d ranks vs one rank evaluating all %d samples; "
+                              "host-buffer form bitwise equal to the device form: %s" % (world, S_job, e2e_same),
+                      "max_rel_err_grad": g_err, "max_rel_err_energy": e_err}
+            del xa, fl1
+    elif not args.no_cpu:
+        cpu = CpuPlane(args.workload)
+        p1 = jb.ResponsePlan(torch.as_tensor(cpu.kern).to(dev), N, n, m, exposure=torch.as_tensor(cpu.expo).to(dev),
+                             exposure_cut=500.0, pixel_area=16.0, data=torch.as_tensor(cpu.d).to(dev), cropped=True,
+                             metric=False)
+        e1, g1 = p1.energy_and_grad(torch.as_tensor(cpu.x).to(dev))
+        eo, go = cpu.step()
+        g_err = float(np.abs(g1.cpu().numpy() - go).max() / np.abs(go).max())
+        e_err = abs(float(e1) - eo) / abs(eo)
+        parity = {"checked": True, "ok": bool(g_err < 1e-10 and e_err < 1e-10 and e2e_same),
+                  "what": "energy + gradient of one (module, bin) plane of the workload at full size vs the CPU oracle; "
+                          "host-buffer form bitwise equal to the device form: %s" % e2e_same,
+                  "max_rel_err_grad": g_err, "max_rel_err_energy": e_err}
+        p1.close()
+
     if rank == 0:
-        # ---- per-kernel durations, live (CUDA events between launches on the launching stream)
+        # ---- per-kernel durations of ONE chunk, live (CUDA events between launches on the launching stream)
         acc = {}
         for _ in range(max(3, min(args.steps, 10))):
             flush.zero_()
-            _, _, ms = plan.profile(x)
+            _, _, ms = plan.profile(x[:chunk])
             for k, v in ms.items():
                 acc.setdefault(k, []).append(v)
         kms = {k: statistics.mean(v) for k, v in acc.items()}
@@ -312,46 +349,69 @@ def run_ours(args):
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         fp64 = measure_fp64_tflops()
         L, P, PH, w = info["L"], info["P"], info["PH"], info["w"]
-        # column pass, forward: read w rows, read the resident spectrum (L*PH), write P rows, all complex128
-        cols_bytes = S * T * E * n * n * (w + P + L) * PH * 16
+        b_alg, f_alg = alg_bytes_flops(N, n, m, T, E, S_job)
+        t_step = t_dev / args.steps
+        ach_f = f_alg / t_step / 1e12 / world          # per GPU
+        ach_b = b_alg / t_step / 1e9 / world
+        binding = "fp64" if f_alg / (fp64 * 1e12) > b_alg / (hbm * 1e9) else "hbm"
+        # dominant kernel = forward column pass; compulsory bytes = the resident PSF spectra it has to read, once per
+        # sample (no intermediate counted), P*(P/2+1) complex per patch
+        khat_b = chunk * T * E * n * n * P * (P // 2 + 1) * 16
         cols_s = kms["cols_fwd"] * 1e-3
-        # DRAM bytes of the same kernel from the committed `ncu --set full` capture (profiles/*_traffic.json)
-        traffic = None
+        # textbook flops of that launch: forward + inverse column FFTs over PH columns + the spectrum multiply
+        cols_f = chunk * T * E * n * n * PH * (2 * 5 * P * np.log2(P) + 6 * P)
+        traffic_ncu = None
         try:
             import glob
-            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1]
+            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "r2*_traffic.json")))[-1]
             tj = json.load(open(tf))
-            if tj.get("workload") == args.workload and tj.get("samples", 1) == S:
-                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            if tj.get("workload") == args.workload:
+                traffic_ncu = dict(tj, file=os.path.relpath(tf, ROOT))
         except Exception:
             pass
-        b_alg, f_alg = alg_bytes_flops(N, n, m, T, E, S)
-        t_step = t_dev / args.steps
-        roof = {"bound": "hbm", "kernel": "k_cols (forward column pass: FFT * K^ * IFFT)",
-                "achieved": cols_bytes / cols_s / 1e9, "peak": hbm, "unit": "GB/s",
-                "frac": cols_bytes / cols_s / 1e9 / hbm, "peak_source": hbm_src, "traffic": traffic,
-                "algorithmic_bytes_per_launch": cols_bytes, "launch_ms": kms["cols_fwd"],
-                "kernel_ms": kms,
-                "path": {"B_alg_bytes": b_alg, "F_alg_flops": f_alg,
-                         "frac_hbm": b_alg / t_step / 1e9 / hbm,
-                         "fp64_peak_tflops_measured": fp64,
-                         "frac_fp64": f_alg / t_step / 1e12 / fp64 if fp64 > 0 else None,
-                         "binding": "fp64" if f_alg / (fp64 * 1e12) > b_alg / (hbm * 1e9) else "hbm"}}
-        cb, _ = cpu_arm(args.workload, 3, 1) if not args.no_cpu else ({"value": None, "unit": UNIT, "cores": 0,
-                                                                      "kind": "port", "sample": "skipped"}, 0)
+        roof = {"bound": binding, "what": "whole path, SURVEY 8(d): textbook FFT flops (compulsory bytes) of one step / "
+                                          "device time, per GPU",
+                "achieved": ach_f if binding == "fp64" else ach_b,
+                "peak": fp64 if binding == "fp64" else hbm,
+                "unit": "TFLOP/s" if binding == "fp64" else "GB/s",
+                "frac": (ach_f / fp64) if binding == "fp64" else (ach_b / hbm),
+                "peak_source": "DFMA micro-benchmark run inside this process (jubik_measure_fp64_tflops)"
+                               if binding == "fp64" else hbm_src,
+                "frac_hbm": ach_b / hbm, "achieved_hbm_gbs": ach_b, "peak_hbm_gbs": hbm, "peak_hbm_source": hbm_src,
+                "frac_fp64": ach_f / fp64 if fp64 > 0 else None, "achieved_fp64_tflops": ach_f, "peak_fp64_tflops": fp64,
+                "B_alg_bytes": b_alg, "F_alg_flops": f_alg,
+                "traffic": None, "traffic_ncu_profile": traffic_ncu,
+                "dominant_kernel": {"name": "k_cols3_pipe (forward column pass: FFT * K^ * IFFT), one chunk of %d samples" % chunk,
+                                    "launch_ms": kms["cols_fwd"],
+                                    "compulsory_bytes_per_launch": khat_b,
+                                    "achieved_gbs": khat_b / cols_s / 1e9, "frac_hbm": khat_b / cols_s / 1e9 / hbm,
+                                    "textbook_flops_per_launch": cols_f,
+                                    "achieved_tflops": cols_f / cols_s / 1e12,
+                                    "frac_fp64": cols_f / cols_s / 1e12 / fp64 if fp64 > 0 else None},
+                "kernel_ms_one_chunk": kms}
+        if cpu is not None:
+            cb, _ = cpu.time(3, 1)
+        else:
+            cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                  "sample": "not run (N > 1 or --no-cpu): the CPU arm is timed at N = 1 only"}
+        cfg = config_of(args.workload)
+        cfg["samples"] = S_job
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": desc, "N": N, "n_patches": n, "margin": m, "T": T, "E": E,
-                           "samples_per_gpu": S, "fft_length": L, "parallelism": "sample-sharded x%d" % world,
-                           "collective": ("torch.distributed all_reduce" if via_torch else
-                                          "one ncclAllReduce of [sum-grad | energies] issued inside the C-ABI call")
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": cfg,
+                "detail": {"samples_per_gpu": S, "samples_per_chunk": chunk, "fft_length": L,
+                           "parallelism": "sample-sharded x%d" % world,
+                           "collective": "ncclAllReduce of [sum-grad | energies] issued inside the C-ABI call, one energy "
+                                         "bin at a time on a second stream (overlaps the next bin's kernels)"
                            if world > 1 else "none",
                            "l2": "flushed (192 MiB write) between timed iterations; working set %.0f MB > L2"
                                  % (info["bytes_total"] / 1e6)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": t_e2e / args.steps * 1e3},
-                "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cb}
+                        "ms_per_step": t_e2e / args.steps * 1e3,
+                        "call": "jubik_poisson_energy_and_grad_sharded_host (pinned host x -> host [sum-grad | energies])"},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cb, "parity": parity,
+                "parity_ok": parity.get("ok")}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
@@ -364,12 +424,12 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--samples-per-gpu", type=int, default=2)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="C5", choices=sorted(WORKLOADS))
+    ap.add_argument("--samples", type=int, default=0, help="override the job's sample count")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / oracle parity leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -163,6 +163,14 @@ int jubik_poisson_energy_and_grad_host(jubik_plan* plan, const double* x_host, i
  *   JUBIK_SHARD_MODULES  every rank holds a plan of its own modules (T_local) and evaluates the same S samples.
  *       flat = [ d energy / d sky (S,E,N,N) | energies (S) ], both summed over ranks; grad_local must be NULL.
  * jubik_sharded_flat_size gives the element count of `flat`.  comm == NULL runs the single-rank path (no collective).
+ * n_samples may EXCEED the plan's max_samples: the samples are then evaluated in chunks of max_samples (the workspace
+ * holds one chunk) and folded into `flat` chunk after chunk in a fixed order -- BASELINE configs[4] on fewer than 8 GPUs
+ * (16 samples: 8 chunks of 2 on one GPU).  With more than one rank and more than one energy bin the all-reduce of bin e
+ * overlaps the kernels of bin e+1 on a second stream (needs JUBIK_PLAN_SHARDED).
+ * jubik_poisson_energy_and_grad_sharded_host is the same call (sample sharding) on HOST buffers -- the end-to-end form:
+ * x_host (n_samples,E,N,N) is copied chunk by chunk, one energy bin at a time, through a two-slot device ring while the
+ * previous chunk computes; flat_host receives [sum-gradient | energies], each bin as soon as it is reduced; then a
+ * stream synchronise.  Needs JUBIK_PLAN_HOST_CALL | JUBIK_PLAN_SHARDED and n_ranks * n_samples <= 4096.
  * NCCL is bound with dlopen("libnccl.so.2") at the first jubik_comm_* call; jubik_comm_create wraps ncclCommInitRank on
  * the current device with a 128-byte ncclUniqueId from jubik_comm_unique_id (rank 0) that the caller distributes;
  * jubik_comm_adopt wraps an ncclComm_t the caller already owns (it is not destroyed by jubik_comm_destroy). */
@@ -177,6 +185,8 @@ int jubik_comm_size(const jubik_comm* comm);
 long long jubik_sharded_flat_size(const jubik_plan* plan, const jubik_comm* comm, int shard_mode, int n_samples);
 int jubik_poisson_energy_and_grad_sharded(jubik_plan* plan, jubik_comm* comm, int shard_mode, const double* x,
                                           int n_samples, double* grad_local, double* flat, void* stream);
+int jubik_poisson_energy_and_grad_sharded_host(jubik_plan* plan, jubik_comm* comm, const double* x_host, int n_samples,
+                                               double* flat_host, void* stream);
 
 /* Measurement helpers (bench.py): the energy+grad sequence with a CUDA event after every kernel,
  * ms_out[0..*n_out) (room for 48) in launch order = rows_fwd, cols_fwd, rows_out, [poisson_epi,] reduce,

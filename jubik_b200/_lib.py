@@ -28,6 +28,7 @@ EXPORTS = [
     "jubik_slice_patches", "jubik_slice_patches_T", "jubik_convolve",
     "jubik_comm_unique_id", "jubik_comm_create", "jubik_comm_adopt", "jubik_comm_destroy", "jubik_comm_rank",
     "jubik_comm_size", "jubik_sharded_flat_size", "jubik_poisson_energy_and_grad_sharded",
+    "jubik_poisson_energy_and_grad_sharded_host",
 ]
 SHARD_SAMPLES, SHARD_MODULES = 0, 1
 
@@ -92,6 +93,7 @@ def bind(lib):
     lib.jubik_sharded_flat_size.argtypes = [vp, vp, i, i]
     lib.jubik_sharded_flat_size.restype = C.c_longlong
     lib.jubik_poisson_energy_and_grad_sharded.argtypes = [vp, vp, i, vp, i, vp, vp, vp]
+    lib.jubik_poisson_energy_and_grad_sharded_host.argtypes = [vp, vp, vp, i, vp, vp]
     for name in EXPORTS:
         if name not in ("jubik_last_error", "jubik_plan_launch_count", "jubik_sharded_flat_size"):
             getattr(lib, name).restype = i

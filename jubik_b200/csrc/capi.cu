@@ -80,6 +80,8 @@ const int k_lengths[] = {
 };
 }  // namespace
 
+#define JB_MAX_SLOTS 4096   // energies (n_ranks x samples) behind the gradient in the host-call flat buffer
+
 struct jubik_plan {
     JbGeom g;
     const JbFftOps* ops = nullptr;
@@ -112,6 +114,7 @@ struct jubik_plan {
     double* gdev = nullptr;
     double* edev = nullptr;
     double* gstage = nullptr;  // per-sample gradients of the sharded call without grad_local (JUBIK_PLAN_SHARDED)
+    double* flatdev = nullptr; // device image of `flat` for the host-buffer sharded call (HOST_CALL | SHARDED)
     size_t bytes_khat = 0, bytes_ws = 0, bytes_total = 0;
     int nblk_out = 0;
     int use_pipe = 0, n_sm = 1;
@@ -135,6 +138,7 @@ struct jubik_plan {
     // host-buffer entry point: copy streams and per-plane events; sharded call: the collective's stream
     cudaStream_t st_in = nullptr, st_out = nullptr, st_c2 = nullptr, st_comm = nullptr;
     cudaEvent_t *ev_in = nullptr, *ev_c = nullptr, ev_start = nullptr, *ev_bin = nullptr, ev_comm = nullptr;
+    cudaEvent_t *ev_ring = nullptr, ev_free[2] = {nullptr, nullptr};   // host-buffer sharded call: x ring (2 slots x E bins)
     int n_ev = 0;
 #endif
 };
@@ -165,7 +169,7 @@ int jubik_plan_destroy(jubik_plan* p) {
     if (!p) return JUBIK_OK;
     void* bufs[] = {p->khat, p->tw_nk, p->tw_kn, p->tw1, p->tw2, p->wgt, p->expo, p->data, p->psums, p->psupp, p->bufA, p->bufB,
                     p->bufA2, p->bufB2, p->gbuf2, p->gbuf, p->fac, p->partial, p->gtab_fwd, p->gtab_adj, p->xdev, p->gdev,
-                    p->edev, p->gstage};
+                    p->edev, p->gstage, p->flatdev};
     for (void* b : bufs) dev_free(b);
 #ifndef JB_EMU
     for (int e = 0; e < p->n_ev; ++e) {
@@ -174,6 +178,8 @@ int jubik_plan_destroy(jubik_plan* p) {
     }
     delete[] p->ev_in; delete[] p->ev_c;
     if (p->ev_bin) { for (int e = 0; e < p->g.E; ++e) if (p->ev_bin[e]) cudaEventDestroy(p->ev_bin[e]); delete[] p->ev_bin; }
+    if (p->ev_ring) { for (int e = 0; e < 2 * p->g.E; ++e) if (p->ev_ring[e]) cudaEventDestroy(p->ev_ring[e]); delete[] p->ev_ring; }
+    for (int i = 0; i < 2; ++i) if (p->ev_free[i]) cudaEventDestroy(p->ev_free[i]);
     if (p->ev_start) cudaEventDestroy(p->ev_start);
     if (p->ev_comm) cudaEventDestroy(p->ev_comm);
     if (p->st_in) cudaStreamDestroy(p->st_in);
@@ -266,6 +272,9 @@ static int ensure_comm_stream(jubik_plan* p) {
     JB_CK(cudaStreamCreateWithFlags(&p->st_comm, cudaStreamNonBlocking));
     p->ev_bin = new cudaEvent_t[p->g.E]();
     for (int e = 0; e < p->g.E; ++e) JB_CK(cudaEventCreateWithFlags(&p->ev_bin[e], cudaEventDisableTiming));
+    p->ev_ring = new cudaEvent_t[2 * p->g.E]();
+    for (int e = 0; e < 2 * p->g.E; ++e) JB_CK(cudaEventCreateWithFlags(&p->ev_ring[e], cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) JB_CK(cudaEventCreateWithFlags(&p->ev_free[i], cudaEventDisableTiming));
     JB_CK(cudaEventCreateWithFlags(&p->ev_comm, cudaEventDisableTiming));
     if (!p->ev_start) JB_CK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
     return 0;
@@ -521,6 +530,8 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
         if (p->S_max * g.E > 1) JB_TRY(ensure_second_workspace(p));
 #endif
     }
+    if ((p->flags & JUBIK_PLAN_SHARDED) && (p->flags & JUBIK_PLAN_HOST_CALL))
+        JB_TRY(alloc(p, (void**)&p->flatdev, ((size_t)g.E * N * N + JB_MAX_SLOTS) * sizeof(double), "host-call flat buffer"));
 #ifndef JB_EMU
     if (p->flags & JUBIK_PLAN_SHARDED) JB_TRY(ensure_comm_stream(p));
 #endif
@@ -1141,75 +1152,159 @@ long long jubik_sharded_flat_size(const jubik_plan* p, const jubik_comm* c, int 
     return -1;
 }
 
-int jubik_poisson_energy_and_grad_sharded(jubik_plan* p, jubik_comm* c, int shard_mode, const double* x, int S,
-                                          double* grad_local, double* flat, void* stream_) {
-    jb_stream_t st = (jb_stream_t)stream_;
-    if (int rc = check_call(p, x, flat, S)) return rc;
+// Sample- / module-sharded fused evaluation.  S may exceed the plan's max_samples: the samples run in chunks of
+// max_samples (the workspace holds one chunk) and their gradients are folded into `flat` chunk after chunk, in a
+// fixed order.  xh/flat_h != NULL: the host-buffer form (x arrives chunk by chunk through a two-slot device ring on a
+// copy stream, one energy bin at a time; the reduced segments of `flat` leave on another copy stream).
+static int sharded_impl(jubik_plan* p, jubik_comm* c, int shard_mode, const double* x, const double* xh, int S,
+                        double* grad_local, double* flat, double* flat_h, jb_stream_t st) {
+    if (!p) return fail(JUBIK_ERR_ARG, "null plan");
+    if ((!x && !xh) || !flat) return fail(JUBIK_ERR_ARG, "null array pointer");
+    if (S < 1) return fail(JUBIK_ERR_ARG, "n_samples must be >= 1");
     if (!p->has_expo || !p->has_data) return fail(JUBIK_ERR_ARG, "plan needs exposures and data for the Poisson energy");
     const JbGeom& g = p->g;
     const size_t npl = (size_t)g.N * g.N, npx = (size_t)g.E * npl;
     const int R = c ? c->n_ranks : 1, rank = c ? c->rank : 0;
-    size_t count = 0;
+    const int SM = p->S_max, nchunks = (S + SM - 1) / SM;
     if (shard_mode == JUBIK_SHARD_MODULES) {
         // this rank's modules only: partial energies (S) and partial gradients (S,E,N,N) land in flat and are summed
         if (grad_local) return fail(JUBIK_ERR_ARG, "module sharding has no per-rank gradient output (pass NULL)");
-        count = (size_t)S * npx + S;
-        if (int rc = jubik_poisson_energy_and_grad(p, x, S, flat + (size_t)S * npx, flat, stream_)) return rc;
-    } else if (shard_mode == JUBIK_SHARD_SAMPLES) {
-        count = npx + (size_t)R * S;
-        double* gl = grad_local;
-        if (!gl && S > 1) {
-            if (!p->gstage) return fail(JUBIK_ERR_ARG, "plan was created without JUBIK_PLAN_SHARDED: pass grad_local (S,E,N,N) "
-                                                       "or create the plan with the flag");
-            gl = p->gstage;
+        if (xh) return fail(JUBIK_ERR_ARG, "the host-buffer form shards samples only");
+        for (int c0 = 0; c0 < S; c0 += SM) {
+            const int Sc = std::min(SM, S - c0);
+            if (int rc = energy_and_grad_impl(p, x + (size_t)c0 * npx, Sc, flat + (size_t)S * npx + c0, flat + (size_t)c0 * npx, false, st))
+                return rc;
         }
-        if (!gl) gl = flat;   // one local sample and no per-sample output wanted: the gradient is written in place
-        double* eslot = flat + npx + (size_t)rank * S;
 #ifndef JB_EMU
-        if (c && c->nccl && R > 1 && g.E > 1 && p->st_comm) {
-            // Overlapped collective: one energy bin at a time; as soon as the sample-summed gradient of bin e is folded
-            // into flat, its all-reduce is issued on the collective's stream while the kernels of bin e+1 run.  Only the
-            // last bin's all-reduce (which also carries the energies, contiguous behind it) is exposed.
-            JbEpi ep; memset(&ep, 0, sizeof(ep));
-            ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
-            JB_CK(cudaEventRecord(p->ev_start, st));
-            JB_CK(cudaStreamWaitEvent(p->st_comm, p->ev_start, 0));
+        if (c && c->nccl)
+            if (int rc = g_nccl.AllReduce(flat, flat, (size_t)S * npx + S, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl, st))
+                return nccl_fail("ncclAllReduce", rc);
+#endif
+        return JUBIK_OK;
+    }
+    if (shard_mode != JUBIK_SHARD_SAMPLES) return fail(JUBIK_ERR_ARG, "unknown shard mode");
+    if (!grad_local && S > 1 && !p->gstage)
+        return fail(JUBIK_ERR_ARG, "plan was created without JUBIK_PLAN_SHARDED: pass grad_local (S,E,N,N) or create the plan with the flag");
+    double* eslot = flat + npx + (size_t)rank * S;
+    // chunk -> where its per-sample gradients go (S == 1 without grad_local: straight into flat, nothing to fold)
+    auto chunk_grad = [&](int c0) -> double* {
+        if (grad_local) return grad_local + (size_t)c0 * npx;
+        return S == 1 ? flat : p->gstage;
+    };
+#ifndef JB_EMU
+    const bool nccl = c && c->nccl;
+    const bool per_bin = p->st_comm && g.E > 1 && ((nccl && R > 1) || xh);
+    if (xh && !(p->st_comm && p->st_in && p->xdev && p->gdev))
+        return fail(JUBIK_ERR_ARG, "the host-buffer sharded call needs a plan created with JUBIK_PLAN_HOST_CALL | JUBIK_PLAN_SHARDED");
+    if (per_bin || xh) {
+        // One energy bin at a time: as soon as the sample-summed gradient of bin e of the LAST chunk is folded into flat,
+        // its all-reduce is issued on the collective's stream (and, host form, its D2H on the copy stream) while the
+        // kernels of bin e+1 run.  Only the last bin's all-reduce (which also carries the energies, contiguous behind
+        // it) is exposed.
+        JbEpi ep; memset(&ep, 0, sizeof(ep));
+        ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
+        JB_CK(cudaEventRecord(p->ev_start, st));
+        JB_CK(cudaStreamWaitEvent(p->st_comm, p->ev_start, 0));
+        double* ring[2] = {p->xdev, p->gdev};
+        auto h2d_chunk = [&](int ci) -> int {      // host form: planes in (bin, sample) order, one event per bin
+            const int c0 = ci * SM, Sc = std::min(SM, S - c0), slot = ci & 1;
+            if (ci >= 2) JB_CK(cudaStreamWaitEvent(p->st_in, p->ev_free[slot], 0));
+            for (int e = 0; e < g.E; ++e) {
+                for (int s = 0; s < Sc; ++s)
+                    JB_CK(cudaMemcpyAsync(ring[slot] + ((size_t)s * g.E + e) * npl, xh + ((size_t)(c0 + s) * g.E + e) * npl,
+                                          npl * sizeof(double), cudaMemcpyHostToDevice, p->st_in));
+                JB_CK(cudaEventRecord(p->ev_ring[slot * g.E + e], p->st_in));
+            }
+            return 0;
+        };
+        if (xh) {
+            JB_CK(cudaStreamWaitEvent(p->st_in, p->ev_start, 0));
+            JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_start, 0));
+            if (int rc = h2d_chunk(0)) return rc;
+        }
+        for (int ci = 0; ci < nchunks; ++ci) {
+            const int c0 = ci * SM, Sc = std::min(SM, S - c0), slot = ci & 1;
+            const bool last_chunk = ci == nchunks - 1;
+            if (xh && !last_chunk) if (int rc = h2d_chunk(ci + 1)) return rc;
+            const double* xc = xh ? ring[slot] : x + (size_t)c0 * npx;
+            double* gl = chunk_grad(c0);
             for (int e = 0; e < g.E; ++e) {
                 JbGeom ge = g;
                 ge.e0 = e; ge.Es = 1;
-                if (int rc = run_forward_g(p, ge, x, S, ep, 0, st)) return rc;
-                if (e == g.E - 1) { if (int rc = reduce_energy(p, S, eslot, st)) return rc; }
-                if (int rc = run_adjoint_g(p, ge, p->gbuf, nullptr, S, gl, nullptr, st)) return rc;
                 const bool last = e == g.E - 1;
+                if (xh) JB_CK(cudaStreamWaitEvent(st, p->ev_ring[slot * g.E + e], 0));
+                if (int rc = run_forward_g(p, ge, xc, Sc, ep, 0, st)) return rc;
+                if (last) { if (int rc = reduce_energy(p, Sc, eslot + c0, st)) return rc; }
+                if (int rc = run_adjoint_g(p, ge, p->gbuf, nullptr, Sc, gl, nullptr, st)) return rc;
+                if (last && xh) JB_CK(cudaEventRecord(p->ev_free[slot], st));
                 JB_LAUNCHED(p, jb_launch(k_fold_samples, dim3(592), dim3(256), 0, st,
-                                         (const double*)(gl == flat ? nullptr : gl + (size_t)e * npl), S, npl, npx,
-                                         flat + (size_t)e * npl, last ? flat + npx : nullptr, rank * S, R * S));
+                                         (const double*)(gl == flat ? nullptr : gl + (size_t)e * npl), Sc, npl, npx,
+                                         flat + (size_t)e * npl, (int)(ci > 0),
+                                         (last && last_chunk) ? flat + npx : nullptr, rank * S, S, R * S));
+                if (!last_chunk) continue;
                 JB_CK(cudaEventRecord(p->ev_bin[e], st));
-                JB_CK(cudaStreamWaitEvent(p->st_comm, p->ev_bin[e], 0));
                 double* seg = flat + (size_t)e * npl;
                 const size_t cnt = last ? npl + (size_t)R * S : npl;
-                if (int rc = g_nccl.AllReduce(seg, seg, cnt, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl, p->st_comm))
-                    return nccl_fail("ncclAllReduce", rc);
+                if (nccl) {
+                    JB_CK(cudaStreamWaitEvent(p->st_comm, p->ev_bin[e], 0));
+                    if (int rc = g_nccl.AllReduce(seg, seg, cnt, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl, p->st_comm))
+                        return nccl_fail("ncclAllReduce", rc);
+                    if (flat_h) JB_CK(cudaEventRecord(p->ev_bin[e], p->st_comm));
+                }
+                if (flat_h) {
+                    JB_CK(cudaStreamWaitEvent(p->st_out, p->ev_bin[e], 0));
+                    JB_CK(cudaMemcpyAsync(flat_h + (size_t)e * npl, seg, cnt * sizeof(double), cudaMemcpyDeviceToHost, p->st_out));
+                }
             }
-            JB_CK(cudaEventRecord(p->ev_comm, p->st_comm));
-            JB_CK(cudaStreamWaitEvent(st, p->ev_comm, 0));
-            return JUBIK_OK;
         }
+        JB_CK(cudaEventRecord(p->ev_comm, p->st_comm));
+        JB_CK(cudaStreamWaitEvent(st, p->ev_comm, 0));
+        if (flat_h) {
+            JB_CK(cudaEventRecord(p->ev_comm, p->st_out));
+            JB_CK(cudaStreamWaitEvent(st, p->ev_comm, 0));
+        }
+        return JUBIK_OK;
+    }
+#else
+    (void)xh; (void)flat_h;
 #endif
-        if (int rc = jubik_poisson_energy_and_grad(p, x, S, eslot, gl, stream_)) return rc;
-        JB_LAUNCHED(p, jb_launch(k_fold_samples, dim3(1184), dim3(256), 0, st, (const double*)(gl == flat ? nullptr : gl), S, npx,
-                                 npx, flat, flat + npx, rank * S, R * S));
-    } else {
-        return fail(JUBIK_ERR_ARG, "unknown shard mode");
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int c0 = ci * SM, Sc = std::min(SM, S - c0);
+        double* gl = chunk_grad(c0);
+        if (int rc = energy_and_grad_impl(p, x + (size_t)c0 * npx, Sc, eslot + c0, gl, false, st)) return rc;
+        JB_LAUNCHED(p, jb_launch(k_fold_samples, dim3(1184), dim3(256), 0, st, (const double*)(gl == flat ? nullptr : gl), Sc, npx,
+                                 npx, flat, (int)(ci > 0), ci == nchunks - 1 ? flat + npx : nullptr, rank * S, S, R * S));
     }
 #ifndef JB_EMU
     if (c && c->nccl) {   // also for a one-rank communicator (NCCL treats it as an in-place copy)
-        if (int rc = g_nccl.AllReduce(flat, flat, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl, st))
+        if (int rc = g_nccl.AllReduce(flat, flat, npx + (size_t)R * S, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl, st))
             return nccl_fail("ncclAllReduce", rc);
     }
 #endif
-    (void)count;
     return JUBIK_OK;
+}
+
+int jubik_poisson_energy_and_grad_sharded(jubik_plan* p, jubik_comm* c, int shard_mode, const double* x, int S,
+                                          double* grad_local, double* flat, void* stream_) {
+    if (!x) return fail(JUBIK_ERR_ARG, "null array pointer");
+    return sharded_impl(p, c, shard_mode, x, nullptr, S, grad_local, flat, nullptr, (jb_stream_t)stream_);
+}
+
+int jubik_poisson_energy_and_grad_sharded_host(jubik_plan* p, jubik_comm* c, const double* x_host, int S, double* flat_host,
+                                               void* stream_) {
+#ifndef JB_EMU
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (!x_host || !flat_host) return fail(JUBIK_ERR_ARG, "null array pointer");
+    if (!p || !p->flatdev) return fail(JUBIK_ERR_ARG, "the host-buffer sharded call needs a plan created with JUBIK_PLAN_HOST_CALL | JUBIK_PLAN_SHARDED");
+    const int R = c ? c->n_ranks : 1;
+    if ((size_t)R * S > (size_t)JB_MAX_SLOTS) return fail(JUBIK_ERR_ARG, "more than 4096 samples over all ranks");
+    if (int rc = sharded_impl(p, c, JUBIK_SHARD_SAMPLES, nullptr, x_host, S, nullptr, p->flatdev, flat_host, st)) return rc;
+    if (stream_sync(st)) return fail(JUBIK_ERR_CUDA, "stream synchronise failed");
+    return JUBIK_OK;
+#else
+    (void)p; (void)c; (void)x_host; (void)S; (void)flat_host; (void)stream_;
+    return fail(JUBIK_ERR_UNSUPPORTED, "host-buffer calls need CUDA");
+#endif
 }
 
 }  // extern "C"

@@ -511,7 +511,7 @@ JB_GLOBAL_S void k_lsm_epi(const double* __restrict__ t, const double* __restric
 // grad == nullptr: the gradient of the single local sample already sits in dst; slots == nullptr: leave the energies alone
 // (the per-energy-bin calls of the overlapped collective clear them with the last bin only).
 JB_GLOBAL_S void k_fold_samples(const double* __restrict__ grad, int S, size_t cnt, size_t sstride, double* __restrict__ dst,
-                                double* __restrict__ slots, int slot0, int nslots) {
+                                int accumulate, double* __restrict__ slots, int slot0, int nown, int nslots) {
     const size_t t0 = (size_t)blockIdx.x * jb_nthr() + jb_tid(), nt = (size_t)gridDim.x * jb_nthr();
     if (grad) {
         const cd* g2 = reinterpret_cast<const cd*>(grad);   // 128-bit accesses (cnt and sstride are multiples of N*N, N even)
@@ -519,13 +519,14 @@ JB_GLOBAL_S void k_fold_samples(const double* __restrict__ grad, int S, size_t c
         const size_t h = cnt / 2, hs = sstride / 2;
         for (size_t i = t0; i < h; i += nt) {
             cd a = g2[i];
-            for (int s = 1; s < S; ++s) { cd b = g2[(size_t)s * hs + i]; a.x += b.x; a.y += b.y; }   // fixed order
+            if (accumulate) { cd o = f2[i]; a.x = o.x + a.x; a.y = o.y + a.y; }   // earlier chunks first: fixed order
+            for (int s = 1; s < S; ++s) { cd b = g2[(size_t)s * hs + i]; a.x += b.x; a.y += b.y; }
             f2[i] = a;
         }
     }
     if (slots)
         for (size_t j = t0; j < (size_t)nslots; j += nt)
-            if ((int)j < slot0 || (int)j >= slot0 + S) slots[j] = 0.0;
+            if ((int)j < slot0 || (int)j >= slot0 + nown) slots[j] = 0.0;
 }
 
 // energy[s] = sum over (t,e) planes and row blocks of the per-CTA partials; one CTA per sample

@@ -29,6 +29,13 @@
 #ifndef JB_R5_CPS
 #define JB_R5_CPS 6   // CTAs per SM the SW = 1 kernel is register-limited to
 #endif
+#ifndef JB_R5_SPF
+#define JB_R5_SPF 2   // spectrum prefetch (forward kernel): 1 = before, 2 = after the assembly of a row, one
+                      // cp.async.bulk.prefetch.L2 per covering (row-patch, column block) spectrum row of the NEXT image row of
+                      // this CTA.  r2b, B200: forward c2r pass 202.7 -> 191.1 us (C2, S = 2), 6.97 -> 6.77 ms (C5 chunk) with
+                      // mode 2; mode 1 is slower (229 us: the prefetches queue in front of the row's own loads).  The adjoint
+                      // kernel gathers T modules per row -- its prefetch volume overflows L2 (2.06 -> 2.61 ms) -- so it stays off.
+#endif
 #ifndef JB_R5_EPF
 #define JB_R5_EPF 1   // 1: warm L2 with this row's exposure / counts (Poisson epilogue operands) before the spectra are
                       //    assembled (r1z: forward c2r pass 124.1 -> 119.8 us at C2, S = 1; bitwise identical results)
@@ -267,6 +274,45 @@ JB_D void jb_rows5_assemble(cd* tile, const cd* const (&pbase)[SW][2], const boo
     else if (cnt == 4) jb_rows5_assemble_c<F3, SW, ADJ, 4, (B / 4 >= 1 ? B / 4 : 1)>(tile, pbase, has, tstride, T, rowoff, wr, atab, lane);
 }
 
+#ifndef JB_EMU
+// L2 prefetch of every spectrum row that image-row item `nxt` will gather: (covering row-patch j) x (column block i)
+// [x (module t) in the adjoint], PH*16 bytes each, spread over the CTA's threads
+template <bool ADJ>
+JB_D void jb_rows5_prefetch_next(const JbGeom& g, const cd* __restrict__ src, long nxt, long nitems, int ROWS, int shift,
+                                 size_t plane_sz, size_t istride, int tid, int NT) {
+    if (nxt >= nitems) return;
+    const int N = g.N, n = g.n, PH = g.PH;
+    const int lp = (int)(nxt / N), r = (int)(nxt - (long)lp * N);
+    const cd* plane0;
+    int T = 1;
+    size_t tstride = 0;
+    if (!ADJ) {
+        int ste, te, se;
+        jb_map_ste(g, lp, ste, te, se);
+        plane0 = src + (size_t)ste * plane_sz;
+    } else {
+        int s_i, e_i;
+        jb_map_se(g, lp, s_i, e_i);
+        T = g.T;
+        plane0 = src + ((size_t)(s_i * g.T) * g.E + e_i) * plane_sz;
+        tstride = (size_t)g.E * plane_sz;
+    }
+    const int per_j = n * T;
+    int base = 0;
+    for (int j = 0; j < n; ++j) {
+        const int u = r + shift - g.offs[j];
+        if (u < 0 || u >= ROWS) continue;
+        for (int idx = tid - base; idx < per_j; idx += NT) {
+            if (idx < 0) continue;
+            const int t = idx / n, i = idx - t * n;
+            jb_bulk_prefetch_l2(plane0 + (size_t)t * tstride + (size_t)i * istride + (size_t)(j * ROWS + u) * PH,
+                                (uint32_t)(PH * sizeof(cd)));
+        }
+        base = (base + per_j) % NT;
+    }
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------------
 // grid: persistent (any size), block = NW*32 threads, NW = ceil(ceil(n/2)/SW).
 //   forward (ADJ = false): src = bufA (STE, n*n, P, PH); items = planes*N over launched (S,T,Es) planes; epilogue ep.
@@ -364,7 +410,13 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
             jb_bulk_prefetch_l2(ep.data + ((size_t)te * N + r) * N, (uint32_t)(N * sizeof(double)));
         }
 #endif
+#if !defined(JB_EMU) && JB_R5_SPF == 1
+        if (!ADJ) jb_rows5_prefetch_next<ADJ>(g, src, it_ + gridDim.x, nitems, ROWS, shift, plane_sz, istride, tid, NT);
+#endif
         jb_rows5_assemble<F3, SW, ADJ>(tile, pbase, has, tstride, T, cnt, rowoff, wr, atab, lane);
+#if !defined(JB_EMU) && JB_R5_SPF == 2
+        if (!ADJ) jb_rows5_prefetch_next<ADJ>(g, src, it_ + gridDim.x, nitems, ROWS, shift, plane_sz, istride, tid, NT);
+#endif
         JB_SYNCWARP();
         R::s3(tile, itab, lane);
         JB_SYNCWARP();

@@ -160,14 +160,14 @@ class ResponsePlan:
         if t.device != self.device:
             raise ValueError("%s lives on %s but the plan on %s" % (what, t.device, self.device))
 
-    def _sky(self, x):
+    def _sky(self, x, chunked=False):
         self._on_device(x, "input")
         squeeze = x.dim() == 3
         if squeeze:
             x = x.unsqueeze(0)
         if x.dim() != 4 or tuple(x.shape[1:]) != (self.E, self.N, self.N):
             raise ValueError("sky should have shape ([S,] E, N, N)")
-        if x.shape[0] > self.S_max:
+        if x.shape[0] > self.S_max and not chunked:
             raise ValueError("more samples than the plan's max_samples")
         return x.contiguous(), squeeze
 
@@ -270,9 +270,10 @@ class ResponsePlan:
           SHARD_SAMPLES: x = this rank's (S,E,N,N) samples -> (energies (n_ranks,S), sample-summed gradient (E,N,N));
                          grad_local (S,E,N,N), if given, receives the per-sample gradients of this rank.
           SHARD_MODULES: the plan holds this rank's modules, x is replicated -> (energies (S,), gradient (S,E,N,N)).
+        S may exceed max_samples: the library then evaluates the samples in chunks of max_samples.
         The returned tensors are views into `flat`."""
         import torch
-        x, _ = self._sky(x)
+        x, _ = self._sky(x, chunked=True)
         S = x.shape[0]
         n = self.flat_size(comm, S, shard_mode)
         if flat is None:
@@ -292,6 +293,24 @@ class ResponsePlan:
             return flat[npx:].view(R, S), flat[:npx].view(self.E, self.N, self.N)
         return flat[S * npx:], flat[:S * npx].view(S, self.E, self.N, self.N)
 
+    def energy_and_grad_sharded_host(self, x_host, comm, flat_host):
+        """End-to-end form of the sample-sharded call on HOST tensors (jubik_poisson_energy_and_grad_sharded_host):
+        x_host (S,E,N,N) float64 CPU (pinned for full PCIe speed; S may exceed max_samples), flat_host float64 CPU of
+        E*N*N + n_ranks*S elements <- [sample-summed gradient over all ranks | energies (n_ranks, S)].  Synchronises."""
+        import torch
+        R = comm.size if comm is not None else 1
+        if x_host.dim() != 4 or tuple(x_host.shape[1:]) != (self.E, self.N, self.N):
+            raise ValueError("x_host should have shape (S, E, N, N)")
+        S = x_host.shape[0]
+        npx = self.E * self.N * self.N
+        for name, t, numel in (("x_host", x_host, S * npx), ("flat_host", flat_host, npx + R * S)):
+            if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous():
+                raise TypeError("%s must be a contiguous float64 CPU tensor" % name)
+            if t.numel() != numel:
+                raise ValueError("%s has %d elements, expected %d" % (name, t.numel(), numel))
+        self._call("jubik_poisson_energy_and_grad_sharded_host", comm.handle if comm is not None else None,
+                   C.c_void_p(x_host.data_ptr()), S, C.c_void_p(flat_host.data_ptr()))
+        return flat_host[npx:].view(R, S), flat_host[:npx].view(self.E, self.N, self.N)
 
     def metric(self, x, v):
         """Fisher metric pulled back through R:  R^T diag(1/(R x)) R v."""

@@ -124,3 +124,14 @@ def test_emulated_sharded_entry_point_single_rank():
     assert flat.shape == (S * npx + S,)
     assert rel(flat[:S * npx].reshape(S, E, N, N), go) < TOL
     assert np.abs((flat[S * npx:] - eo) / eo).max() < TOL
+    # more samples than the workspace holds: chunks of max_samples folded into flat one after the other
+    p2 = EmuPlan(kern, N, n, m, exposure=expo, exposure_cut=500.0, pixel_area=synth.PIXEL_AREA, data=d,
+                 max_samples=2, cropped=True, fft_length=160)
+    for want_local in (True, False):
+        flat, gl = p2.energy_and_grad_sharded(x, _lib.SHARD_SAMPLES, want_local)
+        assert np.abs((flat[npx:] - eo) / eo).max() < TOL
+        assert rel(flat[:npx].reshape(E, N, N), go.sum(0)) < TOL
+        if want_local:
+            assert rel(gl, go) < TOL
+    flat, _ = p2.energy_and_grad_sharded(x, _lib.SHARD_MODULES)
+    assert rel(flat[:S * npx].reshape(S, E, N, N), go) < TOL and np.abs((flat[S * npx:] - eo) / eo).max() < TOL

@@ -578,6 +578,50 @@ def test_error_behaviour_matches_reference(torch_cuda):
         p.psf(torch.zeros((1, 64, 64), dtype=torch.float64))
 
 
+def test_sharded_call_in_chunks_and_its_host_buffer_form(torch_cuda):
+    """More samples than the workspace holds (bench.py's C5 on one GPU: 16 samples in chunks of 2): the chunked sharded
+    call returns every sample's energy bit for bit and the sample-summed gradient of a plan that holds all samples at
+    once; the host-buffer form (x ring on a copy stream, one bin at a time) is bitwise equal to the device form."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    case = (512, 4, 64, 2, 3, 5, False, True)
+    N, n, m, T, E, S, full, eff = case
+    dom, kern, cropped, expo, ea, x, R, d = build_case(*case)
+
+    def mk(smax, **kw):
+        return jb.ResponsePlan(dev(torch, kern), N, n, m, exposure=dev(torch, expo), exposure_cut=500.0,
+                               eff_area=dev(torch, ea), pixel_area=synth.PIXEL_AREA, data=dev(torch, d), max_samples=smax,
+                               cropped=cropped, **kw)
+    xd = dev(torch, x)
+    big = mk(S)
+    e0, g0 = big.energy_and_grad(xd)
+    eo, go = zip(*[orc.energy_and_grad(R, d, x[s]) for s in range(2)])
+    assert rel(g0[:2].cpu().numpy(), np.stack(go)) < TOL
+    npx = E * N * N
+    p = mk(2, host_call=True, sharded=True)
+    for want_local in (False, True):
+        gl = torch.empty_like(xd) if want_local else None
+        en, gs = p.energy_and_grad_sharded(xd, None, jb.SHARD_SAMPLES, grad_local=gl)
+        assert torch.equal(en.flatten(), e0)
+        assert rel(gs.cpu().numpy(), g0.sum(0).cpu().numpy()) < 1e-13
+        if want_local:
+            assert torch.equal(gl, g0)
+    flat = torch.empty(npx + S, dtype=torch.float64, device="cuda")
+    p.energy_and_grad_sharded(xd, None, jb.SHARD_SAMPLES, flat=flat)
+    xh = torch.as_tensor(x).pin_memory()
+    fh = torch.empty(npx + S, dtype=torch.float64).pin_memory()
+    for _ in range(3):
+        fh.zero_()
+        p.energy_and_grad_sharded_host(xh, None, fh)
+        assert torch.equal(fh, flat.cpu())
+    em, gm = p.energy_and_grad_sharded(xd, None, jb.SHARD_MODULES)
+    assert torch.equal(em, e0) and torch.equal(gm, g0)
+    with pytest.raises(jb.JubikError, match="JUBIK_PLAN_HOST_CALL"):
+        big.energy_and_grad_sharded_host(xh, None, fh)
+    p.close()
+    big.close()
+
+
 def test_sharded_entry_point_with_one_rank_nccl_communicator(torch_cuda):
     """jubik_poisson_energy_and_grad_sharded through a real (one-rank) NCCL communicator created by the C library:
     dlopen of libnccl, ncclCommInitRank, the fold kernel and an in-place ncclAllReduce on the plan's stream."""

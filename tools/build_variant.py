@@ -1,5 +1,6 @@
-"""Build a tuning variant of the CUDA library: recompile ONE FFT length with extra -D flags and link it with the
-other objects of the regular build into jubik_b200/_variants/lib_<tag>.so (loaded via JUBIK_B200_LIB=...).
+"""Build a tuning variant of the CUDA library: recompile ONE FFT length with extra -D flags and link it with capi.o
+and null stubs for every other length (a variant serves only geometries of its own length; ~10 MB instead of ~100 MB,
+the gpurun snapshot is capped) into jubik_b200/_variants/lib_<tag>.so (loaded via JUBIK_B200_LIB=...).
 
     python tools/build_variant.py <tag> <L> -DJB_R5_B=6 -DJB_R5_CPS=5
 """
@@ -20,8 +21,11 @@ b.build()
 out = os.path.join(b.HERE, "_variants")
 os.makedirs(out, exist_ok=True)
 objs = []
+stubs = "struct JbFftOps;\n"
 for (l, r1, r2, cb, pipe, q1, q2, q3) in b.fft_list():
-    o = os.path.join(b.OBJ, "fft_%d.o" % l)
+    o = None
+    if l != L:
+        stubs += "const JbFftOps* jb_fft_ops_%d() { return nullptr; }\n" % l
     if l == L:
         if cb_override:
             cb = cb_override
@@ -38,8 +42,12 @@ for (l, r1, r2, cb, pipe, q1, q2, q3) in b.fft_list():
                 print(line[:160])
             if "spill" in line and "0 bytes spill stores" not in line:
                 print("   ", line.strip())
-    objs.append(o)
-objs.append(os.path.join(b.OBJ, "capi.o"))
+    if o:
+        objs.append(o)
+stub_c, stub_o = os.path.join(out, "stubs_%d.cpp" % L), os.path.join(out, "stubs_%d.o" % L)
+open(stub_c, "w").write(stubs)
+subprocess.run(["g++", "-fPIC", "-c", stub_c, "-o", stub_o], check=True)
+objs += [stub_o, os.path.join(b.OBJ, "capi.o")]
 lib = os.path.join(out, "lib_%s.so" % tag)
 subprocess.run(["nvcc", "-shared", "-o", lib] + objs + ["-lcudart"], check=True)
 print(lib)
