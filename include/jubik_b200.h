@@ -108,6 +108,16 @@ int jubik_plan_set_data(jubik_plan* plan, const void* data, int data_dtype, void
  * (erosita_response.py:349-350, erosita_likelihood.py:73-83): the binding calls it only when k actually changed.
  * Fails with JUBIK_ERR_UNSUPPORTED if the new PSF's support no longer fits the plan's transform length. Synchronises. */
 int jubik_plan_set_kernel(jubik_plan* plan, const double* kernel, int kernel_layout, void* stream);
+/* The same, but only if `kernel` differs from the kernels the resident spectra were built from: a 128-bit content
+ * fingerprint (two wrap-around 64-bit sums over the bit patterns, one position-weighted) is taken on the device -- one
+ * streaming read of the array, 0.1 ms for the 700 MB of cropped kernels of BASELINE configs[2] -- and compared with the
+ * plan's.  This is what R(x, k) costs per call when k is a traced argument whose identity the binding cannot see
+ * (FullModel.__call__, erosita_likelihood.py:73-83).  *replanned (may be NULL) <- 1 if the spectra were rebuilt.
+ * Synchronises. */
+int jubik_plan_ensure_kernel(jubik_plan* plan, const double* kernel, int kernel_layout, int* replanned, void* stream);
+/* cudaStreamSynchronize for bindings that have no CUDA runtime of their own at hand (the jax binding synchronises the
+ * stream it created the plan / bound the data on before XLA's streams use them) */
+int jubik_stream_synchronize(void* stream);
 /* kernels launched through this plan so far (bench.py's gpu_launches) */
 long long jubik_plan_launch_count(const jubik_plan* plan);
 
@@ -142,8 +152,12 @@ int jubik_poisson_energy_and_grad_logsky(jubik_plan* plan, const double* log_sky
  *   jubik_slice_patches    jubik/convolve.py:28-63: x (lead,h,w) -> out (n*n, lead, 2dx+2dr, 2dy+2dr), patch k = i*n+j at
  *                          row offset j*dx, column offset i*dy of the dx//2-padded array (dynamic_slice clamping)
  *   jubik_slice_patches_T  its exact transpose (jax.linear_transpose): patches -> (lead,h,w), deterministic gather
- *   jubik_convolve         jubik/convolve.py:148-176: dvol * Re ifftn(fftn(x) * fftn(y)) over the last two axes, evaluated
- *                          as a direct circular sum (n0*n1 <= 256*256); x_lead == 1 is the broadcasting branch :167-171 */
+ *   jubik_convolve         jubik/convolve.py:148-176: dvol * Re ifftn(fftn(x) * fftn(y)) over the last two axes of x
+ *                          (x_lead,n0,n1) and y (lead,n0,n1); x_lead == 1 is the broadcasting branch :167-171.  When both
+ *                          sides are compiled transform lengths (jubik_fft_length_supported; any of them, rectangular
+ *                          too) it runs as r2c rows -> column FFTs * product * inverse -> c2r rows on the library's FFT
+ *                          kernels (workspace: stream-ordered cudaMallocAsync); other shapes, and anything below
+ *                          32 x 32, as a direct circular sum (n0*n1 <= 256*256). */
 int jubik_slice_patches(const double* x, int lead, int h, int w, int n_patches, int dr, double* out, void* stream);
 int jubik_slice_patches_T(const double* patches, int lead, int h, int w, int n_patches, int dr, double* out, void* stream);
 int jubik_convolve(const double* x, const double* y, int lead, int x_lead, int n0, int n1, double dvol, double* out,

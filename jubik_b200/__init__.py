@@ -5,9 +5,9 @@ log-likelihood, forward and exact adjoint, float64.  See DESIGN.md / INTEGRATION
 Importing the package does not need a GPU; every compute entry point does and raises otherwise.
 """
 from ._lib import JubikError, load as load_library  # noqa: F401
-from .api import (Domain, PoissonLikelihood, Vector, build_exposure_function, build_psf_operator,  # noqa: F401
-                  build_readout_function, build_response, convolve, integrate, linpatch_convolve, slice_patches,
-                  slice_patches_T)
+from .api import (Domain, FullModel, PoissonLikelihood, Vector, build_exposure_function,  # noqa: F401
+                  build_mask_adjoint, build_psf_operator, build_readout_function, build_response, calculate_nwr,
+                  convolve, create_mock_data, integrate, linpatch_convolve, slice_patches, slice_patches_T)
 from .plan import Communicator, ResponsePlan  # noqa: F401
 from ._lib import SHARD_MODULES, SHARD_SAMPLES  # noqa: F401
 from . import sharding  # noqa: F401

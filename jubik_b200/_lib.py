@@ -20,6 +20,7 @@ PLAN_HOST_CALL, PLAN_METRIC, PLAN_SHARDED = 1, 2, 4
 EXPORTS = [
     "jubik_last_error", "jubik_version", "jubik_fft_length_supported", "jubik_device_count",
     "jubik_plan_create", "jubik_plan_destroy", "jubik_plan_get_info", "jubik_plan_set_data", "jubik_plan_set_kernel",
+    "jubik_plan_ensure_kernel", "jubik_stream_synchronize",
     "jubik_poisson_set_point", "jubik_poisson_metric_apply_at_point", "jubik_poisson_left_sqrt_metric_at_point",
     "jubik_plan_launch_count", "jubik_psf_apply", "jubik_psf_apply_T", "jubik_response_apply",
     "jubik_response_apply_T", "jubik_poisson_energy_and_grad", "jubik_poisson_metric_apply",
@@ -67,10 +68,12 @@ def bind(lib):
     lib.jubik_plan_get_info.argtypes = [vp, C.POINTER(PlanInfo)]
     lib.jubik_plan_set_data.argtypes = [vp, vp, i, vp]
     lib.jubik_plan_set_kernel.argtypes = [vp, vp, i, vp]
+    lib.jubik_plan_ensure_kernel.argtypes = [vp, vp, i, C.POINTER(C.c_int), vp]
     lib.jubik_poisson_set_point.argtypes = [vp, vp, i, vp]
     lib.jubik_poisson_metric_apply_at_point.argtypes = [vp, vp, i, vp, vp]
     lib.jubik_poisson_left_sqrt_metric_at_point.argtypes = [vp, vp, i, vp, vp]
     lib.jubik_plan_launch_count.argtypes = [vp]
+    lib.jubik_stream_synchronize.argtypes = [vp]
     lib.jubik_plan_launch_count.restype = C.c_longlong
     for name in ("jubik_psf_apply", "jubik_psf_apply_T", "jubik_response_apply", "jubik_response_apply_T"):
         getattr(lib, name).argtypes = [vp, vp, i, vp, vp]

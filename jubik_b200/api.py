@@ -12,6 +12,10 @@ the reference's own:
     build_readout_function      jubik/response.py:48-112
     build_psf_operator          instruments/erosita/erosita_response.py:206-212 (psf_op), chandra :127-130
     build_response              erosita_response.py:307-358 / chandra_response.py:127-149 -> response_dict
+                                (dynamic_kernel=True: the eROSITA call form R(x, k) with 'kernel' in the dict)
+    build_mask_adjoint          jax.linear_transpose(response_dict['mask'], ...)  (data.py:156-160) -> 'mask_adj'
+    create_mock_data            data.py:138-146 (R(sky[, kernel]) + Poisson draw per key)
+    calculate_nwr               diagnostics.py:62-125 (batched R over the samples)
     PoissonLikelihood           jft.Poissonian(masked_data).amend(R)  (erosita_likelihood.py:85-89,
                                 chandra_likelihood.py:37)
 
@@ -173,9 +177,10 @@ def slice_patches_T(patches, shape, n_patches_per_axis, additional_margin):
 
 
 def convolve(x, y, domain, axes):
-    """Drop-in for jubik.convolve (convolve.py:148-176): dvol * Re ifftn(fftn(x) * fftn(y)) over the last two axes,
-    including the broadcasting branch (y.ndim > x.ndim) and its console message.  Stand-alone calls use a direct
-    circular sum on the GPU (arrays up to 256x256); the FFT pipeline is the ResponsePlan / linpatch_convolve path."""
+    """Drop-in for jubik.convolve (convolve.py:148-176): dvol * Re ifftn(fftn(x) * fftn(y)) over the last two axes, any
+    leading shape, including the broadcasting branch (y.ndim > x.ndim: hx[..., newaxis, :, :] * hy) and its console
+    message.  Arrays whose sides are compiled transform lengths run on the library's FFT kernels; anything else (up to
+    256 x 256) as a direct circular sum."""
     torch = _torch()
     from ._lib import load, check
     lib = load()
@@ -194,18 +199,19 @@ def convolve(x, y, domain, axes):
         print("kernel_shape:", tuple(x.shape))
         print("signal_shape:", tuple(y.shape))
         print("Dimension Inconsistency. Broadcasting PSFs")
-        if x.dim() != 2:
-            raise NotImplementedError("convolve: broadcasting is supported for a 2-D kernel")
-        x_lead = 1
-    else:
-        if tuple(x.shape) != tuple(y.shape):
-            raise ValueError("convolve: shapes must agree")
-        x_lead = None
+        x = x[..., None, :, :]
+    out_shape = tuple(torch.broadcast_shapes(tuple(x.shape), tuple(y.shape)))
     lead = 1
-    for v in y.shape[:-2]:
+    for v in out_shape[:-2]:
         lead *= v
-    out = torch.empty_like(y)
-    check(lib, lib.jubik_convolve(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), lead, lead if x_lead is None else 1,
+    x_lead1 = x.numel() == n0 * n1                 # one kernel for every signal plane: no expansion needed
+    xe = x.reshape(1, n0, n1) if x_lead1 else x.expand(out_shape)
+    xe = xe.contiguous()
+    ye = y.expand(out_shape).contiguous()
+    out = torch.empty(out_shape, dtype=torch.float64, device=x.device)
+    if lead == 0:
+        return out
+    check(lib, lib.jubik_convolve(C.c_void_p(xe.data_ptr()), C.c_void_p(ye.data_ptr()), lead, 1 if x_lead1 else lead,
                                   n0, n1, dvol, C.c_void_p(out.data_ptr()), _stream_ptr(torch)))
     return out
 
@@ -270,12 +276,32 @@ def build_psf_operator(kernel, domain, n_patches_per_axis, margin, max_samples=1
     return plan.psf, plan
 
 
-def build_response(kernel, exposures, domain, n_patches_per_axis, margin, pixel_area, exposure_cut=None,
-                   effective_area=None, keys=None, max_samples=1, cropped=False, data=None):
-    """Response dictionary with the reference's keys ('pix_area', 'psf', 'exposure', 'mask', 'R') plus the
-    fused entries ('R_dense', 'R_dense_T', 'plan').
+def build_mask_adjoint(mask, keys):
+    """Transpose of the readout (what `jax.linear_transpose(response_dict['mask'], ...)` yields, data.py:156-160,
+    sugar_plot.py:315-323, demos/x-ray-imaging.py:268-269): Vector{key: 1-D array of the unmasked pixels} -> a 1-tuple
+    holding the dense (T,E,N,N) array with zeros at the masked pixels -- callers take `[0]` like the reference."""
+    def mask_adj(v):
+        torch = _torch()
+        tree = v.tree if isinstance(v, Vector) else v
+        out = torch.zeros(mask.shape, dtype=torch.float64, device=mask.device)
+        for i, key in enumerate(keys):
+            out[i][~mask[i]] = torch.as_tensor(tree[key]).to(mask.device, torch.float64)
+        return (out,)
+    return mask_adj
 
-    R(x) = mask(exposure(psf(x * pixel_area)))  -- erosita_response.py:349-350, chandra_response.py:138-142.
+
+def build_response(kernel, exposures, domain, n_patches_per_axis, margin, pixel_area, exposure_cut=None,
+                   effective_area=None, keys=None, max_samples=1, cropped=False, data=None, dynamic_kernel=False,
+                   **plan_flags):
+    """Response dictionary with the reference's keys ('pix_area', 'psf', 'exposure', 'mask', 'R', and with
+    dynamic_kernel=True also 'kernel') plus 'mask_adj' and the fused entries ('R_dense', 'R_dense_T', 'plan').
+
+    R(x) = mask(exposure(psf(x * pixel_area)))  -- chandra_response.py:138-149.
+    dynamic_kernel=True is the eROSITA form (erosita_response.py:209-212,349-358): psf(x, k) and R(x, k) take the
+    kernel as an argument and the dictionary carries it under 'kernel' (callers branch on that key, data.py:138-142;
+    FullModel holds it as a dynamic leaf, erosita_likelihood.py:73-83).  The PSF spectra stay resident: a call with the
+    dictionary's own kernel object costs nothing extra, any other tensor is fingerprinted on the device and the
+    spectra are rebuilt only if its content differs (jubik_plan_ensure_kernel).
     The exposure cut is applied to both the exposure and the readout mask, as both instruments do
     (SURVEY Appendix A10)."""
     torch = _torch()
@@ -287,7 +313,7 @@ def build_response(kernel, exposures, domain, n_patches_per_axis, margin, pixel_
     eff = None if effective_area is None else _as_cuda(effective_area, kernel.device)
     plan = ResponsePlan(kernel, domain.shape[-1], n_patches_per_axis, margin, exposure=expo_raw,
                         exposure_cut=exposure_cut, eff_area=eff, pixel_area=pixel_area, data=data,
-                        max_samples=max_samples, cropped=cropped, distances=tuple(domain.distances[-2:]))
+                        max_samples=max_samples, cropped=cropped, distances=tuple(domain.distances[-2:]), **plan_flags)
     expo_thr = expo_raw.clone()
     tmp = build_exposure_function(expo_thr, exposure_cut)
     if eff is not None:
@@ -295,53 +321,153 @@ def build_response(kernel, exposures, domain, n_patches_per_axis, margin, pixel_
             return tmp(x) * eff[:, :, None, None]
     else:
         exposure_func = tmp
-    mask_func = build_readout_function(expo_raw.clone(), exposure_cut,
-                                       list(keys) if keys is not None else list(range(T)))
+    key_list = list(keys) if keys is not None else list(range(T))
+    flags = expo_raw.clone()
+    mask_func = build_readout_function(flags, exposure_cut, key_list)
+    mask_adj = build_mask_adjoint(flags == 0, key_list)      # build_readout_function thresholded `flags` in place
+    out = {'pix_area': pixel_area, 'exposure': exposure_func, 'mask': mask_func, 'mask_adj': mask_adj,
+           'R_dense': plan.response, 'R_dense_T': plan.response_T, 'plan': plan}
+    if not dynamic_kernel:
+        def response_func(x):
+            return mask_func(plan.response(x))
+        out.update({'psf': plan.psf, 'R': response_func})
+        return out
 
-    def response_func(x):
+    def use_kernel(k):
+        plan.ensure_kernel(k if getattr(k, "is_cuda", False) else _as_cuda(k, plan.device))
+
+    def psf_func(x, k):
+        use_kernel(k)
+        return plan.psf(x)
+
+    def response_func(x, k):
+        use_kernel(k)
         return mask_func(plan.response(x))
 
-    return {'pix_area': pixel_area, 'psf': plan.psf, 'exposure': exposure_func, 'mask': mask_func,
-            'R': response_func, 'R_dense': plan.response, 'R_dense_T': plan.response_T, 'plan': plan}
+    out.update({'psf': psf_func, 'R': response_func, 'kernel': kernel})
+    return out
+
+
+def create_mock_data(response_dict, sky, seed=0):
+    """The hot-path part of jubik.create_mock_data (data.py:138-146): masked_mock_data = R(sky[, kernel]) followed by
+    one Poisson draw per key, as int64.  (The reference draws with jax.random; the generator differs, the law does not.)"""
+    torch = _torch()
+    if 'kernel' in response_dict:
+        lam = response_dict['R'](sky, response_dict['kernel'])
+    else:
+        lam = response_dict['R'](sky)
+    out = {}
+    for i, (key, v) in enumerate(lam.tree.items()):
+        gen = torch.Generator(device=v.device)
+        gen.manual_seed(int(seed) + i)
+        out[key] = torch.poisson(v.clamp(min=0.0), generator=gen).to(torch.int64)
+    return Vector(out)
+
+
+def calculate_nwr(pos, op, data, response_dict, abs=False, min_counts=None, exposure_mask=True, response=True):
+    """jubik.calculate_nwr (diagnostics.py:62-125) on the batched response: noise-weighted residuals
+    (R(op(x)) - data) / sqrt(R(op(x))) of every sample x of `pos` (leading axis = samples, the reference's vmap), mapped
+    back onto the dense grid with 'mask_adj'.  Returns (res (T,S,E,N,N) like vmap(..., out_axes=1), tot_mask)."""
+    torch = _torch()
+    adj_mask = response_dict['mask_adj']
+    has_k = 'kernel' in response_dict
+
+    def R(x):
+        if not response:
+            return x
+        return response_dict['R'](x, response_dict['kernel']) if has_k else response_dict['R'](x)
+
+    def one(x):
+        lam = R(op(x))
+        if isinstance(lam, Vector):
+            return Vector({k: (lam[k] - data[k]) / torch.sqrt(lam[k]) for k in lam.keys()})
+        return (lam - data) / torch.sqrt(lam)
+
+    res = torch.stack([adj_mask(one(x))[0] for x in pos], dim=1)
+    if abs:
+        res = torch.abs(res)
+    min_count_mask = None
+    if min_counts is not None:
+        tree = data.tree if isinstance(data, Vector) else data
+        mi = Vector({k: (torch.as_tensor(v) < min_counts).to(torch.float64) for k, v in tree.items()})
+        min_count_mask = adj_mask(mi)[0]
+    tot_mask = None
+    if exposure_mask:
+        ones = torch.ones_like(op(pos[0]))
+        exp_mask = response_dict['exposure'](ones) == 0.
+        tot_mask = exp_mask if min_count_mask is None else torch.logical_or(min_count_mask.bool(), exp_mask)
+    elif min_count_mask is not None:
+        tot_mask = min_count_mask
+    if tot_mask is not None:
+        tot_mask = torch.stack([tot_mask] * len(pos), dim=1)
+    return res, tot_mask
+
+
+class FullModel:
+    """erosita_likelihood.py:73-83: the instrument with its kernel held as a (dynamic) leaf and an operator prepended:
+    FullModel(kern, instrument, pre_ops)(x) = instrument(x=pre_ops(x), k=kern)."""
+
+    def __init__(self, kern, instrument, pre_ops):
+        self.kern, self.instrument, self.pre_ops = kern, instrument, pre_ops
+
+    def __call__(self, x):
+        return self.instrument(x=self.pre_ops(x), k=self.kern)
 
 
 class PoissonLikelihood:
-    """jft.Poissonian(masked_data).amend(R) on the fused CUDA path.
+    """jft.Poissonian(masked_data).amend(R) on the fused CUDA path (erosita_likelihood.py:85-89,
+    chandra_likelihood.py:37).
 
     `data` is either dense (T,E,N,N) counts or a Vector/dict of the reference's compacted 1-D arrays per key
-    (response.py:110), which is scattered back onto the dense grid once (transpose of the mask)."""
+    (response.py:110), which is scattered back onto the dense grid once (transpose of the mask).  With the eROSITA
+    form of the response dictionary ('kernel' present) every call takes an optional kernel `k` -- the dynamic leaf of
+    FullModel; the PSF spectra are rebuilt only when its content changed."""
 
     def __init__(self, response_dict, data, keys=None):
         torch = _torch()
         self.plan = response_dict['plan']
+        self.kern = response_dict.get('kernel')
         if isinstance(data, (Vector, dict)):
             tree = data.tree if isinstance(data, Vector) else data
             keys = list(tree.keys()) if keys is None else keys
-            p = self.plan
-            probe = torch.ones((p.T, p.E, p.N, p.N), dtype=torch.float64, device=p.device)
-            expo = response_dict['exposure'](probe)
-            mask = expo != 0
-            dense = torch.zeros((p.T, p.E, p.N, p.N), dtype=torch.float64, device=p.device)
-            for i, k in enumerate(keys):
-                dense[i][mask[i]] = torch.as_tensor(tree[k]).to(p.device, torch.float64)
-            data = dense
+            data = response_dict['mask_adj'](Vector({k: tree[k] for k in keys}))[0] if 'mask_adj' in response_dict \
+                else self._scatter(response_dict, tree, keys)
         self.plan.set_data(torch.as_tensor(data))
 
-    def energy(self, x):
+    def _scatter(self, response_dict, tree, keys):
+        torch = _torch()
+        p = self.plan
+        probe = torch.ones((p.T, p.E, p.N, p.N), dtype=torch.float64, device=p.device)
+        mask = response_dict['exposure'](probe) != 0
+        dense = torch.zeros((p.T, p.E, p.N, p.N), dtype=torch.float64, device=p.device)
+        for i, k in enumerate(keys):
+            dense[i][mask[i]] = torch.as_tensor(tree[k]).to(p.device, torch.float64)
+        return dense
+
+    def _use(self, k):
+        if k is not None:
+            self.plan.ensure_kernel(k if getattr(k, "is_cuda", False) else _as_cuda(k, self.plan.device))
+
+    def energy(self, x, k=None):
+        self._use(k)
         return self.plan.energy(x)
 
-    def value_and_grad(self, x):
+    def value_and_grad(self, x, k=None):
+        self._use(k)
         return self.plan.energy_and_grad(x)
 
-    def metric(self, x, v):
+    def metric(self, x, v, k=None):
+        self._use(k)
         return self.plan.metric(x, v)
 
-    def left_sqrt_metric(self, x, t):
+    def left_sqrt_metric(self, x, t, k=None):
         """R^T (t / sqrt(R x)) for a dense data-space tangent t ([S,] T, E, N, N); masked pixels are ignored."""
+        self._use(k)
         return self.plan.left_sqrt_metric(x, t)
 
-    def value_and_grad_logsky(self, log_sky):
+    def value_and_grad_logsky(self, log_sky, k=None):
         """value_and_grad with respect to log_sky, sky = exp(log_sky) (jubik/sky_models.py:340-341)."""
+        self._use(k)
         return self.plan.energy_and_grad_logsky(log_sky)
 
     __call__ = energy

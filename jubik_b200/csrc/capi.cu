@@ -5,6 +5,8 @@
 #include "../../include/jubik_b200.h"
 #include <algorithm>
 #include <functional>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 #include <new>
@@ -102,6 +104,9 @@ struct jubik_plan {
     double* data = nullptr;    // (T,E,N,N)
     double* psums = nullptr;   // (T*E*n*n) PSF sums and half-supports: plan creation and jubik_plan_set_kernel
     int* psupp = nullptr;
+    unsigned long long* fpdev = nullptr;   // per-CTA fingerprint pairs (jubik_plan_ensure_kernel)
+    unsigned long long fp[2] = {0, 0};     // fingerprint of the kernels the resident spectra were built from
+    int fp_layout = -1;
     // bufA: forward  column-pass output (STE, n^2, P or L, PH) -> rows_out;  adjoint row spectra rowsA (STE, n, N, PH)
     // bufB: adjoint  column-pass output (STE, n^2, w, PH) -> rows_adj_out; forward row spectra rowsF (S*E, n, N, PH)
     // (each direction uses one buffer as its de-duplicated input and the other as its per-patch output)
@@ -167,7 +172,7 @@ int jubik_device_count(void) { return device_count(); }
 
 int jubik_plan_destroy(jubik_plan* p) {
     if (!p) return JUBIK_OK;
-    void* bufs[] = {p->khat, p->tw_nk, p->tw_kn, p->tw1, p->tw2, p->wgt, p->expo, p->data, p->psums, p->psupp, p->bufA, p->bufB,
+    void* bufs[] = {p->fpdev, p->khat, p->tw_nk, p->tw_kn, p->tw1, p->tw2, p->wgt, p->expo, p->data, p->psums, p->psupp, p->bufA, p->bufB,
                     p->bufA2, p->bufB2, p->gbuf2, p->gbuf, p->fac, p->partial, p->gtab_fwd, p->gtab_adj, p->xdev, p->gdev,
                     p->edev, p->gstage, p->flatdev};
     for (void* b : bufs) dev_free(b);
@@ -232,6 +237,25 @@ static int psf_stats(jubik_plan* p, const JbKsrc& ks, jb_stream_t st) {
     int mx = 0;
     for (int v : hs) mx = v > mx ? v : mx;
     p->support = mx;
+    return 0;
+}
+
+#define JB_FP_CTAS 296
+static size_t kernel_elems(const jubik_plan* p, int layout) {
+    const JbGeom& g = p->g;
+    const size_t side = layout == JUBIK_KERNEL_CROPPED ? (size_t)g.w : (size_t)g.N;
+    return (size_t)g.T * g.n * g.n * g.E * side * side;
+}
+// fingerprint of a kernel array -> fp[2]; synchronises the stream
+static int kernel_fingerprint(jubik_plan* p, const double* kernel, int layout, jb_stream_t st, unsigned long long* fp) {
+    if (!p->fpdev && alloc(p, (void**)&p->fpdev, 2 * JB_FP_CTAS * sizeof(unsigned long long), "kernel fingerprint")) return JUBIK_ERR_ALLOC;
+    JB_CK(jb_launch(k_fingerprint, dim3(JB_FP_CTAS), dim3(256), 2 * 256 * sizeof(unsigned long long), st, kernel,
+                    kernel_elems(p, layout), p->fpdev));
+    ++p->launches;
+    unsigned long long h[2 * JB_FP_CTAS];
+    if (d2h(h, p->fpdev, sizeof(h), st) || stream_sync(st)) return fail(JUBIK_ERR_CUDA, "reading the kernel fingerprint failed");
+    fp[0] = fp[1] = 0;
+    for (int i = 0; i < JB_FP_CTAS; ++i) { fp[0] += h[2 * i]; fp[1] += h[2 * i + 1]; }
     return 0;
 }
 
@@ -516,6 +540,8 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
 #endif
     JB_TRY(psf_spectra(p, ks, st));
     if (stream_sync(st)) return fail(JUBIK_ERR_CUDA, "PSF spectrum kernels failed");
+    JB_TRY(kernel_fingerprint(p, d->kernel, d->kernel_layout, st, p->fp));
+    p->fp_layout = d->kernel_layout;
     // ---- optional staging, all of it allocated HERE (no allocation after plan creation)
     if (p->flags & JUBIK_PLAN_METRIC) JB_TRY(alloc(p, (void**)&p->fac, bG, "metric linearisation point"));
     if (p->flags & JUBIK_PLAN_SHARDED)
@@ -572,7 +598,22 @@ int jubik_plan_set_kernel(jubik_plan* p, const double* kernel, int kernel_layout
         if (g.fold) g.ext = p->support > g.m ? p->support - g.m : 0;
     }
     p->point_S = 0;    // a cached linearisation point belongs to the old response
-    return psf_spectra(p, ks, st);
+    p->fp_layout = -1;
+    if (int rc = psf_spectra(p, ks, st)) return rc;
+    if (int rc = kernel_fingerprint(p, kernel, kernel_layout, st, p->fp)) return rc;
+    p->fp_layout = kernel_layout;
+    return JUBIK_OK;
+}
+
+int jubik_plan_ensure_kernel(jubik_plan* p, const double* kernel, int kernel_layout, int* replanned, void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (!p || !kernel) return fail(JUBIK_ERR_ARG, "null plan/kernel");
+    if (replanned) *replanned = 0;
+    unsigned long long fp[2];
+    if (int rc = kernel_fingerprint(p, kernel, kernel_layout, st, fp)) return rc;
+    if (kernel_layout == p->fp_layout && fp[0] == p->fp[0] && fp[1] == p->fp[1]) return JUBIK_OK;
+    if (replanned) *replanned = 1;
+    return jubik_plan_set_kernel(p, kernel, kernel_layout, stream_);
 }
 
 int jubik_plan_set_data(jubik_plan* p, const void* data, int dtype, void* stream_) {
@@ -609,6 +650,11 @@ int jubik_plan_get_info(const jubik_plan* p, jubik_plan_info* i) {
 }
 
 long long jubik_plan_launch_count(const jubik_plan* p) { return p ? p->launches : 0; }
+
+int jubik_stream_synchronize(void* stream_) {
+    if (stream_sync((jb_stream_t)stream_)) return fail(JUBIK_ERR_CUDA, "stream synchronise failed");
+    return JUBIK_OK;
+}
 
 static int check_call(jubik_plan* p, const void* a, const void* b, int S) {
     if (!p) return fail(JUBIK_ERR_ARG, "null plan");
@@ -969,15 +1015,77 @@ int jubik_slice_patches_T(const double* patches, int lead, int h, int w, int n_p
     JB_CK(jb_launch(k_slice_patches_T, dim3(1184), dim3(256), 0, (jb_stream_t)stream_, q, patches, out));
     return JUBIK_OK;
 }
+// twiddle tables of a compiled length for the stand-alone convolution: device-resident, built once per (device, length)
+static int conv_twiddles(int L, const JbFftOps* o, const cd** tw_nk, const cd** tw_kn, jb_stream_t st) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, std::pair<cd*, cd*>> cache;
+    int dev = 0;
+#ifndef JB_EMU
+    cudaGetDevice(&dev);
+#endif
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find({dev, L});
+    if (it == cache.end()) {
+        const int R1 = o->R1, R2 = o->R2;
+        std::vector<cd> a((size_t)L), b((size_t)L);
+        const long double two_pi = 6.283185307179586476925286766559005768L;
+        for (int k1 = 0; k1 < R1; ++k1)
+            for (int n2 = 0; n2 < R2; ++n2) {
+                long double ang = -two_pi * (long double)(((long long)k1 * n2) % L) / (long double)L;
+                cd v = cd_make((double)cosl(ang), (double)sinl(ang));
+                a[(size_t)k1 * R2 + n2] = v;
+                b[(size_t)n2 * R1 + k1] = v;
+            }
+        cd *da = nullptr, *db = nullptr;
+        if (dev_malloc((void**)&da, L * sizeof(cd)) || dev_malloc((void**)&db, L * sizeof(cd)))
+            return fail(JUBIK_ERR_ALLOC, "device allocation failed for convolution twiddles");
+        if (h2d(da, a.data(), L * sizeof(cd), st) || h2d(db, b.data(), L * sizeof(cd), st) || stream_sync(st))
+            return fail(JUBIK_ERR_CUDA, "uploading convolution twiddles failed");
+        it = cache.emplace(std::make_pair(dev, L), std::make_pair(da, db)).first;
+    }
+    *tw_nk = it->second.first; *tw_kn = it->second.second;
+    return 0;
+}
+
 int jubik_convolve(const double* x, const double* y, int lead, int x_lead, int n0, int n1, double dvol, double* out,
                    void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
     if (!x || !y || !out) return fail(JUBIK_ERR_ARG, "null array pointer");
     if (device_count() < 1) return fail(JUBIK_ERR_CUDA, "no CUDA device: jubik_b200 has no CPU fallback");
     if (lead < 1 || n0 < 1 || n1 < 1 || (x_lead != lead && x_lead != 1)) return fail(JUBIK_ERR_ARG, "convolve: bad shape");
-    if ((size_t)n0 * n1 > (size_t)256 * 256)
-        return fail(JUBIK_ERR_UNSUPPORTED, "stand-alone convolve uses direct summation (<= 256x256); the FFT path is "
-                                           "jubik_plan_create + jubik_psf_apply");
-    JB_CK(jb_launch(k_convolve_direct, dim3(1184), dim3(128), 0, (jb_stream_t)stream_, x, y, lead, x_lead, n0, n1, dvol, out));
+    const JbFftOps *orow = find_ops(n1), *ocol = find_ops(n0);
+    const bool small = (size_t)n0 * n1 < (size_t)32 * 32;
+    if (small || !orow || !ocol) {
+        if ((size_t)n0 * n1 > (size_t)256 * 256)
+            return fail(JUBIK_ERR_UNSUPPORTED, "stand-alone convolve: " + std::to_string(n0) + " x " + std::to_string(n1) +
+                        " has a side that is not a compiled transform length (jubik_fft_length_supported) and is too large "
+                        "for the direct sum (<= 256 x 256)");
+        JB_CK(jb_launch(k_convolve_direct, dim3(1184), dim3(128), 0, st, x, y, lead, x_lead, n0, n1, dvol, out));
+        return JUBIK_OK;
+    }
+    // FFT path: rows r2c of both operands, column pass (FFT(y) kept in a scratch slice, FFT(x) * FFT(y), inverse), rows c2r
+    const cd *twr_nk, *twr_kn, *twc_nk, *twc_kn;
+    if (int rc = conv_twiddles(n1, orow, &twr_nk, &twr_kn, st)) return rc;
+    if (int rc = conv_twiddles(n0, ocol, &twc_nk, &twc_kn, st)) return rc;
+    const int PH = n1 / 2 + 1, nstrips = jb_cdiv(PH, ocol->CB);
+    const size_t bx = (size_t)x_lead * n0 * PH, by = (size_t)lead * n0 * PH, bs = (size_t)lead * nstrips * n0 * ocol->CB;
+    cd* ws = nullptr;
+#ifndef JB_EMU
+    JB_CK(cudaMallocAsync((void**)&ws, (bx + by + bs) * sizeof(cd), st));
+#else
+    if (dev_malloc((void**)&ws, (bx + by + bs) * sizeof(cd))) return fail(JUBIK_ERR_ALLOC, "convolve workspace");
+#endif
+    cd *xs = ws, *ys = ws + bx, *sc = ys + by;
+    cudaError_t e = orow->conv_rows_r2c(x, xs, twr_nk, (long)x_lead * n0, st);
+    if (e == cudaSuccess) e = orow->conv_rows_r2c(y, ys, twr_nk, (long)lead * n0, st);
+    if (e == cudaSuccess) e = ocol->conv_cols(xs, ys, sc, twc_nk, PH, lead, x_lead, st);
+    if (e == cudaSuccess) e = orow->conv_rows_c2r(ys, out, twr_kn, (long)lead * n0, dvol / ((double)n0 * (double)n1), st);
+#ifndef JB_EMU
+    cudaFreeAsync(ws, st);
+#else
+    dev_free(ws);
+#endif
+    if (e != cudaSuccess) return fail(JUBIK_ERR_CUDA, "convolve kernels -> " + cuda_msg(e));
     return JUBIK_OK;
 }
 

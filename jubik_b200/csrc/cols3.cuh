@@ -249,7 +249,13 @@ k_cols3_pipe(const
     constexpr int JB_C3_THREADS = C3::THREADS;
     constexpr bool SWEEP = false, KD = false;   // round-1 experiments (column-chain accumulation, K^ straight from L2): see DESIGN.md
     JB_SMEM(unsigned char, smraw);
-    cd* tile0 = reinterpret_cast<cd*>(smraw);
+    // The TMA destination (tile row in_p0 + chunk start) must be 128-byte aligned.  Chunk starts are even, in_p0 is the
+    // margin in the forward direction (0 in the adjoint): with CB*16 = 64-byte rows an ODD margin (e.g. ceil(0.062*2048)
+    // = 127) would put every box on a 64-byte boundary, so the whole tile region is shifted by the missing rows
+    // (compute-sanitizer memcheck, r2c: "misaligned shared address" at m = 17).
+    constexpr int ROWS_PER_128 = (128 / (CB * (int)sizeof(cd))) > 0 ? (128 / (CB * (int)sizeof(cd))) : 1;
+    const int tshift = ADJ ? 0 : (ROWS_PER_128 - g.m % ROWS_PER_128) % ROWS_PER_128;
+    cd* tile0 = reinterpret_cast<cd*>(smraw) + tshift * CB;
     cd* kh0 = tile0 + 2 * TILE;
     cd* tw1 = kh0 + (KD ? 0 : 2 * TILE);
     cd* tw2 = tw1 + L;

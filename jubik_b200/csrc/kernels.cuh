@@ -552,7 +552,76 @@ JB_GLOBAL_S void k_prep_expo(const double* __restrict__ expo, const double* __re
     }
 }
 
+// Content fingerprint of a kernel array (jubik_plan_ensure_kernel: "did the caller pass a different PSF?"): two 64-bit
+// wrap-around sums over the bit patterns, the second weighted by the odd number 2*index+1, one pair per CTA in out[2*block]
+// (the host adds the pairs; integer sums do not depend on the order).
+JB_GLOBAL_S void k_fingerprint(const double* __restrict__ a, size_t total, unsigned long long* __restrict__ out) {
+    JB_SMEM(unsigned long long, red);
+    unsigned long long h1 = 0, h2 = 0;
+    const unsigned long long* bits = reinterpret_cast<const unsigned long long*>(a);
+    for (size_t i = (size_t)blockIdx.x * jb_nthr() + jb_tid(); i < total; i += (size_t)gridDim.x * jb_nthr()) {
+        const unsigned long long v = bits[i];
+        h1 += v;
+        h2 += v * (2ull * (unsigned long long)i + 1ull);
+    }
+    const int t = jb_tid(), nt = jb_nthr();
+    red[t] = h1; red[nt + t] = h2;
+    JB_SYNC();
+    for (int sft = nt / 2; sft > 0; sft >>= 1) {
+        if (t < sft) { red[t] += red[t + sft]; red[nt + t] += red[nt + t + sft]; }
+        JB_SYNC();
+    }
+    if (t == 0) { out[2 * blockIdx.x] = red[0]; out[2 * blockIdx.x + 1] = red[nt]; }
+}
+
 JB_GLOBAL_S void k_i64_to_f64(const long long* __restrict__ in, size_t total, double* __restrict__ out) {
     for (size_t i = (size_t)blockIdx.x * jb_nthr() + jb_tid(); i < total; i += (size_t)gridDim.x * jb_nthr())
         out[i] = (double)in[i];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Stand-alone circular FFT convolution (jubik/convolve.py:148-176: dvol * Re ifftn(fftn(x) * fftn(y)) over the last two
+// axes) for arrays whose side lengths are compiled transform lengths: rows r2c (both operands) -> column pass (forward
+// column FFT of y into a scratch slice in register order, forward column FFT of x, product, inverse column FFT) -> rows
+// c2r with dvol / (n0*n1) folded in.  Row kernels are instantiated for the row length n1, the column kernel for n0.
+template <class FP>
+JB_GLOBAL void k_conv_rows_r2c(const double* __restrict__ in, cd* __restrict__ out, const cd* __restrict__ tw_nk,
+                               long nrows, int PH, int rpc) {
+    JB_SMEM(cd, sm);
+    const long r0 = (long)blockIdx.x * rpc;
+    const int B = (int)(nrows - r0 < rpc ? nrows - r0 : rpc);
+    auto ld = [&](int b, int p) -> double { return jb_ldg(in + (size_t)(r0 + b) * FP::L + p); };
+    auto st = [&](int b, int k, cd X) { out[(size_t)(r0 + b) * PH + k] = X; };
+    rows_r2c<FP>(sm, tw_nk, B, ld, st);
+}
+template <class FP>
+JB_GLOBAL void k_conv_rows_c2r(const cd* __restrict__ in, double* __restrict__ out, const cd* __restrict__ tw_kn,
+                               long nrows, int PH, int rpc, double scale) {
+    JB_SMEM(cd, sm);
+    const long r0 = (long)blockIdx.x * rpc;
+    const int B = (int)(nrows - r0 < rpc ? nrows - r0 : rpc);
+    auto ld = [&](int b, int k) -> cd { return in[(size_t)(r0 + b) * PH + k]; };
+    auto st = [&](int b, int p, double v) { out[(size_t)(r0 + b) * FP::L + p] = scale * v; };
+    rows_c2r<FP>(sm, tw_kn, B, ld, st);
+}
+// grid (nstrips, lead); xs (x_lead, L, PH), ys (lead, L, PH) row spectra; the result overwrites the strip of ys.
+// scratch: (lead, nstrips, L*CB) column spectra of y in the register order of cols_cfft.
+template <class FP, int CB>
+JB_GLOBAL void k_conv_cols(const cd* __restrict__ xs, cd* __restrict__ ys, cd* __restrict__ scratch,
+                           const cd* __restrict__ tw_nk, int PH, int x_lead) {
+    JB_SMEM(cd, sm);
+    constexpr int L = FP::L, R1 = FP::R1;
+    const int strip = blockIdx.x, l = blockIdx.y, col0 = strip * CB;
+    const cd* xb = xs + (size_t)(x_lead == 1 ? 0 : l) * L * PH;
+    cd* yb = ys + (size_t)l * L * PH;
+    cd* sc = scratch + ((size_t)l * gridDim.x + strip) * ((size_t)L * CB);
+    auto ld_y = [&](int p, int b) -> cd { int c = col0 + b; return c < PH ? yb[(size_t)p * PH + c] : cd_make(0.0, 0.0); };
+    auto ld_x = [&](int p, int b) -> cd { int c = col0 + b; return c < PH ? xb[(size_t)p * PH + c] : cd_make(0.0, 0.0); };
+    auto keep = [&](int k1, int k2, int b, cd Y) -> cd { sc[(size_t)(k2 * R1 + k1) * CB + b] = Y; return Y; };
+    auto none = [&](int, int, cd) {};
+    cols_cfft<FP, CB, false>(sm, tw_nk, ld_y, keep, none);
+    JB_SYNC();   // (each thread reads back exactly the slots it wrote; the barrier separates the two uses of sm)
+    auto mul = [&](int k1, int k2, int b, cd X) -> cd { return cd_mul(X, sc[(size_t)(k2 * R1 + k1) * CB + b]); };
+    auto st = [&](int p, int b, cd v) { int c = col0 + b; if (c < PH) yb[(size_t)p * PH + c] = v; };
+    cols_cfft<FP, CB, true>(sm, tw_nk, ld_x, mul, st);
 }

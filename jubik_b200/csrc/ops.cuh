@@ -39,6 +39,10 @@ struct JbFftOps {
     cudaError_t (*rows5_adj)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw1, const cd* tw2,
                              const int* gtab, int gq, double* grad, const double* logsky, int planes_se, int n_sm,
                              jb_stream_t);
+    // stand-alone FFT convolution (jubik_convolve): rows of length L, columns of length L
+    cudaError_t (*conv_rows_r2c)(const double* in, cd* out, const cd* tw_nk, long nrows, jb_stream_t);
+    cudaError_t (*conv_rows_c2r)(const cd* in, double* out, const cd* tw_kn, long nrows, double scale, jb_stream_t);
+    cudaError_t (*conv_cols)(const cd* xs, cd* ys, cd* scratch, const cd* tw_nk, int PH, int lead, int x_lead, jb_stream_t);
     cudaError_t (*prep_rows)(const JbGeom&, const JbKsrc&, const cd* tw_nk, cd* scratch, int rpc, int threads,
                              jb_stream_t);
     // layout 0: K^ in the two-pass register order (tw = tw_nk); layout 2: three-stage order (twa/twb = tw1/tw2)
@@ -55,7 +59,7 @@ struct JbOpsImpl {
                                  const cd* twa, const cd* twb, const double* wgt, int planes, int ctas, jb_stream_t st) {
         if constexpr (PIPE == 2) {
             size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd) + 32 +
-                          2 * sizeof(JbColInfo) + (size_t)g.w * sizeof(double) + 32;
+                          2 * sizeof(JbColInfo) + (size_t)g.w * sizeof(double) + 32 + 128;   // + the tile shift for odd margins
             const dim3 grid(ctas * Cols3<F3, CB>::CPS), block(Cols3<F3, CB>::THREADS);
             if (adj) return jb_launch(k_cols3_pipe<F3, CB, true>, grid, block, smem, st, src, g, out, khat, twa, twb, wgt,
                                       planes);
@@ -245,6 +249,29 @@ struct JbOpsImpl {
             return (cudaError_t)1;
         }
     }
+    static int conv_row_threads(int rpc) {
+        int items = rpc * (FP::R2 > 1 ? (FP::R2 > FP::H1 ? FP::R2 : FP::H1) : 1);
+        int thr = ((items + 31) / 32) * 32;
+        return thr < 32 ? 32 : (thr > 256 ? 256 : thr);
+    }
+    static cudaError_t conv_rows_r2c(const double* in, cd* out, const cd* tw_nk, long nrows, jb_stream_t st) {
+        const int rpc = 8;
+        return jb_launch(k_conv_rows_r2c<FP>, dim3((unsigned)((nrows + rpc - 1) / rpc)), dim3(conv_row_threads(rpc)),
+                         jb_al16((size_t)rpc * FP::LS * sizeof(cd)) + 16, st, in, out, tw_nk, nrows, FP::L / 2 + 1, rpc);
+    }
+    static cudaError_t conv_rows_c2r(const cd* in, double* out, const cd* tw_kn, long nrows, double scale, jb_stream_t st) {
+        const int rpc = 8;
+        return jb_launch(k_conv_rows_c2r<FP>, dim3((unsigned)((nrows + rpc - 1) / rpc)), dim3(conv_row_threads(rpc)),
+                         jb_al16((size_t)rpc * FP::LS * sizeof(cd)) + 16, st, in, out, tw_kn, nrows, FP::L / 2 + 1, rpc, scale);
+    }
+    static cudaError_t conv_cols(const cd* xs, cd* ys, cd* scratch, const cd* tw_nk, int PH, int lead, int x_lead,
+                                 jb_stream_t st) {
+        int ct = ((CB * (FP::R2 > 1 ? (FP::R1 > FP::R2 ? FP::R1 : FP::R2) : 1) + 31) / 32) * 32;
+        if (ct > 128) ct = 128;
+        size_t smem = (FP::R2 == 1) ? 16 : (size_t)FP::L * CB * sizeof(cd);
+        return jb_launch(k_conv_cols<FP, CB>, dim3((unsigned)jb_cdiv(PH, CB), (unsigned)lead), dim3(ct), smem, st, xs, ys, scratch,
+                         tw_nk, PH, x_lead);
+    }
     static cudaError_t prep_rows(const JbGeom& g, const JbKsrc& ks, const cd* tw_nk, cd* scratch, int rpc,
                                  int threads, jb_stream_t st) {
         size_t smem = jb_al16((size_t)rpc * FP::LS * sizeof(cd)) + 16;
@@ -266,7 +293,8 @@ struct JbOpsImpl {
     static const JbFftOps* table() {
         static const JbFftOps t = {FP::L, FP::R1, FP::R2, CB, FP::LS, (FP::R2 > 1 && PIPE == 2) ? 2 : 0, F3::R1, F3::R2, F3::R3,
                                    rows_fwd, rows_adj_in, cols, cols_pipe, rows_out, rows_adj_out, rows_generic_smem,
-                                   rows5_smem, rows5_gather, rows5_fwd, rows5_adj, prep_rows, prep_cols};
+                                   rows5_smem, rows5_gather, rows5_fwd, rows5_adj, conv_rows_r2c, conv_rows_c2r, conv_cols,
+                                   prep_rows, prep_cols};
         return &t;
     }
 };

@@ -126,7 +126,14 @@ class ResponsePlan:
         self.info = self.raw.info
         self.cropped = bool(cropped)
         self.n_patches, self.margin = int(n_patches), int(margin)
+        self._remember_kernel(kernel)                        # identity short-cut of ensure_kernel
         del keep
+
+    def _remember_kernel(self, kernel):
+        """Weak reference (the plan must not keep tens of GB of PSF kernels alive) + version counter of the tensor the
+        resident spectra were built from."""
+        import weakref
+        self._k_obj, self._k_ver = weakref.ref(kernel), kernel._version
 
     def _prep_data(self, data):
         import torch
@@ -228,10 +235,36 @@ class ResponsePlan:
         exp = (self.T, self.n_patches ** 2, self.E) + ((2 * dx, 2 * dx) if cropped else (self.N, self.N))
         if tuple(kernel.shape) != exp:
             raise ValueError("kernel should have shape %s" % (exp,))
+        self._k_obj = None
         self._call("jubik_plan_set_kernel", C.c_void_p(kernel.data_ptr()), _lib.KERNEL_CROPPED if cropped else _lib.KERNEL_FULL)
+        self._remember_kernel(kernel)
         info = PlanInfo()
         check(self.raw.lib, self.raw.lib.jubik_plan_get_info(self.raw.handle, C.byref(info)))
         self.info = self.raw.info = {k: getattr(info, k) for k, _ in PlanInfo._fields_}
+
+    def ensure_kernel(self, kernel, cropped=None):
+        """set_kernel only if `kernel` differs in CONTENT from the kernels the resident spectra were built from
+        (jubik_plan_ensure_kernel: device-side 128-bit fingerprint).  The tensor object last seen (unmodified since) is
+        recognised without touching the device.  Returns True if the spectra were rebuilt."""
+        if self._k_obj is not None and self._k_obj() is kernel and kernel._version == self._k_ver:
+            return False
+        cropped = (tuple(kernel.shape[-2:]) != (self.N, self.N)) if cropped is None else bool(cropped)
+        self._on_device(kernel, "kernel")
+        src, kernel = kernel, kernel.contiguous()
+        dx = int(self.N / self.n_patches)
+        exp = (self.T, self.n_patches ** 2, self.E) + ((2 * dx, 2 * dx) if cropped else (self.N, self.N))
+        if tuple(kernel.shape) != exp:
+            raise ValueError("kernel should have shape %s" % (exp,))
+        flag = C.c_int(0)
+        self._k_obj = None
+        self._call("jubik_plan_ensure_kernel", C.c_void_p(kernel.data_ptr()),
+                   _lib.KERNEL_CROPPED if cropped else _lib.KERNEL_FULL, C.byref(flag))
+        self._remember_kernel(src)
+        if flag.value:
+            info = PlanInfo()
+            check(self.raw.lib, self.raw.lib.jubik_plan_get_info(self.raw.handle, C.byref(info)))
+            self.info = self.raw.info = {k: getattr(info, k) for k, _ in PlanInfo._fields_}
+        return bool(flag.value)
 
     def energy_and_grad(self, x, need_grad=True, out_energy=None, out_grad=None):
         """Poisson energy sum(lambda) - d.log(lambda) per sample and its gradient w.r.t. the sky.

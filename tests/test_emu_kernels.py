@@ -135,3 +135,32 @@ def test_emulated_sharded_entry_point_single_rank():
             assert rel(gl, go) < TOL
     flat, _ = p2.energy_and_grad_sharded(x, _lib.SHARD_MODULES)
     assert rel(flat[:S * npx].reshape(S, E, N, N), go) < TOL and np.abs((flat[S * npx:] - eo) / eo).max() < TOL
+
+
+def test_emulated_standalone_fft_convolve_and_kernel_fingerprint():
+    """jubik_convolve on the FFT kernels (rectangular, broadcasting branch) and jubik_plan_ensure_kernel (fingerprint hit
+    / miss) through the emulation build -- index logic only, no GPU."""
+    import ctypes as C
+    from jubik_b200 import _lib
+    from tests.emu.emu_plan import emu_lib, _p
+    lib = emu_lib()
+    rng = np.random.default_rng(3)
+    for lead, x_lead, n0, n1 in ((2, 2, 96, 160), (3, 1, 160, 96), (1, 1, 24, 28)):
+        x, y = rng.normal(size=(x_lead, n0, n1)), rng.normal(size=(lead, n0, n1))
+        out = np.empty_like(y)
+        _lib.check(lib, lib.jubik_convolve(_p(x), _p(y), lead, x_lead, n0, n1, 0.25, _p(out), None))
+        ref = 0.25 * np.fft.ifft2(np.fft.fft2(x) * np.fft.fft2(y)).real
+        assert rel(out, ref) < 1e-12
+    N, n, m = 64, 4, 6
+    k1 = synth.psf_cropped(1, n, 1, N // n, half_support=m)
+    k2 = synth.psf_cropped(1, n, 1, N // n, half_support=m, seed=8)
+    p = EmuPlan(k1, N, n, m, cropped=True, fft_length=160)
+    flag = C.c_int(-1)
+    k1c = k1.copy()                     # equal content at another address (kept alive across the call)
+    p.raw.call("jubik_plan_ensure_kernel", _p(k1c), _lib.KERNEL_CROPPED, C.byref(flag), None)
+    assert flag.value == 0
+    p.raw.call("jubik_plan_ensure_kernel", _p(k2), _lib.KERNEL_CROPPED, C.byref(flag), None)
+    assert flag.value == 1
+    x = synth.sky(1, 1, N)
+    dom = orc.Domain((1, N, N), synth.DIST)
+    assert rel(p.psf(x)[0, 0], orc.linpatch_convolve(x[0], dom, k2[0], n, m, cropped=True)) < TOL
