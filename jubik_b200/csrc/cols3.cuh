@@ -55,7 +55,12 @@ struct Cols3 {
     static constexpr bool WL = false;
 #endif
     static constexpr int THREADS = WL ? (jb_c3_max3(I1, 32 * R1, 0) + 31) / 32 * 32 : (jb_c3_max3(I1, I2, I3) + 31) / 32 * 32;
-    static constexpr int CPS = THREADS <= 256 ? 2 : 1;   // CTAs per SM the pipeline is sized for
+    // CTAs per SM the pipeline is sized for: by threads (<= 512 resident) and by the ring's shared memory (2 tiles + 2 K^
+    // slices + twiddles + slack)
+    static constexpr int SMEM_EST = 4 * L * CB * 16 + (L + M) * 16 + 4096;
+    static constexpr int CPS_T = THREADS <= 128 ? 4 : (THREADS <= 256 ? 2 : 1);
+    static constexpr int CPS_S = (227 * 1024) / SMEM_EST < 1 ? 1 : (227 * 1024) / SMEM_EST;
+    static constexpr int CPS = CPS_T < CPS_S ? CPS_T : CPS_S;
     static constexpr int CPS_KD = THREADS <= 256 ? 3 : 1; // ... when K^ is read straight from L2 (no staging ring)
     static_assert(THREADS <= 1024, "one item per thread and stage");
     // SWZ: with 4-column tiles two stage-3 items of one quarter-warp (rows 8c + n3 and 8c + 8 + n3) hit the same

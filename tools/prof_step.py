@@ -1,21 +1,28 @@
-"""Tiny driver for ncu: build the C2 plan (BASELINE.json configs[1]) and run a few fused fwd+VJP steps."""
+"""Tiny driver for ncu: build a plan of one bench workload (optionally with fewer modules, so that a `--set full`
+capture with its ~40 replays per launch stays short) and run a few fused fwd+VJP steps.
+
+    python tools/prof_step.py [C5|C2|...] [steps] [samples] [modules]
+"""
 import os
 import sys
 
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 import torch  # noqa: E402
 import jubik_b200 as jb  # noqa: E402
-from bench import WORKLOADS, make_inputs  # noqa: E402
+from bench import WORKLOADS, sample_skies  # noqa: E402
+from tests import synth  # noqa: E402
 
-wl = sys.argv[1] if len(sys.argv) > 1 else "C2"
+wl = sys.argv[1] if len(sys.argv) > 1 else "C5"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-S = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-N, n, m, T, E, _ = WORKLOADS[wl]
-kern, expo, x = make_inputs(wl, S)
+N, n, m, T, E, S_job, chunk, _ = WORKLOADS[wl]
+S = int(sys.argv[3]) if len(sys.argv) > 3 else chunk
+T = int(sys.argv[4]) if len(sys.argv) > 4 else T
+kern = synth.psf_cropped(T, n, E, N // n, half_support=m)
+expo = synth.exposure(T, E, N)
 plan = jb.ResponsePlan(torch.as_tensor(kern).cuda(), N, n, m, exposure=torch.as_tensor(expo).cuda(),
-                       exposure_cut=500.0, pixel_area=16.0, cropped=True, max_samples=S)
-xd = torch.as_tensor(x).cuda()
-lam = plan.response(torch.as_tensor(make_inputs(wl, 1, seed_shift=5)[2]).cuda())[0]
+                       exposure_cut=500.0, pixel_area=16.0, cropped=True, max_samples=S, metric=False)
+xd = torch.as_tensor(sample_skies(wl, 0, S)).cuda()
+lam = plan.response(torch.as_tensor(synth.sky(1, E, N, seed=5)).cuda())[0]
 plan.set_data(torch.poisson(lam.clamp(min=0.0)))
 for _ in range(steps):
     e, g = plan.energy_and_grad(xd)
