@@ -162,6 +162,24 @@ int jubik_slice_patches(const double* x, int lead, int h, int w, int n_patches, 
 int jubik_slice_patches_T(const double* patches, int lead, int h, int w, int n_patches, int dr, double* out, void* stream);
 int jubik_convolve(const double* x, const double* y, int lead, int x_lead, int n0, int n1, double dvol, double* out,
                    void* stream);
+/* Device PSF builder: jubik/instruments/erosita/erosita_psf_utils.py:198-264 psf_interpolator with
+ * :94-171 get_psf, for ONE telescope module.  The PSF tables of the off-axis radii bracketing every patch centre are
+ * rotated to the patch's position angle and bilinearly resampled (map_coordinates order=1, mode='nearest') onto the
+ * sky grid.  out: DEVICE (n*n, E, side, side) -- JUBIK_KERNEL_FULL: side = N, the reference's origin-centred layout;
+ * JUBIK_KERNEL_CROPPED: side = 2*int(N/n), the centred crop that convolve.py:107-111 extracts, i.e. exactly what
+ * jubik_plan_create consumes, so the (T, n*n, E, N, N) array (17-70 GB at the BASELINE configurations) never exists.
+ * d0, d1 = domain.distances[-2:].  Fails like the reference (ValueError -> JUBIK_ERR_ARG) when N is odd or not divisible
+ * by n_patches.  Synchronises. */
+typedef struct jubik_psf_tables {
+    int32_t n_energy, n_rad, px, py;
+    const double* psfs;            /* DEVICE (n_energy, n_rad, px, py): 'psfs' of every energy's psf_infos, any radius order */
+    const double* rs;              /* HOST   (n_energy, n_rad): 'rs', the off-axis radius of each table                      */
+    const double* center_ids;      /* HOST   (n_energy, n_rad, 2): 'patch_center_ids', index of the PSF centre in each table */
+    double delta0, delta1;         /* 'patch_deltas': bin size of the tables                                                */
+    double pointing0, pointing1;   /* 'pointing_center' of this module                                                      */
+} jubik_psf_tables;
+int jubik_psf_interpolate(const jubik_psf_tables* tables, int N, int n_patches, double d0, double d1, int kernel_layout,
+                          double* out, void* stream);
 /* Same as jubik_poisson_energy_and_grad with HOST buffers (pinned or pageable): H2D of x, the kernels,
  * D2H of energy and grad, all on `stream`, then a stream synchronise.  This is the end-to-end call. */
 int jubik_poisson_energy_and_grad_host(jubik_plan* plan, const double* x_host, int n_samples,

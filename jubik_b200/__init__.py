@@ -7,7 +7,8 @@ Importing the package does not need a GPU; every compute entry point does and ra
 from ._lib import JubikError, load as load_library  # noqa: F401
 from .api import (Domain, FullModel, PoissonLikelihood, Vector, build_exposure_function,  # noqa: F401
                   build_mask_adjoint, build_psf_operator, build_readout_function, build_response, calculate_nwr,
-                  convolve, create_mock_data, integrate, linpatch_convolve, slice_patches, slice_patches_T)
+                  convolve, create_mock_data, integrate, linpatch_convolve, psf_interpolator, slice_patches,
+                  slice_patches_T)
 from .plan import Communicator, ResponsePlan  # noqa: F401
 from ._lib import SHARD_MODULES, SHARD_SAMPLES  # noqa: F401
 from . import sharding  # noqa: F401

@@ -26,7 +26,7 @@ EXPORTS = [
     "jubik_response_apply_T", "jubik_poisson_energy_and_grad", "jubik_poisson_metric_apply",
     "jubik_poisson_energy_and_grad_host", "jubik_poisson_profile", "jubik_measure_fp64_tflops",
     "jubik_poisson_left_sqrt_metric", "jubik_poisson_energy_and_grad_logsky",
-    "jubik_slice_patches", "jubik_slice_patches_T", "jubik_convolve",
+    "jubik_slice_patches", "jubik_slice_patches_T", "jubik_convolve", "jubik_psf_interpolate",
     "jubik_comm_unique_id", "jubik_comm_create", "jubik_comm_adopt", "jubik_comm_destroy", "jubik_comm_rank",
     "jubik_comm_size", "jubik_sharded_flat_size", "jubik_poisson_energy_and_grad_sharded",
     "jubik_poisson_energy_and_grad_sharded_host",
@@ -43,6 +43,12 @@ class PlanDesc(C.Structure):
         ("d0", C.c_double), ("d1", C.c_double), ("exposure_cut", C.c_double), ("pixel_area", C.c_double),
         ("kernel", C.c_void_p), ("exposure", C.c_void_p), ("eff_area", C.c_void_p), ("data", C.c_void_p),
     ]
+
+
+class PsfTables(C.Structure):
+    _fields_ = [("n_energy", C.c_int32), ("n_rad", C.c_int32), ("px", C.c_int32), ("py", C.c_int32),
+                ("psfs", C.c_void_p), ("rs", C.c_void_p), ("center_ids", C.c_void_p),
+                ("delta0", C.c_double), ("delta1", C.c_double), ("pointing0", C.c_double), ("pointing1", C.c_double)]
 
 
 class PlanInfo(C.Structure):
@@ -87,6 +93,7 @@ def bind(lib):
     lib.jubik_slice_patches.argtypes = [vp, i, i, i, i, i, vp, vp]
     lib.jubik_slice_patches_T.argtypes = [vp, i, i, i, i, i, vp, vp]
     lib.jubik_convolve.argtypes = [vp, vp, i, i, i, i, d, vp, vp]
+    lib.jubik_psf_interpolate.argtypes = [C.POINTER(PsfTables), i, i, d, d, i, vp, vp]
     lib.jubik_comm_unique_id.argtypes = [vp]
     lib.jubik_comm_create.argtypes = [C.POINTER(vp), vp, i, i]
     lib.jubik_comm_adopt.argtypes = [C.POINTER(vp), vp]

@@ -13,6 +13,7 @@ the reference's own:
     build_psf_operator          instruments/erosita/erosita_response.py:206-212 (psf_op), chandra :127-130
     build_response              erosita_response.py:307-358 / chandra_response.py:127-149 -> response_dict
                                 (dynamic_kernel=True: the eROSITA call form R(x, k) with 'kernel' in the dict)
+    psf_interpolator            instruments/erosita/erosita_psf_utils.py:198-264 (PSF tables -> patch kernels, on the device)
     build_mask_adjoint          jax.linear_transpose(response_dict['mask'], ...)  (data.py:156-160) -> 'mask_adj'
     create_mock_data            data.py:138-146 (R(sky[, kernel]) + Poisson draw per key)
     calculate_nwr               diagnostics.py:62-125 (batched R over the samples)
@@ -274,6 +275,57 @@ def build_psf_operator(kernel, domain, n_patches_per_axis, margin, max_samples=1
     plan = ResponsePlan(kernel, domain.shape[-1], n_patches_per_axis, margin, max_samples=max_samples,
                         cropped=cropped, distances=tuple(domain.distances[-2:]))
     return plan.psf, plan
+
+
+def psf_interpolator(domain, npatch, psf_infos, cropped=False, out=None):
+    """Drop-in for jubik's psf_interpolator (instruments/erosita/erosita_psf_utils.py:198-264) on the device: the PSF
+    tables of one telescope module (`psf_infos`: one dict per energy with 'psfs', 'rs', 'patch_center_ids',
+    'patch_deltas', 'pointing_center' -- eROSITA_PSF._get_psf_infos, erosita_psf.py:211-220) resampled onto the sky
+    grid for every patch centre.  Returns a float64 CUDA tensor (npatch**2, E, N, N) in the reference's origin-centred
+    layout, or with cropped=True the (npatch**2, E, 2dx, 2dx) centred crop that a ResponsePlan(..., cropped=True) consumes
+    -- the full-size array (tens of GB for 7 modules at 1024^2 / 2048^2) is then never materialised.  `out` may be a
+    preallocated slice, e.g. kernel[t] of a (T, n*n, E, 2dx, 2dx) tensor."""
+    import numpy as np
+    from . import _lib
+    torch = _torch()
+    if not isinstance(domain, Domain):
+        raise ValueError("domain has to be an instance of jubik.Domain")
+    lib = _lib.load()
+    N0, N1 = int(domain.shape[-2]), int(domain.shape[-1])
+    for ss in (N0, N1):                                   # erosita_psf_utils.py:209-213
+        if ss % npatch != 0 or ss % 2 != 0:
+            raise ValueError
+    if N0 != N1:
+        raise NotImplementedError("psf_interpolator: square skies only")
+    E = len(psf_infos)
+    tabs = [np.asarray(info['psfs'], dtype=np.float64) for info in psf_infos]
+    if len({t.shape for t in tabs}) != 1:
+        raise ValueError("psf_interpolator: the tables of all energies must share one shape")
+    nrad, px, py = tabs[0].shape
+    rs = np.ascontiguousarray([np.asarray(info['rs'], dtype=np.float64) for info in psf_infos])
+    cid = np.ascontiguousarray([np.asarray(info['patch_center_ids'], dtype=np.float64) for info in psf_infos])
+    if rs.shape != (E, nrad) or cid.shape != (E, nrad, 2):
+        raise ValueError
+    deltas = {tuple(float(v) for v in info['patch_deltas']) for info in psf_infos}
+    points = {tuple(float(v) for v in info['pointing_center']) for info in psf_infos}
+    if len(deltas) != 1 or len(points) != 1:
+        raise ValueError("psf_interpolator: one module at a time (a single bin size and pointing centre)")
+    (dl0, dl1), (p0, p1) = deltas.pop(), points.pop()
+    dev_tabs = torch.as_tensor(np.ascontiguousarray(np.stack(tabs))).to("cuda" if out is None else out.device)
+    dx = N0 // npatch
+    side = 2 * dx if cropped else N0
+    shape = (npatch * npatch, E, side, side)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float64, device=dev_tabs.device)
+    elif tuple(out.shape) != shape or out.dtype != torch.float64 or not out.is_cuda or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float64 CUDA tensor of shape %s" % (shape,))
+    t = _lib.PsfTables(E, nrad, px, py, dev_tabs.data_ptr(), rs.ctypes.data, cid.ctypes.data, dl0, dl1, p0, p1)
+    with torch.cuda.device(out.device):
+        _lib.check(lib, lib.jubik_psf_interpolate(C.byref(t), N0, int(npatch), float(domain.distances[-2]),
+                                                  float(domain.distances[-1]),
+                                                  _lib.KERNEL_CROPPED if cropped else _lib.KERNEL_FULL,
+                                                  C.c_void_p(out.data_ptr()), _stream_ptr(torch)))
+    return out
 
 
 def build_mask_adjoint(mask, keys):

@@ -1089,6 +1089,83 @@ int jubik_convolve(const double* x, const double* y, int lead, int x_lead, int n
     return JUBIK_OK;
 }
 
+int jubik_psf_interpolate(const jubik_psf_tables* t, int N, int n_patches, double d0, double d1, int kernel_layout,
+                          double* out, void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (!t || !t->psfs || !t->rs || !t->center_ids || !out) return fail(JUBIK_ERR_ARG, "null pointer");
+    if (device_count() < 1) return fail(JUBIK_ERR_CUDA, "no CUDA device: jubik_b200 has no CPU fallback");
+    const int E = t->n_energy, nrad = t->n_rad, n = n_patches;
+    if (E < 1 || nrad < 1 || t->px < 1 || t->py < 1 || n < 1) return fail(JUBIK_ERR_ARG, "psf tables: bad shape");
+    // erosita_psf_utils.py:209-213: the patch grid must divide the (even) image
+    if (N < 2 || N % n != 0 || N % 2 != 0) return fail(JUBIK_ERR_ARG, "psf_interpolator: the image size must be even and divisible by npatch");
+    const int nn2 = n * n, ps = N / n;
+    std::vector<double> wts((size_t)E * nn2 * nrad, 0.0), cid((size_t)E * nrad * 2), rot((size_t)nn2 * 2);
+    std::vector<int> perm((size_t)E * nrad);
+    // patch centres: k = a*n + b has ra = cen1[n-1-a], dec = cen0[b] (meshgrid 'xy' + flipped ra list, :236-246)
+    std::vector<double> ra(nn2), dec(nn2);
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+            ra[a * n + b] = ((double)((n - 1 - a) * ps) + (double)ps / 2.0) * d1;
+            dec[a * n + b] = ((double)(b * ps) + (double)ps / 2.0) * d0;
+        }
+    const double half_pi = 1.57079632679489661923;
+    for (int k = 0; k < nn2; ++k) {
+        const double c0 = ra[k] - t->pointing0, c1 = dec[k] - t->pointing1;
+        const double phi = atan2(c1, c0) - half_pi;          // to_r_phi, :17-29
+        rot[2 * k] = cos(phi); rot[2 * k + 1] = sin(phi);
+    }
+    for (int e = 0; e < E; ++e) {
+        const double* rs_in = t->rs + (size_t)e * nrad;
+        std::vector<int> order(nrad);
+        for (int i = 0; i < nrad; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return rs_in[a] < rs_in[b]; });   // np.argsort
+        std::vector<double> rs(nrad);
+        for (int i = 0; i < nrad; ++i) {
+            rs[i] = rs_in[order[i]];
+            perm[(size_t)e * nrad + i] = order[i];
+            const double* c = t->center_ids + ((size_t)e * nrad + order[i]) * 2;
+            if (c[0] < 0 || c[1] < 0 || c[0] > t->px || c[1] > t->py) return fail(JUBIK_ERR_ARG, "psf tables: centre index outside the table");
+            cid[((size_t)e * nrad + i) * 2] = c[0]; cid[((size_t)e * nrad + i) * 2 + 1] = c[1];
+        }
+        for (int k = 0; k < nn2; ++k) {
+            const double c0 = ra[k] - t->pointing0, c1 = dec[k] - t->pointing1;
+            const double r = sqrt(c0 * c0 + c1 * c1);
+            double* w = wts.data() + ((size_t)e * nn2 + k) * nrad;      // get_interpolation_weights, :41-72 (overlaps kept)
+            if (r <= rs[0]) w[0] += 1.0;
+            if (r >= rs[nrad - 1]) w[nrad - 1] += 1.0;
+            for (int i = 0; i + 1 < nrad; ++i)
+                if (rs[i] < r && rs[i + 1] >= r) {
+                    const double wg = (r - rs[i]) / (rs[i + 1] - rs[i]);
+                    w[i] += 1.0 - wg; w[i + 1] += wg;
+                }
+        }
+    }
+    const size_t bw = wts.size() * sizeof(double), bc = cid.size() * sizeof(double), br = rot.size() * sizeof(double),
+                 bp = (perm.size() * sizeof(int) + 15) & ~(size_t)15;
+    unsigned char* ws = nullptr;
+    if (dev_malloc((void**)&ws, bw + bc + br + bp)) return fail(JUBIK_ERR_ALLOC, "psf_interpolator workspace");
+    JbPsfInterp q;
+    q.E = E; q.nrad = nrad; q.px = t->px; q.py = t->py; q.N = N; q.nn2 = nn2; q.dx = N / n;
+    q.cropped = kernel_layout == JUBIK_KERNEL_CROPPED; q.side = q.cropped ? 2 * q.dx : N;
+    q.d0 = d0; q.d1 = d1; q.delta0 = t->delta0; q.delta1 = t->delta1;
+    q.psfs = t->psfs;
+    q.wts = (const double*)ws; q.cid = (const double*)(ws + bw); q.rot = (const double*)(ws + bw + bc);
+    q.perm = (const int*)(ws + bw + bc + br);
+    int rc = JUBIK_OK;
+    if (h2d(ws, wts.data(), bw, st) || h2d(ws + bw, cid.data(), bc, st) || h2d(ws + bw + bc, rot.data(), br, st) ||
+        h2d(ws + bw + bc + br, perm.data(), perm.size() * sizeof(int), st))
+        rc = fail(JUBIK_ERR_CUDA, "uploading the interpolation tables failed");
+    if (!rc) {
+        const size_t npix = (size_t)q.side * q.side;
+        const unsigned gx = (unsigned)std::min<size_t>((npix + 255) / 256, 296);
+        cudaError_t e = jb_launch(k_psf_interp, dim3(gx, (unsigned)nn2, (unsigned)E), dim3(256), 0, st, q, out);
+        if (e != cudaSuccess) rc = fail(JUBIK_ERR_CUDA, "k_psf_interp -> " + cuda_msg(e));
+    }
+    if (stream_sync(st) && !rc) rc = fail(JUBIK_ERR_CUDA, "stream synchronise failed");   // the host tables die with this frame
+    dev_free(ws);
+    return rc;
+}
+
 int jubik_poisson_energy_and_grad_host(jubik_plan* p, const double* xh, int S, double* eh, double* gh, void* stream_) {
     jb_stream_t st = (jb_stream_t)stream_;
     if (int rc = check_call(p, xh, eh, S)) return rc;

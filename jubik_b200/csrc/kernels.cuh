@@ -625,3 +625,52 @@ JB_GLOBAL void k_conv_cols(const cd* __restrict__ xs, cd* __restrict__ ys, cd* _
     auto st = [&](int p, int b, cd v) { int c = col0 + b; if (c < PH) yb[(size_t)p * PH + c] = v; };
     cols_cfft<FP, CB, true>(sm, tw_nk, ld_x, mul, st);
 }
+
+// ------------------------------------------------------------------------------------------------------
+// Device PSF builder: erosita_psf_utils.py:198-264 psf_interpolator with :94-171 get_psf.  For patch k
+// and energy e the PSF tables of the bracketing off-axis radii (host-computed weights wts[e][k][q], radii ascending,
+// table index perm[e][q]) are rotated to the patch's position angle (rot[k] = (cos phi, sin phi)) and bilinearly
+// resampled (map_coordinates order=1, mode='nearest') at every kernel pixel.  Output (n*n, E, side, side): side == N is
+// the reference layout (origin-centred, i.e. rolled by N/2), side == 2dx the centred crop convolve.py:107-111 extracts --
+// the (T, n*n, E, N, N) array (17-70 GB at the BASELINE configurations) never has to exist.
+struct JbPsfInterp {
+    int E, nrad, px, py, N, nn2, side, cropped, dx;
+    double d0, d1, delta0, delta1;
+    const double* psfs;   // (E, nrad, px, py)
+    const double* wts;    // (E, nn2, nrad)
+    const double* cid;    // (E, nrad, 2) sorted like the weights
+    const int* perm;      // (E, nrad): table index of sorted radius q
+    const double* rot;    // (nn2, 2)
+};
+JB_GLOBAL_S void k_psf_interp(JbPsfInterp q, double* __restrict__ out) {
+    const int k = blockIdx.y, e = blockIdx.z;
+    const size_t npix = (size_t)q.side * q.side;
+    const double cs = q.rot[2 * k], sn = q.rot[2 * k + 1];
+    const double* wt = q.wts + ((size_t)e * q.nn2 + k) * q.nrad;
+    double* ob = out + ((size_t)k * q.E + e) * npix;
+    for (size_t idx = (size_t)blockIdx.x * jb_nthr() + jb_tid(); idx < npix; idx += (size_t)gridDim.x * jb_nthr()) {
+        const int u = (int)(idx / q.side), v = (int)(idx - (size_t)u * q.side);
+        int dr, dc;
+        if (q.cropped) { dr = u - q.dx; dc = v - q.dx; }
+        else { dr = u < q.N / 2 ? u : u - q.N; dc = v < q.N / 2 ? v : v - q.N; }
+        const double d_dec = (double)dr * q.d0, d_ra = -1.0 * ((double)dc * q.d1);
+        const double x = d_ra * cs + d_dec * sn, y = d_dec * cs - d_ra * sn;      // (d_ra + i d_dec) * exp(-i phi)
+        double acc = 0.0;
+        for (int r = 0; r < q.nrad; ++r) {
+            const double w = wt[r];
+            if (w == 0.0) continue;
+            const double* tab = q.psfs + ((size_t)e * q.nrad + q.perm[e * q.nrad + r]) * ((size_t)q.px * q.py);
+            const double c0 = q.cid[((size_t)e * q.nrad + r) * 2], c1 = q.cid[((size_t)e * q.nrad + r) * 2 + 1];
+            double a = (x + c0 * q.delta0) / q.delta0, b = (y + c1 * q.delta1) / q.delta1;
+            a = a < 0.0 ? 0.0 : (a > (double)(q.px - 1) ? (double)(q.px - 1) : a);     // mode='nearest'
+            b = b < 0.0 ? 0.0 : (b > (double)(q.py - 1) ? (double)(q.py - 1) : b);
+            const int i0 = (int)floor(a), j0 = (int)floor(b);
+            const int i1 = i0 + 1 < q.px ? i0 + 1 : q.px - 1, j1 = j0 + 1 < q.py ? j0 + 1 : q.py - 1;
+            const double fa = a - (double)i0, fb = b - (double)j0;
+            const double v00 = tab[(size_t)i0 * q.py + j0], v01 = tab[(size_t)i0 * q.py + j1];
+            const double v10 = tab[(size_t)i1 * q.py + j0], v11 = tab[(size_t)i1 * q.py + j1];
+            acc += w * ((1.0 - fa) * ((1.0 - fb) * v00 + fb * v01) + fa * ((1.0 - fb) * v10 + fb * v11));
+        }
+        ob[idx] = acc;
+    }
+}

@@ -17,6 +17,7 @@ Reference lines followed (all under /root/reference):
   jubik/instruments/erosita/erosita_response.py:209-212,307,327-328,349-350  vmap over modules, R
   jubik/instruments/chandra/chandra_response.py:127-142                     vmap over observations, R
   demos/x-ray-imaging.py:313  Poisson energy  sum(lambda) - d*log(lambda)   (arithmetic lives in NIFTy)
+  jubik/instruments/erosita/erosita_psf_utils.py:17-264  psf_interpolator / get_psf (PSF tables -> patch kernels)
 
 Pinning status
   * slice_patches / its transpose, convolve, _bilinear_weights, integrate, exposure and readout
@@ -399,6 +400,79 @@ def energy_and_grad_logsky(resp: Response, data_dense, log_sky):
     x = np.exp(np.asarray(log_sky, dtype=np.float64))
     h, g = energy_and_grad(resp, data_dense, x)
     return h, g * x
+
+
+# ------------------------------------------------- eROSITA PSF interpolation onto the patch grid
+def psf_interpolation_weights(rs, r):
+    """erosita_psf_utils.py:41-72 get_interpolation_weights: linear weights of the (ascending) radii `rs` at `r`, constant
+    extrapolation outside.  Restated with its overlap: at r == rs[-1] both the "back" branch and the last interval fire
+    (the weight of the last table becomes 2), exactly as the reference's sum of cond() terms does."""
+    rs = np.asarray(rs, dtype=np.float64)
+    res = np.zeros(rs.shape)
+    if r <= rs[0]:
+        res[0] += 1.0
+    if r >= rs[-1]:
+        res[-1] += 1.0
+    dr = rs[1:] - rs[:-1]
+    for i in range(rs.size - 1):
+        if rs[i] < r and rs[i + 1] >= r:
+            wgt = (r - rs[i]) / dr[i]
+            res[i] += 1.0 - wgt
+            res[i + 1] += wgt
+    return res
+
+
+def psf_patch_centers(shape, distances, npatch):
+    """erosita_psf_utils.py:213-246: (c_ra, c_dec) of the n*n patches; patch k = a*n + b has ra = cen1[n-1-a], dec = cen0[b]
+    (meshgrid 'xy' + the flip of the ra list)."""
+    cen = [np.array([(i * (ss // npatch) + (ss // npatch) / 2) * dd for i in range(npatch)]) for ss, dd in zip(shape, distances)]
+    c0, c1 = np.meshgrid(cen[0], cen[1], indexing="xy")
+    return np.flip(c1.flatten()), c0.flatten()
+
+
+def psf_interpolator(domain, npatch, psf_infos):
+    """erosita_psf_utils.py:198-264 psf_interpolator with :94-171 get_psf: for every patch centre the PSF tables of the
+    two bracketing off-axis radii are rotated to the patch's position angle and bilinearly resampled
+    (map_coordinates order=1, mode='nearest') onto the sky grid; result (n*n, E, N0, N1), origin-centred (rolled by N/2)."""
+    from scipy import ndimage
+    shp = (domain.shape[-2], domain.shape[-1])
+    dist = (domain.distances[-2], domain.distances[-1])
+    for ss in shp:
+        if ss % npatch != 0 or ss % 2 != 0:
+            raise ValueError
+    c_p = np.meshgrid(*[(np.arange(ss) - ss / 2) * dd for ss, dd in zip(shp, dist)], indexing="ij")
+    d_dec, d_ra = c_p[0], -1.0 * c_p[1]
+    c_ra, c_dec = psf_patch_centers(shp, dist, npatch)
+    out = []
+    for info in psf_infos:
+        rs = np.array(info["rs"], dtype=float)
+        sort = np.argsort(rs)
+        rs = rs[sort]
+        psfs = np.asarray(info["psfs"], dtype=float)[sort]
+        cids = np.asarray(info["patch_center_ids"], dtype=float)[sort]
+        if psfs.shape[0] != rs.size or cids.shape[0] != rs.size:
+            raise ValueError
+        deltas = np.array(list(info["patch_deltas"]), dtype=float)
+        pointing = np.array(list(info["pointing_center"]), dtype=float)
+        patches = []
+        for ra, dec in zip(c_ra, c_dec):
+            cc = np.array([ra, dec]) - pointing
+            r = np.sqrt(cc[0] ** 2 + cc[1] ** 2)
+            phi = np.angle(cc[0] + 1.j * cc[1]) - np.pi / 2.
+            wg = psf_interpolation_weights(rs, r)
+            # rotate the requested slice to the patch's position angle (to_r_phi, phi -= phi_patch, to_ra_dec)
+            ri = np.sqrt(d_ra ** 2 + d_dec ** 2)
+            ph = np.angle(d_ra + 1.j * d_dec) - np.pi / 2. - phi
+            xr = ri * np.cos(ph + np.pi / 2.)
+            yr = ri * np.sin(ph + np.pi / 2.)
+            res = np.zeros(shp)
+            for ids, pp, ww in zip(cids, psfs, wg):
+                q0 = (xr + ids[0] * deltas[0]) / deltas[0]
+                q1 = (yr + ids[1] * deltas[1]) / deltas[1]
+                res += ww * ndimage.map_coordinates(pp, np.stack([q0, q1]), order=1, mode="nearest")
+            patches.append(np.roll(np.roll(res, -shp[0] // 2, axis=0), -shp[1] // 2, axis=1))
+        out.append(np.array(patches))
+    return np.moveaxis(np.stack(out), 0, -3)
 
 
 def default_workers():

@@ -75,3 +75,26 @@ def counts_from(lam_dense, seed=3):
 
 def direction(shape, seed=4):
     return np.random.default_rng(seed).standard_normal(shape)
+
+
+def psf_infos(E, nrad, px, seed=5, pointing=(100.0, 150.0)):
+    """Synthetic stand-in for eROSITA_PSF._get_psf_infos (erosita_psf.py:211-220), one dict per energy: PSF tables
+    (nrad, px, px) = rotated Gaussians widening with the off-axis radius, radii given UNSORTED (the reference sorts them),
+    centre indices jittered around the middle, 4-unit bins."""
+    rng = np.random.default_rng(seed)
+    infos = []
+    yy, xx = np.meshgrid(np.arange(px), np.arange(px), indexing="ij")
+    for e in range(E):
+        rs = np.array([150.0, 0.0, 260.0, 60.0, 330.0][:nrad]) * (1.0 + 0.05 * e)
+        cid = np.stack([np.array([px // 2 + rng.integers(-1, 2), px // 2 + rng.integers(-1, 2)])
+                        for _ in range(nrad)]).astype(float)
+        tabs = []
+        for q in range(nrad):
+            s1, s2 = 1.2 + rs[q] / 120.0 + 0.2 * e, 1.0 + rs[q] / 200.0
+            th = rng.uniform(0, np.pi)
+            u = np.cos(th) * (yy - cid[q, 0]) + np.sin(th) * (xx - cid[q, 1])
+            v = -np.sin(th) * (yy - cid[q, 0]) + np.cos(th) * (xx - cid[q, 1])
+            tabs.append(np.exp(-0.5 * (u / s1) ** 2 - 0.5 * (v / s2) ** 2) * rng.uniform(0.5, 2.0))
+        infos.append({"psfs": np.array(tabs), "rs": rs, "patch_center_ids": cid, "patch_deltas": (4.0, 4.0),
+                      "pointing_center": pointing})
+    return infos

@@ -164,3 +164,28 @@ def test_emulated_standalone_fft_convolve_and_kernel_fingerprint():
     x = synth.sky(1, 1, N)
     dom = orc.Domain((1, N, N), synth.DIST)
     assert rel(p.psf(x)[0, 0], orc.linpatch_convolve(x[0], dom, k2[0], n, m, cropped=True)) < TOL
+
+
+@pytest.mark.parametrize("name", ["psf_interp_N48_n4", "psf_interp_N40_n5"])
+def test_emulated_psf_interpolator_matches_reference_golden(golden_dir, name):
+    """jubik_psf_interpolate (k_psf_interp + its host-side weight / rotation set-up) through the emulation build against
+    the reference source's output, in both layouts."""
+    import ctypes as C
+    from jubik_b200 import _lib
+    from tests.emu.emu_plan import emu_lib, _p
+    lib = emu_lib()
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    E, N, n, nrad, px, dist = int(z["E"]), int(z["N"]), int(z["n"]), int(z["nrad"]), int(z["px"]), float(z["dist"])
+    infos = synth.psf_infos(E, nrad, px, seed=int(z["seed"]))
+    tabs = np.ascontiguousarray(np.stack([i["psfs"] for i in infos]))
+    rs = np.ascontiguousarray(np.stack([i["rs"] for i in infos]))
+    cid = np.ascontiguousarray(np.stack([i["patch_center_ids"] for i in infos]))
+    t = _lib.PsfTables(E, nrad, px, px, tabs.ctypes.data, rs.ctypes.data, cid.ctypes.data, 4.0, 4.0, *infos[0]["pointing_center"])
+    full = np.empty((n * n, E, N, N))
+    _lib.check(lib, lib.jubik_psf_interpolate(C.byref(t), N, n, dist, dist, _lib.KERNEL_FULL, _p(full), None))
+    assert rel(full, z["kernel"]) < 1e-12
+    dx = N // n
+    crop = np.empty((n * n, E, 2 * dx, 2 * dx))
+    _lib.check(lib, lib.jubik_psf_interpolate(C.byref(t), N, n, dist, dist, _lib.KERNEL_CROPPED, _p(crop), None))
+    assert rel(crop, orc.crop_kernel(z["kernel"], (N, N), n)) < 1e-12
+    assert lib.jubik_psf_interpolate(C.byref(t), N + 1, n, dist, dist, _lib.KERNEL_FULL, _p(full), None) == 1

@@ -565,6 +565,41 @@ def test_standalone_slice_patches_and_convolve_match_reference_golden(torch_cuda
     np.testing.assert_allclose(res, sig, rtol=1e-10, atol=1e-10)
 
 
+def test_device_psf_interpolator_feeds_the_plan_without_the_full_size_array(torch_cuda, golden_dir):
+    """psf_interpolator (erosita_psf_utils.py:198-264) on the device against the reference source's output
+    (both layouts), and end to end: the cropped kernels it writes for two modules go straight into a ResponsePlan whose
+    PSF output equals the oracle's linpatch_convolve with the reference's full-size interpolated kernels."""
+    import jubik_b200 as jb
+    torch = torch_cuda
+    for name in ("psf_interp_N48_n4", "psf_interp_N40_n5"):
+        z = np.load(os.path.join(golden_dir, name + ".npz"))
+        E, N, n, dist = int(z["E"]), int(z["N"]), int(z["n"]), float(z["dist"])
+        infos = synth.psf_infos(E, int(z["nrad"]), int(z["px"]), seed=int(z["seed"]))
+        dom = jb.Domain((E, N, N), (1.0, dist, dist))
+        full = jb.psf_interpolator(dom, n, infos)
+        assert tuple(full.shape) == z["kernel"].shape and rel(full.cpu().numpy(), z["kernel"]) < 1e-12
+        crop = jb.psf_interpolator(dom, n, infos, cropped=True)
+        assert rel(crop.cpu().numpy(), orc.crop_kernel(z["kernel"], (N, N), n)) < 1e-12
+        with pytest.raises(ValueError):
+            jb.psf_interpolator(jb.Domain((E, N + 2, N + 2), (1.0, dist, dist)), n, infos)
+    # two modules with different pointings -> (T, n*n, E, 2dx, 2dx) written module by module -> plan
+    E, N, n, m, dist = 2, 240, 4, 10, 8.0
+    dx = N // n
+    dom = jb.Domain((E, N, N), (1.0, dist, dist))
+    dom_o = orc.Domain(dom.shape, dom.distances)
+    mods = [synth.psf_infos(E, 4, 33, seed=31, pointing=(500.0, 900.0)), synth.psf_infos(E, 4, 33, seed=32, pointing=(1200.0, 300.0))]
+    kern = torch.empty((2, n * n, E, 2 * dx, 2 * dx), dtype=torch.float64, device="cuda")
+    for t, infos in enumerate(mods):
+        jb.psf_interpolator(dom, n, infos, cropped=True, out=kern[t])
+    plan = jb.ResponsePlan(kern, N, n, m, cropped=True, distances=dom.distances[-2:])
+    x = synth.sky(1, E, N)[0]
+    y = plan.psf(dev(torch, x)).cpu().numpy()
+    for t, infos in enumerate(mods):
+        kfull = orc.psf_interpolator(dom_o, n, infos)
+        assert rel(y[t], orc.linpatch_convolve(x, dom_o, kfull, n, m)) < TOL
+    plan.close()
+
+
 def test_general_convolve_runs_on_the_fft_kernels(torch_cuda, capsys):
     """jubik.convolve (convolve.py:148-176) for arrays whose sides are compiled transform lengths: square and
     rectangular, any leading shape, NumPy-style broadcasting of the leading axes and the N-D form of the reference's

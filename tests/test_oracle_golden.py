@@ -183,3 +183,20 @@ def test_partition_of_unity_interior():
     dx = N // n
     inner = slice(dx // 2 + 1, N - dx // 2 - 1)
     assert np.abs(y[:, inner, inner] / x[:, inner, inner] - 1).max() < 1e-13
+
+
+@pytest.mark.parametrize("name", ["psf_interp_N48_n4", "psf_interp_N40_n5"])
+def test_oracle_psf_interpolator_matches_reference_source(golden_dir, name):
+    """erosita_psf_utils.py:198-264 psf_interpolator executed from the reference's own source (make_golden_psf.py) on
+    synthetic PSF tables: the oracle's restatement reproduces it bit for bit (unsorted radii, extrapolation at both ends
+    of the radius range, rotation to the patch's position angle, 'nearest' edge handling)."""
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    E, N, n = int(z["E"]), int(z["N"]), int(z["n"])
+    infos = synth.psf_infos(E, int(z["nrad"]), int(z["px"]), seed=int(z["seed"]))
+    dist = float(z["dist"])
+    k = orc.psf_interpolator(orc.Domain((E, N, N), (1.0, dist, dist)), n, infos)
+    assert k.shape == z["kernel"].shape and np.array_equal(k, z["kernel"])
+    with pytest.raises(ValueError):
+        orc.psf_interpolator(orc.Domain((E, N + 1, N + 1), (1.0, dist, dist)), n, infos)
+    w = orc.psf_interpolation_weights(np.array([0.0, 1.0, 3.0]), 2.0)
+    assert np.allclose(w, [0.0, 0.5, 0.5]) and np.allclose(orc.psf_interpolation_weights(np.array([0.0, 1.0]), -1.0), [1, 0])
