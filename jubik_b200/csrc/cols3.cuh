@@ -460,7 +460,7 @@ k_cols3_pipe(const
 template <class F3, int CB>
 JB_GLOBAL void JB_LB((Cols3<F3, CB>::THREADS), 1)
 k_prep_cols3(JbGeom g, const cd* __restrict__ scratch, const double* __restrict__ sums, const cd* __restrict__ tw1g,
-             const cd* __restrict__ tw2g, cd* __restrict__ khat) {
+             const cd* __restrict__ tw2g, cd* __restrict__ khat, int per_column) {
     using C3 = Cols3<F3, CB>;
     constexpr int L = F3::L, R3 = F3::R3, M = F3::M;
     constexpr int JB_C3_THREADS = C3::THREADS;
@@ -492,6 +492,15 @@ k_prep_cols3(JbGeom g, const cd* __restrict__ scratch, const double* __restrict_
         cd v[R3];
         C3::s3_fwd(tile, tid, v);
         const double scale = 1.0 / (sums[pk] * (double)L * (double)L);
-        static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; kb[k3 * C3::I3 + tid] = cd_scale(v[k3], scale); });
+        if (!per_column) {
+            static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; kb[k3 * C3::I3 + tid] = cd_scale(v[k3], scale); });
+        } else {
+            // layout of the warp-private column pass (cols_wp.cuh): (TE, n*n, PH, L) with L = [k3][k1*R2 + k2]
+            const int c = tid / CB, b = tid - c * CB, col = col0 + b;
+            if (col < PH) {
+                cd* kc = khat + (pk * PH + col) * (size_t)L;
+                static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; kc[k3 * (F3::R1 * F3::R2) + c] = cd_scale(v[k3], scale); });
+            }
+        }
     }
 }

@@ -7,6 +7,14 @@
 #include "cols_pipe.cuh"
 #include "cols3.cuh"
 #include "rows5.cuh"
+#include "cols_wp.cuh"
+
+#ifndef JB_COLS_WP
+#define JB_COLS_WP 0   // 1: the column pass runs as warp-private transforms (cols_wp.cuh) instead of the TMA tile pipeline
+#endif
+#ifndef JB_COLS_WP_NW
+#define JB_COLS_WP_NW 8
+#endif
 
 
 struct JbFftOps {
@@ -57,7 +65,22 @@ template <class FP, int CB, int PIPE, class F3>
 struct JbOpsImpl {
     static cudaError_t cols_pipe(const JbGeom& g, bool adj, const JbTileSrc& src, cd* out, const cd* khat,
                                  const cd* twa, const cd* twb, const double* wgt, int planes, int ctas, jb_stream_t st) {
-        if constexpr (PIPE == 2) {
+        if constexpr (PIPE == 2 && JB_COLS_WP) {
+            constexpr int NW = JB_COLS_WP_NW;
+            const size_t smem = jb_cols_wp_smem<F3>(g.w, NW);
+            auto go = [&](auto kern) {
+                int per_sm = 1;
+#ifndef JB_EMU
+                if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+#endif
+                long grid = (long)per_sm * ctas;
+                const long units = (long)planes * g.n * g.n * g.PH, need = (units + NW - 1) / NW;
+                if (grid > need) grid = need;
+                return jb_launch(kern, dim3((unsigned)grid), dim3(NW * 32), smem, st, g, src.base, out, khat, twa, twb, wgt, planes);
+            };
+            return adj ? go(k_cols_wp<F3, true, NW>) : go(k_cols_wp<F3, false, NW>);
+        } else if constexpr (PIPE == 2) {
             size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd) + 32 +
                           2 * sizeof(JbColInfo) + (size_t)g.w * sizeof(double) + 32 + 128;   // + the tile shift for odd margins
             const dim3 grid(ctas * Cols3<F3, CB>::CPS), block(Cols3<F3, CB>::THREADS);
@@ -284,7 +307,8 @@ struct JbOpsImpl {
         if constexpr (PIPE == 2) {
             if (layout == 2) {
                 size_t smem3 = (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd);
-                return jb_launch(k_prep_cols3<F3, CB>, grid, dim3(Cols3<F3, CB>::THREADS), smem3, st, g, scratch, sums, twa, twb, khat);
+                return jb_launch(k_prep_cols3<F3, CB>, grid, dim3(Cols3<F3, CB>::THREADS), smem3, st, g, scratch, sums, twa, twb, khat,
+                                 (int)JB_COLS_WP);
             }
         }
         size_t smem = (FP::R2 == 1) ? 16 : (size_t)FP::L * CB * sizeof(cd);

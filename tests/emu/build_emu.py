@@ -15,12 +15,13 @@ ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
 sys.path.insert(0, ROOT)
 from jubik_b200.build import fft_list, CSRC  # noqa: E402
 
-OUT = os.path.join(HERE, "_build")
+EXTRA = os.environ.get("JUBIK_B200_EMU_EXTRA", "").split()     # kernel-variant switches, e.g. -DJB_COLS_WP=1 (tuning only)
+OUT = os.path.join(HERE, "_build" + ("_" + "".join(c for c in "".join(EXTRA) if c.isalnum()) if EXTRA else ""))
 LIB = os.path.join(OUT, "libjubik_emu.so")
 # -fno-gnu-unique / -Bsymbolic: keep this library's symbols from merging with libjubik_b200.so when a test
 # process loads both (they are built from the same sources)
 FLAGS = ["-std=c++20", "-O1", "-fPIC", "-DJB_EMU", "-x", "c++", "-pthread", "-w", "-fno-gnu-unique",
-         "-fvisibility-inlines-hidden"]
+         "-fvisibility-inlines-hidden"] + EXTRA
 
 
 def _run(cmd):
