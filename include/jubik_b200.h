@@ -148,6 +148,12 @@ int jubik_poisson_left_sqrt_metric_at_point(jubik_plan* plan, const double* t, i
  * row kernel on load and the product by the c2r row kernel on store: no extra pass over the sky. */
 int jubik_poisson_energy_and_grad_logsky(jubik_plan* plan, const double* log_sky, int n_samples,
                                          double* energy, double* grad, void* stream);
+/* The same on the sky model's PADDED log-sky: sky = exp(log_sky[:E, :N, :N]) (jubik/sky_models.py:340-341, the padding of
+ * the correlated-field model).  log_sky, grad: (S, e_pad, n_pad, n_pad) with e_pad >= E, n_pad >= N (even); the r2c row
+ * kernel reads the crop in place with the padded strides, the c2r row kernel writes d energy / d log_sky into the crop
+ * of grad and the rest of grad is zeroed -- no cropped copy, no padded copy. */
+int jubik_poisson_energy_and_grad_logsky_padded(jubik_plan* plan, const double* log_sky, int n_samples, int e_pad, int n_pad,
+                                                double* energy, double* grad, void* stream);
 /* Stand-alone helpers of the reference's public API (no plan needed; device pointers, fp64):
  *   jubik_slice_patches    jubik/convolve.py:28-63: x (lead,h,w) -> out (n*n, lead, 2dx+2dr, 2dy+2dr), patch k = i*n+j at
  *                          row offset j*dx, column offset i*dy of the dx//2-padded array (dynamic_slice clamping)

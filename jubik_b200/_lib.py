@@ -26,6 +26,7 @@ EXPORTS = [
     "jubik_response_apply_T", "jubik_poisson_energy_and_grad", "jubik_poisson_metric_apply",
     "jubik_poisson_energy_and_grad_host", "jubik_poisson_profile", "jubik_measure_fp64_tflops",
     "jubik_poisson_left_sqrt_metric", "jubik_poisson_energy_and_grad_logsky",
+    "jubik_poisson_energy_and_grad_logsky_padded",
     "jubik_slice_patches", "jubik_slice_patches_T", "jubik_convolve", "jubik_psf_interpolate",
     "jubik_comm_unique_id", "jubik_comm_create", "jubik_comm_adopt", "jubik_comm_destroy", "jubik_comm_rank",
     "jubik_comm_size", "jubik_sharded_flat_size", "jubik_poisson_energy_and_grad_sharded",
@@ -90,6 +91,7 @@ def bind(lib):
     lib.jubik_measure_fp64_tflops.argtypes = [C.POINTER(d), vp]
     lib.jubik_poisson_left_sqrt_metric.argtypes = [vp, vp, vp, i, vp, vp]
     lib.jubik_poisson_energy_and_grad_logsky.argtypes = [vp, vp, i, vp, vp, vp]
+    lib.jubik_poisson_energy_and_grad_logsky_padded.argtypes = [vp, vp, i, i, i, vp, vp, vp]
     lib.jubik_slice_patches.argtypes = [vp, i, i, i, i, i, vp, vp]
     lib.jubik_slice_patches_T.argtypes = [vp, i, i, i, i, i, vp, vp]
     lib.jubik_convolve.argtypes = [vp, vp, i, i, i, i, d, vp, vp]

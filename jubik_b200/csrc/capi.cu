@@ -738,15 +738,20 @@ static int reduce_energy(jubik_plan* p, int S, double* energy, jb_stream_t st) {
     return 0;
 }
 
-// fused energy + gradient of sum(lambda) - d log(lambda); logsky: x holds log_sky (exp on load, * exp(log_sky) on store)
-static int energy_and_grad_impl(jubik_plan* p, const double* x, int S, double* energy, double* grad, bool logsky, jb_stream_t st) {
+// fused energy + gradient of sum(lambda) - d log(lambda); logsky: x holds log_sky (exp on load, * exp(log_sky) on store);
+// gs: geometry with the sky-space strides of a padded log-sky (or p->g)
+static int energy_and_grad_geom(jubik_plan* p, const JbGeom& gs, const double* x, int S, double* energy, double* grad, bool logsky,
+                                jb_stream_t st) {
     if (!p->has_expo || !p->has_data) return fail(JUBIK_ERR_ARG, "plan needs exposures and data for the Poisson energy");
     JbEpi ep; memset(&ep, 0, sizeof(ep));
     ep.mode = JB_EPI_POISSON; ep.out = p->gbuf; ep.expo = p->expo; ep.data = p->data; ep.partial = p->partial;
-    if (int rc = run_forward_g(p, p->g, x, S, ep, logsky ? 1 : 0, st)) return rc;
+    if (int rc = run_forward_g(p, gs, x, S, ep, logsky ? 1 : 0, st)) return rc;
     if (int rc = reduce_energy(p, S, energy, st)) return rc;
-    if (grad) return run_adjoint_g(p, p->g, p->gbuf, nullptr, S, grad, logsky ? x : nullptr, st);
+    if (grad) return run_adjoint_g(p, gs, p->gbuf, nullptr, S, grad, logsky ? x : nullptr, st);
     return JUBIK_OK;
+}
+static int energy_and_grad_impl(jubik_plan* p, const double* x, int S, double* energy, double* grad, bool logsky, jb_stream_t st) {
+    return energy_and_grad_geom(p, p->g, x, S, energy, grad, logsky, st);
 }
 
 int jubik_poisson_energy_and_grad(jubik_plan* p, const double* x, int S, double* energy, double* grad, void* stream_) {
@@ -758,6 +763,27 @@ int jubik_poisson_energy_and_grad_logsky(jubik_plan* p, const double* log_sky, i
                                          void* stream_) {
     if (int rc = check_call(p, log_sky, energy, S)) return rc;
     return energy_and_grad_impl(p, log_sky, S, energy, grad, true, (jb_stream_t)stream_);
+}
+
+int jubik_poisson_energy_and_grad_logsky_padded(jubik_plan* p, const double* log_sky, int S, int e_pad, int n_pad, double* energy,
+                                                double* grad, void* stream_) {
+    jb_stream_t st = (jb_stream_t)stream_;
+    if (int rc = check_call(p, log_sky, energy, S)) return rc;
+    const JbGeom& g = p->g;
+    if (e_pad < g.E || n_pad < g.N) return fail(JUBIK_ERR_ARG, "the padded log-sky must be at least (E, N, N)");
+    if (n_pad & 1) return fail(JUBIK_ERR_UNSUPPORTED, "the padded spatial size must be even (16-byte aligned rows)");
+    JbGeom gs = g;
+    gs.sky_row = n_pad;
+    gs.sky_pln = (long long)n_pad * n_pad;
+    gs.sky_smp = (long long)e_pad * n_pad * n_pad;
+    if (grad) {   // zero outside the [:E, :N, :N] crop (the kernels write the crop only)
+#ifndef JB_EMU
+        JB_CK(cudaMemsetAsync(grad, 0, (size_t)S * e_pad * n_pad * n_pad * sizeof(double), st));
+#else
+        memset(grad, 0, (size_t)S * e_pad * n_pad * n_pad * sizeof(double));
+#endif
+    }
+    return energy_and_grad_geom(p, gs, log_sky, S, energy, grad, true, st);
 }
 
 #ifndef JB_EMU
@@ -1378,7 +1404,11 @@ static int sharded_impl(jubik_plan* p, jubik_comm* c, int shard_mode, const doub
     };
 #ifndef JB_EMU
     const bool nccl = c && c->nccl;
-    const bool per_bin = p->st_comm && g.E > 1 && ((nccl && R > 1) || xh);
+    // large planes (BASELINE configs[4]: 2 samples x 7 modules at 2048^2 per bin) also run one bin at a time without a
+    // communicator: the per-bin launch order is ~2 % faster there (r2e: 33.7 vs 34.3 ms per chunk); small ones (C2) lose
+    // more to ragged waves than they gain and keep the batched launches
+    const bool big = (size_t)std::min(SM, S) * g.T * npl >= ((size_t)32 << 20);
+    const bool per_bin = p->st_comm && g.E > 1 && ((nccl && R > 1) || xh || big);
     if (xh && !(p->st_comm && p->st_in && p->xdev && p->gdev))
         return fail(JUBIK_ERR_ARG, "the host-buffer sharded call needs a plan created with JUBIK_PLAN_HOST_CALL | JUBIK_PLAN_SHARDED");
     if (per_bin || xh) {

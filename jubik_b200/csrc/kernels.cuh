@@ -35,7 +35,17 @@ struct JbGeom {
     int fold, ext;              // period-P alias fold (L > P and PSF half-support s > m): ext = s - m rows/columns at either
                                 // end of the P-window alias onto [P, P+ext) / [L-ext, L) of the length-L transform
     int offs[JB_MAXN];          // clamped window starts in the hp-padded frame (lax.dynamic_slice)
+    // sky-space strides in doubles (sample, energy plane, row).  0 = contiguous (S,E,N,N).  The sky-model tail
+    // exp(log_sky[:E, :N, :N]) (sky_models.py:340-341) reads the PADDED log-sky in place with these, and its VJP writes
+    // the padded gradient: the crop costs nothing.
+    long long sky_smp, sky_pln;
+    int sky_row;
 };
+// element offset of sky-space row r of (sample s, energy e)
+JB_HD size_t jb_sky_row(const JbGeom& g, int s, int e, int r) {
+    if (g.sky_row == 0) return (((size_t)s * g.E + e) * g.N + r) * (size_t)g.N;
+    return (size_t)s * (size_t)g.sky_smp + (size_t)e * (size_t)g.sky_pln + (size_t)r * (size_t)g.sky_row;
+}
 
 // Period-P alias fold (hard part 2; reference semantics jubik/convolve.py:92-131,165-176: the convolution is
 // CIRCULAR with period P, so PSF tails beyond the margin wrap around).  With a transform length L >= w + 2s the length-L
@@ -134,14 +144,13 @@ JB_GLOBAL void k_rows_fwd(JbGeom g, const double* __restrict__ x, const double* 
     cd* sm = reinterpret_cast<cd*>(smraw);
     int s_, e_;
     const int r0 = blockIdx.x * rpc, se = jb_map_se(g, blockIdx.y, s_, e_);
-    const double* xp = x + (size_t)se * g.N * g.N;
     const int n = g.n, N = g.N, m = g.m, w = g.w, hp = g.hp, PH = g.PH;
     auto ld = [&](int b, int p) -> double {
         int rr = b / n, i = b - rr * n, r = r0 + rr;
         int q = p - m;
         int c = g.offs[i] - hp + q;
         if (r >= N || q < 0 || q >= w || c < 0 || c >= N) return 0.0;
-        double v = jb_ldg(xp + (size_t)r * N + c);
+        double v = jb_ldg(x + jb_sky_row(g, s_, e_, r) + c);
         if (exp_in) v = exp(v);      // sky-model tail x = exp(log_sky) (sky_models.py:340-341)
         return v * jb_ldg(wgt + q);
     };
@@ -388,7 +397,7 @@ JB_GLOBAL void k_rows_adj_out(JbGeom g, const cd* __restrict__ bufB, const doubl
             int v = c - (g.offs[i] - hp);
             if (v >= 0 && v < w) acc += tile[(size_t)(rr * n + i) * w + v];
         }
-        const size_t o = ((size_t)se * N + r) * N + c;
+        const size_t o = jb_sky_row(g, s, e, r) + c;
         if (logsky) acc *= exp(jb_ldg(logsky + o));   // VJP of x = exp(log_sky): d/dlog_sky = grad_x * x
         grad[o] = acc;
     }

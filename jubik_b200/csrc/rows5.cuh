@@ -382,7 +382,7 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
                 ++cnt;
             }
         }
-        int ste = 0, te = 0, se = 0, T = 1;
+        int ste = 0, te = 0, se = 0, T = 1, sky_s = 0, sky_e = 0;
         const cd* plane0;
         size_t tstride = 0;
         if (!ADJ) {
@@ -391,6 +391,7 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
         } else {
             int s_i, e_i;
             se = jb_map_se(g, lp, s_i, e_i);
+            sky_s = s_i; sky_e = e_i;
             T = g.T;
             plane0 = src + ((size_t)(s_i * g.T) * g.E + e_i) * plane_sz;
             tstride = (size_t)g.E * plane_sz;
@@ -427,7 +428,7 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
         // ---- overlap-add gather over the column blocks, epilogue, store
         const double* tr = reinterpret_cast<const double*>(tiles);
         double esum = 0.0;
-        const size_t orow = ADJ ? ((size_t)se * N + r) * N : ((size_t)ste * N + r) * N;
+        const size_t orow = ADJ ? jb_sky_row(g, sky_s, sky_e, r) : ((size_t)ste * N + r) * N;
         const size_t erow = ((size_t)te * N + r) * N;
         constexpr int GU = JB_R5_GU;
 #pragma unroll GU

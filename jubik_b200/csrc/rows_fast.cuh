@@ -162,6 +162,7 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_in_pf(JbGeom g, const double* __restrict__ i
         int te;
         const int pl = plane_of(lp, te);
         const double* src = in + ((size_t)pl * N + r) * N;
+        if (!ADJ) { int s_, e_; jb_map_se(g, lp, s_, e_); src = in + jb_sky_row(g, s_, e_, r); }   // (padded log-sky: strided)
         double* dst = ring + (size_t)slot * N;
         for (int c = 2 * jb_tid(); c < N; c += 2 * jb_nthr()) jb_cp_async16(dst + c, src + c);
         if (with_expo) {
@@ -404,7 +405,7 @@ JB_GLOBAL void JB_LB(256, 2) k_rows_adj_out2(JbGeom g, const cd* __restrict__ bu
             int v = c + hp - g.offs[i];
             if (v >= 0 && v < w) acc += trow[(size_t)i * w - g.offs[i]];
         }
-        const size_t o = ((size_t)se * N + r) * N + c;
+        const size_t o = jb_sky_row(g, s, e, r) + c;
         if (logsky) acc *= exp(jb_ldg(logsky + o));
         grad[o] = acc;
     }

@@ -393,13 +393,26 @@ class ResponsePlan:
         return out[0] if sq else out
 
     def energy_and_grad_logsky(self, log_sky):
-        """Fused value + gradient with respect to log_sky, sky = exp(log_sky) (sky_models.py:340-341)."""
+        """Fused value + gradient with respect to log_sky, sky = exp(log_sky[:E, :N, :N]) (sky_models.py:340-341).
+        log_sky: ([S,] E, N, N), or the sky model's PADDED array ([S,] e_pad, n_pad, n_pad): the crop is read in place
+        (strided), the gradient comes back in the padded shape with zeros outside the crop."""
         import torch
-        s, sq = self._sky(log_sky)
+        self._on_device(log_sky, "input")
+        sq = log_sky.dim() == 3
+        s = (log_sky.unsqueeze(0) if sq else log_sky).contiguous()
+        if s.dim() != 4 or s.shape[0] > self.S_max:
+            raise ValueError("log_sky should have shape ([S,] E, N, N) with S <= max_samples")
         energy = torch.empty((s.shape[0],), dtype=torch.float64, device=self.device)
         grad = torch.empty_like(s)
-        self._call("jubik_poisson_energy_and_grad_logsky", C.c_void_p(s.data_ptr()), s.shape[0],
-                   C.c_void_p(energy.data_ptr()), C.c_void_p(grad.data_ptr()))
+        if tuple(s.shape[1:]) == (self.E, self.N, self.N):
+            self._call("jubik_poisson_energy_and_grad_logsky", C.c_void_p(s.data_ptr()), s.shape[0],
+                       C.c_void_p(energy.data_ptr()), C.c_void_p(grad.data_ptr()))
+        else:
+            ep, np0, np1 = s.shape[1:]
+            if np0 != np1 or ep < self.E or np0 < self.N:
+                raise ValueError("a padded log_sky should have shape ([S,] e_pad >= E, n_pad >= N, n_pad)")
+            self._call("jubik_poisson_energy_and_grad_logsky_padded", C.c_void_p(s.data_ptr()), s.shape[0], int(ep), int(np0),
+                       C.c_void_p(energy.data_ptr()), C.c_void_p(grad.data_ptr()))
         return (energy[0], grad[0]) if sq else (energy, grad)
 
     def energy_and_grad_host(self, x_host, energy_host, grad_host):

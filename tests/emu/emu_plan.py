@@ -98,7 +98,10 @@ class EmuPlan:
         x4 = ls[None] if sq else ls
         e = np.empty((x4.shape[0],))
         g = np.empty_like(x4)
-        self.raw.call("jubik_poisson_energy_and_grad_logsky", _p(x4), x4.shape[0], _p(e), _p(g), None)
+        if x4.shape[1:] == (self.E, self.N, self.N):
+            self.raw.call("jubik_poisson_energy_and_grad_logsky", _p(x4), x4.shape[0], _p(e), _p(g), None)
+        else:       # the sky model's padded array: exp(log_sky[:E, :N, :N])
+            self.raw.call("jubik_poisson_energy_and_grad_logsky_padded", _p(x4), x4.shape[0], x4.shape[1], x4.shape[2], _p(e), _p(g), None)
         return (e[0], g[0]) if sq else (e, g)
 
     def left_sqrt_metric(self, x, t):

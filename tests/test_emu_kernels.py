@@ -93,6 +93,15 @@ def test_emulated_two_pass_fft_against_oracle(case):
     assert rel(gl, np.stack(glo)) < TOL
     eh, gh = p.energy_and_grad_host(x)
     assert np.array_equal(eh, e) and np.array_equal(gh, gr)
+    # the sky model's padded log-sky: sky = exp(log_sky[:E, :N, :N]) read in place, gradient zero outside the crop
+    Sx, Ex, Nx = x.shape[0], x.shape[1], x.shape[-1]
+    lsp = np.random.default_rng(9).normal(size=(Sx, Ex + 1, Nx + 6, Nx + 6))
+    lsp[:, :Ex, :Nx, :Nx] = np.log(x)
+    ep_, gp_ = p.energy_and_grad_logsky(lsp)
+    assert np.array_equal(ep_, el)
+    assert np.array_equal(gp_[:, :Ex, :Nx, :Nx], gl)
+    gp_[:, :Ex, :Nx, :Nx] = 0.0
+    assert not gp_.any()
 
 
 def test_emulated_sharded_entry_point_single_rank():

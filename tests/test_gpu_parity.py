@@ -168,7 +168,14 @@ def test_oracle_parity_all_entry_points(torch_cuda, case):
                np.stack([orc.metric_apply(R, x[s], v2[s]) for s in range(S)])) < TOL
     assert rel(plan.left_sqrt_metric_at_point(gd).cpu().numpy(), lo) < TOL
     ls = np.log(x)
+    # the sky model's padded array (sky_models.py:340: exp(log_diffuse(x)[:edim, :sdim, :sdim])), cropped in place
+    lsp = np.random.default_rng(9).normal(size=(S, E + 1, N + 8, N + 8))
+    lsp[:, :E, :N, :N] = ls
+    elp, glp = plan.energy_and_grad_logsky(dev(torch, lsp))
     el, gl = plan.energy_and_grad_logsky(dev(torch, ls))
+    assert torch.equal(elp, el) and torch.equal(glp[:, :E, :N, :N], gl)
+    glp[:, :E, :N, :N] = 0.0
+    assert not bool(glp.any())
     elo, glo = zip(*[orc.energy_and_grad_logsky(R, d, ls[s]) for s in range(S)])
     assert np.abs((el.cpu().numpy() - np.array(elo)) / np.array(elo)).max() < TOL
     assert rel(gl.cpu().numpy(), np.stack(glo)) < TOL
