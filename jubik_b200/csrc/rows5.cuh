@@ -29,6 +29,12 @@
 #ifndef JB_R5_CPS
 #define JB_R5_CPS 6   // CTAs per SM the SW = 1 kernel is register-limited to
 #endif
+#ifndef JB_R5_WIDE_T
+#define JB_R5_WIDE_T 256   // launch-bound threads of the WIDE form (5..8 warps)
+#endif
+#ifndef JB_R5_BW
+#define JB_R5_BW JB_R5_B   // load budget (see JB_R5_B) of the WIDE form
+#endif
 #ifndef JB_R5_SPF
 #define JB_R5_SPF 2   // spectrum prefetch (forward kernel): 1 = before, 2 = after the assembly of a row, one
                       // cp.async.bulk.prefetch.L2 per covering (row-patch, column block) spectrum row of the NEXT image row of
@@ -263,11 +269,11 @@ JB_D void jb_rows5_assemble_c(cd* tile, const cd* const (&pbase)[SW][2], const b
 }
 
 // loads in flight per lane and round trip: EG * SW * 2 * CNT, kept at <= 16 (64 registers)
-template <class F3, int SW, bool ADJ>
+template <class F3, int SW, bool ADJ, int BUDGET = JB_R5_B>
 JB_D void jb_rows5_assemble(cd* tile, const cd* const (&pbase)[SW][2], const bool (&has)[SW][2], size_t tstride, int T,
                             int cnt, const int (&rowoff)[JB_MAXQ], const double (&wr)[JB_MAXQ],
                             const unsigned* __restrict__ atab, int lane) {
-    constexpr int B = JB_R5_B / SW;   // EG * CNT budget
+    constexpr int B = BUDGET / SW;   // EG * CNT budget
     if (cnt == 1) jb_rows5_assemble_c<F3, SW, ADJ, 1, (B >= 4 ? 4 : B)>(tile, pbase, has, tstride, T, rowoff, wr, atab, lane);
     else if (cnt == 2) jb_rows5_assemble_c<F3, SW, ADJ, 2, (B / 2 >= 1 ? B / 2 : 1)>(tile, pbase, has, tstride, T, rowoff, wr, atab, lane);
     else if (cnt == 3) jb_rows5_assemble_c<F3, SW, ADJ, 3, (B / 3 >= 1 ? B / 3 : 1)>(tile, pbase, has, tstride, T, rowoff, wr, atab, lane);
@@ -327,7 +333,7 @@ JB_D void jb_rows5_prefetch_next(const JbGeom& g, const cd* __restrict__ src, lo
 // still one sequence per warp and 80 registers, so that e.g. 3 CTAs x 5 warps share an SM at L = 672 where the
 // SW = 2 form (3 warps per CTA, 110-128 registers) keeps 9 warps resident.
 template <class F3, int SW, bool ADJ, bool POIS, bool WIDE = false>
-JB_GLOBAL void JB_LB((SW == 1 ? (WIDE ? 256 : 128) : 512), (SW == 1 ? (WIDE ? 3 : JB_R5_CPS) : 1))
+JB_GLOBAL void JB_LB((SW == 1 ? (WIDE ? JB_R5_WIDE_T : 128) : 512), (SW == 1 ? (WIDE ? 3 : JB_R5_CPS) : 1))
 k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, const cd* __restrict__ tw2,
             const double* __restrict__ wgt, const int* __restrict__ gtab, int GQ, JbEpi ep, double* __restrict__ grad,
             const double* __restrict__ logsky, int planes) {
@@ -414,7 +420,7 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
 #if !defined(JB_EMU) && JB_R5_SPF == 1
         if (!ADJ) jb_rows5_prefetch_next<ADJ>(g, src, it_ + gridDim.x, nitems, ROWS, shift, plane_sz, istride, tid, NT);
 #endif
-        jb_rows5_assemble<F3, SW, ADJ>(tile, pbase, has, tstride, T, cnt, rowoff, wr, atab, lane);
+        jb_rows5_assemble<F3, SW, ADJ, (WIDE ? JB_R5_BW : JB_R5_B)>(tile, pbase, has, tstride, T, cnt, rowoff, wr, atab, lane);
 #if !defined(JB_EMU) && JB_R5_SPF == 2
         if (!ADJ) jb_rows5_prefetch_next<ADJ>(g, src, it_ + gridDim.x, nitems, ROWS, shift, plane_sz, istride, tid, NT);
 #endif
