@@ -149,6 +149,24 @@ ffi::Error EnergyAndGradLogskyImpl(cudaStream_t st, int64_t plan, ffi::Buffer<ff
                                    ffi::ResultBuffer<ffi::F64> g) {
     return energy_grad(st, plan, x, e, g, true);
 }
+// the sky model's padded log-sky: sky = exp(log_sky[:E, :N, :N]) read in place (sky_models.py:340-341); x, grad:
+// ([...], e_pad, n_pad, n_pad)
+ffi::Error EnergyAndGradLogskyPaddedImpl(cudaStream_t st, int64_t handle, int64_t e_pad, int64_t n_pad, ffi::Buffer<ffi::F64> x,
+                                         ffi::ResultBuffer<ffi::F64> energy, ffi::ResultBuffer<ffi::F64> grad) {
+    Shape s;
+    if (auto e = get_shape(handle, &s); e.failure()) return e;
+    const int64_t per = e_pad * n_pad * n_pad;
+    int64_t S = 0;
+    if (auto e = samples_of(x, per, "padded log_sky", &S); e.failure()) return e;
+    if ((int64_t)energy->element_count() != S || (int64_t)grad->element_count() != S * per)
+        return bad("jubik_b200: bad output shapes for energy_and_grad_logsky_padded");
+    const double* xp = x.typed_data();
+    double *ep = energy->typed_data(), *gp = grad->typed_data();
+    return chunked(s, S, "jubik_poisson_energy_and_grad_logsky_padded", [&](int64_t c0, int Sc) {
+        return jubik_poisson_energy_and_grad_logsky_padded(s.plan, xp + c0 * per, Sc, (int)e_pad, (int)n_pad, ep + c0,
+                                                           gp + c0 * per, st);
+    });
+}
 // energy only (no adjoint chain): the primal of the custom_vjp when no gradient is requested
 ffi::Error EnergyImpl(cudaStream_t st, int64_t handle, ffi::Buffer<ffi::F64> x, ffi::ResultBuffer<ffi::F64> energy) {
     Shape s;
@@ -250,6 +268,10 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(JubikPsfApplyTK, PsfApplyTKImpl, JB_BIND_K());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(JubikEnergy, EnergyImpl, JB_BIND_1_1());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(JubikEnergyAndGrad, EnergyAndGradImpl, JB_BIND_1_2());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(JubikEnergyAndGradLogsky, EnergyAndGradLogskyImpl, JB_BIND_1_2());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(JubikEnergyAndGradLogskyPadded, EnergyAndGradLogskyPaddedImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Attr<int64_t>("plan").Attr<int64_t>("e_pad")
+                                  .Attr<int64_t>("n_pad").Arg<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(JubikMetricApply, MetricApplyImpl, JB_BIND_2_1());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(JubikLeftSqrtMetric, LeftSqrtMetricImpl, JB_BIND_2_1());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(JubikSetPoint, SetPointImpl, JB_BIND_1_1());

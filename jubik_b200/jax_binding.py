@@ -45,6 +45,7 @@ TARGETS = {
     "jubik_response_apply_tk": "JubikResponseApplyTK", "jubik_psf_apply_tk": "JubikPsfApplyTK",
     "jubik_energy": "JubikEnergy", "jubik_energy_and_grad": "JubikEnergyAndGrad",
     "jubik_energy_and_grad_logsky": "JubikEnergyAndGradLogsky",
+    "jubik_energy_and_grad_logsky_padded": "JubikEnergyAndGradLogskyPadded",
     "jubik_metric_apply": "JubikMetricApply", "jubik_left_sqrt_metric": "JubikLeftSqrtMetric",
     "jubik_set_point": "JubikSetPoint", "jubik_metric_at_point": "JubikMetricAtPoint",
     "jubik_left_sqrt_metric_at_point": "JubikLeftSqrtMetricAtPoint",
@@ -223,6 +224,25 @@ class JaxPlan:
     def energy_logsky(self):
         """The same with the sky-model tail fused: log_sky -> H(exp(log_sky)) (sky_models.py:340-341)."""
         return self._energy_fn("jubik_energy_and_grad_logsky")
+
+    def energy_logsky_padded(self, e_pad, n_pad):
+        """The same on the sky model's PADDED log-sky (..., e_pad, n_pad, n_pad): exp(log_sky[:E, :N, :N]) is read in
+        place, the gradient comes back padded with zeros outside the crop (sky_models.py:340-341)."""
+        trail = (int(e_pad), int(n_pad), int(n_pad))
+
+        def call(x):
+            lead = tuple(x.shape[:-3])
+            if tuple(x.shape[-3:]) != trail:
+                raise ValueError("padded log_sky should have trailing shape %s" % (trail,))
+            return self._call("jubik_energy_and_grad_logsky_padded", [lead, tuple(x.shape)], x,
+                              e_pad=np.int64(e_pad), n_pad=np.int64(n_pad))
+
+        @jax.custom_vjp
+        def energy(x):
+            return call(x)[0]
+
+        energy.defvjp(lambda x: call(x), lambda g, ct: (g * jnp.reshape(ct, ct.shape + (1, 1, 1)),))
+        return energy
 
     def metric(self, x, v):
         """R^T diag(1 / R x) R v."""
