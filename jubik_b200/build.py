@@ -43,6 +43,8 @@ def _sources_digest(flags):
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(HERE, "..", "include")):
         for f in sorted(os.listdir(root)):
+            if f == "jax_ffi.cc":          # the jax.ffi shim is a separate library (jax_binding.build_ffi_library)
+                continue
             h.update(f.encode())
             with open(os.path.join(root, f), "rb") as fh:
                 h.update(fh.read())
