@@ -455,6 +455,195 @@ k_cols3_pipe(const
     }
 }
 
+// --------------------------------------------------------------------------------------------------------
+// Forward column pass for T > 1 modules: the forward column transform of a windowed sky patch does not depend on the
+// telescope module -- only K^ does.  One work item = (sample, energy bin, patch, strip); the tile is loaded and
+// transformed ONCE (stages 1, 2 and the forward half of stage 3; the spectrum is written back to tile A), then every
+// module t reads it, multiplies by its K^ slice and runs the inverse half (stage 3', 2', 1') on tile B.  Per module this
+// is 4/7 of the FP64 work and 7.9 instead of 11.3 shared-memory passes of the one-module kernel (T = 7: BASELINE
+// configs[2] and [4]).  Shared memory: tile A, tile B, a two-slot ring of K^ slices -- the same 4 * L * CB * 16 bytes.
+template <class F3, int CB>
+JB_GLOBAL void JB_LB((Cols3<F3, CB>::THREADS), (Cols3<F3, CB>::CPS))
+k_cols3_fwd_mt(const
+#ifndef JB_EMU
+               __grid_constant__
+#endif
+               JbTileSrc src, JbGeom g, cd* __restrict__ out, const cd* __restrict__ khat,
+               const cd* __restrict__ tw1g, const cd* __restrict__ tw2g, const double* __restrict__ wgt, int planes_se) {
+    using C3 = Cols3<F3, CB>;
+    constexpr int L = F3::L, R1 = F3::R1, R3 = F3::R3, M = F3::M;
+    constexpr int TILE = L * CB;
+    constexpr int NT = C3::THREADS;
+    JB_SMEM(unsigned char, smraw);
+    constexpr int ROWS_PER_128 = (128 / (CB * (int)sizeof(cd))) > 0 ? (128 / (CB * (int)sizeof(cd))) : 1;
+    const int tshift = (ROWS_PER_128 - g.m % ROWS_PER_128) % ROWS_PER_128;   // odd margins: see k_cols3_pipe
+    cd* tileA = reinterpret_cast<cd*>(smraw) + tshift * CB;
+    cd* tileB = tileA + TILE;
+    cd* kh0 = tileB + TILE;
+    cd* tw1 = kh0 + 2 * TILE;
+    cd* tw2 = tw1 + L;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tw2 + M);     // [0] tile A full, [1..2] K^ slot full, [3..4] K^ slot consumed
+    double* rw = reinterpret_cast<double*>(bars + 6);
+    const int tid = threadIdx.x;
+    const int n = g.n, N = g.N, PH = g.PH, nn2 = n * n, T = g.T;
+    const int nstrips = (PH + CB - 1) / CB;
+    const long nitems = (long)planes_se * nn2 * nstrips;
+    for (int i = tid; i < L; i += NT) tw1[i] = tw1g[i];
+    for (int i = tid; i < M; i += NT) tw2[i] = tw2g[i];
+    for (int i = tid; i < g.w; i += NT) rw[i] = wgt[i];
+    struct Item { int strip, k, s, e, j, i, vlo, vhi, row0, ncols; };
+    auto decode = [&](long item) -> Item {
+        Item q;
+        q.strip = (int)(item % nstrips);
+        long r = item / nstrips;
+        q.k = (int)(r % nn2);
+        const int lp = (int)(r / nn2);
+        q.s = lp / g.Es; q.e = g.e0 + (lp - q.s * g.Es);
+        q.j = q.k % n; q.i = q.k / n;
+        q.row0 = g.offs[q.j] - g.hp;                       // image row of tile row m
+        const int lo = -q.row0, hi = N - q.row0;
+        q.vlo = g.m + (lo > 0 ? lo : 0);
+        q.vhi = g.m + (hi < g.w ? hi : g.w);
+        const int nc = PH - q.strip * CB;
+        q.ncols = nc < CB ? nc : CB;
+        return q;
+    };
+    auto item_of = [&](long it_) -> long {
+        long v = (long)blockIdx.x + it_ * (long)gridDim.x;
+        return v < nitems ? v : -1;
+    };
+    auto k_off = [&](const Item& q, int t) -> size_t {
+        return ((((size_t)t * g.E + q.e) * nn2 + q.k) * nstrips + q.strip) * ((size_t)L * CB);
+    };
+    // my item count (uniform per CTA) and the flattened (item, module) step sequence for the K^ ring
+    long my_items = 0;
+    if ((long)blockIdx.x < nitems) my_items = (nitems - 1 - (long)blockIdx.x) / (long)gridDim.x + 1;
+    const long nsteps = my_items * T;
+#ifndef JB_EMU
+    auto issue_tile = [&](long item) {
+        const Item q = decode(item);
+        const int BR = src.BR;
+        const int in_rows = g.w, in_p0 = g.m;
+        int nch = (in_rows + BR - 1) / BR, issued = 0;
+        for (int c = 0; c < nch; ++c) {
+            int r0 = c * BR;
+            if (r0 + BR > in_rows) r0 = in_rows - BR;
+            int p0 = in_p0 + r0;
+            if (p0 + BR > q.vlo && p0 < q.vhi) ++issued;
+        }
+        jb_mbar_expect_tx(&bars[0], (uint32_t)(issued * BR * CB * sizeof(cd)));
+        for (int c = 0; c < nch; ++c) {
+            int r0 = c * BR;
+            if (r0 + BR > in_rows) r0 = in_rows - BR;
+            int p0 = in_p0 + r0;
+            if (p0 + BR > q.vlo && p0 < q.vhi)
+                jb_tma_load_3d(tileA + (size_t)p0 * CB, &src.map, 2 * q.strip * CB, q.row0 + r0, (q.s * g.E + q.e) * n + q.i, &bars[0]);
+        }
+    };
+    auto issue_k = [&](long step) {           // K^ slice of flattened step `step` -> ring slot step & 1
+        const Item q = decode(item_of(step / T));
+        const int ks = (int)(step & 1);
+        jb_mbar_expect_tx(&bars[1 + ks], (uint32_t)(TILE * sizeof(cd)));
+        jb_bulk_load_1d(kh0 + ks * TILE, khat + k_off(q, (int)(step % T)), (uint32_t)(TILE * sizeof(cd)), &bars[1 + ks]);
+    };
+    if (tid == 0) {
+        jb_mbar_init(&bars[0], 1);
+        jb_mbar_init(&bars[1], 1);
+        jb_mbar_init(&bars[2], 1);
+        jb_mbar_init(&bars[3], NT / 32);
+        jb_mbar_init(&bars[4], NT / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (my_items > 0) issue_tile(item_of(0));
+        if (nsteps > 0) issue_k(0);
+        if (nsteps > 1) issue_k(1);
+    }
+#endif
+    JB_SYNC();
+    for (long it = 0; it < my_items; ++it) {
+        const Item q = decode(item_of(it));
+#ifndef JB_EMU
+        jb_mbar_wait<false>(&bars[0], (uint32_t)(it & 1));
+#else
+        JB_SYNC();
+        for (int idx = tid; idx < g.w * CB; idx += NT) {
+            int r = idx / CB, b = idx - r * CB, col = q.strip * CB + b, ir = q.row0 + r;
+            tileA[(size_t)(g.m + r) * CB + b] = (col < PH && ir >= 0 && ir < src.N)
+                ? src.base[((size_t)((q.s * g.E + q.e) * n + q.i) * src.N + ir) * PH + col] : cd_make(0.0, 0.0);
+        }
+        JB_SYNC();
+#endif
+        // ---- shared by all modules: stages 1, 2 and the forward half of stage 3 (spectrum back into tile A)
+        C3::s1_fwd(tileA, tw1, tid, q.vlo, q.vhi, rw, g.m);
+        JB_SYNC();
+        C3::s2_fwd(tileA, tw2, tid);
+        JB_SYNC();
+        if (tid < C3::I3) {
+            cd v[R3];
+            C3::s3_fwd(tileA, tid, v);
+            const int c = tid / CB, b = tid - c * CB;
+            cd* base = tileA + (size_t)(R3 * c) * CB + b;
+            static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; base[k3 * CB] = v[k3]; });
+        }
+        JB_SYNC();
+        for (int t = 0; t < T; ++t) {
+            const long step = it * T + t;
+            const int ks = (int)(step & 1);
+            const cd* kh = kh0 + ks * TILE;
+#ifndef JB_EMU
+            jb_mbar_wait<false>(&bars[1 + ks], (uint32_t)((step >> 1) & 1));
+#else
+            JB_SYNC();
+            for (int idx = tid; idx < TILE; idx += NT) kh0[ks * TILE + idx] = khat[k_off(q, t) + idx];
+            JB_SYNC();
+#endif
+            // ---- stage 3': spectrum (tile A) * K^_t, inverse radix R3 -> tile B
+            if (tid < C3::I3) {
+                const int c = tid / CB, b = tid - c * CB;
+                const cd* sa = tileA + (size_t)(R3 * c) * CB + b;
+                cd* sb = tileB + (size_t)(R3 * c) * CB + b;
+                cd v[R3];
+                static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; v[k3] = cd_mul(sa[k3 * CB], kh[k3 * C3::I3 + tid]); });
+                dft<R3, +1>(v);
+                static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; sb[n3 * CB] = v[n3]; });
+            }
+#ifndef JB_EMU
+            jb_fence_proxy_async();          // the K^ slot (and, after the last module, tile A) is handed back to the copy engine
+            __syncwarp();
+            if ((tid & 31) == 0) jb_mbar_arrive(&bars[3 + ks]);
+            if (tid == 0 && step + 2 < nsteps) {
+                jb_mbar_wait<false>(&bars[3 + ks], (uint32_t)((step >> 1) & 1));
+                issue_k(step + 2);
+            }
+#endif
+            JB_SYNC();                        // tile B complete; every warp is done with tile A when t == T-1
+#ifndef JB_EMU
+            if (tid == 0 && t == T - 1 && it + 1 < my_items) issue_tile(item_of(it + 1));
+#endif
+            C3::s2_inv(tileB, tw2, tid);
+            JB_SYNC();
+            {
+                const bool act = tid < C3::I1;
+                cd v[R1];
+                if (act) C3::s1_inv_load(tileB, tw1, tid, v);
+                JB_SYNC();                    // tile B may be overwritten by the next module's stage 3'
+                if (act) {
+                    dft<R1, +1>(v);
+                    const int m_ = tid / CB, b = tid - m_ * CB;
+                    if (b < q.ncols) {
+                        const size_t plane = ((size_t)q.s * T + t) * g.E + q.e;
+                        cd* ob = out + ((plane * nn2 + q.k) * (size_t)g.P) * PH + (size_t)q.strip * CB + b;
+                        static_for<0, R1>([&](auto nn) {
+                            constexpr int n1 = nn;
+                            const int qr = M * n1 + m_;
+                            if (qr < g.P) ob[(size_t)qr * PH] = v[n1];
+                        });
+                    }
+                }
+            }
+        }
+    }
+}
+
 // plan time: forward 3-stage column transform of the PSF row spectra, normalised, stored as [k3][k1*R2+k2][b].
 // grid (nstrips, n*n, TE), block JB_C3_THREADS, dyn smem = L*CB*16 + (L+M)*16.
 template <class F3, int CB>

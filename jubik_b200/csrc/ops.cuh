@@ -15,6 +15,9 @@
 #ifndef JB_COLS_WP_NW
 #define JB_COLS_WP_NW 8
 #endif
+#ifndef JB_COLS_MT
+#define JB_COLS_MT 1   // forward column pass shares the forward transform between the modules of a (sample, bin, patch)
+#endif
 
 
 struct JbFftOps {
@@ -84,6 +87,11 @@ struct JbOpsImpl {
             size_t smem = 4 * (size_t)FP::L * CB * sizeof(cd) + (size_t)(F3::L + F3::M) * sizeof(cd) + 32 +
                           2 * sizeof(JbColInfo) + (size_t)g.w * sizeof(double) + 32 + 128;   // + the tile shift for odd margins
             const dim3 grid(ctas * Cols3<F3, CB>::CPS), block(Cols3<F3, CB>::THREADS);
+#if JB_COLS_MT
+            // forward with several modules: the forward column transform is shared by the modules (k_cols3_fwd_mt)
+            if (!adj && g.T > 1 && planes % g.T == 0)
+                return jb_launch(k_cols3_fwd_mt<F3, CB>, grid, block, smem, st, src, g, out, khat, twa, twb, wgt, planes / g.T);
+#endif
             if (adj) return jb_launch(k_cols3_pipe<F3, CB, true>, grid, block, smem, st, src, g, out, khat, twa, twb, wgt,
                                       planes);
             return jb_launch(k_cols3_pipe<F3, CB, false>, grid, block, smem, st, src, g, out, khat, twa, twb, wgt, planes);
