@@ -669,7 +669,8 @@ static int run_forward_g(jubik_plan* p, const JbGeom& g, const double* x, int S,
     const JbFftOps* o = p->ops;
     JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.Es, p->rpc, p->thr_rows, p->fast_rows, exp_in, st));
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, false, p->src_fwd, p->bufA, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, false, p->src_fwd, p->bufA, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm,
+                                    (int)(o->cols_mt && g.T > 1), st));
     } else {
         JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
@@ -691,7 +692,7 @@ static int run_adjoint_g(jubik_plan* p, const JbGeom& g, const double* gin, cons
     const JbFftOps* o = p->ops;
     JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.Es, p->rpc, p->thr_rows, p->fast_rows, st));
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, true, p->src_adj, p->bufB, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, true, p->src_adj, p->bufB, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, 0, st));
     } else {
         JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
