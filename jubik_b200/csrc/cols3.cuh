@@ -400,6 +400,8 @@ k_cols3_pipe(const
             __syncwarp();
             if ((tid & 31) == 0) jb_mbar_arrive(&bars[2 + s]);
             if (tid == 0) {
+                // (refilling behind the next item's first block barrier instead -- what k_cols3_fwd_mt does -- costs this
+                // kernel its prefetch lead: 300 -> 326 us at C2; refilling after thread 0's own stores: 271 -> 281 us, r2u)
                 long nxt = item_of((long)it + 2);
                 if (nxt >= 0) {
                     jb_mbar_wait<false>(&bars[2 + s], (it >> 1) & 1);
@@ -482,7 +484,8 @@ k_cols3_fwd_mt(const
     cd* kh0 = tileB + TILE;
     cd* tw1 = kh0 + 2 * TILE;
     cd* tw2 = tw1 + L;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tw2 + M);     // [0] tile A full, [1..2] K^ slot full, [3..4] K^ slot consumed
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tw2 + M);     // [0] tile A full, [1..2] K^ slot full (the slots are handed back
+                                                               // behind a block barrier: no "consumed" barriers needed)
     double* rw = reinterpret_cast<double*>(bars + 6);
     const int tid = threadIdx.x;
     const int n = g.n, N = g.N, PH = g.PH, nn2 = n * n, T = g.T;
@@ -550,8 +553,6 @@ k_cols3_fwd_mt(const
         jb_mbar_init(&bars[0], 1);
         jb_mbar_init(&bars[1], 1);
         jb_mbar_init(&bars[2], 1);
-        jb_mbar_init(&bars[3], NT / 32);
-        jb_mbar_init(&bars[4], NT / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (my_items > 0) issue_tile(item_of(0));
         if (nsteps > 0) issue_k(0);
@@ -608,16 +609,13 @@ k_cols3_fwd_mt(const
             }
 #ifndef JB_EMU
             jb_fence_proxy_async();          // the K^ slot (and, after the last module, tile A) is handed back to the copy engine
-            __syncwarp();
-            if ((tid & 31) == 0) jb_mbar_arrive(&bars[3 + ks]);
-            if (tid == 0 && step + 2 < nsteps) {
-                jb_mbar_wait<false>(&bars[3 + ks], (uint32_t)((step >> 1) & 1));
-                issue_k(step + 2);
-            }
 #endif
-            JB_SYNC();                        // tile B complete; every warp is done with tile A when t == T-1
+            JB_SYNC();                        // tile B complete; every warp is done with this K^ slot (and with tile A when t == T-1)
 #ifndef JB_EMU
-            if (tid == 0 && t == T - 1 && it + 1 < my_items) issue_tile(item_of(it + 1));
+            if (tid == 0) {
+                if (step + 2 < nsteps) issue_k(step + 2);
+                if (t == T - 1 && it + 1 < my_items) issue_tile(item_of(it + 1));
+            }
 #endif
             C3::s2_inv(tileB, tw2, tid);
             JB_SYNC();
