@@ -35,6 +35,11 @@
 #ifndef JB_R5_BW
 #define JB_R5_BW JB_R5_B   // load budget (see JB_R5_B) of the WIDE form
 #endif
+#ifndef JB_R5_APIPE
+#define JB_R5_APIPE 3   // 1: software-pipelined assembly in the forward WIDE kernel (r2v, C5 chunk: rows_out 6.79 -> 6.21 ms,
+                        //    bitwise identical); 2: also in the narrow forward kernel (no gain at its 80 registers: 190.4 ->
+                        //    190.9 us at C2); 3 (default): also over the modules of the adjoint WIDE kernel (rows_adj_out 2.05 -> 1.93 ms)
+#endif
 #ifndef JB_R5_SPF
 #define JB_R5_SPF 2   // spectrum prefetch (forward kernel): 1 = before, 2 = after the assembly of a row, one
                       // cp.async.bulk.prefetch.L2 per covering (row-patch, column block) spectrum row of the NEXT image row of
@@ -268,6 +273,91 @@ JB_D void jb_rows5_assemble_c(cd* tile, const cd* const (&pbase)[SW][2], const b
     }
 }
 
+// Forward, one sequence per warp: the same assembly with the loads of element e+1 in flight while element e is summed
+// and scattered (two register buffers, fully unrolled) -- the warp pays the memory round trip once per row instead of
+// once per element group.  Costs 8*CNT registers: used where the launch bound leaves them (JB_R5_APIPE).
+template <class F3, int CNT>
+JB_D void jb_rows5_assemble_pipe(cd* tile, const cd* pa, const cd* pb, bool hasb, const int (&rowoff)[JB_MAXQ],
+                                 const unsigned* __restrict__ atab, int lane) {
+    using R = Rows5<F3, 1>;
+    cd va[2][CNT], vb[2][CNT];
+    auto load = [&](auto ee, auto bb) {
+        constexpr int e = ee, buf = bb;
+        if (lane + 32 * e < R::PHL) {
+            static_for<0, CNT>([&](auto qq) {
+                constexpr int q = qq;
+                va[buf][q] = jb_ld_stream(pa + lane + 32 * e + rowoff[q]);
+                vb[buf][q] = jb_ld_stream(pb + lane + 32 * e + rowoff[q]);
+            });
+        }
+    };
+    auto consume = [&](auto ee, auto bb) {
+        constexpr int e = ee, buf = bb;
+        const int k = lane + 32 * e;
+        if (k < R::PHL) {
+            cd a = va[buf][0], b = vb[buf][0];
+            static_for<1, CNT>([&](auto qq) { constexpr int q = qq; a = cd_add(a, va[buf][q]); b = cd_add(b, vb[buf][q]); });
+            if (!hasb) b = cd_make(0.0, 0.0);
+            const unsigned ad = atab[e * 32 + lane];
+            const int adk = (int)(ad & 0xffffu), adm = (int)(ad >> 16);
+            tile[adk] = cd_make(a.x - b.y, a.y + b.x);
+            if (adm != 0xffff) tile[adm] = cd_make(a.x + b.y, b.x - a.y);
+        }
+    };
+    load(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
+    static_for<0, (R::NE + 1) / 2>([&](auto pp) {
+        constexpr int e = 2 * (int)pp;
+        if constexpr (e + 1 < R::NE) load(std::integral_constant<int, e + 1>{}, std::integral_constant<int, 1>{});
+        consume(std::integral_constant<int, e>{}, std::integral_constant<int, 0>{});
+        if constexpr (e + 2 < R::NE) load(std::integral_constant<int, e + 2>{}, std::integral_constant<int, 0>{});
+        if constexpr (e + 1 < R::NE) consume(std::integral_constant<int, e + 1>{}, std::integral_constant<int, 1>{});
+    });
+}
+
+// Adjoint, one sequence per warp: the T modules of an element are summed with the loads of module t+1 in flight while
+// module t is accumulated (two register buffers, the module loop unrolled by two).
+template <class F3, int CNT>
+JB_D void jb_rows5_assemble_pipe_adj(cd* tile, const cd* pa, const cd* pb, bool hasb, size_t tstride, int T,
+                                     const int (&rowoff)[JB_MAXQ], const double (&wr)[JB_MAXQ],
+                                     const unsigned* __restrict__ atab, int lane) {
+    using R = Rows5<F3, 1>;
+    for (int e = 0; e < R::NE; ++e) {
+        const int k = lane + 32 * e;
+        if (k >= R::PHL) break;
+        cd va[2][CNT], vb[2][CNT];
+        cd a = cd_make(0.0, 0.0), b = cd_make(0.0, 0.0);
+        auto load = [&](int t, auto bb) {
+            constexpr int buf = bb;
+            const size_t off = (size_t)t * tstride + k;
+            static_for<0, CNT>([&](auto qq) {
+                constexpr int q = qq;
+                va[buf][q] = jb_ld_stream(pa + off + rowoff[q]);
+                vb[buf][q] = jb_ld_stream(pb + off + rowoff[q]);
+            });
+        };
+        auto consume = [&](auto bb) {
+            constexpr int buf = bb;
+            static_for<0, CNT>([&](auto qq) {
+                constexpr int q = qq;
+                a.x += wr[q] * va[buf][q].x; a.y += wr[q] * va[buf][q].y;
+                b.x += wr[q] * vb[buf][q].x; b.y += wr[q] * vb[buf][q].y;
+            });
+        };
+        load(0, std::integral_constant<int, 0>{});
+        for (int t = 0; t < T; t += 2) {
+            if (t + 1 < T) load(t + 1, std::integral_constant<int, 1>{});
+            consume(std::integral_constant<int, 0>{});
+            if (t + 2 < T) load(t + 2, std::integral_constant<int, 0>{});
+            if (t + 1 < T) consume(std::integral_constant<int, 1>{});
+        }
+        if (!hasb) b = cd_make(0.0, 0.0);
+        const unsigned ad = atab[e * 32 + lane];
+        const int adk = (int)(ad & 0xffffu), adm = (int)(ad >> 16);
+        tile[adk] = cd_make(a.x - b.y, a.y + b.x);
+        if (adm != 0xffff) tile[adm] = cd_make(a.x + b.y, b.x - a.y);
+    }
+}
+
 // loads in flight per lane and round trip: EG * SW * 2 * CNT, kept at <= 16 (64 registers)
 template <class F3, int SW, bool ADJ, int BUDGET = JB_R5_B>
 JB_D void jb_rows5_assemble(cd* tile, const cd* const (&pbase)[SW][2], const bool (&has)[SW][2], size_t tstride, int T,
@@ -419,6 +509,22 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
 #endif
 #if !defined(JB_EMU) && JB_R5_SPF == 1
         if (!ADJ) jb_rows5_prefetch_next<ADJ>(g, src, it_ + gridDim.x, nitems, ROWS, shift, plane_sz, istride, tid, NT);
+#endif
+#if JB_R5_APIPE >= 3
+        if constexpr (ADJ && SW == 1 && WIDE) {
+            if (cnt == 1) jb_rows5_assemble_pipe_adj<F3, 1>(tile, pbase[0][0], pbase[0][1], has[0][1], tstride, T, rowoff, wr, atab, lane);
+            else if (cnt == 2) jb_rows5_assemble_pipe_adj<F3, 2>(tile, pbase[0][0], pbase[0][1], has[0][1], tstride, T, rowoff, wr, atab, lane);
+            else if (cnt == 3) jb_rows5_assemble_pipe_adj<F3, 3>(tile, pbase[0][0], pbase[0][1], has[0][1], tstride, T, rowoff, wr, atab, lane);
+            else if (cnt == 4) jb_rows5_assemble_pipe_adj<F3, 4>(tile, pbase[0][0], pbase[0][1], has[0][1], tstride, T, rowoff, wr, atab, lane);
+        } else
+#endif
+#if JB_R5_APIPE
+        if constexpr (!ADJ && SW == 1 && (WIDE || JB_R5_APIPE == 2 || JB_R5_APIPE == 4)) {
+            if (cnt == 1) jb_rows5_assemble_pipe<F3, 1>(tile, pbase[0][0], pbase[0][1], has[0][1], rowoff, atab, lane);
+            else if (cnt == 2) jb_rows5_assemble_pipe<F3, 2>(tile, pbase[0][0], pbase[0][1], has[0][1], rowoff, atab, lane);
+            else if (cnt == 3) jb_rows5_assemble_pipe<F3, 3>(tile, pbase[0][0], pbase[0][1], has[0][1], rowoff, atab, lane);
+            else if (cnt == 4) jb_rows5_assemble_pipe<F3, 4>(tile, pbase[0][0], pbase[0][1], has[0][1], rowoff, atab, lane);
+        } else
 #endif
         jb_rows5_assemble<F3, SW, ADJ, (WIDE ? JB_R5_BW : JB_R5_B)>(tile, pbase, has, tstride, T, cnt, rowoff, wr, atab, lane);
 #if !defined(JB_EMU) && JB_R5_SPF == 2
