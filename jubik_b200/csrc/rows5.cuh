@@ -35,6 +35,9 @@
 #ifndef JB_R5_BW
 #define JB_R5_BW JB_R5_B   // load budget (see JB_R5_B) of the WIDE form
 #endif
+#ifndef JB_R5_APD
+#define JB_R5_APD 2     // depth of the forward assembly pipeline: spectrum elements in flight per lane
+#endif
 #ifndef JB_R5_APIPE
 #define JB_R5_APIPE 3   // 1: software-pipelined assembly in the forward WIDE kernel (r2v, C5 chunk: rows_out 6.79 -> 6.21 ms,
                         //    bitwise identical); 2: also in the narrow forward kernel (no gain at its 80 registers: 190.4 ->
@@ -280,9 +283,10 @@ template <class F3, int CNT>
 JB_D void jb_rows5_assemble_pipe(cd* tile, const cd* pa, const cd* pb, bool hasb, const int (&rowoff)[JB_MAXQ],
                                  const unsigned* __restrict__ atab, int lane) {
     using R = Rows5<F3, 1>;
-    cd va[2][CNT], vb[2][CNT];
-    auto load = [&](auto ee, auto bb) {
-        constexpr int e = ee, buf = bb;
+    constexpr int D = JB_R5_APD;          // elements in flight (register buffers)
+    cd va[D][CNT], vb[D][CNT];
+    auto load = [&](auto ee) {
+        constexpr int e = ee, buf = e % D;
         if (lane + 32 * e < R::PHL) {
             static_for<0, CNT>([&](auto qq) {
                 constexpr int q = qq;
@@ -291,8 +295,8 @@ JB_D void jb_rows5_assemble_pipe(cd* tile, const cd* pa, const cd* pb, bool hasb
             });
         }
     };
-    auto consume = [&](auto ee, auto bb) {
-        constexpr int e = ee, buf = bb;
+    auto consume = [&](auto ee) {
+        constexpr int e = ee, buf = e % D;
         const int k = lane + 32 * e;
         if (k < R::PHL) {
             cd a = va[buf][0], b = vb[buf][0];
@@ -304,13 +308,11 @@ JB_D void jb_rows5_assemble_pipe(cd* tile, const cd* pa, const cd* pb, bool hasb
             if (adm != 0xffff) tile[adm] = cd_make(a.x + b.y, b.x - a.y);
         }
     };
-    load(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
-    static_for<0, (R::NE + 1) / 2>([&](auto pp) {
-        constexpr int e = 2 * (int)pp;
-        if constexpr (e + 1 < R::NE) load(std::integral_constant<int, e + 1>{}, std::integral_constant<int, 1>{});
-        consume(std::integral_constant<int, e>{}, std::integral_constant<int, 0>{});
-        if constexpr (e + 2 < R::NE) load(std::integral_constant<int, e + 2>{}, std::integral_constant<int, 0>{});
-        if constexpr (e + 1 < R::NE) consume(std::integral_constant<int, e + 1>{}, std::integral_constant<int, 1>{});
+    static_for<0, (D - 1 < R::NE ? D - 1 : R::NE)>([&](auto ee) { load(ee); });
+    static_for<0, R::NE>([&](auto ee) {
+        constexpr int e = ee;
+        if constexpr (e + D - 1 < R::NE) load(std::integral_constant<int, e + D - 1>{});
+        consume(ee);
     });
 }
 
