@@ -120,6 +120,8 @@ struct jubik_plan {
     double* edev = nullptr;
     double* gstage = nullptr;  // per-sample gradients of the sharded call without grad_local (JUBIK_PLAN_SHARDED)
     double* flatdev = nullptr; // device image of `flat` for the host-buffer sharded call (HOST_CALL | SHARDED)
+    cd* cols_acc = nullptr;    // T > 1: per-CTA accumulator tiles of the module-summing adjoint column pass (stays in L2)
+    cd* cols_acc2 = nullptr;   // ... of the second compute stream (JUBIK_PLAN_HOST_CALL)
     size_t bytes_khat = 0, bytes_ws = 0, bytes_total = 0;
     int nblk_out = 0;
     int use_pipe = 0, n_sm = 1;
@@ -174,7 +176,7 @@ int jubik_plan_destroy(jubik_plan* p) {
     if (!p) return JUBIK_OK;
     void* bufs[] = {p->fpdev, p->khat, p->tw_nk, p->tw_kn, p->tw1, p->tw2, p->wgt, p->expo, p->data, p->psums, p->psupp, p->bufA, p->bufB,
                     p->bufA2, p->bufB2, p->gbuf2, p->gbuf, p->fac, p->partial, p->gtab_fwd, p->gtab_adj, p->xdev, p->gdev,
-                    p->edev, p->gstage, p->flatdev};
+                    p->edev, p->gstage, p->flatdev, p->cols_acc, p->cols_acc2};
     for (void* b : bufs) dev_free(b);
 #ifndef JB_EMU
     for (int e = 0; e < p->n_ev; ++e) {
@@ -314,7 +316,9 @@ static int ensure_second_workspace(jubik_plan* p) {
     std::string err;
     if ((!p->bufA2 && alloc(p, (void**)&p->bufA2, TE1 * nn2 * orows * g.PH * sizeof(cd), "second spectrum workspace A")) ||
         (!p->bufB2 && alloc(p, (void**)&p->bufB2, TE1 * nn2 * (size_t)g.w * g.PH * sizeof(cd), "second spectrum workspace B")) ||
-        (!p->gbuf2 && alloc(p, (void**)&p->gbuf2, TE1 * (size_t)g.N * g.N * sizeof(double), "second cotangent workspace")))
+        (!p->gbuf2 && alloc(p, (void**)&p->gbuf2, TE1 * (size_t)g.N * g.N * sizeof(double), "second cotangent workspace")) ||
+        (p->cols_acc && !p->cols_acc2 &&
+         alloc(p, (void**)&p->cols_acc2, (size_t)p->n_sm * p->ops->cols_cps * g.L * p->ops->CB * sizeof(cd), "second adjoint column accumulators")))
         return JUBIK_ERR_ALLOC;
     if (p->use_pipe && (make_tile_src(&p->src_fwd2, p->bufB2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brB, &err) ||
                         make_tile_src(&p->src_adj2, p->bufA2, TE1 * (size_t)g.n, g.N, g.PH, p->ops->CB, brA, &err)))
@@ -538,6 +542,8 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
 #else
     p->n_sm = 2;
 #endif
+    if (p->use_pipe == 2 && p->rows5 && o->cols_mt && g.T > 1)
+        JB_TRY(alloc(p, (void**)&p->cols_acc, (size_t)p->n_sm * o->cols_cps * L * o->CB * sizeof(cd), "adjoint column accumulators"));
     JB_TRY(psf_spectra(p, ks, st));
     if (stream_sync(st)) return fail(JUBIK_ERR_CUDA, "PSF spectrum kernels failed");
     JB_TRY(kernel_fingerprint(p, d->kernel, d->kernel_layout, st, p->fp));
@@ -670,7 +676,7 @@ static int run_forward_g(jubik_plan* p, const JbGeom& g, const double* x, int S,
     JB_LAUNCHED(p, o->rows_fwd(g, x, p->wgt, p->tw_nk, p->bufB, S * g.Es, p->rpc, p->thr_rows, p->fast_rows, exp_in, st));
     if (p->use_pipe) {
         JB_LAUNCHED(p, o->cols_pipe(g, false, p->src_fwd, p->bufA, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm,
-                                    (int)(o->cols_mt && g.T > 1), st));
+                                    (int)(o->cols_mt && g.T > 1), nullptr, st));
     } else {
         JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
@@ -691,13 +697,19 @@ static int run_adjoint_g(jubik_plan* p, const JbGeom& g, const double* gin, cons
                          const double* logsky, jb_stream_t st) {
     const JbFftOps* o = p->ops;
     JB_LAUNCHED(p, o->rows_adj_in(g, gin, expo, p->tw_nk, p->bufA, S * g.T * g.Es, p->rpc, p->thr_rows, p->fast_rows, st));
+    // several modules on the fast path: the column pass sums them in the spectral domain (one inverse transform per
+    // patch) and the c2r row pass reads the module-summed spectra as if there were one module
+    const int mt = (p->use_pipe == 2 && p->rows5 && o->cols_mt && g.T > 1 && p->cols_acc) ? 1 : 0;
     if (p->use_pipe) {
-        JB_LAUNCHED(p, o->cols_pipe(g, true, p->src_adj, p->bufB, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, 0, st));
+        JB_LAUNCHED(p, o->cols_pipe(g, true, p->src_adj, p->bufB, p->khat, p->tw1, p->tw2, p->wgt, S * g.T * g.Es, p->n_sm, mt,
+                                    p->cols_acc, st));
     } else {
         JB_LAUNCHED(p, o->cols(g, true, p->bufA, p->bufB, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
     if (p->rows5) {
-        JB_LAUNCHED(p, o->rows5_adj(g, p->bufB, p->wgt, p->tw1, p->tw2, p->gtab_adj, p->gq_adj, out, logsky, S * g.Es, p->n_sm, st));
+        JbGeom gr = g;
+        if (mt) gr.T = 1;
+        JB_LAUNCHED(p, o->rows5_adj(gr, p->bufB, p->wgt, p->tw1, p->tw2, p->gtab_adj, p->gq_adj, out, logsky, S * g.Es, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->rows_adj_out(g, p->bufB, p->wgt, p->tw_kn, out, logsky, S * g.Es, p->rpc, p->thr_rows, p->fast_rows, st));
     }
@@ -794,6 +806,7 @@ static void swap_workspace(jubik_plan* p) {
     std::swap(p->bufA, p->bufA2); std::swap(p->bufB, p->bufB2);
     std::swap(p->src_fwd, p->src_fwd2); std::swap(p->src_adj, p->src_adj2);
     std::swap(p->gbuf, p->gbuf2);
+    if (p->cols_acc2) std::swap(p->cols_acc, p->cols_acc2);
 }
 // Fused energy + gradient as (sample, energy bin) planes alternating between the caller's stream and a second one.
 // wait_in: wait for the per-plane H2D events; after_plane(c): hook after a plane's kernels were enqueued (D2H).

@@ -642,6 +642,189 @@ k_cols3_fwd_mt(const
     }
 }
 
+// --------------------------------------------------------------------------------------------------------
+// Adjoint column pass for T > 1 modules: the inverse column transform is linear, so the modules' products
+// FFT(cotangent_t) * conj K^_t are summed in the spectral domain and ONE inverse transform per (sample, energy bin,
+// patch, strip) writes the module-summed rows -- out: (S*E, n*n, w, PH); the c2r row pass behind it reads one spectrum
+// instead of T.  Per module 4/7 of the FP64 work.  Shared memory keeps BOTH rings double-buffered (two input tiles, two
+// K^ slices); the accumulator lives in a per-CTA scratch tile in global memory that never leaves L2 (each thread
+// reads and writes only its own elements, loads issued ahead of the stage-3 butterfly).  Ring slots are handed back
+// behind block barriers (no thread ever blocks on a "consumed" mbarrier).
+template <class F3, int CB>
+JB_GLOBAL void JB_LB((Cols3<F3, CB>::THREADS), (Cols3<F3, CB>::CPS))
+k_cols3_adj_mt(const
+#ifndef JB_EMU
+               __grid_constant__
+#endif
+               JbTileSrc src, JbGeom g, cd* __restrict__ out, const cd* __restrict__ khat,
+               const cd* __restrict__ tw1g, const cd* __restrict__ tw2g, cd* __restrict__ accg, int planes_se) {
+    using C3 = Cols3<F3, CB>;
+    constexpr int L = F3::L, R1 = F3::R1, R3 = F3::R3, M = F3::M;
+    constexpr int TILE = L * CB;
+    constexpr int NT = C3::THREADS;
+    JB_SMEM(unsigned char, smraw);
+    cd* tile0 = reinterpret_cast<cd*>(smraw);
+    cd* kh0 = tile0 + 2 * TILE;
+    cd* tw1 = kh0 + 2 * TILE;
+    cd* tw2 = tw1 + L;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tw2 + M);     // [0..1] tile slot full, [2..3] K^ slot full
+    const int tid = threadIdx.x;
+    const int n = g.n, N = g.N, PH = g.PH, nn2 = n * n, T = g.T;
+    const int nstrips = (PH + CB - 1) / CB;
+    const long nitems = (long)planes_se * nn2 * nstrips;
+    cd* acc = accg + (size_t)blockIdx.x * TILE;               // this CTA's accumulator, element k3*I3 + tid per thread
+    for (int i = tid; i < L; i += NT) tw1[i] = tw1g[i];
+    for (int i = tid; i < M; i += NT) tw2[i] = tw2g[i];
+    struct Item { int strip, k, s, e, j, i, vlo, vhi, row0, ncols; };
+    auto decode = [&](long item) -> Item {
+        Item q;
+        q.strip = (int)(item % nstrips);
+        long r = item / nstrips;
+        q.k = (int)(r % nn2);
+        const int lp = (int)(r / nn2);
+        q.s = lp / g.Es; q.e = g.e0 + (lp - q.s * g.Es);
+        q.j = q.k % n; q.i = q.k / n;
+        q.row0 = g.offs[q.j] - g.hp - g.m;                 // image row of tile row 0
+        const int lo = -q.row0, hi = N - q.row0;
+        q.vlo = lo > 0 ? lo : 0;
+        q.vhi = hi < g.P ? hi : g.P;
+        const int nc = PH - q.strip * CB;
+        q.ncols = nc < CB ? nc : CB;
+        return q;
+    };
+    auto item_of = [&](long it_) -> long {
+        long v = (long)blockIdx.x + it_ * (long)gridDim.x;
+        return v < nitems ? v : -1;
+    };
+    auto k_off = [&](const Item& q, int t) -> size_t {
+        return ((((size_t)t * g.E + q.e) * nn2 + q.k) * nstrips + q.strip) * ((size_t)L * CB);
+    };
+    long my_items = 0;
+    if ((long)blockIdx.x < nitems) my_items = (nitems - 1 - (long)blockIdx.x) / (long)gridDim.x + 1;
+    const long nsteps = my_items * T;
+#ifndef JB_EMU
+    auto issue_tile = [&](long step) {
+        const Item q = decode(item_of(step / T));
+        const int t = (int)(step % T), ts = (int)(step & 1);
+        cd* tile = tile0 + ts * TILE;
+        const int BR = src.BR, in_rows = g.P;
+        int nch = (in_rows + BR - 1) / BR, issued = 0;
+        for (int c = 0; c < nch; ++c) {
+            int r0 = c * BR;
+            if (r0 + BR > in_rows) r0 = in_rows - BR;
+            if (r0 + BR > q.vlo && r0 < q.vhi) ++issued;
+        }
+        jb_mbar_expect_tx(&bars[ts], (uint32_t)(issued * BR * CB * sizeof(cd)));
+        const int slab = (((q.s * T + t) * g.E + q.e)) * n + q.i;
+        for (int c = 0; c < nch; ++c) {
+            int r0 = c * BR;
+            if (r0 + BR > in_rows) r0 = in_rows - BR;
+            if (r0 + BR > q.vlo && r0 < q.vhi)
+                jb_tma_load_3d(tile + (size_t)r0 * CB, &src.map, 2 * q.strip * CB, q.row0 + r0, slab, &bars[ts]);
+        }
+    };
+    auto issue_k = [&](long step) {
+        const int ks = (int)(step & 1);
+        jb_mbar_expect_tx(&bars[2 + ks], (uint32_t)(TILE * sizeof(cd)));
+        jb_bulk_load_1d(kh0 + ks * TILE, khat + k_off(decode(item_of(step / T)), (int)(step % T)), (uint32_t)(TILE * sizeof(cd)),
+                        &bars[2 + ks]);
+    };
+    if (tid == 0) {
+        for (int b = 0; b < 4; ++b) jb_mbar_init(&bars[b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (nsteps > 0) { issue_tile(0); issue_k(0); }
+        if (nsteps > 1) { issue_tile(1); issue_k(1); }
+    }
+#endif
+    JB_SYNC();
+    for (long it = 0; it < my_items; ++it) {
+        const Item q = decode(item_of(it));
+        for (int t = 0; t < T; ++t) {
+            const long step = it * T + t;
+            const int ts = (int)(step & 1);
+            const bool lastm = t == T - 1;
+            cd* tile = tile0 + ts * TILE;
+            const cd* kh = kh0 + ts * TILE;
+#ifndef JB_EMU
+            jb_mbar_wait<false>(&bars[ts], (uint32_t)((step >> 1) & 1));
+#else
+            JB_SYNC();
+            for (int idx = tid; idx < g.P * CB; idx += NT) {
+                int r = idx / CB, b = idx - r * CB, col = q.strip * CB + b, ir = q.row0 + r;
+                tile[(size_t)r * CB + b] = (col < PH && ir >= 0 && ir < src.N)
+                    ? src.base[((size_t)((((q.s * T + t) * g.E + q.e)) * n + q.i) * src.N + ir) * PH + col] : cd_make(0.0, 0.0);
+            }
+            for (int idx = tid; idx < TILE; idx += NT) kh0[ts * TILE + idx] = khat[k_off(q, t) + idx];
+            JB_SYNC();
+#endif
+            C3::s1_fwd(tile, tw1, tid, q.vlo, q.vhi, nullptr, 0);
+            JB_SYNC();
+#ifndef JB_EMU
+            // every warp is past stage 1' of the previous item's last module / stage 3 of the previous step: when that step
+            // was a LAST module its tile slot is free only now (its inverse stages used it)
+            if (tid == 0 && step >= 1 && ((step - 1) % T) == T - 1 && step + 1 < nsteps) issue_tile(step + 1);
+#endif
+            C3::s2_fwd(tile, tw2, tid);
+            JB_SYNC();
+#ifndef JB_EMU
+            jb_mbar_wait<false>(&bars[2 + ts], (uint32_t)((step >> 1) & 1));
+#endif
+            if (tid < C3::I3) {
+                cd a[R3];
+                if (t > 0) static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; a[k3] = jb_ld_cg(acc + k3 * C3::I3 + tid); });
+                cd v[R3];
+                C3::s3_fwd(tile, tid, v);
+                static_for<0, R3>([&](auto kk) {
+                    constexpr int k3 = kk;
+                    cd y = cd_mulc(v[k3], kh[k3 * C3::I3 + tid]);
+                    if (t > 0) y = cd_add(a[k3], y);          // modules in ascending order: fixed summation order
+                    v[k3] = y;
+                });
+                if (!lastm) {
+                    static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; acc[k3 * C3::I3 + tid] = v[k3]; });
+                } else {          // last module: the sum goes straight into the inverse transform, in this tile slot
+                    dft<R3, +1>(v);
+                    const int c = tid / CB, b = tid - c * CB;
+                    cd* base = tile + (size_t)(R3 * c) * CB + b;
+                    static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; base[n3 * CB] = v[n3]; });
+                }
+            }
+#ifndef JB_EMU
+            jb_fence_proxy_async();
+#endif
+            JB_SYNC();           // stage 3 done everywhere: this step's K^ slot (and, unless it feeds the inverse, its tile slot) is free
+#ifndef JB_EMU
+            if (tid == 0 && step + 2 < nsteps) {
+                issue_k(step + 2);
+                if (!lastm) issue_tile(step + 2);
+            }
+#endif
+            if (lastm) {
+                C3::s2_inv(tile, tw2, tid);
+                JB_SYNC();
+                const bool act = tid < C3::I1;
+                cd v[R1];
+                if (act) C3::s1_inv_load(tile, tw1, tid, v);
+#ifndef JB_EMU
+                jb_fence_proxy_async();      // (the slot is refilled behind the first block barrier of the next step)
+#endif
+                if (act) {
+                    dft<R1, +1>(v);
+                    const int m_ = tid / CB, b = tid - m_ * CB;
+                    if (b < q.ncols) {
+                        cd* ob = out + ((((size_t)q.s * g.E + q.e) * nn2 + q.k) * (size_t)g.w) * PH + (size_t)q.strip * CB + b;
+                        static_for<0, R1>([&](auto nn) {
+                            constexpr int n1 = nn;
+                            const int qr = M * n1 + m_ - g.m;
+                            if (qr >= 0 && qr < g.w) ob[(size_t)qr * PH] = v[n1];
+                        });
+                    }
+                }
+            }
+        }
+    }
+}
+
 // plan time: forward 3-stage column transform of the PSF row spectra, normalised, stored as [k3][k1*R2+k2][b].
 // grid (nstrips, n*n, TE), block JB_C3_THREADS, dyn smem = L*CB*16 + (L+M)*16.
 template <class F3, int CB>

@@ -34,10 +34,14 @@ struct JbFftOps {
     cudaError_t (*cols)(const JbGeom&, bool adj, const cd* in, cd* out, const cd* khat, const cd* tw_nk,
                         const double* wgt, int planes, int threads, jb_stream_t);
     // three-stage TMA pipeline (pipe == 2): twa/twb = stage-1/stage-2 twiddle tables
-    // mt != 0 (several modules, forward): the forward column transform is shared by the modules (cols3.cuh, k_cols3_fwd_mt)
+    // mt != 0 (several modules): forward -- the forward transform is shared by the modules; adjoint -- the modules are
+    // summed in the spectral domain (accumulator tiles in `scratch`: cols_cps * ctas * L * CB elements) and `out` is the
+    // module-summed layout (S*E, n*n, w, PH) (cols3.cuh, k_cols3_*_mt)
     cudaError_t (*cols_pipe)(const JbGeom&, bool adj, const JbTileSrc& src, cd* out, const cd* khat,
-                             const cd* twa, const cd* twb, const double* wgt, int planes, int ctas, int mt, jb_stream_t);
+                             const cd* twa, const cd* twb, const double* wgt, int planes, int ctas, int mt, cd* scratch,
+                             jb_stream_t);
     int cols_mt;   // the *_mt column kernels are compiled in
+    int cols_cps;  // CTAs per SM of the column pipeline
     cudaError_t (*rows_out)(const JbGeom&, const cd* bufA, const cd* tw_kn, const JbEpi&, int planes, int rpc,
                             int threads, int fast, jb_stream_t);
     cudaError_t (*rows_adj_out)(const JbGeom&, const cd* bufB, const double* wgt, const cd* tw_kn, double* grad,
@@ -69,7 +73,8 @@ inline size_t jb_al16(size_t x) { return (x + 15) & ~(size_t)15; }
 template <class FP, int CB, int PIPE, class F3>
 struct JbOpsImpl {
     static cudaError_t cols_pipe(const JbGeom& g, bool adj, const JbTileSrc& src, cd* out, const cd* khat,
-                                 const cd* twa, const cd* twb, const double* wgt, int planes, int ctas, int mt, jb_stream_t st) {
+                                 const cd* twa, const cd* twb, const double* wgt, int planes, int ctas, int mt, cd* scratch,
+                                 jb_stream_t st) {
         if constexpr (PIPE == 2 && JB_COLS_WP) {
             constexpr int NW = JB_COLS_WP_NW;
             const size_t smem = jb_cols_wp_smem<F3>(g.w, NW);
@@ -90,15 +95,17 @@ struct JbOpsImpl {
                           2 * sizeof(JbColInfo) + (size_t)g.w * sizeof(double) + 32 + 128;   // + the tile shift for odd margins
             const dim3 grid(ctas * Cols3<F3, CB>::CPS), block(Cols3<F3, CB>::THREADS);
 #if JB_COLS_MT
-            if (mt && !adj && g.T > 1 && planes % g.T == 0)
-                return jb_launch(k_cols3_fwd_mt<F3, CB>, grid, block, smem, st, src, g, out, khat, twa, twb, wgt, planes / g.T);
+            if (mt && g.T > 1 && planes % g.T == 0) {
+                if (!adj) return jb_launch(k_cols3_fwd_mt<F3, CB>, grid, block, smem, st, src, g, out, khat, twa, twb, wgt, planes / g.T);
+                if (scratch) return jb_launch(k_cols3_adj_mt<F3, CB>, grid, block, smem, st, src, g, out, khat, twa, twb, scratch, planes / g.T);
+            }
 #endif
             if (adj) return jb_launch(k_cols3_pipe<F3, CB, true>, grid, block, smem, st, src, g, out, khat, twa, twb, wgt,
                                       planes);
             return jb_launch(k_cols3_pipe<F3, CB, false>, grid, block, smem, st, src, g, out, khat, twa, twb, wgt, planes);
         } else {
             (void)g; (void)adj; (void)src; (void)out; (void)khat; (void)twa; (void)twb; (void)wgt;
-            (void)planes; (void)ctas; (void)mt; (void)st;
+            (void)planes; (void)ctas; (void)mt; (void)scratch; (void)st;
             return (cudaError_t)1;
         }
     }
@@ -326,6 +333,7 @@ struct JbOpsImpl {
     static const JbFftOps* table() {
         static const JbFftOps t = {FP::L, FP::R1, FP::R2, CB, FP::LS, (FP::R2 > 1 && PIPE == 2) ? 2 : 0, F3::R1, F3::R2, F3::R3,
                                    rows_fwd, rows_adj_in, cols, cols_pipe, (int)(PIPE == 2 && JB_COLS_MT && !JB_COLS_WP),
+                                   (int)Cols3<F3, CB>::CPS,
                                    rows_out, rows_adj_out, rows_generic_smem,
                                    rows5_smem, rows5_gather, rows5_fwd, rows5_adj, conv_rows_r2c, conv_rows_c2r, conv_cols,
                                    prep_rows, prep_cols};
