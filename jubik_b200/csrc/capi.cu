@@ -99,6 +99,8 @@ struct jubik_plan {
     cd* tw_kn = nullptr;
     cd* tw1 = nullptr;         // three-stage column pass: W_L^{m k1}  [k1*M + m]
     cd* tw2 = nullptr;         //                          W_M^{n3 k2} [k2*R3 + n3]
+    cd* tw1r = nullptr;        // the same two tables in the factor order of the c2r row kernels (rows5.cuh)
+    cd* tw2r = nullptr;
     double* wgt = nullptr;
     double* expo = nullptr;    // (T,E,N,N) effective exposure, 0 == masked
     double* data = nullptr;    // (T,E,N,N)
@@ -174,7 +176,7 @@ int jubik_device_count(void) { return device_count(); }
 
 int jubik_plan_destroy(jubik_plan* p) {
     if (!p) return JUBIK_OK;
-    void* bufs[] = {p->fpdev, p->khat, p->tw_nk, p->tw_kn, p->tw1, p->tw2, p->wgt, p->expo, p->data, p->psums, p->psupp, p->bufA, p->bufB,
+    void* bufs[] = {p->fpdev, p->khat, p->tw_nk, p->tw_kn, p->tw1, p->tw2, p->tw1r, p->tw2r, p->wgt, p->expo, p->data, p->psums, p->psupp, p->bufA, p->bufB,
                     p->bufA2, p->bufB2, p->gbuf2, p->gbuf, p->fac, p->partial, p->gtab_fwd, p->gtab_adj, p->xdev, p->gdev,
                     p->edev, p->gstage, p->flatdev, p->cols_acc, p->cols_acc2};
     for (void* b : bufs) dev_free(b);
@@ -484,23 +486,28 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
     }
     p->use_pipe = g.fold ? 0 : o->pipe;
     if (p->use_pipe == 2) {
-        const int Q1 = o->q1, Q2 = o->q2, Q3 = o->q3, M = Q2 * Q3;
-        std::vector<cd> a((size_t)L), b((size_t)M);
+        // two table pairs: the column pass's factor order (tw1/tw2) and the c2r row kernels' (tw1r/tw2r, fft_list.h)
         const long double two_pi = 6.283185307179586476925286766559005768L;
-        for (int k1 = 0; k1 < Q1; ++k1)
-            for (int mm = 0; mm < M; ++mm) {
-                long double ang = -two_pi * (long double)(((long long)k1 * mm) % L) / (long double)L;
-                a[(size_t)k1 * M + mm] = cd_make((double)cosl(ang), (double)sinl(ang));
-            }
-        for (int k2 = 0; k2 < Q2; ++k2)
-            for (int n3 = 0; n3 < Q3; ++n3) {
-                long double ang = -two_pi * (long double)(((long long)k2 * n3) % M) / (long double)M;
-                b[(size_t)k2 * Q3 + n3] = cd_make((double)cosl(ang), (double)sinl(ang));
-            }
-        JB_TRY(alloc(p, (void**)&p->tw1, L * sizeof(cd), "twiddles"));
-        JB_TRY(alloc(p, (void**)&p->tw2, M * sizeof(cd), "twiddles"));
-        if (h2d(p->tw1, a.data(), L * sizeof(cd), st) || h2d(p->tw2, b.data(), M * sizeof(cd), st) || stream_sync(st))
-            return fail(JUBIK_ERR_CUDA, "uploading three-stage twiddles failed");
+        for (int which = 0; which < 2; ++which) {
+            const int Q1 = which ? o->rq1 : o->q1, Q2 = which ? o->rq2 : o->q2, Q3 = which ? o->rq3 : o->q3, M = Q2 * Q3;
+            std::vector<cd> a((size_t)L), b((size_t)M);
+            for (int k1 = 0; k1 < Q1; ++k1)
+                for (int mm = 0; mm < M; ++mm) {
+                    long double ang = -two_pi * (long double)(((long long)k1 * mm) % L) / (long double)L;
+                    a[(size_t)k1 * M + mm] = cd_make((double)cosl(ang), (double)sinl(ang));
+                }
+            for (int k2 = 0; k2 < Q2; ++k2)
+                for (int n3 = 0; n3 < Q3; ++n3) {
+                    long double ang = -two_pi * (long double)(((long long)k2 * n3) % M) / (long double)M;
+                    b[(size_t)k2 * Q3 + n3] = cd_make((double)cosl(ang), (double)sinl(ang));
+                }
+            cd** d1 = which ? &p->tw1r : &p->tw1;
+            cd** d2 = which ? &p->tw2r : &p->tw2;
+            JB_TRY(alloc(p, (void**)d1, L * sizeof(cd), "twiddles"));
+            JB_TRY(alloc(p, (void**)d2, M * sizeof(cd), "twiddles"));
+            if (h2d(*d1, a.data(), L * sizeof(cd), st) || h2d(*d2, b.data(), M * sizeof(cd), st) || stream_sync(st))
+                return fail(JUBIK_ERR_CUDA, "uploading three-stage twiddles failed");
+        }
     }
     if (p->use_pipe == 2 && p->qmax <= JB_MAXQ)
         p->rows5 = o->rows5_smem(g) <= (size_t)227 * 1024 - 1024;
@@ -681,7 +688,7 @@ static int run_forward_g(jubik_plan* p, const JbGeom& g, const double* x, int S,
         JB_LAUNCHED(p, o->cols(g, false, p->bufB, p->bufA, p->khat, p->tw_nk, p->wgt, S * g.T * g.Es, p->thr_cols, st));
     }
     if (p->rows5) {
-        JB_LAUNCHED(p, o->rows5_fwd(g, p->bufA, p->tw1, p->tw2, p->gtab_fwd, p->gq_fwd, ep, S * g.T * g.Es, p->n_sm, st));
+        JB_LAUNCHED(p, o->rows5_fwd(g, p->bufA, p->tw1r, p->tw2r, p->gtab_fwd, p->gq_fwd, ep, S * g.T * g.Es, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->rows_out(g, p->bufA, p->tw_kn, ep, S * g.T * g.Es, p->rpc, p->thr_rows, p->fast_rows, st));
     }
@@ -709,7 +716,7 @@ static int run_adjoint_g(jubik_plan* p, const JbGeom& g, const double* gin, cons
     if (p->rows5) {
         JbGeom gr = g;
         if (mt) gr.T = 1;
-        JB_LAUNCHED(p, o->rows5_adj(gr, p->bufB, p->wgt, p->tw1, p->tw2, p->gtab_adj, p->gq_adj, out, logsky, S * g.Es, p->n_sm, st));
+        JB_LAUNCHED(p, o->rows5_adj(gr, p->bufB, p->wgt, p->tw1r, p->tw2r, p->gtab_adj, p->gq_adj, out, logsky, S * g.Es, p->n_sm, st));
     } else {
         JB_LAUNCHED(p, o->rows_adj_out(g, p->bufB, p->wgt, p->tw_kn, out, logsky, S * g.Es, p->rpc, p->thr_rows, p->fast_rows, st));
     }

@@ -464,6 +464,18 @@ k_cols3_pipe(const
 // module t reads it, multiplies by its K^ slice and runs the inverse half (stage 3', 2', 1') on tile B.  Per module this
 // is 4/7 of the FP64 work and 7.9 instead of 11.3 shared-memory passes of the one-module kernel (T = 7: BASELINE
 // configs[2] and [4]).  Shared memory: tile A, tile B, a two-slot ring of K^ slices -- the same 4 * L * CB * 16 bytes.
+#ifndef JB_ADJ_ACC_REG
+#define JB_ADJ_ACC_REG 7   // largest last-stage radix R3 whose per-thread spectrum / module accumulator (R3 complex values per stage-3
+                           // thread) is kept in registers by the *_mt kernels; above it the forward kernel keeps the spectrum in tile A
+                           // and the adjoint's accumulator lives in a per-CTA global scratch tile that stays in L2.
+                           // r2w, C5 chunk: R3 = 12 in registers spills (cols_adj 12.15 -> 12.88 ms), R3 = 7 does not (9.79 ms)
+#endif
+#ifndef JB_FWD_SPEC_REG
+#define JB_FWD_SPEC_REG 1
+#endif
+#ifndef JB_ADJ_DEFER
+#define JB_ADJ_DEFER 1
+#endif
 template <class F3, int CB>
 JB_GLOBAL void JB_LB((Cols3<F3, CB>::THREADS), (Cols3<F3, CB>::CPS))
 k_cols3_fwd_mt(const
@@ -573,23 +585,31 @@ k_cols3_fwd_mt(const
         }
         JB_SYNC();
 #endif
-        // ---- shared by all modules: stages 1, 2 and the forward half of stage 3 (spectrum back into tile A)
+        // ---- shared by all modules: stages 1, 2 and the forward half of stage 3
         C3::s1_fwd(tileA, tw1, tid, q.vlo, q.vhi, rw, g.m);
         JB_SYNC();
         C3::s2_fwd(tileA, tw2, tid);
         JB_SYNC();
+        // SPEC_REG: the R3 spectrum values of a stage-3 thread stay in REGISTERS over the module loop (one shared-memory read
+        // pass less per module) and tile A, free from here on, alternates with tile B as the inverse transform's tile: the
+        // barrier that protected the single tile B against the next module's stage 3' goes away (2 block barriers per module
+        // instead of 3).  The last module always works in tile B, so the next item's TMA load into tile A is issued where it was.
+        constexpr bool SPEC_REG = JB_FWD_SPEC_REG && R3 <= JB_ADJ_ACC_REG;
+        cd spec[R3];
         if (tid < C3::I3) {
-            cd v[R3];
-            C3::s3_fwd(tileA, tid, v);
-            const int c = tid / CB, b = tid - c * CB;
-            cd* base = tileA + (size_t)(R3 * c) * CB + b;
-            static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; base[k3 * CB] = v[k3]; });
+            C3::s3_fwd(tileA, tid, spec);
+            if (!SPEC_REG) {
+                const int c = tid / CB, b = tid - c * CB;
+                cd* base = tileA + (size_t)(R3 * c) * CB + b;
+                static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; base[k3 * CB] = spec[k3]; });
+            }
         }
         JB_SYNC();
         for (int t = 0; t < T; ++t) {
             const long step = it * T + t;
             const int ks = (int)(step & 1);
             const cd* kh = kh0 + ks * TILE;
+            cd* tb = (SPEC_REG && ((T - 1 - t) & 1)) ? tileA : tileB;
 #ifndef JB_EMU
             jb_mbar_wait<false>(&bars[1 + ks], (uint32_t)((step >> 1) & 1));
 #else
@@ -597,33 +617,36 @@ k_cols3_fwd_mt(const
             for (int idx = tid; idx < TILE; idx += NT) kh0[ks * TILE + idx] = khat[k_off(q, t) + idx];
             JB_SYNC();
 #endif
-            // ---- stage 3': spectrum (tile A) * K^_t, inverse radix R3 -> tile B
+            // ---- stage 3': spectrum * K^_t, inverse radix R3 -> this module's tile
             if (tid < C3::I3) {
                 const int c = tid / CB, b = tid - c * CB;
                 const cd* sa = tileA + (size_t)(R3 * c) * CB + b;
-                cd* sb = tileB + (size_t)(R3 * c) * CB + b;
+                cd* sb = tb + (size_t)(R3 * c) * CB + b;
                 cd v[R3];
-                static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; v[k3] = cd_mul(sa[k3 * CB], kh[k3 * C3::I3 + tid]); });
+                static_for<0, R3>([&](auto kk) {
+                    constexpr int k3 = kk;
+                    v[k3] = cd_mul(SPEC_REG ? spec[k3] : sa[k3 * CB], kh[k3 * C3::I3 + tid]);
+                });
                 dft<R3, +1>(v);
                 static_for<0, R3>([&](auto nn) { constexpr int n3 = nn; sb[n3 * CB] = v[n3]; });
             }
 #ifndef JB_EMU
             jb_fence_proxy_async();          // the K^ slot (and, after the last module, tile A) is handed back to the copy engine
 #endif
-            JB_SYNC();                        // tile B complete; every warp is done with this K^ slot (and with tile A when t == T-1)
+            JB_SYNC();                        // tile complete; every warp is done with this K^ slot (and with tile A when t == T-1)
 #ifndef JB_EMU
             if (tid == 0) {
                 if (step + 2 < nsteps) issue_k(step + 2);
                 if (t == T - 1 && it + 1 < my_items) issue_tile(item_of(it + 1));
             }
 #endif
-            C3::s2_inv(tileB, tw2, tid);
+            C3::s2_inv(tb, tw2, tid);
             JB_SYNC();
             {
                 const bool act = tid < C3::I1;
                 cd v[R1];
-                if (act) C3::s1_inv_load(tileB, tw1, tid, v);
-                JB_SYNC();                    // tile B may be overwritten by the next module's stage 3'
+                if (act) C3::s1_inv_load(tb, tw1, tid, v);
+                if (!SPEC_REG) JB_SYNC();     // the single tile B may be overwritten by the next module's stage 3'
                 if (act) {
                     dft<R1, +1>(v);
                     const int m_ = tid / CB, b = tid - m_ * CB;
@@ -739,6 +762,8 @@ k_cols3_adj_mt(const
     JB_SYNC();
     for (long it = 0; it < my_items; ++it) {
         const Item q = decode(item_of(it));
+        constexpr bool ACC_REG = R3 <= JB_ADJ_ACC_REG;
+        cd a[R3];                 // spectral-domain sum over the modules: R3 values per stage-3 thread (registers if ACC_REG)
         for (int t = 0; t < T; ++t) {
             const long step = it * T + t;
             const int ts = (int)(step & 1);
@@ -761,8 +786,14 @@ k_cols3_adj_mt(const
             JB_SYNC();
 #ifndef JB_EMU
             // every warp is past stage 1' of the previous item's last module / stage 3 of the previous step: when that step
-            // was a LAST module its tile slot is free only now (its inverse stages used it)
-            if (tid == 0 && step >= 1 && ((step - 1) % T) == T - 1 && step + 1 < nsteps) issue_tile(step + 1);
+            // was a LAST module its tile slot is free only now (its inverse stages used it).  JB_ADJ_DEFER: ALL refills of
+            // the previous step's slots are issued here, so that the block barrier behind stage 3 is only needed in front of
+            // the inverse stages (last module) -- 2 barriers per module instead of 3, for a third of a step less prefetch lead
+            if (JB_ADJ_DEFER) {
+                if (tid == 0 && step >= 1 && step + 1 < nsteps) { issue_k(step + 1); issue_tile(step + 1); }
+            } else {
+                if (tid == 0 && step >= 1 && ((step - 1) % T) == T - 1 && step + 1 < nsteps) issue_tile(step + 1);
+            }
 #endif
             C3::s2_fwd(tile, tw2, tid);
             JB_SYNC();
@@ -770,8 +801,7 @@ k_cols3_adj_mt(const
             jb_mbar_wait<false>(&bars[2 + ts], (uint32_t)((step >> 1) & 1));
 #endif
             if (tid < C3::I3) {
-                cd a[R3];
-                if (t > 0) static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; a[k3] = jb_ld_cg(acc + k3 * C3::I3 + tid); });
+                if (!ACC_REG && t > 0) static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; a[k3] = jb_ld_cg(acc + k3 * C3::I3 + tid); });
                 cd v[R3];
                 C3::s3_fwd(tile, tid, v);
                 static_for<0, R3>([&](auto kk) {
@@ -781,7 +811,8 @@ k_cols3_adj_mt(const
                     v[k3] = y;
                 });
                 if (!lastm) {
-                    static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; acc[k3 * C3::I3 + tid] = v[k3]; });
+                    if (ACC_REG) static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; a[k3] = v[k3]; });
+                    else static_for<0, R3>([&](auto kk) { constexpr int k3 = kk; acc[k3 * C3::I3 + tid] = v[k3]; });
                 } else {          // last module: the sum goes straight into the inverse transform, in this tile slot
                     dft<R3, +1>(v);
                     const int c = tid / CB, b = tid - c * CB;
@@ -791,13 +822,13 @@ k_cols3_adj_mt(const
             }
 #ifndef JB_EMU
             jb_fence_proxy_async();
-#endif
-            JB_SYNC();           // stage 3 done everywhere: this step's K^ slot (and, unless it feeds the inverse, its tile slot) is free
-#ifndef JB_EMU
-            if (tid == 0 && step + 2 < nsteps) {
+            if (!JB_ADJ_DEFER || lastm) JB_SYNC();   // stage 3 done everywhere: this step's K^ slot (and, unless it feeds the inverse, its tile slot) is free
+            if (!JB_ADJ_DEFER && tid == 0 && step + 2 < nsteps) {
                 issue_k(step + 2);
                 if (!lastm) issue_tile(step + 2);
             }
+#else
+            JB_SYNC();
 #endif
             if (lastm) {
                 C3::s2_inv(tile, tw2, tid);

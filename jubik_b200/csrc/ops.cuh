@@ -2,6 +2,7 @@
 // translation unit (fft_L*.cu, one line each) so the lengths compile in parallel; capi.cu picks the
 // table by length at plan creation.
 #pragma once
+#include "fft_list.h"
 #include "kernels.cuh"
 #include "rows_fast.cuh"
 #include "cols_pipe.cuh"
@@ -24,7 +25,8 @@ struct JbFftOps {
     int L, R1, R2, CB;
     int ls;    // cd per real sequence in the exchange buffer
     int pipe;  // 0: plain column kernel only; 2: three-stage TMA pipeline (cols3.cuh)
-    int q1, q2, q3;  // three-stage factors (pipe == 2)
+    int q1, q2, q3;  // three-stage factors of the column pass (pipe == 2): twa/twb of cols_pipe / prep_cols
+    int rq1, rq2, rq3;  // three-stage factors of the c2r row kernels (rows5_*): their own twiddle tables (fft_list.h)
     // fast != 0 selects the low-overhead kernels of rows_fast.cuh (two-pass lengths, <= JB_MAXQ row-patches per row,
     // no alias fold); fast == 0 the generic kernels of kernels.cuh (any geometry, period-P alias fold)
     cudaError_t (*rows_fwd)(const JbGeom&, const double* x, const double* wgt, const cd* tw_nk, cd* bufB,
@@ -70,7 +72,7 @@ struct JbFftOps {
 inline int jb_cdiv(int a, int b) { return (a + b - 1) / b; }
 inline size_t jb_al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-template <class FP, int CB, int PIPE, class F3>
+template <class FP, int CB, int PIPE, class F3, class F3R>
 struct JbOpsImpl {
     static cudaError_t cols_pipe(const JbGeom& g, bool adj, const JbTileSrc& src, cd* out, const cd* khat,
                                  const cd* twa, const cd* twb, const double* wgt, int planes, int ctas, int mt, cd* scratch,
@@ -221,7 +223,7 @@ struct JbOpsImpl {
         if constexpr (PIPE == 2) {
             const int sw = rows5_sw(g), NC = (g.n + 1) / 2, NW = (NC + sw - 1) / sw;
             if (NW * 32 > 512) return (size_t)1 << 30;
-            return sw == 1 ? jb_rows5_smem<F3, 1>(g.n) : jb_rows5_smem<F3, 2>(g.n);
+            return sw == 1 ? jb_rows5_smem<F3R, 1>(g.n) : jb_rows5_smem<F3R, 2>(g.n);
         } else {
             (void)g;
             return (size_t)1 << 30;
@@ -229,8 +231,8 @@ struct JbOpsImpl {
     }
     static int rows5_gather(const JbGeom& g, int adj, int maxq, int* host_tab) {
         if constexpr (PIPE == 2) {
-            return rows5_sw(g) == 1 ? jb_rows5_gather_table<F3, 1>(g, adj != 0, maxq, host_tab)
-                                    : jb_rows5_gather_table<F3, 2>(g, adj != 0, maxq, host_tab);
+            return rows5_sw(g) == 1 ? jb_rows5_gather_table<F3R, 1>(g, adj != 0, maxq, host_tab)
+                                    : jb_rows5_gather_table<F3R, 2>(g, adj != 0, maxq, host_tab);
         } else {
             (void)g; (void)adj; (void)maxq; (void)host_tab;
             return 0;
@@ -251,7 +253,7 @@ struct JbOpsImpl {
                                     const int* gtab, int gq, const JbEpi& ep, double* grad, const double* logsky,
                                     int planes, int n_sm, jb_stream_t st) {
         const int NC = (g.n + 1) / 2, NW = (NC + SW - 1) / SW;
-        const size_t smem = jb_rows5_smem<F3, SW>(g.n);
+        const size_t smem = jb_rows5_smem<F3R, SW>(g.n);
         auto go = [&](auto kern) {
             int grid = rows5_grid(kern, NW * 32, smem, (long)planes * g.N, n_sm);
             return jb_launch(kern, dim3(grid), dim3(NW * 32), smem, st, g, src, tw1, tw2, wgt, gtab, gq, ep, grad, logsky, planes);
@@ -260,9 +262,9 @@ struct JbOpsImpl {
         const bool heavy = ADJ ? (logsky != nullptr) : (ep.mode == JB_EPI_POISSON);
         if constexpr (SW == 1) {
             if (NW > 4)   // 5..8 warps per CTA
-                return heavy ? go(k_rows_c2r5<F3, 1, ADJ, true, true>) : go(k_rows_c2r5<F3, 1, ADJ, false, true>);
+                return heavy ? go(k_rows_c2r5<F3R, 1, ADJ, true, true>) : go(k_rows_c2r5<F3R, 1, ADJ, false, true>);
         }
-        return heavy ? go(k_rows_c2r5<F3, SW, ADJ, true>) : go(k_rows_c2r5<F3, SW, ADJ, false>);
+        return heavy ? go(k_rows_c2r5<F3R, SW, ADJ, true>) : go(k_rows_c2r5<F3R, SW, ADJ, false>);
     }
     static cudaError_t rows5_fwd(const JbGeom& g, const cd* bufA, const cd* tw1, const cd* tw2, const int* gtab, int gq,
                                  const JbEpi& ep, int planes, int n_sm, jb_stream_t st) {
@@ -332,6 +334,7 @@ struct JbOpsImpl {
     }
     static const JbFftOps* table() {
         static const JbFftOps t = {FP::L, FP::R1, FP::R2, CB, FP::LS, (FP::R2 > 1 && PIPE == 2) ? 2 : 0, F3::R1, F3::R2, F3::R3,
+                                   F3R::R1, F3R::R2, F3R::R3,
                                    rows_fwd, rows_adj_in, cols, cols_pipe, (int)(PIPE == 2 && JB_COLS_MT && !JB_COLS_WP),
                                    (int)Cols3<F3, CB>::CPS,
                                    rows_out, rows_adj_out, rows_generic_smem,
@@ -341,7 +344,20 @@ struct JbOpsImpl {
     }
 };
 
+// factor order of the c2r row kernels: the column pass's unless fft_list.h (JB_ROWS_F3_LIST) or the variant builder
+// (-DJB_INST_RQ1/2/3) names another one
+template <int LEN, int Q1, int Q2, int Q3>
+struct JbRowsF3 { using type = Fft3<LEN, Q1, Q2, Q3>; };
+#ifdef JB_INST_RQ1
+template <int Q1, int Q2, int Q3>
+struct JbRowsF3<JB_INST_L, Q1, Q2, Q3> { using type = Fft3<JB_INST_L, JB_INST_RQ1, JB_INST_RQ2, JB_INST_RQ3>; };
+#else
+#define JB_Y_ROWS_F3(LEN, A, B, C) \
+    template <int Q1, int Q2, int Q3> struct JbRowsF3<LEN, Q1, Q2, Q3> { using type = Fft3<LEN, A, B, C>; };
+JB_ROWS_F3_LIST(JB_Y_ROWS_F3)
+#endif
 #define JB_DEFINE_FFT(LEN, R1, R2, CB, PIPE, Q1, Q2, Q3) \
     const JbFftOps* jb_fft_ops_##LEN() { \
-        return JbOpsImpl<FftPlan<LEN, R1, R2>, CB, PIPE, Fft3<(PIPE == 2 ? LEN : 1), Q1, Q2, Q3>>::table(); }
+        return JbOpsImpl<FftPlan<LEN, R1, R2>, CB, PIPE, Fft3<(PIPE == 2 ? LEN : 1), Q1, Q2, Q3>, \
+                         typename JbRowsF3<(PIPE == 2 ? LEN : 1), Q1, Q2, Q3>::type>::table(); }
 #define JB_DECLARE_FFT(LEN) const JbFftOps* jb_fft_ops_##LEN();

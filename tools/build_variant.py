@@ -2,7 +2,7 @@
 and null stubs for every other length (a variant serves only geometries of its own length; ~10 MB instead of ~100 MB,
 the gpurun snapshot is capped) into jubik_b200/_variants/lib_<tag>.so (loaded via JUBIK_B200_LIB=...).
 
-    python tools/build_variant.py <tag> <L> -DJB_R5_B=6 -DJB_R5_CPS=5
+    python tools/build_variant.py <tag> <L> [--cb=2] [--q=8,12,7] -DJB_R5_B=6 -DJB_R5_CPS=5
 """
 import os
 import subprocess
@@ -13,9 +13,16 @@ from jubik_b200 import build as b  # noqa: E402
 
 tag, L, extra = sys.argv[1], int(sys.argv[2]), sys.argv[3:]
 cb_override = None
+q_override = None
 for a in list(extra):
     if a.startswith("--cb="):
         cb_override = int(a[5:])
+        extra.remove(a)
+    if a.startswith("--rq="):         # factor order of the c2r row kernels, e.g. --rq=8,7,12
+        extra += ["-DJB_INST_RQ%d=%s" % (i + 1, v) for i, v in enumerate(a[5:].split(","))]
+        extra.remove(a)
+    if a.startswith("--q="):          # three-stage factor order, e.g. --q=8,12,7
+        q_override = tuple(int(v) for v in a[4:].split(","))
         extra.remove(a)
 b.build()
 out = os.path.join(b.HERE, "_variants")
@@ -29,6 +36,8 @@ for (l, r1, r2, cb, pipe, q1, q2, q3) in b.fft_list():
     if l == L:
         if cb_override:
             cb = cb_override
+        if q_override:
+            q1, q2, q3 = q_override
         o = os.path.join(out, "fft_%d_%s.o" % (l, tag))
         cmd = ["nvcc"] + b.NVCC_FLAGS + extra + ["-DJB_INST_L=%d" % l, "-DJB_INST_R1=%d" % r1, "-DJB_INST_R2=%d" % r2,
                                                 "-DJB_INST_CB=%d" % cb, "-DJB_INST_PIPE=%d" % pipe, "-DJB_INST_Q1=%d" % q1,
@@ -38,7 +47,7 @@ for (l, r1, r2, cb, pipe, q1, q2, q3) in b.fft_list():
         if r.returncode:
             sys.exit(r.stdout[-4000:])
         for line in r.stdout.splitlines():
-            if "k_rows_c2r5" in line or "k_cols3_pipe" in line:
+            if "k_rows_c2r5" in line or "k_cols3_" in line:
                 print(line[:160])
             if "spill" in line and "0 bytes spill stores" not in line:
                 print("   ", line.strip())
