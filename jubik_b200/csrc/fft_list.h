@@ -9,7 +9,7 @@
 // Factor order of the column pass: an ODD last radix Q3 makes stage 3 bank-conflict free with 4-column (64-byte) tile rows
 // (two neighbouring items sit Q3*64 bytes apart) and a small one lets the module-sharing kernels keep Q3 spectrum values
 // per thread in registers.  r2w, C5 chunk (L = 672): 8*7*12 -> 8*12*7 cols_fwd 8.45 -> 7.87 ms, cols_adj 12.15 -> 9.79 ms;
-// 12*8*7: 7.66 / 10.38 ms.  Radix-16 orders with Q3 = 3 / 5 for 384 / 640 were measured slower (profiles/r2w_kbench_factors.txt).
+// 12*8*7: 7.66 / 10.38 ms; C3 (L = 336): 8*6*7 -> 6*8*7 cols_adj 1.157 -> 1.089 ms.  Radix-16 orders with Q3 = 3 / 5 for 384 / 640 were measured slower, 8*8*6 / 6*8*8 and 8*10*8 / 10*8*8 equal to the present orders (profiles/r2w_kbench_factors.txt, r2x_kbench_factors2.txt).
 // The c2r row kernels (rows5.cuh, 80 registers) want the big radix LAST (it needs no twiddles there): JB_ROWS_F3_LIST names
 // their factor order where it differs from the column pass's.
 //
@@ -28,7 +28,7 @@
     X(192, 16, 12, 4, 2, 8, 4, 6)   \
     X(256, 16, 16, 4, 2, 8, 4, 8)   \
     X(320, 20, 16, 4, 2, 8, 5, 8)   \
-    X(336, 24, 14, 4, 2, 8, 6, 7)   \
+    X(336, 24, 14, 4, 2, 6, 8, 7)   \
     X(384, 24, 16, 4, 2, 8, 6, 8)   \
     X(448, 28, 16, 4, 2, 8, 7, 8)   \
     X(512, 32, 16, 4, 2, 8, 8, 8)   \
@@ -39,4 +39,5 @@
     X(1024, 32, 32, 4, 0, 1, 1, 1)
 //   Y(L, Q1, Q2, Q3): factor order of the c2r row kernels for length L (default: the column pass's)
 #define JB_ROWS_F3_LIST(Y) \
+    Y(336, 8, 6, 7)            \
     Y(672, 8, 7, 12)
