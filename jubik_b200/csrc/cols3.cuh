@@ -26,6 +26,8 @@ struct Fft3 {
 // <= 256 threads run two CTAs per SM so that one CTA's barrier/latency stalls overlap the other's butterflies
 JB_HD constexpr int jb_c3_max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
 
+JB_HD constexpr int jb_c3_gk(int per_k1) { int g = 1; while ((g * per_k1) % 32 != 0) ++g; return g; }   // k1 per warp-aligned group
+
 // what the compute threads need to know about a work item; written by thread 0 when it stages the item
 struct JbColInfo {
     long long out_off;  // element offset of (row 0, column strip*CB) of this patch in the output buffer
@@ -63,6 +65,11 @@ struct Cols3 {
     static constexpr int CPS = CPS_T < CPS_S ? CPS_T : CPS_S;
     static constexpr int CPS_KD = THREADS <= 256 ? 3 : 1; // ... when K^ is read straight from L2 (no staging ring)
     static_assert(THREADS <= 1024, "one item per thread and stage");
+    // Stage 2 <-> stage 3 only exchange data within one k1: the threads of GK consecutive k1 (GT = GK*R2*CB threads, whole
+    // warps) form a GROUP that owns these sub-transforms in both stages, so that a named barrier over GT threads replaces
+    // the block barrier between them (module-sharing kernels, JB_MT_GROUP)
+    static constexpr int GK = jb_c3_gk(R2 * CB), GT = GK * R2 * CB, NG = R1 / GK, GI2 = GK * R3 * CB;   // GI2: stage-2 items of a group
+    static constexpr bool GROUPS = (R1 % GK == 0) && NG > 1 && NG <= 15;
     // SWZ: with 4-column tiles two stage-3 items of one quarter-warp (rows 8c + n3 and 8c + 8 + n3) hit the same
     // banks.  Between the first forward stage and the last inverse stage the tile is therefore kept row-swizzled,
     // physical row = row ^ ((row >> 3) & 1): neighbouring 8-row groups swap their even/odd rows, every stage stays
@@ -476,6 +483,9 @@ k_cols3_pipe(const
 #ifndef JB_ADJ_DEFER
 #define JB_ADJ_DEFER 1
 #endif
+#ifndef JB_MT_GROUP
+#define JB_MT_GROUP 1      // stage 2 <-> stage 3 of the module loops synchronise per k1 group (named barriers) instead of per CTA
+#endif
 template <class F3, int CB>
 JB_GLOBAL void JB_LB((Cols3<F3, CB>::THREADS), (Cols3<F3, CB>::CPS))
 k_cols3_fwd_mt(const
@@ -595,6 +605,7 @@ k_cols3_fwd_mt(const
         // barrier that protected the single tile B against the next module's stage 3' goes away (2 block barriers per module
         // instead of 3).  The last module always works in tile B, so the next item's TMA load into tile A is issued where it was.
         constexpr bool SPEC_REG = JB_FWD_SPEC_REG && R3 <= JB_ADJ_ACC_REG;
+        constexpr bool GROUP = JB_MT_GROUP && SPEC_REG && C3::GROUPS;
         cd spec[R3];
         if (tid < C3::I3) {
             C3::s3_fwd(tileA, tid, spec);
@@ -633,15 +644,27 @@ k_cols3_fwd_mt(const
 #ifndef JB_EMU
             jb_fence_proxy_async();          // the K^ slot (and, after the last module, tile A) is handed back to the copy engine
 #endif
-            JB_SYNC();                        // tile complete; every warp is done with this K^ slot (and with tile A when t == T-1)
+            if (GROUP) {
+                // stage 2' of a k1 only reads what the same group's stage 3' wrote: group barrier, then ONE block barrier
+                // per module (behind stage 2'), which is also where the K^ slot / tile A are handed back
+                const int grp = tid / C3::GT, gr = tid - grp * C3::GT;
+                JB_GROUP_SYNC(tid < C3::I3, 1 + grp, C3::GT);
+                if (tid < C3::I3)
+                    for (int idx = gr; idx < C3::GI2; idx += C3::GT) C3::s2_inv(tb, tw2, grp * C3::GI2 + idx);
+                JB_SYNC();
+            } else {
+                JB_SYNC();                    // tile complete; every warp is done with this K^ slot (and with tile A when t == T-1)
+            }
 #ifndef JB_EMU
             if (tid == 0) {
                 if (step + 2 < nsteps) issue_k(step + 2);
                 if (t == T - 1 && it + 1 < my_items) issue_tile(item_of(it + 1));
             }
 #endif
-            C3::s2_inv(tb, tw2, tid);
-            JB_SYNC();
+            if (!GROUP) {
+                C3::s2_inv(tb, tw2, tid);
+                JB_SYNC();
+            }
             {
                 const bool act = tid < C3::I1;
                 cd v[R1];
@@ -763,6 +786,7 @@ k_cols3_adj_mt(const
     for (long it = 0; it < my_items; ++it) {
         const Item q = decode(item_of(it));
         constexpr bool ACC_REG = R3 <= JB_ADJ_ACC_REG;
+        constexpr bool GROUP = JB_MT_GROUP && JB_ADJ_DEFER && C3::GROUPS;
         cd a[R3];                 // spectral-domain sum over the modules: R3 values per stage-3 thread (registers if ACC_REG)
         for (int t = 0; t < T; ++t) {
             const long step = it * T + t;
@@ -795,8 +819,15 @@ k_cols3_adj_mt(const
                 if (tid == 0 && step >= 1 && ((step - 1) % T) == T - 1 && step + 1 < nsteps) issue_tile(step + 1);
             }
 #endif
-            C3::s2_fwd(tile, tw2, tid);
-            JB_SYNC();
+            if (GROUP) {
+                const int grp = tid / C3::GT, gr = tid - grp * C3::GT;
+                if (tid < C3::I3)
+                    for (int idx = gr; idx < C3::GI2; idx += C3::GT) C3::s2_fwd(tile, tw2, grp * C3::GI2 + idx);
+                JB_GROUP_SYNC(tid < C3::I3, 1 + grp, C3::GT);
+            } else {
+                C3::s2_fwd(tile, tw2, tid);
+                JB_SYNC();
+            }
 #ifndef JB_EMU
             jb_mbar_wait<false>(&bars[2 + ts], (uint32_t)((step >> 1) & 1));
 #endif

@@ -51,6 +51,8 @@ JB_D void jb_st_stream(cd* p, cd v) {
 }
 #define JB_SYNC() __syncthreads()
 #define JB_SYNCWARP() __syncwarp()
+// named barrier over a warp-aligned group of `nthr` threads (hardware barrier `id` in 1..15); `pred` is uniform per warp
+#define JB_GROUP_SYNC(pred, id, nthr) do { if (pred) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); } while (0)
 JB_D unsigned jb_atomic_inc(unsigned* p) { return atomicAdd(p, 1u); }
 JB_D void jb_threadfence() { __threadfence(); }
 JB_D double jb_ld_cg_f64(const double* p) {
@@ -99,6 +101,8 @@ extern thread_local jb_emu_ctx jb_ctx;
 // emulated threads are not grouped in warps: a warp-level sync becomes a CTA-level one (callers keep the number
 // of warp syncs uniform across the CTA)
 #define JB_SYNCWARP() jb_ctx.bar->arrive_and_wait()
+// ... and so does a named group barrier (every thread of the CTA reaches the call, members or not)
+#define JB_GROUP_SYNC(pred, id, nthr) jb_ctx.bar->arrive_and_wait()
 typedef void* jb_stream_t;
 typedef int cudaError_t;
 #define cudaSuccess 0
