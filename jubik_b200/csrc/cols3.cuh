@@ -484,7 +484,8 @@ k_cols3_pipe(const
 #define JB_ADJ_DEFER 1
 #endif
 #ifndef JB_MT_GROUP
-#define JB_MT_GROUP 1      // stage 2 <-> stage 3 of the module loops synchronise per k1 group (named barriers) instead of per CTA
+#define JB_MT_GROUP 3      // stage 2 <-> stage 3 of the module loops synchronise per k1 group (named barriers) instead of per CTA:
+                           // bit 0 = adjoint kernel, bit 1 = forward kernel
 #endif
 template <class F3, int CB>
 JB_GLOBAL void JB_LB((Cols3<F3, CB>::THREADS), (Cols3<F3, CB>::CPS))
@@ -605,7 +606,10 @@ k_cols3_fwd_mt(const
         // barrier that protected the single tile B against the next module's stage 3' goes away (2 block barriers per module
         // instead of 3).  The last module always works in tile B, so the next item's TMA load into tile A is issued where it was.
         constexpr bool SPEC_REG = JB_FWD_SPEC_REG && R3 <= JB_ADJ_ACC_REG;
-        constexpr bool GROUP = JB_MT_GROUP && SPEC_REG && C3::GROUPS;
+        // (forward: only where a second CTA shares the SM -- the K^ slot is handed back one stage later in this mode, and at
+        //  one CTA per SM the shorter prefetch lead costs more than the barrier saves: L = 672 cols_fwd 7.30 -> 7.39 ms,
+        //  L = 336 0.840 -> 0.823 ms, r2z)
+        constexpr bool GROUP = (JB_MT_GROUP & 2) && SPEC_REG && C3::GROUPS && C3::CPS >= 2;
         cd spec[R3];
         if (tid < C3::I3) {
             C3::s3_fwd(tileA, tid, spec);
@@ -786,7 +790,7 @@ k_cols3_adj_mt(const
     for (long it = 0; it < my_items; ++it) {
         const Item q = decode(item_of(it));
         constexpr bool ACC_REG = R3 <= JB_ADJ_ACC_REG;
-        constexpr bool GROUP = JB_MT_GROUP && JB_ADJ_DEFER && C3::GROUPS;
+        constexpr bool GROUP = (JB_MT_GROUP & 1) && JB_ADJ_DEFER && C3::GROUPS;   // r2z: L = 672 cols_adj 9.44 -> 8.94 ms
         cd a[R3];                 // spectral-domain sum over the modules: R3 values per stage-3 thread (registers if ACC_REG)
         for (int t = 0; t < T; ++t) {
             const long step = it * T + t;
