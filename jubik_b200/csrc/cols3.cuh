@@ -677,7 +677,7 @@ k_cols3_fwd_mt(const
                 // stage 2' of a k1 only reads what the same group's stage 3' wrote: group barrier, then ONE block barrier
                 // per module (behind stage 2'), which is also where the K^ slot / tile A are handed back
                 const int grp = tid / C3::GT, gr = tid - grp * C3::GT;
-                JB_GROUP_SYNC(tid < C3::I3, 1 + grp, C3::GT);
+                JB_GROUP_SYNC(tid < C3::I3, C3::NG, grp, C3::GT);
                 if (tid < C3::I3)
                     for (int idx = gr; idx < C3::GI2; idx += C3::GT) C3::s2_inv(tb, tw2, grp * C3::GI2 + idx);
                 JB_SYNC();
@@ -868,7 +868,7 @@ k_cols3_adj_mt(const
                 const int grp = tid / C3::GT, gr = tid - grp * C3::GT;
                 if (tid < C3::I3)
                     for (int idx = gr; idx < C3::GI2; idx += C3::GT) C3::s2_fwd(tile, tw2, grp * C3::GI2 + idx);
-                JB_GROUP_SYNC(tid < C3::I3, 1 + grp, C3::GT);
+                JB_GROUP_SYNC(tid < C3::I3, C3::NG, grp, C3::GT);
             } else {
                 C3::s2_fwd(tile, tw2, tid);
                 JB_SYNC();

@@ -51,8 +51,17 @@ JB_D void jb_st_stream(cd* p, cd v) {
 }
 #define JB_SYNC() __syncthreads()
 #define JB_SYNCWARP() __syncwarp()
-// named barrier over a warp-aligned group of `nthr` threads (hardware barrier `id` in 1..15); `pred` is uniform per warp
-#define JB_GROUP_SYNC(pred, id, nthr) do { if (pred) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); } while (0)
+// named barrier over warp-aligned group `grp` (of NG groups, hardware barriers 1..NG) of `nthr` threads; `pred` is uniform per warp
+// The id is spelled as an IMMEDIATE (one branch per group, warp-uniform): with a register operand ptxas reserves all 16
+// hardware barriers for the CTA and a second CTA no longer fits the SM.
+template <int NG, int I = 0>
+__device__ __forceinline__ void jb_group_sync_imm(int grp, int nthr) {
+    if constexpr (I < NG) {
+        if (grp == I) asm volatile("bar.sync %0, %1;" ::"n"(I + 1), "r"(nthr) : "memory");
+        else jb_group_sync_imm<NG, I + 1>(grp, nthr);
+    }
+}
+#define JB_GROUP_SYNC(pred, NG, grp, nthr) do { if (pred) jb_group_sync_imm<NG>(grp, nthr); } while (0)
 JB_D unsigned jb_atomic_inc(unsigned* p) { return atomicAdd(p, 1u); }
 JB_D void jb_threadfence() { __threadfence(); }
 JB_D double jb_ld_cg_f64(const double* p) {
@@ -102,7 +111,7 @@ extern thread_local jb_emu_ctx jb_ctx;
 // of warp syncs uniform across the CTA)
 #define JB_SYNCWARP() jb_ctx.bar->arrive_and_wait()
 // ... and so does a named group barrier (every thread of the CTA reaches the call, members or not)
-#define JB_GROUP_SYNC(pred, id, nthr) jb_ctx.bar->arrive_and_wait()
+#define JB_GROUP_SYNC(pred, NG, grp, nthr) jb_ctx.bar->arrive_and_wait()
 typedef void* jb_stream_t;
 typedef int cudaError_t;
 #define cudaSuccess 0

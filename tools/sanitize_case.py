@@ -2,7 +2,7 @@
 
     compute-sanitizer --tool racecheck python tools/sanitize_case.py
 Cases: C1 (256^2, 4x4, P = L = 160: TMA column pipeline + warp-private c2r rows + prefetching r2c rows), a padded length
-(P = 140 -> L = 160), the WIDE c2r form (10x10 patches), the alias fold on the generic kernels, and the stand-alone helpers.
+(P = 140 -> L = 160), the WIDE c2r form (10x10 patches), the module-sharing column kernels with their k1-group barriers (two modules, L = 96), the alias fold on the generic kernels, and the stand-alone helpers.
 """
 import os
 import sys
@@ -42,6 +42,7 @@ def run(N, n, m, T, E, S, full, tag):
 run(256, 4, 16, 1, 2, 2, True, "C1 exact period")
 run(240, 4, 10, 2, 1, 1, False, "padded length")
 run(330, 10, 17, 1, 1, 1, False, "wide c2r form")
+run(256, 8, 16, 2, 1, 1, False, "module-sharing column kernels (L = 96 = 4*4*6: register spectrum / accumulator, k1-group barriers)")
 run(100, 5, 7, 1, 2, 1, True, "alias fold")
 rng = np.random.default_rng(0)
 a = torch.as_tensor(rng.normal(size=(2, 96, 160))).cuda()
