@@ -17,8 +17,9 @@ BASELINE configurations (C1..C4, their own sample counts).
 `e2e`    : the same operation through jubik_poisson_energy_and_grad_sharded_host with pinned HOST buffers: H2D of every
            sample and D2H of [gradient | energies] inside the timed region.
 `roofline`: SURVEY 8(d) whole-path fraction against the binding roof (FP64 pipe, measured DFMA peak) with the HBM
-           fraction beside it; `dominant_kernel` = the forward column pass against its compulsory bytes (the resident
-           PSF spectra it must read); per-kernel durations measured live with CUDA events.
+           fraction beside it; `dominant_kernel` = the slower of the two column passes against its compulsory bytes (the
+           resident PSF spectra it must read), `traffic` = its DRAM bytes per launch from the committed ncu capture of
+           the same workload (profiles/r2*_traffic.json); per-kernel durations measured live with CUDA events.
 `parity` : N = 1: one (module, bin) plane of the workload against the CPU oracle; N > 1: rank 0 re-evaluates all samples
            alone and compares with the all-reduced result.
 `cpu_baseline`: the NumPy/scipy oracle (the reference's op sequence; jax is not installable here) timed on this box's
@@ -354,19 +355,32 @@ def run_ours(args):
         ach_f = f_alg / t_step / 1e12 / world          # per GPU
         ach_b = b_alg / t_step / 1e9 / world
         binding = "fp64" if f_alg / (fp64 * 1e12) > b_alg / (hbm * 1e9) else "hbm"
-        # dominant kernel = forward column pass; compulsory bytes = the resident PSF spectra it has to read, once per
-        # sample (no intermediate counted), P*(P/2+1) complex per patch
+        # dominant kernel = the slower of the two column passes (same compulsory bytes and textbook flops); compulsory
+        # bytes = the resident PSF spectra it has to read, once per sample (no intermediate counted),
+        # P*(P/2+1) complex per patch
         khat_b = chunk * T * E * n * n * P * (P // 2 + 1) * 16
-        cols_s = kms["cols_fwd"] * 1e-3
+        dom = "cols_adj" if kms.get("cols_adj", 0.0) > kms["cols_fwd"] else "cols_fwd"
+        cols_s = kms[dom] * 1e-3
+        if T > 1 and info.get("fast_path"):
+            dom_name = {"cols_fwd": "k_cols3_fwd_mt (forward column pass, forward transform shared by the modules: FFT, "
+                                    "per module * K^ and IFFT)",
+                        "cols_adj": "k_cols3_adj_mt (adjoint column pass, modules summed in the spectral domain: per module "
+                                    "FFT * conj K^, one IFFT)"}[dom]
+        else:
+            dom_name = {"cols_fwd": "k_cols3_pipe (forward column pass: FFT * K^ * IFFT)",
+                        "cols_adj": "k_cols3_pipe (adjoint column pass: FFT * conj K^ * IFFT)"}[dom]
         # textbook flops of that launch: forward + inverse column FFTs over PH columns + the spectrum multiply
         cols_f = chunk * T * E * n * n * PH * (2 * 5 * P * np.log2(P) + 6 * P)
-        traffic_ncu = None
+        # DRAM bytes of that kernel per launch from the committed `ncu --set full` capture of the same workload and chunk
+        # (profiles/r2*_traffic.json; null when no capture of this workload / kernel exists)
+        traffic_ncu, traffic = None, None
         try:
             import glob
             tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "r2*_traffic.json")))[-1]
             tj = json.load(open(tf))
-            if tj.get("workload") == args.workload:
-                traffic_ncu = dict(tj, file=os.path.relpath(tf, ROOT))
+            if tj.get("workload") == args.workload and tj.get("samples") == chunk and dom in tj.get("kernels", {}):
+                traffic_ncu = dict(tj["kernels"][dom], file=os.path.relpath(tf, ROOT), source=tj.get("source"))
+                traffic = traffic_ncu["dram_bytes_read"] + traffic_ncu["dram_bytes_write"]
         except Exception:
             pass
         roof = {"bound": binding, "what": "whole path, SURVEY 8(d): textbook FFT flops (compulsory bytes) of one step / "
@@ -380,9 +394,9 @@ def run_ours(args):
                 "frac_hbm": ach_b / hbm, "achieved_hbm_gbs": ach_b, "peak_hbm_gbs": hbm, "peak_hbm_source": hbm_src,
                 "frac_fp64": ach_f / fp64 if fp64 > 0 else None, "achieved_fp64_tflops": ach_f, "peak_fp64_tflops": fp64,
                 "B_alg_bytes": b_alg, "F_alg_flops": f_alg,
-                "traffic": None, "traffic_ncu_profile": traffic_ncu,
-                "dominant_kernel": {"name": "k_cols3_pipe (forward column pass: FFT * K^ * IFFT), one chunk of %d samples" % chunk,
-                                    "launch_ms": kms["cols_fwd"],
+                "traffic": traffic, "traffic_ncu_profile": traffic_ncu,
+                "dominant_kernel": {"name": "%s, one chunk of %d samples" % (dom_name, chunk),
+                                    "launch_ms": kms[dom],
                                     "compulsory_bytes_per_launch": khat_b,
                                     "achieved_gbs": khat_b / cols_s / 1e9, "frac_hbm": khat_b / cols_s / 1e9 / hbm,
                                     "textbook_flops_per_launch": cols_f,
