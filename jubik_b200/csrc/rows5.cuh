@@ -43,6 +43,9 @@
                         //    bitwise identical); 2: also in the narrow forward kernel (no gain at its 80 registers: 190.4 ->
                         //    190.9 us at C2); 3 (default): also over the modules of the adjoint WIDE kernel (rows_adj_out 2.05 -> 1.93 ms)
 #endif
+#ifndef JB_R5_APIPE_ADJ1
+#define JB_R5_APIPE_ADJ1 1   // adjoint WIDE kernel on module-summed input (T == 1): element-pipelined assembly
+#endif
 #ifndef JB_R5_SPF
 #define JB_R5_SPF 2   // spectrum prefetch (forward kernel): 1 = before, 2 = after the assembly of a row, one
                       // cp.async.bulk.prefetch.L2 per covering (row-patch, column block) spectrum row of the NEXT image row of
@@ -279,9 +282,9 @@ JB_D void jb_rows5_assemble_c(cd* tile, const cd* const (&pbase)[SW][2], const b
 // Forward, one sequence per warp: the same assembly with the loads of element e+1 in flight while element e is summed
 // and scattered (two register buffers, fully unrolled) -- the warp pays the memory round trip once per row instead of
 // once per element group.  Costs 8*CNT registers: used where the launch bound leaves them (JB_R5_APIPE).
-template <class F3, int CNT>
+template <class F3, int CNT, bool WGT = false>
 JB_D void jb_rows5_assemble_pipe(cd* tile, const cd* pa, const cd* pb, bool hasb, const int (&rowoff)[JB_MAXQ],
-                                 const unsigned* __restrict__ atab, int lane) {
+                                 const unsigned* __restrict__ atab, int lane, const double* wr = nullptr) {
     using R = Rows5<F3, 1>;
     constexpr int D = JB_R5_APD;          // elements in flight (register buffers)
     cd va[D][CNT], vb[D][CNT];
@@ -300,7 +303,16 @@ JB_D void jb_rows5_assemble_pipe(cd* tile, const cd* pa, const cd* pb, bool hasb
         const int k = lane + 32 * e;
         if (k < R::PHL) {
             cd a = va[buf][0], b = vb[buf][0];
-            static_for<1, CNT>([&](auto qq) { constexpr int q = qq; a = cd_add(a, va[buf][q]); b = cd_add(b, vb[buf][q]); });
+            if (WGT) { a = cd_scale(a, wr[0]); b = cd_scale(b, wr[0]); }     // adjoint: window row weights (same order of
+            static_for<1, CNT>([&](auto qq) {                                  // operations as jb_rows5_assemble_pipe_adj)
+                constexpr int q = qq;
+                if (WGT) {
+                    a.x += wr[q] * va[buf][q].x; a.y += wr[q] * va[buf][q].y;
+                    b.x += wr[q] * vb[buf][q].x; b.y += wr[q] * vb[buf][q].y;
+                } else {
+                    a = cd_add(a, va[buf][q]); b = cd_add(b, vb[buf][q]);
+                }
+            });
             if (!hasb) b = cd_make(0.0, 0.0);
             const unsigned ad = atab[e * 32 + lane];
             const int adk = (int)(ad & 0xffffu), adm = (int)(ad >> 16);
@@ -514,6 +526,14 @@ k_rows_c2r5(JbGeom g, const cd* __restrict__ src, const cd* __restrict__ tw1, co
 #endif
 #if JB_R5_APIPE >= 3
         if constexpr (ADJ && SW == 1 && WIDE) {
+            // T == 1 (the module-summing column pass has already collapsed the modules): nothing to pipeline over the
+            // modules, so the ELEMENTS are pipelined as in the forward kernel (JB_R5_APIPE & 4)
+            if ((JB_R5_APIPE_ADJ1) && T == 1) {
+                if (cnt == 1) jb_rows5_assemble_pipe<F3, 1, true>(tile, pbase[0][0], pbase[0][1], has[0][1], rowoff, atab, lane, wr);
+                else if (cnt == 2) jb_rows5_assemble_pipe<F3, 2, true>(tile, pbase[0][0], pbase[0][1], has[0][1], rowoff, atab, lane, wr);
+                else if (cnt == 3) jb_rows5_assemble_pipe<F3, 3, true>(tile, pbase[0][0], pbase[0][1], has[0][1], rowoff, atab, lane, wr);
+                else if (cnt == 4) jb_rows5_assemble_pipe<F3, 4, true>(tile, pbase[0][0], pbase[0][1], has[0][1], rowoff, atab, lane, wr);
+            } else
             if (cnt == 1) jb_rows5_assemble_pipe_adj<F3, 1>(tile, pbase[0][0], pbase[0][1], has[0][1], tstride, T, rowoff, wr, atab, lane);
             else if (cnt == 2) jb_rows5_assemble_pipe_adj<F3, 2>(tile, pbase[0][0], pbase[0][1], has[0][1], tstride, T, rowoff, wr, atab, lane);
             else if (cnt == 3) jb_rows5_assemble_pipe_adj<F3, 3>(tile, pbase[0][0], pbase[0][1], has[0][1], tstride, T, rowoff, wr, atab, lane);
