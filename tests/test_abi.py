@@ -112,3 +112,33 @@ def test_hot_kernels_use_tma_bulk_copies_and_fp64_pipe(lib_path):
     for mnemonic in ("UTMALDG.3D", "UBLKCP", "SYNCS.ARRIVE.TRANS64", "LDGSTS.E.BYPASS.128", "DFMA", "DADD"):
         assert mnemonic in sass, mnemonic
     assert "HMMA" not in sass and "UTCHMMA" not in sass      # no tensor-core path: FP64 FFT / stencil work
+
+
+def test_factor_orders_of_fft_list_are_consistent():
+    """csrc/fft_list.h: every three-stage length factors exactly (column pass: X(... Q1, Q2, Q3); c2r rows: JB_ROWS_F3_LIST),
+    the row list only names compiled pipeline lengths, and the module-sharing kernels' register paths (R3 <= 7) are what
+    BASELINE's multi-module configurations (C3: L = 336, C5: L = 672) run."""
+    import re
+    from jubik_b200.build import fft_list, CSRC
+    cols = {L: (pipe, q1, q2, q3) for (L, r1, r2, cb, pipe, q1, q2, q3) in fft_list()}
+    for L, (pipe, q1, q2, q3) in cols.items():
+        if pipe == 2:
+            assert q1 * q2 * q3 == L, L
+    txt = open(os.path.join(CSRC, "fft_list.h")).read()
+    rows = [tuple(int(v) for v in m.groups()) for m in re.finditer(r"Y\((\d+),\s*(\d+),\s*(\d+),\s*(\d+)\)", txt)]
+    assert rows, "JB_ROWS_F3_LIST not found"
+    for (L, a, b, c) in rows:
+        assert L in cols and cols[L][0] == 2 and a * b * c == L, L
+    for L in (336, 672):
+        assert cols[L][3] == 7 and cols[L][3] % 2 == 1      # odd last radix: conflict-free stage 3, register accumulator
+
+
+def test_module_sharing_kernels_use_named_group_barriers(lib_path):
+    """SASS evidence: the k1-group barriers of the module-sharing column kernels are hardware named barriers with
+    immediate ids (BAR.SYNC with a non-zero id), and ptxas reserved only the groups' barriers, not all 16."""
+    log = os.path.join(ROOT, "jubik_b200", "_build", "fft_672.o.log")
+    assert os.path.exists(log)
+    txt = open(log).read()
+    i = txt.index("Function properties for _Z14k_cols3_adj_mt")
+    used = txt[i:txt.index("\n", txt.index("Used", i))]
+    assert "used 5 barriers" in used, used
