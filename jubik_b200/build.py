@@ -72,6 +72,12 @@ def build(force=False, jobs=None, verbose=False):
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
         return LIB
     os.makedirs(OBJ, exist_ok=True)
+    # one build at a time: concurrent callers (e.g. several tools/build_variant.py processes) would write the same objects
+    import fcntl
+    lock = open(os.path.join(OBJ, ".lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
+        return LIB          # another process built it while this one waited
     jobs = jobs or os.cpu_count() or 4
     tasks = []
     for (L, r1, r2, cb, pipe, q1, q2, q3) in fft_list():
