@@ -37,6 +37,20 @@ std::string cuda_msg(cudaError_t) { return "emu"; }
 int device_count() { return 1; }
 #endif
 
+// Rows per TMA box of a column-pass input tile of `rows` rows: as few boxes as the 256-row limit of a box allows, equal in
+// size (the last box overlaps the one before it by at most one row), even (box starts stay 128-byte aligned with 64-byte
+// tile rows).  Thread 0 issues these copies between two stages of its own butterflies: 3 boxes instead of the 11 of
+// 64-row boxes at P = 664 (JB_TILE_BOX_ROWS = 64 restores the old size).
+#ifndef JB_TILE_BOX_ROWS
+#define JB_TILE_BOX_ROWS 256
+#endif
+static int tile_box_rows(int rows) {
+    const int nbox = (rows + JB_TILE_BOX_ROWS - 1) / JB_TILE_BOX_ROWS;
+    int br = (rows + nbox - 1) / nbox;
+    br += br & 1;
+    return br > rows ? rows : br;
+}
+
 // 3-D fp64 TMA view of a row-spectrum buffer (slabs, N, PH) complex: box = CB columns x BR rows x 1 slab.
 int make_tile_src(JbTileSrc* ts, const cd* base, size_t slabs, int N, int PH, int CB, int BR, std::string* err) {
     memset(ts, 0, sizeof(*ts));
@@ -313,7 +327,7 @@ static int ensure_second_workspace(jubik_plan* p) {
     if (p->ws2_ready) return 0;
     const JbGeom& g = p->g;
     const size_t TE1 = (size_t)g.T * g.E, nn2 = (size_t)g.n * g.n;
-    const int brB = std::min(std::min(g.w, 64), g.N), brA = std::min(std::min(g.P, 64), g.N);
+    const int brB = std::min(tile_box_rows(g.w), g.N), brA = std::min(tile_box_rows(g.P), g.N);
     const size_t orows = g.fold ? g.L : g.P;
     std::string err;
     if ((!p->bufA2 && alloc(p, (void**)&p->bufA2, TE1 * nn2 * orows * g.PH * sizeof(cd), "second spectrum workspace A")) ||
@@ -531,7 +545,7 @@ int jubik_plan_create(jubik_plan** out, const jubik_plan_desc* d, void* stream_)
                                            "three-stage pipeline) and their shared-memory tile exceeds 227 KB: use fewer patches per axis");
     if (p->use_pipe) {
         std::string err;
-        int brB = g.w < 64 ? g.w : 64, brA = g.P < 64 ? g.P : 64;
+        int brB = tile_box_rows(g.w), brA = tile_box_rows(g.P);
         if (brB > N) brB = N;
         if (brA > N) brA = N;
         // the row-spectrum buffers (slabs = planes*n, N rows, PH) live in the first part of bufB (forward) / bufA (adjoint)
