@@ -28,6 +28,10 @@ JB_HD constexpr int jb_c3_max3(int a, int b, int c) { return a > b ? (a > c ? a 
 
 JB_HD constexpr int jb_c3_gk(int per_k1) { int g = 1; while ((g * per_k1) % 32 != 0) ++g; return g; }   // k1 per warp-aligned group
 
+#ifndef JB_MT_ISSUER
+#define JB_MT_ISSUER 1        // ring refills issued by an otherwise idle warp instead of thread 0
+#endif
+
 // what the compute threads need to know about a work item; written by thread 0 when it stages the item
 struct JbColInfo {
     long long out_off;  // element offset of (row 0, column strip*CB) of this patch in the output buffer
@@ -406,7 +410,10 @@ k_cols3_pipe(const
             jb_fence_proxy_async();
             __syncwarp();
             if ((tid & 31) == 0) jb_mbar_arrive(&bars[2 + s]);
-            if (tid == 0) {
+            // the refill is issued by the first lane of a warp WITHOUT a stage-1' item where there is one (I1 < THREADS, e.g.
+            // L = 384: warps 6 and 7): waiting for the "consumed" barrier and feeding the copy engine then delays no butterfly
+            constexpr int PISSUER = JB_MT_ISSUER && ((C3::I1 + 31) / 32 * 32 < JB_C3_THREADS) ? (C3::I1 + 31) / 32 * 32 : 0;
+            if (tid == PISSUER) {
                 // (refilling behind the next item's first block barrier instead -- what k_cols3_fwd_mt does -- costs this
                 // kernel its prefetch lead: 300 -> 326 us at C2; refilling after thread 0's own stores: 271 -> 281 us, r2u)
                 long nxt = item_of((long)it + 2);
@@ -635,6 +642,11 @@ k_cols3_fwd_mt(const
         //  one CTA per SM the shorter prefetch lead costs more than the barrier saves: L = 672 cols_fwd 7.30 -> 7.39 ms,
         //  L = 336 0.840 -> 0.823 ms, r2z)
         constexpr bool GROUP = (JB_MT_GROUP & 2) && SPEC_REG && C3::GROUPS && C3::CPS >= 2;
+        // the ring refills are issued by the first lane of a warp that has NO item in the stage that follows the hand-back
+        // (stage 2' with I2 items, stage 1' with I1 in group mode), so that the copy-engine commands stay off the critical
+        // path of the warps the next barrier waits for; thread 0 when every warp is busy there
+        constexpr int NEXT_ITEMS = GROUP ? C3::I1 : C3::I2;
+        constexpr int ISSUER = JB_MT_ISSUER && ((NEXT_ITEMS + 31) / 32 * 32 < NT) ? (NEXT_ITEMS + 31) / 32 * 32 : 0;
         cd spec[R3];
         if (tid < C3::I3) {
             C3::s3_fwd(tileA, tid, spec);
@@ -685,7 +697,7 @@ k_cols3_fwd_mt(const
                 JB_SYNC();                    // tile complete; every warp is done with this K^ slot (and with tile A when t == T-1)
             }
 #ifndef JB_EMU
-            if (tid == 0) {
+            if (tid == ISSUER) {
                 if (step + 2 < nsteps) issue_k(step + 2);
                 if (t == T - 1 && it + 1 < my_items) issue_tile(item_of(it + 1));
             }
@@ -832,6 +844,12 @@ k_cols3_adj_mt(const
         const Item q = decode(item_of(it));
         constexpr bool ACC_REG = R3 <= JB_ADJ_ACC_REG;
         constexpr bool GROUP = (JB_MT_GROUP & 1) && JB_ADJ_DEFER && C3::GROUPS;   // r2z: L = 672 cols_adj 9.44 -> 8.94 ms
+        // deferred refills are issued by the first lane of a warp without a stage-2 item (group mode: the warps of group 0
+        // behind its GI2 items; otherwise the warps behind the I2 items), thread 0 when there is none -- see k_cols3_fwd_mt
+        constexpr int S2_BUSY = GROUP ? (C3::GI2 + 31) / 32 * 32 : (C3::I2 + 31) / 32 * 32;
+        constexpr int ISSUER = !(JB_MT_ISSUER && JB_ADJ_DEFER) ? 0
+                               : (GROUP && C3::I3 < NT) ? C3::I3               // a warp outside every group: idle in stages 2 and 3
+                               : (S2_BUSY < (GROUP ? C3::GT : NT)) ? S2_BUSY : 0;
         cd a[R3];                 // spectral-domain sum over the modules: R3 values per stage-3 thread (registers if ACC_REG)
         for (int t = 0; t < T; ++t) {
             const long step = it * T + t;
@@ -859,7 +877,7 @@ k_cols3_adj_mt(const
             // the previous step's slots are issued here, so that the block barrier behind stage 3 is only needed in front of
             // the inverse stages (last module) -- 2 barriers per module instead of 3, for a third of a step less prefetch lead
             if (JB_ADJ_DEFER) {
-                if (tid == 0 && step >= 1 && step + 1 < nsteps) { issue_k(step + 1); issue_tile(step + 1); }
+                if (tid == ISSUER && step >= 1 && step + 1 < nsteps) { issue_k(step + 1); issue_tile(step + 1); }
             } else {
                 if (tid == 0 && step >= 1 && ((step - 1) % T) == T - 1 && step + 1 < nsteps) issue_tile(step + 1);
             }
