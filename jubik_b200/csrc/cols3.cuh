@@ -494,6 +494,9 @@ k_cols3_pipe(const
 #define JB_MT_SAMPLE_FAST 0   // 1: neighbouring CTAs work on the samples of one (bin, patch, strip) at the same time (shared K^ slices
                               //    come from L2).  r2z, C5 chunk: cols_fwd 7.32 -> 7.27 ms, cols_adj 8.94 -> 10.20 ms -- off
 #endif
+#ifndef JB_MT_GROUP_FWD_MINCPS
+#define JB_MT_GROUP_FWD_MINCPS 2   // forward kernel: group barriers only from this many CTAs per SM on (see the kernel)
+#endif
 #ifndef JB_MT_KPF
 #define JB_MT_KPF 0           // > 0: K^ slices are also prefetched into L2 this many ring steps ahead of their bulk copy.  r2z, C5
                               // chunk, 2 or 4 steps ahead: cols_fwd 7.30 -> 8.29 ms, cols_adj 8.94 -> 10.10 ms (the prefetched lines
@@ -640,8 +643,8 @@ k_cols3_fwd_mt(const
         constexpr bool SPEC_REG = JB_FWD_SPEC_REG && R3 <= JB_ADJ_ACC_REG;
         // (forward: only where a second CTA shares the SM -- the K^ slot is handed back one stage later in this mode, and at
         //  one CTA per SM the shorter prefetch lead costs more than the barrier saves: L = 672 cols_fwd 7.30 -> 7.39 ms,
-        //  L = 336 0.840 -> 0.823 ms, r2z)
-        constexpr bool GROUP = (JB_MT_GROUP & 2) && SPEC_REG && C3::GROUPS && C3::CPS >= 2;
+        //  L = 336 0.840 -> 0.823 ms, r2z; again with the producer warp, r2G: L = 672 6.80 -> 7.63 ms)
+        constexpr bool GROUP = (JB_MT_GROUP & 2) && SPEC_REG && C3::GROUPS && C3::CPS >= JB_MT_GROUP_FWD_MINCPS;
         // the ring refills are issued by the first lane of a warp that has NO item in the stage that follows the hand-back
         // (stage 2' with I2 items, stage 1' with I1 in group mode), so that the copy-engine commands stay off the critical
         // path of the warps the next barrier waits for; thread 0 when every warp is busy there
