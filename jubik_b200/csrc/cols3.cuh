@@ -474,10 +474,12 @@ k_cols3_pipe(const
 // --------------------------------------------------------------------------------------------------------
 // Forward column pass for T > 1 modules: the forward column transform of a windowed sky patch does not depend on the
 // telescope module -- only K^ does.  One work item = (sample, energy bin, patch, strip); the tile is loaded and
-// transformed ONCE (stages 1, 2 and the forward half of stage 3; the spectrum is written back to tile A), then every
-// module t reads it, multiplies by its K^ slice and runs the inverse half (stage 3', 2', 1') on tile B.  Per module this
-// is 4/7 of the FP64 work and 7.9 instead of 11.3 shared-memory passes of the one-module kernel (T = 7: BASELINE
-// configs[2] and [4]).  Shared memory: tile A, tile B, a two-slot ring of K^ slices -- the same 4 * L * CB * 16 bytes.
+// transformed ONCE (stages 1, 2 and the forward half of stage 3); the spectrum stays in the stage-3 threads' REGISTERS
+// (R3 <= JB_ADJ_ACC_REG; otherwise it is written back to tile A), then every module t multiplies it by its K^ slice and
+// runs the inverse half (stage 3', 2', 1') on tile A / tile B alternately (tile B only, when the spectrum lives in tile A).
+// Per module this is 4/7 of the FP64 work and 6.9 (7.9) instead of 11.3 shared-memory passes of the one-module kernel
+// (T = 7: BASELINE configs[2] and [4]).  Shared memory: tile A, tile B, a two-slot ring of K^ slices -- the same
+// 4 * L * CB * 16 bytes.  Refills are issued by a warp that is idle in the following stage (ISSUER).
 #ifndef JB_ADJ_ACC_REG
 #define JB_ADJ_ACC_REG 7   // largest last-stage radix R3 whose per-thread spectrum / module accumulator (R3 complex values per stage-3
                            // thread) is kept in registers by the *_mt kernels; above it the forward kernel keeps the spectrum in tile A
@@ -737,9 +739,11 @@ k_cols3_fwd_mt(const
 // FFT(cotangent_t) * conj K^_t are summed in the spectral domain and ONE inverse transform per (sample, energy bin,
 // patch, strip) writes the module-summed rows -- out: (S*E, n*n, w, PH); the c2r row pass behind it reads one spectrum
 // instead of T.  Per module 4/7 of the FP64 work.  Shared memory keeps BOTH rings double-buffered (two input tiles, two
-// K^ slices); the accumulator lives in a per-CTA scratch tile in global memory that never leaves L2 (each thread
-// reads and writes only its own elements, loads issued ahead of the stage-3 butterfly).  Ring slots are handed back
-// behind block barriers (no thread ever blocks on a "consumed" mbarrier).
+// K^ slices); the accumulator is R3 complex values per stage-3 thread, in REGISTERS for R3 <= JB_ADJ_ACC_REG, otherwise in
+// a per-CTA scratch tile in global memory that never leaves L2 (each thread reads and writes only its own elements, loads
+// issued ahead of the stage-3 butterfly).  Ring slots are handed back behind block barriers -- with JB_ADJ_DEFER behind the
+// FIRST barrier of the next step -- by a warp that is idle in the following stage (no thread ever blocks on a "consumed"
+// mbarrier); stage 2 and stage 3 synchronise per k1 group (JB_MT_GROUP).
 template <class F3, int CB>
 JB_GLOBAL void JB_LB((Cols3<F3, CB>::THREADS), (Cols3<F3, CB>::CPS))
 k_cols3_adj_mt(const
