@@ -492,17 +492,11 @@ k_cols3_pipe(const
 #ifndef JB_ADJ_DEFER
 #define JB_ADJ_DEFER 1
 #endif
-#ifndef JB_MT_SAMPLE_FAST
-#define JB_MT_SAMPLE_FAST 0   // 1: neighbouring CTAs work on the samples of one (bin, patch, strip) at the same time (shared K^ slices
-                              //    come from L2).  r2z, C5 chunk: cols_fwd 7.32 -> 7.27 ms, cols_adj 8.94 -> 10.20 ms -- off
-#endif
+// Measured and removed (r2z): the sample index as the fastest item index (neighbouring CTAs share K^ slices through L2:
+// cols_fwd 7.32 -> 7.27 ms, cols_adj 8.94 -> 10.20 ms) and an L2 prefetch of the K^ slices 2 / 4 ring steps ahead of their bulk copy
+// (7.30 -> 8.29 ms, 8.94 -> 10.10 ms).
 #ifndef JB_MT_GROUP_FWD_MINCPS
 #define JB_MT_GROUP_FWD_MINCPS 2   // forward kernel: group barriers only from this many CTAs per SM on (see the kernel)
-#endif
-#ifndef JB_MT_KPF
-#define JB_MT_KPF 0           // > 0: K^ slices are also prefetched into L2 this many ring steps ahead of their bulk copy.  r2z, C5
-                              // chunk, 2 or 4 steps ahead: cols_fwd 7.30 -> 8.29 ms, cols_adj 8.94 -> 10.10 ms (the prefetched lines
-                              // are gone again before the copy asks for them: K^ crosses HBM twice) -- off
 #endif
 #ifndef JB_MT_GROUP
 #define JB_MT_GROUP 3      // stage 2 <-> stage 3 of the module loops synchronise per k1 group (named barriers) instead of per CTA:
@@ -541,23 +535,11 @@ k_cols3_fwd_mt(const
     struct Item { int strip, k, s, e, j, i, vlo, vhi, row0, ncols; };
     auto decode = [&](long item) -> Item {
         Item q;
-#if JB_MT_SAMPLE_FAST
-        // the sample index runs fastest: neighbouring CTAs work on the samples of one (bin, patch, strip) at the same time,
-        // so that the K^ slices they share are fetched from HBM once and from L2 afterwards
-        const int S_ = planes_se / g.Es;
-        q.s = (int)(item % S_);
-        long r = item / S_;
-        q.strip = (int)(r % nstrips);
-        r /= nstrips;
-        q.k = (int)(r % nn2);
-        q.e = g.e0 + (int)(r / nn2);
-#else
         q.strip = (int)(item % nstrips);
         long r = item / nstrips;
         q.k = (int)(r % nn2);
         const int lp = (int)(r / nn2);
         q.s = lp / g.Es; q.e = g.e0 + (lp - q.s * g.Es);
-#endif
         q.j = q.k % n; q.i = q.k / n;
         q.row0 = g.offs[q.j] - g.hp;                       // image row of tile row m
         const int lo = -q.row0, hi = N - q.row0;
@@ -604,10 +586,6 @@ k_cols3_fwd_mt(const
         const int ks = (int)(step & 1);
         jb_mbar_expect_tx(&bars[1 + ks], (uint32_t)(TILE * sizeof(cd)));
         jb_bulk_load_1d(kh0 + ks * TILE, khat + k_off(q, (int)(step % T)), (uint32_t)(TILE * sizeof(cd)), &bars[1 + ks]);
-        if (JB_MT_KPF > 0 && step + JB_MT_KPF < nsteps) {     // warm L2 with the slice the ring will ask for JB_MT_KPF steps later
-            const long sp = step + JB_MT_KPF;
-            jb_bulk_prefetch_l2(khat + k_off(decode(item_of(sp / T)), (int)(sp % T)), (uint32_t)(TILE * sizeof(cd)));
-        }
     };
     if (tid == 0) {
         jb_mbar_init(&bars[0], 1);
@@ -772,23 +750,11 @@ k_cols3_adj_mt(const
     struct Item { int strip, k, s, e, j, i, vlo, vhi, row0, ncols; };
     auto decode = [&](long item) -> Item {
         Item q;
-#if JB_MT_SAMPLE_FAST
-        // the sample index runs fastest: neighbouring CTAs work on the samples of one (bin, patch, strip) at the same time,
-        // so that the K^ slices they share are fetched from HBM once and from L2 afterwards
-        const int S_ = planes_se / g.Es;
-        q.s = (int)(item % S_);
-        long r = item / S_;
-        q.strip = (int)(r % nstrips);
-        r /= nstrips;
-        q.k = (int)(r % nn2);
-        q.e = g.e0 + (int)(r / nn2);
-#else
         q.strip = (int)(item % nstrips);
         long r = item / nstrips;
         q.k = (int)(r % nn2);
         const int lp = (int)(r / nn2);
         q.s = lp / g.Es; q.e = g.e0 + (lp - q.s * g.Es);
-#endif
         q.j = q.k % n; q.i = q.k / n;
         q.row0 = g.offs[q.j] - g.hp - g.m;                 // image row of tile row 0
         const int lo = -q.row0, hi = N - q.row0;
@@ -834,10 +800,6 @@ k_cols3_adj_mt(const
         jb_mbar_expect_tx(&bars[2 + ks], (uint32_t)(TILE * sizeof(cd)));
         jb_bulk_load_1d(kh0 + ks * TILE, khat + k_off(decode(item_of(step / T)), (int)(step % T)), (uint32_t)(TILE * sizeof(cd)),
                         &bars[2 + ks]);
-        if (JB_MT_KPF > 0 && step + JB_MT_KPF < nsteps) {
-            const long sp = step + JB_MT_KPF;
-            jb_bulk_prefetch_l2(khat + k_off(decode(item_of(sp / T)), (int)(sp % T)), (uint32_t)(TILE * sizeof(cd)));
-        }
     };
     if (tid == 0) {
         for (int b = 0; b < 4; ++b) jb_mbar_init(&bars[b], 1);
